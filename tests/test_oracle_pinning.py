@@ -1,0 +1,114 @@
+"""CPU: pin the C oracle (oracle/sb_oracle.c) to the reference.
+
+Two anchors: (1) the committed golden fixtures produced by the unmodified
+reference (tests/golden/make_golden.py), incl. the SURVEY section-4 hashes;
+(2) when oracle/_ref/libsbref.so is present, the reference itself, live.
+"""
+import numpy as np
+import pytest
+
+from conftest import CASES, load_case, load_synthetic, synthetic_specs
+from oracle import Ref, fnv1a64
+
+SURVEY_HASHES = {  # SURVEY.md section 4 (pairs, hits, segments)
+    "simple-ring": ("417a7631554d1725", "f5c8fb94fe697d25", "28894104c51956e7"),
+    "cube-sphere": ("281f0cf346df2da5", "178e3433f46c031a", "13756fda0f219a33"),
+    "complex": ("d51f9f0a7f34aea1", "b78cfc299e750cf1", "10a237b628700c83"),
+    "addax-and-meerkat": ("3d338a306d83169f", "c8c2a4ba6b4338ad", "d0a81ab21cb2d3fc"),
+}
+SURVEY_COUNTS = {  # tris A, tris B, P, H, insideA, insideB
+    "simple-ring": (12, 12, 16, 8, 0, 6),
+    "cube-sphere": (12, 48, 40, 20, 0, 13),
+    "complex": (100, 3688, 5008, 274, 1, 1606),
+    "addax-and-meerkat": (3458, 2952, 2026, 208, 20, 318),
+}
+
+
+def _hash_pairs(p):
+    return "%016x" % fnv1a64(np.asarray(p, np.uint64).astype("<u8").tobytes())
+
+
+def check_against(oracle, a, b, out):
+    pairs = oracle.candidate_pairs(a, b)
+    assert np.array_equal(pairs, out["pairs"])
+    ret, cop, hit, seg = oracle.predicate_pairs(a, b, pairs)
+    assert np.array_equal(ret, out["ret"])
+    assert np.array_equal(cop, out["coplanar"])
+    assert np.array_equal(hit, out["hit"])
+    assert seg[hit.astype(bool)].tobytes() == out["seg_hits"].tobytes()
+    ia, pa, _ = oracle.classify(b, oracle.centroids(*a))
+    ib, pb, _ = oracle.classify(a, oracle.centroids(*b))
+    assert np.array_equal(ia, out["inside_a"]) and np.array_equal(pa, out["per_axis_a"])
+    assert np.array_equal(ib, out["inside_b"]) and np.array_equal(pb, out["per_axis_b"])
+    return pairs, hit, seg
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_bundled_cases_match_reference_fixtures(oracle, golden_cases, golden_json, case):
+    a, b, out = load_case(golden_cases, case)
+    pairs, hit, seg = check_against(oracle, a, b, out)
+    na, nb, P, H, ina, inb = SURVEY_COUNTS[case]
+    assert (len(a[1]), len(b[1]), len(pairs), int(hit.sum())) == (na, nb, P, H)
+    assert (int(out["inside_a"].sum()), int(out["inside_b"].sum())) == (ina, inb)
+    hp, hh, hs = SURVEY_HASHES[case]
+    assert _hash_pairs(pairs) == hp
+    assert _hash_pairs(pairs[hit.astype(bool)]) == hh
+    assert "%016x" % fnv1a64(seg[hit.astype(bool)].tobytes()) == hs
+    assert golden_json["cases"][case]["hash_pairs"] == hp
+
+
+@pytest.mark.parametrize("name", sorted(synthetic_specs()))
+def test_synthetic_match_reference_fixtures(oracle, golden_synthetic, golden_json, name):
+    a, b, out = load_synthetic(golden_synthetic, name)
+    pairs, hit, _ = check_against(oracle, a, b, out)
+    meta = golden_json["synthetic"][name]
+    assert (len(pairs), int(hit.sum())) == (meta["P"], meta["H"])
+    assert _hash_pairs(pairs) == meta["hash_pairs"]
+
+
+def test_predicate_known_answers(oracle, golden_kat, golden_json):
+    ret, cop, seg = oracle.tri_tri_batch(golden_kat["tris"])
+    assert np.array_equal(ret, golden_kat["ret"])
+    assert np.array_equal(cop, golden_kat["coplanar"])
+    assert seg.tobytes() == golden_kat["seg"].tobytes()
+    assert "%016x" % fnv1a64(seg.tobytes()) == golden_json["tritri_kat"]["hash_seg"]
+    # the crafted set must reach the coplanar branch and both outcomes
+    assert cop.sum() > 1000 and 0 < ret.sum() < len(ret)
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_vs_live_reference_random(oracle):
+    R = Ref.get()
+    rng = np.random.default_rng(7)
+    tris = np.concatenate([
+        rng.uniform(-1, 1, (20000, 18)),
+        rng.integers(-2, 3, (20000, 18)).astype(np.float64),
+        rng.uniform(-1, 1, (5000, 18)).astype(np.float32).astype(np.float64),
+    ])
+    r0, c0, s0 = R.tri_tri_batch(tris)
+    r1, c1, s1 = oracle.tri_tri_batch(tris)
+    assert np.array_equal(r0, r1) and np.array_equal(c0, c1) and s0.tobytes() == s1.tobytes()
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_vs_live_reference_mesh(oracle):
+    from solidboolean_b200 import meshgen
+    R = Ref.get()
+    a = meshgen.icosphere(4, center=(0.1, 0.0, 0.0))
+    b = meshgen.torus(40, 20, R=0.9, r=0.3, center=(0.013, 0.007, 0.011))
+    ma, mb = R.mesh(*a), R.mesh(*b)
+    op = R.op(ma, mb)
+    pr = op.search()
+    prs = pr[np.lexsort((pr[:, 1], pr[:, 0]))]
+    assert np.array_equal(oracle.candidate_pairs(a, b), prs)
+    ret, cop, hit, seg, _ = op.predicate(prs)
+    oret, ocop, ohit, oseg = oracle.predicate_pairs(a, b, prs)
+    assert np.array_equal(ret, oret) and np.array_equal(cop, ocop) and np.array_equal(hit, ohit)
+    assert seg.tobytes() == oseg.tobytes()
+    assert oracle.normals(*a).tobytes() == ma.normals().tobytes()
+    assert oracle.tri_boxes(*b).tobytes() == mb.boxes().tobytes()
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-1.5, 1.5, (3000, 3))
+    i0, p0, _ = op.classify(1, pts)
+    i1, p1, _ = oracle.classify(b, pts)
+    assert np.array_equal(i0, i1) and np.array_equal(p0, p1)
