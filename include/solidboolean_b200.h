@@ -1,0 +1,184 @@
+/*
+ * solidboolean_b200 -- C ABI of the B200 (sm_100a) intersection front end.
+ *
+ * This is the drop-in boundary for the data-parallel path of
+ * huxingyi/solidboolean.  The reference has no FFI of its own: its
+ * boundary is the SolidMesh / SolidBoolean C++ classes.  Each entry point below
+ * names the reference code it replaces (paths relative to the reference tree);
+ * INTEGRATION.md shows the three call sites a maintainer patches.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success or an
+ *     SB_ERR_* code, and sb_last_error() returns a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails
+ *     with SB_ERR_CUDA;
+ *   - vertices are AoS double[3] (the layout of Vector3, src/vector3.h:306),
+ *     triangles are uint32[3] (the reference's size_t triples, narrowed);
+ *   - all output index pairs are ORIGINAL triangle ids, sorted by (a, b);
+ *   - a context owns one CUDA stream; objects of one context must not be used
+ *     from two host threads at once, different contexts are independent
+ *     (the reference allows concurrent SolidBooleans over shared const meshes).
+ */
+#ifndef SOLIDBOOLEAN_B200_H
+#define SOLIDBOOLEAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID 1  /* bad argument (null pointer, index out of range ...) */
+#define SB_ERR_CUDA 2     /* CUDA runtime error / no device */
+#define SB_ERR_CAPACITY 3 /* an internal bound was exceeded (see message) */
+#define SB_ERR_NOMEM 4
+
+typedef struct sb_context sb_context;
+typedef struct sb_mesh sb_mesh;
+typedef struct sb_isect sb_isect;
+
+/* Thread-local message of the last failing call ("" if none). */
+const char *sb_last_error(void);
+/* Library version string, e.g. "solidboolean_b200 0.1 sm_100a". */
+const char *sb_version(void);
+
+/* ---- context -------------------------------------------------------------- */
+int sb_context_create(int device, sb_context **out);
+void sb_context_destroy(sb_context *ctx);
+/* Block until everything enqueued on the context's stream has finished. */
+int sb_context_synchronize(sb_context *ctx);
+/* The context's cudaStream_t (as void*), for callers that enqueue NCCL or their
+ * own kernels behind this library's work. */
+void *sb_context_stream(sb_context *ctx);
+int sb_context_device(const sb_context *ctx);
+
+/* ---- mesh: replaces SolidMesh::prepare(), src/solidmesh.cpp:42-76 ----------
+ * normals (:47-55), per-triangle boxes (:57-62), whole-mesh box (:64-72) and
+ * the AxisAlignedBoudingBoxTree build (:74-75, axisalignedboundingboxtree.cpp:
+ * 27-141), the latter as a Morton-code LBVH over clusters of triangles. */
+
+/* Host buffers in, copy + build enqueued; returns after the build completed. */
+int sb_mesh_create(sb_context *ctx, const double *xyz, size_t nV,
+                   const uint32_t *tri, size_t nT, sb_mesh **out);
+/* Split form used for device-resident timing: upload copies the geometry to the
+ * device (no build), build (re)builds every derived array from the resident
+ * geometry.  build is asynchronous on the context stream. */
+int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV,
+                   const uint32_t *tri, size_t nT, sb_mesh **out);
+int sb_mesh_build(sb_mesh *mesh);
+void sb_mesh_destroy(sb_mesh *mesh);
+
+size_t sb_mesh_num_triangles(const sb_mesh *mesh);
+size_t sb_mesh_num_vertices(const sb_mesh *mesh);
+/* SolidMesh::triangleNormals(): 3 doubles per triangle (src/solidmesh.cpp:47-55,
+ * Vector3::normal src/vector3.h:155-176), bit-exact. */
+int sb_mesh_normals(const sb_mesh *mesh, double *out3nT);
+/* SolidMesh::triangleAxisAlignedBoundingBoxes(): lower xyz, upper xyz per
+ * triangle (src/axisalignedboundingbox.h:31-41), bit-exact. */
+int sb_mesh_triangle_boxes(const sb_mesh *mesh, double *out6nT);
+/* Whole-mesh box over all vertices: lower xyz, upper xyz. */
+int sb_mesh_bounds(const sb_mesh *mesh, double *out6);
+/* Morton order: sorted position -> original triangle id (nT entries). */
+int sb_mesh_order(const sb_mesh *mesh, uint32_t *outnT);
+
+/* LBVH introspection for invariant tests.  Nodes are records of 8 x 32-bit:
+ * float lo[3], hi[3]; int32 ref; int32 aux.  Internal node p = records 2p, 2p+1
+ * (its two children); ref >= 0 is an internal node index, ref < 0 is ~cluster.
+ * Cluster c covers sorted triangles [c*K, min((c+1)*K, nT)). */
+typedef struct sb_bvh_info {
+    uint32_t cluster_size; /* K */
+    uint32_t num_clusters; /* M */
+    uint32_t num_internal; /* M - 1 (0 when M <= 1) */
+    int32_t root;          /* internal node index, or ~0 (= -1) when M == 1 */
+} sb_bvh_info;
+int sb_mesh_bvh_info(const sb_mesh *mesh, sb_bvh_info *out);
+int sb_mesh_bvh_nodes(const sb_mesh *mesh, void *out_records /* 2*num_internal*32 B */);
+int sb_mesh_bvh_leaves(const sb_mesh *mesh, void *out_records /* padded nT * 32 B */,
+                       size_t *padded_count);
+
+/* ---- intersection: replaces SolidBoolean::searchPotentialIntersectedPairs
+ * (src/solidboolean.cpp:94-101 -> axisalignedboundingboxtree.h:54-95) and the
+ * predicate loop (src/solidboolean.cpp:315-320 -> intersectTwoFaces :103-122 ->
+ * tri_tri_intersection_test_3d, thirdparty/GuigueDevillers03/
+ * tri_tri_intersect.c:395-472). */
+
+#define SB_ISECT_DEFAULT 0u
+#define SB_ISECT_NO_SORT 1u /* leave candidates/hits in emission order */
+
+int sb_intersect(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out);
+/* Same, restricted to A's triangles at Morton-sorted positions [begin, end)
+ * (begin a multiple of 32) -- the multi-GPU shard of SURVEY 8e. */
+int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t end,
+                       unsigned flags, sb_isect **out);
+void sb_isect_destroy(sb_isect *isect);
+
+int sb_isect_counts(const sb_isect *isect, size_t *nCand, size_t *nHit);
+/* Candidate pairs (triangle boxes overlap, closed intervals in double).
+ * ab: 2*nCand uint32.  code (optional): per pair, bit0 = predicate return
+ * value, bit1 = *coplanar. */
+int sb_isect_candidates(const sb_isect *isect, uint32_t *ab, uint8_t *code);
+/* Intersecting, non-coplanar pairs (what intersectTwoFaces accepts) and their
+ * segments: seg = source xyz, target xyz per hit. */
+int sb_isect_hits(const sb_isect *isect, uint32_t *ab, double *seg);
+/* Per-face "intersected" flags (m_firstIntersectedFaces / m_secondIntersectedFaces,
+ * src/solidboolean.cpp:318-319): nT(A) and nT(B) bytes. */
+int sb_isect_face_flags(const sb_isect *isect, uint8_t *flagsA, uint8_t *flagsB);
+/* Device pointers of the result arrays (valid until sb_isect_destroy), for
+ * gathering over NCCL without a host round trip.  Any out pointer may be NULL.
+ * cand_keys: nCand uint64 = (((a << bits_b) | b) << 2) | code;
+ * hit_ab: 2*nHit uint32; hit_seg: 6*nHit double. */
+int sb_isect_device_ptrs(const sb_isect *isect, void **cand_keys, unsigned *bits_b,
+                         void **hit_ab, void **hit_seg, void **flagsA, void **flagsB);
+
+/* Raw predicate on explicit triangles: 18 doubles per pair (p1 q1 r1 p2 q2 r2).
+ * ret/coplanar as tri_tri_intersection_test_3d; seg = 6 doubles per pair, left
+ * zero where the predicate does not write them. */
+int sb_tri_tri_batch(sb_context *ctx, const double *tris18, size_t n,
+                     int32_t *ret, int32_t *coplanar, double *seg6);
+
+/* ---- classification: replaces SolidBoolean::isPointInMesh
+ * (src/solidboolean.cpp:48-92) as driven by decideGroupSide (:482-510): three
+ * rays (g_testAxisList :31-35) per point, PositionKey de-duplication
+ * (src/positionkey.cpp:32-37), odd/even, majority of three. */
+
+/* inside: Q bytes.  per_axis (optional): 3 bytes per point. */
+int sb_classify(const sb_mesh *target, const double *pts, size_t Q,
+                uint8_t *inside, uint8_t *per_axis);
+/* Query points = face centroids ((v0+v1)+v2)/3.0 of `query`'s triangles
+ * (src/solidboolean.cpp:497-499), computed on the device. Outputs are indexed
+ * by original triangle id of `query`. */
+int sb_classify_faces(const sb_mesh *query, const sb_mesh *target,
+                      uint8_t *inside, uint8_t *per_axis);
+/* Device-resident form: classify query triangles at Morton-sorted positions
+ * [begin, end) (begin a multiple of 32) -- the multi-GPU shard of SURVEY 8e.
+ * d_inside is a caller-owned DEVICE buffer of nT(query) bytes indexed by
+ * original triangle id; entries outside the range are left untouched.  No host
+ * copy of the flags is made (one 40-byte counter read-back only). */
+int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target,
+                             size_t begin, size_t end, void *d_inside);
+
+/* ---- instrumentation --------------------------------------------------------
+ * Stage timing with CUDA events on the context stream.  Stages accumulate the
+ * device time of the kernels they enclose since the last reset. */
+enum {
+    SB_STAGE_BUILD = 0,    /* bounds, boxes, normals, Morton, sort, LBVH */
+    SB_STAGE_BROAD = 1,    /* traversal + pair emission */
+    SB_STAGE_NARROW = 2,   /* predicate + hit compaction + sorts */
+    SB_STAGE_CLASSIFY = 3, /* ray classification */
+    SB_STAGE_COUNT = 4
+};
+int sb_context_enable_timing(sb_context *ctx, int enable);
+int sb_context_reset_timing(sb_context *ctx);
+/* Synchronises the stream, then writes SB_STAGE_COUNT floats (ms) and the
+ * number of kernel launches issued by this library since the last reset. */
+int sb_context_get_timing(sb_context *ctx, float *ms, uint64_t *kernel_launches);
+/* Work counters of the last classification on this context: rays traced and
+ * ray/triangle candidates evaluated (roofline accounting). */
+int sb_context_classify_stats(sb_context *ctx, uint64_t *rays, uint64_t *candidates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLIDBOOLEAN_B200_H */

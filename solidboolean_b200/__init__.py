@@ -1,0 +1,329 @@
+"""solidboolean_b200 -- B200 (sm_100a) intersection front end of solidboolean.
+
+This package is a thin ctypes binding over the C ABI declared in
+``include/solidboolean_b200.h`` (the drop-in boundary; the C++ SolidMesh /
+SolidBoolean classes in ``solidboolean_b200/host`` sit on the same ABI).  There
+is no CPU implementation here: importing works anywhere, but every compute call
+needs the CUDA library ``lib/libsolidboolean_b200.so`` and a GPU, and raises
+``SolidBooleanError`` otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsolidboolean_b200.so")
+
+STAGES = ("build", "broad", "narrow", "classify")
+ISECT_NO_SORT = 1
+
+
+class SolidBooleanError(RuntimeError):
+    pass
+
+
+class _BvhInfo(C.Structure):
+    _fields_ = [("cluster_size", C.c_uint32), ("num_clusters", C.c_uint32),
+                ("num_internal", C.c_uint32), ("root", C.c_int32)]
+
+
+_lib = None
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks
+# against the header.
+_vp = C.c_void_p
+_sz = C.c_size_t
+ABI = {
+    "sb_last_error": (C.c_char_p, []),
+    "sb_version": (C.c_char_p, []),
+    "sb_context_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "sb_context_destroy": (None, [_vp]),
+    "sb_context_synchronize": (C.c_int, [_vp]),
+    "sb_context_stream": (_vp, [_vp]),
+    "sb_context_device": (C.c_int, [_vp]),
+    "sb_mesh_create": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_vp)]),
+    "sb_mesh_upload": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_vp)]),
+    "sb_mesh_build": (C.c_int, [_vp]),
+    "sb_mesh_destroy": (None, [_vp]),
+    "sb_mesh_num_triangles": (_sz, [_vp]),
+    "sb_mesh_num_vertices": (_sz, [_vp]),
+    "sb_mesh_normals": (C.c_int, [_vp, _vp]),
+    "sb_mesh_triangle_boxes": (C.c_int, [_vp, _vp]),
+    "sb_mesh_bounds": (C.c_int, [_vp, _vp]),
+    "sb_mesh_order": (C.c_int, [_vp, _vp]),
+    "sb_mesh_bvh_info": (C.c_int, [_vp, C.POINTER(_BvhInfo)]),
+    "sb_mesh_bvh_nodes": (C.c_int, [_vp, _vp]),
+    "sb_mesh_bvh_leaves": (C.c_int, [_vp, _vp, C.POINTER(_sz)]),
+    "sb_intersect": (C.c_int, [_vp, _vp, C.c_uint, C.POINTER(_vp)]),
+    "sb_intersect_range": (C.c_int, [_vp, _vp, _sz, _sz, C.c_uint, C.POINTER(_vp)]),
+    "sb_isect_destroy": (None, [_vp]),
+    "sb_isect_counts": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    "sb_isect_candidates": (C.c_int, [_vp, _vp, _vp]),
+    "sb_isect_hits": (C.c_int, [_vp, _vp, _vp]),
+    "sb_isect_face_flags": (C.c_int, [_vp, _vp, _vp]),
+    "sb_isect_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint), C.POINTER(_vp),
+                                       C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sb_tri_tri_batch": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "sb_classify": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "sb_classify_faces": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "sb_classify_faces_device": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
+    "sb_context_enable_timing": (C.c_int, [_vp, C.c_int]),
+    "sb_context_reset_timing": (C.c_int, [_vp]),
+    "sb_context_get_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+    "sb_context_classify_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+}
+
+
+def load_library():
+    """Load the CUDA library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SolidBooleanError(
+            "CUDA library %s is missing: run `python -m solidboolean_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(code):
+    if code != 0:
+        msg = load_library().sb_last_error().decode(errors="replace")
+        raise SolidBooleanError("solidboolean_b200 error %d: %s" % (code, msg))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+class Context:
+    """One device + one CUDA stream (sb_context)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _vp()
+        _check(self.lib.sb_context_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(self.lib.sb_context_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.sb_context_stream(self.h) or 0)
+
+    def enable_timing(self, on=True):
+        _check(self.lib.sb_context_enable_timing(self.h, 1 if on else 0))
+
+    def reset_timing(self):
+        _check(self.lib.sb_context_reset_timing(self.h))
+
+    def timing(self):
+        """-> ({stage: ms}, kernel launches) since the last reset (synchronises)."""
+        ms = (C.c_float * len(STAGES))()
+        n = C.c_uint64(0)
+        _check(self.lib.sb_context_get_timing(self.h, ms, C.byref(n)))
+        return {k: float(ms[i]) for i, k in enumerate(STAGES)}, int(n.value)
+
+    def classify_stats(self):
+        r, c = C.c_uint64(0), C.c_uint64(0)
+        _check(self.lib.sb_context_classify_stats(self.h, C.byref(r), C.byref(c)))
+        return int(r.value), int(c.value)
+
+    def mesh(self, xyz, tri, build=True) -> "Mesh":
+        return Mesh(self, xyz, tri, build=build)
+
+    def tri_tri_batch(self, tris18):
+        """Raw predicate on explicit triangle pairs [n,18] -> ret, coplanar, seg[n,6]."""
+        t = np.ascontiguousarray(tris18, dtype=np.float64).reshape(-1, 18)
+        n = t.shape[0]
+        ret = np.zeros(n, np.int32)
+        cop = np.zeros(n, np.int32)
+        seg = np.zeros((n, 6), np.float64)
+        _check(self.lib.sb_tri_tri_batch(self.h, _ptr(t), n, _ptr(ret), _ptr(cop), _ptr(seg)))
+        return ret, cop, seg
+
+
+class Mesh:
+    """Device-resident mesh + LBVH (sb_mesh); mirrors SolidMesh::prepare()."""
+
+    def __init__(self, ctx: Context, xyz, tri, build=True):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        # keep the host arrays alive while an async upload may still read them
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        self.tri = np.ascontiguousarray(tri, dtype=np.uint32).reshape(-1, 3)
+        h = _vp()
+        fn = self.lib.sb_mesh_create if build else self.lib.sb_mesh_upload
+        _check(fn(ctx.h, _ptr(self.xyz), self.xyz.shape[0], _ptr(self.tri), self.tri.shape[0], C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_pointers(cls, ctx: Context, xyz_ptr: int, nV: int, tri_ptr: int, nT: int, build=True, keep=None):
+        """Create from raw host pointers (e.g. pinned torch tensors)."""
+        self = cls.__new__(cls)
+        self.ctx, self.lib = ctx, ctx.lib
+        self.xyz = self.tri = None
+        self._keep = keep
+        h = _vp()
+        fn = self.lib.sb_mesh_create if build else self.lib.sb_mesh_upload
+        _check(fn(ctx.h, _vp(xyz_ptr), nV, _vp(tri_ptr), nT, C.byref(h)))
+        self.h = h
+        return self
+
+    def build(self):
+        _check(self.lib.sb_mesh_build(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.lib.sb_mesh_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_triangles(self) -> int:
+        return int(self.lib.sb_mesh_num_triangles(self.h))
+
+    @property
+    def num_vertices(self) -> int:
+        return int(self.lib.sb_mesh_num_vertices(self.h))
+
+    def normals(self):
+        out = np.zeros((self.num_triangles, 3), np.float64)
+        _check(self.lib.sb_mesh_normals(self.h, _ptr(out)))
+        return out
+
+    def triangle_boxes(self):
+        out = np.zeros((self.num_triangles, 6), np.float64)
+        _check(self.lib.sb_mesh_triangle_boxes(self.h, _ptr(out)))
+        return out
+
+    def bounds(self):
+        out = np.zeros(6, np.float64)
+        _check(self.lib.sb_mesh_bounds(self.h, _ptr(out)))
+        return out
+
+    def order(self):
+        out = np.zeros(self.num_triangles, np.uint32)
+        _check(self.lib.sb_mesh_order(self.h, _ptr(out)))
+        return out
+
+    def bvh(self):
+        """-> dict(info, nodes [2*I] records, leaves [nTpad] records)."""
+        info = _BvhInfo()
+        _check(self.lib.sb_mesh_bvh_info(self.h, C.byref(info)))
+        rec = np.dtype([("lo", np.float32, 3), ("hi", np.float32, 3), ("ref", np.int32), ("aux", np.int32)])
+        nodes = np.zeros(2 * info.num_internal, rec)
+        _check(self.lib.sb_mesh_bvh_nodes(self.h, _ptr(nodes)))
+        npad = (self.num_triangles + 31) // 32 * 32
+        leaves = np.zeros(npad, rec)
+        cnt = _sz(0)
+        _check(self.lib.sb_mesh_bvh_leaves(self.h, _ptr(leaves), C.byref(cnt)))
+        assert cnt.value == npad
+        return dict(cluster_size=info.cluster_size, num_clusters=info.num_clusters,
+                    num_internal=info.num_internal, root=info.root, nodes=nodes, leaves=leaves)
+
+    def intersect(self, other: "Mesh", flags=0, begin=None, end=None) -> "Isect":
+        return Isect(self, other, flags, begin, end)
+
+    def classify(self, pts):
+        """isPointInMesh majority vote for explicit points against THIS mesh."""
+        p = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        q = p.shape[0]
+        inside = np.zeros(q, np.uint8)
+        per_axis = np.zeros((q, 3), np.uint8)
+        _check(self.lib.sb_classify(self.h, _ptr(p), q, _ptr(inside), _ptr(per_axis)))
+        return inside, per_axis
+
+    def classify_faces_against(self, target: "Mesh"):
+        """Classify this mesh's face centroids against `target`."""
+        n = self.num_triangles
+        inside = np.zeros(n, np.uint8)
+        per_axis = np.zeros((n, 3), np.uint8)
+        _check(self.lib.sb_classify_faces(self.h, target.h, _ptr(inside), _ptr(per_axis)))
+        return inside, per_axis
+
+    def classify_faces_device(self, target: "Mesh", d_inside_ptr: int, begin=0, end=None):
+        end = self.num_triangles if end is None else end
+        _check(self.lib.sb_classify_faces_device(self.h, target.h, begin, end, _vp(d_inside_ptr)))
+
+
+class Isect:
+    """Candidate pairs + intersecting pairs of two meshes (sb_isect)."""
+
+    def __init__(self, a: Mesh, b: Mesh, flags=0, begin=None, end=None):
+        self.a, self.b = a, b
+        self.lib = a.lib
+        h = _vp()
+        if begin is None and end is None:
+            _check(self.lib.sb_intersect(a.h, b.h, flags, C.byref(h)))
+        else:
+            _check(self.lib.sb_intersect_range(a.h, b.h, begin or 0, a.num_triangles if end is None else end,
+                                               flags, C.byref(h)))
+        self.h = h
+        nc, nh = _sz(0), _sz(0)
+        _check(self.lib.sb_isect_counts(h, C.byref(nc), C.byref(nh)))
+        self.num_candidates, self.num_hits = int(nc.value), int(nh.value)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.a.ctx, "h", None):
+            self.lib.sb_isect_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def candidates(self):
+        ab = np.zeros((self.num_candidates, 2), np.uint32)
+        code = np.zeros(self.num_candidates, np.uint8)
+        _check(self.lib.sb_isect_candidates(self.h, _ptr(ab), _ptr(code)))
+        return ab, code
+
+    def hits(self):
+        ab = np.zeros((self.num_hits, 2), np.uint32)
+        seg = np.zeros((self.num_hits, 6), np.float64)
+        _check(self.lib.sb_isect_hits(self.h, _ptr(ab), _ptr(seg)))
+        return ab, seg
+
+    def face_flags(self):
+        fa = np.zeros(self.a.num_triangles, np.uint8)
+        fb = np.zeros(self.b.num_triangles, np.uint8)
+        _check(self.lib.sb_isect_face_flags(self.h, _ptr(fa), _ptr(fb)))
+        return fa, fb
+
+    def device_ptrs(self):
+        ck, ha, hs, fa, fb = _vp(), _vp(), _vp(), _vp(), _vp()
+        bits = C.c_uint(0)
+        _check(self.lib.sb_isect_device_ptrs(self.h, C.byref(ck), C.byref(bits), C.byref(ha), C.byref(hs),
+                                             C.byref(fa), C.byref(fb)))
+        return dict(cand_keys=ck.value or 0, bits_b=bits.value, hit_ab=ha.value or 0, hit_seg=hs.value or 0,
+                    flags_a=fa.value or 0, flags_b=fb.value or 0)

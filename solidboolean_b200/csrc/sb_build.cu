@@ -1,0 +1,255 @@
+// Stage 1: everything SolidMesh::prepare() computes (reference src/solidmesh.cpp:
+// 42-76), rebuilt for the device:
+//   K2  bounds_pad    whole-mesh box (:64-72) + 32-byte padded vertex copy
+//   K1  tri_prepare   unit normals (:47-55), exact per-triangle boxes (:57-62),
+//                     Morton key of the box centre
+//   K3  onesweep radix sort of (Morton key, triangle id)
+//   K1b leaf_gather   sorted leaf records + warp-shuffle reduction of every K
+//                     consecutive leaves into a cluster box (the bottom log2 K
+//                     levels of the bottom-up refit, done in registers)
+//   K4  tree_build    agglomerative bottom-up LBVH over the clusters: topology
+//                     and boxes in ONE pass with an atomic rendezvous per node
+// The reference's top-down mean-split tree (axisalignedboundingboxtree.cpp:27-141)
+// is not reproduced: the candidate-pair set only depends on the leaf boxes.
+#include "sb_internal.h"
+#include "sb_radix.cuh"
+
+namespace {
+
+constexpr int K = SB_CLUSTER;
+static_assert(K == 1 || K == 2 || K == 4 || K == 8 || K == 16 || K == 32, "cluster size must divide the warp");
+
+// ---- K2 ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bounds_pad_kernel(const double *__restrict__ xyz, uint32_t nV,
+    double4 *__restrict__ vtx, unsigned long long *__restrict__ bounds)
+{
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nV; i += gridDim.x * blockDim.x) {
+        double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        double2 *o = reinterpret_cast<double2 *>(vtx + i);
+        o[0] = make_double2(x, y);
+        o[1] = make_double2(z, 0.0);
+        lo[0] = fmin(lo[0], x); hi[0] = fmax(hi[0], x);
+        lo[1] = fmin(lo[1], y); hi[1] = fmax(hi[1], y);
+        lo[2] = fmin(lo[2], z); hi[2] = fmax(hi[2], z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(SB_FULL, lo[k], off));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(SB_FULL, hi[k], off));
+        }
+    __shared__ double s_lo[8][3], s_hi[8][3];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) {
+            s_lo[warp][k] = lo[k];
+            s_hi[warp][k] = hi[k];
+        }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int k = threadIdx.x;
+        double l = s_lo[0][k], h = s_hi[0][k];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            l = fmin(l, s_lo[w][k]);
+            h = fmax(h, s_hi[w][k]);
+        }
+        atomicMin(&bounds[k], dkey(l));
+        atomicMax(&bounds[3 + k], dkey(h));
+    }
+}
+
+// ---- K1 ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand10(uint32_t v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
+{
+    float f = (float)((c - lo) * inv) * 1024.0f;
+    f = fminf(fmaxf(f, 0.0f), 1023.0f); // NaN -> 0
+    return (uint32_t)f;
+}
+
+__global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
+    uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double2 *__restrict__ tbox,
+    double *__restrict__ normal, uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nT)
+        return;
+    uint32_t i0 = tri[3 * (size_t)i], i1 = tri[3 * (size_t)i + 1], i2 = tri[3 * (size_t)i + 2];
+    if (i0 >= nV || i1 >= nV || i2 >= nV) { // reported as SB_ERR_INVALID by the host
+        *err = 1;
+        i0 = i1 = i2 = 0;
+    }
+    d3 a = load_vertex(vtx, i0), b = load_vertex(vtx, i1), c = load_vertex(vtx, i2);
+
+    // AxisAlignedBoudingBox::update x3 from the +-DBL_MAX seeds, strict compares
+    // (src/axisalignedboundingbox.h:31-41)
+    BoxD bx = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
+#define SB_UPD(v)                                   \
+    if (v.x > bx.hix) bx.hix = v.x;                 \
+    if (v.x < bx.lox) bx.lox = v.x;                 \
+    if (v.y > bx.hiy) bx.hiy = v.y;                 \
+    if (v.y < bx.loy) bx.loy = v.y;                 \
+    if (v.z > bx.hiz) bx.hiz = v.z;                 \
+    if (v.z < bx.loz) bx.loz = v.z;
+    SB_UPD(a) SB_UPD(b) SB_UPD(c)
+#undef SB_UPD
+    store_boxd(tbox + 3 * (size_t)i, bx);
+
+    // Vector3::normal (src/vector3.h:155-176)
+    d3 ba = d3sub(b, a), ca = d3sub(c, a);
+    d3 cr = d3cross(ba, ca);
+    double len2 = xadd(xadd(xmul(cr.x, cr.x), xmul(cr.y, cr.y)), xmul(cr.z, cr.z));
+    double len = xsqrt(len2);
+    d3 n = {0.0, 0.0, 0.0};
+    if (!(fabs(len) <= 2.2204460492503131e-16))
+        n = {xdiv(cr.x, len), xdiv(cr.y, len), xdiv(cr.z, len)};
+    normal[3 * (size_t)i] = n.x;
+    normal[3 * (size_t)i + 1] = n.y;
+    normal[3 * (size_t)i + 2] = n.z;
+
+    // 30-bit Morton key of the box centre inside the mesh box (ordering only)
+    double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
+    double ex = dkey_inv(bounds[3]) - blx, ey = dkey_inv(bounds[4]) - bly, ez = dkey_inv(bounds[5]) - blz;
+    double ix = ex > 0 ? 1.0 / ex : 0.0, iy = ey > 0 ? 1.0 / ey : 0.0, iz = ez > 0 ? 1.0 / ez : 0.0;
+    uint32_t qx = quant10(0.5 * (bx.lox + bx.hix), blx, ix);
+    uint32_t qy = quant10(0.5 * (bx.loy + bx.hiy), bly, iy);
+    uint32_t qz = quant10(0.5 * (bx.loz + bx.hiz), blz, iz);
+    mkey[i] = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
+    order[i] = i;
+}
+
+// ---- K1b --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__restrict__ sortedTri,
+    const uint32_t *__restrict__ sortedKey, const double2 *__restrict__ tbox, uint32_t nT, uint32_t nTpad,
+    Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey)
+{
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nTpad) // nTpad is a multiple of 32: whole warps leave together
+        return;
+    BoxD bd = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
+    BoxF bf = empty_boxf();
+    int ref = -1;
+    if (j < nT) {
+        uint32_t t = sortedTri[j];
+        bd = load_boxd(tbox + 3 * (size_t)t);
+        bf = enclose(bd);
+        ref = (int)t;
+    }
+    store_boxd(sbox + 3 * (size_t)j, bd);
+    store_rec(leaf + j, bf, ref, (int)j);
+    // segmented (width K) min/max reduction in registers
+    BoxF cb = bf;
+#pragma unroll
+    for (int off = 1; off < K; off <<= 1) {
+        BoxF o = shfl_xor_box(cb, off);
+        merge_f(cb, o);
+    }
+    if ((j % K) == 0 && j < nT) {
+        uint32_t c = j / K;
+        store_rec(cbox + c, cb, ~(int)c, 0);
+        ckey[c] = sortedKey[j];
+    }
+}
+
+// ---- K4 ---------------------------------------------------------------------
+// Highest differing bit of the composite keys (Morton << 32 | index) of
+// clusters i and i+1; distinct for the two ends of any radix-tree range.
+__device__ __forceinline__ int split_level(const uint32_t *__restrict__ ckey, uint32_t i)
+{
+    uint32_t x = __ldg(ckey + i) ^ __ldg(ckey + i + 1);
+    if (x)
+        return 63 - __clz(x);
+    return 31 - __clz(i ^ (i + 1));
+}
+
+__global__ void __launch_bounds__(256) tree_build_kernel(const Rec32 *__restrict__ cbox, const uint32_t *__restrict__ ckey,
+    uint32_t M, Rec32 *nodes, int *slot, int *root)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M)
+        return;
+    if (M == 1) {
+        *root = -1; // ~0: the single cluster is the root
+        return;
+    }
+    Rec32 me = load_rec(cbox + c);
+    BoxF box = {me.lox, me.loy, me.loz, me.hix, me.hiy, me.hiz};
+    int ref = ~(int)c;
+    uint32_t l = c, r = c;
+    while (true) {
+        bool up; // true: parent is node r (we are its left child)
+        if (l == 0)
+            up = true;
+        else if (r == M - 1)
+            up = false;
+        else
+            up = split_level(ckey, r) < split_level(ckey, l - 1);
+        uint32_t p = up ? r : l - 1;
+        int side = up ? 0 : 1;
+        store_rec(nodes + 2 * (size_t)p + side, box, ref, (int)(up ? l : r));
+        __threadfence();
+        int other = atomicExch(slot + p, (int)(up ? l : r));
+        if (other < 0)
+            return; // first to arrive: the sibling's thread carries on
+        __threadfence();
+        Rec32 sib = load_rec_cg(nodes + 2 * (size_t)p + (1 - side));
+        BoxF sb = {sib.lox, sib.loy, sib.loz, sib.hix, sib.hiy, sib.hiz};
+        merge_f(box, sb);
+        if (up)
+            r = (uint32_t)other;
+        else
+            l = (uint32_t)other;
+        ref = (int)p;
+        if (l == 0 && r == M - 1) {
+            *root = (int)p;
+            return;
+        }
+    }
+}
+
+} // namespace
+
+size_t sbk_radix_workspace_words(size_t n) { return sbradix::Workspace::words(sbradix::tiles_for(n)); }
+
+cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t radixWsWords, int smCount, LaunchCounter &lc)
+{
+    (void)radixWsWords;
+    if (m.nT == 0)
+        return cudaSuccess;
+    // bounds seeds: min slots all-ones, max slots zero (order-encoded doubles)
+    cudaMemsetAsync(m.bounds, 0xff, 3 * sizeof(unsigned long long), s);
+    cudaMemsetAsync(m.bounds + 3, 0x00, 3 * sizeof(unsigned long long), s);
+    int vb = (int)((m.nV + 255) / 256);
+    if (vb > smCount * 8)
+        vb = smCount * 8;
+    if (vb < 1)
+        vb = 1;
+    bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds);
+    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.tbox, m.normal, m.mkey,
+        m.order, m.err);
+    lc.kernels += 2;
+    sbradix::Workspace ws;
+    ws.mem = radixWs;
+    uint32_t *sk = nullptr, *sv = nullptr;
+    lc.kernels += sbradix::sort<uint32_t>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, 0, 30, ws, smCount, &sk, &sv);
+    m.sortedKey = sk;
+    m.sortedTri = sv;
+    leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.tbox, m.nT, m.nTpad, m.leaf,
+        m.sbox, m.cbox, m.ckey);
+    lc.kernels += 1;
+    if (m.M > 1)
+        cudaMemsetAsync(m.slot, 0xff, sizeof(int) * (m.M - 1), s);
+    tree_build_kernel<<<(m.M + 255) / 256, 256, 0, s>>>(m.cbox, m.ckey, m.M, m.nodes, m.slot, m.root);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}

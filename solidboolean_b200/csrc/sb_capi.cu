@@ -1,0 +1,956 @@
+// C ABI (include/solidboolean_b200.h): contexts, device memory, stage timing
+// and the orchestration of the kernel stages.  No CPU fallback anywhere: every
+// compute entry point needs a CUDA device and fails with SB_ERR_CUDA otherwise.
+#include "../../include/solidboolean_b200.h"
+#include "sb_internal.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SB_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(SB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+unsigned bits_for(size_t n)
+{
+    unsigned b = 1;
+    while (((size_t)1 << b) < n)
+        ++b;
+    return b;
+}
+
+struct DeviceScalars { // one 256-byte block of device counters per context
+    unsigned long long pairCount;
+    unsigned long long stats[2];
+    unsigned int hitCount;
+    unsigned int overflowCount;
+    int err;
+    int pad;
+};
+
+} // namespace
+
+struct sb_context {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    LaunchCounter lc;
+    // stage timing
+    bool timing = false;
+    struct Span {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> freeEvents;
+    float acc[SB_STAGE_COUNT] = {0, 0, 0, 0};
+    // scratch
+    uint32_t *radixWs = nullptr;
+    size_t radixWsWords = 0;
+    DeviceScalars *dScalars = nullptr;
+    DeviceScalars *hScalars = nullptr; // pinned mirror
+    uint8_t *classifyOut = nullptr;    // inside flags (+ per-axis) of the last classify call
+    size_t classifyOutBytes = 0;
+    uint32_t *overflowList = nullptr;
+    uint32_t overflowCap = 0;
+    uint64_t lastRays = 0, lastCands = 0;
+};
+
+struct sb_mesh {
+    sb_context *ctx = nullptr;
+    MeshDev d;
+    void *arena = nullptr;
+    bool built = false;
+};
+
+struct sb_isect {
+    sb_context *ctx = nullptr;
+    const sb_mesh *A = nullptr, *B = nullptr;
+    unsigned bitsA = 1, bitsB = 1;
+    size_t nCand = 0, nHit = 0;
+    unsigned long long *candKeys = nullptr; // final (sorted) candidate keys
+    void *candAlloc[2] = {nullptr, nullptr};
+    uint32_t *hitAB = nullptr;
+    double2 *hitSeg = nullptr;
+    uint8_t *flagsA = nullptr, *flagsB = nullptr;
+    std::vector<void *> owned; // stream-ordered allocations to release
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess)
+            ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+struct StageTimer {
+    sb_context *c;
+    sb_context::Span span;
+    bool on;
+    StageTimer(sb_context *ctx, int stage) : c(ctx), on(ctx->timing)
+    {
+        if (!on)
+            return;
+        span.stage = stage;
+        span.a = grab();
+        span.b = grab();
+        cudaEventRecord(span.a, c->stream);
+    }
+    ~StageTimer()
+    {
+        if (!on)
+            return;
+        cudaEventRecord(span.b, c->stream);
+        c->spans.push_back(span);
+    }
+    cudaEvent_t grab()
+    {
+        if (!c->freeEvents.empty()) {
+            cudaEvent_t e = c->freeEvents.back();
+            c->freeEvents.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+int ensure_radix_ws(sb_context *c, size_t n)
+{
+    size_t words = sbk_radix_workspace_words(n);
+    if (words <= c->radixWsWords)
+        return SB_OK;
+    if (c->radixWs) {
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        SB_CUDA(cudaFree(c->radixWs));
+        c->radixWs = nullptr;
+        c->radixWsWords = 0;
+    }
+    words = words + words / 4;
+    SB_CUDA(cudaMalloc(&c->radixWs, words * sizeof(uint32_t)));
+    c->radixWsWords = words;
+    return SB_OK;
+}
+
+int ensure_classify_out(sb_context *c, size_t bytes, uint32_t overflowCap)
+{
+    if (bytes > c->classifyOutBytes) {
+        if (c->classifyOut) {
+            SB_CUDA(cudaStreamSynchronize(c->stream));
+            SB_CUDA(cudaFree(c->classifyOut));
+            c->classifyOut = nullptr;
+        }
+        SB_CUDA(cudaMalloc(&c->classifyOut, bytes));
+        c->classifyOutBytes = bytes;
+    }
+    if (overflowCap > c->overflowCap) {
+        if (c->overflowList) {
+            SB_CUDA(cudaStreamSynchronize(c->stream));
+            SB_CUDA(cudaFree(c->overflowList));
+            c->overflowList = nullptr;
+        }
+        SB_CUDA(cudaMalloc(&c->overflowList, sizeof(uint32_t) * overflowCap));
+        c->overflowCap = overflowCap;
+    }
+    return SB_OK;
+}
+
+template <typename T>
+int alloc_async(sb_context *c, T **p, size_t count, std::vector<void *> *owned)
+{
+    void *q = nullptr;
+    SB_CUDA(cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), c->stream));
+    *p = static_cast<T *>(q);
+    if (owned)
+        owned->push_back(q);
+    return SB_OK;
+}
+
+int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
+{
+    if (nV >= (1ull << 31) || nT >= (1ull << 30))
+        return fail(SB_ERR_INVALID, "mesh too large: %zu vertices, %zu triangles", nV, nT);
+    sb_mesh *m = new (std::nothrow) sb_mesh;
+    if (!m)
+        return fail(SB_ERR_NOMEM, "out of host memory");
+    m->ctx = ctx;
+    MeshDev &d = m->d;
+    d.nV = (uint32_t)nV;
+    d.nT = (uint32_t)nT;
+    d.nTpad = (uint32_t)((nT + 31) / 32 * 32);
+    d.M = (uint32_t)((nT + SB_CLUSTER - 1) / SB_CLUSTER);
+    size_t nI = d.M > 1 ? d.M - 1 : 0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align256(std::max<size_t>(bytes, 16));
+        return o;
+    };
+    size_t oXyz = take(24 * nV), oTri = take(12 * nT), oVtx = take(32 * nV), oBounds = take(48);
+    size_t oTbox = take(48 * nT), oNormal = take(24 * nT);
+    size_t oKey = take(4 * nT), oKeyT = take(4 * nT), oOrd = take(4 * nT), oOrdT = take(4 * nT);
+    size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad);
+    size_t oCbox = take(32 * (size_t)d.M), oCkey = take(4 * (size_t)d.M + 4);
+    size_t oNodes = take(64 * nI), oSlot = take(4 * nI), oRoot = take(8);
+    cudaError_t e = cudaMalloc(&m->arena, off);
+    if (e != cudaSuccess) {
+        delete m;
+        return fail(e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, "cudaMalloc(%zu): %s", off,
+            cudaGetErrorString(e));
+    }
+    char *b = static_cast<char *>(m->arena);
+    d.xyz = (double *)(b + oXyz);
+    d.tri = (uint32_t *)(b + oTri);
+    d.vtx = (double4 *)(b + oVtx);
+    d.bounds = (unsigned long long *)(b + oBounds);
+    d.tbox = (double2 *)(b + oTbox);
+    d.normal = (double *)(b + oNormal);
+    d.mkey = (uint32_t *)(b + oKey);
+    d.mkeyTmp = (uint32_t *)(b + oKeyT);
+    d.order = (uint32_t *)(b + oOrd);
+    d.orderTmp = (uint32_t *)(b + oOrdT);
+    d.leaf = (Rec32 *)(b + oLeaf);
+    d.sbox = (double2 *)(b + oSbox);
+    d.cbox = (Rec32 *)(b + oCbox);
+    d.ckey = (uint32_t *)(b + oCkey);
+    d.nodes = (Rec32 *)(b + oNodes);
+    d.slot = (int *)(b + oSlot);
+    d.root = (int *)(b + oRoot);
+    d.err = d.root + 1;
+    *out = m;
+    return SB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *sb_last_error(void) { return g_err; }
+
+const char *sb_version(void) { return "solidboolean_b200 0.1 sm_100a"; }
+
+int sb_context_create(int device, sb_context **out)
+{
+    if (!out)
+        return fail(SB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SB_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return fail(SB_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+    DeviceGuard g(device);
+    if (!g.ok)
+        return fail(SB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    sb_context *c = new (std::nothrow) sb_context;
+    if (!c)
+        return fail(SB_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->smCount = prop.multiProcessorCount;
+    SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaMalloc(&c->dScalars, 256));
+    SB_CUDA(cudaMallocHost(&c->hScalars, 256));
+    // keep stream-ordered allocations cached in the pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return SB_OK;
+}
+
+void sb_context_destroy(sb_context *c)
+{
+    if (!c)
+        return;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &s : c->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    for (auto e : c->freeEvents)
+        cudaEventDestroy(e);
+    cudaFree(c->radixWs);
+    cudaFree(c->dScalars);
+    cudaFreeHost(c->hScalars);
+    cudaFree(c->classifyOut);
+    cudaFree(c->overflowList);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int sb_context_synchronize(sb_context *c)
+{
+    if (!c)
+        return fail(SB_ERR_INVALID, "context is null");
+    DeviceGuard g(c->device);
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+void *sb_context_stream(sb_context *c) { return c ? (void *)c->stream : nullptr; }
+int sb_context_device(const sb_context *c) { return c ? c->device : -1; }
+
+int sb_context_enable_timing(sb_context *c, int enable)
+{
+    if (!c)
+        return fail(SB_ERR_INVALID, "context is null");
+    c->timing = enable != 0;
+    return SB_OK;
+}
+
+static int drain_spans(sb_context *c)
+{
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto &s : c->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
+            c->acc[s.stage] += ms;
+        c->freeEvents.push_back(s.a);
+        c->freeEvents.push_back(s.b);
+    }
+    c->spans.clear();
+    return SB_OK;
+}
+
+int sb_context_reset_timing(sb_context *c)
+{
+    if (!c)
+        return fail(SB_ERR_INVALID, "context is null");
+    DeviceGuard g(c->device);
+    int r = drain_spans(c);
+    if (r)
+        return r;
+    for (float &a : c->acc)
+        a = 0;
+    c->lc.kernels = 0;
+    return SB_OK;
+}
+
+int sb_context_get_timing(sb_context *c, float *ms, uint64_t *kernel_launches)
+{
+    if (!c)
+        return fail(SB_ERR_INVALID, "context is null");
+    DeviceGuard g(c->device);
+    int r = drain_spans(c);
+    if (r)
+        return r;
+    if (ms)
+        for (int i = 0; i < SB_STAGE_COUNT; ++i)
+            ms[i] = c->acc[i];
+    if (kernel_launches)
+        *kernel_launches = c->lc.kernels;
+    return SB_OK;
+}
+
+int sb_context_classify_stats(sb_context *c, uint64_t *rays, uint64_t *candidates)
+{
+    if (!c)
+        return fail(SB_ERR_INVALID, "context is null");
+    if (rays)
+        *rays = c->lastRays;
+    if (candidates)
+        *candidates = c->lastCands;
+    return SB_OK;
+}
+
+// ---- mesh ---------------------------------------------------------------------
+
+int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t *tri, size_t nT, sb_mesh **out)
+{
+    if (!ctx || !out)
+        return fail(SB_ERR_INVALID, "null context or out");
+    *out = nullptr;
+    if ((nV && !xyz) || (nT && !tri))
+        return fail(SB_ERR_INVALID, "null geometry pointer");
+    if (nT && !nV)
+        return fail(SB_ERR_INVALID, "triangles without vertices");
+    DeviceGuard g(ctx->device);
+    sb_mesh *m = nullptr;
+    int r = mesh_alloc(ctx, nV, nT, &m);
+    if (r)
+        return r;
+    cudaError_t e = cudaSuccess;
+    if (nV)
+        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nT)
+        e = cudaMemcpyAsync(m->d.tri, tri, 12 * nT, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(m->arena);
+        delete m;
+        return fail(SB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return SB_OK;
+}
+
+int sb_mesh_build(sb_mesh *m)
+{
+    if (!m)
+        return fail(SB_ERR_INVALID, "mesh is null");
+    sb_context *c = m->ctx;
+    DeviceGuard g(c->device);
+    int r = ensure_radix_ws(c, m->d.nT);
+    if (r)
+        return r;
+    StageTimer t(c, SB_STAGE_BUILD);
+    SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, c->stream));
+    SB_CUDA(sbk_build_mesh(c->stream, m->d, c->radixWs, c->radixWsWords, c->smCount, c->lc));
+    m->built = true;
+    return SB_OK;
+}
+
+static int mesh_check(sb_mesh *m)
+{
+    sb_context *c = m->ctx;
+    int err = 0;
+    SB_CUDA(cudaMemcpyAsync(&c->hScalars->err, m->d.err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    err = c->hScalars->err;
+    if (err)
+        return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
+    return SB_OK;
+}
+
+int sb_mesh_create(sb_context *ctx, const double *xyz, size_t nV, const uint32_t *tri, size_t nT, sb_mesh **out)
+{
+    int r = sb_mesh_upload(ctx, xyz, nV, tri, nT, out);
+    if (r)
+        return r;
+    DeviceGuard g(ctx->device);
+    r = sb_mesh_build(*out);
+    if (!r)
+        r = mesh_check(*out);
+    if (r) {
+        sb_mesh_destroy(*out);
+        *out = nullptr;
+    }
+    return r;
+}
+
+void sb_mesh_destroy(sb_mesh *m)
+{
+    if (!m)
+        return;
+    DeviceGuard g(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->arena);
+    delete m;
+}
+
+size_t sb_mesh_num_triangles(const sb_mesh *m) { return m ? m->d.nT : 0; }
+size_t sb_mesh_num_vertices(const sb_mesh *m) { return m ? m->d.nV : 0; }
+
+static int mesh_download(const sb_mesh *m, void *dst, const void *src, size_t bytes)
+{
+    if (!m || !dst)
+        return fail(SB_ERR_INVALID, "null mesh or output");
+    if (!m->built)
+        return fail(SB_ERR_INVALID, "mesh not built");
+    DeviceGuard g(m->ctx->device);
+    if (bytes)
+        SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return SB_OK;
+}
+
+int sb_mesh_normals(const sb_mesh *m, double *out) { return mesh_download(m, out, m ? m->d.normal : nullptr, m ? 24 * (size_t)m->d.nT : 0); }
+int sb_mesh_triangle_boxes(const sb_mesh *m, double *out) { return mesh_download(m, out, m ? m->d.tbox : nullptr, m ? 48 * (size_t)m->d.nT : 0); }
+int sb_mesh_order(const sb_mesh *m, uint32_t *out) { return mesh_download(m, out, m ? m->d.sortedTri : nullptr, m ? 4 * (size_t)m->d.nT : 0); }
+
+int sb_mesh_bounds(const sb_mesh *m, double *out6)
+{
+    unsigned long long enc[6];
+    int r = mesh_download(m, enc, m ? m->d.bounds : nullptr, sizeof(enc));
+    if (r)
+        return r;
+    for (int i = 0; i < 6; ++i)
+        out6[i] = dkey_inv(enc[i]);
+    return SB_OK;
+}
+
+int sb_mesh_bvh_info(const sb_mesh *m, sb_bvh_info *out)
+{
+    int root = 0;
+    int r = mesh_download(m, &root, m ? m->d.root : nullptr, sizeof(int));
+    if (r)
+        return r;
+    out->cluster_size = SB_CLUSTER;
+    out->num_clusters = m->d.M;
+    out->num_internal = m->d.M > 1 ? m->d.M - 1 : 0;
+    out->root = root;
+    return SB_OK;
+}
+
+int sb_mesh_bvh_nodes(const sb_mesh *m, void *out)
+{
+    size_t nI = m && m->d.M > 1 ? m->d.M - 1 : 0;
+    return mesh_download(m, out, m ? m->d.nodes : nullptr, 64 * nI);
+}
+
+int sb_mesh_bvh_leaves(const sb_mesh *m, void *out, size_t *padded)
+{
+    if (padded)
+        *padded = m ? m->d.nTpad : 0;
+    return mesh_download(m, out, m ? m->d.leaf : nullptr, m ? 32 * (size_t)m->d.nTpad : 0);
+}
+
+// ---- intersection -----------------------------------------------------------------
+
+void sb_isect_destroy(sb_isect *x)
+{
+    if (!x)
+        return;
+    DeviceGuard g(x->ctx->device);
+    for (void *p : x->owned)
+        cudaFreeAsync(p, x->ctx->stream);
+    delete x;
+}
+
+int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t end, unsigned flags, sb_isect **out)
+{
+    if (!A || !B || !out)
+        return fail(SB_ERR_INVALID, "null mesh or out");
+    *out = nullptr;
+    if (A->ctx != B->ctx)
+        return fail(SB_ERR_INVALID, "meshes belong to different contexts");
+    if (!A->built || !B->built)
+        return fail(SB_ERR_INVALID, "mesh not built");
+    if (end > A->d.nT)
+        end = A->d.nT;
+    if (begin > end)
+        begin = end;
+    if (begin % 32)
+        return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
+    sb_context *c = A->ctx;
+    DeviceGuard g(c->device);
+    sb_isect *x = new (std::nothrow) sb_isect;
+    if (!x)
+        return fail(SB_ERR_NOMEM, "out of host memory");
+    x->ctx = c;
+    x->A = A;
+    x->B = B;
+    x->bitsA = bits_for(A->d.nT);
+    x->bitsB = bits_for(B->d.nT);
+    int r = SB_OK;
+    auto bail = [&](int code) {
+        sb_isect_destroy(x);
+        return code;
+    };
+#define SB_TRY(expr)          \
+    do {                      \
+        r = (expr);           \
+        if (r)                \
+            return bail(r);   \
+    } while (0)
+#define SB_CUDA_X(expr)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return bail(fail(SB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+
+    SB_TRY(alloc_async(c, &x->flagsA, A->d.nT, &x->owned));
+    SB_TRY(alloc_async(c, &x->flagsB, B->d.nT, &x->owned));
+    SB_CUDA_X(cudaMemsetAsync(x->flagsA, 0, std::max<size_t>(A->d.nT, 1), c->stream));
+    SB_CUDA_X(cudaMemsetAsync(x->flagsB, 0, std::max<size_t>(B->d.nT, 1), c->stream));
+
+    // ---- broad phase (retry once with the exact size if the guess was small) ----
+    uint32_t gBegin = (uint32_t)(begin / 32), gEnd = (uint32_t)((end + 31) / 32);
+    size_t cap = std::max<size_t>(1 << 16, 4 * ((end - begin) + (size_t)B->d.nT));
+    unsigned long long *keys = nullptr;
+    size_t nCand = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        SB_TRY(alloc_async(c, &keys, cap, nullptr));
+        {
+            StageTimer t(c, SB_STAGE_BROAD);
+            SB_CUDA_X(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
+            SB_CUDA_X(sbk_broad_phase(c->stream, A->d, B->d, gBegin, gEnd, x->bitsB, keys, cap, &c->dScalars->pairCount,
+                &c->dScalars->err, c->lc));
+        }
+        SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA_X(cudaStreamSynchronize(c->stream));
+        nCand = (size_t)c->hScalars->pairCount;
+        if (nCand <= cap)
+            break;
+        cudaFreeAsync(keys, c->stream);
+        keys = nullptr;
+        if (attempt == 1)
+            return bail(fail(SB_ERR_CAPACITY, "candidate buffer overflow after retry (%zu > %zu)", nCand, cap));
+        cap = nCand;
+    }
+    x->owned.push_back(keys);
+    if (nCand >= (1ull << 32))
+        return bail(fail(SB_ERR_CAPACITY, "too many candidate pairs (%zu)", nCand));
+    x->nCand = nCand;
+    x->candKeys = keys;
+
+    // ---- narrow phase ----
+    unsigned long long *hitKeys = nullptr, *hitKeysTmp = nullptr, *keysTmp = nullptr;
+    uint32_t *hitSlot = nullptr, *hitSlotTmp = nullptr;
+    double2 *hitSegRaw = nullptr;
+    if (nCand) {
+        SB_TRY(alloc_async(c, &hitKeys, nCand, &x->owned));
+        SB_TRY(alloc_async(c, &hitSlot, nCand, &x->owned));
+        SB_TRY(alloc_async(c, &hitSegRaw, 3 * nCand, &x->owned));
+        {
+            StageTimer t(c, SB_STAGE_NARROW);
+            SB_CUDA_X(sbk_predicate(c->stream, A->d, B->d, keys, (uint32_t)nCand, x->bitsB, hitKeys, hitSlot, hitSegRaw,
+                &c->dScalars->hitCount, x->flagsA, x->flagsB, c->lc));
+        }
+        SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA_X(cudaStreamSynchronize(c->stream));
+        x->nHit = c->hScalars->hitCount;
+    }
+    if (nCand) {
+        StageTimer t(c, SB_STAGE_NARROW);
+        const bool doSort = !(flags & SB_ISECT_NO_SORT);
+        unsigned long long *sortedHitKeys = hitKeys;
+        uint32_t *sortedSlot = hitSlot;
+        if (doSort) {
+            SB_TRY(ensure_radix_ws(c, nCand));
+            SB_TRY(alloc_async(c, &keysTmp, nCand, &x->owned));
+            unsigned long long *sortedKeys = nullptr;
+            SB_CUDA_X(sbk_sort_keys(c->stream, keys, keysTmp, nullptr, nullptr, nCand, 2, 2 + (int)(x->bitsA + x->bitsB),
+                c->radixWs, c->smCount, &sortedKeys, nullptr, c->lc));
+            x->candKeys = sortedKeys;
+            if (x->nHit > 1) {
+                SB_TRY(alloc_async(c, &hitKeysTmp, x->nHit, &x->owned));
+                SB_TRY(alloc_async(c, &hitSlotTmp, x->nHit, &x->owned));
+                SB_CUDA_X(sbk_sort_keys(c->stream, hitKeys, hitKeysTmp, hitSlot, hitSlotTmp, x->nHit, 0,
+                    (int)(x->bitsA + x->bitsB), c->radixWs, c->smCount, &sortedHitKeys, &sortedSlot, c->lc));
+            }
+        }
+        if (x->nHit) {
+            SB_TRY(alloc_async(c, &x->hitAB, 2 * x->nHit, &x->owned));
+            SB_TRY(alloc_async(c, &x->hitSeg, 3 * x->nHit, &x->owned));
+            SB_CUDA_X(sbk_gather_hits(c->stream, sortedHitKeys, sortedSlot, hitSegRaw, (uint32_t)x->nHit, x->bitsB, x->hitAB,
+                x->hitSeg, c->lc));
+        }
+    }
+#undef SB_TRY
+#undef SB_CUDA_X
+    *out = x;
+    return SB_OK;
+}
+
+int sb_intersect(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out)
+{
+    return sb_intersect_range(A, B, 0, A ? A->d.nT : 0, flags, out);
+}
+
+int sb_isect_counts(const sb_isect *x, size_t *nCand, size_t *nHit)
+{
+    if (!x)
+        return fail(SB_ERR_INVALID, "isect is null");
+    if (nCand)
+        *nCand = x->nCand;
+    if (nHit)
+        *nHit = x->nHit;
+    return SB_OK;
+}
+
+int sb_isect_candidates(const sb_isect *x, uint32_t *ab, uint8_t *code)
+{
+    if (!x || !ab)
+        return fail(SB_ERR_INVALID, "null isect or output");
+    sb_context *c = x->ctx;
+    DeviceGuard g(c->device);
+    if (!x->nCand)
+        return SB_OK;
+    uint32_t *dAB = nullptr;
+    uint8_t *dCode = nullptr;
+    int r = alloc_async(c, &dAB, 2 * x->nCand, nullptr);
+    if (r)
+        return r;
+    r = alloc_async(c, &dCode, x->nCand, nullptr);
+    if (r)
+        return r;
+    SB_CUDA(sbk_decode_candidates(c->stream, x->candKeys, (uint32_t)x->nCand, x->bitsB, dAB, dCode, c->lc));
+    SB_CUDA(cudaMemcpyAsync(ab, dAB, 8 * x->nCand, cudaMemcpyDeviceToHost, c->stream));
+    if (code)
+        SB_CUDA(cudaMemcpyAsync(code, dCode, x->nCand, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(dAB, c->stream);
+    cudaFreeAsync(dCode, c->stream);
+    return SB_OK;
+}
+
+int sb_isect_hits(const sb_isect *x, uint32_t *ab, double *seg)
+{
+    if (!x)
+        return fail(SB_ERR_INVALID, "isect is null");
+    sb_context *c = x->ctx;
+    DeviceGuard g(c->device);
+    if (!x->nHit)
+        return SB_OK;
+    if (ab)
+        SB_CUDA(cudaMemcpyAsync(ab, x->hitAB, 8 * x->nHit, cudaMemcpyDeviceToHost, c->stream));
+    if (seg)
+        SB_CUDA(cudaMemcpyAsync(seg, x->hitSeg, 48 * x->nHit, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_isect_face_flags(const sb_isect *x, uint8_t *flagsA, uint8_t *flagsB)
+{
+    if (!x)
+        return fail(SB_ERR_INVALID, "isect is null");
+    sb_context *c = x->ctx;
+    DeviceGuard g(c->device);
+    if (flagsA && x->A->d.nT)
+        SB_CUDA(cudaMemcpyAsync(flagsA, x->flagsA, x->A->d.nT, cudaMemcpyDeviceToHost, c->stream));
+    if (flagsB && x->B->d.nT)
+        SB_CUDA(cudaMemcpyAsync(flagsB, x->flagsB, x->B->d.nT, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_isect_device_ptrs(const sb_isect *x, void **cand_keys, unsigned *bits_b, void **hit_ab, void **hit_seg,
+    void **flagsA, void **flagsB)
+{
+    if (!x)
+        return fail(SB_ERR_INVALID, "isect is null");
+    if (cand_keys) *cand_keys = x->candKeys;
+    if (bits_b) *bits_b = x->bitsB;
+    if (hit_ab) *hit_ab = x->hitAB;
+    if (hit_seg) *hit_seg = x->hitSeg;
+    if (flagsA) *flagsA = x->flagsA;
+    if (flagsB) *flagsB = x->flagsB;
+    return SB_OK;
+}
+
+int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret, int32_t *coplanar, double *seg6)
+{
+    if (!c || (n && (!tris18 || !ret || !coplanar || !seg6)))
+        return fail(SB_ERR_INVALID, "null argument");
+    if (n >= (1ull << 31))
+        return fail(SB_ERR_INVALID, "batch too large");
+    if (!n)
+        return SB_OK;
+    DeviceGuard g(c->device);
+    double *dT = nullptr, *dSeg = nullptr;
+    int32_t *dRet = nullptr, *dCop = nullptr;
+    std::vector<void *> owned;
+    int r = alloc_async(c, &dT, 18 * n, &owned);
+    if (!r) r = alloc_async(c, &dSeg, 6 * n, &owned);
+    if (!r) r = alloc_async(c, &dRet, n, &owned);
+    if (!r) r = alloc_async(c, &dCop, n, &owned);
+    if (!r) {
+        cudaError_t e = cudaMemcpyAsync(dT, tris18, 144 * n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            StageTimer t(c, SB_STAGE_NARROW);
+            e = sbk_tri_tri_batch(c->stream, dT, (uint32_t)n, dRet, dCop, dSeg, c->lc);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ret, dRet, 4 * n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(coplanar, dCop, 4 * n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(seg6, dSeg, 48 * n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess)
+            r = fail(SB_ERR_CUDA, "sb_tri_tri_batch: %s", cudaGetErrorString(e));
+    }
+    for (void *p : owned)
+        cudaFreeAsync(p, c->stream);
+    return r;
+}
+
+// ---- classification --------------------------------------------------------------
+
+// Runs the kernel, reads the counters back, and sends overflowed points through
+// the exact slow path.  dInside / dPerAxis are device buffers.
+static int classify_run(sb_context *c, const sb_mesh *target, ClassifyArgs a, bool syncAndFinish)
+{
+    uint32_t ovCap = c->overflowCap;
+    a.stats = c->dScalars->stats;
+    a.overflowList = c->overflowList;
+    a.overflowCount = &c->dScalars->overflowCount;
+    a.overflowCap = ovCap;
+    {
+        StageTimer t(c, SB_STAGE_CLASSIFY);
+        SB_CUDA(sbk_classify(c->stream, target->d, a, &c->dScalars->err, c->lc));
+    }
+    if (!syncAndFinish)
+        return SB_OK;
+    SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    c->lastRays = c->hScalars->stats[0];
+    c->lastCands = c->hScalars->stats[1];
+    uint32_t nOv = c->hScalars->overflowCount;
+    if (nOv == 0)
+        return SB_OK;
+    if (nOv > ovCap)
+        return fail(SB_ERR_CAPACITY, "%u rays exceeded the per-ray hit list and the overflow list (%u)", nOv, ovCap);
+    const uint32_t keysPerRay = 1024;
+    const uint32_t chunk = 1024;
+    long long *scratch = nullptr;
+    size_t scratchBytes = (size_t)chunk * 3 * keysPerRay * 3 * sizeof(long long) + (size_t)chunk * 3 + 64;
+    SB_CUDA(cudaMallocAsync((void **)&scratch, scratchBytes, c->stream));
+    for (uint32_t o = 0; o < nOv; o += chunk) {
+        ClassifyArgs b = a;
+        b.overflowList = c->overflowList + o;
+        uint32_t n = std::min(chunk, nOv - o);
+        StageTimer t(c, SB_STAGE_CLASSIFY);
+        SB_CUDA(sbk_classify_overflow(c->stream, target->d, b, n, scratch, keysPerRay, &c->dScalars->err, c->lc));
+    }
+    SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(scratch, c->stream);
+    if (c->hScalars->err)
+        return fail(SB_ERR_CAPACITY, "a ray crossed more than %u distinct surface points", keysPerRay);
+    return SB_OK;
+}
+
+int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *inside, uint8_t *per_axis)
+{
+    if (!target || (Q && (!pts || !inside)))
+        return fail(SB_ERR_INVALID, "null argument");
+    if (!target->built)
+        return fail(SB_ERR_INVALID, "mesh not built");
+    if (Q >= (1ull << 31))
+        return fail(SB_ERR_INVALID, "too many points");
+    if (!Q)
+        return SB_OK;
+    sb_context *c = target->ctx;
+    DeviceGuard g(c->device);
+    int r = ensure_classify_out(c, 4 * Q, (uint32_t)std::min<size_t>(Q, 1 << 20));
+    if (r)
+        return r;
+    double *dPts = nullptr;
+    r = alloc_async(c, &dPts, 3 * Q, nullptr);
+    if (r)
+        return r;
+    SB_CUDA(cudaMemcpyAsync(dPts, pts, 24 * Q, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
+    ClassifyArgs a;
+    a.pts = dPts;
+    a.begin = 0;
+    a.end = (uint32_t)Q;
+    a.inside = c->classifyOut;
+    a.perAxis = c->classifyOut + Q;
+    if (target->d.nT == 0) {
+        SB_CUDA(cudaMemsetAsync(c->classifyOut, 0, 4 * Q, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        r = classify_run(c, target, a, true);
+    }
+    if (!r) {
+        SB_CUDA(cudaMemcpyAsync(inside, a.inside, Q, cudaMemcpyDeviceToHost, c->stream));
+        if (per_axis)
+            SB_CUDA(cudaMemcpyAsync(per_axis, a.perAxis, 3 * Q, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    cudaFreeAsync(dPts, c->stream);
+    return r;
+}
+
+static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size_t begin, size_t end, bool finish,
+    uint8_t *externalInside, uint8_t **dInside, uint8_t **dPerAxis)
+{
+    if (!query || !target)
+        return fail(SB_ERR_INVALID, "null mesh");
+    if (query->ctx != target->ctx)
+        return fail(SB_ERR_INVALID, "meshes belong to different contexts");
+    if (!query->built || !target->built)
+        return fail(SB_ERR_INVALID, "mesh not built");
+    sb_context *c = query->ctx;
+    size_t n = query->d.nT;
+    if (end > n)
+        end = n;
+    if (begin > end)
+        begin = end;
+    if (begin % 32)
+        return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
+    int r = ensure_classify_out(c, 4 * std::max<size_t>(n, 1), (uint32_t)std::min<size_t>(std::max<size_t>(n, 1), 1 << 20));
+    if (r)
+        return r;
+    SB_CUDA(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
+    ClassifyArgs a;
+    a.queryMesh = &query->d;
+    a.begin = (uint32_t)begin;
+    a.end = (uint32_t)end;
+    a.inside = externalInside ? externalInside : c->classifyOut;
+    a.perAxis = c->classifyOut + n;
+    *dInside = a.inside;
+    *dPerAxis = a.perAxis;
+    if (target->d.nT == 0) {
+        SB_CUDA(cudaMemsetAsync(c->classifyOut, 0, 4 * std::max<size_t>(n, 1), c->stream));
+        if (externalInside && n)
+            SB_CUDA(cudaMemsetAsync(externalInside, 0, n, c->stream));
+        return SB_OK;
+    }
+    return classify_run(c, target, a, finish);
+}
+
+int sb_classify_faces(const sb_mesh *query, const sb_mesh *target, uint8_t *inside, uint8_t *per_axis)
+{
+    if (!inside)
+        return fail(SB_ERR_INVALID, "inside is null");
+    if (!query)
+        return fail(SB_ERR_INVALID, "null mesh");
+    DeviceGuard g(query->ctx->device);
+    uint8_t *dIn = nullptr, *dAx = nullptr;
+    int r = classify_faces_impl(query, target, 0, query->d.nT, true, nullptr, &dIn, &dAx);
+    if (r)
+        return r;
+    sb_context *c = query->ctx;
+    size_t n = query->d.nT;
+    if (n) {
+        SB_CUDA(cudaMemcpyAsync(inside, dIn, n, cudaMemcpyDeviceToHost, c->stream));
+        if (per_axis)
+            SB_CUDA(cudaMemcpyAsync(per_axis, dAx, 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target, size_t begin, size_t end, void *d_inside)
+{
+    if (!query || !d_inside)
+        return fail(SB_ERR_INVALID, "null mesh or output");
+    DeviceGuard g(query->ctx->device);
+    uint8_t *dIn = nullptr, *dAx = nullptr;
+    // the slow path for overflowing rays needs the counters on the host, so this
+    // call synchronises once after the kernel (a 40-byte read-back)
+    return classify_faces_impl(query, target, begin, end, true, static_cast<uint8_t *>(d_inside), &dIn, &dAx);
+}
+
+} // extern "C"

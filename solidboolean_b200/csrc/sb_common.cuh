@@ -1,0 +1,147 @@
+// Shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include <string.h>
+#include "sb_fp64.cuh"
+
+#define SB_WARP 32
+#define SB_FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------
+// 32-byte record shared by LBVH children, cluster boxes and sorted-triangle
+// leaves: conservative float box + a reference.  Exactly one 32-B sector.
+struct __align__(32) Rec32 {
+    float lox, loy, loz, hix;
+    float hiy, hiz;
+    int ref; // child: >=0 internal node, <0 ~cluster; leaf: original triangle id
+    int aux;
+};
+
+struct BoxF {
+    float lox, loy, loz, hix, hiy, hiz;
+};
+
+struct BoxD {
+    double lox, loy, loz, hix, hiy, hiz;
+};
+
+__device__ __forceinline__ Rec32 load_rec(const Rec32 *p)
+{
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    float4 a = __ldg(q);
+    float4 b = __ldg(q + 1);
+    Rec32 r;
+    r.lox = a.x; r.loy = a.y; r.loz = a.z; r.hix = a.w;
+    r.hiy = b.x; r.hiz = b.y;
+    r.ref = __float_as_int(b.z);
+    r.aux = __float_as_int(b.w);
+    return r;
+}
+
+// coherent (L2) load, for data written earlier in the same kernel by another thread
+__device__ __forceinline__ Rec32 load_rec_cg(const Rec32 *p)
+{
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    float4 a = __ldcg(q);
+    float4 b = __ldcg(q + 1);
+    Rec32 r;
+    r.lox = a.x; r.loy = a.y; r.loz = a.z; r.hix = a.w;
+    r.hiy = b.x; r.hiz = b.y;
+    r.ref = __float_as_int(b.z);
+    r.aux = __float_as_int(b.w);
+    return r;
+}
+
+__device__ __forceinline__ void store_rec(Rec32 *p, const BoxF &b, int ref, int aux)
+{
+    float4 *q = reinterpret_cast<float4 *>(p);
+    q[0] = make_float4(b.lox, b.loy, b.loz, b.hix);
+    q[1] = make_float4(b.hiy, b.hiz, __int_as_float(ref), __int_as_float(aux));
+}
+
+// closed-interval overlap, written with the same comparisons as
+// AxisAlignedBoudingBox::intersectWith (axisalignedboundingbox.h:95-105) so NaN
+// behaves identically (any NaN -> no overlap).
+__device__ __forceinline__ bool overlap_f(const BoxF &a, float lox, float loy, float loz, float hix, float hiy, float hiz)
+{
+    return a.lox <= hix && a.hix >= lox && a.loy <= hiy && a.hiy >= loy && a.loz <= hiz && a.hiz >= loz;
+}
+
+__device__ __forceinline__ bool overlap_d(const BoxD &a, const BoxD &b)
+{
+    return a.lox <= b.hix && a.hix >= b.lox && a.loy <= b.hiy && a.hiy >= b.loy && a.loz <= b.hiz && a.hiz >= b.loz;
+}
+
+// double box stored as 3 x double2: {lox,loy} {loz,hix} {hiy,hiz}
+__device__ __forceinline__ BoxD load_boxd(const double2 *p)
+{
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    return {a.x, a.y, b.x, b.y, c.x, c.y};
+}
+
+__device__ __forceinline__ void store_boxd(double2 *p, const BoxD &b)
+{
+    p[0] = make_double2(b.lox, b.loy);
+    p[1] = make_double2(b.loz, b.hix);
+    p[2] = make_double2(b.hiy, b.hiz);
+}
+
+// conservative float enclosure of a double box
+__device__ __forceinline__ BoxF enclose(const BoxD &b)
+{
+    return {__double2float_rd(b.lox), __double2float_rd(b.loy), __double2float_rd(b.loz),
+            __double2float_ru(b.hix), __double2float_ru(b.hiy), __double2float_ru(b.hiz)};
+}
+
+__device__ __forceinline__ BoxF empty_boxf()
+{
+    return {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+}
+
+__device__ __forceinline__ void merge_f(BoxF &a, const BoxF &b)
+{
+    a.lox = fminf(a.lox, b.lox); a.loy = fminf(a.loy, b.loy); a.loz = fminf(a.loz, b.loz);
+    a.hix = fmaxf(a.hix, b.hix); a.hiy = fmaxf(a.hiy, b.hiy); a.hiz = fmaxf(a.hiz, b.hiz);
+}
+
+__device__ __forceinline__ BoxF shfl_xor_box(const BoxF &b, int mask)
+{
+    return {__shfl_xor_sync(SB_FULL, b.lox, mask), __shfl_xor_sync(SB_FULL, b.loy, mask),
+            __shfl_xor_sync(SB_FULL, b.loz, mask), __shfl_xor_sync(SB_FULL, b.hix, mask),
+            __shfl_xor_sync(SB_FULL, b.hiy, mask), __shfl_xor_sync(SB_FULL, b.hiz, mask)};
+}
+
+// vertices are stored padded to double4 (one 32-B sector each, two 128-bit loads)
+__device__ __forceinline__ d3 load_vertex(const double4 *v, uint32_t i)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(v + i);
+    double2 a = __ldg(p), b = __ldg(p + 1);
+    return {a.x, a.y, b.x};
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// order-preserving double <-> uint64 map (for atomicMin/Max on doubles)
+__device__ __forceinline__ unsigned long long dkey(double x)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dkey_inv(unsigned long long k)
+{
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, sizeof(d));
+    return d;
+#endif
+}

@@ -1,0 +1,87 @@
+// Internal host-side interface between the C ABI (sb_capi.cu) and the kernel
+// translation units.  Not installed; include/solidboolean_b200.h is the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "sb_common.cuh"
+
+// Cluster size K of the LBVH (leaves are K Morton-consecutive triangles).
+#ifndef SB_CLUSTER
+#define SB_CLUSTER 8
+#endif
+
+// Device-resident mesh (all pointers are device pointers).
+struct MeshDev {
+    uint32_t nV = 0, nT = 0;
+    uint32_t nTpad = 0; // nT rounded up to a multiple of 32
+    uint32_t M = 0;     // clusters = ceil(nT / K)
+    // geometry as uploaded
+    double *xyz = nullptr;   // AoS 3*nV
+    uint32_t *tri = nullptr; // 3*nT
+    // derived (sb_mesh_build)
+    double4 *vtx = nullptr;             // padded vertices
+    unsigned long long *bounds = nullptr; // 6 order-encoded doubles: min xyz, max xyz
+    double2 *tbox = nullptr;            // 3*nT: exact triangle boxes, original order
+    double *normal = nullptr;           // 3*nT, original order
+    uint32_t *mkey = nullptr, *mkeyTmp = nullptr;   // Morton keys (sort ping-pong)
+    uint32_t *order = nullptr, *orderTmp = nullptr; // triangle ids (sort ping-pong)
+    uint32_t *sortedKey = nullptr;      // -> mkey or mkeyTmp after the sort
+    uint32_t *sortedTri = nullptr;      // -> order or orderTmp: sorted position -> triangle id
+    Rec32 *leaf = nullptr;              // nTpad sorted-triangle records (float box + id)
+    double2 *sbox = nullptr;            // 3*nTpad exact boxes in sorted order
+    Rec32 *cbox = nullptr;              // M cluster boxes
+    uint32_t *ckey = nullptr;           // M cluster keys
+    Rec32 *nodes = nullptr;             // 2*(M-1) child records
+    int *slot = nullptr;                // M-1 rendezvous slots
+    int *root = nullptr;                // device scalar
+    int *err = nullptr;                 // device scalar: 1 = triangle index out of range
+};
+
+struct LaunchCounter {
+    uint64_t kernels = 0;
+};
+
+// sb_build.cu
+cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t radixWsWords, int smCount, LaunchCounter &lc);
+
+// sb_broad.cu -- candidate keys: (((a << bitsB) | b) << 2), code bits zero
+cudaError_t sbk_broad_phase(cudaStream_t s, const MeshDev &A, const MeshDev &B, uint32_t groupBegin, uint32_t groupEnd,
+    unsigned bitsB, unsigned long long *outKeys, unsigned long long capacity, unsigned long long *outCount,
+    int *errFlag, LaunchCounter &lc);
+
+// sb_narrow.cu
+cudaError_t sbk_predicate(cudaStream_t s, const MeshDev &A, const MeshDev &B, unsigned long long *keys, uint32_t nPairs,
+    unsigned bitsB, unsigned long long *hitKeys, uint32_t *hitSlot, double2 *hitSeg, unsigned int *hitCount,
+    uint8_t *flagsA, uint8_t *flagsB, LaunchCounter &lc);
+cudaError_t sbk_gather_hits(cudaStream_t s, const unsigned long long *sortedHitKeys, const uint32_t *sortedSlot,
+    const double2 *hitSeg, uint32_t nHits, unsigned bitsB, uint32_t *outAB, double2 *outSeg, LaunchCounter &lc);
+cudaError_t sbk_decode_candidates(cudaStream_t s, const unsigned long long *keys, uint32_t n, unsigned bitsB,
+    uint32_t *outAB, uint8_t *outCode, LaunchCounter &lc);
+cudaError_t sbk_tri_tri_batch(cudaStream_t s, const double *tris18, uint32_t n, int32_t *ret, int32_t *coplanar,
+    double *seg6, LaunchCounter &lc);
+cudaError_t sbk_sort_keys(cudaStream_t s, unsigned long long *keys, unsigned long long *keysTmp, uint32_t *vals,
+    uint32_t *valsTmp, size_t n, int beginBit, int endBit, uint32_t *radixWs, int smCount,
+    unsigned long long **outKeys, uint32_t **outVals, LaunchCounter &lc);
+
+// sb_classify.cu
+struct ClassifyArgs {
+    // query points: either explicit (pts != null, AoS 3*Q, processed in given order)
+    // or the face centroids of `queryMesh` at sorted positions [begin, end)
+    const double *pts = nullptr;
+    const MeshDev *queryMesh = nullptr;
+    uint32_t begin = 0, end = 0; // point range (explicit) or sorted-position range (faces)
+    uint8_t *inside = nullptr;   // indexed by point index / original triangle id
+    uint8_t *perAxis = nullptr;  // optional, 3 per point
+    unsigned long long *stats = nullptr; // [0] rays, [1] candidates
+    uint32_t *overflowList = nullptr;    // point indices whose hit list overflowed
+    unsigned int *overflowCount = nullptr;
+    uint32_t overflowCap = 0;
+};
+cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, int *errFlag, LaunchCounter &lc);
+// exact slow path for the points in overflowList (one thread per ray, brute force
+// over the target's triangles, hit keys kept in `scratch`)
+cudaError_t sbk_classify_overflow(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, uint32_t nOverflow,
+    long long *scratch, uint32_t scratchKeysPerRay, int *errFlag, LaunchCounter &lc);
+
+size_t sbk_radix_workspace_words(size_t n);

@@ -1,0 +1,162 @@
+// Stage 3: narrow phase.  Replaces the candidate loop of SolidBoolean::combine()
+// (reference src/solidboolean.cpp:315-320) and intersectTwoFaces (:103-122):
+// one thread per candidate pair runs the Guigue-Devillers predicate
+// (sb_tritri.cuh) in strict binary64, records (ret, coplanar) in the two low
+// bits of the pair key, and compacts accepted pairs (ret && !coplanar) with their
+// segment into the hit buffer (warp-aggregated atomics).  Both lists are then
+// ordered by (a, b) with the onesweep radix sort.
+#include "sb_internal.h"
+#include "sb_radix.cuh"
+#include "sb_tritri.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__restrict__ keys, uint32_t nPairs, unsigned bitsB,
+    const double4 *__restrict__ vtxA, const uint32_t *__restrict__ triA,
+    const double4 *__restrict__ vtxB, const uint32_t *__restrict__ triB,
+    unsigned long long *__restrict__ hitKeys, uint32_t *__restrict__ hitSlot, double2 *__restrict__ hitSeg,
+    unsigned int *__restrict__ hitCount, uint8_t *__restrict__ flagsA, uint8_t *__restrict__ flagsB)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool hit = false;
+    unsigned long long ab = 0;
+    d3 src = {0, 0, 0}, tgt = {0, 0, 0};
+    uint32_t a = 0, b = 0;
+    if (i < nPairs) {
+        unsigned long long key = keys[i];
+        ab = key >> 2;
+        a = (uint32_t)(ab >> bitsB);
+        b = (uint32_t)(ab & ((1ull << bitsB) - 1));
+        uint32_t a0 = __ldg(triA + 3 * (size_t)a), a1 = __ldg(triA + 3 * (size_t)a + 1), a2 = __ldg(triA + 3 * (size_t)a + 2);
+        uint32_t b0 = __ldg(triB + 3 * (size_t)b), b1 = __ldg(triB + 3 * (size_t)b + 1), b2 = __ldg(triB + 3 * (size_t)b + 2);
+        d3 p1 = load_vertex(vtxA, a0), q1 = load_vertex(vtxA, a1), r1 = load_vertex(vtxA, a2);
+        d3 p2 = load_vertex(vtxB, b0), q2 = load_vertex(vtxB, b1), r2 = load_vertex(vtxB, b2);
+        int coplanar = 0;
+        int ret = tri_tri_intersection(p1, q1, r1, p2, q2, r2, coplanar, src, tgt);
+        keys[i] = key | (unsigned long long)((ret ? 1 : 0) | (coplanar ? 2 : 0));
+        hit = ret && !coplanar; // intersectTwoFaces, src/solidboolean.cpp:117-121
+    }
+    uint32_t m = __ballot_sync(SB_FULL, hit);
+    if (m == 0)
+        return;
+    unsigned int base = 0;
+    if (lane == __ffs(m) - 1)
+        base = atomicAdd(hitCount, (unsigned int)__popc(m));
+    base = __shfl_sync(SB_FULL, base, __ffs(m) - 1);
+    if (hit) {
+        unsigned int slot = base + __popc(m & lanemask_lt());
+        hitKeys[slot] = ab;
+        hitSlot[slot] = slot;
+        double2 *o = hitSeg + 3 * (size_t)slot;
+        o[0] = make_double2(src.x, src.y);
+        o[1] = make_double2(src.z, tgt.x);
+        o[2] = make_double2(tgt.y, tgt.z);
+        flagsA[a] = 1;
+        flagsB[b] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_hits_kernel(const unsigned long long *__restrict__ sortedKeys,
+    const uint32_t *__restrict__ sortedSlot, const double2 *__restrict__ hitSeg, uint32_t nHits, unsigned bitsB,
+    uint32_t *__restrict__ outAB, double2 *__restrict__ outSeg)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nHits)
+        return;
+    unsigned long long ab = sortedKeys[i];
+    outAB[2 * (size_t)i] = (uint32_t)(ab >> bitsB);
+    outAB[2 * (size_t)i + 1] = (uint32_t)(ab & ((1ull << bitsB) - 1));
+    const double2 *src = hitSeg + 3 * (size_t)sortedSlot[i];
+    double2 *dst = outSeg + 3 * (size_t)i;
+    dst[0] = src[0];
+    dst[1] = src[1];
+    dst[2] = src[2];
+}
+
+__global__ void __launch_bounds__(256) decode_candidates_kernel(const unsigned long long *__restrict__ keys, uint32_t n,
+    unsigned bitsB, uint32_t *__restrict__ outAB, uint8_t *__restrict__ outCode)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    unsigned long long key = keys[i];
+    unsigned long long ab = key >> 2;
+    reinterpret_cast<uint2 *>(outAB)[i] = make_uint2((uint32_t)(ab >> bitsB), (uint32_t)(ab & ((1ull << bitsB) - 1)));
+    if (outCode)
+        outCode[i] = (uint8_t)(key & 3);
+}
+
+__global__ void __launch_bounds__(128) tri_tri_batch_kernel(const double *__restrict__ tris, uint32_t n,
+    int32_t *__restrict__ ret, int32_t *__restrict__ coplanar, double *__restrict__ seg)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double *v = tris + 18 * (size_t)i;
+    d3 p1 = {v[0], v[1], v[2]}, q1 = {v[3], v[4], v[5]}, r1 = {v[6], v[7], v[8]};
+    d3 p2 = {v[9], v[10], v[11]}, q2 = {v[12], v[13], v[14]}, r2 = {v[15], v[16], v[17]};
+    int cop = 0;
+    d3 s = {0, 0, 0}, t = {0, 0, 0};
+    int r = tri_tri_intersection(p1, q1, r1, p2, q2, r2, cop, s, t);
+    ret[i] = r;
+    coplanar[i] = cop;
+    double *o = seg + 6 * (size_t)i;
+    o[0] = s.x; o[1] = s.y; o[2] = s.z;
+    o[3] = t.x; o[4] = t.y; o[5] = t.z;
+}
+
+} // namespace
+
+cudaError_t sbk_predicate(cudaStream_t s, const MeshDev &A, const MeshDev &B, unsigned long long *keys, uint32_t nPairs,
+    unsigned bitsB, unsigned long long *hitKeys, uint32_t *hitSlot, double2 *hitSeg, unsigned int *hitCount,
+    uint8_t *flagsA, uint8_t *flagsB, LaunchCounter &lc)
+{
+    if (nPairs == 0)
+        return cudaSuccess;
+    predicate_kernel<<<(nPairs + 127) / 128, 128, 0, s>>>(keys, nPairs, bitsB, A.vtx, A.tri, B.vtx, B.tri, hitKeys, hitSlot,
+        hitSeg, hitCount, flagsA, flagsB);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sbk_gather_hits(cudaStream_t s, const unsigned long long *sortedHitKeys, const uint32_t *sortedSlot,
+    const double2 *hitSeg, uint32_t nHits, unsigned bitsB, uint32_t *outAB, double2 *outSeg, LaunchCounter &lc)
+{
+    if (nHits == 0)
+        return cudaSuccess;
+    gather_hits_kernel<<<(nHits + 255) / 256, 256, 0, s>>>(sortedHitKeys, sortedSlot, hitSeg, nHits, bitsB, outAB, outSeg);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sbk_decode_candidates(cudaStream_t s, const unsigned long long *keys, uint32_t n, unsigned bitsB,
+    uint32_t *outAB, uint8_t *outCode, LaunchCounter &lc)
+{
+    if (n == 0)
+        return cudaSuccess;
+    decode_candidates_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, n, bitsB, outAB, outCode);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sbk_tri_tri_batch(cudaStream_t s, const double *tris18, uint32_t n, int32_t *ret, int32_t *coplanar,
+    double *seg6, LaunchCounter &lc)
+{
+    if (n == 0)
+        return cudaSuccess;
+    tri_tri_batch_kernel<<<(n + 127) / 128, 128, 0, s>>>(tris18, n, ret, coplanar, seg6);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sbk_sort_keys(cudaStream_t s, unsigned long long *keys, unsigned long long *keysTmp, uint32_t *vals,
+    uint32_t *valsTmp, size_t n, int beginBit, int endBit, uint32_t *radixWs, int smCount,
+    unsigned long long **outKeys, uint32_t **outVals, LaunchCounter &lc)
+{
+    sbradix::Workspace ws;
+    ws.mem = radixWs;
+    lc.kernels += sbradix::sort<unsigned long long>(s, keys, keysTmp, vals, valsTmp, n, beginBit, endBit, ws, smCount,
+        outKeys, outVals);
+    return cudaGetLastError();
+}

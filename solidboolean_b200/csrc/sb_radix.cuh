@@ -1,0 +1,257 @@
+// Onesweep LSD radix sort (8-bit digits, chained scan with decoupled lookback):
+// one histogram pass over the keys for ALL digit positions, then one
+// read+write pass per digit.  Used for the Morton sort of triangles (u32 key +
+// u32 payload) and for ordering candidate / hit pair keys (u64 key, optional
+// u32 payload).  Stable; keys-only or key-value.
+#pragma once
+#include "sb_common.cuh"
+
+namespace sbradix {
+
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int ITEMS = 16;
+constexpr int TILE = THREADS * ITEMS; // 4096 keys per CTA
+constexpr int RADIX = 256;
+constexpr int MAX_PASSES = 8;
+
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t VALUE_MASK = (1u << 30) - 1;
+
+// Histogram of every digit position in one pass; the last CTA to finish turns
+// each 256-bin histogram into an exclusive prefix (global digit offsets).
+template <typename KeyT>
+__global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ keys, uint32_t n,
+    int beginBit, int passes, uint32_t *__restrict__ hist /* [passes][256] */, uint32_t *__restrict__ ticket)
+{
+    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    __shared__ bool s_last;
+    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
+        s_hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n; i += gridDim.x * THREADS) {
+        KeyT k = keys[i];
+        for (int p = 0; p < passes; ++p)
+            atomicAdd(&s_hist[p * RADIX + (uint32_t)((k >> (beginBit + 8 * p)) & 0xff)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
+        if (s_hist[i])
+            atomicAdd(&hist[i], s_hist[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    // exclusive scan of each pass's 256 bins (thread d owns bin d)
+    __shared__ uint32_t s_scan[RADIX];
+    for (int p = 0; p < passes; ++p) {
+        uint32_t v = __ldcg(&hist[p * RADIX + threadIdx.x]);
+        s_scan[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < RADIX; off <<= 1) {
+            uint32_t t = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += t;
+            __syncthreads();
+        }
+        hist[p * RADIX + threadIdx.x] = s_scan[threadIdx.x] - v;
+        __syncthreads();
+    }
+}
+
+template <typename KeyT, bool HAS_VALUES>
+__global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restrict__ keysIn, KeyT *__restrict__ keysOut,
+    const uint32_t *__restrict__ valsIn, uint32_t *__restrict__ valsOut, uint32_t n, int shift,
+    const uint32_t *__restrict__ digitBase /* [256] exclusive */, volatile uint32_t *lookback /* [tiles][256] */,
+    uint32_t *__restrict__ tileCounter)
+{
+    __shared__ uint32_t s_warpHist[WARPS][RADIX];
+    __shared__ uint32_t s_digitStart[RADIX];
+    __shared__ uint32_t s_globalOff[RADIX];
+    __shared__ uint32_t s_scanTmp[WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ __align__(16) unsigned char s_raw[TILE * sizeof(KeyT)];
+    KeyT *s_keys = reinterpret_cast<KeyT *>(s_raw);
+    uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+        s_tile = atomicAdd(tileCounter, 1u);
+    for (int i = tid; i < WARPS * RADIX; i += THREADS)
+        (&s_warpHist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tileBase = tile * TILE;
+    const uint32_t tileCount = min((uint32_t)TILE, n - tileBase);
+
+    // striped load: item i of lane l sits at warpBase + i*32 + l (memory order =
+    // (i, l) lexicographic, which is the order ranks are handed out in -> stable)
+    KeyT key[ITEMS];
+    uint32_t rank[ITEMS];
+    const uint32_t warpBase = tileBase + warp * (32 * ITEMS);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint32_t idx = warpBase + i * 32 + lane;
+        key[i] = idx < n ? keysIn[idx] : (KeyT)~(KeyT)0;
+    }
+    const uint32_t ltMask = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint32_t digit = (uint32_t)((key[i] >> shift) & 0xff);
+        uint32_t peers = __match_any_sync(SB_FULL, digit);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = s_warpHist[warp][digit];
+            s_warpHist[warp][digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(SB_FULL, old, leader);
+        rank[i] = old + __popc(peers & ltMask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d: exclusive scan of digit d over the warps, tile aggregate, lookback
+    {
+        const int d = tid;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            uint32_t t = s_warpHist[w][d];
+            s_warpHist[w][d] = sum;
+            sum += t;
+        }
+        uint32_t excl = 0;
+        if (tile == 0) {
+            lookback[d] = sum | FLAG_PREFIX;
+        } else {
+            lookback[tile * RADIX + d] = sum | FLAG_AGG;
+            int t = (int)tile - 1;
+            while (true) {
+                uint32_t v = lookback[t * RADIX + d];
+                if (v & FLAG_PREFIX) {
+                    excl += v & VALUE_MASK;
+                    break;
+                }
+                if (v & FLAG_AGG) {
+                    excl += v & VALUE_MASK;
+                    --t;
+                }
+            }
+            lookback[tile * RADIX + d] = (excl + sum) | FLAG_PREFIX;
+        }
+        // block-wide exclusive scan of `sum` over the 256 digits
+        uint32_t incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
+            if (lane >= off)
+                incl += t;
+        }
+        if (lane == 31)
+            s_scanTmp[warp] = incl;
+        __syncthreads();
+        uint32_t warpOff = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w)
+            if (w < warp)
+                warpOff += s_scanTmp[w];
+        uint32_t start = warpOff + incl - sum;
+        s_digitStart[d] = start;
+        s_globalOff[d] = digitBase[d] + excl - start;
+    }
+    __syncthreads();
+
+    // local scatter so that the global writes below are runs of consecutive addresses
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint32_t digit = (uint32_t)((key[i] >> shift) & 0xff);
+        rank[i] += s_digitStart[digit] + s_warpHist[warp][digit];
+        s_keys[rank[i]] = key[i];
+    }
+    __syncthreads();
+    uint32_t gpos[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        uint32_t j = tid + i * THREADS;
+        KeyT k = s_keys[j];
+        uint32_t digit = (uint32_t)((k >> shift) & 0xff);
+        gpos[i] = s_globalOff[digit] + j;
+        if (j < tileCount)
+            keysOut[gpos[i]] = k;
+    }
+    if (HAS_VALUES) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint32_t idx = warpBase + i * 32 + lane;
+            s_vals[rank[i]] = idx < n ? valsIn[idx] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint32_t j = tid + i * THREADS;
+            if (j < tileCount)
+                valsOut[gpos[i]] = s_vals[j];
+        }
+    }
+}
+
+struct Workspace {
+    uint32_t *mem = nullptr; // [hist: MAX_PASSES*256][ticket+counters: 16][lookback: MAX_PASSES * tiles * 256]
+    size_t tilesCap = 0;
+    static size_t words(size_t tiles) { return MAX_PASSES * RADIX + 16 + MAX_PASSES * tiles * RADIX; }
+};
+
+inline size_t tiles_for(size_t n) { return (n + TILE - 1) / TILE; }
+
+// Sort n keys on bits [beginBit, endBit).  Results land in *outKeys/*outVals
+// (either the primary or the tmp buffers).  Returns the number of kernels launched.
+template <typename KeyT>
+int sort(cudaStream_t stream, KeyT *keys, KeyT *keysTmp, uint32_t *vals, uint32_t *valsTmp, size_t n,
+    int beginBit, int endBit, const Workspace &ws, int smCount, KeyT **outKeys, uint32_t **outVals)
+{
+    *outKeys = keys;
+    if (outVals)
+        *outVals = vals;
+    if (n < 2 || endBit <= beginBit)
+        return 0;
+    int passes = (endBit - beginBit + 7) / 8;
+    if (passes > MAX_PASSES)
+        passes = MAX_PASSES;
+    size_t tiles = tiles_for(n);
+    uint32_t *hist = ws.mem;
+    uint32_t *ticket = ws.mem + MAX_PASSES * RADIX;
+    uint32_t *counters = ticket + 1;
+    uint32_t *lookback = ws.mem + MAX_PASSES * RADIX + 16;
+    cudaMemsetAsync(ws.mem, 0, sizeof(uint32_t) * (MAX_PASSES * RADIX + 16 + (size_t)passes * tiles * RADIX), stream);
+    int histBlocks = (int)((n + THREADS * 8 - 1) / (THREADS * 8));
+    if (histBlocks > smCount * 4)
+        histBlocks = smCount * 4;
+    if (histBlocks < 1)
+        histBlocks = 1;
+    hist_kernel<KeyT><<<histBlocks, THREADS, 0, stream>>>(keys, (uint32_t)n, beginBit, passes, hist, ticket);
+    KeyT *kin = keys, *kout = keysTmp;
+    uint32_t *vin = vals, *vout = valsTmp;
+    for (int p = 0; p < passes; ++p) {
+        if (vals)
+            onesweep_kernel<KeyT, true><<<(unsigned)tiles, THREADS, 0, stream>>>(kin, kout, vin, vout, (uint32_t)n,
+                beginBit + 8 * p, hist + p * RADIX, lookback + (size_t)p * tiles * RADIX, counters + p);
+        else
+            onesweep_kernel<KeyT, false><<<(unsigned)tiles, THREADS, 0, stream>>>(kin, kout, nullptr, nullptr, (uint32_t)n,
+                beginBit + 8 * p, hist + p * RADIX, lookback + (size_t)p * tiles * RADIX, counters + p);
+        KeyT *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    *outKeys = kin;
+    if (outVals)
+        *outVals = vin;
+    return 1 + passes;
+}
+
+} // namespace sbradix

@@ -1,0 +1,68 @@
+// Per-candidate arithmetic of SolidBoolean::isPointInMesh
+// (src/solidboolean.cpp:66-87), bit-exact: segment/plane intersection
+// (Vector3::intersectSegmentAndPlane, src/vector3.h:264-280), three edge normals
+// (Vector3::normal, src/vector3.h:155-176), two sign tests, PositionKey
+// quantisation (src/positionkey.cpp:32-37).
+#pragma once
+#include "sb_fp64.cuh"
+
+#define SB_DBL_EPSILON 2.2204460492503131e-16
+#define SB_DBL_MAX 1.7976931348623157e+308
+
+// Vector3::normal; the zero vector when |cross| <= DBL_EPSILON (Double::isZero).
+__device__ __forceinline__ d3 tri_normal(const d3 &a, const d3 &b, const d3 &c)
+{
+    d3 ba = d3sub(b, a);
+    d3 ca = d3sub(c, a);
+    d3 cr = d3cross(ba, ca);
+    double len2 = xadd(xadd(xmul(cr.x, cr.x), xmul(cr.y, cr.y)), xmul(cr.z, cr.z));
+    double len = xsqrt(len2);
+    if (fabs(len) <= SB_DBL_EPSILON)
+        return {0.0, 0.0, 0.0};
+    return {xdiv(cr.x, len), xdiv(cr.y, len), xdiv(cr.z, len)};
+}
+
+// testEnd = testPosition + testAxis for axis k of g_testAxisList
+// (src/solidboolean.cpp:31-35, :53)
+__device__ __forceinline__ d3 ray_end(const d3 &p, int axis)
+{
+    return {xadd(p.x, axis == 0 ? SB_DBL_MAX : SB_DBL_EPSILON),
+            xadd(p.y, axis == 1 ? SB_DBL_MAX : SB_DBL_EPSILON),
+            xadd(p.z, axis == 2 ? SB_DBL_MAX : SB_DBL_EPSILON)};
+}
+
+// true when the reference would insert PositionKey(hit) for this candidate
+__device__ __forceinline__ bool ray_tri_hit(const d3 &p, const d3 &end,
+    const d3 &t0, const d3 &t1, const d3 &t2, const d3 &nrm, d3 &hit)
+{
+    d3 u = d3sub(end, p);
+    d3 w = d3sub(p, t0);
+    double d = d3dot(nrm, u);
+    d3 neg = {-nrm.x, -nrm.y, -nrm.z};
+    double n = d3dot(neg, w);
+    if (fabs(d) <= SB_DBL_EPSILON)
+        return false;
+    double s = xdiv(n, d);
+    // s < 0 || s > 1 || isnan(s) || isinf(s)  (src/vector3.h:274)
+    if (!(s >= 0.0 && s <= 1.0))
+        return false;
+    hit = {xadd(p.x, xmul(s, u.x)), xadd(p.y, xmul(s, u.y)), xadd(p.z, xmul(s, u.z))};
+    d3 n0 = tri_normal(hit, t0, t1);
+    d3 n1 = tri_normal(hit, t1, t2);
+    d3 n2 = tri_normal(hit, t2, t0);
+    return d3dot(n0, n1) > 0 && d3dot(n0, n2) > 0;
+}
+
+// (long)(x * 100000) with x86-64 cvttsd2si semantics (NaN / out of range ->
+// LLONG_MIN, the "integer indefinite" value).
+__device__ __forceinline__ long long position_key(double x)
+{
+    double v = xmul(x, 100000.0);
+#ifdef SB_HOST_SIM
+    return (long long)(long)v;
+#else
+    if (!(v > -9223372036854775808.0 && v < 9223372036854775808.0))
+        return (long long)0x8000000000000000ull;
+    return __double2ll_rz(v);
+#endif
+}

@@ -1,0 +1,336 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the oracle and
+the committed reference fixtures.  Bit-exact for pairs, codes, flags; segments
+are compared bit-for-bit too (north_star allows 1e-12 relative, we get 0)."""
+import numpy as np
+import pytest
+
+import solidboolean_b200 as sb
+from conftest import CASES, load_case, load_synthetic, synthetic_specs
+from solidboolean_b200 import meshgen
+
+pytestmark = pytest.mark.gpu
+
+SEG_RTOL = 1e-12  # north_star tolerance for segment endpoints
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sb.Context(0)
+    yield c
+    c.close()
+
+
+def assert_segments(seg, ref):
+    assert seg.shape == ref.shape
+    if seg.tobytes() == ref.tobytes():
+        return
+    scale = np.maximum(np.abs(ref), 1e-300)
+    assert np.all(np.abs(seg - ref) <= SEG_RTOL * scale), "segment endpoints differ beyond 1e-12 relative"
+    raise AssertionError("segments within tolerance but not bit-identical (expected bit-exact)")
+
+
+def check_pair(ctx, a, b, out, oracle=None):
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x = ma.intersect(mb)
+    ab, code = x.candidates()
+    assert np.array_equal(ab, out["pairs"]), "candidate-pair set differs"
+    assert np.array_equal(code & 1, out["ret"].astype(np.uint8))
+    assert np.array_equal((code >> 1) & 1, out["coplanar"].astype(np.uint8))
+    hab, seg = x.hits()
+    assert np.array_equal(hab, out["pairs"][out["hit"].astype(bool)])
+    assert_segments(seg, out["seg_hits"])
+    fa, fb = x.face_flags()
+    ea = np.zeros(len(a[1]), np.uint8)
+    eb = np.zeros(len(b[1]), np.uint8)
+    ea[hab[:, 0]] = 1
+    eb[hab[:, 1]] = 1
+    assert np.array_equal(fa, ea) and np.array_equal(fb, eb)
+    ia, pa = ma.classify_faces_against(mb)
+    ib, pb = mb.classify_faces_against(ma)
+    assert np.array_equal(pa, out["per_axis_a"]) and np.array_equal(ia, out["inside_a"])
+    assert np.array_equal(pb, out["per_axis_b"]) and np.array_equal(ib, out["inside_b"])
+    if oracle is not None:
+        assert ma.normals().tobytes() == oracle.normals(*a).tobytes()
+        assert mb.triangle_boxes().tobytes() == oracle.tri_boxes(*b).tobytes()
+    x.close(); ma.close(); mb.close()
+
+
+def test_predicate_known_answers(ctx, golden_kat):
+    ret, cop, seg = ctx.tri_tri_batch(golden_kat["tris"])
+    assert np.array_equal(ret, golden_kat["ret"])
+    assert np.array_equal(cop, golden_kat["coplanar"])
+    assert seg.tobytes() == golden_kat["seg"].tobytes()
+
+
+def test_predicate_random_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(11)
+    tris = np.concatenate([
+        rng.uniform(-1, 1, (300000, 18)),
+        rng.integers(-2, 3, (300000, 18)).astype(np.float64),
+        rng.uniform(-1, 1, (100000, 18)).astype(np.float32).astype(np.float64),
+        rng.uniform(-1, 1, (50000, 18)) * 1e-150,
+        rng.uniform(-1, 1, (50000, 18)) * 1e150,
+    ])
+    r0, c0, s0 = oracle.tri_tri_batch(tris)
+    r1, c1, s1 = ctx.tri_tri_batch(tris)
+    assert np.array_equal(r0, r1) and np.array_equal(c0, c1)
+    assert s0.tobytes() == s1.tobytes()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_bundled_cases(ctx, oracle, golden_cases, case):
+    a, b, out = load_case(golden_cases, case)
+    check_pair(ctx, a, b, out, oracle)
+
+
+@pytest.mark.parametrize("name", sorted(synthetic_specs()))
+def test_synthetic_fixtures(ctx, oracle, golden_synthetic, name):
+    a, b, out = load_synthetic(golden_synthetic, name)
+    check_pair(ctx, a, b, out, oracle)
+
+
+def check_bvh(mesh, boxes):
+    """Every cluster reachable exactly once; every child box encloses its subtree."""
+    t = mesh.bvh()
+    K, M = t["cluster_size"], t["num_clusters"]
+    n = mesh.num_triangles
+    assert M == (n + K - 1) // K
+    leaves = t["leaves"]
+    order = mesh.order()
+    assert sorted(order.tolist()) == list(range(n))
+    assert np.array_equal(leaves["ref"][:n], order.astype(np.int32))
+    assert np.all(leaves["ref"][n:] == -1)
+    lb = boxes[order]
+    assert np.all(leaves["lo"][:n] <= lb[:, :3]) and np.all(leaves["hi"][:n] >= lb[:, 3:])
+    # tight: conservative rounding moves a bound by at most one float ulp
+    assert np.all(leaves["lo"][:n].astype(np.float64) >= lb[:, :3] - np.abs(lb[:, :3]) * 2.0 ** -22 - 1e-37)
+    clo = np.full((M, 3), np.inf)
+    chi = np.full((M, 3), -np.inf)
+    for c in range(M):
+        s = slice(c * K, min((c + 1) * K, n))
+        clo[c] = leaves["lo"][s].min(axis=0)
+        chi[c] = leaves["hi"][s].max(axis=0)
+    if M == 1:
+        assert t["root"] == -1
+        return
+    nodes = t["nodes"]
+    seen = np.zeros(M, np.int32)
+    visited = np.zeros(M - 1, np.int32)
+
+    def walk(ref):
+        # returns (lo, hi) of the subtree; iterative to survive deep trees
+        stack = [(ref, False)]
+        res = {}
+        while stack:
+            r, done = stack.pop()
+            if r < 0:
+                c = ~r
+                seen[c] += 1
+                res[r] = (clo[c], chi[c])
+                continue
+            if not done:
+                visited[r] += 1
+                stack.append((r, True))
+                stack.append((int(nodes["ref"][2 * r]), False))
+                stack.append((int(nodes["ref"][2 * r + 1]), False))
+            else:
+                lo = np.full(3, np.inf)
+                hi = np.full(3, -np.inf)
+                for side in (0, 1):
+                    cr = int(nodes["ref"][2 * r + side])
+                    slo, shi = res[cr]
+                    rec = nodes[2 * r + side]
+                    assert np.all(rec["lo"] <= slo) and np.all(rec["hi"] >= shi)
+                    assert np.array_equal(rec["lo"], slo.astype(np.float32)) and np.array_equal(rec["hi"], shi.astype(np.float32))
+                    lo = np.minimum(lo, slo)
+                    hi = np.maximum(hi, shi)
+                res[r] = (lo, hi)
+        return res[ref]
+
+    walk(int(t["root"]))
+    assert np.all(seen == 1), "cluster not reached exactly once"
+    assert np.all(visited == 1), "internal node not reached exactly once"
+
+
+@pytest.mark.parametrize("gen", ["ico3", "torus", "slab", "tiny"])
+def test_lbvh_invariants(ctx, oracle, gen):
+    mesh = {"ico3": lambda: meshgen.icosphere(3), "torus": lambda: meshgen.torus(40, 24),
+            "slab": lambda: meshgen.slab(9), "tiny": lambda: meshgen.icosphere(0)}[gen]()
+    m = ctx.mesh(*mesh)
+    check_bvh(m, oracle.tri_boxes(*mesh))
+    b = m.bounds()
+    assert np.array_equal(b[:3], mesh[0].min(axis=0)) and np.array_equal(b[3:], mesh[0].max(axis=0))
+    m.close()
+
+
+def test_duplicate_morton_codes_and_degenerate_extent(ctx, oracle):
+    """All triangles in one plane / many identical centroids: index tie-break path."""
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float64)
+    tri = np.tile(np.array([[0, 1, 2]], np.uint32), (300, 1))
+    m = ctx.mesh(xyz, tri)
+    check_bvh(m, oracle.tri_boxes(xyz, tri))
+    x = m.intersect(m)
+    assert x.num_candidates == 300 * 300
+    ab, code = x.candidates()
+    assert np.array_equal(ab, oracle.candidate_pairs((xyz, tri), (xyz, tri)))
+    assert np.all((code >> 1) & 1 == 1)  # identical triangles are coplanar
+    assert x.num_hits == 0
+    x.close(); m.close()
+
+
+def test_small_and_ragged_inputs(ctx, oracle):
+    for k, (nu, nv) in ((0, (3, 3)), (1, (4, 3)), (2, (5, 7))):
+        a = meshgen.icosphere(k)
+        b = meshgen.torus(nu, nv, R=0.8, r=0.4, center=(0.1, 0.05, 0.02))
+        ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+        x = ma.intersect(mb)
+        ab, code = x.candidates()
+        ref = oracle.candidate_pairs(a, b)
+        assert np.array_equal(ab, ref)
+        ret, cop, hit, seg = oracle.predicate_pairs(a, b, ref)
+        assert np.array_equal(code, (ret | (cop << 1)).astype(np.uint8))
+        hab, hseg = x.hits()
+        assert np.array_equal(hab, ref[hit.astype(bool)])
+        assert hseg.tobytes() == seg[hit.astype(bool)].tobytes()
+        ia, pa = ma.classify_faces_against(mb)
+        oi, op, _ = oracle.classify(b, oracle.centroids(*a))
+        assert np.array_equal(ia, oi) and np.array_equal(pa, op)
+        x.close(); ma.close(); mb.close()
+
+
+def test_single_triangle_and_disjoint(ctx, oracle):
+    one = (np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float64), np.array([[0, 1, 2]], np.uint32))
+    sph = meshgen.icosphere(2, radius=0.5, center=(0.2, 0.2, 0.0))
+    far = meshgen.icosphere(2, center=(10, 10, 10))
+    m1, ms, mf = ctx.mesh(*one), ctx.mesh(*sph), ctx.mesh(*far)
+    x = m1.intersect(ms)
+    assert np.array_equal(x.candidates()[0], oracle.candidate_pairs(one, sph))
+    x.close()
+    x = ms.intersect(m1)
+    assert np.array_equal(x.candidates()[0], oracle.candidate_pairs(sph, one))
+    x.close()
+    x = ms.intersect(mf)
+    assert x.num_candidates == 0 and x.num_hits == 0
+    assert x.candidates()[0].shape == (0, 2) and x.hits()[1].shape == (0, 6)
+    fa, fb = x.face_flags()
+    assert not fa.any() and not fb.any()
+    x.close()
+    ins, _ = ms.classify_faces_against(mf)
+    assert not ins.any()
+    for m in (m1, ms, mf):
+        m.close()
+
+
+def test_invalid_arguments(ctx):
+    xyz = np.zeros((3, 3))
+    with pytest.raises(sb.SolidBooleanError, match="out of range"):
+        ctx.mesh(xyz, np.array([[0, 1, 3]], np.uint32))
+    m = ctx.mesh(*meshgen.icosphere(1))
+    with pytest.raises(sb.SolidBooleanError, match="multiple of 32"):
+        m.intersect(m, begin=5, end=40)
+    m.close()
+
+
+def test_explicit_points_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(5)
+    for mesh in (meshgen.icosphere(4), meshgen.torus(64, 32, center=(0.013, 0.007, 0.011)),
+                 meshgen.slab(16, 1.0, 0.3, tilt=0.2)):
+        pts = np.concatenate([rng.uniform(-1.6, 1.6, (20000, 3)),
+                              mesh[0][rng.integers(0, len(mesh[0]), 2000)],          # exactly on vertices
+                              oracle.centroids(*mesh)[:2000]])                       # exactly on faces
+        m = ctx.mesh(*mesh)
+        ins, per = m.classify(pts)
+        oi, op, _ = oracle.classify(mesh, pts)
+        assert np.array_equal(per, op) and np.array_equal(ins, oi)
+        m.close()
+
+
+def test_many_layers_hit_list_overflow_path(ctx, oracle):
+    """A ray crossing > 16 distinct surface points takes the exact slow path."""
+    parts_v, parts_t = [], []
+    off = 0
+    for i in range(24):  # 24 nested thin slabs stacked along x -> 48 crossings for +x rays
+        v, t = meshgen.slab(2, 1.0, 0.01, center=(0, 0, 0))
+        rot = np.array([[0, 0, 1], [0, 1, 0], [-1, 0, 0]], np.float64)  # slab normal along x
+        v = v @ rot.T + np.array([0.05 * i, 0, 0])
+        parts_v.append(v); parts_t.append(t + off); off += len(v)
+    mesh = (np.concatenate(parts_v), np.concatenate(parts_t).astype(np.uint32))
+    rng = np.random.default_rng(9)
+    pts = np.concatenate([rng.uniform(-0.4, 0.4, (500, 3)) * [0, 1, 1] + [-1.0, 0, 0],
+                          rng.uniform(-0.6, 1.5, (500, 3))])
+    m = ctx.mesh(*mesh)
+    ins, per = m.classify(pts)
+    oi, op, _ = oracle.classify(mesh, pts)
+    assert np.array_equal(per, op) and np.array_equal(ins, oi)
+    m.close()
+
+
+def test_sharded_ranges_cover_whole(ctx):
+    """A's Morton range split in R shards == the unsharded result."""
+    a, b = meshgen.icosphere(5), meshgen.torus(96, 48, center=(0.013, 0.007, 0.011))
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    whole = ma.intersect(mb)
+    wab, wcode = whole.candidates()
+    whab, wseg = whole.hits()
+    n = ma.num_triangles
+    for R in (2, 3, 8):
+        cuts = [((n * r // R) // 32) * 32 for r in range(R)] + [n]
+        abs_, codes, habs, segs = [], [], [], []
+        for r in range(R):
+            x = ma.intersect(mb, begin=cuts[r], end=cuts[r + 1])
+            ab, code = x.candidates(); hab, seg = x.hits()
+            abs_.append(ab); codes.append(code); habs.append(hab); segs.append(seg)
+            x.close()
+        ab = np.concatenate(abs_); code = np.concatenate(codes)
+        o = np.lexsort((ab[:, 1], ab[:, 0]))
+        assert np.array_equal(ab[o], wab) and np.array_equal(code[o], wcode)
+        hab = np.concatenate(habs); seg = np.concatenate(segs)
+        o = np.lexsort((hab[:, 1], hab[:, 0]))
+        assert np.array_equal(hab[o], whab) and seg[o].tobytes() == wseg.tobytes()
+    whole.close(); ma.close(); mb.close()
+
+
+def test_no_sort_flag_same_set(ctx):
+    a, b = meshgen.icosphere(4), meshgen.icosphere(4, center=(0.71, 0.13, 0.07))
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    s = ma.intersect(mb)
+    u = ma.intersect(mb, flags=sb.ISECT_NO_SORT)
+    sab, scode = s.candidates(); uab, ucode = u.candidates()
+    o = np.lexsort((uab[:, 1], uab[:, 0]))
+    assert np.array_equal(uab[o], sab) and np.array_equal(ucode[o], scode)
+    shab, sseg = s.hits(); uhab, useg = u.hits()
+    o = np.lexsort((uhab[:, 1], uhab[:, 0]))
+    assert np.array_equal(uhab[o], shab) and useg[o].tobytes() == sseg.tobytes()
+    s.close(); u.close(); ma.close(); mb.close()
+
+
+def test_rebuild_is_idempotent(ctx):
+    a, b = meshgen.icosphere(4), meshgen.torus(48, 24, center=(0.013, 0.007, 0.011))
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x0 = ma.intersect(mb); r0 = (x0.candidates(), x0.hits()); x0.close()
+    o0 = ma.order()
+    ma.build(); mb.build()
+    assert np.array_equal(ma.order(), o0)
+    x1 = ma.intersect(mb); r1 = (x1.candidates(), x1.hits()); x1.close()
+    for u, v in zip(r0[0] + r0[1], r1[0] + r1[1]):
+        assert u.tobytes() == v.tobytes()
+    ma.close(); mb.close()
+
+
+def test_config_c2_vs_oracle(ctx, oracle):
+    """BASELINE config 2: two offset icospheres, 81,920 + 81,920 triangles."""
+    a, b = meshgen.config_c2()
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x = ma.intersect(mb)
+    ab, code = x.candidates()
+    ref = oracle.candidate_pairs(a, b)
+    assert np.array_equal(ab, ref)
+    ret, cop, hit, seg = oracle.predicate_pairs(a, b, ref)
+    assert np.array_equal(code, (ret | (cop << 1)).astype(np.uint8))
+    hab, hseg = x.hits()
+    assert np.array_equal(hab, ref[hit.astype(bool)]) and hseg.tobytes() == seg[hit.astype(bool)].tobytes()
+    assert (x.num_candidates, x.num_hits) == (7754, 1386)  # BASELINE.md probe table
+    ia, pa = ma.classify_faces_against(mb)
+    oi, op, _ = oracle.classify(b, oracle.centroids(*a))
+    assert np.array_equal(pa, op) and np.array_equal(ia, oi)
+    x.close(); ma.close(); mb.close()
