@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""Benchmark of the solidboolean intersection front end on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
+
+One "step" = one pass of the hot path over the workload:
+build(A) + build(B) + broad phase + predicate + hit compaction + inside/outside
+classification of every face of A against B and of B against A.
+
+* value  : intersecting tri-pairs/s with the geometry already resident in HBM
+           (per-step CUDA-event time on the library's stream, L2 flushed between
+           steps, max over ranks).
+* e2e    : the same metric through the host-buffer C ABI (sb_mesh_create from
+           pinned host memory -> H2D inside, results read back to the host).
+* roofline: the dominant kernel group (classification) against the measured HBM
+           copy bandwidth, using the algorithmic-bytes formula of SURVEY 8d.
+* cpu_baseline: the reference's own CPU implementation (oracle/_ref, or the C
+           port when it is absent) on this box's host cores, bounded sample.
+
+`--impl reference` times only the CPU reference on the same config and metric.
+N > 1 (torchrun): mesh A's Morton range and both classification query sets are
+sharded over the ranks, mesh B's (and A's) LBVH replicated; hit lists are
+all-gathered and the face flags summed over NCCL.  Total work is fixed -> strong
+scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "intersecting_tri_pairs_per_s"
+UNIT = "pairs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(name):
+    from solidboolean_b200 import meshgen
+    a, b = {"c2": meshgen.config_c2, "c3": meshgen.config_c3, "c4": meshgen.config_c4}[name]()
+    desc = {
+        "c2": "two offset icospheres k=6, 81,920 + 81,920 triangles (BASELINE configs[1])",
+        "c3": "icosphere k=8 (1,310,720 tris) vs torus 1024x512 (1,048,576 tris), BASELINE configs[2] = the 1M+1M config the metric is quoted on",
+        "c4": "near-coincident icospheres k=7, 327,680 x2 triangles, ~2.3M candidate pairs (BASELINE configs[3] proxy)",
+    }[name]
+    return a, b, desc
+
+
+# ----------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for i, n in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# CPU reference (oracle/_ref = the unmodified reference; else the C port)
+
+def cpu_reference_step(a, b, sample_points, threads):
+    """One bounded pass of the reference front end on the host.  Returns
+    (seconds scaled to the full workload, H, detail dict)."""
+    from oracle import Oracle, Ref
+    nA, nB = len(a[1]), len(b[1])
+    Q = nA + nB
+    rng = np.random.default_rng(0)
+    if Ref.available():
+        R = Ref.get()
+        out = [None, None]
+
+        def prep(i, m):
+            out[i] = R.mesh(*m)
+        t0 = time.perf_counter()
+        ts = [threading.Thread(target=prep, args=(i, m)) for i, m in enumerate((a, b))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        t_prepare = time.perf_counter() - t0          # two meshes on two cores (ctypes drops the GIL)
+        ma, mb = out
+        op = R.op(ma, mb)
+        t0 = time.perf_counter()
+        pairs = op.search()
+        t_search = time.perf_counter() - t0
+        ret, cop, hit, seg, ms_pred = op.predicate(pairs)
+        t_pred = ms_pred / 1e3
+        H = int(hit.sum())
+        # classification on a bounded sample of the face centroids, spread over host threads
+        ca, cb = ma.centroids(), mb.centroids()
+        sa = rng.choice(nA, size=min(nA, sample_points * nA // Q), replace=False)
+        sb_ = rng.choice(nB, size=min(nB, sample_points * nB // Q), replace=False)
+        jobs = [(1, chunk) for chunk in np.array_split(ca[sa], threads)] + \
+               [(0, chunk) for chunk in np.array_split(cb[sb_], threads)]
+        t0 = time.perf_counter()
+        ws = [threading.Thread(target=lambda j=j: op.classify(j[0], j[1])) for j in jobs if len(j[1])]
+        for i in range(0, len(ws), threads):
+            [w.start() for w in ws[i:i + threads]]
+            [w.join() for w in ws[i:i + threads]]
+        t_cls_sample = time.perf_counter() - t0
+        n_sample = len(sa) + len(sb_)
+        kind = "reference"
+        op.close(); ma.close(); mb.close()
+    else:
+        O = Oracle.get()
+        t0 = time.perf_counter()
+        O.tri_boxes(*a); O.tri_boxes(*b); O.normals(*a); O.normals(*b)
+        t_prepare = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        pairs = O.candidate_pairs(a, b)
+        t_search = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ret, cop, hit, seg = O.predicate_pairs(a, b, pairs)
+        t_pred = time.perf_counter() - t0
+        H = int(hit.sum())
+        ca, cb = O.centroids(*a), O.centroids(*b)
+        sa = rng.choice(nA, size=min(nA, sample_points * nA // Q), replace=False)
+        sb_ = rng.choice(nB, size=min(nB, sample_points * nB // Q), replace=False)
+        t0 = time.perf_counter()
+        O.classify(b, ca[sa]); O.classify(a, cb[sb_])
+        t_cls_sample = time.perf_counter() - t0
+        n_sample = len(sa) + len(sb_)
+        kind = "port"
+    t_cls = t_cls_sample * (Q / max(n_sample, 1))
+    total = t_prepare + t_search + t_pred + t_cls
+    detail = dict(kind=kind, prepare_s=t_prepare, search_s=t_search, predicate_s=t_pred,
+                  classify_sample_s=t_cls_sample, classify_scaled_s=t_cls, sample_points=n_sample, H=H,
+                  P=int(len(pairs)))
+    return total, H, detail
+
+
+def host_threads():
+    try:
+        return max(1, min(len(os.sched_getaffinity(0)), 32))
+    except AttributeError:
+        return max(1, min(os.cpu_count() or 1, 32))
+
+
+def sample_description(detail, threads):
+    return ("full prepare() x2 (2 threads) + full broad phase + full predicate loop; isPointInMesh on %d of the "
+            "face centroids x 3 axes over %d threads, scaled to all faces" % (detail["sample_points"], threads))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    a, b, desc = workload(args.config)
+    threads = host_threads()
+    sample = 65536
+    times, H, detail = [], 0, None
+    for i in range(args.warmup + args.steps):
+        t, H, detail = cpu_reference_step(a, b, sample, threads)
+        if i >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    val = H / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "name": args.config, "tris_a": int(len(a[1])), "tris_b": int(len(b[1]))},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": detail["kind"],
+                         "sample": sample_description(detail, threads)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "front_end_ms": sec * 1e3, "detail": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in detail.items()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+
+def shard_bounds(n, world):
+    cuts = [((n * r // world) // 32) * 32 for r in range(world)] + [n]
+    return cuts
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import solidboolean_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(sb.LIB_PATH):
+        if local == 0:
+            from solidboolean_b200.build import build
+            build()
+        if world > 1:
+            dist.barrier()
+
+    a, b, desc = workload(args.config)
+    nA, nB = len(a[1]), len(b[1])
+    nVA, nVB = len(a[0]), len(b[0])
+    ctx = sb.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    # pinned host copies of the inputs (what a caller of the C ABI hands over)
+    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (a[0], a[1].view(np.int32), b[0], b[1].view(np.int32))]
+
+    cutsA, cutsB = shard_bounds(nA, world), shard_bounds(nB, world)
+    a0, a1 = cutsA[rank], cutsA[rank + 1]
+    b0, b1 = cutsB[rank], cutsB[rank + 1]
+
+    dev = torch.device("cuda", local)
+    flagsA = torch.zeros(nA, dtype=torch.uint8, device=dev)
+    flagsB = torch.zeros(nB, dtype=torch.uint8, device=dev)
+    l2_flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    counts_all = torch.zeros((world, 2), dtype=torch.int64, device=dev)
+
+    def gather_results(x):
+        """NCCL exchange of the shard results. Returns global (P, H)."""
+        mine = torch.tensor([[x.num_candidates, x.num_hits]], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts_all, mine)
+        cnt = counts_all.cpu()
+        hmax = int(cnt[:, 1].max())
+        if hmax:
+            ptrs = x.device_ptrs()
+            pad_ab = torch.zeros((hmax, 2), dtype=torch.int32, device=dev)
+            pad_seg = torch.zeros((hmax, 6), dtype=torch.float64, device=dev)
+            if x.num_hits:
+                pad_ab[:x.num_hits] = _as_tensor(torch, ptrs["hit_ab"], (x.num_hits, 2), torch.int32, dev)
+                pad_seg[:x.num_hits] = _as_tensor(torch, ptrs["hit_seg"], (x.num_hits, 6), torch.float64, dev)
+            all_ab = torch.empty((world * hmax, 2), dtype=torch.int32, device=dev)
+            all_seg = torch.empty((world * hmax, 6), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(all_ab, pad_ab)
+            dist.all_gather_into_tensor(all_seg, pad_seg)
+        # every face is classified by exactly one rank: summing the byte masks is the gather
+        dist.all_reduce(flagsA)
+        dist.all_reduce(flagsB)
+        return int(cnt[:, 0].sum()), int(cnt[:, 1].sum())
+
+    # ---------------- resident loop: `value` ----------------
+    ma = ctx.mesh(a[0], a[1], build=False)
+    mb = ctx.mesh(b[0], b[1], build=False)
+    ctx.synchronize()
+    ctx.enable_timing(True)
+
+    rays_cands = [0, 0]
+
+    def resident_step():
+        with torch.cuda.stream(ext):
+            if world > 1:
+                flagsA.zero_(); flagsB.zero_()
+            ma.build(); mb.build()
+            x = ma.intersect(mb, begin=a0, end=a1)
+            ma.classify_faces_device(mb, flagsA.data_ptr(), a0, a1)
+            r1 = ctx.classify_stats()
+            mb.classify_faces_device(ma, flagsB.data_ptr(), b0, b1)
+            r2 = ctx.classify_stats()
+            rays_cands[0], rays_cands[1] = r1[0] + r2[0], r1[1] + r2[1]
+            if world > 1:
+                P, H = gather_results(x)
+            else:
+                P, H = x.num_candidates, x.num_hits
+            x.close()
+        return P, H
+
+    def timed_loop(step_fn, steps, warmup, device_timed):
+        for _ in range(warmup):
+            res = step_fn()
+        torch.cuda.synchronize()
+        ctx.reset_timing()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = 0.0
+        sampler = ClockSampler(local)
+        sampler.start()
+        for _ in range(steps):
+            with torch.cuda.stream(ext):
+                l2_flush.zero_()          # evict L2 between timed iterations (untimed)
+            torch.cuda.synchronize()
+            if device_timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
+                res = step_fn()
+                e1.record(ext)
+                e1.synchronize()
+                total_ms += e0.elapsed_time(e1)
+            else:
+                t0 = time.perf_counter()
+                res = step_fn()
+                torch.cuda.synchronize()
+                total_ms += (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, res, clocks
+
+    ms_step, (P, H), clocks = timed_loop(resident_step, args.steps, args.warmup, True)
+    stage_ms, launches = ctx.timing()
+    stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+    launches_per_step = launches / args.steps
+    insideA, insideB = int(flagsA.sum().item()), int(flagsB.sum().item())
+    rays, cands = rays_cands
+    if world > 1:
+        rc = torch.tensor([rays, cands], dtype=torch.int64, device=dev)
+        dist.all_reduce(rc)
+        rays_total, cands_total = int(rc[0]), int(rc[1])
+    else:
+        rays_total, cands_total = rays, cands
+
+    # ---------------- host-buffer loop: `e2e` ----------------
+    out_in_a = np.zeros(nA, np.uint8)
+    out_in_b = np.zeros(nB, np.uint8)
+
+    def e2e_step():
+        with torch.cuda.stream(ext):
+            xa = sb.Mesh.from_pointers(ctx, pin[0].data_ptr(), nVA, pin[1].data_ptr(), nA, build=True, keep=pin)
+            xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=True, keep=pin)
+            x = xa.intersect(xb, begin=a0, end=a1)
+            if world > 1:
+                flagsA.zero_(); flagsB.zero_()
+                xa.classify_faces_device(xb, flagsA.data_ptr(), a0, a1)
+                xb.classify_faces_device(xa, flagsB.data_ptr(), b0, b1)
+                Pg, Hg = gather_results(x)
+                if rank == 0:
+                    out_in_a[:] = flagsA.cpu().numpy()
+                    out_in_b[:] = flagsB.cpu().numpy()
+                    x.hits()
+            else:
+                hab, hseg = x.hits()
+                ia, _ = xa.classify_faces_against(xb)
+                ib, _ = xb.classify_faces_against(xa)
+                Pg, Hg = x.num_candidates, x.num_hits
+            x.close(); xa.close(); xb.close()
+        return Pg, Hg
+
+    ctx.enable_timing(False)
+    e2e_ms, (P2, H2), _ = timed_loop(e2e_step, max(3, args.steps // 2), 2, False)
+    h2d = 24 * (nVA + nVB) + 12 * (nA + nB)
+    d2h = (nA + nB) * (4 if world == 1 else 1) + 56 * H + 64
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        # classification bytes = 25 Q + 104 nTarget + 108 C, both launches of a step
+        cls_bytes = 25 * (nA + nB) + 104 * (nA + nB) + 108 * cands_total
+        cls_ms = stage_ms["classify"]
+        achieved = cls_bytes / (cls_ms * 1e-3) / 1e9 if cls_ms > 0 else 0.0
+        build_bytes = 24 * (nVA + nVB) + 296 * (nA + nB)
+        broad_bytes = 48 * nA + 104 * nB + 8 * P
+        narrow_bytes = 8 * P + 24 * (nVA + nVB) + 12 * (nA + nB) + 56 * H
+
+        def gbs(bytes_, ms):
+            return round(bytes_ / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
+        line = {
+            "metric": METRIC, "value": H / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "name": args.config, "tris_a": nA, "tris_b": nB,
+                       "l2": "512 MiB buffer written between timed steps (L2 flush)",
+                       "parallelism": "A-range + query shards x%d, LBVHs replicated" % world},
+            "front_end_ms": ms_step,
+            "candidate_pairs": P, "intersecting_pairs": H, "inside_a": insideA, "inside_b": insideB,
+            "candidate_pairs_per_s": P / (ms_step * 1e-3),
+            "triangles_per_s": (nA + nB) / (ms_step * 1e-3),
+            "rays_per_s": rays_total / (stage_ms["classify"] * 1e-3) if stage_ms["classify"] > 0 else None,
+            "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+            "stage_gbs_algorithmic": {"build": gbs(build_bytes, stage_ms["build"]), "broad": gbs(broad_bytes, stage_ms["broad"]),
+                                      "narrow": gbs(narrow_bytes, stage_ms["narrow"]), "classify": gbs(cls_bytes, cls_ms)},
+            "roofline": {"bound": "hbm", "kernel": "classify_kernel (2 launches/step)", "achieved": round(achieved, 1),
+                         "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": cls_bytes,
+                         "kernel_ms_per_step": round(cls_ms, 4)},
+            "e2e": {"value": H2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            sec, Href, detail = cpu_reference_step(a, b, 32768, threads)
+            line["cpu_baseline"] = {"value": Href / sec, "unit": UNIT, "cores": threads, "kind": detail["kind"],
+                                    "sample": sample_description(detail, threads), "front_end_ms": sec * 1e3,
+                                    "H": Href, "P": detail["P"]}
+        print(json.dumps(line), flush=True)
+    ma.close(); mb.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _as_tensor(torch, ptr, shape, dtype, dev):
+    """Zero-copy torch view of a device pointer owned by the library."""
+    n = int(np.prod(shape))
+    itemsize = torch.empty((), dtype=dtype).element_size()
+
+    class _Holder:
+        pass
+    h = _Holder()
+    typestr = {torch.int32: "<i4", torch.float64: "<f8", torch.uint8: "|u1", torch.int64: "<i8"}[dtype]
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2,
+                                  "strides": None}
+    assert n * itemsize >= 0
+    return torch.as_tensor(h, device=dev)
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

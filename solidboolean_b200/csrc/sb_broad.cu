@@ -40,13 +40,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
     const BoxF myF = {me.lox, me.loy, me.loz, me.hix, me.hiy, me.hiz};
     const BoxD myD = load_boxd(sboxA + 3 * (size_t)j);
     const unsigned long long myA = (unsigned long long)(uint32_t)me.ref;
-    BoxF G = myF; // padding lanes hold an empty box and never match
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        BoxF o = shfl_xor_box(G, off);
-        merge_f(G, o);
-    }
-
     sbtrav::BvhView bvh = {nodesB, leafB, __ldg(rootB)};
     int ocount = 0;
     auto flush = [&]() {
@@ -61,22 +54,40 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
         __syncwarp();
     };
 
-    sbtrav::group_traverse<K>(bvh, G, s.trav, lane, [&](const Rec32 &r, uint32_t posB) {
-        bool pass = overlap_f(myF, r.lox, r.loy, r.loz, r.hix, r.hiy, r.hiz);
-        if (pass) {
-            BoxD bd = load_boxd(sboxB + 3 * (size_t)posB);
-            // boxes[a].intersectWith(secondBoxes[b]) -- the reference's leaf test
-            pass = overlap_d(myD, bd);
-        }
-        uint32_t m = __ballot_sync(SB_FULL, pass);
-        if (m) {
-            if (pass)
-                s.out[ocount + __popc(m & lt)] = ((myA << bitsB) | (unsigned long long)(uint32_t)r.ref) << 2;
-            ocount += __popc(m);
-            __syncwarp();
-            if (ocount >= 32)
-                flush();
-        }
+    // surface-area measure of a query box (0 for an empty one); the pad keeps
+    // flat boxes from measuring zero
+    BoxF all = myF; // padding lanes hold an empty box and never match
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        BoxF o = shfl_xor_box(all, off);
+        merge_f(all, o);
+    }
+    const float pad = 0.015625f * fmaxf(fmaxf(all.hix - all.lox, all.hiy - all.loy), all.hiz - all.loz);
+    auto measure = [pad](const BoxF &b) {
+        float ex = b.hix - b.lox, ey = b.hiy - b.loy, ez = b.hiz - b.loz;
+        if (ex < 0.0f || ey < 0.0f || ez < 0.0f)
+            return 0.0f;
+        ex += pad; ey += pad; ez += pad;
+        return ex * ey + ey * ez + ez * ex;
+    };
+    sbtrav::split_and_run(myF, lane, s.trav.segs, measure, [&](const BoxF &G, bool inSeg) {
+        sbtrav::group_traverse<K>(bvh, G, s.trav, lane, [&](const Rec32 &r, uint32_t posB) {
+            bool pass = inSeg && overlap_f(myF, r.lox, r.loy, r.loz, r.hix, r.hiy, r.hiz);
+            if (pass) {
+                BoxD bd = load_boxd(sboxB + 3 * (size_t)posB);
+                // boxes[a].intersectWith(secondBoxes[b]) -- the reference's leaf test
+                pass = overlap_d(myD, bd);
+            }
+            uint32_t m = __ballot_sync(SB_FULL, pass);
+            if (m) {
+                if (pass)
+                    s.out[ocount + __popc(m & lt)] = ((myA << bitsB) | (unsigned long long)(uint32_t)r.ref) << 2;
+                ocount += __popc(m);
+                __syncwarp();
+                if (ocount >= 32)
+                    flush();
+            }
+        });
     });
     if (ocount > 0)
         flush();

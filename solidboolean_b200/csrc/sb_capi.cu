@@ -225,10 +225,11 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad);
     size_t oCbox = take(32 * (size_t)d.M), oCkey = take(4 * (size_t)d.M + 4);
     size_t oNodes = take(64 * nI), oSlot = take(4 * nI), oRoot = take(8);
-    cudaError_t e = cudaMalloc(&m->arena, off);
+    // stream-ordered allocation: the pool keeps the block cached between calls
+    cudaError_t e = cudaMallocAsync(&m->arena, off, ctx->stream);
     if (e != cudaSuccess) {
         delete m;
-        return fail(e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, "cudaMalloc(%zu): %s", off,
+        return fail(e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, "cudaMallocAsync(%zu): %s", off,
             cudaGetErrorString(e));
     }
     char *b = static_cast<char *>(m->arena);
@@ -415,7 +416,7 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
     if (e == cudaSuccess && nT)
         e = cudaMemcpyAsync(m->d.tri, tri, 12 * nT, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) {
-        cudaFree(m->arena);
+        cudaFreeAsync(m->arena, ctx->stream);
         delete m;
         return fail(SB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
     }
@@ -472,8 +473,7 @@ void sb_mesh_destroy(sb_mesh *m)
     if (!m)
         return;
     DeviceGuard g(m->ctx->device);
-    cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->arena);
+    cudaFreeAsync(m->arena, m->ctx->stream);
     delete m;
 }
 

@@ -91,15 +91,26 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) classify_kernel(
         const d3 e = ray_end(p, axis);
         const BoxD myD = ray_box(p, e);
         BoxF myF = active ? enclose(myD) : empty_boxf();
-        BoxF G = myF;
+        // beam measure: cross-section perpendicular to the ray axis
+        BoxF all = myF;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            BoxF o = shfl_xor_box(G, off);
-            merge_f(G, o);
+            BoxF o = shfl_xor_box(all, off);
+            merge_f(all, o);
         }
+        const float ax = all.hix - all.lox, ay = all.hiy - all.loy, az = all.hiz - all.loz;
+        const float pad = 0.015625f * (axis == 0 ? fmaxf(ay, az) : axis == 1 ? fmaxf(ax, az) : fmaxf(ax, ay));
+        auto measure = [pad, axis](const BoxF &b) {
+            float ex = b.hix - b.lox, ey = b.hiy - b.loy, ez = b.hiz - b.loz;
+            if (ex < 0.0f || ey < 0.0f || ez < 0.0f)
+                return 0.0f;
+            float u = axis == 0 ? ey : ex, v = axis == 2 ? ey : ez;
+            return (u + pad) * (v + pad);
+        };
         int nKeys = 0;
+        sbtrav::split_and_run(myF, lane, sh[warp].segs, measure, [&](const BoxF &G, bool inSeg) {
         sbtrav::group_traverse<K>(bvh, G, sh[warp], lane, [&](const Rec32 &r, uint32_t posB) {
-            if (!overlap_f(myF, r.lox, r.loy, r.loz, r.hix, r.hiy, r.hiz))
+            if (!inSeg || !overlap_f(myF, r.lox, r.loy, r.loz, r.hix, r.hiy, r.hiz))
                 return;
             BoxD bd = load_boxd(sbox + 3 * (size_t)posB);
             if (!overlap_d(bd, myD)) // meshTree boxes .intersectWith(rayBox)
@@ -125,6 +136,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) classify_kernel(
             } else {
                 overflow = true;
             }
+        });
         });
         bool in = (nKeys & 1) != 0;
         if (active && perAxis)

@@ -27,6 +27,7 @@ struct WarpScratch {
     uint32_t stack[STACK_CAP];
     uint32_t lq[LQ_CAP];
     Rec32 stage[32];
+    uint16_t segs[32];
 };
 
 struct BvhView {
@@ -113,6 +114,88 @@ __device__ __forceinline__ void group_traverse(const BvhView &bvh, const BoxF &G
             }
             __syncwarp();
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Query-side splitting.  32 curve-consecutive queries are usually one compact
+// patch, but a space-filling-curve jump can put two distant patches into one
+// warp; the union box then covers a large part of the target and that single
+// warp would decide the kernel's run time.  Before traversing, the lane range is
+// therefore split top-down at the position that minimises
+// measure(prefix box) + measure(suffix box) (a surface-area heuristic on the
+// QUERY side, evaluated with two warp scans), as long as a split at least
+// halves... see SPLIT_RATIO.  run(G, inSeg) is called once per final segment.
+constexpr float SPLIT_RATIO = 0.6f;
+
+__device__ __forceinline__ BoxF shfl_up_box(const BoxF &b, int d)
+{
+    return {__shfl_up_sync(SB_FULL, b.lox, d), __shfl_up_sync(SB_FULL, b.loy, d), __shfl_up_sync(SB_FULL, b.loz, d),
+            __shfl_up_sync(SB_FULL, b.hix, d), __shfl_up_sync(SB_FULL, b.hiy, d), __shfl_up_sync(SB_FULL, b.hiz, d)};
+}
+__device__ __forceinline__ BoxF shfl_down_box(const BoxF &b, int d)
+{
+    return {__shfl_down_sync(SB_FULL, b.lox, d), __shfl_down_sync(SB_FULL, b.loy, d), __shfl_down_sync(SB_FULL, b.loz, d),
+            __shfl_down_sync(SB_FULL, b.hix, d), __shfl_down_sync(SB_FULL, b.hiy, d), __shfl_down_sync(SB_FULL, b.hiz, d)};
+}
+__device__ __forceinline__ BoxF shfl_box(const BoxF &b, int src)
+{
+    return {__shfl_sync(SB_FULL, b.lox, src), __shfl_sync(SB_FULL, b.loy, src), __shfl_sync(SB_FULL, b.loz, src),
+            __shfl_sync(SB_FULL, b.hix, src), __shfl_sync(SB_FULL, b.hiy, src), __shfl_sync(SB_FULL, b.hiz, src)};
+}
+
+// measure(box) must return 0 for an empty box and grow with the expected
+// traversal cost of a query box.
+template <typename Measure, typename Run>
+__device__ __forceinline__ void split_and_run(const BoxF &myF, int lane, uint16_t *segs, Measure &&measure, Run &&run)
+{
+    int nseg = 1;
+    if (lane == 0)
+        segs[0] = (uint16_t)(0 | (32 << 8));
+    __syncwarp();
+    while (nseg > 0) {
+        uint16_t se = segs[nseg - 1];
+        --nseg;
+        __syncwarp();
+        const int s = se & 0xff, e = se >> 8;
+        const bool inSeg = lane >= s && lane < e;
+        BoxF mine = inSeg ? myF : empty_boxf();
+        // inclusive prefix / suffix unions over the lanes
+        BoxF pre = mine, suf = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            BoxF a = shfl_up_box(pre, d);
+            BoxF b = shfl_down_box(suf, d);
+            if (lane >= d)
+                merge_f(pre, a);
+            if (lane + d < 32)
+                merge_f(suf, b);
+        }
+        const BoxF G = shfl_box(pre, 31);
+        if (e - s > 1) {
+            BoxF nextSuf = shfl_down_box(suf, 1);
+            float cost = (lane >= s && lane < e - 1) ? measure(pre) + measure(nextSuf) : 3.0e38f;
+            int best = lane;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                float oc = __shfl_xor_sync(SB_FULL, cost, d);
+                int ob = __shfl_xor_sync(SB_FULL, best, d);
+                if (oc < cost || (oc == cost && ob < best)) {
+                    cost = oc;
+                    best = ob;
+                }
+            }
+            if (cost < SPLIT_RATIO * measure(G)) {
+                if (lane == 0) {
+                    segs[nseg] = (uint16_t)((best + 1) | (e << 8));
+                    segs[nseg + 1] = (uint16_t)(s | ((best + 1) << 8));
+                }
+                nseg += 2;
+                __syncwarp();
+                continue;
+            }
+        }
+        run(G, inSeg);
     }
 }
 
