@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -76,12 +78,17 @@ struct sb_context {
     uint32_t *overflowList = nullptr;
     uint32_t overflowCap = 0;
     uint64_t lastRays = 0, lastCands = 0;
+    uint32_t *scanScratch = nullptr; // grid-build scan status words
+    size_t scanScratchWords = 0;
+    int gridDensityLog2 = -2;        // cells per axis ~ nT * 2^this (SB_GRID_DENSITY_LOG2)
 };
 
 struct sb_mesh {
     sb_context *ctx = nullptr;
     MeshDev d;
     void *arena = nullptr;
+    void *gridArena = nullptr; // references, sized after the count pass
+    size_t gridArenaBytes = 0;
     bool built = false;
 };
 
@@ -165,6 +172,21 @@ int ensure_radix_ws(sb_context *c, size_t n)
     return SB_OK;
 }
 
+int ensure_scan_scratch(sb_context *c, uint32_t totalCells)
+{
+    size_t words = sbk_grid_scan_status_words(totalCells);
+    if (words <= c->scanScratchWords)
+        return SB_OK;
+    if (c->scanScratch) {
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        SB_CUDA(cudaFree(c->scanScratch));
+        c->scanScratch = nullptr;
+    }
+    SB_CUDA(cudaMalloc(&c->scanScratch, words * sizeof(uint32_t)));
+    c->scanScratchWords = words;
+    return SB_OK;
+}
+
 int ensure_classify_out(sb_context *c, size_t bytes, uint32_t overflowCap)
 {
     if (bytes > c->classifyOutBytes) {
@@ -225,6 +247,12 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad);
     size_t oCbox = take(32 * (size_t)d.M), oCkey = take(4 * (size_t)d.M + 4);
     size_t oNodes = take(64 * nI), oSlot = take(4 * nI), oRoot = take(8);
+    {
+        double lg = nT ? std::log2((double)nT) + ctx->gridDensityLog2 : 0.0;
+        int bits = (int)std::floor(lg + 0.5);
+        d.gridCellBits = (uint32_t)std::max(0, std::min(bits, 24));
+    }
+    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32);
     // stream-ordered allocation: the pool keeps the block cached between calls
     cudaError_t e = cudaMallocAsync(&m->arena, off, ctx->stream);
     if (e != cudaSuccess) {
@@ -251,6 +279,9 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.slot = (int *)(b + oSlot);
     d.root = (int *)(b + oRoot);
     d.err = d.root + 1;
+    d.gridParams = (GridParams *)(b + oGridP);
+    d.gridE = (uint32_t *)(b + oGridE);
+    d.gridBigCount = (uint32_t *)(b + oGridBig);
     *out = m;
     return SB_OK;
 }
@@ -288,6 +319,8 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SB_CUDA(cudaMalloc(&c->dScalars, 256));
     SB_CUDA(cudaMallocHost(&c->hScalars, 256));
+    if (const char *e = getenv("SB_GRID_DENSITY_LOG2"))
+        c->gridDensityLog2 = atoi(e);
     // keep stream-ordered allocations cached in the pool between calls
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -315,6 +348,7 @@ void sb_context_destroy(sb_context *c)
     cudaFreeHost(c->hScalars);
     cudaFree(c->classifyOut);
     cudaFree(c->overflowList);
+    cudaFree(c->scanScratch);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -433,9 +467,43 @@ int sb_mesh_build(sb_mesh *m)
     int r = ensure_radix_ws(c, m->d.nT);
     if (r)
         return r;
-    StageTimer t(c, SB_STAGE_BUILD);
-    SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, c->stream));
-    SB_CUDA(sbk_build_mesh(c->stream, m->d, c->radixWs, c->radixWsWords, c->smCount, c->lc));
+    if (m->d.nT) {
+        r = ensure_scan_scratch(c, 3u << m->d.gridCellBits);
+        if (r)
+            return r;
+    }
+    {
+        StageTimer t(c, SB_STAGE_BUILD);
+        SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, c->stream));
+        SB_CUDA(sbk_build_mesh(c->stream, m->d, c->radixWs, c->radixWsWords, c->smCount, c->lc));
+        SB_CUDA(sbk_grid_count(c->stream, m->d, c->scanScratch, c->lc));
+    }
+    if (m->d.nT) {
+        // the reference list is sized from the counts: one 16-byte read-back
+        uint32_t *h = reinterpret_cast<uint32_t *>(c->hScalars) + 32;
+        const uint32_t totalCells = 3u << m->d.gridCellBits;
+        SB_CUDA(cudaMemcpyAsync(h, m->d.gridE + totalCells, 4, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        size_t nRefs = h[0];
+        uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
+        for (int k = 0; k < 3; ++k)
+            m->d.gridBigN[k] = h[1 + k];
+        size_t bytes = 16 * (std::max<size_t>(nRefs, 1) + 3 * (size_t)std::max<uint32_t>(bigMax, 1));
+        if (bytes > m->gridArenaBytes) {
+            if (m->gridArena)
+                cudaFreeAsync(m->gridArena, c->stream);
+            m->gridArena = nullptr;
+            m->gridArenaBytes = 0;
+            SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, c->stream));
+            m->gridArenaBytes = bytes;
+        }
+        m->d.gridRefs = static_cast<uint4 *>(m->gridArena);
+        m->d.gridBigRefs = m->d.gridRefs + std::max<size_t>(nRefs, 1);
+        m->d.gridBigCap = std::max<uint32_t>(bigMax, 1);
+        StageTimer t(c, SB_STAGE_BUILD);
+        SB_CUDA(sbk_grid_fill(c->stream, m->d, c->lc));
+    }
     m->built = true;
     return SB_OK;
 }
@@ -474,6 +542,8 @@ void sb_mesh_destroy(sb_mesh *m)
         return;
     DeviceGuard g(m->ctx->device);
     cudaFreeAsync(m->arena, m->ctx->stream);
+    if (m->gridArena)
+        cudaFreeAsync(m->gridArena, m->ctx->stream);
     delete m;
 }
 

@@ -1,25 +1,26 @@
 // Stage 4: inside/outside classification.  Replaces SolidBoolean::isPointInMesh
 // (reference src/solidboolean.cpp:48-92) as driven by decideGroupSide (:482-510).
 //
-// One warp per group of 32 query points (face centroids in the query mesh's
-// Morton order, or caller-supplied points).  For each of the three reference
-// axes (g_testAxisList, :31-35) the 32 rays form a thin "beam" whose union box
-// walks the target's cluster LBVH once (sb_traverse.cuh); every staged leaf is
-// then tested by each lane against ITS ray box -- first the conservative float
-// box, then the exact double box (the reference's candidate definition, a ray
-// box against triangle boxes through AxisAlignedBoudingBoxTree::test, :55-63) --
-// and accepted candidates run the reference arithmetic (sb_raytri.cuh).  Hits
-// are de-duplicated per ray by PositionKey in a small per-lane list; parity of
-// the distinct count is the per-axis answer, the majority of three the result.
+// One thread per query point (face centroids in the query mesh's Morton order,
+// so a warp's 32 rays read neighbouring grid cells; or caller-supplied points).
+// For each of the three reference axes (g_testAxisList, :31-35):
+//   1. ray box = {p, p + axis} exactly as :53-58;
+//   2. candidates: the ray's cell(s) of the target's axis-projected grid
+//      (sb_grid.cu) -- 16-byte references, quantised test, then the EXACT double
+//      box test that defines the reference's candidate set (ray box against
+//      triangle boxes through AxisAlignedBoudingBoxTree::test, :55-63);
+//   3. per candidate the reference arithmetic (sb_raytri.cuh), hits de-duplicated
+//      by PositionKey (std::set<PositionKey>, :64/:85) in a small per-thread
+//      list; odd count = inside for that axis (:89);
+// then the majority of the three axes (:508).  A ray that collects more than
+// KEY_LIST distinct keys is redone by the exact slow path below.
 #include "sb_internal.h"
 #include "sb_raytri.cuh"
-#include "sb_traverse.cuh"
 
 namespace {
 
-constexpr int K = SB_CLUSTER;
-constexpr int WARPS_PER_CTA = 8;
 constexpr int KEY_LIST = 16; // distinct hit keys kept per ray before the slow path
+constexpr int THREADS = 128;
 
 struct KeyList {
     long long x[KEY_LIST], y[KEY_LIST], z[KEY_LIST];
@@ -41,26 +42,47 @@ __device__ __forceinline__ BoxD ray_box(const d3 &p, const d3 &e)
     return b;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) classify_kernel(
+__device__ __forceinline__ uint32_t quant16(double x, double org, double scl)
+{
+    double t = floor((x - org) * scl);
+    t = fmin(fmax(t, 0.0), 65535.0); // NaN -> 0; identical to the grid build
+    return (uint32_t)t;
+}
+
+__device__ __forceinline__ double comp(const BoxD &b, int d, bool hi)
+{
+    return d == 0 ? (hi ? b.hix : b.lox) : d == 1 ? (hi ? b.hiy : b.loy) : (hi ? b.hiz : b.loz);
+}
+
+struct Target {
+    const GridParams *gp;
+    const uint32_t *E;
+    const uint4 *refs;
+    const uint4 *bigRefs;
+    uint32_t bigCap;
+    uint32_t bigN[3];
+    const double2 *tbox;
+    const double4 *vtx;
+    const uint32_t *tri;
+    const double *normal;
+};
+
+__global__ void __launch_bounds__(THREADS) classify_kernel(
     const double *__restrict__ pts,              // explicit points, or null
     const Rec32 *__restrict__ qLeaf,             // query mesh leaves (faces mode)
     const double4 *__restrict__ qVtx, const uint32_t *__restrict__ qTri,
-    uint32_t begin, uint32_t end,
-    const Rec32 *__restrict__ nodes, const Rec32 *__restrict__ leaf, const double2 *__restrict__ sbox,
-    const int *__restrict__ root, const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
-    const double *__restrict__ normal,
+    uint32_t begin, uint32_t end, Target T,
     uint8_t *__restrict__ inside, uint8_t *__restrict__ perAxis, unsigned long long *__restrict__ stats,
     uint32_t *__restrict__ overflowList, unsigned int *__restrict__ overflowCount, uint32_t overflowCap)
 {
-    __shared__ sbtrav::WarpScratch sh[WARPS_PER_CTA];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t group = blockIdx.x * WARPS_PER_CTA + warp;
-    const uint32_t first = begin + group * 32;
-    if (first >= end)
-        return;
-    const uint32_t idx = first + lane;
+    __shared__ GridParams g;
+    if (threadIdx.x == 0)
+        g = *T.gp;
+    __syncthreads();
+    const uint32_t idx = begin + blockIdx.x * THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
 
-    // ---- this lane's query point ----
+    // ---- this thread's query point ----
     bool active = idx < end;
     uint32_t outIndex = idx;
     d3 p = {0, 0, 0};
@@ -81,69 +103,81 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) classify_kernel(
         }
     }
 
-    sbtrav::BvhView bvh = {nodes, leaf, __ldg(root)};
     KeyList keys;
     int insideCount = 0;
     bool overflow = false;
     unsigned int candCount = 0;
+    const BoxD meshBox = {g.lo[0], g.lo[1], g.lo[2], g.hi[0], g.hi[1], g.hi[2]};
 
-    for (int axis = 0; axis < 3; ++axis) {
-        const d3 e = ray_end(p, axis);
-        const BoxD myD = ray_box(p, e);
-        BoxF myF = active ? enclose(myD) : empty_boxf();
-        // beam measure: cross-section perpendicular to the ray axis
-        BoxF all = myF;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            BoxF o = shfl_xor_box(all, off);
-            merge_f(all, o);
-        }
-        const float ax = all.hix - all.lox, ay = all.hiy - all.loy, az = all.hiz - all.loz;
-        const float pad = 0.015625f * (axis == 0 ? fmaxf(ay, az) : axis == 1 ? fmaxf(ax, az) : fmaxf(ax, ay));
-        auto measure = [pad, axis](const BoxF &b) {
-            float ex = b.hix - b.lox, ey = b.hiy - b.loy, ez = b.hiz - b.loz;
-            if (ex < 0.0f || ey < 0.0f || ez < 0.0f)
-                return 0.0f;
-            float u = axis == 0 ? ey : ex, v = axis == 2 ? ey : ez;
-            return (u + pad) * (v + pad);
-        };
-        int nKeys = 0;
-        sbtrav::split_and_run(myF, lane, sh[warp].segs, measure, [&](const BoxF &G, bool inSeg) {
-        sbtrav::group_traverse<K>(bvh, G, sh[warp], lane, [&](const Rec32 &r, uint32_t posB) {
-            if (!inSeg || !overlap_f(myF, r.lox, r.loy, r.loz, r.hix, r.hiy, r.hiz))
-                return;
-            BoxD bd = load_boxd(sbox + 3 * (size_t)posB);
-            if (!overlap_d(bd, myD)) // meshTree boxes .intersectWith(rayBox)
-                return;
-            ++candCount;
-            const uint32_t f = (uint32_t)r.ref;
-            d3 t0 = load_vertex(vtx, __ldg(tri + 3 * (size_t)f));
-            d3 t1 = load_vertex(vtx, __ldg(tri + 3 * (size_t)f + 1));
-            d3 t2 = load_vertex(vtx, __ldg(tri + 3 * (size_t)f + 2));
-            d3 nrm = {__ldg(normal + 3 * (size_t)f), __ldg(normal + 3 * (size_t)f + 1), __ldg(normal + 3 * (size_t)f + 2)};
-            d3 hit;
-            if (!ray_tri_hit(p, e, t0, t1, t2, nrm, hit))
-                return;
-            long long kx = position_key(hit.x), ky = position_key(hit.y), kz = position_key(hit.z);
-            for (int q = 0; q < nKeys; ++q)
-                if (keys.x[q] == kx && keys.y[q] == ky && keys.z[q] == kz)
-                    return; // std::set<PositionKey> insert of an existing key
-            if (nKeys < KEY_LIST) {
-                keys.x[nKeys] = kx;
-                keys.y[nKeys] = ky;
-                keys.z[nKeys] = kz;
-                ++nKeys;
-            } else {
-                overflow = true;
-            }
-        });
-        });
-        bool in = (nKeys & 1) != 0;
-        if (active && perAxis)
-            perAxis[3 * (size_t)outIndex + axis] = in ? 1 : 0;
-        insideCount += in ? 1 : 0;
-    }
     if (active) {
+        for (int axis = 0; axis < 3; ++axis) {
+            const d3 e = ray_end(p, axis);
+            const BoxD myD = ray_box(p, e);
+            int nKeys = 0;
+
+            auto consider = [&](const uint4 &r, uint32_t aU, uint32_t bU, uint32_t aV, uint32_t bV, uint32_t aA) {
+                // quantised closed-interval test (over-accepts only)
+                if ((r.x & 0xffffu) > bU || (r.x >> 16) < aU || (r.y & 0xffffu) > bV || (r.y >> 16) < aV ||
+                    (r.z & 0xffffu) < aA)
+                    return;
+                const uint32_t f = r.w;
+                BoxD bd = load_boxd(T.tbox + 3 * (size_t)f);
+                if (!overlap_d(bd, myD)) // the reference's candidate test, exact
+                    return;
+                ++candCount;
+                d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
+                d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
+                d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
+                d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1),
+                          __ldg(T.normal + 3 * (size_t)f + 2)};
+                d3 hit;
+                if (!ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit))
+                    return;
+                long long kx = position_key(hit.x), ky = position_key(hit.y), kz = position_key(hit.z);
+                for (int q = 0; q < nKeys; ++q)
+                    if (keys.x[q] == kx && keys.y[q] == ky && keys.z[q] == kz)
+                        return; // std::set<PositionKey> insert of an existing key
+                if (nKeys < KEY_LIST) {
+                    keys.x[nKeys] = kx;
+                    keys.y[nKeys] = ky;
+                    keys.z[nKeys] = kz;
+                    ++nKeys;
+                } else {
+                    overflow = true;
+                }
+            };
+
+            if (overlap_d(meshBox, myD)) { // otherwise no triangle box can overlap the ray box
+                const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
+                const uint32_t aU = quant16(comp(myD, u, false), g.org[u], g.scl[u]);
+                const uint32_t bU = quant16(comp(myD, u, true), g.org[u], g.scl[u]);
+                const uint32_t aV = quant16(comp(myD, v, false), g.org[v], g.scl[v]);
+                const uint32_t bV = quant16(comp(myD, v, true), g.org[v], g.scl[v]);
+                const uint32_t aA = quant16(comp(myD, axis, false), g.org[axis], g.scl[axis]);
+                const uint32_t cu0 = aU >> g.shiftU[axis], cu1 = bU >> g.shiftU[axis];
+                const uint32_t cv0 = aV >> g.shiftV[axis], cv1 = bV >> g.shiftV[axis];
+                for (uint32_t cv = cv0; cv <= cv1; ++cv)
+                    for (uint32_t cu = cu0; cu <= cu1; ++cu) {
+                        const uint32_t cell = g.cellBase[axis] + cv * g.nu[axis] + cu;
+                        const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2);
+                        for (uint32_t i = i0; i < i1; ++i) {
+                            const uint4 r = __ldg(T.refs + i);
+                            // a triangle spanning several of the ray's cells is taken in the first one only
+                            const uint32_t tcu = max((r.x & 0xffffu) >> g.shiftU[axis], cu0);
+                            const uint32_t tcv = max((r.y & 0xffffu) >> g.shiftV[axis], cv0);
+                            if (tcu != cu || tcv != cv)
+                                continue;
+                            consider(r, aU, bU, aV, bV, aA);
+                        }
+                    }
+                for (uint32_t i = 0; i < T.bigN[axis]; ++i)
+                    consider(__ldg(T.bigRefs + (size_t)axis * T.bigCap + i), aU, bU, aV, bV, aA);
+            }
+            const bool in = (nKeys & 1) != 0;
+            if (perAxis)
+                perAxis[3 * (size_t)outIndex + axis] = in ? 1 : 0;
+            insideCount += in ? 1 : 0;
+        }
         // (float)insideCount / totalCount > 0.5 with totalCount == 3
         inside[outIndex] = insideCount >= 2 ? 1 : 0;
         if (overflow) {
@@ -159,7 +193,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) classify_kernel(
         candCount += __shfl_xor_sync(SB_FULL, candCount, off);
         rays += __shfl_xor_sync(SB_FULL, rays, off);
     }
-    if (lane == 0 && stats) {
+    if (lane == 0 && stats && rays) {
         atomicAdd(&stats[0], (unsigned long long)rays);
         atomicAdd(&stats[1], (unsigned long long)candCount);
     }
@@ -244,12 +278,22 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     (void)errFlag;
     if (a.end <= a.begin)
         return cudaSuccess;
-    uint32_t groups = (a.end - a.begin + 31) / 32;
-    uint32_t blocks = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    uint32_t blocks = (a.end - a.begin + THREADS - 1) / THREADS;
     const MeshDev *q = a.queryMesh;
-    classify_kernel<<<blocks, WARPS_PER_CTA * 32, 0, s>>>(a.pts, q ? q->leaf : nullptr, q ? q->vtx : nullptr,
-        q ? q->tri : nullptr, a.begin, a.end, target.nodes, target.leaf, target.sbox, target.root, target.vtx, target.tri,
-        target.normal, a.inside, a.perAxis, a.stats, a.overflowList, a.overflowCount, a.overflowCap);
+    Target T;
+    T.gp = target.gridParams;
+    T.E = target.gridE;
+    T.refs = target.gridRefs;
+    T.bigRefs = target.gridBigRefs;
+    T.bigCap = target.gridBigCap;
+    for (int k = 0; k < 3; ++k)
+        T.bigN[k] = target.gridBigN[k];
+    T.tbox = target.tbox;
+    T.vtx = target.vtx;
+    T.tri = target.tri;
+    T.normal = target.normal;
+    classify_kernel<<<blocks, THREADS, 0, s>>>(a.pts, q ? q->leaf : nullptr, q ? q->vtx : nullptr, q ? q->tri : nullptr,
+        a.begin, a.end, T, a.inside, a.perAxis, a.stats, a.overflowList, a.overflowCount, a.overflowCap);
     lc.kernels += 1;
     return cudaGetLastError();
 }

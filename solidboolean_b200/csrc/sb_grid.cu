@@ -1,0 +1,247 @@
+// Axis-projected uniform grids for the inside/outside rays.
+//
+// The three test rays of SolidBoolean::isPointInMesh (reference
+// src/solidboolean.cpp:31-35, 48-92) are axis aligned, so "all triangles whose
+// box overlaps the ray box" is a 2-D point-location problem in the plane
+// perpendicular to the ray plus a half-line test along it.  For every mesh and
+// every axis we therefore bin the triangles' boxes into a 2-D grid over the two
+// perpendicular dimensions (CSR layout: per-cell ranges into one array of
+// 16-byte references).  A ray then reads ONE cell list instead of walking a tree.
+//
+// Exactness: cells and the 16-bit coordinates inside a reference are produced by
+// one monotone quantiser per world axis, q(x) = clamp(floor((x - org) * scl)),
+// applied to triangle bounds and to ray bounds alike.  Monotonicity means
+// lo <= x <= hi  =>  q(lo) <= q(x) <= q(hi), so the quantised test can only
+// over-accept; the exact double test of the reference follows in the classifier.
+//
+// Build = count (atomics) -> in-place chained scan -> fill (atomics), three axes
+// in one pass each, triangles visited in Morton order so neighbouring threads
+// hit neighbouring cells.
+#include "sb_internal.h"
+
+namespace {
+
+constexpr uint32_t MAX_CELLS_PER_TRI = 1024; // larger footprints go to the per-axis "big" list
+
+__device__ __forceinline__ uint32_t quant16(double x, double org, double scl)
+{
+    double t = floor((x - org) * scl);
+    t = fmin(fmax(t, 0.0), 65535.0); // NaN -> 0
+    return (uint32_t)t;
+}
+
+__global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds, int cellBits, GridParams *out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    GridParams g;
+    double ext[3];
+    for (int d = 0; d < 3; ++d) {
+        double lo = dkey_inv(bounds[d]), hi = dkey_inv(bounds[3 + d]);
+        ext[d] = hi - lo;
+        g.org[d] = lo;
+        // hi maps to 65535.99..; finite and > 0 extents only
+        g.scl[d] = (ext[d] > 0.0 && ext[d] < 1.0e300) ? 65535.999 / ext[d] : 0.0;
+        g.lo[d] = lo;
+        g.hi[d] = hi;
+    }
+    for (int a = 0; a < 3; ++a) {
+        int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+        // split cellBits between u and v so that cells come out roughly square
+        double ratio = (ext[u] > 0.0 && ext[v] > 0.0) ? log2(ext[u] / ext[v]) : 0.0;
+        int ku = (int)floor(0.5 * ((double)cellBits + ratio) + 0.5);
+        ku = max(0, min(ku, min(cellBits, 16)));
+        int kv = cellBits - ku;
+        if (kv > 16) {
+            kv = 16;
+            ku = min(16, cellBits - kv);
+        }
+        g.shiftU[a] = 16 - ku;
+        g.shiftV[a] = 16 - kv;
+        g.nu[a] = 1u << ku;
+        g.cellBase[a] = (uint32_t)a << cellBits; // ku + kv <= cellBits cells per axis
+    }
+    g.totalCells = 3u << cellBits;
+    *out = g;
+}
+
+struct TriCells {
+    uint32_t qlo[3], qhi[3];
+};
+
+__device__ __forceinline__ TriCells quantise_box(const BoxD &b, const GridParams &g)
+{
+    TriCells t;
+    t.qlo[0] = quant16(b.lox, g.org[0], g.scl[0]); t.qhi[0] = quant16(b.hix, g.org[0], g.scl[0]);
+    t.qlo[1] = quant16(b.loy, g.org[1], g.scl[1]); t.qhi[1] = quant16(b.hiy, g.org[1], g.scl[1]);
+    t.qlo[2] = quant16(b.loz, g.org[2], g.scl[2]); t.qhi[2] = quant16(b.hiz, g.org[2], g.scl[2]);
+    return t;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) grid_bin_kernel(const double2 *__restrict__ sbox, const Rec32 *__restrict__ leaf,
+    uint32_t nT, const GridParams *__restrict__ gp, uint32_t *__restrict__ E, uint4 *__restrict__ refs,
+    uint4 *__restrict__ bigRefs, uint32_t *__restrict__ bigCount, uint32_t bigCap)
+{
+    __shared__ GridParams g;
+    if (threadIdx.x == 0)
+        g = *gp;
+    __syncthreads();
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nT)
+        return;
+    BoxD b = load_boxd(sbox + 3 * (size_t)j);
+    TriCells t = quantise_box(b, g);
+    uint32_t tri = FILL ? (uint32_t)load_rec(leaf + j).ref : 0u;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+        const uint32_t cu0 = t.qlo[u] >> g.shiftU[a], cu1 = t.qhi[u] >> g.shiftU[a];
+        const uint32_t cv0 = t.qlo[v] >> g.shiftV[a], cv1 = t.qhi[v] >> g.shiftV[a];
+        const uint32_t ncell = (cu1 - cu0 + 1) * (cv1 - cv0 + 1);
+        uint4 rec;
+        if (FILL) {
+            rec.x = t.qlo[u] | (t.qhi[u] << 16);
+            rec.y = t.qlo[v] | (t.qhi[v] << 16);
+            rec.z = t.qhi[a] | (t.qlo[a] << 16);
+            rec.w = tri;
+        }
+        if (ncell > MAX_CELLS_PER_TRI) {
+            uint32_t slot = atomicAdd(&bigCount[FILL ? 3 + a : a], 1u);
+            if (FILL && slot < bigCap)
+                bigRefs[(size_t)a * bigCap + slot] = rec;
+            continue;
+        }
+        const uint32_t base = g.cellBase[a];
+        for (uint32_t cv = cv0; cv <= cv1; ++cv)
+            for (uint32_t cu = cu0; cu <= cu1; ++cu) {
+                uint32_t cell = base + cv * g.nu[a] + cu;
+                if (FILL) {
+                    uint32_t pos = atomicSub(&E[cell + 1], 1u) - 1u; // fill each cell back to front
+                    refs[pos] = rec;
+                } else {
+                    atomicAdd(&E[cell + 1], 1u);
+                }
+            }
+    }
+}
+
+// In-place inclusive scan of a u32 array (single pass, chained tiles with
+// decoupled look-back -- same protocol as the radix sort's digit offsets).
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_PREFIX = 2ull << 62, SCAN_MASK = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *__restrict__ data, uint32_t n,
+    volatile unsigned long long *status, uint32_t *__restrict__ tileCounter)
+{
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+        s_tile = atomicAdd(tileCounter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * SCAN_TILE + tid * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = base + i < n ? data[base + i] : 0u;
+        sum += v[i];
+        v[i] = sum; // inclusive within the thread
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
+        if (lane >= off)
+            incl += t;
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t warpOff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp)
+            warpOff += s_warp[w];
+        total += s_warp[w];
+    }
+    if (tid == 0) {
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            status[0] = (unsigned long long)total | SCAN_PREFIX;
+        } else {
+            status[tile] = (unsigned long long)total | SCAN_AGG;
+            int t = (int)tile - 1;
+            while (true) {
+                unsigned long long s = status[t];
+                if (s & SCAN_PREFIX) {
+                    excl += s & SCAN_MASK;
+                    break;
+                }
+                if (s & SCAN_AGG) {
+                    excl += s & SCAN_MASK;
+                    --t;
+                }
+            }
+            status[tile] = (excl + total) | SCAN_PREFIX;
+        }
+        s_excl = excl;
+    }
+    __syncthreads();
+    const uint32_t off = (uint32_t)s_excl + warpOff + incl - sum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n)
+            data[base + i] = off + v[i];
+}
+
+} // namespace
+
+size_t sbk_grid_scan_status_words(uint32_t totalCells)
+{
+    size_t tiles = ((size_t)totalCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    return 2 * tiles + 4; // u64 status per tile + the tile counter
+}
+
+// Phase 1: parameters, per-cell counts, inclusive scan.  Afterwards
+// E[c + 1] = end of cell c and E[totalCells] = total number of references.
+cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    const uint32_t totalCells = 3u << m.gridCellBits;
+    cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)totalCells + 2), s);
+    cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
+    size_t statusWords = sbk_grid_scan_status_words(totalCells);
+    cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * statusWords, s);
+    grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, (int)m.gridCellBits, m.gridParams);
+    grid_bin_kernel<false><<<(m.nT + 255) / 256, 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, nullptr, nullptr,
+        m.gridBigCount, 0);
+    uint32_t n = totalCells + 1;
+    uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(scanScratch);
+    uint32_t *counter = scanScratch + statusWords - 2;
+    inclusive_scan_kernel<<<tiles, SCAN_THREADS, 0, s>>>(m.gridE, n, status, counter);
+    lc.kernels += 3;
+    return cudaGetLastError();
+}
+
+// Phase 2 (after the caller sized refs / bigRefs from the counts).
+cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    const uint32_t totalCells = 3u << m.gridCellBits;
+    // E[totalCells + 1] = total (end of the last cell once the fill has turned
+    // every E[c + 1] into the START of cell c)
+    cudaMemcpyAsync(m.gridE + totalCells + 1, m.gridE + totalCells, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+    grid_bin_kernel<true><<<(m.nT + 255) / 256, 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, m.gridRefs,
+        m.gridBigRefs, m.gridBigCount, m.gridBigCap);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}

@@ -11,6 +11,18 @@
 #define SB_CLUSTER 8
 #endif
 
+// Axis-projected grids (sb_grid.cu).  One 16-bit quantiser per world axis;
+// grid a (rays along axis a) bins the two perpendicular dimensions u, v.
+struct GridParams {
+    double org[3], scl[3]; // q(x) = clamp(floor((x - org) * scl), 0, 65535)
+    double lo[3], hi[3];   // mesh bounds
+    int shiftU[3], shiftV[3]; // cell = q >> shift
+    uint32_t nu[3];        // cells along u
+    uint32_t cellBase[3];  // first cell of axis a in the concatenated cell space
+    uint32_t totalCells;
+    uint32_t pad;
+};
+
 // Device-resident mesh (all pointers are device pointers).
 struct MeshDev {
     uint32_t nV = 0, nT = 0;
@@ -36,6 +48,15 @@ struct MeshDev {
     int *slot = nullptr;                // M-1 rendezvous slots
     int *root = nullptr;                // device scalar
     int *err = nullptr;                 // device scalar: 1 = triangle index out of range
+    // ray grids
+    uint32_t gridCellBits = 0;          // 2^bits cells per axis
+    GridParams *gridParams = nullptr;
+    uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
+    uint4 *gridRefs = nullptr;          // {qlo_u|qhi_u<<16, qlo_v|qhi_v<<16, qhi_a|qlo_a<<16, triangle id}
+    uint4 *gridBigRefs = nullptr;       // 3 * gridBigCap: triangles covering too many cells
+    uint32_t *gridBigCount = nullptr;   // [0..2] counts (count pass), [3..5] fill cursors
+    uint32_t gridBigCap = 0;
+    uint32_t gridBigN[3] = {0, 0, 0};   // host copy of the big-list lengths
 };
 
 struct LaunchCounter {
@@ -85,3 +106,8 @@ cudaError_t sbk_classify_overflow(cudaStream_t s, const MeshDev &target, const C
     long long *scratch, uint32_t scratchKeysPerRay, int *errFlag, LaunchCounter &lc);
 
 size_t sbk_radix_workspace_words(size_t n);
+
+// sb_grid.cu
+size_t sbk_grid_scan_status_words(uint32_t totalCells);
+cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc);
+cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc);

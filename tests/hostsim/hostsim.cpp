@@ -23,7 +23,7 @@ void hs_tri_tri_batch(const double *tris, size_t n, int32_t *ret, int32_t *copla
 }
 
 // one ray against one triangle: rec = p(3) t0(3) t1(3) t2(3); out hit flag + key
-void hs_ray_tri_batch(const double *rec, const int32_t *axis, size_t n, uint8_t *hitFlag, long long *keys)
+void hs_ray_tri_batch(const double *rec, const int32_t *axis, size_t n, uint8_t *hitFlag, long long *keys, int filtered)
 {
     for (size_t i = 0; i < n; ++i) {
         const double *v = rec + 12 * i;
@@ -31,7 +31,7 @@ void hs_ray_tri_batch(const double *rec, const int32_t *axis, size_t n, uint8_t 
         d3 nrm = tri_normal(t0, t1, t2);
         d3 end = ray_end(p, axis[i]);
         d3 hit = {0, 0, 0};
-        bool h = ray_tri_hit(p, end, t0, t1, t2, nrm, hit);
+        bool h = filtered ? ray_tri_hit_filtered(p, end, t0, t1, t2, nrm, hit) : ray_tri_hit(p, end, t0, t1, t2, nrm, hit);
         hitFlag[i] = h ? 1 : 0;
         keys[3 * i] = h ? position_key(hit.x) : 0;
         keys[3 * i + 1] = h ? position_key(hit.y) : 0;

@@ -265,6 +265,51 @@ def test_many_layers_hit_list_overflow_path(ctx, oracle):
     m.close()
 
 
+def test_mixed_scale_mesh_big_triangle_list(ctx, oracle):
+    """A fine sphere inside a 12-triangle box: the box faces cover the whole ray
+    grid (per-axis 'big' list) while the sphere fills ordinary cells."""
+    sph = meshgen.icosphere(5, radius=0.4, center=(0.1, 0.05, -0.02))
+    s = 1.0
+    bx = np.array([[-s, -s, -s], [s, -s, -s], [s, s, -s], [-s, s, -s], [-s, -s, s], [s, -s, s], [s, s, s], [-s, s, s]], np.float64)
+    bt = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [1, 2, 6], [1, 6, 5],
+                   [2, 3, 7], [2, 7, 6], [3, 0, 4], [3, 4, 7]], np.uint32)
+    mesh = (np.concatenate([sph[0], bx]), np.concatenate([sph[1], bt + len(sph[0])]).astype(np.uint32))
+    rng = np.random.default_rng(12)
+    pts = np.concatenate([rng.uniform(-1.3, 1.3, (30000, 3)), oracle.centroids(*mesh)[::7]])
+    m = ctx.mesh(*mesh)
+    ins, per = m.classify(pts)
+    oi, op, _ = oracle.classify(mesh, pts)
+    assert np.array_equal(per, op) and np.array_equal(ins, oi)
+    other = meshgen.icosphere(4, radius=0.7, center=(0.5, 0.4, 0.3))
+    mo = ctx.mesh(*other)
+    ia, pa = mo.classify_faces_against(m)
+    oa, opa, _ = oracle.classify(mesh, oracle.centroids(*other))
+    assert np.array_equal(pa, opa) and np.array_equal(ia, oa)
+    x = m.intersect(mo)
+    assert np.array_equal(x.candidates()[0], oracle.candidate_pairs(mesh, other))
+    x.close(); m.close(); mo.close()
+
+
+def test_flat_and_degenerate_targets(ctx, oracle):
+    """Zero-extent dimensions (all triangles in one plane) and a single triangle."""
+    rng = np.random.default_rng(2)
+    g = np.linspace(-1, 1, 9)
+    gx, gy = np.meshgrid(g, g, indexing="ij")
+    xyz = np.stack([gx, gy, np.zeros_like(gx)], -1).reshape(-1, 3)
+    i = np.arange(8)[:, None]; j = np.arange(8)[None, :]
+    a = (i * 9 + j).ravel(); b = ((i + 1) * 9 + j).ravel(); c = ((i + 1) * 9 + j + 1).ravel(); d = (i * 9 + j + 1).ravel()
+    tri = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.uint32)
+    one = (np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float64), np.array([[0, 1, 2]], np.uint32))
+    for mesh in ((xyz, tri), one):
+        pts = np.concatenate([rng.uniform(-1.5, 1.5, (5000, 3)), rng.uniform(-1.5, 1.5, (5000, 3)) * [1, 1, 0],
+                              rng.uniform(-1.5, 1.5, (2000, 3)) * [1, 0, 1] + [0, 0.25, -2]])
+        m = ctx.mesh(*mesh)
+        ins, per = m.classify(pts)
+        oi, op, _ = oracle.classify(mesh, pts)
+        assert np.array_equal(per, op) and np.array_equal(ins, oi)
+        m.close()
+
+
 def test_sharded_ranges_cover_whole(ctx):
     """A's Morton range split in R shards == the unsharded result."""
     a, b = meshgen.icosphere(5), meshgen.torus(96, 48, center=(0.013, 0.007, 0.011))
