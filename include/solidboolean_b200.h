@@ -98,6 +98,17 @@ int sb_mesh_bvh_nodes(const sb_mesh *mesh, void *out_records /* 2*num_internal*3
 int sb_mesh_bvh_leaves(const sb_mesh *mesh, void *out_records /* padded nT * 32 B */,
                        size_t *padded_count);
 
+/* Ray-grid introspection (sb_grid.cu): per axis a (rays along a) the grid has
+ * nu[a] x nv[a] cells over the two perpendicular dimensions. */
+typedef struct sb_grid_info {
+    uint32_t nu[3], nv[3];
+    uint32_t total_cells;
+    uint32_t total_refs;    /* 16-byte references over the three grids */
+    uint32_t big[3];        /* triangles kept on the per-axis "big" list */
+    float mean_extent[3];   /* mean triangle-box extent per world axis */
+} sb_grid_info;
+int sb_mesh_grid_info(const sb_mesh *mesh, sb_grid_info *out);
+
 /* ---- intersection: replaces SolidBoolean::searchPotentialIntersectedPairs
  * (src/solidboolean.cpp:94-101 -> axisalignedboundingboxtree.h:54-95) and the
  * predicate loop (src/solidboolean.cpp:315-320 -> intersectTwoFaces :103-122 ->

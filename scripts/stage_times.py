@@ -33,3 +33,4 @@ for it in range(reps):
                           launches=launches, P=x.num_candidates, H=x.num_hits, raysA=rA, raysB=rB,
                           insideA=int(da.sum()), insideB=int(db.sum()))), flush=True)
     x.close()
+print("gridA", ma.grid_info()); print("gridB", mb.grid_info())

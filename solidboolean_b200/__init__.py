@@ -30,6 +30,11 @@ class _BvhInfo(C.Structure):
                 ("num_internal", C.c_uint32), ("root", C.c_int32)]
 
 
+class _GridInfo(C.Structure):
+    _fields_ = [("nu", C.c_uint32 * 3), ("nv", C.c_uint32 * 3), ("total_cells", C.c_uint32),
+                ("total_refs", C.c_uint32), ("big", C.c_uint32 * 3), ("mean_extent", C.c_float * 3)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks
@@ -57,6 +62,7 @@ ABI = {
     "sb_mesh_bvh_info": (C.c_int, [_vp, C.POINTER(_BvhInfo)]),
     "sb_mesh_bvh_nodes": (C.c_int, [_vp, _vp]),
     "sb_mesh_bvh_leaves": (C.c_int, [_vp, _vp, C.POINTER(_sz)]),
+    "sb_mesh_grid_info": (C.c_int, [_vp, C.POINTER(_GridInfo)]),
     "sb_intersect": (C.c_int, [_vp, _vp, C.c_uint, C.POINTER(_vp)]),
     "sb_intersect_range": (C.c_int, [_vp, _vp, _sz, _sz, C.c_uint, C.POINTER(_vp)]),
     "sb_isect_destroy": (None, [_vp]),
@@ -248,6 +254,12 @@ class Mesh:
         assert cnt.value == npad
         return dict(cluster_size=info.cluster_size, num_clusters=info.num_clusters,
                     num_internal=info.num_internal, root=info.root, nodes=nodes, leaves=leaves)
+
+    def grid_info(self):
+        gi = _GridInfo()
+        _check(self.lib.sb_mesh_grid_info(self.h, C.byref(gi)))
+        return dict(nu=list(gi.nu), nv=list(gi.nv), total_cells=gi.total_cells, total_refs=gi.total_refs,
+                    big=list(gi.big), mean_extent=list(gi.mean_extent))
 
     def intersect(self, other: "Mesh", flags=0, begin=None, end=None) -> "Isect":
         return Isect(self, other, flags, begin, end)

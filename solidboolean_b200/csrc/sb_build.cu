@@ -79,11 +79,12 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 
 __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double2 *__restrict__ tbox,
-    double *__restrict__ normal, uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err)
+    double *__restrict__ normal, uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
+    float *__restrict__ extentSum)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nT)
-        return;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f; // this triangle's box extents
+    if (i < nT) {
     uint32_t i0 = tri[3 * (size_t)i], i1 = tri[3 * (size_t)i + 1], i2 = tri[3 * (size_t)i + 2];
     if (i0 >= nV || i1 >= nV || i2 >= nV) { // reported as SB_ERR_INVALID by the host
         *err = 1;
@@ -126,6 +127,23 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     uint32_t qz = quant10(0.5 * (bx.loz + bx.hiz), blz, iz);
     mkey[i] = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
     order[i] = i;
+    sx = (float)(bx.hix - bx.lox); sy = (float)(bx.hiy - bx.loy); sz = (float)(bx.hiz - bx.loz);
+    if (!(sx >= 0.0f && sx < 1e30f)) sx = 0.0f; // NaN / overflow guards (sizing heuristic only)
+    if (!(sy >= 0.0f && sy < 1e30f)) sy = 0.0f;
+    if (!(sz >= 0.0f && sz < 1e30f)) sz = 0.0f;
+    }
+    // mean triangle-box extent per axis (sizes the ray grids): one atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sx += __shfl_xor_sync(SB_FULL, sx, off);
+        sy += __shfl_xor_sync(SB_FULL, sy, off);
+        sz += __shfl_xor_sync(SB_FULL, sz, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(extentSum, sx);
+        atomicAdd(extentSum + 1, sy);
+        atomicAdd(extentSum + 2, sz);
+    }
 }
 
 // ---- K1b --------------------------------------------------------------------
@@ -229,6 +247,7 @@ cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t
     // bounds seeds: min slots all-ones, max slots zero (order-encoded doubles)
     cudaMemsetAsync(m.bounds, 0xff, 3 * sizeof(unsigned long long), s);
     cudaMemsetAsync(m.bounds + 3, 0x00, 3 * sizeof(unsigned long long), s);
+    cudaMemsetAsync(m.extentSum, 0, 4 * sizeof(float), s);
     int vb = (int)((m.nV + 255) / 256);
     if (vb > smCount * 8)
         vb = smCount * 8;
@@ -236,7 +255,7 @@ cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t
         vb = 1;
     bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds);
     tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.tbox, m.normal, m.mkey,
-        m.order, m.err);
+        m.order, m.err, m.extentSum);
     lc.kernels += 2;
     sbradix::Workspace ws;
     ws.mem = radixWs;

@@ -78,9 +78,10 @@ struct sb_context {
     uint32_t *overflowList = nullptr;
     uint32_t overflowCap = 0;
     uint64_t lastRays = 0, lastCands = 0;
+    double candPerRayHint = 3.0;     // sizes the candidate list; adapts to the last call
     uint32_t *scanScratch = nullptr; // grid-build scan status words
     size_t scanScratchWords = 0;
-    int gridDensityLog2 = -2;        // cells per axis ~ nT * 2^this (SB_GRID_DENSITY_LOG2)
+    float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
 };
 
 struct sb_mesh {
@@ -248,11 +249,13 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     size_t oCbox = take(32 * (size_t)d.M), oCkey = take(4 * (size_t)d.M + 4);
     size_t oNodes = take(64 * nI), oSlot = take(4 * nI), oRoot = take(8);
     {
-        double lg = nT ? std::log2((double)nT) + ctx->gridDensityLog2 : 0.0;
+        // allocation bound: at most ~2 nT cells per axis (the device picks the
+        // actual resolution from the mean triangle extent, sb_grid.cu)
+        double lg = nT ? std::log2((double)nT) + 1.0 : 0.0;
         int bits = (int)std::floor(lg + 0.5);
-        d.gridCellBits = (uint32_t)std::max(0, std::min(bits, 24));
+        d.gridCellBits = (uint32_t)std::max(0, std::min(bits, 26));
     }
-    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32);
+    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(48);
     // stream-ordered allocation: the pool keeps the block cached between calls
     cudaError_t e = cudaMallocAsync(&m->arena, off, ctx->stream);
     if (e != cudaSuccess) {
@@ -282,6 +285,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.gridParams = (GridParams *)(b + oGridP);
     d.gridE = (uint32_t *)(b + oGridE);
     d.gridBigCount = (uint32_t *)(b + oGridBig);
+    d.extentSum = (float *)(d.gridBigCount + 8);
     *out = m;
     return SB_OK;
 }
@@ -319,8 +323,11 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SB_CUDA(cudaMalloc(&c->dScalars, 256));
     SB_CUDA(cudaMallocHost(&c->hScalars, 256));
-    if (const char *e = getenv("SB_GRID_DENSITY_LOG2"))
-        c->gridDensityLog2 = atoi(e);
+    if (const char *e = getenv("SB_GRID_BETA")) {
+        float b = (float)atof(e);
+        if (b > 0.01f && b < 100.0f)
+            c->gridBeta = b;
+    }
     // keep stream-ordered allocations cached in the pool between calls
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -476,13 +483,12 @@ int sb_mesh_build(sb_mesh *m)
         StageTimer t(c, SB_STAGE_BUILD);
         SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, c->stream));
         SB_CUDA(sbk_build_mesh(c->stream, m->d, c->radixWs, c->radixWsWords, c->smCount, c->lc));
-        SB_CUDA(sbk_grid_count(c->stream, m->d, c->scanScratch, c->lc));
+        SB_CUDA(sbk_grid_count(c->stream, m->d, c->scanScratch, c->gridBeta, c->lc));
     }
     if (m->d.nT) {
         // the reference list is sized from the counts: one 16-byte read-back
         uint32_t *h = reinterpret_cast<uint32_t *>(c->hScalars) + 32;
-        const uint32_t totalCells = 3u << m->d.gridCellBits;
-        SB_CUDA(cudaMemcpyAsync(h, m->d.gridE + totalCells, 4, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaMemcpyAsync(h, m->d.gridBigCount + 6, 4, cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA(cudaStreamSynchronize(c->stream));
         size_t nRefs = h[0];
@@ -602,6 +608,35 @@ int sb_mesh_bvh_leaves(const sb_mesh *m, void *out, size_t *padded)
     if (padded)
         *padded = m ? m->d.nTpad : 0;
     return mesh_download(m, out, m ? m->d.leaf : nullptr, m ? 32 * (size_t)m->d.nTpad : 0);
+}
+
+int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
+{
+    if (!m || !out)
+        return fail(SB_ERR_INVALID, "null mesh or output");
+    memset(out, 0, sizeof(*out));
+    if (!m->d.nT)
+        return SB_OK;
+    GridParams g;
+    int r = mesh_download(m, &g, m->d.gridParams, sizeof(g));
+    if (r)
+        return r;
+    uint32_t cnt[8];
+    float ext[4];
+    r = mesh_download(m, cnt, m->d.gridBigCount, sizeof(cnt));
+    if (!r)
+        r = mesh_download(m, ext, m->d.extentSum, sizeof(ext));
+    if (r)
+        return r;
+    for (int a = 0; a < 3; ++a) {
+        out->nu[a] = g.nu[a];
+        out->nv[a] = 1u << (16 - g.shiftV[a]);
+        out->big[a] = cnt[a];
+        out->mean_extent[a] = ext[a] / (float)m->d.nT;
+    }
+    out->total_cells = g.totalCells;
+    out->total_refs = cnt[6];
+    return SB_OK;
 }
 
 // ---- intersection -----------------------------------------------------------------
@@ -865,47 +900,37 @@ int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret
 
 // ---- classification --------------------------------------------------------------
 
-// Runs the kernel, reads the counters back, and sends overflowed points through
-// the exact slow path.  dInside / dPerAxis are device buffers.
-static int classify_run(sb_context *c, const sb_mesh *target, ClassifyArgs a, bool syncAndFinish)
+// Runs the three classification kernels and reads the candidate count back; if
+// the candidate list was too small the pass is repeated once with the exact size.
+static int classify_run(sb_context *c, const sb_mesh *target, ClassifyArgs a)
 {
-    uint32_t ovCap = c->overflowCap;
-    a.stats = c->dScalars->stats;
-    a.overflowList = c->overflowList;
-    a.overflowCount = &c->dScalars->overflowCount;
-    a.overflowCap = ovCap;
-    {
-        StageTimer t(c, SB_STAGE_CLASSIFY);
-        SB_CUDA(sbk_classify(c->stream, target->d, a, &c->dScalars->err, c->lc));
+    const uint32_t points = a.end - a.begin;
+    const bool faces = a.pts == nullptr;
+    const unsigned long long rays = 3ull * points;
+    unsigned long long cap = std::max<unsigned long long>(4096, (unsigned long long)(c->candPerRayHint * (double)rays) + 1024);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t bytes = sbk_classify_scratch_bytes(points, cap, faces);
+        void *scratch = nullptr;
+        SB_CUDA(cudaMallocAsync(&scratch, bytes, c->stream));
+        SB_CUDA(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
+        {
+            StageTimer t(c, SB_STAGE_CLASSIFY);
+            SB_CUDA(sbk_classify(c->stream, target->d, a, scratch, cap, &c->dScalars->stats[1], c->lc));
+        }
+        SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFreeAsync(scratch, c->stream);
+        const unsigned long long cands = c->hScalars->stats[1];
+        c->lastRays = rays;
+        c->lastCands = cands;
+        if (rays)
+            c->candPerRayHint = std::max(0.25, 1.25 * (double)cands / (double)rays);
+        if (cands <= cap)
+            return SB_OK;
+        if (attempt == 1)
+            return fail(SB_ERR_CAPACITY, "candidate list overflow after retry (%llu > %llu)", cands, cap);
+        cap = cands;
     }
-    if (!syncAndFinish)
-        return SB_OK;
-    SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
-    SB_CUDA(cudaStreamSynchronize(c->stream));
-    c->lastRays = c->hScalars->stats[0];
-    c->lastCands = c->hScalars->stats[1];
-    uint32_t nOv = c->hScalars->overflowCount;
-    if (nOv == 0)
-        return SB_OK;
-    if (nOv > ovCap)
-        return fail(SB_ERR_CAPACITY, "%u rays exceeded the per-ray hit list and the overflow list (%u)", nOv, ovCap);
-    const uint32_t keysPerRay = 1024;
-    const uint32_t chunk = 1024;
-    long long *scratch = nullptr;
-    size_t scratchBytes = (size_t)chunk * 3 * keysPerRay * 3 * sizeof(long long) + (size_t)chunk * 3 + 64;
-    SB_CUDA(cudaMallocAsync((void **)&scratch, scratchBytes, c->stream));
-    for (uint32_t o = 0; o < nOv; o += chunk) {
-        ClassifyArgs b = a;
-        b.overflowList = c->overflowList + o;
-        uint32_t n = std::min(chunk, nOv - o);
-        StageTimer t(c, SB_STAGE_CLASSIFY);
-        SB_CUDA(sbk_classify_overflow(c->stream, target->d, b, n, scratch, keysPerRay, &c->dScalars->err, c->lc));
-    }
-    SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
-    SB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFreeAsync(scratch, c->stream);
-    if (c->hScalars->err)
-        return fail(SB_ERR_CAPACITY, "a ray crossed more than %u distinct surface points", keysPerRay);
     return SB_OK;
 }
 
@@ -921,7 +946,7 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
         return SB_OK;
     sb_context *c = target->ctx;
     DeviceGuard g(c->device);
-    int r = ensure_classify_out(c, 4 * Q, (uint32_t)std::min<size_t>(Q, 1 << 20));
+    int r = ensure_classify_out(c, 4 * Q, 0);
     if (r)
         return r;
     double *dPts = nullptr;
@@ -929,7 +954,6 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
     if (r)
         return r;
     SB_CUDA(cudaMemcpyAsync(dPts, pts, 24 * Q, cudaMemcpyHostToDevice, c->stream));
-    SB_CUDA(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
     ClassifyArgs a;
     a.pts = dPts;
     a.begin = 0;
@@ -940,7 +964,7 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
         SB_CUDA(cudaMemsetAsync(c->classifyOut, 0, 4 * Q, c->stream));
         SB_CUDA(cudaStreamSynchronize(c->stream));
     } else {
-        r = classify_run(c, target, a, true);
+        r = classify_run(c, target, a);
     }
     if (!r) {
         SB_CUDA(cudaMemcpyAsync(inside, a.inside, Q, cudaMemcpyDeviceToHost, c->stream));
@@ -969,10 +993,9 @@ static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size
         begin = end;
     if (begin % 32)
         return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
-    int r = ensure_classify_out(c, 4 * std::max<size_t>(n, 1), (uint32_t)std::min<size_t>(std::max<size_t>(n, 1), 1 << 20));
+    int r = ensure_classify_out(c, 4 * std::max<size_t>(n, 1), 0);
     if (r)
         return r;
-    SB_CUDA(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
     ClassifyArgs a;
     a.queryMesh = &query->d;
     a.begin = (uint32_t)begin;
@@ -987,7 +1010,8 @@ static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size
             SB_CUDA(cudaMemsetAsync(externalInside, 0, n, c->stream));
         return SB_OK;
     }
-    return classify_run(c, target, a, finish);
+    (void)finish;
+    return classify_run(c, target, a);
 }
 
 int sb_classify_faces(const sb_mesh *query, const sb_mesh *target, uint8_t *inside, uint8_t *per_axis)

@@ -1,30 +1,29 @@
 // Stage 4: inside/outside classification.  Replaces SolidBoolean::isPointInMesh
 // (reference src/solidboolean.cpp:48-92) as driven by decideGroupSide (:482-510).
 //
-// One thread per query point (face centroids in the query mesh's Morton order,
-// so a warp's 32 rays read neighbouring grid cells; or caller-supplied points).
-// For each of the three reference axes (g_testAxisList, :31-35):
-//   1. ray box = {p, p + axis} exactly as :53-58;
-//   2. candidates: the ray's cell(s) of the target's axis-projected grid
-//      (sb_grid.cu) -- 16-byte references, quantised test, then the EXACT double
-//      box test that defines the reference's candidate set (ray box against
-//      triangle boxes through AxisAlignedBoudingBoxTree::test, :55-63);
-//   3. per candidate the reference arithmetic (sb_raytri.cuh), hits de-duplicated
-//      by PositionKey (std::set<PositionKey>, :64/:85) in a small per-thread
-//      list; odd count = inside for that axis (:89);
-// then the majority of the three axes (:508).  A ray that collects more than
-// KEY_LIST distinct keys is redone by the exact slow path below.
+// Three kernels, so that the memory-latency-bound part runs at full occupancy
+// and the FP64 part runs on a dense list with every lane busy:
+//
+//  A  ray_scan_kernel    one thread per RAY (point x axis; a CTA = 256
+//     neighbouring points of one axis, so its threads read neighbouring grid
+//     cells).  Ray box exactly as :53-58; the ray's cell list of the target's
+//     axis-projected grid (sb_grid.cu): quantised 16-byte references first, then
+//     the EXACT double box test that defines the reference's candidate set
+//     (:55-63).  Candidates are counted, a warp scan reserves one contiguous
+//     range of the global candidate list per warp (one atomic per warp), and
+//     every ray writes its (ray, triangle) entries ray-contiguously.
+//  B  ray_hit_kernel     one thread per CANDIDATE: segment/plane hit, the two
+//     edge-normal sign tests (sb_raytri.cuh, bit-exact), PositionKey of the hit.
+//  C  ray_finish_kernel  one thread per point: per axis, count the DISTINCT hit
+//     keys (std::set<PositionKey>, :64/:85), odd = inside (:89); majority of the
+//     three axes ((float)insideCount / totalCount > 0.5, :508).
 #include "sb_internal.h"
 #include "sb_raytri.cuh"
 
 namespace {
 
-constexpr int KEY_LIST = 16; // distinct hit keys kept per ray before the slow path
-constexpr int THREADS = 128;
-
-struct KeyList {
-    long long x[KEY_LIST], y[KEY_LIST], z[KEY_LIST];
-};
+constexpr int SCAN_THREADS = 256;
+constexpr int KEEP = 4; // candidates a scan thread keeps in registers before re-scanning
 
 __device__ __forceinline__ BoxD ray_box(const d3 &p, const d3 &e)
 {
@@ -60,257 +59,301 @@ struct Target {
     const uint4 *refs;
     const uint4 *bigRefs;
     uint32_t bigCap;
-    uint32_t bigN[3];
+    uint32_t bigN0, bigN1, bigN2;
     const double2 *tbox;
     const double4 *vtx;
     const uint32_t *tri;
     const double *normal;
 };
 
-__global__ void __launch_bounds__(THREADS) classify_kernel(
-    const double *__restrict__ pts,              // explicit points, or null
-    const Rec32 *__restrict__ qLeaf,             // query mesh leaves (faces mode)
-    const double4 *__restrict__ qVtx, const uint32_t *__restrict__ qTri,
-    uint32_t begin, uint32_t end, Target T,
-    uint8_t *__restrict__ inside, uint8_t *__restrict__ perAxis, unsigned long long *__restrict__ stats,
-    uint32_t *__restrict__ overflowList, unsigned int *__restrict__ overflowCount, uint32_t overflowCap)
+struct Query {
+    const double *pts;  // explicit points (AoS), or null
+    const Rec32 *leaf;  // faces mode: query mesh leaves ...
+    const double4 *vtx; // ... its vertices
+    const uint32_t *tri;
+    uint32_t begin;     // first point / sorted position
+    uint32_t count;     // points in this launch
+};
+
+// Walk the ray's candidates in a fixed order; visit(triangle id) for each
+// triangle whose EXACT box overlaps the ray box.
+template <typename Visit>
+__device__ __forceinline__ void for_each_candidate(const GridParams &g, const Target &T, int axis, const BoxD &myD,
+    Visit &&visit)
+{
+    const BoxD meshBox = {g.lo[0], g.lo[1], g.lo[2], g.hi[0], g.hi[1], g.hi[2]};
+    if (!overlap_d(meshBox, myD)) // no triangle box can overlap the ray box
+        return;
+    const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
+    const uint32_t aU = quant16(comp(myD, u, false), g.org[u], g.scl[u]);
+    const uint32_t bU = quant16(comp(myD, u, true), g.org[u], g.scl[u]);
+    const uint32_t aV = quant16(comp(myD, v, false), g.org[v], g.scl[v]);
+    const uint32_t bV = quant16(comp(myD, v, true), g.org[v], g.scl[v]);
+    const uint32_t aA = quant16(comp(myD, axis, false), g.org[axis], g.scl[axis]);
+    auto consider = [&](const uint4 &r) {
+        // quantised closed-interval test (over-accepts only)
+        if ((r.x & 0xffffu) > bU || (r.x >> 16) < aU || (r.y & 0xffffu) > bV || (r.y >> 16) < aV ||
+            (r.z & 0xffffu) < aA)
+            return;
+        BoxD bd = load_boxd(T.tbox + 3 * (size_t)r.w);
+        if (overlap_d(bd, myD)) // the reference's candidate test, exact
+            visit(r.w);
+    };
+    const int su = g.shiftU[axis], sv = g.shiftV[axis];
+    const uint32_t cu0 = aU >> su, cu1 = bU >> su, cv0 = aV >> sv, cv1 = bV >> sv;
+    for (uint32_t cv = cv0; cv <= cv1; ++cv)
+        for (uint32_t cu = cu0; cu <= cu1; ++cu) {
+            const uint32_t cell = g.cellBase[axis] + cv * g.nu[axis] + cu;
+            const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2);
+            // four independent 16-byte loads in flight per thread
+            auto take = [&](const uint4 &r, uint32_t i) {
+                // a triangle spanning several of the ray's cells is taken in the first one only
+                if (i < i1 && max((r.x & 0xffffu) >> su, cu0) == cu && max((r.y & 0xffffu) >> sv, cv0) == cv)
+                    consider(r);
+            };
+            for (uint32_t i = i0; i < i1; i += 4) {
+                const uint4 r0 = __ldg(T.refs + i);
+                const uint4 r1 = __ldg(T.refs + min(i + 1, i1 - 1));
+                const uint4 r2 = __ldg(T.refs + min(i + 2, i1 - 1));
+                const uint4 r3 = __ldg(T.refs + min(i + 3, i1 - 1));
+                take(r0, i);
+                take(r1, i + 1);
+                take(r2, i + 2);
+                take(r3, i + 3);
+            }
+        }
+    const uint32_t nBig = axis == 0 ? T.bigN0 : axis == 1 ? T.bigN1 : T.bigN2;
+    for (uint32_t i = 0; i < nBig; ++i)
+        consider(__ldg(T.bigRefs + (size_t)axis * T.bigCap + i));
+}
+
+__device__ __forceinline__ bool query_point(const Query &q, uint32_t j, d3 &p, uint32_t &outIndex)
+{
+    if (j >= q.count)
+        return false;
+    const uint32_t idx = q.begin + j;
+    if (q.pts) {
+        p = {q.pts[3 * (size_t)idx], q.pts[3 * (size_t)idx + 1], q.pts[3 * (size_t)idx + 2]};
+        outIndex = idx;
+        return true;
+    }
+    int t = load_rec(q.leaf + idx).ref;
+    if (t < 0)
+        return false; // padding leaf
+    outIndex = (uint32_t)t;
+    d3 a = load_vertex(q.vtx, __ldg(q.tri + 3 * (size_t)t));
+    d3 b = load_vertex(q.vtx, __ldg(q.tri + 3 * (size_t)t + 1));
+    d3 c = load_vertex(q.vtx, __ldg(q.tri + 3 * (size_t)t + 2));
+    // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
+    p = {xdiv(xadd(xadd(a.x, b.x), c.x), 3.0), xdiv(xadd(xadd(a.y, b.y), c.y), 3.0),
+         xdiv(xadd(xadd(a.z, b.z), c.z), 3.0)};
+    return true;
+}
+
+// ---- A ------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) ray_scan_kernel(Query q, Target T, uint32_t blocksPerAxis,
+    double *__restrict__ qpt, uint2 *__restrict__ cand, unsigned long long cap,
+    unsigned long long *__restrict__ candCount, uint2 *__restrict__ rayRange)
 {
     __shared__ GridParams g;
     if (threadIdx.x == 0)
         g = *T.gp;
     __syncthreads();
-    const uint32_t idx = begin + blockIdx.x * THREADS + threadIdx.x;
+    const int axis = blockIdx.x / blocksPerAxis;
+    const uint32_t j = (blockIdx.x % blocksPerAxis) * SCAN_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
 
-    // ---- this thread's query point ----
-    bool active = idx < end;
-    uint32_t outIndex = idx;
     d3 p = {0, 0, 0};
-    if (pts) {
-        if (active)
-            p = {pts[3 * (size_t)idx], pts[3 * (size_t)idx + 1], pts[3 * (size_t)idx + 2]};
-    } else {
-        int t = active ? load_rec(qLeaf + idx).ref : -1;
-        active = t >= 0;
-        if (active) {
-            outIndex = (uint32_t)t;
-            d3 a = load_vertex(qVtx, __ldg(qTri + 3 * (size_t)t));
-            d3 b = load_vertex(qVtx, __ldg(qTri + 3 * (size_t)t + 1));
-            d3 c = load_vertex(qVtx, __ldg(qTri + 3 * (size_t)t + 2));
-            // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
-            p = {xdiv(xadd(xadd(a.x, b.x), c.x), 3.0), xdiv(xadd(xadd(a.y, b.y), c.y), 3.0),
-                 xdiv(xadd(xadd(a.z, b.z), c.z), 3.0)};
-        }
-    }
-
-    KeyList keys;
-    int insideCount = 0;
-    bool overflow = false;
-    unsigned int candCount = 0;
-    const BoxD meshBox = {g.lo[0], g.lo[1], g.lo[2], g.hi[0], g.hi[1], g.hi[2]};
-
-    if (active) {
-        for (int axis = 0; axis < 3; ++axis) {
-            const d3 e = ray_end(p, axis);
-            const BoxD myD = ray_box(p, e);
-            int nKeys = 0;
-
-            auto consider = [&](const uint4 &r, uint32_t aU, uint32_t bU, uint32_t aV, uint32_t bV, uint32_t aA) {
-                // quantised closed-interval test (over-accepts only)
-                if ((r.x & 0xffffu) > bU || (r.x >> 16) < aU || (r.y & 0xffffu) > bV || (r.y >> 16) < aV ||
-                    (r.z & 0xffffu) < aA)
-                    return;
-                const uint32_t f = r.w;
-                BoxD bd = load_boxd(T.tbox + 3 * (size_t)f);
-                if (!overlap_d(bd, myD)) // the reference's candidate test, exact
-                    return;
-                ++candCount;
-                d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
-                d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
-                d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
-                d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1),
-                          __ldg(T.normal + 3 * (size_t)f + 2)};
-                d3 hit;
-                if (!ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit))
-                    return;
-                long long kx = position_key(hit.x), ky = position_key(hit.y), kz = position_key(hit.z);
-                for (int q = 0; q < nKeys; ++q)
-                    if (keys.x[q] == kx && keys.y[q] == ky && keys.z[q] == kz)
-                        return; // std::set<PositionKey> insert of an existing key
-                if (nKeys < KEY_LIST) {
-                    keys.x[nKeys] = kx;
-                    keys.y[nKeys] = ky;
-                    keys.z[nKeys] = kz;
-                    ++nKeys;
-                } else {
-                    overflow = true;
-                }
-            };
-
-            if (overlap_d(meshBox, myD)) { // otherwise no triangle box can overlap the ray box
-                const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
-                const uint32_t aU = quant16(comp(myD, u, false), g.org[u], g.scl[u]);
-                const uint32_t bU = quant16(comp(myD, u, true), g.org[u], g.scl[u]);
-                const uint32_t aV = quant16(comp(myD, v, false), g.org[v], g.scl[v]);
-                const uint32_t bV = quant16(comp(myD, v, true), g.org[v], g.scl[v]);
-                const uint32_t aA = quant16(comp(myD, axis, false), g.org[axis], g.scl[axis]);
-                const uint32_t cu0 = aU >> g.shiftU[axis], cu1 = bU >> g.shiftU[axis];
-                const uint32_t cv0 = aV >> g.shiftV[axis], cv1 = bV >> g.shiftV[axis];
-                for (uint32_t cv = cv0; cv <= cv1; ++cv)
-                    for (uint32_t cu = cu0; cu <= cu1; ++cu) {
-                        const uint32_t cell = g.cellBase[axis] + cv * g.nu[axis] + cu;
-                        const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2);
-                        for (uint32_t i = i0; i < i1; ++i) {
-                            const uint4 r = __ldg(T.refs + i);
-                            // a triangle spanning several of the ray's cells is taken in the first one only
-                            const uint32_t tcu = max((r.x & 0xffffu) >> g.shiftU[axis], cu0);
-                            const uint32_t tcv = max((r.y & 0xffffu) >> g.shiftV[axis], cv0);
-                            if (tcu != cu || tcv != cv)
-                                continue;
-                            consider(r, aU, bU, aV, bV, aA);
-                        }
-                    }
-                for (uint32_t i = 0; i < T.bigN[axis]; ++i)
-                    consider(__ldg(T.bigRefs + (size_t)axis * T.bigCap + i), aU, bU, aV, bV, aA);
-            }
-            const bool in = (nKeys & 1) != 0;
-            if (perAxis)
-                perAxis[3 * (size_t)outIndex + axis] = in ? 1 : 0;
-            insideCount += in ? 1 : 0;
-        }
-        // (float)insideCount / totalCount > 0.5 with totalCount == 3
-        inside[outIndex] = insideCount >= 2 ? 1 : 0;
-        if (overflow) {
-            unsigned int slot = atomicAdd(overflowCount, 1u);
-            if (slot < overflowCap)
-                overflowList[slot] = pts ? idx : outIndex;
-        }
-    }
-    // work counters (one atomic per warp)
-    unsigned int rays = active ? 3u : 0u;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        candCount += __shfl_xor_sync(SB_FULL, candCount, off);
-        rays += __shfl_xor_sync(SB_FULL, rays, off);
-    }
-    if (lane == 0 && stats && rays) {
-        atomicAdd(&stats[0], (unsigned long long)rays);
-        atomicAdd(&stats[1], (unsigned long long)candCount);
-    }
-}
-
-// Exact slow path: one thread per (overflowed point, axis), brute force over all
-// target triangles, distinct keys kept in global scratch.
-__global__ void __launch_bounds__(128) classify_overflow_kernel(
-    const double *__restrict__ pts, const double4 *__restrict__ qVtx, const uint32_t *__restrict__ qTri,
-    const uint32_t *__restrict__ list, uint32_t nList,
-    const double2 *__restrict__ tbox, const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
-    const double *__restrict__ normal, uint32_t nT,
-    long long *__restrict__ scratch, uint32_t keysPerRay, uint8_t *__restrict__ axisOut, int *__restrict__ errFlag)
-{
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nList * 3)
-        return;
-    uint32_t li = g / 3;
-    int axis = (int)(g % 3);
-    uint32_t id = list[li];
-    d3 p;
-    if (pts) {
-        p = {pts[3 * (size_t)id], pts[3 * (size_t)id + 1], pts[3 * (size_t)id + 2]};
-    } else {
-        d3 a = load_vertex(qVtx, qTri[3 * (size_t)id]);
-        d3 b = load_vertex(qVtx, qTri[3 * (size_t)id + 1]);
-        d3 c = load_vertex(qVtx, qTri[3 * (size_t)id + 2]);
-        p = {xdiv(xadd(xadd(a.x, b.x), c.x), 3.0), xdiv(xadd(xadd(a.y, b.y), c.y), 3.0),
-             xdiv(xadd(xadd(a.z, b.z), c.z), 3.0)};
+    uint32_t outIndex = 0;
+    const bool active = query_point(q, j, p, outIndex);
+    if (active && axis == 0 && qpt) {
+        qpt[3 * (size_t)j] = p.x;
+        qpt[3 * (size_t)j + 1] = p.y;
+        qpt[3 * (size_t)j + 2] = p.z;
     }
     const d3 e = ray_end(p, axis);
     const BoxD myD = ray_box(p, e);
-    long long *my = scratch + (size_t)g * keysPerRay * 3;
-    uint32_t nKeys = 0;
-    for (uint32_t f = 0; f < nT; ++f) {
-        BoxD bd = load_boxd(tbox + 3 * (size_t)f);
-        if (!overlap_d(bd, myD))
-            continue;
-        d3 t0 = load_vertex(vtx, tri[3 * (size_t)f]);
-        d3 t1 = load_vertex(vtx, tri[3 * (size_t)f + 1]);
-        d3 t2 = load_vertex(vtx, tri[3 * (size_t)f + 2]);
-        d3 nrm = {normal[3 * (size_t)f], normal[3 * (size_t)f + 1], normal[3 * (size_t)f + 2]};
-        d3 hit;
-        if (!ray_tri_hit(p, e, t0, t1, t2, nrm, hit))
-            continue;
-        long long kx = position_key(hit.x), ky = position_key(hit.y), kz = position_key(hit.z);
-        bool dup = false;
-        for (uint32_t q = 0; q < nKeys && !dup; ++q)
-            dup = my[3 * q] == kx && my[3 * q + 1] == ky && my[3 * q + 2] == kz;
-        if (dup)
-            continue;
-        if (nKeys >= keysPerRay) {
-            *errFlag = 1;
-            break;
-        }
-        my[3 * nKeys] = kx;
-        my[3 * nKeys + 1] = ky;
-        my[3 * nKeys + 2] = kz;
-        ++nKeys;
+
+    uint32_t n = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (active)
+        for_each_candidate(g, T, axis, myD, [&](uint32_t f) {
+            if (n == 0) c0 = f;
+            else if (n == 1) c1 = f;
+            else if (n == 2) c2 = f;
+            else if (n == 3) c3 = f;
+            ++n;
+        });
+
+    // warp-wide exclusive scan of n; one atomic per warp reserves its output range
+    // (no block barrier: a warp whose rays hit long cell lists does not hold up the rest)
+    uint32_t incl = n;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
+        if (lane >= off)
+            incl += t;
     }
-    axisOut[g] = (uint8_t)(nKeys & 1);
+    const uint32_t total = __shfl_sync(SB_FULL, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total)
+        base = atomicAdd(candCount, (unsigned long long)total);
+    base = __shfl_sync(SB_FULL, base, 0);
+    if (!active)
+        return;
+    const unsigned long long first = base + incl - n;
+    const uint32_t ray = (uint32_t)axis * q.count + j;
+    rayRange[ray] = make_uint2((uint32_t)min(first, 0xffffffffull), n);
+    if (first + n > cap)
+        return; // list too small: the host sees candCount > cap and retries
+    if (n > 0) cand[first] = make_uint2(ray, c0);
+    if (n > 1) cand[first + 1] = make_uint2(ray, c1);
+    if (n > 2) cand[first + 2] = make_uint2(ray, c2);
+    if (n > 3) cand[first + 3] = make_uint2(ray, c3);
+    if (n > KEEP) {
+        uint32_t k = 0;
+        for_each_candidate(g, T, axis, myD, [&](uint32_t f) {
+            if (k >= KEEP)
+                cand[first + k] = make_uint2(ray, f);
+            ++k;
+        });
+    }
 }
 
-__global__ void classify_overflow_finish_kernel(const uint32_t *__restrict__ list, uint32_t nList,
-    const uint8_t *__restrict__ axisOut, uint8_t *__restrict__ inside, uint8_t *__restrict__ perAxis)
+// ---- B ------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ray_hit_kernel(Query q, Target T, const double *__restrict__ qpt,
+    const uint2 *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ candCount,
+    uint32_t nTargetTris, long long *__restrict__ keys /* 3 per candidate */, uint8_t *__restrict__ hitFlag)
 {
-    uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= nList)
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = min(__ldg(candCount), cap);
+    if (i >= total)
         return;
-    uint32_t id = list[li];
-    int c = axisOut[3 * li] + axisOut[3 * li + 1] + axisOut[3 * li + 2];
-    inside[id] = c >= 2 ? 1 : 0;
-    if (perAxis)
-        for (int k = 0; k < 3; ++k)
-            perAxis[3 * (size_t)id + k] = axisOut[3 * li + k];
+    const uint2 c = __ldg(cand + i);
+    // when the list overflowed (the host will retry) some entries below cap were never written
+    if (c.x >= 3u * q.count || c.y >= nTargetTris)
+        return;
+    const int axis = (int)(c.x / q.count);
+    const uint32_t j = c.x % q.count;
+    const double *src = q.pts ? q.pts + 3 * (size_t)(q.begin + j) : qpt + 3 * (size_t)j;
+    const d3 p = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+    const d3 e = ray_end(p, axis);
+    const uint32_t f = c.y;
+    d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
+    d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
+    d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
+    d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
+    d3 hit;
+    const bool h = ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit);
+    hitFlag[i] = h ? 1 : 0;
+    if (h) {
+        keys[3 * i] = position_key(hit.x);
+        keys[3 * i + 1] = position_key(hit.y);
+        keys[3 * i + 2] = position_key(hit.z);
+    }
+}
+
+// ---- C ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ray_finish_kernel(Query q, const uint2 *__restrict__ rayRange,
+    unsigned long long cap, const long long *__restrict__ keys, const uint8_t *__restrict__ hitFlag,
+    uint8_t *__restrict__ inside, uint8_t *__restrict__ perAxis)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= q.count)
+        return;
+    uint32_t outIndex;
+    if (q.pts) {
+        outIndex = q.begin + j;
+    } else {
+        int t = load_rec(q.leaf + q.begin + j).ref;
+        if (t < 0)
+            return;
+        outIndex = (uint32_t)t;
+    }
+    int insideCount = 0;
+    for (int axis = 0; axis < 3; ++axis) {
+        const uint2 r = __ldg(rayRange + (size_t)axis * q.count + j);
+        uint32_t distinct = 0;
+        if ((unsigned long long)r.x + r.y <= cap) {
+            for (uint32_t a = 0; a < r.y; ++a) {
+                const size_t ia = (size_t)r.x + a;
+                if (!hitFlag[ia])
+                    continue;
+                const long long kx = keys[3 * ia], ky = keys[3 * ia + 1], kz = keys[3 * ia + 2];
+                bool dup = false; // std::set<PositionKey>: equal keys count once
+                for (uint32_t b = 0; b < a && !dup; ++b) {
+                    const size_t ib = (size_t)r.x + b;
+                    dup = hitFlag[ib] && keys[3 * ib] == kx && keys[3 * ib + 1] == ky && keys[3 * ib + 2] == kz;
+                }
+                distinct += dup ? 0u : 1u;
+            }
+        }
+        const bool in = (distinct & 1u) != 0;
+        if (perAxis)
+            perAxis[3 * (size_t)outIndex + axis] = in ? 1 : 0;
+        insideCount += in ? 1 : 0;
+    }
+    // (float)insideCount / totalCount > 0.5 with totalCount == 3
+    inside[outIndex] = insideCount >= 2 ? 1 : 0;
 }
 
 } // namespace
 
-cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, int *errFlag, LaunchCounter &lc)
+size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, bool facesMode)
 {
-    (void)errFlag;
+    size_t b = 0;
+    b += ((size_t)cap * 8 + 255) & ~(size_t)255;      // cand
+    b += ((size_t)cap * 24 + 255) & ~(size_t)255;     // keys
+    b += ((size_t)cap + 255) & ~(size_t)255;          // hit flags
+    b += ((size_t)points * 3 * 8 + 255) & ~(size_t)255; // rayRange
+    if (facesMode)
+        b += ((size_t)points * 24 + 255) & ~(size_t)255; // qpt
+    return b + 256;
+}
+
+cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, void *scratch,
+    unsigned long long cap, unsigned long long *candCount, LaunchCounter &lc)
+{
     if (a.end <= a.begin)
         return cudaSuccess;
-    uint32_t blocks = (a.end - a.begin + THREADS - 1) / THREADS;
-    const MeshDev *q = a.queryMesh;
+    const MeshDev *qm = a.queryMesh;
+    Query q;
+    q.pts = a.pts;
+    q.leaf = qm ? qm->leaf : nullptr;
+    q.vtx = qm ? qm->vtx : nullptr;
+    q.tri = qm ? qm->tri : nullptr;
+    q.begin = a.begin;
+    q.count = a.end - a.begin;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;
     T.refs = target.gridRefs;
     T.bigRefs = target.gridBigRefs;
     T.bigCap = target.gridBigCap;
-    for (int k = 0; k < 3; ++k)
-        T.bigN[k] = target.gridBigN[k];
+    T.bigN0 = target.gridBigN[0];
+    T.bigN1 = target.gridBigN[1];
+    T.bigN2 = target.gridBigN[2];
     T.tbox = target.tbox;
     T.vtx = target.vtx;
     T.tri = target.tri;
     T.normal = target.normal;
-    classify_kernel<<<blocks, THREADS, 0, s>>>(a.pts, q ? q->leaf : nullptr, q ? q->vtx : nullptr, q ? q->tri : nullptr,
-        a.begin, a.end, T, a.inside, a.perAxis, a.stats, a.overflowList, a.overflowCount, a.overflowCap);
-    lc.kernels += 1;
-    return cudaGetLastError();
-}
 
-cudaError_t sbk_classify_overflow(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, uint32_t nOverflow,
-    long long *scratch, uint32_t scratchKeysPerRay, int *errFlag, LaunchCounter &lc)
-{
-    if (nOverflow == 0)
-        return cudaSuccess;
-    const MeshDev *q = a.queryMesh;
-    uint8_t *axisOut = reinterpret_cast<uint8_t *>(scratch + (size_t)nOverflow * 3 * scratchKeysPerRay * 3);
-    uint32_t rays = nOverflow * 3;
-    classify_overflow_kernel<<<(rays + 127) / 128, 128, 0, s>>>(a.pts, q ? q->vtx : nullptr, q ? q->tri : nullptr,
-        a.overflowList, nOverflow, target.tbox, target.vtx, target.tri, target.normal, target.nT, scratch,
-        scratchKeysPerRay, axisOut, errFlag);
-    classify_overflow_finish_kernel<<<(nOverflow + 127) / 128, 128, 0, s>>>(a.overflowList, nOverflow, axisOut, a.inside,
-        a.perAxis);
-    lc.kernels += 2;
+    char *b = static_cast<char *>(scratch);
+    auto take = [&](size_t bytes) {
+        char *p = b;
+        b += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    uint2 *cand = reinterpret_cast<uint2 *>(take((size_t)cap * 8));
+    long long *keys = reinterpret_cast<long long *>(take((size_t)cap * 24));
+    uint8_t *hitFlag = reinterpret_cast<uint8_t *>(take((size_t)cap));
+    uint2 *rayRange = reinterpret_cast<uint2 *>(take((size_t)q.count * 3 * 8));
+    double *qpt = a.pts ? nullptr : reinterpret_cast<double *>(take((size_t)q.count * 24));
+
+    const uint32_t bpa = (q.count + SCAN_THREADS - 1) / SCAN_THREADS;
+    ray_scan_kernel<<<3 * bpa, SCAN_THREADS, 0, s>>>(q, T, bpa, qpt, cand, cap, candCount, rayRange);
+    const unsigned long long hitBlocks = (cap + 127) / 128;
+    ray_hit_kernel<<<(unsigned)hitBlocks, 128, 0, s>>>(q, T, qpt, cand, cap, candCount, target.nT, keys, hitFlag);
+    ray_finish_kernel<<<(q.count + 255) / 256, 256, 0, s>>>(q, rayRange, cap, keys, hitFlag, a.inside, a.perAxis);
+    lc.kernels += 3;
     return cudaGetLastError();
 }

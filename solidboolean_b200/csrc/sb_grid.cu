@@ -30,38 +30,47 @@ __device__ __forceinline__ uint32_t quant16(double x, double org, double scl)
     return (uint32_t)t;
 }
 
-__global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds, int cellBits, GridParams *out)
+// Cell size = beta x mean triangle-box extent along each world axis, so a
+// triangle covers about (1 + 1/beta)^2 cells on every grid whatever the mesh's
+// aspect ratio or anisotropy; resolutions are powers of two so that a cell index
+// is a shift of the 16-bit coordinate.  maxBits bounds cells per axis (allocation).
+__global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds, const float *__restrict__ extentSum,
+    uint32_t nT, int maxBits, float beta, GridParams *out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
     GridParams g;
-    double ext[3];
+    int bitsWanted[3];
     for (int d = 0; d < 3; ++d) {
         double lo = dkey_inv(bounds[d]), hi = dkey_inv(bounds[3 + d]);
-        ext[d] = hi - lo;
+        double ext = hi - lo;
         g.org[d] = lo;
         // hi maps to 65535.99..; finite and > 0 extents only
-        g.scl[d] = (ext[d] > 0.0 && ext[d] < 1.0e300) ? 65535.999 / ext[d] : 0.0;
+        g.scl[d] = (ext > 0.0 && ext < 1.0e300) ? 65535.999 / ext : 0.0;
         g.lo[d] = lo;
         g.hi[d] = hi;
+        double mean = nT ? (double)extentSum[d] / (double)nT : 0.0;
+        double cells = (ext > 0.0 && mean > 0.0) ? ext / ((double)beta * mean) : 1.0;
+        int b = (int)floor(log2(fmax(cells, 1.0)) + 0.5);
+        bitsWanted[d] = max(0, min(b, 16));
     }
+    uint32_t base = 0;
     for (int a = 0; a < 3; ++a) {
         int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
-        // split cellBits between u and v so that cells come out roughly square
-        double ratio = (ext[u] > 0.0 && ext[v] > 0.0) ? log2(ext[u] / ext[v]) : 0.0;
-        int ku = (int)floor(0.5 * ((double)cellBits + ratio) + 0.5);
-        ku = max(0, min(ku, min(cellBits, 16)));
-        int kv = cellBits - ku;
-        if (kv > 16) {
-            kv = 16;
-            ku = min(16, cellBits - kv);
+        int ku = bitsWanted[u], kv = bitsWanted[v];
+        while (ku + kv > maxBits) { // shrink the finer dimension first
+            if (ku >= kv && ku > 0) --ku;
+            else if (kv > 0) --kv;
+            else break;
         }
         g.shiftU[a] = 16 - ku;
         g.shiftV[a] = 16 - kv;
         g.nu[a] = 1u << ku;
-        g.cellBase[a] = (uint32_t)a << cellBits; // ku + kv <= cellBits cells per axis
+        g.cellBase[a] = base;
+        base += 1u << (ku + kv);
     }
-    g.totalCells = 3u << cellBits;
+    g.totalCells = base;
+    g.pad = 0;
     *out = g;
 }
 
@@ -133,9 +142,13 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_PREFIX = 2ull << 62, SCAN_MASK = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *__restrict__ data, uint32_t n,
-    volatile unsigned long long *status, uint32_t *__restrict__ tileCounter)
+__global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *__restrict__ data,
+    const GridParams *__restrict__ gp, volatile unsigned long long *status, uint32_t *__restrict__ tileCounter,
+    uint32_t *__restrict__ totalOut)
 {
+    const uint32_t n = gp->totalCells + 1; // E[0 .. totalCells]
+    if ((unsigned long long)blockIdx.x * SCAN_TILE >= n)
+        return; // launched for the allocation bound; only the first ceil(n / TILE) CTAs take a ticket
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ unsigned long long s_excl;
@@ -196,50 +209,52 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
     const uint32_t off = (uint32_t)s_excl + warpOff + incl - sum;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < n)
+        if (base + i < n) {
             data[base + i] = off + v[i];
+            if (base + i == n - 1) { // E[totalCells] = number of references
+                data[n] = off + v[i]; // E[totalCells + 1]: end of the last cell after the fill
+                *totalOut = off + v[i];
+            }
+        }
 }
 
 } // namespace
 
-size_t sbk_grid_scan_status_words(uint32_t totalCells)
+size_t sbk_grid_scan_status_words(uint32_t maxCells)
 {
-    size_t tiles = ((size_t)totalCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    size_t tiles = ((size_t)maxCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
     return 2 * tiles + 4; // u64 status per tile + the tile counter
 }
 
 // Phase 1: parameters, per-cell counts, inclusive scan.  Afterwards
-// E[c + 1] = end of cell c and E[totalCells] = total number of references.
-cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc)
+// E[c + 1] = end of cell c and gridBigCount[6] = total number of references.
+cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc)
 {
     if (m.nT == 0)
         return cudaSuccess;
-    const uint32_t totalCells = 3u << m.gridCellBits;
-    cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)totalCells + 2), s);
+    const uint32_t maxCells = 3u << m.gridCellBits;
+    cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)maxCells + 2), s);
     cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
-    size_t statusWords = sbk_grid_scan_status_words(totalCells);
+    size_t statusWords = sbk_grid_scan_status_words(maxCells);
     cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * statusWords, s);
-    grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, (int)m.gridCellBits, m.gridParams);
+    grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, m.extentSum, m.nT, (int)m.gridCellBits, beta, m.gridParams);
     grid_bin_kernel<false><<<(m.nT + 255) / 256, 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, nullptr, nullptr,
         m.gridBigCount, 0);
-    uint32_t n = totalCells + 1;
-    uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t tiles = (maxCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
     unsigned long long *status = reinterpret_cast<unsigned long long *>(scanScratch);
     uint32_t *counter = scanScratch + statusWords - 2;
-    inclusive_scan_kernel<<<tiles, SCAN_THREADS, 0, s>>>(m.gridE, n, status, counter);
+    inclusive_scan_kernel<<<tiles, SCAN_THREADS, 0, s>>>(m.gridE, m.gridParams, status, counter, m.gridBigCount + 6);
     lc.kernels += 3;
     return cudaGetLastError();
 }
 
-// Phase 2 (after the caller sized refs / bigRefs from the counts).
+// Phase 2 (after the caller sized refs / bigRefs from the counts): every
+// E[c + 1] turns from the END of cell c into its START as the cell is filled
+// back to front; E[totalCells + 1] (written by the scan) closes the last cell.
 cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
 {
     if (m.nT == 0)
         return cudaSuccess;
-    const uint32_t totalCells = 3u << m.gridCellBits;
-    // E[totalCells + 1] = total (end of the last cell once the fill has turned
-    // every E[c + 1] into the START of cell c)
-    cudaMemcpyAsync(m.gridE + totalCells + 1, m.gridE + totalCells, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
     grid_bin_kernel<true><<<(m.nT + 255) / 256, 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, m.gridRefs,
         m.gridBigRefs, m.gridBigCount, m.gridBigCap);
     lc.kernels += 1;

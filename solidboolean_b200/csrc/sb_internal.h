@@ -49,12 +49,13 @@ struct MeshDev {
     int *root = nullptr;                // device scalar
     int *err = nullptr;                 // device scalar: 1 = triangle index out of range
     // ray grids
-    uint32_t gridCellBits = 0;          // 2^bits cells per axis
+    float *extentSum = nullptr;         // 3 floats: sum of triangle-box extents per world axis
+    uint32_t gridCellBits = 0;          // at most 2^bits cells per axis (allocation bound)
     GridParams *gridParams = nullptr;
     uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
     uint4 *gridRefs = nullptr;          // {qlo_u|qhi_u<<16, qlo_v|qhi_v<<16, qhi_a|qlo_a<<16, triangle id}
     uint4 *gridBigRefs = nullptr;       // 3 * gridBigCap: triangles covering too many cells
-    uint32_t *gridBigCount = nullptr;   // [0..2] counts (count pass), [3..5] fill cursors
+    uint32_t *gridBigCount = nullptr;   // [0..2] counts (count pass), [3..5] fill cursors, [6] total refs
     uint32_t gridBigCap = 0;
     uint32_t gridBigN[3] = {0, 0, 0};   // host copy of the big-list lengths
 };
@@ -94,20 +95,18 @@ struct ClassifyArgs {
     uint32_t begin = 0, end = 0; // point range (explicit) or sorted-position range (faces)
     uint8_t *inside = nullptr;   // indexed by point index / original triangle id
     uint8_t *perAxis = nullptr;  // optional, 3 per point
-    unsigned long long *stats = nullptr; // [0] rays, [1] candidates
-    uint32_t *overflowList = nullptr;    // point indices whose hit list overflowed
-    unsigned int *overflowCount = nullptr;
-    uint32_t overflowCap = 0;
 };
-cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, int *errFlag, LaunchCounter &lc);
-// exact slow path for the points in overflowList (one thread per ray, brute force
-// over the target's triangles, hit keys kept in `scratch`)
-cudaError_t sbk_classify_overflow(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, uint32_t nOverflow,
-    long long *scratch, uint32_t scratchKeysPerRay, int *errFlag, LaunchCounter &lc);
+// scratch: sbk_classify_scratch_bytes(points, cap, facesMode) bytes; cap = capacity of
+// the candidate list; *candCount (device, zeroed by the caller) receives the number
+// of ray/triangle candidates -- if it exceeds cap the results are invalid and the
+// call must be repeated with a larger cap.
+size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, bool facesMode);
+cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, void *scratch,
+    unsigned long long cap, unsigned long long *candCount, LaunchCounter &lc);
 
 size_t sbk_radix_workspace_words(size_t n);
 
 // sb_grid.cu
-size_t sbk_grid_scan_status_words(uint32_t totalCells);
-cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc);
+size_t sbk_grid_scan_status_words(uint32_t maxCells);
+cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc);
 cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
