@@ -45,7 +45,7 @@ UNIT = "pairs/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -322,6 +322,10 @@ def run_ours(args):
         return P, H
 
     def timed_loop(step_fn, steps, warmup, device_timed):
+        # the sampler runs from the warm-up on (the GPU is under the same load there),
+        # so that even a ~50 ms timed region is covered by 100 ms nvidia-smi samples
+        sampler = ClockSampler(local)
+        sampler.start()
         for _ in range(warmup):
             res = step_fn()
         torch.cuda.synchronize()
@@ -330,8 +334,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         total_ms = 0.0
-        sampler = ClockSampler(local)
-        sampler.start()
         for _ in range(steps):
             with torch.cuda.stream(ext):
                 l2_flush.zero_()          # evict L2 between timed iterations (untimed)
