@@ -70,6 +70,7 @@ __device__ __forceinline__ uint32_t expand10(uint32_t v)
     return v;
 }
 
+// 10 bits per axis -> 30-bit Morton key = four 8-bit radix passes
 __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 {
     float f = (float)((c - lo) * inv) * 1024.0f;
@@ -79,8 +80,8 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 
 __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double2 *__restrict__ tbox,
-    double *__restrict__ normal, uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
-    float *__restrict__ extentSum)
+    double *__restrict__ normal, double *__restrict__ cent, uint32_t *__restrict__ mkey, uint32_t *__restrict__ order,
+    int *__restrict__ err, float *__restrict__ extentSum)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float sx = 0.0f, sy = 0.0f, sz = 0.0f; // this triangle's box extents
@@ -117,6 +118,11 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     normal[3 * (size_t)i] = n.x;
     normal[3 * (size_t)i + 1] = n.y;
     normal[3 * (size_t)i + 2] = n.z;
+    // face centroid exactly as decideGroupSide forms its query point:
+    // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
+    cent[3 * (size_t)i] = xdiv(xadd(xadd(a.x, b.x), c.x), 3.0);
+    cent[3 * (size_t)i + 1] = xdiv(xadd(xadd(a.y, b.y), c.y), 3.0);
+    cent[3 * (size_t)i + 2] = xdiv(xadd(xadd(a.z, b.z), c.z), 3.0);
 
     // 30-bit Morton key of the box centre inside the mesh box (ordering only)
     double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
@@ -132,24 +138,35 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     if (!(sy >= 0.0f && sy < 1e30f)) sy = 0.0f;
     if (!(sz >= 0.0f && sz < 1e30f)) sz = 0.0f;
     }
-    // mean triangle-box extent per axis (sizes the ray grids): one atomic per warp
+    // mean triangle-box extent per axis (sizes the ray grids): CTA reduction, then
+    // three atomics per CTA spread over 32 slots (same-address atomics serialise)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         sx += __shfl_xor_sync(SB_FULL, sx, off);
         sy += __shfl_xor_sync(SB_FULL, sy, off);
         sz += __shfl_xor_sync(SB_FULL, sz, off);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(extentSum, sx);
-        atomicAdd(extentSum + 1, sy);
-        atomicAdd(extentSum + 2, sz);
+    __shared__ float s_ext[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_ext[warp][0] = sx;
+        s_ext[warp][1] = sy;
+        s_ext[warp][2] = sz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w)
+            t += s_ext[w][threadIdx.x];
+        atomicAdd(extentSum + 3 * (blockIdx.x & 31) + threadIdx.x, t);
     }
 }
 
 // ---- K1b --------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__restrict__ sortedTri,
-    const uint32_t *__restrict__ sortedKey, const double2 *__restrict__ tbox, uint32_t nT, uint32_t nTpad,
-    Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey)
+    const uint32_t *__restrict__ sortedKey, const double2 *__restrict__ tbox, const double *__restrict__ cent,
+    uint32_t nT, uint32_t nTpad, Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, double *__restrict__ scent,
+    Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey)
 {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nTpad) // nTpad is a multiple of 32: whole warps leave together
@@ -162,6 +179,9 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
         bd = load_boxd(tbox + 3 * (size_t)t);
         bf = enclose(bd);
         ref = (int)t;
+        scent[3 * (size_t)j] = __ldg(cent + 3 * (size_t)t);
+        scent[3 * (size_t)j + 1] = __ldg(cent + 3 * (size_t)t + 1);
+        scent[3 * (size_t)j + 2] = __ldg(cent + 3 * (size_t)t + 2);
     }
     store_boxd(sbox + 3 * (size_t)j, bd);
     store_rec(leaf + j, bf, ref, (int)j);
@@ -247,24 +267,24 @@ cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t
     // bounds seeds: min slots all-ones, max slots zero (order-encoded doubles)
     cudaMemsetAsync(m.bounds, 0xff, 3 * sizeof(unsigned long long), s);
     cudaMemsetAsync(m.bounds + 3, 0x00, 3 * sizeof(unsigned long long), s);
-    cudaMemsetAsync(m.extentSum, 0, 4 * sizeof(float), s);
+    cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(float), s);
     int vb = (int)((m.nV + 255) / 256);
     if (vb > smCount * 8)
         vb = smCount * 8;
     if (vb < 1)
         vb = 1;
     bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds);
-    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.tbox, m.normal, m.mkey,
-        m.order, m.err, m.extentSum);
+    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.tbox, m.normal, m.cent, m.mkey, m.order,
+        m.err, m.extentSum);
     lc.kernels += 2;
     sbradix::Workspace ws;
     ws.mem = radixWs;
     uint32_t *sk = nullptr, *sv = nullptr;
-    lc.kernels += sbradix::sort<uint32_t>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, 0, 30, ws, smCount, &sk, &sv);
+    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, 0, 30, ws, smCount, &sk, &sv);
     m.sortedKey = sk;
     m.sortedTri = sv;
-    leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.tbox, m.nT, m.nTpad, m.leaf,
-        m.sbox, m.cbox, m.ckey);
+    leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.tbox, m.cent, m.nT, m.nTpad,
+        m.leaf, m.sbox, m.scent, m.cbox, m.ckey);
     lc.kernels += 1;
     if (m.M > 1)
         cudaMemsetAsync(m.slot, 0xff, sizeof(int) * (m.M - 1), s);

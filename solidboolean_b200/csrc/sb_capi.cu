@@ -243,7 +243,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
         return o;
     };
     size_t oXyz = take(24 * nV), oTri = take(12 * nT), oVtx = take(32 * nV), oBounds = take(48);
-    size_t oTbox = take(48 * nT), oNormal = take(24 * nT);
+    size_t oTbox = take(48 * nT), oNormal = take(24 * nT), oCent = take(24 * nT), oScent = take(24 * (size_t)((nT + 31) / 32 * 32));
     size_t oKey = take(4 * nT), oKeyT = take(4 * nT), oOrd = take(4 * nT), oOrdT = take(4 * nT);
     size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad);
     size_t oCbox = take(32 * (size_t)d.M), oCkey = take(4 * (size_t)d.M + 4);
@@ -255,7 +255,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
         int bits = (int)std::floor(lg + 0.5);
         d.gridCellBits = (uint32_t)std::max(0, std::min(bits, 26));
     }
-    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(48);
+    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32 + 96 * 4);
     // stream-ordered allocation: the pool keeps the block cached between calls
     cudaError_t e = cudaMallocAsync(&m->arena, off, ctx->stream);
     if (e != cudaSuccess) {
@@ -270,6 +270,8 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.bounds = (unsigned long long *)(b + oBounds);
     d.tbox = (double2 *)(b + oTbox);
     d.normal = (double *)(b + oNormal);
+    d.cent = (double *)(b + oCent);
+    d.scent = (double *)(b + oScent);
     d.mkey = (uint32_t *)(b + oKey);
     d.mkeyTmp = (uint32_t *)(b + oKeyT);
     d.order = (uint32_t *)(b + oOrd);
@@ -505,6 +507,7 @@ int sb_mesh_build(sb_mesh *m)
             m->gridArenaBytes = bytes;
         }
         m->d.gridRefs = static_cast<uint4 *>(m->gridArena);
+        m->d.gridRefCap = (uint32_t)std::max<size_t>(nRefs, 1);
         m->d.gridBigRefs = m->d.gridRefs + std::max<size_t>(nRefs, 1);
         m->d.gridBigCap = std::max<uint32_t>(bigMax, 1);
         StageTimer t(c, SB_STAGE_BUILD);
@@ -622,7 +625,7 @@ int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
     if (r)
         return r;
     uint32_t cnt[8];
-    float ext[4];
+    float ext[96];
     r = mesh_download(m, cnt, m->d.gridBigCount, sizeof(cnt));
     if (!r)
         r = mesh_download(m, ext, m->d.extentSum, sizeof(ext));
@@ -632,7 +635,10 @@ int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
         out->nu[a] = g.nu[a];
         out->nv[a] = 1u << (16 - g.shiftV[a]);
         out->big[a] = cnt[a];
-        out->mean_extent[a] = ext[a] / (float)m->d.nT;
+        float sum = 0.0f;
+        for (int k = 0; k < 32; ++k)
+            sum += ext[3 * k + a];
+        out->mean_extent[a] = sum / (float)m->d.nT;
     }
     out->total_cells = g.totalCells;
     out->total_refs = cnt[6];
@@ -915,14 +921,14 @@ static int classify_run(sb_context *c, const sb_mesh *target, ClassifyArgs a)
         SB_CUDA(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
         {
             StageTimer t(c, SB_STAGE_CLASSIFY);
-            SB_CUDA(sbk_classify(c->stream, target->d, a, scratch, cap, &c->dScalars->stats[1], c->lc));
+            SB_CUDA(sbk_classify(c->stream, target->d, a, scratch, cap, &c->dScalars->stats[1], &c->dScalars->stats[0], c->lc));
         }
         SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA(cudaStreamSynchronize(c->stream));
         cudaFreeAsync(scratch, c->stream);
-        const unsigned long long cands = c->hScalars->stats[1];
+        const unsigned long long cands = c->hScalars->stats[1]; // list entries (quantised matches)
         c->lastRays = rays;
-        c->lastCands = cands;
+        c->lastCands = c->hScalars->stats[0];                   // exact candidates
         if (rays)
             c->candPerRayHint = std::max(0.25, 1.25 * (double)cands / (double)rays);
         if (cands <= cap)

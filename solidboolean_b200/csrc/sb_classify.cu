@@ -7,13 +7,14 @@
 //  A  ray_scan_kernel    one thread per RAY (point x axis; a CTA = 256
 //     neighbouring points of one axis, so its threads read neighbouring grid
 //     cells).  Ray box exactly as :53-58; the ray's cell list of the target's
-//     axis-projected grid (sb_grid.cu): quantised 16-byte references first, then
-//     the EXACT double box test that defines the reference's candidate set
-//     (:55-63).  Candidates are counted, a warp scan reserves one contiguous
-//     range of the global candidate list per warp (one atomic per warp), and
-//     every ray writes its (ray, triangle) entries ray-contiguously.
-//  B  ray_hit_kernel     one thread per CANDIDATE: segment/plane hit, the two
-//     edge-normal sign tests (sb_raytri.cuh, bit-exact), PositionKey of the hit.
+//     axis-projected grid (sb_grid.cu) is filtered with the quantised 16-byte
+//     references -- integer work only, which over-accepts slightly.  A warp scan
+//     reserves one contiguous range of the global list per warp (one atomic per
+//     warp) and every ray writes its (ray, triangle) entries ray-contiguously.
+//  B  ray_hit_kernel     one thread per list entry, dense: first the EXACT
+//     double box test that defines the reference's candidate set (ray box against
+//     triangle boxes, :55-63), then segment/plane hit and the two edge-normal sign
+//     tests (sb_raytri.cuh, bit-exact), PositionKey of the hit.
 //  C  ray_finish_kernel  one thread per point: per axis, count the DISTINCT hit
 //     keys (std::set<PositionKey>, :64/:85), odd = inside (:89); majority of the
 //     three axes ((float)insideCount / totalCount > 0.5, :508).
@@ -67,16 +68,17 @@ struct Target {
 };
 
 struct Query {
-    const double *pts;  // explicit points (AoS), or null
-    const Rec32 *leaf;  // faces mode: query mesh leaves ...
-    const double4 *vtx; // ... its vertices
-    const uint32_t *tri;
-    uint32_t begin;     // first point / sorted position
-    uint32_t count;     // points in this launch
+    const double *pts;   // explicit points (AoS), or null
+    const double *scent; // faces mode: query mesh centroids in Morton order ...
+    const Rec32 *leaf;   // ... and its leaves (sorted position -> triangle id)
+    uint32_t nT;
+    uint32_t begin;      // first point / sorted position
+    uint32_t count;      // points in this launch
 };
 
-// Walk the ray's candidates in a fixed order; visit(triangle id) for each
-// triangle whose EXACT box overlaps the ray box.
+// Walk the ray's cell list(s) in a fixed order; visit(triangle id) for each
+// triangle whose QUANTISED box overlaps the quantised ray box (a superset of the
+// reference's candidates; ray_hit_kernel applies the exact test).
 template <typename Visit>
 __device__ __forceinline__ void for_each_candidate(const GridParams &g, const Target &T, int axis, const BoxD &myD,
     Visit &&visit)
@@ -95,12 +97,12 @@ __device__ __forceinline__ void for_each_candidate(const GridParams &g, const Ta
         if ((r.x & 0xffffu) > bU || (r.x >> 16) < aU || (r.y & 0xffffu) > bV || (r.y >> 16) < aV ||
             (r.z & 0xffffu) < aA)
             return;
-        BoxD bd = load_boxd(T.tbox + 3 * (size_t)r.w);
-        if (overlap_d(bd, myD)) // the reference's candidate test, exact
-            visit(r.w);
+        visit(r.w);
     };
     const int su = g.shiftU[axis], sv = g.shiftV[axis];
     const uint32_t cu0 = aU >> su, cu1 = bU >> su, cv0 = aV >> sv, cv1 = bV >> sv;
+    // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell
+    const bool multi = cu0 != cu1 || cv0 != cv1;
     for (uint32_t cv = cv0; cv <= cv1; ++cv)
         for (uint32_t cu = cu0; cu <= cu1; ++cu) {
             const uint32_t cell = g.cellBase[axis] + cv * g.nu[axis] + cu;
@@ -108,7 +110,7 @@ __device__ __forceinline__ void for_each_candidate(const GridParams &g, const Ta
             // four independent 16-byte loads in flight per thread
             auto take = [&](const uint4 &r, uint32_t i) {
                 // a triangle spanning several of the ray's cells is taken in the first one only
-                if (i < i1 && max((r.x & 0xffffu) >> su, cu0) == cu && max((r.y & 0xffffu) >> sv, cv0) == cv)
+                if (i < i1 && (!multi || (max((r.x & 0xffffu) >> su, cu0) == cu && max((r.y & 0xffffu) >> sv, cv0) == cv)))
                     consider(r);
             };
             for (uint32_t i = i0; i < i1; i += 4) {
@@ -137,22 +139,18 @@ __device__ __forceinline__ bool query_point(const Query &q, uint32_t j, d3 &p, u
         outIndex = idx;
         return true;
     }
-    int t = load_rec(q.leaf + idx).ref;
-    if (t < 0)
-        return false; // padding leaf
-    outIndex = (uint32_t)t;
-    d3 a = load_vertex(q.vtx, __ldg(q.tri + 3 * (size_t)t));
-    d3 b = load_vertex(q.vtx, __ldg(q.tri + 3 * (size_t)t + 1));
-    d3 c = load_vertex(q.vtx, __ldg(q.tri + 3 * (size_t)t + 2));
-    // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
-    p = {xdiv(xadd(xadd(a.x, b.x), c.x), 3.0), xdiv(xadd(xadd(a.y, b.y), c.y), 3.0),
-         xdiv(xadd(xadd(a.z, b.z), c.z), 3.0)};
+    // faces mode: the centroids ((v0 + v1) + v2) / 3.0 (src/solidboolean.cpp:497-499) were
+    // formed at build time and stored in Morton order; positions >= nT are padding
+    if (idx >= q.nT)
+        return false;
+    outIndex = idx;
+    p = {__ldg(q.scent + 3 * (size_t)idx), __ldg(q.scent + 3 * (size_t)idx + 1), __ldg(q.scent + 3 * (size_t)idx + 2)};
     return true;
 }
 
 // ---- A ------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) ray_scan_kernel(Query q, Target T, uint32_t blocksPerAxis,
-    double *__restrict__ qpt, uint2 *__restrict__ cand, unsigned long long cap,
+    uint2 *__restrict__ cand, unsigned long long cap,
     unsigned long long *__restrict__ candCount, uint2 *__restrict__ rayRange)
 {
     __shared__ GridParams g;
@@ -166,11 +164,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) ray_scan_kernel(Query q, Target 
     d3 p = {0, 0, 0};
     uint32_t outIndex = 0;
     const bool active = query_point(q, j, p, outIndex);
-    if (active && axis == 0 && qpt) {
-        qpt[3 * (size_t)j] = p.x;
-        qpt[3 * (size_t)j + 1] = p.y;
-        qpt[3 * (size_t)j + 2] = p.z;
-    }
     const d3 e = ray_end(p, axis);
     const BoxD myD = ray_box(p, e);
 
@@ -220,37 +213,49 @@ __global__ void __launch_bounds__(SCAN_THREADS) ray_scan_kernel(Query q, Target 
 }
 
 // ---- B ------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ray_hit_kernel(Query q, Target T, const double *__restrict__ qpt,
+__global__ void __launch_bounds__(128) ray_hit_kernel(Query q, Target T,
     const uint2 *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ candCount,
-    uint32_t nTargetTris, long long *__restrict__ keys /* 3 per candidate */, uint8_t *__restrict__ hitFlag)
+    uint32_t nTargetTris, long long *__restrict__ keys /* 3 per entry */, uint8_t *__restrict__ hitFlag,
+    unsigned long long *__restrict__ exactCount)
 {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long total = min(__ldg(candCount), cap);
-    if (i >= total)
-        return;
-    const uint2 c = __ldg(cand + i);
-    // when the list overflowed (the host will retry) some entries below cap were never written
-    if (c.x >= 3u * q.count || c.y >= nTargetTris)
-        return;
-    const int axis = (int)(c.x / q.count);
-    const uint32_t j = c.x % q.count;
-    const double *src = q.pts ? q.pts + 3 * (size_t)(q.begin + j) : qpt + 3 * (size_t)j;
-    const d3 p = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
-    const d3 e = ray_end(p, axis);
-    const uint32_t f = c.y;
-    d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
-    d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
-    d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
-    d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
-    d3 hit;
-    const bool h = ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit);
-    hitFlag[i] = h ? 1 : 0;
-    if (h) {
-        keys[3 * i] = position_key(hit.x);
-        keys[3 * i + 1] = position_key(hit.y);
-        keys[3 * i + 2] = position_key(hit.z);
+    bool isCand = false, h = false;
+    d3 hit = {0, 0, 0};
+    if (i < total) {
+        const uint2 c = __ldg(cand + i);
+        // when the list overflowed (the host will retry) some entries below cap were never written
+        if (c.x < 3u * q.count && c.y < nTargetTris) {
+            const int axis = (int)(c.x / q.count);
+            const uint32_t j = c.x % q.count;
+            const double *src = (q.pts ? q.pts : q.scent) + 3 * (size_t)(q.begin + j);
+            const d3 p = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+            const d3 e = ray_end(p, axis);
+            const uint32_t f = c.y;
+            // the reference's candidate test: triangle box .intersectWith(ray box), exact doubles
+            isCand = overlap_d(load_boxd(T.tbox + 3 * (size_t)f), ray_box(p, e));
+            if (isCand) {
+                d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
+                d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
+                d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
+                d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1),
+                          __ldg(T.normal + 3 * (size_t)f + 2)};
+                h = ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit);
+            }
+        }
+        hitFlag[i] = h ? 1 : 0;
+        if (h) {
+            keys[3 * i] = position_key(hit.x);
+            keys[3 * i + 1] = position_key(hit.y);
+            keys[3 * i + 2] = position_key(hit.z);
+        }
     }
+    // exact candidate count (roofline accounting): one atomic per warp
+    const uint32_t m = __ballot_sync(SB_FULL, isCand);
+    if ((threadIdx.x & 31) == 0 && m)
+        atomicAdd(exactCount, (unsigned long long)__popc(m));
 }
+
 
 // ---- C ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ray_finish_kernel(Query q, const uint2 *__restrict__ rayRange,
@@ -264,27 +269,33 @@ __global__ void __launch_bounds__(256) ray_finish_kernel(Query q, const uint2 *_
     if (q.pts) {
         outIndex = q.begin + j;
     } else {
-        int t = load_rec(q.leaf + q.begin + j).ref;
-        if (t < 0)
+        if (q.begin + j >= q.nT)
             return;
-        outIndex = (uint32_t)t;
+        outIndex = (uint32_t)load_rec(q.leaf + q.begin + j).ref;
     }
     int insideCount = 0;
     for (int axis = 0; axis < 3; ++axis) {
         const uint2 r = __ldg(rayRange + (size_t)axis * q.count + j);
         uint32_t distinct = 0;
-        if ((unsigned long long)r.x + r.y <= cap) {
-            for (uint32_t a = 0; a < r.y; ++a) {
-                const size_t ia = (size_t)r.x + a;
-                if (!hitFlag[ia])
-                    continue;
-                const long long kx = keys[3 * ia], ky = keys[3 * ia + 1], kz = keys[3 * ia + 2];
-                bool dup = false; // std::set<PositionKey>: equal keys count once
-                for (uint32_t b = 0; b < a && !dup; ++b) {
-                    const size_t ib = (size_t)r.x + b;
-                    dup = hitFlag[ib] && keys[3 * ib] == kx && keys[3 * ib + 1] == ky && keys[3 * ib + 2] == kz;
+        if (r.y && (unsigned long long)r.x + r.y <= cap) {
+            uint32_t hits = 0;
+            for (uint32_t a = 0; a < r.y; ++a)
+                hits += hitFlag[(size_t)r.x + a];
+            distinct = hits;
+            if (hits > 1) { // std::set<PositionKey>: equal keys count once
+                distinct = 0;
+                for (uint32_t a = 0; a < r.y; ++a) {
+                    const size_t ia = (size_t)r.x + a;
+                    if (!hitFlag[ia])
+                        continue;
+                    const long long kx = keys[3 * ia], ky = keys[3 * ia + 1], kz = keys[3 * ia + 2];
+                    bool dup = false;
+                    for (uint32_t b = 0; b < a && !dup; ++b) {
+                        const size_t ib = (size_t)r.x + b;
+                        dup = hitFlag[ib] && keys[3 * ib] == kx && keys[3 * ib + 1] == ky && keys[3 * ib + 2] == kz;
+                    }
+                    distinct += dup ? 0u : 1u;
                 }
-                distinct += dup ? 0u : 1u;
             }
         }
         const bool in = (distinct & 1u) != 0;
@@ -305,22 +316,21 @@ size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, bool 
     b += ((size_t)cap * 24 + 255) & ~(size_t)255;     // keys
     b += ((size_t)cap + 255) & ~(size_t)255;          // hit flags
     b += ((size_t)points * 3 * 8 + 255) & ~(size_t)255; // rayRange
-    if (facesMode)
-        b += ((size_t)points * 24 + 255) & ~(size_t)255; // qpt
+    (void)facesMode;
     return b + 256;
 }
 
 cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, void *scratch,
-    unsigned long long cap, unsigned long long *candCount, LaunchCounter &lc)
+    unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount, LaunchCounter &lc)
 {
     if (a.end <= a.begin)
         return cudaSuccess;
     const MeshDev *qm = a.queryMesh;
     Query q;
     q.pts = a.pts;
+    q.scent = qm ? qm->scent : nullptr;
     q.leaf = qm ? qm->leaf : nullptr;
-    q.vtx = qm ? qm->vtx : nullptr;
-    q.tri = qm ? qm->tri : nullptr;
+    q.nT = qm ? qm->nT : 0;
     q.begin = a.begin;
     q.count = a.end - a.begin;
     Target T;
@@ -347,12 +357,11 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     long long *keys = reinterpret_cast<long long *>(take((size_t)cap * 24));
     uint8_t *hitFlag = reinterpret_cast<uint8_t *>(take((size_t)cap));
     uint2 *rayRange = reinterpret_cast<uint2 *>(take((size_t)q.count * 3 * 8));
-    double *qpt = a.pts ? nullptr : reinterpret_cast<double *>(take((size_t)q.count * 24));
 
     const uint32_t bpa = (q.count + SCAN_THREADS - 1) / SCAN_THREADS;
-    ray_scan_kernel<<<3 * bpa, SCAN_THREADS, 0, s>>>(q, T, bpa, qpt, cand, cap, candCount, rayRange);
+    ray_scan_kernel<<<3 * bpa, SCAN_THREADS, 0, s>>>(q, T, bpa, cand, cap, candCount, rayRange);
     const unsigned long long hitBlocks = (cap + 127) / 128;
-    ray_hit_kernel<<<(unsigned)hitBlocks, 128, 0, s>>>(q, T, qpt, cand, cap, candCount, target.nT, keys, hitFlag);
+    ray_hit_kernel<<<(unsigned)hitBlocks, 128, 0, s>>>(q, T, cand, cap, candCount, target.nT, keys, hitFlag, exactCount);
     ray_finish_kernel<<<(q.count + 255) / 256, 256, 0, s>>>(q, rayRange, cap, keys, hitFlag, a.inside, a.perAxis);
     lc.kernels += 3;
     return cudaGetLastError();

@@ -49,7 +49,10 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
         g.scl[d] = (ext > 0.0 && ext < 1.0e300) ? 65535.999 / ext : 0.0;
         g.lo[d] = lo;
         g.hi[d] = hi;
-        double mean = nT ? (double)extentSum[d] / (double)nT : 0.0;
+        double sum = 0.0;
+        for (int k = 0; k < 32; ++k)
+            sum += (double)extentSum[3 * k + d];
+        double mean = nT ? sum / (double)nT : 0.0;
         double cells = (ext > 0.0 && mean > 0.0) ? ext / ((double)beta * mean) : 1.0;
         int b = (int)floor(log2(fmax(cells, 1.0)) + 0.5);
         bitsWanted[d] = max(0, min(b, 16));
@@ -87,52 +90,55 @@ __device__ __forceinline__ TriCells quantise_box(const BoxD &b, const GridParams
     return t;
 }
 
+// One thread per (triangle, axis): three times the parallelism and a third of the
+// serial atomic chain of a per-triangle loop.  Triangles are visited in Morton
+// order, so neighbouring threads update neighbouring cells.
 template <bool FILL>
 __global__ void __launch_bounds__(256) grid_bin_kernel(const double2 *__restrict__ sbox, const Rec32 *__restrict__ leaf,
     uint32_t nT, const GridParams *__restrict__ gp, uint32_t *__restrict__ E, uint4 *__restrict__ refs,
-    uint4 *__restrict__ bigRefs, uint32_t *__restrict__ bigCount, uint32_t bigCap)
+    uint32_t refCap, uint4 *__restrict__ bigRefs, uint32_t *__restrict__ bigCount, uint32_t bigCap)
 {
     __shared__ GridParams g;
     if (threadIdx.x == 0)
         g = *gp;
     __syncthreads();
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t blocksPerAxis = (nT + 255) / 256;
+    const int a = blockIdx.x / blocksPerAxis;
+    const uint32_t j = (blockIdx.x % blocksPerAxis) * 256 + threadIdx.x;
     if (j >= nT)
         return;
     BoxD b = load_boxd(sbox + 3 * (size_t)j);
     TriCells t = quantise_box(b, g);
-    uint32_t tri = FILL ? (uint32_t)load_rec(leaf + j).ref : 0u;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
-        const uint32_t cu0 = t.qlo[u] >> g.shiftU[a], cu1 = t.qhi[u] >> g.shiftU[a];
-        const uint32_t cv0 = t.qlo[v] >> g.shiftV[a], cv1 = t.qhi[v] >> g.shiftV[a];
-        const uint32_t ncell = (cu1 - cu0 + 1) * (cv1 - cv0 + 1);
-        uint4 rec;
-        if (FILL) {
-            rec.x = t.qlo[u] | (t.qhi[u] << 16);
-            rec.y = t.qlo[v] | (t.qhi[v] << 16);
-            rec.z = t.qhi[a] | (t.qlo[a] << 16);
-            rec.w = tri;
-        }
-        if (ncell > MAX_CELLS_PER_TRI) {
-            uint32_t slot = atomicAdd(&bigCount[FILL ? 3 + a : a], 1u);
-            if (FILL && slot < bigCap)
-                bigRefs[(size_t)a * bigCap + slot] = rec;
-            continue;
-        }
-        const uint32_t base = g.cellBase[a];
-        for (uint32_t cv = cv0; cv <= cv1; ++cv)
-            for (uint32_t cu = cu0; cu <= cu1; ++cu) {
-                uint32_t cell = base + cv * g.nu[a] + cu;
-                if (FILL) {
-                    uint32_t pos = atomicSub(&E[cell + 1], 1u) - 1u; // fill each cell back to front
-                    refs[pos] = rec;
-                } else {
-                    atomicAdd(&E[cell + 1], 1u);
-                }
-            }
+    const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+    const uint32_t qlu = t.qlo[u], qhu = t.qhi[u], qlv = t.qlo[v], qhv = t.qhi[v];
+    const uint32_t cu0 = qlu >> g.shiftU[a], cu1 = qhu >> g.shiftU[a];
+    const uint32_t cv0 = qlv >> g.shiftV[a], cv1 = qhv >> g.shiftV[a];
+    const uint32_t ncell = (cu1 - cu0 + 1) * (cv1 - cv0 + 1);
+    uint4 rec = make_uint4(0, 0, 0, 0);
+    if (FILL) {
+        rec.x = qlu | (qhu << 16);
+        rec.y = qlv | (qhv << 16);
+        rec.z = t.qhi[a] | (t.qlo[a] << 16);
+        rec.w = (uint32_t)load_rec(leaf + j).ref;
     }
+    if (ncell > MAX_CELLS_PER_TRI) {
+        uint32_t slot = atomicAdd(&bigCount[FILL ? 3 + a : a], 1u);
+        if (FILL && slot < bigCap)
+            bigRefs[(size_t)a * bigCap + slot] = rec;
+        return;
+    }
+    const uint32_t base = g.cellBase[a], nu = g.nu[a];
+    for (uint32_t cv = cv0; cv <= cv1; ++cv)
+        for (uint32_t cu = cu0; cu <= cu1; ++cu) {
+            uint32_t cell = base + cv * nu + cu;
+            if (FILL) {
+                uint32_t pos = atomicSub(&E[cell + 1], 1u) - 1u; // fill each cell back to front
+                if (pos < refCap)
+                    refs[pos] = rec;
+            } else {
+                atomicAdd(&E[cell + 1], 1u);
+            }
+        }
 }
 
 // In-place inclusive scan of a u32 array (single pass, chained tiles with
@@ -238,8 +244,8 @@ cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, fl
     size_t statusWords = sbk_grid_scan_status_words(maxCells);
     cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * statusWords, s);
     grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, m.extentSum, m.nT, (int)m.gridCellBits, beta, m.gridParams);
-    grid_bin_kernel<false><<<(m.nT + 255) / 256, 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, nullptr, nullptr,
-        m.gridBigCount, 0);
+    grid_bin_kernel<false><<<3 * ((m.nT + 255) / 256), 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, nullptr, 0,
+        nullptr, m.gridBigCount, 0);
     uint32_t tiles = (maxCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
     unsigned long long *status = reinterpret_cast<unsigned long long *>(scanScratch);
     uint32_t *counter = scanScratch + statusWords - 2;
@@ -255,8 +261,8 @@ cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
 {
     if (m.nT == 0)
         return cudaSuccess;
-    grid_bin_kernel<true><<<(m.nT + 255) / 256, 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, m.gridRefs,
-        m.gridBigRefs, m.gridBigCount, m.gridBigCap);
+    grid_bin_kernel<true><<<3 * ((m.nT + 255) / 256), 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, m.gridRefs,
+        m.gridRefCap, m.gridBigRefs, m.gridBigCount, m.gridBigCap);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -36,6 +36,8 @@ struct MeshDev {
     unsigned long long *bounds = nullptr; // 6 order-encoded doubles: min xyz, max xyz
     double2 *tbox = nullptr;            // 3*nT: exact triangle boxes, original order
     double *normal = nullptr;           // 3*nT, original order
+    double *cent = nullptr;             // 3*nT face centroids ((v0+v1)+v2)/3.0, original order
+    double *scent = nullptr;            // 3*nTpad the same in Morton order (classification queries)
     uint32_t *mkey = nullptr, *mkeyTmp = nullptr;   // Morton keys (sort ping-pong)
     uint32_t *order = nullptr, *orderTmp = nullptr; // triangle ids (sort ping-pong)
     uint32_t *sortedKey = nullptr;      // -> mkey or mkeyTmp after the sort
@@ -49,11 +51,12 @@ struct MeshDev {
     int *root = nullptr;                // device scalar
     int *err = nullptr;                 // device scalar: 1 = triangle index out of range
     // ray grids
-    float *extentSum = nullptr;         // 3 floats: sum of triangle-box extents per world axis
+    float *extentSum = nullptr;         // 32 x 3 partial sums of triangle-box extents per world axis
     uint32_t gridCellBits = 0;          // at most 2^bits cells per axis (allocation bound)
     GridParams *gridParams = nullptr;
     uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
     uint4 *gridRefs = nullptr;          // {qlo_u|qhi_u<<16, qlo_v|qhi_v<<16, qhi_a|qlo_a<<16, triangle id}
+    uint32_t gridRefCap = 0;            // entries allocated behind gridRefs
     uint4 *gridBigRefs = nullptr;       // 3 * gridBigCap: triangles covering too many cells
     uint32_t *gridBigCount = nullptr;   // [0..2] counts (count pass), [3..5] fill cursors, [6] total refs
     uint32_t gridBigCap = 0;
@@ -97,12 +100,13 @@ struct ClassifyArgs {
     uint8_t *perAxis = nullptr;  // optional, 3 per point
 };
 // scratch: sbk_classify_scratch_bytes(points, cap, facesMode) bytes; cap = capacity of
-// the candidate list; *candCount (device, zeroed by the caller) receives the number
-// of ray/triangle candidates -- if it exceeds cap the results are invalid and the
-// call must be repeated with a larger cap.
+// the list; *candCount (device, zeroed by the caller) receives the number of list
+// entries (quantised-box matches) -- if it exceeds cap the results are invalid and
+// the call must be repeated with a larger cap; *exactCount receives the number of
+// true ray/triangle candidates (exact box overlap).
 size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, bool facesMode);
 cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, void *scratch,
-    unsigned long long cap, unsigned long long *candCount, LaunchCounter &lc);
+    unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount, LaunchCounter &lc);
 
 size_t sbk_radix_workspace_words(size_t n);
 

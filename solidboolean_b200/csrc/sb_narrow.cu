@@ -156,7 +156,7 @@ cudaError_t sbk_sort_keys(cudaStream_t s, unsigned long long *keys, unsigned lon
 {
     sbradix::Workspace ws;
     ws.mem = radixWs;
-    lc.kernels += sbradix::sort<unsigned long long>(s, keys, keysTmp, vals, valsTmp, n, beginBit, endBit, ws, smCount,
+    lc.kernels += sbradix::sort<unsigned long long, 8>(s, keys, keysTmp, vals, valsTmp, n, beginBit, endBit, ws, smCount,
         outKeys, outVals);
     return cudaGetLastError();
 }

@@ -12,7 +12,6 @@ constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int ITEMS = 16;
 constexpr int TILE = THREADS * ITEMS; // 4096 keys per CTA
-constexpr int RADIX = 256;
 constexpr int MAX_PASSES = 8;
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
@@ -21,11 +20,13 @@ constexpr uint32_t VALUE_MASK = (1u << 30) - 1;
 
 // Histogram of every digit position in one pass; the last CTA to finish turns
 // each 256-bin histogram into an exclusive prefix (global digit offsets).
-template <typename KeyT>
+template <typename KeyT, int BITS>
 __global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ keys, uint32_t n,
     int beginBit, int passes, uint32_t *__restrict__ hist /* [passes][256] */, uint32_t *__restrict__ ticket)
 {
-    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    constexpr int RADIX = 1 << BITS;
+    constexpr int MAXP = BITS == 8 ? MAX_PASSES : 4;
+    __shared__ uint32_t s_hist[MAXP * RADIX];
     __shared__ bool s_last;
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
         s_hist[i] = 0;
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ 
     for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n; i += gridDim.x * THREADS) {
         KeyT k = keys[i];
         for (int p = 0; p < passes; ++p)
-            atomicAdd(&s_hist[p * RADIX + (uint32_t)((k >> (beginBit + 8 * p)) & 0xff)], 1u);
+            atomicAdd(&s_hist[p * RADIX + (uint32_t)((k >> (beginBit + BITS * p)) & (RADIX - 1))], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
@@ -47,29 +48,43 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ 
     if (!s_last)
         return;
     __threadfence();
-    // exclusive scan of each pass's 256 bins (thread d owns bin d)
-    __shared__ uint32_t s_scan[RADIX];
+    // exclusive scan of each pass's bins (thread t owns bins t*PER .. t*PER+PER-1)
+    constexpr int PER = RADIX / THREADS;
+    __shared__ uint32_t s_scan[THREADS];
     for (int p = 0; p < passes; ++p) {
-        uint32_t v = __ldcg(&hist[p * RADIX + threadIdx.x]);
-        s_scan[threadIdx.x] = v;
+        uint32_t v[PER];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            v[i] = __ldcg(&hist[p * RADIX + threadIdx.x * PER + i]);
+            sum += v[i];
+        }
+        s_scan[threadIdx.x] = sum;
         __syncthreads();
-        for (int off = 1; off < RADIX; off <<= 1) {
+        for (int off = 1; off < THREADS; off <<= 1) {
             uint32_t t = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
             __syncthreads();
             s_scan[threadIdx.x] += t;
             __syncthreads();
         }
-        hist[p * RADIX + threadIdx.x] = s_scan[threadIdx.x] - v;
+        uint32_t excl = s_scan[threadIdx.x] - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            hist[p * RADIX + threadIdx.x * PER + i] = excl;
+            excl += v[i];
+        }
         __syncthreads();
     }
 }
 
-template <typename KeyT, bool HAS_VALUES>
+template <typename KeyT, bool HAS_VALUES, int BITS>
 __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restrict__ keysIn, KeyT *__restrict__ keysOut,
     const uint32_t *__restrict__ valsIn, uint32_t *__restrict__ valsOut, uint32_t n, int shift,
-    const uint32_t *__restrict__ digitBase /* [256] exclusive */, volatile uint32_t *lookback /* [tiles][256] */,
+    const uint32_t *__restrict__ digitBase /* [RADIX] exclusive */, volatile uint32_t *lookback /* [tiles][RADIX] */,
     uint32_t *__restrict__ tileCounter)
 {
+    constexpr int RADIX = 1 << BITS;
+    constexpr int PER = RADIX / THREADS; // digits owned by one thread in the scan / look-back phase
     __shared__ uint32_t s_warpHist[WARPS][RADIX];
     __shared__ uint32_t s_digitStart[RADIX];
     __shared__ uint32_t s_globalOff[RADIX];
@@ -102,7 +117,7 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
     const uint32_t ltMask = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        uint32_t digit = (uint32_t)((key[i] >> shift) & 0xff);
+        uint32_t digit = (uint32_t)((key[i] >> shift) & (RADIX - 1));
         uint32_t peers = __match_any_sync(SB_FULL, digit);
         int leader = __ffs(peers) - 1;
         uint32_t old = 0;
@@ -116,37 +131,50 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
     }
     __syncthreads();
 
-    // thread d: exclusive scan of digit d over the warps, tile aggregate, lookback
+    // thread t owns digits t*PER..: exclusive scan over the warps, tile aggregate, look-back
     {
-        const int d = tid;
-        uint32_t sum = 0;
+        uint32_t sums[PER], excls[PER];
+        uint32_t mySum = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            uint32_t t = s_warpHist[w][d];
-            s_warpHist[w][d] = sum;
-            sum += t;
-        }
-        uint32_t excl = 0;
-        if (tile == 0) {
-            lookback[d] = sum | FLAG_PREFIX;
-        } else {
-            lookback[tile * RADIX + d] = sum | FLAG_AGG;
-            int t = (int)tile - 1;
-            while (true) {
-                uint32_t v = lookback[t * RADIX + d];
-                if (v & FLAG_PREFIX) {
-                    excl += v & VALUE_MASK;
-                    break;
-                }
-                if (v & FLAG_AGG) {
-                    excl += v & VALUE_MASK;
-                    --t;
-                }
+        for (int i = 0; i < PER; ++i) {
+            const int d = tid * PER + i;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                uint32_t t = s_warpHist[w][d];
+                s_warpHist[w][d] = sum;
+                sum += t;
             }
-            lookback[tile * RADIX + d] = (excl + sum) | FLAG_PREFIX;
+            sums[i] = sum;
+            mySum += sum;
+            if (tile == 0)
+                lookback[d] = sum | FLAG_PREFIX;
+            else
+                lookback[tile * RADIX + d] = sum | FLAG_AGG;
         }
-        // block-wide exclusive scan of `sum` over the 256 digits
-        uint32_t incl = sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int d = tid * PER + i;
+            uint32_t excl = 0;
+            if (tile != 0) {
+                int t = (int)tile - 1;
+                while (true) {
+                    uint32_t v = lookback[t * RADIX + d];
+                    if (v & FLAG_PREFIX) {
+                        excl += v & VALUE_MASK;
+                        break;
+                    }
+                    if (v & FLAG_AGG) {
+                        excl += v & VALUE_MASK;
+                        --t;
+                    }
+                }
+                lookback[tile * RADIX + d] = (excl + sums[i]) | FLAG_PREFIX;
+            }
+            excls[i] = excl;
+        }
+        // block-wide exclusive scan of the per-thread digit totals
+        uint32_t incl = mySum;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
@@ -161,16 +189,21 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
         for (int w = 0; w < WARPS; ++w)
             if (w < warp)
                 warpOff += s_scanTmp[w];
-        uint32_t start = warpOff + incl - sum;
-        s_digitStart[d] = start;
-        s_globalOff[d] = digitBase[d] + excl - start;
+        uint32_t start = warpOff + incl - mySum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int d = tid * PER + i;
+            s_digitStart[d] = start;
+            s_globalOff[d] = digitBase[d] + excls[i] - start;
+            start += sums[i];
+        }
     }
     __syncthreads();
 
     // local scatter so that the global writes below are runs of consecutive addresses
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        uint32_t digit = (uint32_t)((key[i] >> shift) & 0xff);
+        uint32_t digit = (uint32_t)((key[i] >> shift) & (RADIX - 1));
         rank[i] += s_digitStart[digit] + s_warpHist[warp][digit];
         s_keys[rank[i]] = key[i];
     }
@@ -180,7 +213,7 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
     for (int i = 0; i < ITEMS; ++i) {
         uint32_t j = tid + i * THREADS;
         KeyT k = s_keys[j];
-        uint32_t digit = (uint32_t)((k >> shift) & 0xff);
+        uint32_t digit = (uint32_t)((k >> shift) & (RADIX - 1));
         gpos[i] = s_globalOff[digit] + j;
         if (j < tileCount)
             keysOut[gpos[i]] = k;
@@ -203,48 +236,50 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
 }
 
 struct Workspace {
-    uint32_t *mem = nullptr; // [hist: MAX_PASSES*256][ticket+counters: 16][lookback: MAX_PASSES * tiles * 256]
-    size_t tilesCap = 0;
-    static size_t words(size_t tiles) { return MAX_PASSES * RADIX + 16 + MAX_PASSES * tiles * RADIX; }
+    uint32_t *mem = nullptr; // [hist: MAX_PASSES*512][ticket+counters: 16][lookback: passes * tiles * RADIX]
+    static size_t words(size_t tiles) { return MAX_PASSES * 512 + 16 + MAX_PASSES * tiles * 512; }
 };
 
 inline size_t tiles_for(size_t n) { return (n + TILE - 1) / TILE; }
 
-// Sort n keys on bits [beginBit, endBit).  Results land in *outKeys/*outVals
-// (either the primary or the tmp buffers).  Returns the number of kernels launched.
-template <typename KeyT>
+// Sort n keys on bits [beginBit, endBit) with BITS-bit digits.  Results land in
+// *outKeys/*outVals (either the primary or the tmp buffers).  Returns the number of
+// kernels launched.
+template <typename KeyT, int BITS>
 int sort(cudaStream_t stream, KeyT *keys, KeyT *keysTmp, uint32_t *vals, uint32_t *valsTmp, size_t n,
     int beginBit, int endBit, const Workspace &ws, int smCount, KeyT **outKeys, uint32_t **outVals)
 {
+    constexpr int RADIX = 1 << BITS;
+    constexpr int MAXP = BITS == 8 ? MAX_PASSES : 4;
     *outKeys = keys;
     if (outVals)
         *outVals = vals;
     if (n < 2 || endBit <= beginBit)
         return 0;
-    int passes = (endBit - beginBit + 7) / 8;
-    if (passes > MAX_PASSES)
-        passes = MAX_PASSES;
+    int passes = (endBit - beginBit + BITS - 1) / BITS;
+    if (passes > MAXP)
+        passes = MAXP;
     size_t tiles = tiles_for(n);
     uint32_t *hist = ws.mem;
-    uint32_t *ticket = ws.mem + MAX_PASSES * RADIX;
+    uint32_t *ticket = ws.mem + MAX_PASSES * 512;
     uint32_t *counters = ticket + 1;
-    uint32_t *lookback = ws.mem + MAX_PASSES * RADIX + 16;
-    cudaMemsetAsync(ws.mem, 0, sizeof(uint32_t) * (MAX_PASSES * RADIX + 16 + (size_t)passes * tiles * RADIX), stream);
+    uint32_t *lookback = ws.mem + MAX_PASSES * 512 + 16;
+    cudaMemsetAsync(ws.mem, 0, sizeof(uint32_t) * (MAX_PASSES * 512 + 16 + (size_t)passes * tiles * RADIX), stream);
     int histBlocks = (int)((n + THREADS * 8 - 1) / (THREADS * 8));
     if (histBlocks > smCount * 4)
         histBlocks = smCount * 4;
     if (histBlocks < 1)
         histBlocks = 1;
-    hist_kernel<KeyT><<<histBlocks, THREADS, 0, stream>>>(keys, (uint32_t)n, beginBit, passes, hist, ticket);
+    hist_kernel<KeyT, BITS><<<histBlocks, THREADS, 0, stream>>>(keys, (uint32_t)n, beginBit, passes, hist, ticket);
     KeyT *kin = keys, *kout = keysTmp;
     uint32_t *vin = vals, *vout = valsTmp;
     for (int p = 0; p < passes; ++p) {
         if (vals)
-            onesweep_kernel<KeyT, true><<<(unsigned)tiles, THREADS, 0, stream>>>(kin, kout, vin, vout, (uint32_t)n,
-                beginBit + 8 * p, hist + p * RADIX, lookback + (size_t)p * tiles * RADIX, counters + p);
+            onesweep_kernel<KeyT, true, BITS><<<(unsigned)tiles, THREADS, 0, stream>>>(kin, kout, vin, vout, (uint32_t)n,
+                beginBit + BITS * p, hist + p * RADIX, lookback + (size_t)p * tiles * RADIX, counters + p);
         else
-            onesweep_kernel<KeyT, false><<<(unsigned)tiles, THREADS, 0, stream>>>(kin, kout, nullptr, nullptr, (uint32_t)n,
-                beginBit + 8 * p, hist + p * RADIX, lookback + (size_t)p * tiles * RADIX, counters + p);
+            onesweep_kernel<KeyT, false, BITS><<<(unsigned)tiles, THREADS, 0, stream>>>(kin, kout, nullptr, nullptr,
+                (uint32_t)n, beginBit + BITS * p, hist + p * RADIX, lookback + (size_t)p * tiles * RADIX, counters + p);
         KeyT *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
     }
