@@ -81,10 +81,12 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double2 *__restrict__ tbox,
     double *__restrict__ normal, double *__restrict__ cent, uint32_t *__restrict__ mkey, uint32_t *__restrict__ order,
-    int *__restrict__ err, float *__restrict__ extentSum)
+    int *__restrict__ err, unsigned long long *__restrict__ extentSum)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    float sx = 0.0f, sy = 0.0f, sz = 0.0f; // this triangle's box extents
+    // this triangle's box extents as 2^-24 fractions of the mesh extent (integers:
+    // the sums, and with them the ray-grid resolution, do not depend on atomic order)
+    unsigned int sx = 0, sy = 0, sz = 0;
     if (i < nT) {
     uint32_t i0 = tri[3 * (size_t)i], i1 = tri[3 * (size_t)i + 1], i2 = tri[3 * (size_t)i + 2];
     if (i0 >= nV || i1 >= nV || i2 >= nV) { // reported as SB_ERR_INVALID by the host
@@ -133,10 +135,9 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     uint32_t qz = quant10(0.5 * (bx.loz + bx.hiz), blz, iz);
     mkey[i] = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
     order[i] = i;
-    sx = (float)(bx.hix - bx.lox); sy = (float)(bx.hiy - bx.loy); sz = (float)(bx.hiz - bx.loz);
-    if (!(sx >= 0.0f && sx < 1e30f)) sx = 0.0f; // NaN / overflow guards (sizing heuristic only)
-    if (!(sy >= 0.0f && sy < 1e30f)) sy = 0.0f;
-    if (!(sz >= 0.0f && sz < 1e30f)) sz = 0.0f;
+    sx = (unsigned int)fmin(fmax((bx.hix - bx.lox) * ix * 16777216.0, 0.0), 16777216.0); // NaN -> 0
+    sy = (unsigned int)fmin(fmax((bx.hiy - bx.loy) * iy * 16777216.0, 0.0), 16777216.0);
+    sz = (unsigned int)fmin(fmax((bx.hiz - bx.loz) * iz * 16777216.0, 0.0), 16777216.0);
     }
     // mean triangle-box extent per axis (sizes the ray grids): CTA reduction, then
     // three atomics per CTA spread over 32 slots (same-address atomics serialise)
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
         sy += __shfl_xor_sync(SB_FULL, sy, off);
         sz += __shfl_xor_sync(SB_FULL, sz, off);
     }
-    __shared__ float s_ext[8][3];
+    __shared__ unsigned int s_ext[8][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_ext[warp][0] = sx;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     }
     __syncthreads();
     if (threadIdx.x < 3) {
-        float t = 0.0f;
+        unsigned long long t = 0;
         for (int w = 0; w < 8; ++w)
             t += s_ext[w][threadIdx.x];
         atomicAdd(extentSum + 3 * (blockIdx.x & 31) + threadIdx.x, t);
@@ -267,7 +268,7 @@ cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t
     // bounds seeds: min slots all-ones, max slots zero (order-encoded doubles)
     cudaMemsetAsync(m.bounds, 0xff, 3 * sizeof(unsigned long long), s);
     cudaMemsetAsync(m.bounds + 3, 0x00, 3 * sizeof(unsigned long long), s);
-    cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(float), s);
+    cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(unsigned long long), s);
     int vb = (int)((m.nV + 255) / 256);
     if (vb > smCount * 8)
         vb = smCount * 8;

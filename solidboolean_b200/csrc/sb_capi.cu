@@ -68,11 +68,15 @@ struct sb_context {
     std::vector<Span> spans;
     std::vector<cudaEvent_t> freeEvents;
     float acc[SB_STAGE_COUNT] = {0, 0, 0, 0};
+    cudaEvent_t t0 = nullptr;      // timing reference (recorded at reset)
+    cudaEvent_t orderEvent = nullptr; // orders per-mesh streams behind the context stream
     // scratch
     uint32_t *radixWs = nullptr;
     size_t radixWsWords = 0;
     DeviceScalars *dScalars = nullptr;
     DeviceScalars *hScalars = nullptr; // pinned mirror
+    uint32_t *hPool = nullptr;         // pinned: 256 slots of 4 words for per-mesh count read-backs
+    unsigned hPoolNext = 0;
     uint8_t *classifyOut = nullptr;    // inside flags (+ per-axis) of the last classify call
     size_t classifyOutBytes = 0;
     uint32_t *overflowList = nullptr;
@@ -91,6 +95,14 @@ struct sb_mesh {
     void *gridArena = nullptr; // references, sized after the count pass
     size_t gridArenaBytes = 0;
     bool built = false;
+    // builds run on the mesh's own stream so that independent meshes overlap;
+    // consumers on the context stream wait for `ready`
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr;
+    uint32_t *radixWs = nullptr;     // in the arena
+    uint32_t *scanScratch = nullptr; // in the arena
+    uint32_t *hCounts = nullptr;     // pinned: [0] total refs, [1..3] big-list lengths
+    bool gridSized = false;          // reference list already sized by an earlier build
 };
 
 struct sb_isect {
@@ -104,6 +116,8 @@ struct sb_isect {
     double2 *hitSeg = nullptr;
     uint8_t *flagsA = nullptr, *flagsB = nullptr;
     std::vector<void *> owned; // stream-ordered allocations to release
+    bool candSorted = false;   // candidates are ordered lazily, when somebody asks for them
+    bool noSort = false;
 };
 
 namespace {
@@ -127,20 +141,21 @@ struct StageTimer {
     sb_context *c;
     sb_context::Span span;
     bool on;
-    StageTimer(sb_context *ctx, int stage) : c(ctx), on(ctx->timing)
+    cudaStream_t st;
+    StageTimer(sb_context *ctx, int stage, cudaStream_t stream = nullptr) : c(ctx), on(ctx->timing), st(stream ? stream : ctx->stream)
     {
         if (!on)
             return;
         span.stage = stage;
         span.a = grab();
         span.b = grab();
-        cudaEventRecord(span.a, c->stream);
+        cudaEventRecord(span.a, st);
     }
     ~StageTimer()
     {
         if (!on)
             return;
-        cudaEventRecord(span.b, c->stream);
+        cudaEventRecord(span.b, st);
         c->spans.push_back(span);
     }
     cudaEvent_t grab()
@@ -211,6 +226,20 @@ int ensure_classify_out(sb_context *c, size_t bytes, uint32_t overflowCap)
     return SB_OK;
 }
 
+// make the context stream wait for the mesh's last build
+inline void use_mesh(sb_context *c, const sb_mesh *m)
+{
+    if (m->ready)
+        cudaStreamWaitEvent(c->stream, m->ready, 0);
+}
+
+// make the mesh stream wait for everything enqueued so far on the context stream
+inline void order_after_context(sb_context *c, const sb_mesh *m)
+{
+    cudaEventRecord(c->orderEvent, c->stream);
+    cudaStreamWaitEvent(m->stream, c->orderEvent, 0);
+}
+
 template <typename T>
 int alloc_async(sb_context *c, T **p, size_t count, std::vector<void *> *owned)
 {
@@ -255,7 +284,9 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
         int bits = (int)std::floor(lg + 0.5);
         d.gridCellBits = (uint32_t)std::max(0, std::min(bits, 26));
     }
-    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32 + 96 * 4);
+    size_t oRadix = take(4 * sbk_radix_workspace_words(nT));
+    size_t oScan = take(4 * sbk_grid_scan_status_words(3u << d.gridCellBits));
+    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32 + 96 * 8);
     // stream-ordered allocation: the pool keeps the block cached between calls
     cudaError_t e = cudaMallocAsync(&m->arena, off, ctx->stream);
     if (e != cudaSuccess) {
@@ -287,7 +318,17 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.gridParams = (GridParams *)(b + oGridP);
     d.gridE = (uint32_t *)(b + oGridE);
     d.gridBigCount = (uint32_t *)(b + oGridBig);
-    d.extentSum = (float *)(d.gridBigCount + 8);
+    d.extentSum = (unsigned long long *)(d.gridBigCount + 8);
+    m->radixWs = (uint32_t *)(b + oRadix);
+    m->scanScratch = (uint32_t *)(b + oScan);
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming) != cudaSuccess) {
+        cudaFreeAsync(m->arena, ctx->stream);
+        delete m;
+        return fail(SB_ERR_CUDA, "stream/event creation failed");
+    }
+    m->hCounts = ctx->hPool + 4 * (ctx->hPoolNext++ % 256);
+    order_after_context(ctx, m); // the arena was allocated in context-stream order
     *out = m;
     return SB_OK;
 }
@@ -325,6 +366,10 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SB_CUDA(cudaMalloc(&c->dScalars, 256));
     SB_CUDA(cudaMallocHost(&c->hScalars, 256));
+    SB_CUDA(cudaMallocHost(&c->hPool, 256 * 16));
+    SB_CUDA(cudaEventCreate(&c->t0));
+    SB_CUDA(cudaEventCreateWithFlags(&c->orderEvent, cudaEventDisableTiming));
+    SB_CUDA(cudaEventRecord(c->t0, c->stream));
     if (const char *e = getenv("SB_GRID_BETA")) {
         float b = (float)atof(e);
         if (b > 0.01f && b < 100.0f)
@@ -355,6 +400,9 @@ void sb_context_destroy(sb_context *c)
     cudaFree(c->radixWs);
     cudaFree(c->dScalars);
     cudaFreeHost(c->hScalars);
+    cudaFreeHost(c->hPool);
+    cudaEventDestroy(c->t0);
+    cudaEventDestroy(c->orderEvent);
     cudaFree(c->classifyOut);
     cudaFree(c->overflowList);
     cudaFree(c->scanScratch);
@@ -382,17 +430,36 @@ int sb_context_enable_timing(sb_context *c, int enable)
     return SB_OK;
 }
 
+// Spans of one stage may overlap (meshes build concurrently on their own streams):
+// a stage's time is the length of the UNION of its spans.
 static int drain_spans(sb_context *c)
 {
-    SB_CUDA(cudaStreamSynchronize(c->stream));
+    SB_CUDA(cudaDeviceSynchronize());
+    std::vector<std::pair<float, float>> iv[SB_STAGE_COUNT];
     for (auto &s : c->spans) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
-            c->acc[s.stage] += ms;
+        float a = 0, b = 0;
+        if (cudaEventElapsedTime(&a, c->t0, s.a) == cudaSuccess && cudaEventElapsedTime(&b, c->t0, s.b) == cudaSuccess)
+            iv[s.stage].push_back({a, b});
         c->freeEvents.push_back(s.a);
         c->freeEvents.push_back(s.b);
     }
     c->spans.clear();
+    for (int st = 0; st < SB_STAGE_COUNT; ++st) {
+        std::sort(iv[st].begin(), iv[st].end());
+        float curA = 0, curB = -1;
+        for (auto &p : iv[st]) {
+            if (curB < curA || p.first > curB) {
+                if (curB > curA)
+                    c->acc[st] += curB - curA;
+                curA = p.first;
+                curB = p.second;
+            } else {
+                curB = std::max(curB, p.second);
+            }
+        }
+        if (curB > curA)
+            c->acc[st] += curB - curA;
+    }
     return SB_OK;
 }
 
@@ -407,6 +474,7 @@ int sb_context_reset_timing(sb_context *c)
     for (float &a : c->acc)
         a = 0;
     c->lc.kernels = 0;
+    SB_CUDA(cudaEventRecord(c->t0, c->stream));
     return SB_OK;
 }
 
@@ -455,12 +523,13 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
         return r;
     cudaError_t e = cudaSuccess;
     if (nV)
-        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, ctx->stream);
+        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, m->stream);
     if (e == cudaSuccess && nT)
-        e = cudaMemcpyAsync(m->d.tri, tri, 12 * nT, cudaMemcpyHostToDevice, ctx->stream);
+        e = cudaMemcpyAsync(m->d.tri, tri, 12 * nT, cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(m->ready, m->stream);
     if (e != cudaSuccess) {
-        cudaFreeAsync(m->arena, ctx->stream);
-        delete m;
+        sb_mesh_destroy(m);
         return fail(SB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
     }
     *out = m;
@@ -473,46 +542,43 @@ int sb_mesh_build(sb_mesh *m)
         return fail(SB_ERR_INVALID, "mesh is null");
     sb_context *c = m->ctx;
     DeviceGuard g(c->device);
-    int r = ensure_radix_ws(c, m->d.nT);
-    if (r)
-        return r;
-    if (m->d.nT) {
-        r = ensure_scan_scratch(c, 3u << m->d.gridCellBits);
-        if (r)
-            return r;
-    }
+    cudaStream_t st = m->stream;
+    // after whatever the context stream still does with this mesh's buffers
+    order_after_context(c, m);
     {
-        StageTimer t(c, SB_STAGE_BUILD);
-        SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, c->stream));
-        SB_CUDA(sbk_build_mesh(c->stream, m->d, c->radixWs, c->radixWsWords, c->smCount, c->lc));
-        SB_CUDA(sbk_grid_count(c->stream, m->d, c->scanScratch, c->gridBeta, c->lc));
+        StageTimer t(c, SB_STAGE_BUILD, st);
+        SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, st));
+        SB_CUDA(sbk_build_mesh(st, m->d, m->radixWs, 0, c->smCount, c->lc));
+        SB_CUDA(sbk_grid_count(st, m->d, m->scanScratch, c->gridBeta, c->lc));
+        if (m->d.nT && m->gridSized) {
+            // Rebuild of the same (immutable) geometry: every step above is
+            // deterministic, so the reference count equals the one the list was
+            // sized for -- no host round trip (the fill is bounds-guarded anyway).
+            SB_CUDA(sbk_grid_fill(st, m->d, c->lc));
+        }
     }
-    if (m->d.nT) {
-        // the reference list is sized from the counts: one 16-byte read-back
-        uint32_t *h = reinterpret_cast<uint32_t *>(c->hScalars) + 32;
-        SB_CUDA(cudaMemcpyAsync(h, m->d.gridBigCount + 6, 4, cudaMemcpyDeviceToHost, c->stream));
-        SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, c->stream));
-        SB_CUDA(cudaStreamSynchronize(c->stream));
+    if (m->d.nT && !m->gridSized) {
+        // first build: the reference list is sized from the counts (16-byte read-back)
+        uint32_t *h = m->hCounts;
+        SB_CUDA(cudaMemcpyAsync(h, m->d.gridBigCount + 6, 4, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
         size_t nRefs = h[0];
         uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
         for (int k = 0; k < 3; ++k)
             m->d.gridBigN[k] = h[1 + k];
         size_t bytes = 16 * (std::max<size_t>(nRefs, 1) + 3 * (size_t)std::max<uint32_t>(bigMax, 1));
-        if (bytes > m->gridArenaBytes) {
-            if (m->gridArena)
-                cudaFreeAsync(m->gridArena, c->stream);
-            m->gridArena = nullptr;
-            m->gridArenaBytes = 0;
-            SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, c->stream));
-            m->gridArenaBytes = bytes;
-        }
+        SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, st));
+        m->gridArenaBytes = bytes;
         m->d.gridRefs = static_cast<uint4 *>(m->gridArena);
         m->d.gridRefCap = (uint32_t)std::max<size_t>(nRefs, 1);
         m->d.gridBigRefs = m->d.gridRefs + std::max<size_t>(nRefs, 1);
         m->d.gridBigCap = std::max<uint32_t>(bigMax, 1);
-        StageTimer t(c, SB_STAGE_BUILD);
-        SB_CUDA(sbk_grid_fill(c->stream, m->d, c->lc));
+        m->gridSized = true;
+        StageTimer t(c, SB_STAGE_BUILD, st);
+        SB_CUDA(sbk_grid_fill(st, m->d, c->lc));
     }
+    SB_CUDA(cudaEventRecord(m->ready, st));
     m->built = true;
     return SB_OK;
 }
@@ -521,6 +587,7 @@ static int mesh_check(sb_mesh *m)
 {
     sb_context *c = m->ctx;
     int err = 0;
+    use_mesh(c, m);
     SB_CUDA(cudaMemcpyAsync(&c->hScalars->err, m->d.err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
     err = c->hScalars->err;
@@ -550,9 +617,18 @@ void sb_mesh_destroy(sb_mesh *m)
     if (!m)
         return;
     DeviceGuard g(m->ctx->device);
-    cudaFreeAsync(m->arena, m->ctx->stream);
-    if (m->gridArena)
-        cudaFreeAsync(m->gridArena, m->ctx->stream);
+    if (m->stream) {
+        // free in mesh-stream order, after the context stream is done with the buffers
+        order_after_context(m->ctx, m);
+        cudaFreeAsync(m->arena, m->stream);
+        if (m->gridArena)
+            cudaFreeAsync(m->gridArena, m->stream);
+        cudaStreamDestroy(m->stream); // deferred by the runtime until the stream drains
+    } else {
+        cudaFreeAsync(m->arena, m->ctx->stream);
+    }
+    if (m->ready)
+        cudaEventDestroy(m->ready);
     delete m;
 }
 
@@ -566,6 +642,7 @@ static int mesh_download(const sb_mesh *m, void *dst, const void *src, size_t by
     if (!m->built)
         return fail(SB_ERR_INVALID, "mesh not built");
     DeviceGuard g(m->ctx->device);
+    use_mesh(m->ctx, m);
     if (bytes)
         SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->ctx->stream));
     SB_CUDA(cudaStreamSynchronize(m->ctx->stream));
@@ -625,7 +702,7 @@ int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
     if (r)
         return r;
     uint32_t cnt[8];
-    float ext[96];
+    unsigned long long ext[96];
     r = mesh_download(m, cnt, m->d.gridBigCount, sizeof(cnt));
     if (!r)
         r = mesh_download(m, ext, m->d.extentSum, sizeof(ext));
@@ -635,10 +712,10 @@ int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
         out->nu[a] = g.nu[a];
         out->nv[a] = 1u << (16 - g.shiftV[a]);
         out->big[a] = cnt[a];
-        float sum = 0.0f;
+        unsigned long long sum = 0;
         for (int k = 0; k < 32; ++k)
             sum += ext[3 * k + a];
-        out->mean_extent[a] = sum / (float)m->d.nT;
+        out->mean_extent[a] = (float)((double)sum / 16777216.0 * (g.hi[a] - g.lo[a]) / (double)m->d.nT);
     }
     out->total_cells = g.totalCells;
     out->total_refs = cnt[6];
@@ -674,6 +751,8 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
     sb_context *c = A->ctx;
     DeviceGuard g(c->device);
+    use_mesh(c, A);
+    use_mesh(c, B);
     sb_isect *x = new (std::nothrow) sb_isect;
     if (!x)
         return fail(SB_ERR_NOMEM, "out of host memory");
@@ -757,13 +836,10 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         const bool doSort = !(flags & SB_ISECT_NO_SORT);
         unsigned long long *sortedHitKeys = hitKeys;
         uint32_t *sortedSlot = hitSlot;
+        x->noSort = !doSort;
+        (void)keysTmp;
         if (doSort) {
-            SB_TRY(ensure_radix_ws(c, nCand));
-            SB_TRY(alloc_async(c, &keysTmp, nCand, &x->owned));
-            unsigned long long *sortedKeys = nullptr;
-            SB_CUDA_X(sbk_sort_keys(c->stream, keys, keysTmp, nullptr, nullptr, nCand, 2, 2 + (int)(x->bitsA + x->bitsB),
-                c->radixWs, c->smCount, &sortedKeys, nullptr, c->lc));
-            x->candKeys = sortedKeys;
+            SB_TRY(ensure_radix_ws(c, std::max<size_t>(x->nHit, 1)));
             if (x->nHit > 1) {
                 SB_TRY(alloc_async(c, &hitKeysTmp, x->nHit, &x->owned));
                 SB_TRY(alloc_async(c, &hitSlotTmp, x->nHit, &x->owned));
@@ -800,14 +876,44 @@ int sb_isect_counts(const sb_isect *x, size_t *nCand, size_t *nHit)
     return SB_OK;
 }
 
-int sb_isect_candidates(const sb_isect *x, uint32_t *ab, uint8_t *code)
+// The full candidate list is only consumed by tests / callers that ask for it:
+// ordering it by (a, b) is deferred to the first request.
+static int ensure_candidates_sorted(sb_isect *x)
 {
+    if (x->candSorted || x->noSort || x->nCand < 2) {
+        x->candSorted = true;
+        return SB_OK;
+    }
+    sb_context *c = x->ctx;
+    int r = ensure_radix_ws(c, x->nCand);
+    if (r)
+        return r;
+    unsigned long long *tmp = nullptr, *sorted = nullptr;
+    r = alloc_async(c, &tmp, x->nCand, &x->owned);
+    if (r)
+        return r;
+    StageTimer t(c, SB_STAGE_NARROW);
+    SB_CUDA(sbk_sort_keys(c->stream, x->candKeys, tmp, nullptr, nullptr, x->nCand, 2, 2 + (int)(x->bitsA + x->bitsB),
+        c->radixWs, c->smCount, &sorted, nullptr, c->lc));
+    x->candKeys = sorted;
+    x->candSorted = true;
+    return SB_OK;
+}
+
+int sb_isect_candidates(const sb_isect *xc, uint32_t *ab, uint8_t *code)
+{
+    sb_isect *x = const_cast<sb_isect *>(xc);
     if (!x || !ab)
         return fail(SB_ERR_INVALID, "null isect or output");
     sb_context *c = x->ctx;
     DeviceGuard g(c->device);
     if (!x->nCand)
         return SB_OK;
+    {
+        int rs = ensure_candidates_sorted(x);
+        if (rs)
+            return rs;
+    }
     uint32_t *dAB = nullptr;
     uint8_t *dCode = nullptr;
     int r = alloc_async(c, &dAB, 2 * x->nCand, nullptr);
@@ -856,11 +962,18 @@ int sb_isect_face_flags(const sb_isect *x, uint8_t *flagsA, uint8_t *flagsB)
     return SB_OK;
 }
 
-int sb_isect_device_ptrs(const sb_isect *x, void **cand_keys, unsigned *bits_b, void **hit_ab, void **hit_seg,
+int sb_isect_device_ptrs(const sb_isect *xc, void **cand_keys, unsigned *bits_b, void **hit_ab, void **hit_seg,
     void **flagsA, void **flagsB)
 {
+    sb_isect *x = const_cast<sb_isect *>(xc);
     if (!x)
         return fail(SB_ERR_INVALID, "isect is null");
+    if (cand_keys) {
+        DeviceGuard g(x->ctx->device);
+        int rs = ensure_candidates_sorted(x);
+        if (rs)
+            return rs;
+    }
     if (cand_keys) *cand_keys = x->candKeys;
     if (bits_b) *bits_b = x->bitsB;
     if (hit_ab) *hit_ab = x->hitAB;
@@ -952,6 +1065,7 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
         return SB_OK;
     sb_context *c = target->ctx;
     DeviceGuard g(c->device);
+    use_mesh(c, target);
     int r = ensure_classify_out(c, 4 * Q, 0);
     if (r)
         return r;
@@ -992,6 +1106,8 @@ static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size
     if (!query->built || !target->built)
         return fail(SB_ERR_INVALID, "mesh not built");
     sb_context *c = query->ctx;
+    use_mesh(c, query);
+    use_mesh(c, target);
     size_t n = query->d.nT;
     if (end > n)
         end = n;

@@ -34,7 +34,8 @@ __device__ __forceinline__ uint32_t quant16(double x, double org, double scl)
 // triangle covers about (1 + 1/beta)^2 cells on every grid whatever the mesh's
 // aspect ratio or anisotropy; resolutions are powers of two so that a cell index
 // is a shift of the 16-bit coordinate.  maxBits bounds cells per axis (allocation).
-__global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds, const float *__restrict__ extentSum,
+__global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds,
+    const unsigned long long *__restrict__ extentSum,
     uint32_t nT, int maxBits, float beta, GridParams *out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0)
@@ -49,10 +50,10 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
         g.scl[d] = (ext > 0.0 && ext < 1.0e300) ? 65535.999 / ext : 0.0;
         g.lo[d] = lo;
         g.hi[d] = hi;
-        double sum = 0.0;
+        unsigned long long isum = 0; // fixed point: 2^-24 fractions of the mesh extent
         for (int k = 0; k < 32; ++k)
-            sum += (double)extentSum[3 * k + d];
-        double mean = nT ? sum / (double)nT : 0.0;
+            isum += extentSum[3 * k + d];
+        double mean = nT ? (double)isum / 16777216.0 * ext / (double)nT : 0.0;
         double cells = (ext > 0.0 && mean > 0.0) ? ext / ((double)beta * mean) : 1.0;
         int b = (int)floor(log2(fmax(cells, 1.0)) + 0.5);
         bitsWanted[d] = max(0, min(b, 16));

@@ -51,7 +51,7 @@ struct MeshDev {
     int *root = nullptr;                // device scalar
     int *err = nullptr;                 // device scalar: 1 = triangle index out of range
     // ray grids
-    float *extentSum = nullptr;         // 32 x 3 partial sums of triangle-box extents per world axis
+    unsigned long long *extentSum = nullptr; // 32 x 3 partial sums of triangle-box extents (2^-24 of the mesh extent)
     uint32_t gridCellBits = 0;          // at most 2^bits cells per axis (allocation bound)
     GridParams *gridParams = nullptr;
     uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
