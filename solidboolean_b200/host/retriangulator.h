@@ -1,0 +1,44 @@
+// Cuts one mesh triangle along the intersection segments that cross it and
+// re-triangulates the pieces (the job of the reference's ReTriangulator,
+// src/retriangulator.{h,cpp}; same public interface, implementation written for
+// this project on top of earclip.h).  Runs on the host, as in the reference.
+//
+// Points are numbered 0..2 = the triangle's corners, 3.. = the intersection points
+// handed to setEdges(); the neighbour map links those points into open polylines
+// (ending on the triangle's boundary) and closed loops (strictly inside).
+#ifndef RE_TRIANGULATOR_H
+#define RE_TRIANGULATOR_H
+#include <array>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#include "vector3.h"
+
+class ReTriangulator
+{
+public:
+    ReTriangulator(const std::vector<Vector3> &trianglePoints, const Vector3 &normal);
+    void setEdges(const std::vector<Vector3> &points,
+        const std::unordered_map<size_t, std::unordered_set<size_t>> *neighborMapFrom3);
+    bool reTriangulate();
+    const std::vector<std::vector<size_t>> &polygons() const { return m_polygons; }
+    const std::vector<std::vector<size_t>> &triangles() const { return m_triangles; }
+
+private:
+    typedef std::array<double, 2> P2;
+    P2 project(const Vector3 &p) const;
+    bool collectChains();
+    bool splitBoundaryRing();
+    void triangulateRegions();
+    bool pointInRing(const P2 &p, const std::vector<size_t> &ring) const;
+
+    Vector3 m_origin, m_axisU, m_axisV;
+    std::vector<P2> m_points;
+    std::vector<std::vector<size_t>> m_adjacency; // per point, sorted neighbours
+    std::vector<std::vector<size_t>> m_polylines; // open chains, endpoints on the boundary
+    std::vector<std::vector<size_t>> m_loops;     // closed chains
+    std::vector<std::vector<size_t>> m_polygons;  // boundary ring split by the polylines
+    std::vector<std::vector<size_t>> m_triangles;
+};
+
+#endif

@@ -1,0 +1,382 @@
+#include "solidboolean.h"
+#include <algorithm>
+#include <deque>
+#include <iostream>
+#include "retriangulator.h"
+#include "solidboolean_b200.h"
+
+namespace
+{
+inline SolidBoolean::TimePoint now() { return std::chrono::high_resolution_clock::now(); }
+}
+
+SolidBoolean::SolidBoolean(const SolidMesh *firstMesh, const SolidMesh *secondMesh)
+    : m_firstMesh(firstMesh), m_secondMesh(secondMesh)
+{
+}
+
+SolidBoolean::~SolidBoolean() {}
+
+const std::vector<Vector3> &SolidBoolean::resultVertices() { return m_newVertices; }
+
+// ---- per-triangle cut bookkeeping (reference src/solidboolean.cpp:296-311, 321-339)
+
+size_t SolidBoolean::CutTriangle::addPoint(const Vector3 &p)
+{
+    auto ins = lookup.insert({PositionKey(p), points.size()});
+    if (ins.second)
+        points.push_back(p);
+    return ins.first->second;
+}
+
+void SolidBoolean::CutTriangle::addSegment(const Vector3 &a, const Vector3 &b)
+{
+    size_t ia = 3 + addPoint(a), ib = 3 + addPoint(b);
+    if (ia == ib)
+        return;
+    neighbors[ia].insert(ib);
+    neighbors[ib].insert(ia);
+}
+
+size_t SolidBoolean::weldPoint(const Vector3 &p)
+{
+    auto ins = m_weldMap.insert({PositionKey(p), m_newVertices.size()});
+    if (ins.second)
+        m_newVertices.push_back(p);
+    return ins.first->second;
+}
+
+bool SolidBoolean::appendTriangle(size_t a, size_t b, size_t c, HalfEdgeMap &halfEdges)
+{
+    size_t index = m_newTriangles.size();
+    m_newTriangles.push_back({a, b, c});
+    bool ok = true;
+    ok &= halfEdges.insert({halfEdgeKey(a, b), index}).second;
+    ok &= halfEdges.insert({halfEdgeKey(b, c), index}).second;
+    ok &= halfEdges.insert({halfEdgeKey(c, a), index}).second;
+    return ok;
+}
+
+// triangles the intersection does not touch are taken over as they are
+// (reference addUnintersectedTriangles, src/solidboolean.cpp:250-286)
+bool SolidBoolean::copyUncutTriangles(const SolidMesh *mesh, const std::unordered_set<size_t> &cut, size_t vertexOffset,
+    HalfEdgeMap &halfEdges)
+{
+    const auto &triangles = *mesh->triangles();
+    bool ok = true;
+    for (size_t i = 0; i < triangles.size(); ++i) {
+        if (cut.count(i))
+            continue;
+        const auto &t = triangles[i];
+        if (!appendTriangle(t[0] + vertexOffset, t[1] + vertexOffset, t[2] + vertexOffset, halfEdges)) {
+            std::cout << "Found repeated halfedge:" << t[0] + vertexOffset << "," << t[1] + vertexOffset << std::endl;
+            ok = false;
+        }
+    }
+    return ok;
+}
+
+// reference reTriangulate lambda, src/solidboolean.cpp:352-407
+bool SolidBoolean::retriangulateCutTriangles(const std::map<size_t, CutTriangle> &cuts, const SolidMesh *mesh,
+    size_t vertexOffset, HalfEdgeMap &halfEdges, EdgeGraph &loopEdges)
+{
+    const auto &vertices = *mesh->vertices();
+    const auto &triangles = *mesh->triangles();
+    const auto &normals = *mesh->triangleNormals();
+    for (const auto &it : cuts) {
+        const auto &t = triangles[it.first];
+        ReTriangulator splitter({vertices[t[0]], vertices[t[1]], vertices[t[2]]}, normals[it.first]);
+        splitter.setEdges(it.second.points, &it.second.neighbors);
+        if (!splitter.reTriangulate()) {
+            std::cout << "Retriangle failed" << std::endl;
+            return false;
+        }
+        std::vector<size_t> global = {t[0] + vertexOffset, t[1] + vertexOffset, t[2] + vertexOffset};
+        for (const Vector3 &p : it.second.points)
+            global.push_back(weldPoint(p));
+        for (const auto &piece : splitter.triangles()) {
+            size_t a = global[piece[0]], b = global[piece[1]], c = global[piece[2]];
+            if (a == b || b == c || c == a)
+                continue; // collapsed by welding
+            if (!appendTriangle(a, b, c, halfEdges))
+                std::cout << "Found repeated halfedge:" << a << "," << b << std::endl;
+        }
+        for (const auto &nb : it.second.neighbors)
+            for (size_t other : nb.second) {
+                size_t from = global[nb.first], to = global[other];
+                if (from == to)
+                    continue;
+                loopEdges[from].insert(to);
+                loopEdges[to].insert(from);
+            }
+    }
+    return true;
+}
+
+// the welded intersection segments form closed curves
+// (reference buildPolygonsFromEdges, src/solidboolean.cpp:124-165)
+bool SolidBoolean::traceLoops(const EdgeGraph &edges, std::vector<std::vector<size_t>> &loops)
+{
+    std::vector<size_t> nodes;
+    nodes.reserve(edges.size());
+    for (const auto &e : edges)
+        nodes.push_back(e.first);
+    std::sort(nodes.begin(), nodes.end());
+    std::unordered_set<size_t> seen;
+    for (size_t start : nodes) {
+        if (seen.count(start))
+            continue;
+        std::vector<size_t> loop;
+        size_t cur = start;
+        while (true) {
+            seen.insert(cur);
+            loop.push_back(cur);
+            auto it = edges.find(cur);
+            if (it == edges.end())
+                break;
+            std::vector<size_t> next(it->second.begin(), it->second.end());
+            std::sort(next.begin(), next.end());
+            size_t chosen = cur;
+            for (size_t n : next)
+                if (!seen.count(n)) {
+                    chosen = n;
+                    break;
+                }
+            if (chosen == cur)
+                break;
+            cur = chosen;
+        }
+        if (loop.size() <= 2) {
+            std::cout << "buildPolygonsFromEdges failed, too short" << std::endl;
+            return false;
+        }
+        auto last = edges.find(loop.back());
+        if (last == edges.end() || !last->second.count(start)) {
+            std::cout << "buildPolygonsFromEdges failed, could not form a ring" << std::endl;
+            return false;
+        }
+        loops.push_back(loop);
+    }
+    return true;
+}
+
+// Flood-fill the triangles of one mesh into groups bounded by the intersection
+// loops: loop k seeds group 2k on the side of its forward half-edges and group
+// 2k+1 on the other side; triangles no loop reaches form further groups
+// (reference buildFaceGroups, src/solidboolean.cpp:167-239).
+void SolidBoolean::growFaceGroups(const std::vector<std::vector<size_t>> &loops, const HalfEdgeMap &halfEdges,
+    size_t firstTriangle, size_t triangleCount, std::vector<std::vector<size_t>> &groups)
+{
+    std::unordered_map<uint64_t, size_t> fence; // half-edges a fill must not cross again
+    std::deque<std::pair<size_t, size_t>> queue;
+    size_t groupIndex = 0;
+    for (const auto &loop : loops) {
+        for (size_t i = 0; i < loop.size(); ++i) {
+            size_t a = loop[i], b = loop[(i + 1) % loop.size()];
+            for (int side = 0; side < 2; ++side) {
+                uint64_t key = side == 0 ? halfEdgeKey(a, b) : halfEdgeKey(b, a);
+                fence.insert({key, groupIndex + side});
+                auto he = halfEdges.find(key);
+                if (he != halfEdges.end())
+                    queue.push_back({he->second, groupIndex + side});
+            }
+        }
+        groupIndex += 2;
+    }
+    groups.assign(groupIndex, std::vector<size_t>());
+    std::unordered_set<size_t> visited;
+    auto drain = [&]() {
+        while (!queue.empty()) {
+            auto item = queue.front();
+            queue.pop_front();
+            if (!visited.insert(item.first).second)
+                continue;
+            groups[item.second].push_back(item.first);
+            const auto &t = m_newTriangles[item.first];
+            for (size_t i = 0; i < 3; ++i) {
+                size_t a = t[i], b = t[(i + 1) % 3];
+                if (!fence.insert({halfEdgeKey(a, b), item.second}).second)
+                    continue;
+                auto opposite = halfEdges.find(halfEdgeKey(b, a));
+                if (opposite != halfEdges.end())
+                    queue.push_back({opposite->second, item.second});
+            }
+        }
+    };
+    drain();
+    for (size_t t = firstTriangle; t < firstTriangle + triangleCount; ++t) {
+        if (visited.count(t))
+            continue;
+        groups.push_back(std::vector<size_t>());
+        queue.push_back({t, groupIndex++});
+        drain();
+    }
+}
+
+// One representative point per group -- the centroid of its first triangle,
+// (v0 + v1 + v2) / 3.0 -- classified on the GPU with the reference's three-ray
+// majority vote (reference decideGroupSide, src/solidboolean.cpp:482-510).
+bool SolidBoolean::classifyGroups(const std::vector<std::vector<size_t>> &groups, const SolidMesh *against,
+    std::vector<bool> &inside)
+{
+    inside.assign(groups.size(), false);
+    std::vector<double> points;
+    std::vector<size_t> owner;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        if (groups[g].empty())
+            continue;
+        const auto &t = m_newTriangles[groups[g][0]];
+        Vector3 c = (m_newVertices[t[0]] + m_newVertices[t[1]] + m_newVertices[t[2]]) / 3.0;
+        points.push_back(c.x());
+        points.push_back(c.y());
+        points.push_back(c.z());
+        owner.push_back(g);
+    }
+    if (owner.empty())
+        return true;
+    std::vector<uint8_t> flags(owner.size(), 0);
+    if (!against->deviceMesh() ||
+        sb_classify(against->deviceMesh(), points.data(), owner.size(), flags.data(), nullptr) != SB_OK) {
+        std::cout << "decideGroupSide failed: " << sb_last_error() << std::endl;
+        return false;
+    }
+    for (size_t k = 0; k < owner.size(); ++k)
+        inside[owner[k]] = flags[k] != 0;
+    return true;
+}
+
+bool SolidBoolean::combine()
+{
+    m_newVertices.clear();
+    m_newTriangles.clear();
+    m_weldMap.clear();
+    m_firstGroups.clear();
+    m_secondGroups.clear();
+    m_hitPairs.clear();
+    m_hitSegments.clear();
+    if (!m_firstMesh || !m_secondMesh || !m_firstMesh->deviceMesh() || !m_secondMesh->deviceMesh()) {
+        std::cout << "combine failed: meshes are not prepared" << std::endl;
+        return false;
+    }
+
+    // ---- GPU: broad phase + tri/tri predicate (replaces searchPotentialIntersectedPairs
+    // and the predicate loop, reference src/solidboolean.cpp:292, 315-320) ----
+    benchBegin_searchPotentialIntersectedPairs = now();
+    sb_isect *isect = nullptr;
+    if (sb_intersect(m_firstMesh->deviceMesh(), m_secondMesh->deviceMesh(), SB_ISECT_DEFAULT, &isect) != SB_OK) {
+        std::cout << "combine failed: " << sb_last_error() << std::endl;
+        return false;
+    }
+    benchEnd_searchPotentialIntersectedPairs = now();
+    benchBegin_processPotentialIntersectedPairs = now();
+    size_t hitCount = 0;
+    sb_isect_counts(isect, &m_candidateCount, &hitCount);
+    m_hitPairs.resize(2 * hitCount);
+    m_hitSegments.resize(6 * hitCount);
+    int rc = sb_isect_hits(isect, m_hitPairs.data(), m_hitSegments.data());
+    sb_isect_destroy(isect);
+    if (rc != SB_OK) {
+        std::cout << "combine failed: " << sb_last_error() << std::endl;
+        return false;
+    }
+    std::map<size_t, CutTriangle> firstCuts, secondCuts; // ordered: deterministic output
+    std::unordered_set<size_t> firstCutFaces, secondCutFaces;
+    for (size_t h = 0; h < hitCount; ++h) {
+        size_t a = m_hitPairs[2 * h], b = m_hitPairs[2 * h + 1];
+        const double *s = &m_hitSegments[6 * h];
+        Vector3 source(s[0], s[1], s[2]), target(s[3], s[4], s[5]);
+        firstCutFaces.insert(a);
+        secondCutFaces.insert(b);
+        firstCuts[a].addSegment(source, target);
+        secondCuts[b].addSegment(source, target);
+    }
+    benchEnd_processPotentialIntersectedPairs = now();
+
+    // ---- host topology, as in the reference ----
+    benchBegin_addUnintersectedTriangles = now();
+    const size_t firstVertexCount = m_firstMesh->vertices()->size();
+    m_newVertices.reserve(firstVertexCount + m_secondMesh->vertices()->size());
+    m_newVertices.insert(m_newVertices.end(), m_firstMesh->vertices()->begin(), m_firstMesh->vertices()->end());
+    m_newVertices.insert(m_newVertices.end(), m_secondMesh->vertices()->begin(), m_secondMesh->vertices()->end());
+    HalfEdgeMap firstHalfEdges, secondHalfEdges;
+    size_t firstStart = m_newTriangles.size();
+    if (!copyUncutTriangles(m_firstMesh, firstCutFaces, 0, firstHalfEdges))
+        std::cout << "Add first mesh remaining triangles failed" << std::endl;
+    size_t firstCount = m_newTriangles.size() - firstStart;
+    size_t secondStart = m_newTriangles.size();
+    if (!copyUncutTriangles(m_secondMesh, secondCutFaces, firstVertexCount, secondHalfEdges))
+        std::cout << "Add second mesh remaining triangles failed" << std::endl;
+    size_t secondCount = m_newTriangles.size() - secondStart;
+    benchEnd_addUnintersectedTriangles = now();
+
+    benchBegin_reTriangulate = now();
+    EdgeGraph firstLoopEdges, secondLoopEdges;
+    if (!retriangulateCutTriangles(firstCuts, m_firstMesh, 0, firstHalfEdges, firstLoopEdges)) {
+        std::cout << "Retriangulate first mesh failed" << std::endl;
+        return false;
+    }
+    if (!retriangulateCutTriangles(secondCuts, m_secondMesh, firstVertexCount, secondHalfEdges, secondLoopEdges)) {
+        std::cout << "Retriangulate second mesh failed" << std::endl;
+        return false;
+    }
+    benchEnd_reTriangulate = now();
+
+    benchBegin_buildPolygonsFromEdges = now();
+    std::vector<std::vector<size_t>> loops;
+    if (!traceLoops(firstLoopEdges, loops)) {
+        std::cout << "Build polygons from edges failed" << std::endl;
+        return false;
+    }
+    benchEnd_buildPolygonsFromEdges = now();
+
+    benchBegin_buildFaceGroups = now();
+    growFaceGroups(loops, firstHalfEdges, firstStart, firstCount, m_firstGroups);
+    growFaceGroups(loops, secondHalfEdges, secondStart, secondCount, m_secondGroups);
+    benchEnd_buildFaceGroups = now();
+
+    // ---- GPU: inside/outside of every group ----
+    benchBegin_decideGroupSide = now();
+    bool ok = classifyGroups(m_firstGroups, m_secondMesh, m_firstGroupInside);
+    ok = classifyGroups(m_secondGroups, m_firstMesh, m_secondGroupInside) && ok;
+    benchEnd_decideGroupSide = now();
+    return ok;
+}
+
+// reference src/solidboolean.cpp:512-565
+void SolidBoolean::fetchUnion(std::vector<std::vector<size_t>> &resultTriangles)
+{
+    for (size_t g = 0; g < m_firstGroups.size(); ++g)
+        if (!m_firstGroupInside[g])
+            for (size_t t : m_firstGroups[g])
+                resultTriangles.push_back(m_newTriangles[t]);
+    for (size_t g = 0; g < m_secondGroups.size(); ++g)
+        if (!m_secondGroupInside[g])
+            for (size_t t : m_secondGroups[g])
+                resultTriangles.push_back(m_newTriangles[t]);
+}
+
+void SolidBoolean::fetchDiff(std::vector<std::vector<size_t>> &resultTriangles)
+{
+    for (size_t g = 0; g < m_firstGroups.size(); ++g)
+        if (!m_firstGroupInside[g])
+            for (size_t t : m_firstGroups[g])
+                resultTriangles.push_back(m_newTriangles[t]);
+    for (size_t g = 0; g < m_secondGroups.size(); ++g)
+        if (m_secondGroupInside[g])
+            for (size_t t : m_secondGroups[g]) { // the cavity wall faces inward: reverse the winding
+                const auto &tri = m_newTriangles[t];
+                resultTriangles.push_back({tri[2], tri[1], tri[0]});
+            }
+}
+
+void SolidBoolean::fetchIntersect(std::vector<std::vector<size_t>> &resultTriangles)
+{
+    for (size_t g = 0; g < m_firstGroups.size(); ++g)
+        if (m_firstGroupInside[g])
+            for (size_t t : m_firstGroups[g])
+                resultTriangles.push_back(m_newTriangles[t]);
+    for (size_t g = 0; g < m_secondGroups.size(); ++g)
+        if (m_secondGroupInside[g])
+            for (size_t t : m_secondGroups[g])
+                resultTriangles.push_back(m_newTriangles[t]);
+}

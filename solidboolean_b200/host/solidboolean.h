@@ -1,0 +1,81 @@
+// SolidBoolean with the reference's public interface (reference
+// src/solidboolean.h:33-108).  combine() runs the intersection front end on the
+// GPU through the C ABI -- broad phase + Guigue-Devillers predicate
+// (sb_intersect) and the inside/outside test of every face group (sb_classify) --
+// and keeps retriangulation, vertex welding, face grouping and mesh assembly on
+// the host, as the reference does.  Errors follow the reference's convention:
+// message on std::cout, combine() returns false, no exceptions.
+#ifndef SOLID_BOOLEAN_H
+#define SOLID_BOOLEAN_H
+#include <chrono>
+#include <cstdint>
+#include <map>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#include "positionkey.h"
+#include "solidmesh.h"
+#include "vector3.h"
+
+class SolidBoolean
+{
+public:
+    SolidBoolean(const SolidMesh *firstMesh, const SolidMesh *secondMesh);
+    ~SolidBoolean();
+    bool combine();
+    // each call APPENDS index triples into resultVertices()
+    void fetchUnion(std::vector<std::vector<size_t>> &resultTriangles);
+    void fetchDiff(std::vector<std::vector<size_t>> &resultTriangles);
+    void fetchIntersect(std::vector<std::vector<size_t>> &resultTriangles);
+    // first mesh's vertices, then the second mesh's, then the welded new points
+    const std::vector<Vector3> &resultVertices();
+
+    // stage time points, same names as the reference (src/solidboolean.h:45-58)
+    typedef std::chrono::time_point<std::chrono::high_resolution_clock> TimePoint;
+    TimePoint benchBegin_searchPotentialIntersectedPairs, benchEnd_searchPotentialIntersectedPairs;
+    TimePoint benchBegin_processPotentialIntersectedPairs, benchEnd_processPotentialIntersectedPairs;
+    TimePoint benchBegin_addUnintersectedTriangles, benchEnd_addUnintersectedTriangles;
+    TimePoint benchBegin_reTriangulate, benchEnd_reTriangulate;
+    TimePoint benchBegin_buildPolygonsFromEdges, benchEnd_buildPolygonsFromEdges;
+    TimePoint benchBegin_buildFaceGroups, benchEnd_buildFaceGroups;
+    TimePoint benchBegin_decideGroupSide, benchEnd_decideGroupSide;
+
+    // front-end results of the last combine() (for tests and diagnostics)
+    size_t candidatePairCount() const { return m_candidateCount; }
+    size_t intersectingPairCount() const { return m_hitPairs.size() / 2; }
+
+private:
+    struct CutTriangle { // per intersected triangle: welded local points + segments between them
+        std::vector<Vector3> points;
+        std::map<PositionKey, size_t> lookup;
+        std::unordered_map<size_t, std::unordered_set<size_t>> neighbors; // indices are 3 + local point
+        size_t addPoint(const Vector3 &p);
+        void addSegment(const Vector3 &a, const Vector3 &b);
+    };
+    typedef std::unordered_map<uint64_t, size_t> HalfEdgeMap;
+    typedef std::unordered_map<size_t, std::unordered_set<size_t>> EdgeGraph;
+
+    static uint64_t halfEdgeKey(size_t from, size_t to) { return ((uint64_t)from << 32) | (uint64_t)to; }
+    size_t weldPoint(const Vector3 &p);
+    bool appendTriangle(size_t a, size_t b, size_t c, HalfEdgeMap &halfEdges);
+    bool copyUncutTriangles(const SolidMesh *mesh, const std::unordered_set<size_t> &cut, size_t vertexOffset, HalfEdgeMap &halfEdges);
+    bool retriangulateCutTriangles(const std::map<size_t, CutTriangle> &cuts, const SolidMesh *mesh, size_t vertexOffset,
+        HalfEdgeMap &halfEdges, EdgeGraph &loopEdges);
+    bool traceLoops(const EdgeGraph &edges, std::vector<std::vector<size_t>> &loops);
+    void growFaceGroups(const std::vector<std::vector<size_t>> &loops, const HalfEdgeMap &halfEdges, size_t firstTriangle,
+        size_t triangleCount, std::vector<std::vector<size_t>> &groups);
+    bool classifyGroups(const std::vector<std::vector<size_t>> &groups, const SolidMesh *against, std::vector<bool> &inside);
+
+    const SolidMesh *m_firstMesh = nullptr;
+    const SolidMesh *m_secondMesh = nullptr;
+    size_t m_candidateCount = 0;
+    std::vector<uint32_t> m_hitPairs;  // 2 per intersecting pair, sorted by (first, second)
+    std::vector<double> m_hitSegments; // 6 per intersecting pair
+    std::vector<Vector3> m_newVertices;
+    std::vector<std::vector<size_t>> m_newTriangles;
+    std::map<PositionKey, size_t> m_weldMap;
+    std::vector<std::vector<size_t>> m_firstGroups, m_secondGroups;
+    std::vector<bool> m_firstGroupInside, m_secondGroupInside;
+};
+
+#endif

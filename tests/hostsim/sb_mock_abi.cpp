@@ -1,0 +1,97 @@
+// TEST ONLY: a CPU stand-in for the subset of the C ABI the C++ host classes call,
+// backed by the oracle (oracle/libsboracle.so), so that the HOST logic
+// (retriangulation, welding, face groups, fetch*) can be exercised in the CPU test
+// suite.  It is linked only into tests/hostsim/libsbhost_mock.so; the product
+// library solidboolean_b200/lib/libsolidboolean_host.so links the CUDA library and
+// has no CPU path.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/solidboolean_b200.h"
+
+extern "C" {
+void sbo_normals(const double *xyz, const uint32_t *tri, size_t nT, double *out);
+void sbo_tri_boxes(const double *xyz, const uint32_t *tri, size_t nT, double *out);
+size_t sbo_candidate_pairs(const double *boxesA, size_t nA, const double *boxesB, size_t nB, uint32_t **outPairs);
+void sbo_free(void *p);
+void sbo_predicate_pairs(const double *xyzA, const uint32_t *triA, const double *xyzB, const uint32_t *triB,
+    const uint32_t *pairs, size_t n, int8_t *ret, int8_t *coplanar, uint8_t *hit, double *seg);
+void sbo_classify(const double *xyz, const uint32_t *tri, size_t nT, const double *pts, size_t q, uint8_t *inside,
+    uint8_t *perAxis, uint64_t *candCount);
+}
+
+struct sb_context { int dummy; };
+struct sb_mesh {
+    std::vector<double> xyz;
+    std::vector<uint32_t> tri;
+};
+struct sb_isect {
+    size_t nCand = 0;
+    std::vector<uint32_t> hitAB;
+    std::vector<double> hitSeg;
+};
+
+extern "C" {
+
+const char *sb_last_error(void) { return "mock"; }
+int sb_context_create(int, sb_context **out) { *out = new sb_context; return SB_OK; }
+void sb_context_destroy(sb_context *c) { delete c; }
+
+int sb_mesh_create(sb_context *, const double *xyz, size_t nV, const uint32_t *tri, size_t nT, sb_mesh **out)
+{
+    sb_mesh *m = new sb_mesh;
+    m->xyz.assign(xyz, xyz + 3 * nV);
+    m->tri.assign(tri, tri + 3 * nT);
+    *out = m;
+    return SB_OK;
+}
+void sb_mesh_destroy(sb_mesh *m) { delete m; }
+int sb_mesh_normals(const sb_mesh *m, double *out) { sbo_normals(m->xyz.data(), m->tri.data(), m->tri.size() / 3, out); return SB_OK; }
+int sb_mesh_triangle_boxes(const sb_mesh *m, double *out) { sbo_tri_boxes(m->xyz.data(), m->tri.data(), m->tri.size() / 3, out); return SB_OK; }
+
+int sb_intersect(const sb_mesh *A, const sb_mesh *B, unsigned, sb_isect **out)
+{
+    size_t nA = A->tri.size() / 3, nB = B->tri.size() / 3;
+    std::vector<double> ba(6 * nA + 6), bb(6 * nB + 6);
+    sbo_tri_boxes(A->xyz.data(), A->tri.data(), nA, ba.data());
+    sbo_tri_boxes(B->xyz.data(), B->tri.data(), nB, bb.data());
+    uint32_t *pairs = nullptr;
+    size_t n = sbo_candidate_pairs(ba.data(), nA, bb.data(), nB, &pairs);
+    std::vector<uint8_t> hit(n + 1);
+    std::vector<double> seg(6 * n + 6);
+    if (n)
+        sbo_predicate_pairs(A->xyz.data(), A->tri.data(), B->xyz.data(), B->tri.data(), pairs, n, nullptr, nullptr,
+            hit.data(), seg.data());
+    sb_isect *x = new sb_isect;
+    x->nCand = n;
+    for (size_t i = 0; i < n; ++i)
+        if (hit[i]) {
+            x->hitAB.push_back(pairs[2 * i]);
+            x->hitAB.push_back(pairs[2 * i + 1]);
+            x->hitSeg.insert(x->hitSeg.end(), seg.begin() + 6 * i, seg.begin() + 6 * i + 6);
+        }
+    sbo_free(pairs);
+    *out = x;
+    return SB_OK;
+}
+void sb_isect_destroy(sb_isect *x) { delete x; }
+int sb_isect_counts(const sb_isect *x, size_t *nCand, size_t *nHit)
+{
+    if (nCand) *nCand = x->nCand;
+    if (nHit) *nHit = x->hitAB.size() / 2;
+    return SB_OK;
+}
+int sb_isect_hits(const sb_isect *x, uint32_t *ab, double *seg)
+{
+    if (ab && !x->hitAB.empty()) std::memcpy(ab, x->hitAB.data(), 4 * x->hitAB.size());
+    if (seg && !x->hitSeg.empty()) std::memcpy(seg, x->hitSeg.data(), 8 * x->hitSeg.size());
+    return SB_OK;
+}
+int sb_classify(const sb_mesh *t, const double *pts, size_t Q, uint8_t *inside, uint8_t *per_axis)
+{
+    if (Q)
+        sbo_classify(t->xyz.data(), t->tri.data(), t->tri.size() / 3, pts, Q, inside, per_axis, nullptr);
+    return SB_OK;
+}
+}
