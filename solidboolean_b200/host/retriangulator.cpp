@@ -1,6 +1,7 @@
 #include "retriangulator.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <iostream>
 #include "earclip.h"
 
@@ -103,7 +104,12 @@ bool ReTriangulator::splitBoundaryRing()
         const P2 &a = m_points[i], &b = m_points[(i + 1) % 3];
         size2 = std::max(size2, (b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1]));
     }
-    const double tolerance2 = 1e-12 * size2; // (1e-6 of the longest edge)^2
+    // A polyline end is either on an edge up to rounding (1e-6 of the triangle's size)
+    // or was welded, inside this triangle, to a neighbouring intersection point by the
+    // 1e-5 PositionKey grid (the segment between them collapsed): it can then sit up to
+    // one key cell away from the edge.  The reference tests exact collinearity with an
+    // absolute DBL_EPSILON (src/vector2.h:212-215) and gives up on such triangles.
+    const double tolerance2 = std::max(1e-12 * size2, 2e-5 * 2e-5);
     std::vector<RingEntry> onEdge[3];
     auto attach = [&](size_t point, int polyline, bool front) {
         int bestEdge = -1;
@@ -123,8 +129,18 @@ bool ReTriangulator::splitBoundaryRing()
                 bestT = tc;
             }
         }
-        if (bestEdge < 0 || bestD > tolerance2)
+        if (bestEdge < 0 || bestD > tolerance2) {
+#ifdef RETRI_DEBUG
+            fprintf(stderr, "attach fail: point %zu polyline %d (len %zu) front %d dist %g size %g ; npts %zu nlines %zu nloops %zu\n", point, polyline,
+                m_polylines[polyline].size(), (int)front, std::sqrt(bestD), std::sqrt(size2), m_points.size(), m_polylines.size(), m_loops.size());
+            for (size_t q = 0; q < m_points.size(); ++q) {
+                fprintf(stderr, "   p%zu (%.12g, %.12g) adj:", q, m_points[q][0], m_points[q][1]);
+                for (size_t nb : m_adjacency[q]) fprintf(stderr, " %zu", nb);
+                fprintf(stderr, "\n");
+            }
+#endif
             return false;
+        }
         onEdge[bestEdge].push_back(RingEntry{point, polyline, front, bestT});
         return true;
     };
