@@ -378,8 +378,11 @@ def run_ours(args):
 
     def e2e_step():
         with torch.cuda.stream(ext):
-            xa = sb.Mesh.from_pointers(ctx, pin[0].data_ptr(), nVA, pin[1].data_ptr(), nA, build=True, keep=pin)
-            xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=True, keep=pin)
+            # host buffers in through the C ABI: sb_mesh_upload (H2D) for both meshes first,
+            # so that B's copy overlaps A's build; then sb_mesh_build for each
+            xa = sb.Mesh.from_pointers(ctx, pin[0].data_ptr(), nVA, pin[1].data_ptr(), nA, build=False, keep=pin)
+            xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=False, keep=pin)
+            xa.build(); xb.build()
             x = xa.intersect(xb, begin=a0, end=a1)
             if world > 1:
                 flagsA.zero_(); flagsB.zero_()
@@ -392,8 +395,8 @@ def run_ours(args):
                     x.hits()
             else:
                 hab, hseg = x.hits()
-                ia, _ = xa.classify_faces_against(xb)
-                ib, _ = xb.classify_faces_against(xa)
+                xa.classify_faces_against(xb, per_axis=False, out=out_in_a)
+                xb.classify_faces_against(xa, per_axis=False, out=out_in_b)
                 Pg, Hg = x.num_candidates, x.num_hits
             x.close(); xa.close(); xb.close()
         return Pg, Hg
@@ -401,7 +404,7 @@ def run_ours(args):
     ctx.enable_timing(False)
     e2e_ms, (P2, H2), _ = timed_loop(e2e_step, max(3, args.steps // 2), 2, False)
     h2d = 24 * (nVA + nVB) + 12 * (nA + nB)
-    d2h = (nA + nB) * (4 if world == 1 else 1) + 56 * H + 64
+    d2h = (nA + nB) + 56 * H + 64
 
     if rank == 0:
         peaks = {}

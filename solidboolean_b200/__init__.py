@@ -273,13 +273,14 @@ class Mesh:
         _check(self.lib.sb_classify(self.h, _ptr(p), q, _ptr(inside), _ptr(per_axis)))
         return inside, per_axis
 
-    def classify_faces_against(self, target: "Mesh"):
-        """Classify this mesh's face centroids against `target`."""
+    def classify_faces_against(self, target: "Mesh", per_axis=True, out=None):
+        """Classify this mesh's face centroids against `target`.
+        -> (inside[nT], per_axis[nT,3] or None); `out` = optional preallocated inside array."""
         n = self.num_triangles
-        inside = np.zeros(n, np.uint8)
-        per_axis = np.zeros((n, 3), np.uint8)
-        _check(self.lib.sb_classify_faces(self.h, target.h, _ptr(inside), _ptr(per_axis)))
-        return inside, per_axis
+        inside = np.zeros(n, np.uint8) if out is None else out
+        axes = np.zeros((n, 3), np.uint8) if per_axis else None
+        _check(self.lib.sb_classify_faces(self.h, target.h, _ptr(inside), _ptr(axes)))
+        return inside, axes
 
     def classify_faces_device(self, target: "Mesh", d_inside_ptr: int, begin=0, end=None):
         end = self.num_triangles if end is None else end

@@ -102,6 +102,7 @@ struct sb_mesh {
     uint32_t *radixWs = nullptr;     // in the arena
     uint32_t *scanScratch = nullptr; // in the arena
     uint32_t *hCounts = nullptr;     // pinned: [0] total refs, [1..3] big-list lengths
+    uint32_t *hErr = nullptr;        // pinned: index-validation flag read back with the counts
     bool gridSized = false;          // reference list already sized by an earlier build
 };
 
@@ -327,7 +328,8 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
         delete m;
         return fail(SB_ERR_CUDA, "stream/event creation failed");
     }
-    m->hCounts = ctx->hPool + 4 * (ctx->hPoolNext++ % 256);
+    m->hCounts = ctx->hPool + 8 * (ctx->hPoolNext++ % 256);
+    m->hErr = m->hCounts + 4;
     order_after_context(ctx, m); // the arena was allocated in context-stream order
     *out = m;
     return SB_OK;
@@ -366,7 +368,7 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SB_CUDA(cudaMalloc(&c->dScalars, 256));
     SB_CUDA(cudaMallocHost(&c->hScalars, 256));
-    SB_CUDA(cudaMallocHost(&c->hPool, 256 * 16));
+    SB_CUDA(cudaMallocHost(&c->hPool, 256 * 32));
     SB_CUDA(cudaEventCreate(&c->t0));
     SB_CUDA(cudaEventCreateWithFlags(&c->orderEvent, cudaEventDisableTiming));
     SB_CUDA(cudaEventRecord(c->t0, c->stream));
@@ -562,7 +564,11 @@ int sb_mesh_build(sb_mesh *m)
         uint32_t *h = m->hCounts;
         SB_CUDA(cudaMemcpyAsync(h, m->d.gridBigCount + 6, 4, cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, st));
+        int *hErr = reinterpret_cast<int *>(m->hErr);
+        SB_CUDA(cudaMemcpyAsync(hErr, m->d.err, sizeof(int), cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaStreamSynchronize(st));
+        if (*hErr)
+            return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
         size_t nRefs = h[0];
         uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
         for (int k = 0; k < 3; ++k)
