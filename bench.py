@@ -307,13 +307,11 @@ def run_ours(args):
         with torch.cuda.stream(ext):
             if world > 1:
                 flagsA.zero_(); flagsB.zero_()
-            ma.build(); mb.build()
-            x = ma.intersect(mb, begin=a0, end=a1)
-            ma.classify_faces_device(mb, flagsA.data_ptr(), a0, a1)
-            r1 = ctx.classify_stats()
-            mb.classify_faces_device(ma, flagsB.data_ptr(), b0, b1)
-            r2 = ctx.classify_stats()
-            rays_cands[0], rays_cands[1] = r1[0] + r2[0], r1[1] + r2[1]
+            ma.build(); mb.build()          # concurrent: each mesh builds on its own stream
+            # sb_front_end_range: intersection on the context stream, the two
+            # classification directions overlapped on internal streams
+            x = sb.Isect.front_end(ma, mb, flagsA.data_ptr(), flagsB.data_ptr(), a_range=(a0, a1), b_range=(b0, b1))
+            rays_cands[0], rays_cands[1] = ctx.classify_stats()
             if world > 1:
                 P, H = gather_results(x)
             else:
@@ -373,8 +371,8 @@ def run_ours(args):
         rays_total, cands_total = rays, cands
 
     # ---------------- host-buffer loop: `e2e` ----------------
-    out_in_a = np.zeros(nA, np.uint8)
-    out_in_b = np.zeros(nB, np.uint8)
+    out_in_a_t = torch.zeros(nA, dtype=torch.uint8).pin_memory()
+    out_in_b_t = torch.zeros(nB, dtype=torch.uint8).pin_memory()
 
     def e2e_step():
         with torch.cuda.stream(ext):
@@ -383,21 +381,18 @@ def run_ours(args):
             xa = sb.Mesh.from_pointers(ctx, pin[0].data_ptr(), nVA, pin[1].data_ptr(), nA, build=False, keep=pin)
             xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=False, keep=pin)
             xa.build(); xb.build()
-            x = xa.intersect(xb, begin=a0, end=a1)
             if world > 1:
                 flagsA.zero_(); flagsB.zero_()
-                xa.classify_faces_device(xb, flagsA.data_ptr(), a0, a1)
-                xb.classify_faces_device(xa, flagsB.data_ptr(), b0, b1)
+            x = sb.Isect.front_end(xa, xb, flagsA.data_ptr(), flagsB.data_ptr(), a_range=(a0, a1), b_range=(b0, b1))
+            if world > 1:
                 Pg, Hg = gather_results(x)
-                if rank == 0:
-                    out_in_a[:] = flagsA.cpu().numpy()
-                    out_in_b[:] = flagsB.cpu().numpy()
-                    x.hits()
             else:
-                hab, hseg = x.hits()
-                xa.classify_faces_against(xb, per_axis=False, out=out_in_a)
-                xb.classify_faces_against(xa, per_axis=False, out=out_in_b)
                 Pg, Hg = x.num_candidates, x.num_hits
+            if rank == 0:  # results back to the host: hit pairs + segments, per-face flags
+                x.hits()
+                out_in_a_t.copy_(flagsA, non_blocking=True)
+                out_in_b_t.copy_(flagsB, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
             x.close(); xa.close(); xb.close()
         return Pg, Hg
 
@@ -456,10 +451,18 @@ def run_ours(args):
                                     "sample": sample_description(detail, threads), "front_end_ms": sec * 1e3,
                                     "H": Href, "P": detail["P"]}
         print(json.dumps(line), flush=True)
+    # release everything that was used on the library's stream while that stream is alive
+    # (torch's pinned-memory allocator records an event on the stream a block was used on)
+    torch.cuda.synchronize()
+    del out_in_a_t, out_in_b_t, flagsA, flagsB, l2_flush, pin
     ma.close(); mb.close()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)  # skip interpreter teardown: CUDA objects of two runtimes have no defined order there
 
 
 def _as_tensor(torch, ptr, shape, dtype, dev):

@@ -170,6 +170,20 @@ int sb_classify_faces(const sb_mesh *query, const sb_mesh *target,
 int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target,
                              size_t begin, size_t end, void *d_inside);
 
+/* ---- the whole front end of one boolean in one call ------------------------------
+ * sb_intersect(A, B) on the context stream, overlapped with the classification of
+ * A's faces against B and of B's faces against A on two internal streams (what
+ * SolidBoolean::combine() needs from the GPU: src/solidboolean.cpp:292, 315-320 and
+ * the isPointInMesh calls of :468-472 applied to every face).  d_insideA / d_insideB:
+ * caller-owned DEVICE buffers of nT(A) / nT(B) bytes indexed by original triangle id.
+ * The _range form restricts A's triangles (for the intersection and as queries) and
+ * B's query triangles to Morton-sorted position ranges -- the multi-GPU shard. */
+int sb_front_end(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out,
+                 void *d_insideA, void *d_insideB);
+int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t a_begin, size_t a_end,
+                       size_t b_begin, size_t b_end, unsigned flags, sb_isect **out,
+                       void *d_insideA, void *d_insideB);
+
 /* ---- instrumentation --------------------------------------------------------
  * Stage timing with CUDA events on the context stream.  Stages accumulate the
  * device time of the kernels they enclose since the last reset. */

@@ -21,11 +21,15 @@ for it in range(reps):
     ctx.reset_timing()
     t0 = time.perf_counter()
     ma.build(); mb.build()
-    x = ma.intersect(mb)
-    ma.classify_faces_device(mb, da.data_ptr())
-    rA = ctx.classify_stats()
-    mb.classify_faces_device(ma, db.data_ptr())
-    rB = ctx.classify_stats()
+    if "--serial" in sys.argv:
+        x = ma.intersect(mb)
+        ma.classify_faces_device(mb, da.data_ptr())
+        rA = ctx.classify_stats()
+        mb.classify_faces_device(ma, db.data_ptr())
+        rB = ctx.classify_stats()
+    else:
+        x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+        rA = rB = ctx.classify_stats()
     ctx.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
     ms, launches = ctx.timing()

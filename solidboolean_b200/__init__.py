@@ -76,6 +76,8 @@ ABI = {
     "sb_classify": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "sb_classify_faces": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sb_classify_faces_device": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
+    "sb_front_end": (C.c_int, [_vp, _vp, C.c_uint, C.POINTER(_vp), _vp, _vp]),
+    "sb_front_end_range": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, C.c_uint, C.POINTER(_vp), _vp, _vp]),
     "sb_context_enable_timing": (C.c_int, [_vp, C.c_int]),
     "sb_context_reset_timing": (C.c_int, [_vp]),
     "sb_context_get_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
@@ -289,6 +291,21 @@ class Mesh:
 
 class Isect:
     """Candidate pairs + intersecting pairs of two meshes (sb_isect)."""
+
+    @classmethod
+    def front_end(cls, a: Mesh, b: Mesh, d_inside_a: int, d_inside_b: int, flags=0, a_range=None, b_range=None):
+        """sb_front_end(_range): intersection + both classifications, overlapped."""
+        self = cls.__new__(cls)
+        self.a, self.b, self.lib = a, b, a.lib
+        h = _vp()
+        a0, a1 = a_range if a_range else (0, a.num_triangles)
+        b0, b1 = b_range if b_range else (0, b.num_triangles)
+        _check(self.lib.sb_front_end_range(a.h, b.h, a0, a1, b0, b1, flags, C.byref(h), _vp(d_inside_a), _vp(d_inside_b)))
+        self.h = h
+        nc, nh = _sz(0), _sz(0)
+        _check(self.lib.sb_isect_counts(h, C.byref(nc), C.byref(nh)))
+        self.num_candidates, self.num_hits = int(nc.value), int(nh.value)
+        return self
 
     def __init__(self, a: Mesh, b: Mesh, flags=0, begin=None, end=None):
         self.a, self.b = a, b

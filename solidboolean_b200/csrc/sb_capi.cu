@@ -82,7 +82,15 @@ struct sb_context {
     uint32_t *overflowList = nullptr;
     uint32_t overflowCap = 0;
     uint64_t lastRays = 0, lastCands = 0;
-    double candPerRayHint = 3.0;     // sizes the candidate list; adapts to the last call
+    // "lanes": stream + device/host counter block.  Lane 0 is the context stream; lanes 1
+    // and 2 let the two classification directions of sb_front_end overlap the
+    // intersection stages.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        DeviceScalars *d = nullptr, *h = nullptr;
+        cudaEvent_t done = nullptr;
+        double candPerRayHint = 3.0; // sizes the candidate list; adapts to the last call
+    } lanes[3];
     uint32_t *scanScratch = nullptr; // grid-build scan status words
     size_t scanScratchWords = 0;
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
@@ -369,6 +377,15 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaMalloc(&c->dScalars, 256));
     SB_CUDA(cudaMallocHost(&c->hScalars, 256));
     SB_CUDA(cudaMallocHost(&c->hPool, 256 * 32));
+    for (int l = 0; l < 3; ++l) {
+        c->lanes[l].d = reinterpret_cast<DeviceScalars *>(reinterpret_cast<char *>(c->dScalars) + 64 * l);
+        c->lanes[l].h = reinterpret_cast<DeviceScalars *>(reinterpret_cast<char *>(c->hScalars) + 64 * l);
+        if (l == 0)
+            c->lanes[l].stream = c->stream;
+        else
+            SB_CUDA(cudaStreamCreateWithFlags(&c->lanes[l].stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&c->lanes[l].done, cudaEventDisableTiming));
+    }
     SB_CUDA(cudaEventCreate(&c->t0));
     SB_CUDA(cudaEventCreateWithFlags(&c->orderEvent, cudaEventDisableTiming));
     SB_CUDA(cudaEventRecord(c->t0, c->stream));
@@ -403,6 +420,14 @@ void sb_context_destroy(sb_context *c)
     cudaFree(c->dScalars);
     cudaFreeHost(c->hScalars);
     cudaFreeHost(c->hPool);
+    for (int l = 0; l < 3; ++l) {
+        if (l && c->lanes[l].stream) {
+            cudaStreamSynchronize(c->lanes[l].stream);
+            cudaStreamDestroy(c->lanes[l].stream);
+        }
+        if (c->lanes[l].done)
+            cudaEventDestroy(c->lanes[l].done);
+    }
     cudaEventDestroy(c->t0);
     cudaEventDestroy(c->orderEvent);
     cudaFree(c->classifyOut);
@@ -1025,38 +1050,68 @@ int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret
 
 // ---- classification --------------------------------------------------------------
 
-// Runs the three classification kernels and reads the candidate count back; if
-// the candidate list was too small the pass is repeated once with the exact size.
-static int classify_run(sb_context *c, const sb_mesh *target, ClassifyArgs a)
+// One classification pass on a lane: launch enqueues the three kernels and the
+// counter read-back; finish waits for the lane, and if the candidate list was too
+// small repeats the pass once with the exact size.
+struct ClassifyJob {
+    void *scratch = nullptr;
+    unsigned long long cap = 0, rays = 0;
+    bool launched = false;
+};
+
+static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a,
+    ClassifyJob &job, unsigned long long forceCap = 0)
 {
     const uint32_t points = a.end - a.begin;
-    const bool faces = a.pts == nullptr;
-    const unsigned long long rays = 3ull * points;
-    unsigned long long cap = std::max<unsigned long long>(4096, (unsigned long long)(c->candPerRayHint * (double)rays) + 1024);
+    job.rays = 3ull * points;
+    job.cap = forceCap ? forceCap
+                       : std::max<unsigned long long>(4096, (unsigned long long)(lane.candPerRayHint * (double)job.rays) + 1024);
+    size_t bytes = sbk_classify_scratch_bytes(points, job.cap, a.pts == nullptr);
+    SB_CUDA(cudaMallocAsync(&job.scratch, bytes, lane.stream));
+    SB_CUDA(cudaMemsetAsync(lane.d, 0, sizeof(DeviceScalars), lane.stream));
+    {
+        StageTimer t(c, SB_STAGE_CLASSIFY, lane.stream);
+        SB_CUDA(sbk_classify(lane.stream, target->d, a, job.scratch, job.cap, &lane.d->stats[1], &lane.d->stats[0], c->lc));
+    }
+    SB_CUDA(cudaMemcpyAsync(lane.h, lane.d, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, lane.stream));
+    job.launched = true;
+    return SB_OK;
+}
+
+static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a,
+    ClassifyJob &job, bool accumulateStats)
+{
     for (int attempt = 0; attempt < 2; ++attempt) {
-        size_t bytes = sbk_classify_scratch_bytes(points, cap, faces);
-        void *scratch = nullptr;
-        SB_CUDA(cudaMallocAsync(&scratch, bytes, c->stream));
-        SB_CUDA(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
-        {
-            StageTimer t(c, SB_STAGE_CLASSIFY);
-            SB_CUDA(sbk_classify(c->stream, target->d, a, scratch, cap, &c->dScalars->stats[1], &c->dScalars->stats[0], c->lc));
-        }
-        SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
-        SB_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFreeAsync(scratch, c->stream);
-        const unsigned long long cands = c->hScalars->stats[1]; // list entries (quantised matches)
-        c->lastRays = rays;
-        c->lastCands = c->hScalars->stats[0];                   // exact candidates
-        if (rays)
-            c->candPerRayHint = std::max(0.25, 1.25 * (double)cands / (double)rays);
-        if (cands <= cap)
+        SB_CUDA(cudaStreamSynchronize(lane.stream));
+        cudaFreeAsync(job.scratch, lane.stream);
+        job.scratch = nullptr;
+        const unsigned long long entries = lane.h->stats[1]; // list entries (quantised matches)
+        if (job.rays)
+            lane.candPerRayHint = std::max(0.25, 1.25 * (double)entries / (double)job.rays);
+        if (getenv("SB_DEBUG"))
+            fprintf(stderr, "[sb] classify: rays %llu list entries %llu exact candidates %llu cap %llu\n", job.rays, entries,
+                (unsigned long long)lane.h->stats[0], job.cap);
+        if (entries <= job.cap) {
+            c->lastRays = (accumulateStats ? c->lastRays : 0) + job.rays;
+            c->lastCands = (accumulateStats ? c->lastCands : 0) + lane.h->stats[0]; // exact candidates
             return SB_OK;
+        }
         if (attempt == 1)
-            return fail(SB_ERR_CAPACITY, "candidate list overflow after retry (%llu > %llu)", cands, cap);
-        cap = cands;
+            return fail(SB_ERR_CAPACITY, "candidate list overflow after retry (%llu > %llu)", entries, job.cap);
+        int r = classify_launch(c, lane, target, a, job, entries);
+        if (r)
+            return r;
     }
     return SB_OK;
+}
+
+static int classify_run(sb_context *c, const sb_mesh *target, ClassifyArgs a)
+{
+    ClassifyJob job;
+    int r = classify_launch(c, c->lanes[0], target, a, job);
+    if (r)
+        return r;
+    return classify_finish(c, c->lanes[0], target, a, job, false);
 }
 
 int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *inside, uint8_t *per_axis)
@@ -1173,6 +1228,71 @@ int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target, size_t
     // the slow path for overflowing rays needs the counters on the host, so this
     // call synchronises once after the kernel (a 40-byte read-back)
     return classify_faces_impl(query, target, begin, end, true, static_cast<uint8_t *>(d_inside), &dIn, &dAx);
+}
+
+int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t aEnd, size_t bBegin, size_t bEnd,
+    unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
+{
+    if (!A || !B || !out || !d_insideA || !d_insideB)
+        return fail(SB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (A->ctx != B->ctx)
+        return fail(SB_ERR_INVALID, "meshes belong to different contexts");
+    if (!A->built || !B->built)
+        return fail(SB_ERR_INVALID, "mesh not built");
+    sb_context *c = A->ctx;
+    DeviceGuard g(c->device);
+    aEnd = std::min<size_t>(aEnd, A->d.nT);
+    bEnd = std::min<size_t>(bEnd, B->d.nT);
+    aBegin = std::min(aBegin, aEnd);
+    bBegin = std::min(bBegin, bEnd);
+    if (aBegin % 32 || bBegin % 32)
+        return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
+    // the two classification directions run on their own lanes, behind whatever the
+    // context stream has enqueued so far and behind the builds they read
+    cudaEventRecord(c->orderEvent, c->stream);
+    ClassifyArgs qa, qb;
+    qa.queryMesh = &A->d; qa.begin = (uint32_t)aBegin; qa.end = (uint32_t)aEnd; qa.inside = static_cast<uint8_t *>(d_insideA);
+    qb.queryMesh = &B->d; qb.begin = (uint32_t)bBegin; qb.end = (uint32_t)bEnd; qb.inside = static_cast<uint8_t *>(d_insideB);
+    ClassifyJob ja, jb;
+    int r = SB_OK;
+    for (int l = 1; l <= 2 && !r; ++l) {
+        sb_context::Lane &lane = c->lanes[l];
+        cudaStreamWaitEvent(lane.stream, c->orderEvent, 0);
+        cudaStreamWaitEvent(lane.stream, A->ready, 0);
+        cudaStreamWaitEvent(lane.stream, B->ready, 0);
+        const sb_mesh *target = l == 1 ? B : A;
+        const ClassifyArgs &q = l == 1 ? qa : qb;
+        if (q.end > q.begin && target->d.nT)
+            r = classify_launch(c, lane, target, q, l == 1 ? ja : jb);
+        else if (q.end > q.begin) // empty target: nothing is inside it
+            cudaMemsetAsync(q.inside, 0, q.queryMesh->nT, lane.stream);
+    }
+    // broad + narrow phase on the context stream meanwhile
+    int ri = r ? r : sb_intersect_range(A, B, aBegin, aEnd, flags, out);
+    c->lastRays = c->lastCands = 0;
+    if (ja.launched) {
+        int rf = classify_finish(c, c->lanes[1], B, qa, ja, true);
+        if (!r) r = rf;
+    }
+    if (jb.launched) {
+        int rf = classify_finish(c, c->lanes[2], A, qb, jb, true);
+        if (!r) r = rf;
+    }
+    cudaStreamSynchronize(c->lanes[1].stream);
+    cudaStreamSynchronize(c->lanes[2].stream);
+    if (!r)
+        r = ri;
+    if (r && *out) {
+        sb_isect_destroy(*out);
+        *out = nullptr;
+    }
+    return r;
+}
+
+int sb_front_end(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
+{
+    return sb_front_end_range(A, B, 0, A ? A->d.nT : 0, 0, B ? B->d.nT : 0, flags, out, d_insideA, d_insideB);
 }
 
 } // extern "C"

@@ -129,6 +129,21 @@ __global__ void __launch_bounds__(256) grid_bin_kernel(const double2 *__restrict
         return;
     }
     const uint32_t base = g.cellBase[a], nu = g.nu[a];
+    if (FILL && cu1 - cu0 <= 1 && cv1 - cv0 <= 1) {
+        // common case (footprint at most 2 x 2 cells): all atomics are issued before the
+        // first dependent store, so their round trips overlap instead of adding up
+        const bool du = cu1 != cu0, dv = cv1 != cv0;
+        const uint32_t c00 = base + cv0 * nu + cu0;
+        uint32_t p00 = atomicSub(&E[c00 + 1], 1u) - 1u, p10 = 0, p01 = 0, p11 = 0;
+        if (du) p10 = atomicSub(&E[c00 + 2], 1u) - 1u;
+        if (dv) p01 = atomicSub(&E[c00 + nu + 1], 1u) - 1u;
+        if (du && dv) p11 = atomicSub(&E[c00 + nu + 2], 1u) - 1u;
+        if (p00 < refCap) refs[p00] = rec;
+        if (du && p10 < refCap) refs[p10] = rec;
+        if (dv && p01 < refCap) refs[p01] = rec;
+        if (du && dv && p11 < refCap) refs[p11] = rec;
+        return;
+    }
     for (uint32_t cv = cv0; cv <= cv1; ++cv)
         for (uint32_t cu = cu0; cu <= cu1; ++cu) {
             uint32_t cell = base + cv * nu + cu;

@@ -339,6 +339,38 @@ def test_sharded_ranges_cover_whole(ctx):
     whole.close(); ma.close(); mb.close()
 
 
+def test_front_end_overlapped_equals_separate_calls(ctx):
+    """sb_front_end(_range) = sb_intersect + both sb_classify_faces, stages overlapped."""
+    import torch
+    a, b = meshgen.icosphere(5), meshgen.torus(96, 48, center=(0.013, 0.007, 0.011))
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    ref_x = ma.intersect(mb)
+    ia, _ = ma.classify_faces_against(mb)
+    ib, _ = mb.classify_faces_against(ma)
+    da = torch.full((len(a[1]),), 7, dtype=torch.uint8, device="cuda")
+    db = torch.full((len(b[1]),), 7, dtype=torch.uint8, device="cuda")
+    x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+    assert np.array_equal(da.cpu().numpy(), ia) and np.array_equal(db.cpu().numpy(), ib)
+    for u, v in zip(x.candidates() + x.hits(), ref_x.candidates() + ref_x.hits()):
+        assert u.tobytes() == v.tobytes()
+    rays, cands = ctx.classify_stats()
+    assert rays == 3 * (len(a[1]) + len(b[1])) and cands > 0
+    # sharded: two halves of each query set fill disjoint parts of the flag arrays
+    da.fill_(0); db.fill_(0)
+    na, nb = len(a[1]), len(b[1])
+    ca, cb = (na // 2) // 32 * 32, (nb // 2) // 32 * 32
+    parts = []
+    for ra, rb in (((0, ca), (0, cb)), ((ca, na), (cb, nb))):
+        ta = torch.zeros_like(da); tb = torch.zeros_like(db)
+        xs = sb.Isect.front_end(ma, mb, ta.data_ptr(), tb.data_ptr(), a_range=ra, b_range=rb)
+        da += ta; db += tb
+        parts.append(xs.hits()[0]); xs.close()
+    assert np.array_equal(da.cpu().numpy(), ia) and np.array_equal(db.cpu().numpy(), ib)
+    hab = np.concatenate(parts)
+    assert np.array_equal(hab[np.lexsort((hab[:, 1], hab[:, 0]))], ref_x.hits()[0])
+    x.close(); ref_x.close(); ma.close(); mb.close()
+
+
 def test_no_sort_flag_same_set(ctx):
     a, b = meshgen.icosphere(4), meshgen.icosphere(4, center=(0.71, 0.13, 0.07))
     ma, mb = ctx.mesh(*a), ctx.mesh(*b)
