@@ -266,14 +266,15 @@ class Mesh:
     def intersect(self, other: "Mesh", flags=0, begin=None, end=None) -> "Isect":
         return Isect(self, other, flags, begin, end)
 
-    def classify(self, pts):
-        """isPointInMesh majority vote for explicit points against THIS mesh."""
+    def classify(self, pts, per_axis=True):
+        """isPointInMesh majority vote for explicit points against THIS mesh.
+        per_axis=False lets the library skip the third ray wherever the first two agree."""
         p = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
         q = p.shape[0]
         inside = np.zeros(q, np.uint8)
-        per_axis = np.zeros((q, 3), np.uint8)
-        _check(self.lib.sb_classify(self.h, _ptr(p), q, _ptr(inside), _ptr(per_axis)))
-        return inside, per_axis
+        axes = np.zeros((q, 3), np.uint8) if per_axis else None
+        _check(self.lib.sb_classify(self.h, _ptr(p), q, _ptr(inside), _ptr(axes)))
+        return inside, axes
 
     def classify_faces_against(self, target: "Mesh", per_axis=True, out=None):
         """Classify this mesh's face centroids against `target`.

@@ -1050,28 +1050,36 @@ int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret
 
 // ---- classification --------------------------------------------------------------
 
-// One classification pass on a lane: launch enqueues the three kernels and the
-// counter read-back; finish waits for the lane, and if the candidate list was too
-// small repeats the pass once with the exact size.
+// One classification on a lane: launch enqueues the kernels of a pass and the counter
+// read-back; finish waits for the lane, repeats the pass once with the exact size if
+// the ray/triangle list was too small, and runs the second pass of the lazy vote when
+// some points are still undecided.
 struct ClassifyJob {
     void *scratch = nullptr;
     unsigned long long cap = 0, rays = 0;
+    uint32_t points = 0;
+    ClassifyPass pass;
     bool launched = false;
 };
 
 static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a,
     ClassifyJob &job, unsigned long long forceCap = 0)
 {
-    const uint32_t points = a.end - a.begin;
-    job.rays = 3ull * points;
+    if (!job.launched) { // first pass: all three axes when per-axis bits are wanted, else the lazy vote
+        job.pass = ClassifyPass();
+        job.pass.naxes = a.perAxis ? 3 : 2;
+        job.points = a.end - a.begin;
+    }
+    job.rays = (unsigned long long)job.pass.naxes * job.points;
     job.cap = forceCap ? forceCap
                        : std::max<unsigned long long>(4096, (unsigned long long)(lane.candPerRayHint * (double)job.rays) + 1024);
-    size_t bytes = sbk_classify_scratch_bytes(points, job.cap, a.pts == nullptr);
+    size_t bytes = sbk_classify_scratch_bytes(job.points, job.cap, job.pass.naxes);
     SB_CUDA(cudaMallocAsync(&job.scratch, bytes, lane.stream));
     SB_CUDA(cudaMemsetAsync(lane.d, 0, sizeof(DeviceScalars), lane.stream));
     {
         StageTimer t(c, SB_STAGE_CLASSIFY, lane.stream);
-        SB_CUDA(sbk_classify(lane.stream, target->d, a, job.scratch, job.cap, &lane.d->stats[1], &lane.d->stats[0], c->lc));
+        SB_CUDA(sbk_classify(lane.stream, target->d, a, job.pass, job.scratch, job.cap, &lane.d->stats[1], &lane.d->stats[0],
+            &lane.d->overflowCount, c->lc));
     }
     SB_CUDA(cudaMemcpyAsync(lane.h, lane.d, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, lane.stream));
     job.launched = true;
@@ -1081,28 +1089,54 @@ static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh 
 static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a,
     ClassifyJob &job, bool accumulateStats)
 {
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    if (!accumulateStats)
+        c->lastRays = c->lastCands = 0;
+    void *firstScratch = nullptr; // keeps the undecided list alive during the second pass
+    int attempt = 0;
+    while (true) {
         SB_CUDA(cudaStreamSynchronize(lane.stream));
-        cudaFreeAsync(job.scratch, lane.stream);
-        job.scratch = nullptr;
         const unsigned long long entries = lane.h->stats[1]; // list entries (quantised matches)
-        if (job.rays)
+        const uint32_t undecided = lane.h->overflowCount;
+        if (job.rays && job.pass.naxes > 1)
             lane.candPerRayHint = std::max(0.25, 1.25 * (double)entries / (double)job.rays);
         if (getenv("SB_DEBUG"))
-            fprintf(stderr, "[sb] classify: rays %llu list entries %llu exact candidates %llu cap %llu\n", job.rays, entries,
-                (unsigned long long)lane.h->stats[0], job.cap);
-        if (entries <= job.cap) {
-            c->lastRays = (accumulateStats ? c->lastRays : 0) + job.rays;
-            c->lastCands = (accumulateStats ? c->lastCands : 0) + lane.h->stats[0]; // exact candidates
-            return SB_OK;
+            fprintf(stderr, "[sb] classify pass(axis0=%d,n=%d): rays %llu list entries %llu exact %llu cap %llu undecided %u\n",
+                job.pass.axis0, job.pass.naxes, job.rays, entries, (unsigned long long)lane.h->stats[0], job.cap, undecided);
+        if (entries > job.cap) { // list too small: repeat this pass with the exact size
+            cudaFreeAsync(job.scratch, lane.stream);
+            job.scratch = nullptr;
+            if (++attempt > 1) {
+                if (firstScratch)
+                    cudaFreeAsync(firstScratch, lane.stream);
+                return fail(SB_ERR_CAPACITY, "ray/triangle list overflow after retry (%llu > %llu)", entries, job.cap);
+            }
+            int r = classify_launch(c, lane, target, a, job, entries);
+            if (r)
+                return r;
+            continue;
         }
-        if (attempt == 1)
-            return fail(SB_ERR_CAPACITY, "candidate list overflow after retry (%llu > %llu)", entries, job.cap);
-        int r = classify_launch(c, lane, target, a, job, entries);
-        if (r)
-            return r;
+        c->lastRays += job.rays;
+        c->lastCands += lane.h->stats[0]; // exact candidates
+        if (job.pass.naxes == 2 && undecided) {
+            // second pass of the lazy vote: the third axis, only where the first two disagree
+            firstScratch = job.scratch;
+            job.pass.list = sbk_classify_undecided_list(firstScratch, job.points, job.cap, 2);
+            job.pass.listCount = undecided;
+            job.pass.axis0 = 2;
+            job.pass.naxes = 1;
+            job.points = undecided;
+            attempt = 0;
+            int r = classify_launch(c, lane, target, a, job, std::max<unsigned long long>(4096, 8ull * undecided));
+            if (r)
+                return r;
+            continue;
+        }
+        cudaFreeAsync(job.scratch, lane.stream);
+        job.scratch = nullptr;
+        if (firstScratch)
+            cudaFreeAsync(firstScratch, lane.stream);
+        return SB_OK;
     }
-    return SB_OK;
 }
 
 static int classify_run(sb_context *c, const sb_mesh *target, ClassifyArgs a)
@@ -1140,7 +1174,7 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
     a.begin = 0;
     a.end = (uint32_t)Q;
     a.inside = c->classifyOut;
-    a.perAxis = c->classifyOut + Q;
+    a.perAxis = per_axis ? c->classifyOut + Q : nullptr; // without it the vote is lazy (third ray on demand)
     if (target->d.nT == 0) {
         SB_CUDA(cudaMemsetAsync(c->classifyOut, 0, 4 * Q, c->stream));
         SB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1157,7 +1191,7 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
     return r;
 }
 
-static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size_t begin, size_t end, bool finish,
+static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size_t begin, size_t end, bool wantPerAxis,
     uint8_t *externalInside, uint8_t **dInside, uint8_t **dPerAxis)
 {
     if (!query || !target)
@@ -1184,7 +1218,7 @@ static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size
     a.begin = (uint32_t)begin;
     a.end = (uint32_t)end;
     a.inside = externalInside ? externalInside : c->classifyOut;
-    a.perAxis = c->classifyOut + n;
+    a.perAxis = wantPerAxis ? c->classifyOut + n : nullptr;
     *dInside = a.inside;
     *dPerAxis = a.perAxis;
     if (target->d.nT == 0) {
@@ -1193,7 +1227,6 @@ static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size
             SB_CUDA(cudaMemsetAsync(externalInside, 0, n, c->stream));
         return SB_OK;
     }
-    (void)finish;
     return classify_run(c, target, a);
 }
 
@@ -1205,7 +1238,7 @@ int sb_classify_faces(const sb_mesh *query, const sb_mesh *target, uint8_t *insi
         return fail(SB_ERR_INVALID, "null mesh");
     DeviceGuard g(query->ctx->device);
     uint8_t *dIn = nullptr, *dAx = nullptr;
-    int r = classify_faces_impl(query, target, 0, query->d.nT, true, nullptr, &dIn, &dAx);
+    int r = classify_faces_impl(query, target, 0, query->d.nT, per_axis != nullptr, nullptr, &dIn, &dAx);
     if (r)
         return r;
     sb_context *c = query->ctx;
@@ -1227,7 +1260,7 @@ int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target, size_t
     uint8_t *dIn = nullptr, *dAx = nullptr;
     // the slow path for overflowing rays needs the counters on the host, so this
     // call synchronises once after the kernel (a 40-byte read-back)
-    return classify_faces_impl(query, target, begin, end, true, static_cast<uint8_t *>(d_inside), &dIn, &dAx);
+    return classify_faces_impl(query, target, begin, end, false, static_cast<uint8_t *>(d_inside), &dIn, &dAx);
 }
 
 int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t aEnd, size_t bBegin, size_t bEnd,
@@ -1271,12 +1304,15 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
     // broad + narrow phase on the context stream meanwhile
     int ri = r ? r : sb_intersect_range(A, B, aBegin, aEnd, flags, out);
     c->lastRays = c->lastCands = 0;
+    bool firstStats = true;
     if (ja.launched) {
-        int rf = classify_finish(c, c->lanes[1], B, qa, ja, true);
+        int rf = classify_finish(c, c->lanes[1], B, qa, ja, !firstStats);
+        firstStats = false;
         if (!r) r = rf;
     }
     if (jb.launched) {
-        int rf = classify_finish(c, c->lanes[2], A, qb, jb, true);
+        int rf = classify_finish(c, c->lanes[2], A, qb, jb, !firstStats);
+        firstStats = false;
         if (!r) r = rf;
     }
     cudaStreamSynchronize(c->lanes[1].stream);

@@ -74,7 +74,17 @@ struct Query {
     uint32_t nT;
     uint32_t begin;      // first point / sorted position
     uint32_t count;      // points in this launch
+    // Lazy majority vote: the first pass traces axes 0 and 1 only (naxes = 2); the third
+    // ray can change the result only where those two disagree, and is traced in a second
+    // pass over just those points (list = their local indices, axis0 = 2, naxes = 1).
+    const uint32_t *list;
+    int axis0, naxes;
 };
+
+__device__ __forceinline__ uint32_t local_point(const Query &q, uint32_t j)
+{
+    return q.list ? __ldg(q.list + j) : j;
+}
 
 // Walk the ray's cell list(s) in a fixed order; visit(triangle id) for each
 // triangle whose QUANTISED box overlaps the quantised ray box (a superset of the
@@ -133,7 +143,7 @@ __device__ __forceinline__ bool query_point(const Query &q, uint32_t j, d3 &p, u
 {
     if (j >= q.count)
         return false;
-    const uint32_t idx = q.begin + j;
+    const uint32_t idx = q.begin + local_point(q, j);
     if (q.pts) {
         p = {q.pts[3 * (size_t)idx], q.pts[3 * (size_t)idx + 1], q.pts[3 * (size_t)idx + 2]};
         outIndex = idx;
@@ -157,7 +167,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) ray_scan_kernel(Query q, Target 
     if (threadIdx.x == 0)
         g = *T.gp;
     __syncthreads();
-    const int axis = blockIdx.x / blocksPerAxis;
+    const int slot = blockIdx.x / blocksPerAxis;
+    const int axis = q.axis0 + slot;
     const uint32_t j = (blockIdx.x % blocksPerAxis) * SCAN_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
 
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) ray_scan_kernel(Query q, Target 
     if (!active)
         return;
     const unsigned long long first = base + incl - n;
-    const uint32_t ray = (uint32_t)axis * q.count + j;
+    const uint32_t ray = (uint32_t)slot * q.count + j;
     rayRange[ray] = make_uint2((uint32_t)min(first, 0xffffffffull), n);
     if (first + n > cap)
         return; // list too small: the host sees candCount > cap and retries
@@ -225,10 +236,10 @@ __global__ void __launch_bounds__(128) ray_hit_kernel(Query q, Target T,
     if (i < total) {
         const uint2 c = __ldg(cand + i);
         // when the list overflowed (the host will retry) some entries below cap were never written
-        if (c.x < 3u * q.count && c.y < nTargetTris) {
-            const int axis = (int)(c.x / q.count);
+        if (c.x < (uint32_t)q.naxes * q.count && c.y < nTargetTris) {
+            const int axis = q.axis0 + (int)(c.x / q.count);
             const uint32_t j = c.x % q.count;
-            const double *src = (q.pts ? q.pts : q.scent) + 3 * (size_t)(q.begin + j);
+            const double *src = (q.pts ? q.pts : q.scent) + 3 * (size_t)(q.begin + local_point(q, j));
             const d3 p = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
             const d3 e = ray_end(p, axis);
             const uint32_t f = c.y;
@@ -260,22 +271,25 @@ __global__ void __launch_bounds__(128) ray_hit_kernel(Query q, Target T,
 // ---- C ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ray_finish_kernel(Query q, const uint2 *__restrict__ rayRange,
     unsigned long long cap, const long long *__restrict__ keys, const uint8_t *__restrict__ hitFlag,
-    uint8_t *__restrict__ inside, uint8_t *__restrict__ perAxis)
+    uint8_t *__restrict__ inside, uint8_t *__restrict__ perAxis, uint32_t *__restrict__ undecided,
+    unsigned int *__restrict__ undecidedCount)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= q.count)
         return;
+    const uint32_t local = local_point(q, j);
     uint32_t outIndex;
     if (q.pts) {
-        outIndex = q.begin + j;
+        outIndex = q.begin + local;
     } else {
-        if (q.begin + j >= q.nT)
+        if (q.begin + local >= q.nT)
             return;
-        outIndex = (uint32_t)load_rec(q.leaf + q.begin + j).ref;
+        outIndex = (uint32_t)load_rec(q.leaf + q.begin + local).ref;
     }
     int insideCount = 0;
-    for (int axis = 0; axis < 3; ++axis) {
-        const uint2 r = __ldg(rayRange + (size_t)axis * q.count + j);
+    bool first = false;
+    for (int slot = 0; slot < q.naxes; ++slot) {
+        const uint2 r = __ldg(rayRange + (size_t)slot * q.count + j);
         uint32_t distinct = 0;
         if (r.y && (unsigned long long)r.x + r.y <= cap) {
             uint32_t hits = 0;
@@ -298,30 +312,54 @@ __global__ void __launch_bounds__(256) ray_finish_kernel(Query q, const uint2 *_
                 }
             }
         }
-        const bool in = (distinct & 1u) != 0;
+        const bool in = (distinct & 1u) != 0; // odd number of distinct crossings (:89)
         if (perAxis)
-            perAxis[3 * (size_t)outIndex + axis] = in ? 1 : 0;
+            perAxis[3 * (size_t)outIndex + q.axis0 + slot] = in ? 1 : 0;
         insideCount += in ? 1 : 0;
+        if (slot == 0)
+            first = in;
     }
-    // (float)insideCount / totalCount > 0.5 with totalCount == 3
-    inside[outIndex] = insideCount >= 2 ? 1 : 0;
+    if (q.naxes == 3) {
+        // (float)insideCount / totalCount > 0.5 with totalCount == 3 (:508)
+        inside[outIndex] = insideCount >= 2 ? 1 : 0;
+    } else if (q.naxes == 2) {
+        if (insideCount != 1) {
+            inside[outIndex] = first ? 1 : 0; // two equal votes already are the majority
+        } else {
+            const unsigned int slot = atomicAdd(undecidedCount, 1u);
+            undecided[slot] = local;         // the third ray decides
+        }
+    } else {
+        inside[outIndex] = insideCount ? 1 : 0; // votes 0 and 1 disagreed: the majority is vote 2
+    }
 }
 
 } // namespace
 
-size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, bool facesMode)
+size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, int naxes)
 {
     size_t b = 0;
-    b += ((size_t)cap * 8 + 255) & ~(size_t)255;      // cand
-    b += ((size_t)cap * 24 + 255) & ~(size_t)255;     // keys
-    b += ((size_t)cap + 255) & ~(size_t)255;          // hit flags
-    b += ((size_t)points * 3 * 8 + 255) & ~(size_t)255; // rayRange
-    (void)facesMode;
+    b += ((size_t)cap * 8 + 255) & ~(size_t)255;               // cand
+    b += ((size_t)cap * 24 + 255) & ~(size_t)255;              // keys
+    b += ((size_t)cap + 255) & ~(size_t)255;                   // hit flags
+    b += ((size_t)points * naxes * 8 + 255) & ~(size_t)255;    // rayRange
+    b += ((size_t)points * 4 + 255) & ~(size_t)255;            // undecided list
     return b + 256;
 }
 
-cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, void *scratch,
-    unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount, LaunchCounter &lc)
+uint32_t *sbk_classify_undecided_list(void *scratch, uint32_t points, unsigned long long cap, int naxes)
+{
+    size_t b = 0;
+    b += ((size_t)cap * 8 + 255) & ~(size_t)255;
+    b += ((size_t)cap * 24 + 255) & ~(size_t)255;
+    b += ((size_t)cap + 255) & ~(size_t)255;
+    b += ((size_t)points * naxes * 8 + 255) & ~(size_t)255;
+    return reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) + b);
+}
+
+cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, const ClassifyPass &pass,
+    void *scratch, unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount,
+    unsigned int *undecidedCount, LaunchCounter &lc)
 {
     if (a.end <= a.begin)
         return cudaSuccess;
@@ -332,7 +370,12 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     q.leaf = qm ? qm->leaf : nullptr;
     q.nT = qm ? qm->nT : 0;
     q.begin = a.begin;
-    q.count = a.end - a.begin;
+    q.count = pass.list ? pass.listCount : a.end - a.begin;
+    q.list = pass.list;
+    q.axis0 = pass.axis0;
+    q.naxes = pass.naxes;
+    if (q.count == 0)
+        return cudaSuccess;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;
@@ -356,13 +399,15 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     uint2 *cand = reinterpret_cast<uint2 *>(take((size_t)cap * 8));
     long long *keys = reinterpret_cast<long long *>(take((size_t)cap * 24));
     uint8_t *hitFlag = reinterpret_cast<uint8_t *>(take((size_t)cap));
-    uint2 *rayRange = reinterpret_cast<uint2 *>(take((size_t)q.count * 3 * 8));
+    uint2 *rayRange = reinterpret_cast<uint2 *>(take((size_t)q.count * q.naxes * 8));
+    uint32_t *undecided = reinterpret_cast<uint32_t *>(take((size_t)q.count * 4));
 
     const uint32_t bpa = (q.count + SCAN_THREADS - 1) / SCAN_THREADS;
-    ray_scan_kernel<<<3 * bpa, SCAN_THREADS, 0, s>>>(q, T, bpa, cand, cap, candCount, rayRange);
+    ray_scan_kernel<<<q.naxes * bpa, SCAN_THREADS, 0, s>>>(q, T, bpa, cand, cap, candCount, rayRange);
     const unsigned long long hitBlocks = (cap + 127) / 128;
     ray_hit_kernel<<<(unsigned)hitBlocks, 128, 0, s>>>(q, T, cand, cap, candCount, target.nT, keys, hitFlag, exactCount);
-    ray_finish_kernel<<<(q.count + 255) / 256, 256, 0, s>>>(q, rayRange, cap, keys, hitFlag, a.inside, a.perAxis);
+    ray_finish_kernel<<<(q.count + 255) / 256, 256, 0, s>>>(q, rayRange, cap, keys, hitFlag, a.inside, a.perAxis, undecided,
+        undecidedCount);
     lc.kernels += 3;
     return cudaGetLastError();
 }

@@ -99,14 +99,26 @@ struct ClassifyArgs {
     uint8_t *inside = nullptr;   // indexed by point index / original triangle id
     uint8_t *perAxis = nullptr;  // optional, 3 per point
 };
-// scratch: sbk_classify_scratch_bytes(points, cap, facesMode) bytes; cap = capacity of
-// the list; *candCount (device, zeroed by the caller) receives the number of list
-// entries (quantised-box matches) -- if it exceeds cap the results are invalid and
-// the call must be repeated with a larger cap; *exactCount receives the number of
-// true ray/triangle candidates (exact box overlap).
-size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, bool facesMode);
-cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, void *scratch,
-    unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount, LaunchCounter &lc);
+// One pass of the classifier.  Full vote: axis0 = 0, naxes = 3.  Lazy vote (only
+// `inside` wanted): pass 1 = axes 0,1 over all points (axis0 = 0, naxes = 2), which
+// appends the points whose two votes disagree to the scratch's undecided list; pass 2
+// = axis 2 over that list (axis0 = 2, naxes = 1, list/listCount set).
+struct ClassifyPass {
+    int axis0 = 0, naxes = 3;
+    const uint32_t *list = nullptr;
+    uint32_t listCount = 0;
+};
+// scratch: sbk_classify_scratch_bytes(points in this pass, cap, naxes) bytes; cap =
+// capacity of the ray/triangle list; *candCount (device, zeroed by the caller)
+// receives the number of list entries (quantised-box matches) -- if it exceeds cap
+// the results are invalid and the pass must be repeated with a larger cap;
+// *exactCount accumulates the true candidates (exact box overlap); *undecidedCount
+// the length of the undecided list (naxes == 2 only).
+size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, int naxes);
+uint32_t *sbk_classify_undecided_list(void *scratch, uint32_t points, unsigned long long cap, int naxes);
+cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, const ClassifyPass &pass,
+    void *scratch, unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount,
+    unsigned int *undecidedCount, LaunchCounter &lc);
 
 size_t sbk_radix_workspace_words(size_t n);
 

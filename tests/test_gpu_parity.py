@@ -246,6 +246,13 @@ def test_explicit_points_vs_oracle(ctx, oracle):
         ins, per = m.classify(pts)
         oi, op, _ = oracle.classify(mesh, pts)
         assert np.array_equal(per, op) and np.array_equal(ins, oi)
+        # lazy vote (third ray only where the first two disagree) gives the same majority;
+        # the on-vertex / on-face points make the axes disagree, so pass 2 really runs
+        lazy, none = m.classify(pts, per_axis=False)
+        assert none is None and np.array_equal(lazy, oi)
+        assert (op[:, 0] != op[:, 1]).sum() > 0
+        rays, _ = ctx.classify_stats()
+        assert rays == 2 * len(pts) + int((op[:, 0] != op[:, 1]).sum())
         m.close()
 
 
@@ -354,7 +361,8 @@ def test_front_end_overlapped_equals_separate_calls(ctx):
     for u, v in zip(x.candidates() + x.hits(), ref_x.candidates() + ref_x.hits()):
         assert u.tobytes() == v.tobytes()
     rays, cands = ctx.classify_stats()
-    assert rays == 3 * (len(a[1]) + len(b[1])) and cands > 0
+    q = len(a[1]) + len(b[1])
+    assert 2 * q <= rays <= 3 * q and cands > 0   # lazy vote: third ray only where two disagree
     # sharded: two halves of each query set fill disjoint parts of the flag arrays
     da.fill_(0); db.fill_(0)
     na, nb = len(a[1]), len(b[1])
