@@ -45,7 +45,7 @@ UNIT = "pairs/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -82,7 +82,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -412,6 +412,13 @@ def run_ours(args):
         # classification bytes = 25 Q + 104 nTarget + 108 C, both launches of a step
         cls_bytes = 25 * (nA + nB) + 104 * (nA + nB) + 108 * cands_total
         cls_ms = stage_ms["classify"]
+        traffic = None
+        try:  # DRAM bytes of the classification kernels of one step, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("config") == args.config and world == 1:
+                traffic = tj["classify_dram_bytes_per_step"]
+        except Exception:
+            pass
         achieved = cls_bytes / (cls_ms * 1e-3) / 1e9 if cls_ms > 0 else 0.0
         build_bytes = 24 * (nVA + nVB) + 296 * (nA + nB)
         broad_bytes = 48 * nA + 104 * nB + 8 * P
@@ -434,8 +441,8 @@ def run_ours(args):
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "stage_gbs_algorithmic": {"build": gbs(build_bytes, stage_ms["build"]), "broad": gbs(broad_bytes, stage_ms["broad"]),
                                       "narrow": gbs(narrow_bytes, stage_ms["narrow"]), "classify": gbs(cls_bytes, cls_ms)},
-            "roofline": {"bound": "hbm", "kernel": "classify_kernel (2 launches/step)", "achieved": round(achieved, 1),
-                         "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "classification: ray_scan + ray_hit + ray_finish kernels, both directions (6+ launches/step)", "achieved": round(achieved, 1),
+                         "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": cls_bytes,
                          "kernel_ms_per_step": round(cls_ms, 4)},
             "e2e": {"value": H2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
