@@ -423,3 +423,50 @@ def test_config_c2_vs_oracle(ctx, oracle):
     oi, op, _ = oracle.classify(b, oracle.centroids(*a))
     assert np.array_equal(pa, op) and np.array_equal(ia, oi)
     x.close(); ma.close(); mb.close()
+
+
+@pytest.mark.slow
+def test_config_c3_full_size_properties(ctx, oracle):
+    """BASELINE config 3 (1,310,720 + 1,048,576 triangles): size-independent properties
+    plus sampled oracle checks (the full oracle classification would take minutes)."""
+    import torch
+    a, b = meshgen.config_c3()
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    da = torch.zeros(len(a[1]), dtype=torch.uint8, device="cuda")
+    db = torch.zeros(len(b[1]), dtype=torch.uint8, device="cuda")
+    x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+    assert (x.num_candidates, x.num_hits) == (36125, 9606)          # BASELINE.md probe table
+    ab, code = x.candidates()
+    hab, seg = x.hits()
+    # sortedness, uniqueness, hits are exactly the candidates with ret=1, coplanar=0
+    key = ab[:, 0].astype(np.int64) << 32 | ab[:, 1]
+    assert np.all(np.diff(key) > 0)
+    assert np.array_equal(hab, ab[code == 1])
+    # the full candidate set against the oracle's own accelerator (exact equality)
+    assert np.array_equal(ab, oracle.candidate_pairs(a, b))
+    ret, cop, hit, oseg = oracle.predicate_pairs(a, b, ab)
+    assert np.array_equal(code, (ret | (cop << 1)).astype(np.uint8))
+    assert seg.tobytes() == oseg[hit.astype(bool)].tobytes()
+    # symmetry: B against A finds the transposed candidate set
+    y = mb.intersect(ma)
+    ba, _ = y.candidates()
+    t = ba[:, ::-1]
+    assert np.array_equal(t[np.lexsort((t[:, 1], t[:, 0]))], ab)
+    y.close()
+    # classification: totals, a 20K-face sample per mesh against the oracle, and
+    # every face far inside / far outside by construction
+    ia, ib = da.cpu().numpy(), db.cpu().numpy()
+    assert (int(ia.sum()), int(ib.sum())) == (454612, 465529)
+    rng = np.random.default_rng(8)
+    sa = rng.choice(len(a[1]), 20000, replace=False)
+    sb_ = rng.choice(len(b[1]), 20000, replace=False)
+    oa, _, _ = oracle.classify(b, oracle.centroids(*a)[sa])
+    ob, _, _ = oracle.classify(a, oracle.centroids(*b)[sb_])
+    assert np.array_equal(ia[sa], oa) and np.array_equal(ib[sb_], ob)
+    cb = oracle.centroids(*b)
+    r = np.linalg.norm(cb, axis=1)
+    assert np.all(ib[r < 0.99] == 1) and np.all(ib[r > 1.01] == 0)   # torus faces inside / outside the unit sphere
+    # the lazy vote equals the full three-axis vote
+    full, per = ma.classify_faces_against(mb)
+    assert np.array_equal(full, ia) and np.array_equal((per.sum(axis=1) >= 2).astype(np.uint8), ia)
+    x.close(); ma.close(); mb.close()
