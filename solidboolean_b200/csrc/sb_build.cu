@@ -281,12 +281,21 @@ cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t
     sbradix::Workspace ws;
     ws.mem = radixWs;
     uint32_t *sk = nullptr, *sv = nullptr;
-    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, 0, 30, ws, smCount, &sk, &sv);
+    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, 30, ws, smCount, &sk, &sv);
     m.sortedKey = sk;
     m.sortedTri = sv;
     leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.tbox, m.cent, m.nT, m.nTpad,
         m.leaf, m.sbox, m.scent, m.cbox, m.ckey);
     lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+// The LBVH topology + inner boxes are only needed when the mesh is the TARGET of a
+// traversal (mesh B of sb_intersect); they are built on first such use.
+cudaError_t sbk_build_tree(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
     if (m.M > 1)
         cudaMemsetAsync(m.slot, 0xff, sizeof(int) * (m.M - 1), s);
     tree_build_kernel<<<(m.M + 255) / 256, 256, 0, s>>>(m.cbox, m.ckey, m.M, m.nodes, m.slot, m.root);

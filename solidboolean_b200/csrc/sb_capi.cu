@@ -94,6 +94,7 @@ struct sb_context {
     uint32_t *scanScratch = nullptr; // grid-build scan status words
     size_t scanScratchWords = 0;
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
+    int sortBeginBit = 0;            // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT)
 };
 
 struct sb_mesh {
@@ -112,6 +113,7 @@ struct sb_mesh {
     uint32_t *hCounts = nullptr;     // pinned: [0] total refs, [1..3] big-list lengths
     uint32_t *hErr = nullptr;        // pinned: index-validation flag read back with the counts
     bool gridSized = false;          // reference list already sized by an earlier build
+    bool treeBuilt = false;          // LBVH topology built (lazily, on first use as a traversal target)
 };
 
 struct sb_isect {
@@ -389,6 +391,8 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaEventCreate(&c->t0));
     SB_CUDA(cudaEventCreateWithFlags(&c->orderEvent, cudaEventDisableTiming));
     SB_CUDA(cudaEventRecord(c->t0, c->stream));
+    if (const char *e = getenv("SB_SORT_BEGIN_BIT"))
+        c->sortBeginBit = std::max(0, std::min(atoi(e), 24));
     if (const char *e = getenv("SB_GRID_BETA")) {
         float b = (float)atof(e);
         if (b > 0.01f && b < 100.0f)
@@ -570,6 +574,7 @@ int sb_mesh_build(sb_mesh *m)
     sb_context *c = m->ctx;
     DeviceGuard g(c->device);
     cudaStream_t st = m->stream;
+    m->d.sortBeginBit = c->sortBeginBit;
     // after whatever the context stream still does with this mesh's buffers
     order_after_context(c, m);
     {
@@ -611,6 +616,23 @@ int sb_mesh_build(sb_mesh *m)
     }
     SB_CUDA(cudaEventRecord(m->ready, st));
     m->built = true;
+    m->treeBuilt = false;
+    return SB_OK;
+}
+
+// LBVH of a traversal target, built on the mesh's stream on first use
+static int ensure_tree(const sb_mesh *mc)
+{
+    sb_mesh *m = const_cast<sb_mesh *>(mc);
+    if (m->treeBuilt)
+        return SB_OK;
+    sb_context *c = m->ctx;
+    {
+        StageTimer t(c, SB_STAGE_BUILD, m->stream);
+        SB_CUDA(sbk_build_tree(m->stream, m->d, c->lc));
+    }
+    SB_CUDA(cudaEventRecord(m->ready, m->stream));
+    m->treeBuilt = true;
     return SB_OK;
 }
 
@@ -697,6 +719,14 @@ int sb_mesh_bounds(const sb_mesh *m, double *out6)
 
 int sb_mesh_bvh_info(const sb_mesh *m, sb_bvh_info *out)
 {
+    if (!m || !out || !m->built)
+        return fail(SB_ERR_INVALID, "null or unbuilt mesh");
+    {
+        DeviceGuard g(m->ctx->device);
+        int rt = ensure_tree(m);
+        if (rt)
+            return rt;
+    }
     int root = 0;
     int r = mesh_download(m, &root, m ? m->d.root : nullptr, sizeof(int));
     if (r)
@@ -710,6 +740,12 @@ int sb_mesh_bvh_info(const sb_mesh *m, sb_bvh_info *out)
 
 int sb_mesh_bvh_nodes(const sb_mesh *m, void *out)
 {
+    if (m && m->built) {
+        DeviceGuard g(m->ctx->device);
+        int rt = ensure_tree(m);
+        if (rt)
+            return rt;
+    }
     size_t nI = m && m->d.M > 1 ? m->d.M - 1 : 0;
     return mesh_download(m, out, m ? m->d.nodes : nullptr, 64 * nI);
 }
@@ -782,6 +818,11 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
     sb_context *c = A->ctx;
     DeviceGuard g(c->device);
+    {
+        int rt = ensure_tree(B);
+        if (rt)
+            return rt;
+    }
     use_mesh(c, A);
     use_mesh(c, B);
     sb_isect *x = new (std::nothrow) sb_isect;

@@ -28,6 +28,7 @@ struct MeshDev {
     uint32_t nV = 0, nT = 0;
     uint32_t nTpad = 0; // nT rounded up to a multiple of 32
     uint32_t M = 0;     // clusters = ceil(nT / K)
+    int sortBeginBit = 0; // Morton bits below this are not sorted (fewer radix passes)
     // geometry as uploaded
     double *xyz = nullptr;   // AoS 3*nV
     uint32_t *tri = nullptr; // 3*nT
@@ -69,6 +70,7 @@ struct LaunchCounter {
 
 // sb_build.cu
 cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t radixWsWords, int smCount, LaunchCounter &lc);
+cudaError_t sbk_build_tree(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
 
 // sb_broad.cu -- candidate keys: (((a << bitsB) | b) << 2), code bits zero
 cudaError_t sbk_broad_phase(cudaStream_t s, const MeshDev &A, const MeshDev &B, uint32_t groupBegin, uint32_t groupEnd,
