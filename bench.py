@@ -302,6 +302,7 @@ def run_ours(args):
     ctx.enable_timing(True)
 
     rays_cands = [0, 0]
+    paths = [0, 0, 0, 0, 0]
 
     def resident_step():
         with torch.cuda.stream(ext):
@@ -316,6 +317,7 @@ def run_ours(args):
                 P, H = gather_results(x)
             else:
                 P, H = x.num_candidates, x.num_hits
+            paths[:] = x.path_counts()
             x.close()
         return P, H
 
@@ -451,6 +453,23 @@ def run_ours(args):
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
         }
+        # FP64 view of the predicate stage: flops = 41 R1 + 82 R2 + 139 R3 + 185 H
+        # (coplanar pairs counted like R3), against the measured non-FMA DMUL+DADD rate
+        try:
+            nofma, fma = ctx.fp64_peak()
+            r1, r2, cop, r3, hh = paths
+            flops = 41 * r1 + 82 * r2 + 139 * (r3 + cop) + 185 * hh
+            pms = stage_ms.get("predicate", 0.0)
+            line["fp64"] = {"predicate_ms_per_step": round(pms, 5), "pairs": int(sum(paths)),
+                            "exit_histogram": {"plane2_reject": r1, "plane1_reject": r2, "coplanar": cop,
+                                               "interval_reject": r3, "segment": hh},
+                            "flops_per_step": flops,
+                            "achieved_gflops": round(flops / (pms * 1e-3) / 1e9, 2) if pms > 0 else None,
+                            "peak_nofma_gflops": round(nofma, 1), "peak_fma_gflops": round(fma, 1),
+                            "frac_of_nofma_peak": round(flops / (pms * 1e-3) / 1e9 / nofma, 5) if pms > 0 and nofma > 0 else None,
+                            "note": "shard of rank 0" if world > 1 else "whole workload"}
+        except Exception as e:  # the microbenchmark must never break the bench line
+            line["fp64"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             sec, Href, detail = cpu_reference_step(a, b, 32768, threads)

@@ -143,6 +143,14 @@ int sb_isect_face_flags(const sb_isect *isect, uint8_t *flagsA, uint8_t *flagsB)
 int sb_isect_device_ptrs(const sb_isect *isect, void **cand_keys, unsigned *bits_b,
                          void **hit_ab, void **hit_seg, void **flagsA, void **flagsB);
 
+/* How the candidate pairs left the predicate (flop accounting): out5 =
+ * {rejected at plane(T2) test, rejected at plane(T1) test, coplanar 2-D test,
+ *  rejected at the interval test, segment constructed}. */
+int sb_isect_path_counts(const sb_isect *isect, uint64_t *out5);
+/* FP64 issue-rate microbenchmark on the context's device, GFLOP/s: separate
+ * DMUL+DADD (what the predicate may use: no FMA contraction) and DFMA (counted as 2). */
+int sb_fp64_peak(sb_context *ctx, double *nofma_gflops, double *fma_gflops);
+
 /* Raw predicate on explicit triangles: 18 doubles per pair (p1 q1 r1 p2 q2 r2).
  * ret/coplanar as tri_tri_intersection_test_3d; seg = 6 doubles per pair, left
  * zero where the predicate does not write them. */
@@ -190,9 +198,10 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t a_begin, size_
 enum {
     SB_STAGE_BUILD = 0,    /* bounds, boxes, normals, Morton, sort, LBVH */
     SB_STAGE_BROAD = 1,    /* traversal + pair emission */
-    SB_STAGE_NARROW = 2,   /* predicate + hit compaction + sorts */
+    SB_STAGE_NARROW = 2,   /* hit / candidate sorts + gather */
     SB_STAGE_CLASSIFY = 3, /* ray classification */
-    SB_STAGE_COUNT = 4
+    SB_STAGE_PREDICATE = 4,/* the tri/tri predicate kernel alone (FP64 roofline) */
+    SB_STAGE_COUNT = 5
 };
 int sb_context_enable_timing(sb_context *ctx, int enable);
 int sb_context_reset_timing(sb_context *ctx);

@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsolidboolean_b200.so")
 
-STAGES = ("build", "broad", "narrow", "classify")
+STAGES = ("build", "broad", "narrow", "classify", "predicate")
 ISECT_NO_SORT = 1
 
 
@@ -72,6 +72,8 @@ ABI = {
     "sb_isect_face_flags": (C.c_int, [_vp, _vp, _vp]),
     "sb_isect_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint), C.POINTER(_vp),
                                        C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sb_isect_path_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "sb_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sb_tri_tri_batch": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "sb_classify": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "sb_classify_faces": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -153,6 +155,12 @@ class Context:
         n = C.c_uint64(0)
         _check(self.lib.sb_context_get_timing(self.h, ms, C.byref(n)))
         return {k: float(ms[i]) for i, k in enumerate(STAGES)}, int(n.value)
+
+    def fp64_peak(self):
+        """-> (GFLOP/s with separate DMUL+DADD, GFLOP/s with DFMA counted as 2)."""
+        a, b = C.c_double(0), C.c_double(0)
+        _check(self.lib.sb_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     def classify_stats(self):
         r, c = C.c_uint64(0), C.c_uint64(0)
@@ -344,6 +352,12 @@ class Isect:
         seg = np.zeros((self.num_hits, 6), np.float64)
         _check(self.lib.sb_isect_hits(self.h, _ptr(ab), _ptr(seg)))
         return ab, seg
+
+    def path_counts(self):
+        """Predicate exit histogram: plane2 reject, plane1 reject, coplanar, interval reject, segment."""
+        out = (C.c_uint64 * 5)()
+        _check(self.lib.sb_isect_path_counts(self.h, out))
+        return [int(v) for v in out]
 
     def face_flags(self):
         fa = np.zeros(self.a.num_triangles, np.uint8)

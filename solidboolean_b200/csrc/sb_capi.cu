@@ -43,14 +43,16 @@ unsigned bits_for(size_t n)
     return b;
 }
 
-struct DeviceScalars { // one 256-byte block of device counters per context
+struct DeviceScalars { // device counters of one lane (128-byte slots)
     unsigned long long pairCount;
     unsigned long long stats[2];
     unsigned int hitCount;
     unsigned int overflowCount;
     int err;
     int pad;
+    unsigned long long paths[5]; // predicate exit histogram (TriTriPath)
 };
+static_assert(sizeof(DeviceScalars) <= 128, "lane slot too small");
 
 } // namespace
 
@@ -126,6 +128,7 @@ struct sb_isect {
     uint32_t *hitAB = nullptr;
     double2 *hitSeg = nullptr;
     uint8_t *flagsA = nullptr, *flagsB = nullptr;
+    unsigned long long paths[5] = {0, 0, 0, 0, 0}; // predicate exit histogram
     std::vector<void *> owned; // stream-ordered allocations to release
     bool candSorted = false;   // candidates are ordered lazily, when somebody asks for them
     bool noSort = false;
@@ -376,12 +379,12 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->smCount = prop.multiProcessorCount;
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    SB_CUDA(cudaMalloc(&c->dScalars, 256));
-    SB_CUDA(cudaMallocHost(&c->hScalars, 256));
+    SB_CUDA(cudaMalloc(&c->dScalars, 512));
+    SB_CUDA(cudaMallocHost(&c->hScalars, 512));
     SB_CUDA(cudaMallocHost(&c->hPool, 256 * 32));
     for (int l = 0; l < 3; ++l) {
-        c->lanes[l].d = reinterpret_cast<DeviceScalars *>(reinterpret_cast<char *>(c->dScalars) + 64 * l);
-        c->lanes[l].h = reinterpret_cast<DeviceScalars *>(reinterpret_cast<char *>(c->hScalars) + 64 * l);
+        c->lanes[l].d = reinterpret_cast<DeviceScalars *>(reinterpret_cast<char *>(c->dScalars) + 128 * l);
+        c->lanes[l].h = reinterpret_cast<DeviceScalars *>(reinterpret_cast<char *>(c->hScalars) + 128 * l);
         if (l == 0)
             c->lanes[l].stream = c->stream;
         else
@@ -895,13 +898,15 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         SB_TRY(alloc_async(c, &hitSlot, nCand, &x->owned));
         SB_TRY(alloc_async(c, &hitSegRaw, 3 * nCand, &x->owned));
         {
-            StageTimer t(c, SB_STAGE_NARROW);
+            StageTimer t(c, SB_STAGE_PREDICATE);
             SB_CUDA_X(sbk_predicate(c->stream, A->d, B->d, keys, (uint32_t)nCand, x->bitsB, hitKeys, hitSlot, hitSegRaw,
-                &c->dScalars->hitCount, x->flagsA, x->flagsB, c->lc));
+                &c->dScalars->hitCount, x->flagsA, x->flagsB, c->dScalars->paths, c->lc));
         }
         SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA_X(cudaStreamSynchronize(c->stream));
         x->nHit = c->hScalars->hitCount;
+        for (int k = 0; k < 5; ++k)
+            x->paths[k] = c->hScalars->paths[k];
     }
     if (nCand) {
         StageTimer t(c, SB_STAGE_NARROW);
@@ -935,6 +940,52 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
 int sb_intersect(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out)
 {
     return sb_intersect_range(A, B, 0, A ? A->d.nT : 0, flags, out);
+}
+
+int sb_isect_path_counts(const sb_isect *x, uint64_t *out5)
+{
+    if (!x || !out5)
+        return fail(SB_ERR_INVALID, "null argument");
+    for (int k = 0; k < 5; ++k)
+        out5[k] = x->paths[k];
+    return SB_OK;
+}
+
+int sb_fp64_peak(sb_context *c, double *nofma_gflops, double *fma_gflops)
+{
+    if (!c)
+        return fail(SB_ERR_INVALID, "context is null");
+    DeviceGuard g(c->device);
+    double *scratch = nullptr;
+    SB_CUDA(cudaMalloc(&scratch, 64));
+    cudaEvent_t e0, e1;
+    SB_CUDA(cudaEventCreate(&e0));
+    SB_CUDA(cudaEventCreate(&e1));
+    double results[2] = {0, 0};
+    for (int fma = 0; fma < 2; ++fma) {
+        unsigned long long flops = 0;
+        sbk_fp64_peak(c->stream, c->smCount, scratch, 2000, fma != 0, &flops); // warm-up
+        double best = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0, c->stream);
+            sbk_fp64_peak(c->stream, c->smCount, scratch, 20000, fma != 0, &flops);
+            cudaEventRecord(e1, c->stream);
+            SB_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms > 0)
+                best = std::max(best, (double)flops / (ms * 1e-3) / 1e9);
+        }
+        results[fma] = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(scratch);
+    if (nofma_gflops)
+        *nofma_gflops = results[0];
+    if (fma_gflops)
+        *fma_gflops = results[1];
+    return SB_OK;
 }
 
 int sb_isect_counts(const sb_isect *x, size_t *nCand, size_t *nHit)

@@ -15,11 +15,13 @@ __global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__re
     const double4 *__restrict__ vtxA, const uint32_t *__restrict__ triA,
     const double4 *__restrict__ vtxB, const uint32_t *__restrict__ triB,
     unsigned long long *__restrict__ hitKeys, uint32_t *__restrict__ hitSlot, double2 *__restrict__ hitSeg,
-    unsigned int *__restrict__ hitCount, uint8_t *__restrict__ flagsA, uint8_t *__restrict__ flagsB)
+    unsigned int *__restrict__ hitCount, uint8_t *__restrict__ flagsA, uint8_t *__restrict__ flagsB,
+    unsigned long long *__restrict__ pathCounts)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool hit = false;
+    int path = -1;
     unsigned long long ab = 0;
     d3 src = {0, 0, 0}, tgt = {0, 0, 0};
     uint32_t a = 0, b = 0;
@@ -33,9 +35,17 @@ __global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__re
         d3 p1 = load_vertex(vtxA, a0), q1 = load_vertex(vtxA, a1), r1 = load_vertex(vtxA, a2);
         d3 p2 = load_vertex(vtxB, b0), q2 = load_vertex(vtxB, b1), r2 = load_vertex(vtxB, b2);
         int coplanar = 0;
-        int ret = tri_tri_intersection(p1, q1, r1, p2, q2, r2, coplanar, src, tgt);
+        int ret = tri_tri_intersection(p1, q1, r1, p2, q2, r2, coplanar, src, tgt, path);
         keys[i] = key | (unsigned long long)((ret ? 1 : 0) | (coplanar ? 2 : 0));
         hit = ret && !coplanar; // intersectTwoFaces, src/solidboolean.cpp:117-121
+    }
+    if (pathCounts) { // exit histogram (flop accounting): one atomic per warp and exit taken
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            uint32_t pm = __ballot_sync(SB_FULL, path == k);
+            if (pm && lane == 0)
+                atomicAdd(pathCounts + k, (unsigned long long)__popc(pm));
+        }
     }
     uint32_t m = __ballot_sync(SB_FULL, hit);
     if (m == 0)
@@ -110,12 +120,12 @@ __global__ void __launch_bounds__(128) tri_tri_batch_kernel(const double *__rest
 
 cudaError_t sbk_predicate(cudaStream_t s, const MeshDev &A, const MeshDev &B, unsigned long long *keys, uint32_t nPairs,
     unsigned bitsB, unsigned long long *hitKeys, uint32_t *hitSlot, double2 *hitSeg, unsigned int *hitCount,
-    uint8_t *flagsA, uint8_t *flagsB, LaunchCounter &lc)
+    uint8_t *flagsA, uint8_t *flagsB, unsigned long long *pathCounts, LaunchCounter &lc)
 {
     if (nPairs == 0)
         return cudaSuccess;
     predicate_kernel<<<(nPairs + 127) / 128, 128, 0, s>>>(keys, nPairs, bitsB, A.vtx, A.tri, B.vtx, B.tri, hitKeys, hitSlot,
-        hitSeg, hitCount, flagsA, flagsB);
+        hitSeg, hitCount, flagsA, flagsB, pathCounts);
     lc.kernels += 1;
     return cudaGetLastError();
 }
@@ -147,6 +157,40 @@ cudaError_t sbk_tri_tri_batch(cudaStream_t s, const double *tris18, uint32_t n, 
         return cudaSuccess;
     tri_tri_batch_kernel<<<(n + 127) / 128, 128, 0, s>>>(tris18, n, ret, coplanar, seg6);
     lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+// Issue-rate microbenchmark for the FP64 roofline of the predicate: the
+// predicate is built without FMA contraction, so its ceiling is the DADD/DMUL rate.
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        if (FMA) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        } else {
+            a0 = __dadd_rn(__dmul_rn(a0, m), c); a1 = __dadd_rn(__dmul_rn(a1, m), c);
+            a2 = __dadd_rn(__dmul_rn(a2, m), c); a3 = __dadd_rn(__dmul_rn(a3, m), c);
+            a4 = __dadd_rn(__dmul_rn(a4, m), c); a5 = __dadd_rn(__dmul_rn(a5, m), c);
+            a6 = __dadd_rn(__dmul_rn(a6, m), c); a7 = __dadd_rn(__dmul_rn(a7, m), c);
+        }
+    }
+    double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678)
+        out[0] = r; // never true: keeps the chains alive
+}
+
+cudaError_t sbk_fp64_peak(cudaStream_t s, int smCount, double *scratch, int iters, bool fma, unsigned long long *flops)
+{
+    const int blocks = smCount * 8;
+    if (fma)
+        fp64_peak_kernel<true><<<blocks, 256, 0, s>>>(scratch, iters, 0.5);
+    else
+        fp64_peak_kernel<false><<<blocks, 256, 0, s>>>(scratch, iters, 0.5);
+    *flops = (unsigned long long)blocks * 256ull * 8ull * 2ull * (unsigned long long)iters; // FMA counted as 2
     return cudaGetLastError();
 }
 

@@ -208,16 +208,26 @@ __device__ __forceinline__ int tt_construct(const d3 &p1, const d3 &q1, const d3
     return 1;
 }
 
+// Which exit a pair took (flop accounting of SURVEY 8d: 41 / 82 / 139 / 185 flops)
+enum TriTriPath {
+    TT_REJECT_PLANE2 = 0, // T1 entirely on one side of plane(T2)   (:421)
+    TT_REJECT_PLANE1 = 1, // T2 entirely on one side of plane(T1)   (:438)
+    TT_COPLANAR = 2,      // 2-D overlap test
+    TT_REJECT_INTERVAL = 3, // intervals on the common line do not overlap
+    TT_SEGMENT = 4        // intersection segment constructed
+};
+
 // tri_tri_intersection_test_3d, tri_tri_intersect.c:395-472.
 // coplanar is only ever set to 1; source/target only written with a segment.
 __device__ __forceinline__ int tri_tri_intersection(const d3 &p1, const d3 &q1, const d3 &r1,
-    const d3 &p2, const d3 &q2, const d3 &r2, int &coplanar, d3 &source, d3 &target)
+    const d3 &p2, const d3 &q2, const d3 &r2, int &coplanar, d3 &source, d3 &target, int &path)
 {
     // signs of T1's vertices against plane(T2)  (:407-421)
     d3 N2 = d3cross(d3sub(p2, r2), d3sub(q2, r2));
     double dp1 = d3dot(d3sub(p1, r2), N2);
     double dq1 = d3dot(d3sub(q1, r2), N2);
     double dr1 = d3dot(d3sub(r1, r2), N2);
+    path = TT_REJECT_PLANE2;
     if (xmul(dp1, dq1) > 0.0 && xmul(dp1, dr1) > 0.0)
         return 0;
     // signs of T2's vertices against plane(T1)  (:424-438)
@@ -225,8 +235,10 @@ __device__ __forceinline__ int tri_tri_intersection(const d3 &p1, const d3 &q1, 
     double dp2 = d3dot(d3sub(p2, r1), N1);
     double dq2 = d3dot(d3sub(q2, r1), N1);
     double dr2 = d3dot(d3sub(r2, r1), N1);
+    path = TT_REJECT_PLANE1;
     if (xmul(dp2, dq2) > 0.0 && xmul(dp2, dr2) > 0.0)
         return 0;
+    path = TT_COPLANAR;
 
     // canonical form of T1 (:443-471)
     SignCase c1 = sign_case(dp1, dq1, dr1);
@@ -253,5 +265,14 @@ __device__ __forceinline__ int tri_tri_intersection(const d3 &p1, const d3 &q1, 
     d3 cc2 = sel3(c2.rot, c2v, b2, p2);
     d3 bb1 = c2.swap ? c1v : b1;
     d3 cc1 = c2.swap ? b1 : c1v;
-    return tt_construct(a1, bb1, cc1, a2, bb2, cc2, N1, N2, source, target);
+    int r = tt_construct(a1, bb1, cc1, a2, bb2, cc2, N1, N2, source, target);
+    path = r ? TT_SEGMENT : TT_REJECT_INTERVAL;
+    return r;
+}
+
+__device__ __forceinline__ int tri_tri_intersection(const d3 &p1, const d3 &q1, const d3 &r1,
+    const d3 &p2, const d3 &q2, const d3 &r2, int &coplanar, d3 &source, d3 &target)
+{
+    int path = 0;
+    return tri_tri_intersection(p1, q1, r1, p2, q2, r2, coplanar, source, target, path);
 }

@@ -379,6 +379,21 @@ def test_front_end_overlapped_equals_separate_calls(ctx):
     x.close(); ref_x.close(); ma.close(); mb.close()
 
 
+def test_predicate_exit_histogram_and_fp64_probe(ctx, oracle):
+    a, b = meshgen.icosphere(4), meshgen.icosphere(4, center=(0.71, 0.13, 0.07))
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x = ma.intersect(mb)
+    paths = x.path_counts()
+    ab, code = x.candidates()
+    assert sum(paths) == x.num_candidates
+    assert paths[4] == int(((code & 1) == 1).sum() - ((code >> 1) & 1 & (code & 1)).sum())  # segments = ret && !coplanar
+    assert paths[2] == int(((code >> 1) & 1).sum())                                        # coplanar flag set
+    assert paths[0] + paths[1] + paths[3] == int((code == 0).sum())
+    nofma, fma = ctx.fp64_peak()
+    assert 1e3 < nofma < 1e5 and fma > 1.5 * nofma     # B200: tens of TFLOP/s, FMA = 2 flops per issue
+    x.close(); ma.close(); mb.close()
+
+
 def test_no_sort_flag_same_set(ctx):
     a, b = meshgen.icosphere(4), meshgen.icosphere(4, center=(0.71, 0.13, 0.07))
     ma, mb = ctx.mesh(*a), ctx.mesh(*b)
