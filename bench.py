@@ -268,32 +268,42 @@ def run_ours(args):
     b0, b1 = cutsB[rank], cutsB[rank + 1]
 
     dev = torch.device("cuda", local)
-    flagsA = torch.zeros(nA, dtype=torch.uint8, device=dev)
-    flagsB = torch.zeros(nB, dtype=torch.uint8, device=dev)
+    # one buffer for both flag arrays: a single NCCL collective exchanges them
+    flagsAB = torch.zeros(nA + nB, dtype=torch.uint8, device=dev)
+    flagsA, flagsB = flagsAB[:nA], flagsAB[nA:]
+    assert flagsB.data_ptr() == flagsAB.data_ptr() + nA
     l2_flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    counts_all = torch.zeros((world, 2), dtype=torch.int64, device=dev)
+
+    hit_cap = [4096]  # padded hit capacity per rank; grows to fit (a retry costs one extra gather)
 
     def gather_results(x):
-        """NCCL exchange of the shard results. Returns global (P, H)."""
-        mine = torch.tensor([[x.num_candidates, x.num_hits]], dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts_all, mine)
-        cnt = counts_all.cpu()
-        hmax = int(cnt[:, 1].max())
-        if hmax:
-            ptrs = x.device_ptrs()
-            pad_ab = torch.zeros((hmax, 2), dtype=torch.int32, device=dev)
-            pad_seg = torch.zeros((hmax, 6), dtype=torch.float64, device=dev)
-            if x.num_hits:
-                pad_ab[:x.num_hits] = _as_tensor(torch, ptrs["hit_ab"], (x.num_hits, 2), torch.int32, dev)
-                pad_seg[:x.num_hits] = _as_tensor(torch, ptrs["hit_seg"], (x.num_hits, 6), torch.float64, dev)
-            all_ab = torch.empty((world * hmax, 2), dtype=torch.int32, device=dev)
-            all_seg = torch.empty((world * hmax, 6), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(all_ab, pad_ab)
-            dist.all_gather_into_tensor(all_seg, pad_seg)
-        # every face is classified by exactly one rank: summing the byte masks is the gather
-        dist.all_reduce(flagsA)
-        dist.all_reduce(flagsB)
+        """NCCL exchange of the shard results: ONE all_gather of a packed
+        per-rank record {nCand, nHit, hit pairs, hit segments} straight from the library's
+        device buffers, and ONE all_reduce over both per-face flag arrays (every face is
+        classified by exactly one rank, so summing the byte masks is the gather).
+        Returns global (P, H)."""
+        while True:
+            cap = hit_cap[0]
+            rec = 16 + 8 * cap + 48 * cap                     # header + int32[cap,2] + float64[cap,6]
+            mine = torch.zeros(rec, dtype=torch.uint8, device=dev)
+            mine[:16].view(torch.int64).copy_(torch.tensor([x.num_candidates, x.num_hits], dtype=torch.int64))
+            n = min(x.num_hits, cap)
+            if n:
+                ptrs = x.device_ptrs()
+                mine[16:16 + 8 * n].view(torch.int32).copy_(_as_tensor(torch, ptrs["hit_ab"], (2 * n,), torch.int32, dev))
+                mine[16 + 8 * cap:16 + 8 * cap + 48 * n].view(torch.float64).copy_(
+                    _as_tensor(torch, ptrs["hit_seg"], (6 * n,), torch.float64, dev))
+            everyone = torch.empty(world * rec, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(everyone, mine)
+            cnt = everyone.view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2).cpu()
+            if int(cnt[:, 1].max()) <= cap:
+                break
+            hit_cap[0] = int(cnt[:, 1].max()) * 3 // 2 + 64   # some rank had more hits than the padding: once more
+        dist.all_reduce(flagsAB)
+        gathered["hits"] = everyone
         return int(cnt[:, 0].sum()), int(cnt[:, 1].sum())
+
+    gathered = {}
 
     # ---------------- resident loop: `value` ----------------
     ma = ctx.mesh(a[0], a[1], build=False)
@@ -307,7 +317,7 @@ def run_ours(args):
     def resident_step():
         with torch.cuda.stream(ext):
             if world > 1:
-                flagsA.zero_(); flagsB.zero_()
+                flagsAB.zero_()
             ma.build(); mb.build()          # concurrent: each mesh builds on its own stream
             # sb_front_end_range: intersection on the context stream, the two
             # classification directions overlapped on internal streams
@@ -384,7 +394,7 @@ def run_ours(args):
             xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=False, keep=pin)
             xa.build(); xb.build()
             if world > 1:
-                flagsA.zero_(); flagsB.zero_()
+                flagsAB.zero_()
             x = sb.Isect.front_end(xa, xb, flagsA.data_ptr(), flagsB.data_ptr(), a_range=(a0, a1), b_range=(b0, b1))
             if world > 1:
                 Pg, Hg = gather_results(x)
@@ -480,7 +490,8 @@ def run_ours(args):
     # release everything that was used on the library's stream while that stream is alive
     # (torch's pinned-memory allocator records an event on the stream a block was used on)
     torch.cuda.synchronize()
-    del out_in_a_t, out_in_b_t, flagsA, flagsB, l2_flush, pin
+    gathered.clear()
+    del out_in_a_t, out_in_b_t, flagsA, flagsB, flagsAB, l2_flush, pin
     ma.close(); mb.close()
     torch.cuda.synchronize()
     if world > 1:

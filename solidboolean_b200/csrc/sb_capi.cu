@@ -109,13 +109,16 @@ struct sb_mesh {
     // builds run on the mesh's own stream so that independent meshes overlap;
     // consumers on the context stream wait for `ready`
     cudaStream_t stream = nullptr;
-    cudaEvent_t ready = nullptr;
+    cudaEvent_t ready = nullptr;     // everything built (incl. the ray grids)
+    cudaEvent_t leafReady = nullptr; // sorted leaves / boxes / centroids (+ LBVH when wanted): all the
+                                     // intersection needs, recorded before the grids are built
     uint32_t *radixWs = nullptr;     // in the arena
     uint32_t *scanScratch = nullptr; // in the arena
     uint32_t *hCounts = nullptr;     // pinned: [0] total refs, [1..3] big-list lengths
     uint32_t *hErr = nullptr;        // pinned: index-validation flag read back with the counts
     bool gridSized = false;          // reference list already sized by an earlier build
     bool treeBuilt = false;          // LBVH topology built (lazily, on first use as a traversal target)
+    bool treeWanted = false;         // the mesh has been a traversal target: rebuilds include the LBVH
 };
 
 struct sb_isect {
@@ -246,6 +249,12 @@ inline void use_mesh(sb_context *c, const sb_mesh *m)
     if (m->ready)
         cudaStreamWaitEvent(c->stream, m->ready, 0);
 }
+// ... or only for the part of it the intersection reads (leaves, boxes, LBVH)
+inline void use_mesh_leaves(sb_context *c, const sb_mesh *m)
+{
+    if (m->leafReady)
+        cudaStreamWaitEvent(c->stream, m->leafReady, 0);
+}
 
 // make the mesh stream wait for everything enqueued so far on the context stream
 inline void order_after_context(sb_context *c, const sb_mesh *m)
@@ -335,8 +344,13 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.extentSum = (unsigned long long *)(d.gridBigCount + 8);
     m->radixWs = (uint32_t *)(b + oRadix);
     m->scanScratch = (uint32_t *)(b + oScan);
-    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming) != cudaSuccess) {
+    // builds are on the critical path of everything that follows: highest priority, so
+    // that work started early on the context / lane streams only fills their gaps
+    int prioLow = 0, prioHigh = 0;
+    cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
+    if (cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prioHigh) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->leafReady, cudaEventDisableTiming) != cudaSuccess) {
         cudaFreeAsync(m->arena, ctx->stream);
         delete m;
         return fail(SB_ERR_CUDA, "stream/event creation failed");
@@ -562,6 +576,8 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
         e = cudaMemcpyAsync(m->d.tri, tri, 12 * nT, cudaMemcpyHostToDevice, m->stream);
     if (e == cudaSuccess)
         e = cudaEventRecord(m->ready, m->stream);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(m->leafReady, m->stream);
     if (e != cudaSuccess) {
         sb_mesh_destroy(m);
         return fail(SB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
@@ -584,6 +600,13 @@ int sb_mesh_build(sb_mesh *m)
         StageTimer t(c, SB_STAGE_BUILD, st);
         SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, st));
         SB_CUDA(sbk_build_mesh(st, m->d, m->radixWs, 0, c->smCount, c->lc));
+        m->treeBuilt = false;
+        if (m->treeWanted) { // known traversal target: LBVH right away, before the grids
+            SB_CUDA(sbk_build_tree(st, m->d, c->lc));
+            m->treeBuilt = true;
+        }
+        // the intersection can start here, while the ray grids are still being built
+        SB_CUDA(cudaEventRecord(m->leafReady, st));
         SB_CUDA(sbk_grid_count(st, m->d, m->scanScratch, c->gridBeta, c->lc));
         if (m->d.nT && m->gridSized) {
             // Rebuild of the same (immutable) geometry: every step above is
@@ -619,7 +642,6 @@ int sb_mesh_build(sb_mesh *m)
     }
     SB_CUDA(cudaEventRecord(m->ready, st));
     m->built = true;
-    m->treeBuilt = false;
     return SB_OK;
 }
 
@@ -635,7 +657,9 @@ static int ensure_tree(const sb_mesh *mc)
         SB_CUDA(sbk_build_tree(m->stream, m->d, c->lc));
     }
     SB_CUDA(cudaEventRecord(m->ready, m->stream));
+    SB_CUDA(cudaEventRecord(m->leafReady, m->stream));
     m->treeBuilt = true;
+    m->treeWanted = true;
     return SB_OK;
 }
 
@@ -685,6 +709,8 @@ void sb_mesh_destroy(sb_mesh *m)
     }
     if (m->ready)
         cudaEventDestroy(m->ready);
+    if (m->leafReady)
+        cudaEventDestroy(m->leafReady);
     delete m;
 }
 
@@ -826,8 +852,8 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         if (rt)
             return rt;
     }
-    use_mesh(c, A);
-    use_mesh(c, B);
+    use_mesh_leaves(c, A); // the grids are not read here: the broad phase may overlap their build
+    use_mesh_leaves(c, B);
     sb_isect *x = new (std::nothrow) sb_isect;
     if (!x)
         return fail(SB_ERR_NOMEM, "out of host memory");
@@ -1384,8 +1410,9 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
     for (int l = 1; l <= 2 && !r; ++l) {
         sb_context::Lane &lane = c->lanes[l];
         cudaStreamWaitEvent(lane.stream, c->orderEvent, 0);
-        cudaStreamWaitEvent(lane.stream, A->ready, 0);
-        cudaStreamWaitEvent(lane.stream, B->ready, 0);
+        // queries need the other mesh's sorted centroids only; the target needs its grids
+        cudaStreamWaitEvent(lane.stream, l == 1 ? A->leafReady : A->ready, 0);
+        cudaStreamWaitEvent(lane.stream, l == 1 ? B->ready : B->leafReady, 0);
         const sb_mesh *target = l == 1 ? B : A;
         const ClassifyArgs &q = l == 1 ? qa : qb;
         if (q.end > q.begin && target->d.nT)

@@ -46,23 +46,31 @@ def _worker(rank, world, port, out):
     ib, _, _ = O.classify(a, O.centroids(*b)[mine_b])
     flags_a[torch.from_numpy(mine_a)] = torch.from_numpy(ia)
     flags_b[torch.from_numpy(mine_b)] = torch.from_numpy(ib)
-    # ---- the exchange step (same calls as bench.py::gather_results) ----
-    counts_all = torch.zeros((world, 2), dtype=torch.int64)
-    dist.all_gather_into_tensor(counts_all, torch.tensor([[len(pairs), len(hab)]], dtype=torch.int64))
-    hmax = int(counts_all[:, 1].max())
-    pad_ab = torch.zeros((hmax, 2), dtype=torch.int32)
-    pad_seg = torch.zeros((hmax, 6), dtype=torch.float64)
-    pad_ab[:len(hab)] = torch.from_numpy(hab)
-    pad_seg[:len(hab)] = torch.from_numpy(hseg)
-    all_ab = torch.empty((world * hmax, 2), dtype=torch.int32)
-    all_seg = torch.empty((world * hmax, 6), dtype=torch.float64)
-    dist.all_gather_into_tensor(all_ab, pad_ab)
-    dist.all_gather_into_tensor(all_seg, pad_seg)
-    dist.all_reduce(flags_a)
-    dist.all_reduce(flags_b)
-    # unpad + global sort by (a, b)
-    keep = torch.cat([torch.arange(hmax) < counts_all[r, 1] for r in range(world)])
-    gab, gseg = all_ab[keep].numpy(), all_seg[keep].numpy()
+    # ---- the exchange step (same protocol as bench.py::gather_results): one all_gather of
+    # a packed per-rank record {nCand, nHit, pairs, segments}, one all_reduce over both flag arrays ----
+    flags_ab = torch.cat([flags_a, flags_b])
+    cap = 8                                   # deliberately too small: exercises the regrow-and-repeat path
+    while True:
+        rec = 16 + 8 * cap + 48 * cap
+        mine = torch.zeros(rec, dtype=torch.uint8)
+        mine[:16].view(torch.int64).copy_(torch.tensor([len(pairs), len(hab)], dtype=torch.int64))
+        n = min(len(hab), cap)
+        if n:
+            mine[16:16 + 8 * n].view(torch.int32).copy_(torch.from_numpy(hab[:n].reshape(-1)))
+            mine[16 + 8 * cap:16 + 8 * cap + 48 * n].view(torch.float64).copy_(torch.from_numpy(hseg[:n].reshape(-1)))
+        everyone = torch.empty(world * rec, dtype=torch.uint8)
+        dist.all_gather_into_tensor(everyone, mine)
+        counts_all = everyone.view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2)
+        if int(counts_all[:, 1].max()) <= cap:
+            break
+        cap = int(counts_all[:, 1].max()) * 3 // 2 + 64
+    dist.all_reduce(flags_ab)
+    flags_a, flags_b = flags_ab[:nA], flags_ab[nA:]
+    ev = everyone.view(world, rec)
+    gab = np.concatenate([ev[r, 16:16 + 8 * int(counts_all[r, 1])].contiguous().view(torch.int32).view(-1, 2).numpy()
+                          for r in range(world)])
+    gseg = np.concatenate([ev[r, 16 + 8 * cap:16 + 8 * cap + 48 * int(counts_all[r, 1])].contiguous().view(torch.float64).view(-1, 6).numpy()
+                           for r in range(world)])
     o = np.lexsort((gab[:, 1], gab[:, 0]))
     gab, gseg = gab[o], gseg[o]
     # ---- every rank compares with the unsharded oracle ----
