@@ -91,19 +91,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        """Clocks / throttle reasons of the samples taken in [t0, t1] (monotonic seconds);
+        if the window is shorter than the sampling period, the samples nearest to it."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1]
+        note = "samples inside the timed region"
+        if not rows and self.rows:
+            mid = 0.5 * (t0 + t1)
+            rows = [r for (_, r) in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            note = "timed region shorter than the sampling period: nearest samples (GPU under the same load)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -113,7 +124,7 @@ class ClockSampler:
                 if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "note": note}
 
 
 # ----------------------------------------------------------------------------
@@ -254,6 +265,10 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    # clocks are sampled for the whole run (nvidia-smi needs a moment to start); the
+    # samples falling into each timed region are reported
+    sampler = ClockSampler(local)
+    sampler.start()
     a, b, desc = workload(args.config)
     nA, nB = len(a[1]), len(b[1])
     nVA, nVB = len(a[0]), len(b[0])
@@ -332,10 +347,6 @@ def run_ours(args):
         return P, H
 
     def timed_loop(step_fn, steps, warmup, device_timed):
-        # the sampler runs from the warm-up on (the GPU is under the same load there),
-        # so that even a ~50 ms timed region is covered by 100 ms nvidia-smi samples
-        sampler = ClockSampler(local)
-        sampler.start()
         for _ in range(warmup):
             res = step_fn()
         torch.cuda.synchronize()
@@ -344,6 +355,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         total_ms = 0.0
+        t_begin = time.monotonic()
         for _ in range(steps):
             with torch.cuda.stream(ext):
                 l2_flush.zero_()          # evict L2 between timed iterations (untimed)
@@ -360,7 +372,7 @@ def run_ours(args):
                 res = step_fn()
                 torch.cuda.synchronize()
                 total_ms += (time.perf_counter() - t0) * 1e3
-        clocks = sampler.stop()
+        clocks = sampler.summary(t_begin, time.monotonic())
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -410,6 +422,7 @@ def run_ours(args):
 
     ctx.enable_timing(False)
     e2e_ms, (P2, H2), _ = timed_loop(e2e_step, max(3, args.steps // 2), 2, False)
+    sampler.stop()
     h2d = 24 * (nVA + nVB) + 12 * (nA + nB)
     d2h = (nA + nB) + 56 * H + 64
 
