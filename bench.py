@@ -466,7 +466,7 @@ def run_ours(args):
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "stage_gbs_algorithmic": {"build": gbs(build_bytes, stage_ms["build"]), "broad": gbs(broad_bytes, stage_ms["broad"]),
                                       "narrow": gbs(narrow_bytes, stage_ms["narrow"]), "classify": gbs(cls_bytes, cls_ms)},
-            "roofline": {"bound": "hbm", "kernel": "classification: ray_scan + ray_hit + ray_finish kernels, both directions (6+ launches/step)", "achieved": round(achieved, 1),
+            "roofline": {"bound": "hbm", "kernel": "classification: classify_kernel, both directions (2 launches/step)", "achieved": round(achieved, 1),
                          "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": cls_bytes,
                          "kernel_ms_per_step": round(cls_ms, 4)},

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsolidboolean_b200.so")
+LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(HERE, "lib", "libsolidboolean_b200.so")  # override: dev builds
 
 STAGES = ("build", "broad", "narrow", "classify", "predicate")
 ISECT_NO_SORT = 1

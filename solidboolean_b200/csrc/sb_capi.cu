@@ -91,12 +91,13 @@ struct sb_context {
         cudaStream_t stream = nullptr;
         DeviceScalars *d = nullptr, *h = nullptr;
         cudaEvent_t done = nullptr;
-        double candPerRayHint = 3.0; // sizes the candidate list; adapts to the last call
+        unsigned long long bigHint = 0; // scratch entries the many-layer rays of the last call needed
     } lanes[3];
     uint32_t *scanScratch = nullptr; // grid-build scan status words
     size_t scanScratchWords = 0;
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
     int sortBeginBit = 0;            // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT)
+    uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
 };
 
 struct sb_mesh {
@@ -410,6 +411,8 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaEventRecord(c->t0, c->stream));
     if (const char *e = getenv("SB_SORT_BEGIN_BIT"))
         c->sortBeginBit = std::max(0, std::min(atoi(e), 24));
+    if (const char *e = getenv("SB_CLASSIFY_POOL_LIMIT"))
+        c->classifyPoolLimit = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("SB_GRID_BETA")) {
         float b = (float)atof(e);
         if (b > 0.01f && b < 100.0f)
@@ -629,7 +632,8 @@ int sb_mesh_build(sb_mesh *m)
         uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
         for (int k = 0; k < 3; ++k)
             m->d.gridBigN[k] = h[1 + k];
-        size_t bytes = 16 * (std::max<size_t>(nRefs, 1) + 3 * (size_t)std::max<uint32_t>(bigMax, 1));
+        size_t bytes = 16 * (std::max<size_t>(nRefs, 1) + 3 * (size_t)std::max<uint32_t>(bigMax, 1) + 8); // + 8: the classifier reads
+                                                                                    // whole groups of 8 references
         SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, st));
         m->gridArenaBytes = bytes;
         m->d.gridRefs = static_cast<uint4 *>(m->gridArena);
@@ -806,7 +810,7 @@ int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
         return r;
     for (int a = 0; a < 3; ++a) {
         out->nu[a] = g.nu[a];
-        out->nv[a] = 1u << (16 - g.shiftV[a]);
+        out->nv[a] = 1u << (15 - g.shiftV[a]);
         out->big[a] = cnt[a];
         unsigned long long sum = 0;
         for (int k = 0; k < 32; ++k)
@@ -1168,36 +1172,46 @@ int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret
 
 // ---- classification --------------------------------------------------------------
 
-// One classification on a lane: launch enqueues the kernels of a pass and the counter
-// read-back; finish waits for the lane, repeats the pass once with the exact size if
-// the ray/triangle list was too small, and runs the second pass of the lazy vote when
-// some points are still undecided.
+// One classification on a lane: launch enqueues the kernel and the counter read-back;
+// finish waits for the lane and repeats the call once, with the exact size, if the
+// scratch of the many-layer rays was too small.
 struct ClassifyJob {
     void *scratch = nullptr;
-    unsigned long long cap = 0, rays = 0;
+    unsigned long long cap = 0;
     uint32_t points = 0;
-    ClassifyPass pass;
+    int firstAxes = 2;
     bool launched = false;
 };
 
 static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a,
     ClassifyJob &job, unsigned long long forceCap = 0)
 {
-    if (!job.launched) { // first pass: all three axes when per-axis bits are wanted, else the lazy vote
-        job.pass = ClassifyPass();
-        job.pass.naxes = a.perAxis ? 3 : 2;
-        job.points = a.end - a.begin;
-    }
-    job.rays = (unsigned long long)job.pass.naxes * job.points;
-    job.cap = forceCap ? forceCap
-                       : std::max<unsigned long long>(4096, (unsigned long long)(lane.candPerRayHint * (double)job.rays) + 1024);
-    size_t bytes = sbk_classify_scratch_bytes(job.points, job.cap, job.pass.naxes);
-    SB_CUDA(cudaMallocAsync(&job.scratch, bytes, lane.stream));
+    job.points = a.end - a.begin;
+    job.firstAxes = a.perAxis ? 3 : 2; // without the per-axis bits the vote is lazy (third ray on demand)
+    job.cap = forceCap ? forceCap : std::max<unsigned long long>(1 << 16, lane.bigHint + lane.bigHint / 4);
+    SB_CUDA(cudaMallocAsync(&job.scratch, 24 * (size_t)job.cap, lane.stream));
     SB_CUDA(cudaMemsetAsync(lane.d, 0, sizeof(DeviceScalars), lane.stream));
+    unsigned long long *trace = nullptr;
+    const char *traceFile = getenv("SB_CLASSIFY_TRACE"); // dev: per-CTA timeline of every classification launch
+    const uint32_t traceBlocks = sbk_classify_blocks(job.points);
+    if (traceFile)
+        SB_CUDA(cudaMalloc(&trace, 32 * (size_t)traceBlocks));
     {
         StageTimer t(c, SB_STAGE_CLASSIFY, lane.stream);
-        SB_CUDA(sbk_classify(lane.stream, target->d, a, job.pass, job.scratch, job.cap, &lane.d->stats[1], &lane.d->stats[0],
-            &lane.d->overflowCount, c->lc));
+        SB_CUDA(sbk_classify(lane.stream, target->d, a, static_cast<long long *>(job.scratch), job.cap, &lane.d->stats[1],
+            &lane.d->stats[0], &lane.d->overflowCount, c->classifyPoolLimit, trace, c->lc));
+    }
+    if (trace) {
+        std::vector<unsigned long long> h(4 * (size_t)traceBlocks);
+        SB_CUDA(cudaStreamSynchronize(lane.stream));
+        SB_CUDA(cudaMemcpy(h.data(), trace, 32 * (size_t)traceBlocks, cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        if (FILE *f = fopen(traceFile, "ab")) {
+            unsigned long long hdr[4] = {0xffffffffffffffffull, traceBlocks, job.points, 0};
+            fwrite(hdr, 8, 4, f);
+            fwrite(h.data(), 8, h.size(), f);
+            fclose(f);
+        }
     }
     SB_CUDA(cudaMemcpyAsync(lane.h, lane.d, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, lane.stream));
     job.launched = true;
@@ -1209,50 +1223,26 @@ static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh 
 {
     if (!accumulateStats)
         c->lastRays = c->lastCands = 0;
-    void *firstScratch = nullptr; // keeps the undecided list alive during the second pass
-    int attempt = 0;
-    while (true) {
+    for (int attempt = 0;; ++attempt) {
         SB_CUDA(cudaStreamSynchronize(lane.stream));
-        const unsigned long long entries = lane.h->stats[1]; // list entries (quantised matches)
+        const unsigned long long needed = lane.h->stats[1]; // scratch entries the many-layer rays asked for
         const uint32_t undecided = lane.h->overflowCount;
-        if (job.rays && job.pass.naxes > 1)
-            lane.candPerRayHint = std::max(0.25, 1.25 * (double)entries / (double)job.rays);
+        lane.bigHint = needed;
         if (getenv("SB_DEBUG"))
-            fprintf(stderr, "[sb] classify pass(axis0=%d,n=%d): rays %llu list entries %llu exact %llu cap %llu undecided %u\n",
-                job.pass.axis0, job.pass.naxes, job.rays, entries, (unsigned long long)lane.h->stats[0], job.cap, undecided);
-        if (entries > job.cap) { // list too small: repeat this pass with the exact size
-            cudaFreeAsync(job.scratch, lane.stream);
-            job.scratch = nullptr;
-            if (++attempt > 1) {
-                if (firstScratch)
-                    cudaFreeAsync(firstScratch, lane.stream);
-                return fail(SB_ERR_CAPACITY, "ray/triangle list overflow after retry (%llu > %llu)", entries, job.cap);
-            }
-            int r = classify_launch(c, lane, target, a, job, entries);
-            if (r)
-                return r;
-            continue;
-        }
-        c->lastRays += job.rays;
-        c->lastCands += lane.h->stats[0]; // exact candidates
-        if (job.pass.naxes == 2 && undecided) {
-            // second pass of the lazy vote: the third axis, only where the first two disagree
-            firstScratch = job.scratch;
-            job.pass.list = sbk_classify_undecided_list(firstScratch, job.points, job.cap, 2);
-            job.pass.listCount = undecided;
-            job.pass.axis0 = 2;
-            job.pass.naxes = 1;
-            job.points = undecided;
-            attempt = 0;
-            int r = classify_launch(c, lane, target, a, job, std::max<unsigned long long>(4096, 8ull * undecided));
-            if (r)
-                return r;
-            continue;
-        }
+            fprintf(stderr, "[sb] classify: points %u axes %d undecided %u exact candidates %llu big-ray entries %llu (cap %llu)\n",
+                job.points, job.firstAxes, undecided, (unsigned long long)lane.h->stats[0], needed, job.cap);
         cudaFreeAsync(job.scratch, lane.stream);
         job.scratch = nullptr;
-        if (firstScratch)
-            cudaFreeAsync(firstScratch, lane.stream);
+        if (needed > job.cap) { // scratch too small: repeat with the exact size
+            if (attempt)
+                return fail(SB_ERR_CAPACITY, "many-layer ray scratch overflow after retry (%llu > %llu)", needed, job.cap);
+            int r = classify_launch(c, lane, target, a, job, needed);
+            if (r)
+                return r;
+            continue;
+        }
+        c->lastRays += (unsigned long long)job.firstAxes * job.points + (job.firstAxes == 2 ? undecided : 0);
+        c->lastCands += lane.h->stats[0]; // exact candidates
         return SB_OK;
     }
 }

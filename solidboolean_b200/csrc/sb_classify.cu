@@ -1,52 +1,98 @@
 // Stage 4: inside/outside classification.  Replaces SolidBoolean::isPointInMesh
 // (reference src/solidboolean.cpp:48-92) as driven by decideGroupSide (:482-510).
 //
-// Three kernels, so that the memory-latency-bound part runs at full occupancy
-// and the FP64 part runs on a dense list with every lane busy:
+// ONE kernel; a warp owns 32 neighbouring query points.  Round 1 traces the rays of
+// axes 0 and 1 of every point; round 2 traces axis 2 only where those two votes
+// disagree -- the third ray cannot change the majority otherwise -- or for every point
+// when the per-axis bits are wanted.  Within a round the warp alternates between
+// phases so that neither the latency-bound nor the FP64-bound part runs divergent:
 //
-//  A  ray_scan_kernel    one thread per RAY (point x axis; a CTA = 256
-//     neighbouring points of one axis, so its threads read neighbouring grid
-//     cells).  Ray box exactly as :53-58; the ray's cell list of the target's
-//     axis-projected grid (sb_grid.cu) is filtered with the quantised 16-byte
-//     references -- integer work only, which over-accepts slightly.  A warp scan
-//     reserves one contiguous range of the global list per warp (one atomic per
-//     warp) and every ray writes its (ray, triangle) entries ray-contiguously.
-//  B  ray_hit_kernel     one thread per list entry, dense: first the EXACT
-//     double box test that defines the reference's candidate set (ray box against
-//     triangle boxes, :55-63), then segment/plane hit and the two edge-normal sign
-//     tests (sb_raytri.cuh, bit-exact), PositionKey of the hit.
-//  C  ray_finish_kernel  one thread per point: per axis, count the DISTINCT hit
-//     keys (std::set<PositionKey>, :64/:85), odd = inside (:89); majority of the
-//     three axes ((float)insideCount / totalCount > 0.5, :508).
+//  count  one lane per POINT (its two rays one after the other, both cell ranges
+//         fetched up front).  Ray box exactly as :53-58; the ray's cell list of the
+//         target's axis-projected grid (sb_grid.cu) is filtered with the quantised
+//         16-byte references (sb_gridq.cuh: three subtractions and a mask per
+//         reference, integer only, slightly over-accepting).
+//  fill   a prefix sum over the warp's 64 rays lays their matches out ray by ray in a
+//         shared-memory pool (the first 8 matches of a ray were kept by the count
+//         pass; a ray with more walks its, now cached, list again).
+//  eval   one lane per staged (ray, triangle) ENTRY, dense, 32 at a time (chunks end
+//         on ray boundaries).  Exact double box test = the reference's candidate set
+//         (:55-63), then segment/plane hit + the two edge-normal sign tests
+//         (sb_raytri.cuh, bit-exact) and the PositionKey of the hit.  Hits whose key
+//         equals that of an earlier hit of the same ray are dropped
+//         (std::set<PositionKey>, :64/:85); one ballot then gives every ray the
+//         number of its distinct crossings; odd = inside (:89).
+//
+// A ray with more than 32 matches (stacked layers, silhouettes) gets the whole warp
+// for its entries, its distinct keys collected in a list (64 in shared memory, the
+// rest in a global scratch that the host sizes and, if ever too small, re-sizes
+// exactly).  A ray whose box straddles a cell border or that has more matches than
+// the pool holds is traced reference by reference by the warp (big_ray).
+// Majority: (float)insideCount / totalCount > 0.5 with totalCount == 3 (:508).
 #include "sb_internal.h"
+#include "sb_gridq.cuh"
 #include "sb_raytri.cuh"
 
 namespace {
 
-constexpr int SCAN_THREADS = 256;
-constexpr int KEEP = 4; // candidates a scan thread keeps in registers before re-scanning
+#ifndef SB_CLS_CT
+#define SB_CLS_CT 128
+#endif
+#ifndef SB_CLS_MINB
+#define SB_CLS_MINB 6
+#endif
+#ifndef SB_CLS_UNROLL
+#define SB_CLS_UNROLL 4 // references loaded per scan step (<= 8: allocation padding)
+#endif
+#ifndef SB_CLS_KEEP
+#define SB_CLS_KEEP 0   // the count pass keeps the first RCAP matches of a ray
+#endif
+#ifndef SB_CLS_NPREF
+#define SB_CLS_NPREF 0  // normals fetched before the exact box test
+#endif
+#ifndef SB_CLS_RBOX
+#define SB_CLS_RBOX 0   // ray box shortcut for finite points
+#endif
+constexpr int CT = SB_CLS_CT; // threads per CTA
+constexpr int CW = CT / 32;   // warps per CTA
+constexpr int POOL = 1024;    // staged (ray, triangle) entries per warp
+constexpr int RCAP = 8;       // matches per ray kept during the count pass (more: the list is walked again)
+constexpr int KSM = 64;       // distinct keys of a long ray held in shared memory
+constexpr int KS = 128;       // ... of a big_ray ray (in the then idle pool)
 
-__device__ __forceinline__ BoxD ray_box(const d3 &p, const d3 &e)
-{
-    // box.update(testPosition); box.update(testEnd)  (src/solidboolean.cpp:55-58)
-    BoxD b = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
-#define SB_UPD(v)                                 \
+struct __align__(16) WarpStage {
+    uint32_t tri[POOL];     // triangle ids, ray by ray
+#if SB_CLS_KEEP
+    uint32_t first[2][RCAP][32]; // [slot][k][lane]: the first matches of the lane's rays (conflict-free columns)
+#endif
+    long long key[32][3];   // PositionKeys of the current chunk's hits
+    long long list[KSM][3]; // distinct keys of the long ray being evaluated
+    uint8_t owner[POOL];    // entry -> slot * 32 + owner lane
+    uint8_t hit[32];
+};
+static_assert(KS * 24 <= POOL * 4, "big_ray keeps its keys in the pool");
+
+#define SB_BOX_UPD(b, v)                          \
     if (v.x > b.hix) b.hix = v.x;                 \
     if (v.x < b.lox) b.lox = v.x;                 \
     if (v.y > b.hiy) b.hiy = v.y;                 \
     if (v.y < b.loy) b.loy = v.y;                 \
     if (v.z > b.hiz) b.hiz = v.z;                 \
     if (v.z < b.loz) b.loz = v.z;
-    SB_UPD(p) SB_UPD(e)
-#undef SB_UPD
-    return b;
-}
 
-__device__ __forceinline__ uint32_t quant16(double x, double org, double scl)
+__device__ __forceinline__ BoxD ray_box(const d3 &p, const d3 &e)
 {
-    double t = floor((x - org) * scl);
-    t = fmin(fmax(t, 0.0), 65535.0); // NaN -> 0; identical to the grid build
-    return (uint32_t)t;
+    // box.update(testPosition); box.update(testEnd)  (src/solidboolean.cpp:55-58).
+    // For a point with |coordinates| < DBL_MAX the updates leave lo = p and hi = e: the
+    // first one stores p in both (-DBL_MAX < p < DBL_MAX), and e = p + (DBL_MAX or
+    // DBL_EPSILON) >= p (rounding is monotone; +inf compares greater) only ever raises hi.
+#if SB_CLS_RBOX
+    if (fabs(p.x) < DBL_MAX && fabs(p.y) < DBL_MAX && fabs(p.z) < DBL_MAX)
+        return {p.x, p.y, p.z, e.x, e.y, e.z};
+#endif
+    BoxD b = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
+    SB_BOX_UPD(b, p) SB_BOX_UPD(b, e)
+    return b;
 }
 
 __device__ __forceinline__ double comp(const BoxD &b, int d, bool hi)
@@ -61,305 +107,552 @@ struct Target {
     const uint4 *bigRefs;
     uint32_t bigCap;
     uint32_t bigN0, bigN1, bigN2;
-    const double2 *tbox;
     const double4 *vtx;
     const uint32_t *tri;
     const double *normal;
 };
 
 struct Query {
-    const double *pts;   // explicit points (AoS), or null
-    const double *scent; // faces mode: query mesh centroids in Morton order ...
-    const Rec32 *leaf;   // ... and its leaves (sorted position -> triangle id)
+    const double *pts;         // explicit points (AoS), or null
+    const double *scent;       // faces mode: query mesh centroids in Morton order ...
+    const uint32_t *sortedTri; // ... and sorted position -> triangle id
     uint32_t nT;
-    uint32_t begin;      // first point / sorted position
-    uint32_t count;      // points in this launch
-    // Lazy majority vote: the first pass traces axes 0 and 1 only (naxes = 2); the third
-    // ray can change the result only where those two disagree, and is traced in a second
-    // pass over just those points (list = their local indices, axis0 = 2, naxes = 1).
-    const uint32_t *list;
-    int axis0, naxes;
+    uint32_t begin;            // first point / sorted position
+    uint32_t count;            // points in this launch
 };
 
-__device__ __forceinline__ uint32_t local_point(const Query &q, uint32_t j)
-{
-    return q.list ? __ldg(q.list + j) : j;
-}
+struct Out {
+    uint8_t *inside;           // indexed by point index / original triangle id
+    uint8_t *perAxis;          // optional, 3 per point: all three rays are traced
+    long long *bigKeys;        // scratch of the many-layer rays, 3 x bigCap
+    unsigned long long bigCap;
+    unsigned long long *bigNeeded;  // entries the many-layer rays asked for (> bigCap: repeat)
+    unsigned long long *exactCount; // true candidates (exact box overlap), roofline accounting
+    unsigned int *undecidedCount;   // points whose first two votes disagreed
+    uint32_t poolLimit;        // rays with more matches go through big_ray (<= POOL; smaller only in tests)
+    unsigned long long *trace; // dev: per CTA {sm id, start ns, end ns, entries evaluated} (SB_CLASSIFY_TRACE), or null
+};
 
-// Walk the ray's cell list(s) in a fixed order; visit(triangle id) for each
-// triangle whose QUANTISED box overlaps the quantised ray box (a superset of the
-// reference's candidates; ray_hit_kernel applies the exact test).
-template <typename Visit>
-__device__ __forceinline__ void for_each_candidate(const GridParams &g, const Target &T, int axis, const BoxD &myD,
-    Visit &&visit)
+struct RaySetup {
+    RayQ rq;
+    uint32_t cu0, cu1, cv0, cv1;
+    bool any; // the ray box overlaps the mesh box
+};
+
+__device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, const d3 &p)
 {
+    RaySetup rs;
+    const d3 e = ray_end(p, axis);
+    const BoxD myD = ray_box(p, e);
     const BoxD meshBox = {g.lo[0], g.lo[1], g.lo[2], g.hi[0], g.hi[1], g.hi[2]};
-    if (!overlap_d(meshBox, myD)) // no triangle box can overlap the ray box
-        return;
+    rs.any = overlap_d(meshBox, myD); // otherwise no triangle box can overlap the ray box
     const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
-    const uint32_t aU = quant16(comp(myD, u, false), g.org[u], g.scl[u]);
-    const uint32_t bU = quant16(comp(myD, u, true), g.org[u], g.scl[u]);
-    const uint32_t aV = quant16(comp(myD, v, false), g.org[v], g.scl[v]);
-    const uint32_t bV = quant16(comp(myD, v, true), g.org[v], g.scl[v]);
-    const uint32_t aA = quant16(comp(myD, axis, false), g.org[axis], g.scl[axis]);
-    auto consider = [&](const uint4 &r) {
-        // quantised closed-interval test (over-accepts only)
-        if ((r.x & 0xffffu) > bU || (r.x >> 16) < aU || (r.y & 0xffffu) > bV || (r.y >> 16) < aV ||
-            (r.z & 0xffffu) < aA)
-            return;
-        visit(r.w);
-    };
+    const uint32_t aU = quant15(comp(myD, u, false), g.org[u], g.scl[u]);
+    const uint32_t bU = quant15(comp(myD, u, true), g.org[u], g.scl[u]);
+    const uint32_t aV = quant15(comp(myD, v, false), g.org[v], g.scl[v]);
+    const uint32_t bV = quant15(comp(myD, v, true), g.org[v], g.scl[v]);
+    const uint32_t aA = quant15(comp(myD, axis, false), g.org[axis], g.scl[axis]);
+    rs.rq = ray_pack(aU, bU, aV, bV, aA);
     const int su = g.shiftU[axis], sv = g.shiftV[axis];
-    const uint32_t cu0 = aU >> su, cu1 = bU >> su, cv0 = aV >> sv, cv1 = bV >> sv;
-    // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell
-    const bool multi = cu0 != cu1 || cv0 != cv1;
-    for (uint32_t cv = cv0; cv <= cv1; ++cv)
-        for (uint32_t cu = cu0; cu <= cu1; ++cu) {
-            const uint32_t cell = g.cellBase[axis] + cv * g.nu[axis] + cu;
-            const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2);
-            // four independent 16-byte loads in flight per thread
-            auto take = [&](const uint4 &r, uint32_t i) {
-                // a triangle spanning several of the ray's cells is taken in the first one only
-                if (i < i1 && (!multi || (max((r.x & 0xffffu) >> su, cu0) == cu && max((r.y & 0xffffu) >> sv, cv0) == cv)))
-                    consider(r);
-            };
-            for (uint32_t i = i0; i < i1; i += 4) {
-                const uint4 r0 = __ldg(T.refs + i);
-                const uint4 r1 = __ldg(T.refs + min(i + 1, i1 - 1));
-                const uint4 r2 = __ldg(T.refs + min(i + 2, i1 - 1));
-                const uint4 r3 = __ldg(T.refs + min(i + 3, i1 - 1));
-                take(r0, i);
-                take(r1, i + 1);
-                take(r2, i + 2);
-                take(r3, i + 3);
-            }
-        }
-    const uint32_t nBig = axis == 0 ? T.bigN0 : axis == 1 ? T.bigN1 : T.bigN2;
-    for (uint32_t i = 0; i < nBig; ++i)
-        consider(__ldg(T.bigRefs + (size_t)axis * T.bigCap + i));
+    rs.cu0 = aU >> su; rs.cu1 = bU >> su;
+    rs.cv0 = aV >> sv; rs.cv1 = bV >> sv;
+    return rs;
 }
 
-__device__ __forceinline__ bool query_point(const Query &q, uint32_t j, d3 &p, uint32_t &outIndex)
+// a triangle spanning several of the ray's cells is taken in the first of them only
+__device__ __forceinline__ bool first_cell(const GridParams &g, int axis, const RaySetup &rs, const uint4 &r, uint32_t cu,
+    uint32_t cv)
 {
-    if (j >= q.count)
+    return max(grid_ref_lo_u(r) >> g.shiftU[axis], rs.cu0) == cu && max(grid_ref_lo_v(r) >> g.shiftV[axis], rs.cv0) == cv;
+}
+
+__device__ __forceinline__ uint32_t big_list_length(const Target &T, int axis)
+{
+    return axis == 0 ? T.bigN0 : axis == 1 ? T.bigN1 : T.bigN2;
+}
+
+// triangle box .intersectWith(ray box) (axisalignedboundingbox.h:95-105) without forming
+// the triangle box: AxisAlignedBoudingBox::update (:31-41) leaves lo = min(DBL_MAX,
+// {c : c < DBL_MAX}) and hi = max(-DBL_MAX, {c : c > -DBL_MAX}) over the vertex
+// coordinates c (NaN never updates), so
+//     lo <= X  <=>  DBL_MAX <= X || c0 <= X || c1 <= X || c2 <= X
+//     hi >= Y  <=>  -DBL_MAX >= Y || c0 >= Y || c1 >= Y || c2 >= Y
+// (a c >= DBL_MAX that satisfies c <= X implies DBL_MAX <= X; mirrored for hi).
+// Bitwise operators: 24 predicate-setting compares, no branches.
+__device__ __forceinline__ bool tri_box_overlaps(const d3 &t0, const d3 &t1, const d3 &t2, const BoxD &rb)
+{
+    return ((DBL_MAX <= rb.hix) | (t0.x <= rb.hix) | (t1.x <= rb.hix) | (t2.x <= rb.hix)) &
+           ((-DBL_MAX >= rb.lox) | (t0.x >= rb.lox) | (t1.x >= rb.lox) | (t2.x >= rb.lox)) &
+           ((DBL_MAX <= rb.hiy) | (t0.y <= rb.hiy) | (t1.y <= rb.hiy) | (t2.y <= rb.hiy)) &
+           ((-DBL_MAX >= rb.loy) | (t0.y >= rb.loy) | (t1.y >= rb.loy) | (t2.y >= rb.loy)) &
+           ((DBL_MAX <= rb.hiz) | (t0.z <= rb.hiz) | (t1.z <= rb.hiz) | (t2.z <= rb.hiz)) &
+           ((-DBL_MAX >= rb.loz) | (t0.z >= rb.loz) | (t1.z >= rb.loz) | (t2.z >= rb.loz));
+}
+
+// One (ray, triangle) entry: is it a candidate of the reference (triangle box
+// .intersectWith(ray box), exact doubles, :55-63), and does the reference insert
+// PositionKey(hit) for it (:66-87)?
+__device__ __forceinline__ bool eval_entry(const Target &T, const d3 &p, int axis, uint32_t f, long long &k0, long long &k1,
+    long long &k2, bool &isCand)
+{
+    const d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
+    const d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
+    const d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
+#if SB_CLS_NPREF
+    // fetched before the box test decides (one round trip less; 98 % of the entries pass)
+    const d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
+#endif
+    const d3 e = ray_end(p, axis);
+    isCand = tri_box_overlaps(t0, t1, t2, ray_box(p, e));
+    if (!isCand)
         return false;
-    const uint32_t idx = q.begin + local_point(q, j);
-    if (q.pts) {
-        p = {q.pts[3 * (size_t)idx], q.pts[3 * (size_t)idx + 1], q.pts[3 * (size_t)idx + 2]};
-        outIndex = idx;
-        return true;
-    }
-    // faces mode: the centroids ((v0 + v1) + v2) / 3.0 (src/solidboolean.cpp:497-499) were
-    // formed at build time and stored in Morton order; positions >= nT are padding
-    if (idx >= q.nT)
+#if !SB_CLS_NPREF
+    const d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
+#endif
+    d3 hit = {0, 0, 0};
+    if (!ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit))
         return false;
-    outIndex = idx;
-    p = {__ldg(q.scent + 3 * (size_t)idx), __ldg(q.scent + 3 * (size_t)idx + 1), __ldg(q.scent + 3 * (size_t)idx + 2)};
+    k0 = position_key(hit.x);
+    k1 = position_key(hit.y);
+    k2 = position_key(hit.z);
     return true;
 }
 
-// ---- A ------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) ray_scan_kernel(Query q, Target T, uint32_t blocksPerAxis,
-    uint2 *__restrict__ cand, unsigned long long cap,
-    unsigned long long *__restrict__ candCount, uint2 *__restrict__ rayRange)
+// A ray with more than one cell or more matches than the pool takes, traced by the
+// whole warp: 32 references per step, hits de-duplicated against the ray's key list
+// (the first KS keys in the idle pool, the rest in the global scratch).  n = its
+// number of quantised matches, 0 if not known.  Returns {distinct hit keys, exact
+// candidates seen}.
+__device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, const Out &o, long long *skeys, int axis, double px,
+    double py, double pz, uint32_t n, int lane)
 {
-    __shared__ GridParams g;
-    if (threadIdx.x == 0)
-        g = *T.gp;
-    __syncthreads();
-    const int slot = blockIdx.x / blocksPerAxis;
-    const int axis = q.axis0 + slot;
-    const uint32_t j = (blockIdx.x % blocksPerAxis) * SCAN_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-
-    d3 p = {0, 0, 0};
-    uint32_t outIndex = 0;
-    const bool active = query_point(q, j, p, outIndex);
-    const d3 e = ray_end(p, axis);
-    const BoxD myD = ray_box(p, e);
-
-    uint32_t n = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    if (active)
-        for_each_candidate(g, T, axis, myD, [&](uint32_t f) {
-            if (n == 0) c0 = f;
-            else if (n == 1) c1 = f;
-            else if (n == 2) c2 = f;
-            else if (n == 3) c3 = f;
-            ++n;
-        });
-
-    // warp-wide exclusive scan of n; one atomic per warp reserves its output range
-    // (no block barrier: a warp whose rays hit long cell lists does not hold up the rest)
-    uint32_t incl = n;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
-        if (lane >= off)
-            incl += t;
-    }
-    const uint32_t total = __shfl_sync(SB_FULL, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 0 && total)
-        base = atomicAdd(candCount, (unsigned long long)total);
-    base = __shfl_sync(SB_FULL, base, 0);
-    if (!active)
-        return;
-    const unsigned long long first = base + incl - n;
-    const uint32_t ray = (uint32_t)slot * q.count + j;
-    rayRange[ray] = make_uint2((uint32_t)min(first, 0xffffffffull), n);
-    if (first + n > cap)
-        return; // list too small: the host sees candCount > cap and retries
-    if (n > 0) cand[first] = make_uint2(ray, c0);
-    if (n > 1) cand[first + 1] = make_uint2(ray, c1);
-    if (n > 2) cand[first + 2] = make_uint2(ray, c2);
-    if (n > 3) cand[first + 3] = make_uint2(ray, c3);
-    if (n > KEEP) {
-        uint32_t k = 0;
-        for_each_candidate(g, T, axis, myD, [&](uint32_t f) {
-            if (k >= KEEP)
-                cand[first + k] = make_uint2(ray, f);
-            ++k;
-        });
-    }
-}
-
-// ---- B ------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ray_hit_kernel(Query q, Target T,
-    const uint2 *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ candCount,
-    uint32_t nTargetTris, long long *__restrict__ keys /* 3 per entry */, uint8_t *__restrict__ hitFlag,
-    unsigned long long *__restrict__ exactCount)
-{
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long total = min(__ldg(candCount), cap);
-    bool isCand = false, h = false;
-    d3 hit = {0, 0, 0};
-    if (i < total) {
-        const uint2 c = __ldg(cand + i);
-        // when the list overflowed (the host will retry) some entries below cap were never written
-        if (c.x < (uint32_t)q.naxes * q.count && c.y < nTargetTris) {
-            const int axis = q.axis0 + (int)(c.x / q.count);
-            const uint32_t j = c.x % q.count;
-            const double *src = (q.pts ? q.pts : q.scent) + 3 * (size_t)(q.begin + local_point(q, j));
-            const d3 p = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
-            const d3 e = ray_end(p, axis);
-            const uint32_t f = c.y;
-            // the reference's candidate test: triangle box .intersectWith(ray box), exact doubles
-            isCand = overlap_d(load_boxd(T.tbox + 3 * (size_t)f), ray_box(p, e));
-            if (isCand) {
-                d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
-                d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
-                d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
-                d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1),
-                          __ldg(T.normal + 3 * (size_t)f + 2)};
-                h = ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit);
+    const d3 p = {px, py, pz};
+    const RaySetup rs = ray_setup(g, axis, p);
+    if (!rs.any)
+        return make_uint2(0, 0);
+    const uint32_t cbase = g.cellBase[axis], nu = g.nu[axis];
+    const bool multi = rs.cu0 != rs.cu1 || rs.cv0 != rs.cv1;
+    const uint4 *bigList = T.bigRefs + (size_t)axis * T.bigCap;
+    const uint32_t nBig = big_list_length(T, axis);
+    // visit(source, i0, i1, cellRule, cu, cv) for each reference range of the ray
+    auto ranges = [&](auto &&visit) {
+        for (uint32_t cv = rs.cv0; cv <= rs.cv1; ++cv)
+            for (uint32_t cu = rs.cu0; cu <= rs.cu1; ++cu) {
+                const uint32_t cell = cbase + cv * nu + cu;
+                visit(T.refs, __ldg(T.E + cell + 1), __ldg(T.E + cell + 2), multi, cu, cv);
             }
-        }
-        hitFlag[i] = h ? 1 : 0;
-        if (h) {
-            keys[3 * i] = position_key(hit.x);
-            keys[3 * i + 1] = position_key(hit.y);
-            keys[3 * i + 2] = position_key(hit.z);
-        }
+        visit(bigList, 0u, nBig, false, 0u, 0u);
+    };
+    if (n == 0) { // count the matches (bounds the number of distinct keys)
+        ranges([&](const uint4 *src, uint32_t i0, uint32_t i1, bool cellRule, uint32_t cu, uint32_t cv) {
+            for (uint32_t i = i0 + lane; i < i1; i += 32) {
+                const uint4 r = __ldg(src + i);
+                n += (ray_ref_match(rs.rq, r) && (!cellRule || first_cell(g, axis, rs, r, cu, cv))) ? 1u : 0u;
+            }
+        });
+        n = __reduce_add_sync(SB_FULL, n);
+        if (n == 0)
+            return make_uint2(0, 0);
     }
-    // exact candidate count (roofline accounting): one atomic per warp
-    const uint32_t m = __ballot_sync(SB_FULL, isCand);
-    if ((threadIdx.x & 31) == 0 && m)
-        atomicAdd(exactCount, (unsigned long long)__popc(m));
-}
-
-
-// ---- C ------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ray_finish_kernel(Query q, const uint2 *__restrict__ rayRange,
-    unsigned long long cap, const long long *__restrict__ keys, const uint8_t *__restrict__ hitFlag,
-    uint8_t *__restrict__ inside, uint8_t *__restrict__ perAxis, uint32_t *__restrict__ undecided,
-    unsigned int *__restrict__ undecidedCount)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= q.count)
-        return;
-    const uint32_t local = local_point(q, j);
-    uint32_t outIndex;
-    if (q.pts) {
-        outIndex = q.begin + local;
-    } else {
-        if (q.begin + local >= q.nT)
-            return;
-        outIndex = (uint32_t)load_rec(q.leaf + q.begin + local).ref;
+    long long *gkeys = nullptr;
+    if (n > KS) {
+        unsigned long long base = 0;
+        if (lane == 0)
+            base = atomicAdd(o.bigNeeded, (unsigned long long)(n - KS));
+        base = __shfl_sync(SB_FULL, base, 0);
+        if (base + (n - KS) > o.bigCap)
+            return make_uint2(0, 0); // scratch too small: the host sees bigNeeded > bigCap and repeats the call
+        gkeys = o.bigKeys + 3 * base;
     }
-    int insideCount = 0;
-    bool first = false;
-    for (int slot = 0; slot < q.naxes; ++slot) {
-        const uint2 r = __ldg(rayRange + (size_t)slot * q.count + j);
-        uint32_t distinct = 0;
-        if (r.y && (unsigned long long)r.x + r.y <= cap) {
-            uint32_t hits = 0;
-            for (uint32_t a = 0; a < r.y; ++a)
-                hits += hitFlag[(size_t)r.x + a];
-            distinct = hits;
-            if (hits > 1) { // std::set<PositionKey>: equal keys count once
-                distinct = 0;
-                for (uint32_t a = 0; a < r.y; ++a) {
-                    const size_t ia = (size_t)r.x + a;
-                    if (!hitFlag[ia])
-                        continue;
-                    const long long kx = keys[3 * ia], ky = keys[3 * ia + 1], kz = keys[3 * ia + 2];
-                    bool dup = false;
-                    for (uint32_t b = 0; b < a && !dup; ++b) {
-                        const size_t ib = (size_t)r.x + b;
-                        dup = hitFlag[ib] && keys[3 * ib] == kx && keys[3 * ib + 1] == ky && keys[3 * ib + 2] == kz;
+    uint32_t count = 0, exact = 0; // distinct hit keys so far (<= n)
+    ranges([&](const uint4 *src, uint32_t i0, uint32_t i1, bool cellRule, uint32_t cu, uint32_t cv) {
+        for (uint32_t i = i0; i < i1; i += 32) {
+            const uint32_t ii = i + lane;
+            bool h = false;
+            long long k0 = 0, k1 = 0, k2 = 0;
+            if (ii < i1) {
+                const uint4 r = __ldg(src + ii);
+                if (ray_ref_match(rs.rq, r) && (!cellRule || first_cell(g, axis, rs, r, cu, cv))) {
+                    bool isCand;
+                    h = eval_entry(T, p, axis, r.w, k0, k1, k2, isCand);
+                    exact += isCand ? 1u : 0u;
+                }
+            }
+            uint32_t hm = __ballot_sync(SB_FULL, h);
+            while (hm) {
+                const int s = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const long long x = __shfl_sync(SB_FULL, k0, s), y = __shfl_sync(SB_FULL, k1, s), z = __shfl_sync(SB_FULL, k2, s);
+                bool dup = false;
+                for (uint32_t t = lane; t < count; t += 32) {
+                    if (t < KS)
+                        dup |= skeys[3 * t] == x && skeys[3 * t + 1] == y && skeys[3 * t + 2] == z;
+                    else
+                        dup |= __ldcg(gkeys + 3 * (t - KS)) == x && __ldcg(gkeys + 3 * (t - KS) + 1) == y &&
+                               __ldcg(gkeys + 3 * (t - KS) + 2) == z;
+                }
+                if (!__any_sync(SB_FULL, dup)) {
+                    if (lane == 0) {
+                        long long *dst = count < KS ? skeys + 3 * count : gkeys + 3 * (count - KS);
+                        dst[0] = x;
+                        dst[1] = y;
+                        dst[2] = z;
                     }
-                    distinct += dup ? 0u : 1u;
+                    ++count;
+                    __syncwarp();
                 }
             }
         }
-        const bool in = (distinct & 1u) != 0; // odd number of distinct crossings (:89)
-        if (perAxis)
-            perAxis[3 * (size_t)outIndex + q.axis0 + slot] = in ? 1 : 0;
-        insideCount += in ? 1 : 0;
-        if (slot == 0)
-            first = in;
+    });
+    return make_uint2(count, __reduce_add_sync(SB_FULL, exact));
+}
+
+// the single cell list (+ the per-axis big list) of one ray, as seen by its lane
+struct RayScan {
+    RayQ rq;
+    uint32_t i0, i1; // cell list range in T.refs
+    uint32_t nBig;   // length of the axis's big list (0 when the ray cannot hit anything)
+    const uint4 *big;
+};
+
+// f(matched, triangle id) for every reference of the ray, in a fixed order
+template <typename F>
+__device__ __forceinline__ void for_refs(const Target &T, const RayScan &r, F &&f)
+{
+    // eight independent 16-byte loads in flight; a cell list is followed by at least
+    // seven more references (big lists + allocation padding), so i + 7 stays in bounds
+    for (uint32_t i = r.i0; i < r.i1; i += SB_CLS_UNROLL) {
+        uint4 q[SB_CLS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SB_CLS_UNROLL; ++k)
+            q[k] = __ldg(T.refs + i + k);
+#pragma unroll
+        for (int k = 0; k < SB_CLS_UNROLL; ++k)
+            f((i + k < r.i1) & ray_ref_match(r.rq, q[k]), q[k].w);
     }
-    if (q.naxes == 3) {
-        // (float)insideCount / totalCount > 0.5 with totalCount == 3 (:508)
-        inside[outIndex] = insideCount >= 2 ? 1 : 0;
-    } else if (q.naxes == 2) {
-        if (insideCount != 1) {
-            inside[outIndex] = first ? 1 : 0; // two equal votes already are the majority
-        } else {
-            const unsigned int slot = atomicAdd(undecidedCount, 1u);
-            undecided[slot] = local;         // the third ray decides
+    for (uint32_t i = 0; i < r.nBig; ++i) {
+        const uint4 q = __ldg(r.big + i);
+        f(ray_ref_match(r.rq, q), q.w);
+    }
+}
+
+__device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32 ? 0xffffffffu : (1u << n) - 1u; }
+
+// One round for the warp's points: rays along axis0 .. axis0 + nax - 1 (nax = 1 or 2)
+// of the lanes that `want` them.  Returns bit s set when the ray along axis0 + s
+// crosses an odd number of distinct surface points (:89).
+__device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Target &T, const Out &o, WarpStage &W, int axis0, int nax,
+    bool want, const d3 &p, int lane, uint32_t &exact)
+{
+    // ---- count ----
+    RayScan rs[2];
+    uint32_t n[2];
+    bool legacy[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        rs[s].i0 = rs[s].i1 = rs[s].nBig = 0;
+        rs[s].big = nullptr;
+        rs[s].rq.x = rs[s].rq.y = rs[s].rq.z = 0;
+        legacy[s] = false;
+        if (want && s < nax) {
+            const RaySetup r = ray_setup(g, axis0 + s, p);
+            rs[s].rq = r.rq;
+            // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell;
+            // the others go the general way (big_ray)
+            legacy[s] = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
+            if (r.any && !legacy[s]) {
+                const uint32_t cell = g.cellBase[axis0 + s] + r.cv0 * g.nu[axis0 + s] + r.cu0;
+                rs[s].i0 = __ldg(T.E + cell + 1);
+                rs[s].i1 = __ldg(T.E + cell + 2);
+                rs[s].nBig = big_list_length(T, axis0 + s);
+                rs[s].big = T.bigRefs + (size_t)(axis0 + s) * T.bigCap;
+            }
         }
-    } else {
-        inside[outIndex] = insideCount ? 1 : 0; // votes 0 and 1 disagreed: the majority is vote 2
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        uint32_t m = 0;
+        for_refs(T, rs[s], [&](bool hit, uint32_t f) {
+#if SB_CLS_KEEP
+            if (hit && m < RCAP)
+                W.first[s][m][lane] = f;
+#endif
+            m += hit ? 1u : 0u;
+        });
+        n[s] = m;
+        legacy[s] = legacy[s] || m > o.poolLimit;
+    }
+    const uint32_t ns0 = legacy[0] ? 0u : n[0], ns1 = legacy[1] ? 0u : n[1];
+    uint32_t incl0 = ns0, incl1 = ns1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t0 = __shfl_up_sync(SB_FULL, incl0, d), t1 = __shfl_up_sync(SB_FULL, incl1, d);
+        if (lane >= d) {
+            incl0 += t0;
+            incl1 += t1;
+        }
+    }
+    // dense order: the entries of the slot-0 rays (by lane), then those of the slot-1 rays
+    const uint32_t total0 = __shfl_sync(SB_FULL, incl0, 31);
+    const uint32_t total = total0 + __shfl_sync(SB_FULL, incl1, 31);
+    const uint32_t off0 = incl0 - ns0, off1 = total0 + incl1 - ns1;
+    const uint32_t lelane = lanemask_lt() | (1u << lane);
+    uint32_t parity = 0;
+    // windows of at most POOL entries (almost always one), ending on ray boundaries
+    for (uint32_t Wb = 0; Wb < total;) {
+        const uint32_t w0 = (ns0 && off0 >= Wb && off0 + ns0 > Wb + POOL) ? off0 : total;
+        const uint32_t w1 = (ns1 && off1 >= Wb && off1 + ns1 > Wb + POOL) ? off1 : total;
+        const uint32_t We = __reduce_min_sync(SB_FULL, min(w0, w1));
+        // ---- fill ----
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t nss = s ? ns1 : ns0, offs = s ? off1 : off0;
+            if (nss && offs >= Wb && offs < We) {
+                const uint32_t pos0 = offs - Wb;
+                const uint8_t rid = (uint8_t)(32 * s + lane);
+#if SB_CLS_KEEP
+                if (nss <= RCAP) {
+                    for (uint32_t k = 0; k < nss; ++k) {
+                        W.tri[pos0 + k] = W.first[s][k][lane];
+                        W.owner[pos0 + k] = rid;
+                    }
+                } else
+#endif
+                { // more matches than were kept: walk the (cached) list again
+                    uint32_t pos = pos0;
+                    for_refs(T, rs[s], [&](bool hit, uint32_t f) {
+                        if (hit) {
+                            W.tri[pos] = f;
+                            W.owner[pos] = rid;
+                        }
+                        pos += hit ? 1u : 0u;
+                    });
+                }
+            }
+        }
+        __syncwarp();
+        // ---- eval ----
+        for (uint32_t S = Wb; S < We;) {
+            // the chunk ends where the first ray that does not fit into 32 entries begins
+            const uint32_t c0 = (ns0 && off0 >= S && off0 + ns0 > S + 32) ? off0 : We;
+            const uint32_t c1 = (ns1 && off1 >= S && off1 + ns1 > S + 32) ? off1 : We;
+            const uint32_t Snext = min(__reduce_min_sync(SB_FULL, min(c0, c1)), We);
+            if (Snext == S) {
+                // a ray with more than 32 entries starts here: the whole warp takes it, 32
+                // entries per step, distinct keys collected in W.list / the global scratch
+                const uint32_t m0 = __ballot_sync(SB_FULL, ns0 > 32 && off0 == S);
+                const uint32_t m1 = __ballot_sync(SB_FULL, ns1 > 32 && off1 == S);
+                const int sl = m0 ? 0 : 1;
+                const int b = __ffs(m0 ? m0 : m1) - 1;
+                const uint32_t nl = __shfl_sync(SB_FULL, sl ? ns1 : ns0, b);
+                const d3 pb = {__shfl_sync(SB_FULL, p.x, b), __shfl_sync(SB_FULL, p.y, b), __shfl_sync(SB_FULL, p.z, b)};
+                long long *gl = nullptr;
+                bool ok = true;
+                if (nl > KSM) {
+                    unsigned long long base = 0;
+                    if (lane == 0)
+                        base = atomicAdd(o.bigNeeded, (unsigned long long)(nl - KSM));
+                    base = __shfl_sync(SB_FULL, base, 0);
+                    ok = base + (nl - KSM) <= o.bigCap; // else the host repeats the call with a larger scratch
+                    gl = o.bigKeys + 3 * base;
+                }
+                uint32_t count = 0;
+                for (uint32_t c = 0; c < nl && ok; c += 32) {
+                    bool h = false;
+                    long long k0 = 0, k1 = 0, k2 = 0;
+                    if (c + lane < nl) {
+                        bool isCand;
+                        h = eval_entry(T, pb, axis0 + sl, W.tri[S - Wb + c + lane], k0, k1, k2, isCand);
+                        exact += isCand ? 1u : 0u;
+                    }
+                    W.hit[lane] = h ? 1 : 0;
+                    if (h) {
+                        W.key[lane][0] = k0;
+                        W.key[lane][1] = k1;
+                        W.key[lane][2] = k2;
+                    }
+                    __syncwarp();
+                    if (h)
+                        for (int q = 0; q < lane; ++q)
+                            if (W.hit[q] && W.key[q][0] == k0 && W.key[q][1] == k1 && W.key[q][2] == k2) {
+                                h = false;
+                                break;
+                            }
+                    for (uint32_t t = 0; t < count; ++t) {
+                        long long x, y, z;
+                        if (t < KSM) {
+                            x = W.list[t][0]; y = W.list[t][1]; z = W.list[t][2];
+                        } else {
+                            x = __ldcg(gl + 3 * (t - KSM)); y = __ldcg(gl + 3 * (t - KSM) + 1); z = __ldcg(gl + 3 * (t - KSM) + 2);
+                        }
+                        h = h && !(x == k0 && y == k1 && z == k2);
+                    }
+                    const uint32_t sm = __ballot_sync(SB_FULL, h);
+                    if (h) {
+                        const uint32_t pos = count + __popc(sm & lanemask_lt());
+                        long long *dst = pos < KSM ? &W.list[pos][0] : gl + 3 * (pos - KSM);
+                        dst[0] = k0;
+                        dst[1] = k1;
+                        dst[2] = k2;
+                    }
+                    count += __popc(sm);
+                    __syncwarp();
+                }
+                if (lane == b)
+                    parity |= (count & 1u) << sl;
+                S += nl;
+                continue;
+            }
+            const bool have = (uint32_t)lane < Snext - S;
+            uint32_t rid = lane;
+            if (have)
+                rid = W.owner[S - Wb + lane];
+            const int ow = rid & 31, sl = rid >> 5;
+            // first lane of this entry's ray (chunks start on ray boundaries)
+            const uint32_t ridPrev = __shfl_up_sync(SB_FULL, rid, 1);
+            const uint32_t heads = __ballot_sync(SB_FULL, have && (lane == 0 || rid != ridPrev));
+            const int segStart = 31 - __clz(heads & lelane);
+            const d3 pp = {__shfl_sync(SB_FULL, p.x, ow), __shfl_sync(SB_FULL, p.y, ow), __shfl_sync(SB_FULL, p.z, ow)};
+            bool h = false;
+            long long k0 = 0, k1 = 0, k2 = 0;
+            if (have) {
+                bool isCand;
+                h = eval_entry(T, pp, axis0 + sl, W.tri[S - Wb + lane], k0, k1, k2, isCand);
+                exact += isCand ? 1u : 0u;
+                W.hit[lane] = h ? 1 : 0;
+                if (h) {
+                    W.key[lane][0] = k0;
+                    W.key[lane][1] = k1;
+                    W.key[lane][2] = k2;
+                }
+            }
+            __syncwarp();
+            // std::set<PositionKey>: a hit whose key equals that of an earlier hit of the ray does not count
+            if (h)
+                for (int q = segStart; q < lane; ++q)
+                    if (W.hit[q] && W.key[q][0] == k0 && W.key[q][1] == k1 && W.key[q][2] == k2) {
+                        h = false;
+                        break;
+                    }
+            const uint32_t dm = __ballot_sync(SB_FULL, h);
+            if (ns0 && off0 >= S && off0 + ns0 <= Snext)
+                parity |= __popc((dm >> (off0 - S)) & low_mask(ns0)) & 1u;
+            if (ns1 && off1 >= S && off1 + ns1 <= Snext)
+                parity |= (__popc((dm >> (off1 - S)) & low_mask(ns1)) & 1u) << 1;
+            __syncwarp();
+            S = Snext;
+        }
+        Wb = We;
+    }
+    // ---- rays that span several cells or overflow the pool ----
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        uint32_t bigMask = __ballot_sync(SB_FULL, legacy[s]);
+        while (bigMask) {
+            const int b = __ffs(bigMask) - 1;
+            bigMask &= bigMask - 1;
+            const uint32_t nb = __shfl_sync(SB_FULL, n[s], b); // 0 for a ray of several cells: not counted yet
+            const uint2 d = big_ray(g, T, o, reinterpret_cast<long long *>(W.tri), axis0 + s, __shfl_sync(SB_FULL, p.x, b),
+                __shfl_sync(SB_FULL, p.y, b), __shfl_sync(SB_FULL, p.z, b), nb, lane);
+            if (lane == b)
+                parity |= (d.x & 1u) << s;
+            if (lane == 0)
+                exact += d.y;
+            __syncwarp();
+        }
+    }
+    return parity;
+}
+
+__global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_constant__ Query q, const __grid_constant__ Target T,
+    const __grid_constant__ Out o)
+{
+    __shared__ GridParams g;
+    __shared__ WarpStage s_stage[CW];
+    unsigned long long traceStart = 0;
+    if (o.trace && threadIdx.x == 0)
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(traceStart));
+    if (threadIdx.x < sizeof(GridParams) / 4)
+        reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(T.gp)[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    WarpStage &W = s_stage[threadIdx.x >> 5];
+    const uint32_t j = blockIdx.x * CT + threadIdx.x;
+
+    d3 p = {0, 0, 0};
+    uint32_t outIndex = 0;
+    bool active = j < q.count;
+    if (active) {
+        const uint32_t idx = q.begin + j;
+        if (q.pts) {
+            p = {q.pts[3 * (size_t)idx], q.pts[3 * (size_t)idx + 1], q.pts[3 * (size_t)idx + 2]};
+            outIndex = idx;
+        } else if (idx < q.nT) {
+            // faces mode: the centroids ((v0 + v1) + v2) / 3.0 (src/solidboolean.cpp:497-499) were
+            // formed at build time and stored in Morton order
+            p = {__ldg(q.scent + 3 * (size_t)idx), __ldg(q.scent + 3 * (size_t)idx + 1), __ldg(q.scent + 3 * (size_t)idx + 2)};
+            outIndex = __ldg(q.sortedTri + idx);
+        } else {
+            active = false; // padding of the sorted order
+        }
+    }
+
+    uint32_t votes = 0, exact = 0;
+    bool undecided = false;
+    for (int round = 0; round < 2; ++round) {
+        bool want = active;
+        if (round == 1 && !o.perAxis) {
+            // lazy majority: the third ray only where the first two disagree
+            undecided = active && (((votes >> 1) ^ votes) & 1u);
+            want = undecided;
+        }
+        if (!__any_sync(SB_FULL, want))
+            continue;
+        votes |= trace_round(g, T, o, W, 2 * round, 2 - round, want, p, lane, exact) << (2 * round);
+    }
+    if (active) {
+        bool in;
+        if (o.perAxis) {
+            o.perAxis[3 * (size_t)outIndex] = votes & 1u;
+            o.perAxis[3 * (size_t)outIndex + 1] = (votes >> 1) & 1u;
+            o.perAxis[3 * (size_t)outIndex + 2] = (votes >> 2) & 1u;
+            in = __popc(votes) >= 2; // (float)insideCount / totalCount > 0.5 (:508)
+        } else {
+            in = undecided ? ((votes >> 2) & 1u) != 0 : (votes & 1u) != 0;
+        }
+        o.inside[outIndex] = in ? 1 : 0;
+    }
+    const uint32_t ex = __reduce_add_sync(SB_FULL, exact);
+    const uint32_t um = __ballot_sync(SB_FULL, undecided);
+    if (lane == 0) {
+        if (ex)
+            atomicAdd(o.exactCount, (unsigned long long)ex);
+        if (um)
+            atomicAdd(o.undecidedCount, (unsigned int)__popc(um));
+    }
+    if (o.trace) { // dev instrumentation
+        if (lane == 0 && ex)
+            atomicAdd(o.trace + 4 * (size_t)blockIdx.x + 3, (unsigned long long)ex);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t1;
+            uint32_t smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            o.trace[4 * (size_t)blockIdx.x] = smid;
+            o.trace[4 * (size_t)blockIdx.x + 1] = traceStart;
+            o.trace[4 * (size_t)blockIdx.x + 2] = t1;
+        }
     }
 }
 
 } // namespace
 
-size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, int naxes)
-{
-    size_t b = 0;
-    b += ((size_t)cap * 8 + 255) & ~(size_t)255;               // cand
-    b += ((size_t)cap * 24 + 255) & ~(size_t)255;              // keys
-    b += ((size_t)cap + 255) & ~(size_t)255;                   // hit flags
-    b += ((size_t)points * naxes * 8 + 255) & ~(size_t)255;    // rayRange
-    b += ((size_t)points * 4 + 255) & ~(size_t)255;            // undecided list
-    return b + 256;
-}
+uint32_t sbk_classify_blocks(uint32_t points) { return (points + CT - 1) / CT; }
 
-uint32_t *sbk_classify_undecided_list(void *scratch, uint32_t points, unsigned long long cap, int naxes)
-{
-    size_t b = 0;
-    b += ((size_t)cap * 8 + 255) & ~(size_t)255;
-    b += ((size_t)cap * 24 + 255) & ~(size_t)255;
-    b += ((size_t)cap + 255) & ~(size_t)255;
-    b += ((size_t)points * naxes * 8 + 255) & ~(size_t)255;
-    return reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) + b);
-}
-
-cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, const ClassifyPass &pass,
-    void *scratch, unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount,
-    unsigned int *undecidedCount, LaunchCounter &lc)
+cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, long long *bigKeys,
+    unsigned long long bigCap, unsigned long long *bigNeeded, unsigned long long *exactCount, unsigned int *undecidedCount,
+    uint32_t poolLimit, unsigned long long *trace, LaunchCounter &lc)
 {
     if (a.end <= a.begin)
         return cudaSuccess;
@@ -367,15 +660,10 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     Query q;
     q.pts = a.pts;
     q.scent = qm ? qm->scent : nullptr;
-    q.leaf = qm ? qm->leaf : nullptr;
+    q.sortedTri = qm ? qm->sortedTri : nullptr;
     q.nT = qm ? qm->nT : 0;
     q.begin = a.begin;
-    q.count = pass.list ? pass.listCount : a.end - a.begin;
-    q.list = pass.list;
-    q.axis0 = pass.axis0;
-    q.naxes = pass.naxes;
-    if (q.count == 0)
-        return cudaSuccess;
+    q.count = a.end - a.begin;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;
@@ -385,29 +673,22 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     T.bigN0 = target.gridBigN[0];
     T.bigN1 = target.gridBigN[1];
     T.bigN2 = target.gridBigN[2];
-    T.tbox = target.tbox;
     T.vtx = target.vtx;
     T.tri = target.tri;
     T.normal = target.normal;
-
-    char *b = static_cast<char *>(scratch);
-    auto take = [&](size_t bytes) {
-        char *p = b;
-        b += (bytes + 255) & ~(size_t)255;
-        return p;
-    };
-    uint2 *cand = reinterpret_cast<uint2 *>(take((size_t)cap * 8));
-    long long *keys = reinterpret_cast<long long *>(take((size_t)cap * 24));
-    uint8_t *hitFlag = reinterpret_cast<uint8_t *>(take((size_t)cap));
-    uint2 *rayRange = reinterpret_cast<uint2 *>(take((size_t)q.count * q.naxes * 8));
-    uint32_t *undecided = reinterpret_cast<uint32_t *>(take((size_t)q.count * 4));
-
-    const uint32_t bpa = (q.count + SCAN_THREADS - 1) / SCAN_THREADS;
-    ray_scan_kernel<<<q.naxes * bpa, SCAN_THREADS, 0, s>>>(q, T, bpa, cand, cap, candCount, rayRange);
-    const unsigned long long hitBlocks = (cap + 127) / 128;
-    ray_hit_kernel<<<(unsigned)hitBlocks, 128, 0, s>>>(q, T, cand, cap, candCount, target.nT, keys, hitFlag, exactCount);
-    ray_finish_kernel<<<(q.count + 255) / 256, 256, 0, s>>>(q, rayRange, cap, keys, hitFlag, a.inside, a.perAxis, undecided,
-        undecidedCount);
-    lc.kernels += 3;
+    Out o;
+    o.inside = a.inside;
+    o.perAxis = a.perAxis;
+    o.bigKeys = bigKeys;
+    o.bigCap = bigCap;
+    o.bigNeeded = bigNeeded;
+    o.exactCount = exactCount;
+    o.undecidedCount = undecidedCount;
+    o.trace = trace;
+    o.poolLimit = poolLimit ? (poolLimit < (uint32_t)POOL ? poolLimit : (uint32_t)POOL) : (uint32_t)POOL;
+    if (trace)
+        cudaMemsetAsync(trace, 0, 32 * (size_t)((q.count + CT - 1) / CT), s);
+    classify_kernel<<<(q.count + CT - 1) / CT, CT, 0, s>>>(q, T, o);
+    lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -8,32 +8,25 @@
 // perpendicular dimensions (CSR layout: per-cell ranges into one array of
 // 16-byte references).  A ray then reads ONE cell list instead of walking a tree.
 //
-// Exactness: cells and the 16-bit coordinates inside a reference are produced by
-// one monotone quantiser per world axis, q(x) = clamp(floor((x - org) * scl)),
-// applied to triangle bounds and to ray bounds alike.  Monotonicity means
-// lo <= x <= hi  =>  q(lo) <= q(x) <= q(hi), so the quantised test can only
-// over-accept; the exact double test of the reference follows in the classifier.
+// Exactness: cells and the 15-bit coordinates inside a reference are produced by
+// one monotone quantiser per world axis (sb_gridq.cuh), applied to triangle
+// bounds and to ray bounds alike, so the quantised test can only over-accept; the
+// exact double test of the reference follows in the classifier.
 //
 // Build = count (atomics) -> in-place chained scan -> fill (atomics), three axes
 // in one pass each, triangles visited in Morton order so neighbouring threads
 // hit neighbouring cells.
 #include "sb_internal.h"
+#include "sb_gridq.cuh"
 
 namespace {
 
 constexpr uint32_t MAX_CELLS_PER_TRI = 1024; // larger footprints go to the per-axis "big" list
 
-__device__ __forceinline__ uint32_t quant16(double x, double org, double scl)
-{
-    double t = floor((x - org) * scl);
-    t = fmin(fmax(t, 0.0), 65535.0); // NaN -> 0
-    return (uint32_t)t;
-}
-
 // Cell size = beta x mean triangle-box extent along each world axis, so a
 // triangle covers about (1 + 1/beta)^2 cells on every grid whatever the mesh's
 // aspect ratio or anisotropy; resolutions are powers of two so that a cell index
-// is a shift of the 16-bit coordinate.  maxBits bounds cells per axis (allocation).
+// is a shift of the 15-bit coordinate.  maxBits bounds cells per axis (allocation).
 __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds,
     const unsigned long long *__restrict__ extentSum,
     uint32_t nT, int maxBits, float beta, GridParams *out)
@@ -46,8 +39,8 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
         double lo = dkey_inv(bounds[d]), hi = dkey_inv(bounds[3 + d]);
         double ext = hi - lo;
         g.org[d] = lo;
-        // hi maps to 65535.99..; finite and > 0 extents only
-        g.scl[d] = (ext > 0.0 && ext < 1.0e300) ? 65535.999 / ext : 0.0;
+        // hi maps to 32767.99..; finite and > 0 extents only
+        g.scl[d] = (ext > 0.0 && ext < 1.0e300) ? 32767.999 / ext : 0.0;
         g.lo[d] = lo;
         g.hi[d] = hi;
         unsigned long long isum = 0; // fixed point: 2^-24 fractions of the mesh extent
@@ -56,7 +49,7 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
         double mean = nT ? (double)isum / 16777216.0 * ext / (double)nT : 0.0;
         double cells = (ext > 0.0 && mean > 0.0) ? ext / ((double)beta * mean) : 1.0;
         int b = (int)floor(log2(fmax(cells, 1.0)) + 0.5);
-        bitsWanted[d] = max(0, min(b, 16));
+        bitsWanted[d] = max(0, min(b, SB_Q_BITS));
     }
     uint32_t base = 0;
     for (int a = 0; a < 3; ++a) {
@@ -67,8 +60,8 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
             else if (kv > 0) --kv;
             else break;
         }
-        g.shiftU[a] = 16 - ku;
-        g.shiftV[a] = 16 - kv;
+        g.shiftU[a] = SB_Q_BITS - ku;
+        g.shiftV[a] = SB_Q_BITS - kv;
         g.nu[a] = 1u << ku;
         g.cellBase[a] = base;
         base += 1u << (ku + kv);
@@ -85,9 +78,9 @@ struct TriCells {
 __device__ __forceinline__ TriCells quantise_box(const BoxD &b, const GridParams &g)
 {
     TriCells t;
-    t.qlo[0] = quant16(b.lox, g.org[0], g.scl[0]); t.qhi[0] = quant16(b.hix, g.org[0], g.scl[0]);
-    t.qlo[1] = quant16(b.loy, g.org[1], g.scl[1]); t.qhi[1] = quant16(b.hiy, g.org[1], g.scl[1]);
-    t.qlo[2] = quant16(b.loz, g.org[2], g.scl[2]); t.qhi[2] = quant16(b.hiz, g.org[2], g.scl[2]);
+    t.qlo[0] = quant15(b.lox, g.org[0], g.scl[0]); t.qhi[0] = quant15(b.hix, g.org[0], g.scl[0]);
+    t.qlo[1] = quant15(b.loy, g.org[1], g.scl[1]); t.qhi[1] = quant15(b.hiy, g.org[1], g.scl[1]);
+    t.qlo[2] = quant15(b.loz, g.org[2], g.scl[2]); t.qhi[2] = quant15(b.hiz, g.org[2], g.scl[2]);
     return t;
 }
 
@@ -117,10 +110,7 @@ __global__ void __launch_bounds__(256) grid_bin_kernel(const double2 *__restrict
     const uint32_t ncell = (cu1 - cu0 + 1) * (cv1 - cv0 + 1);
     uint4 rec = make_uint4(0, 0, 0, 0);
     if (FILL) {
-        rec.x = qlu | (qhu << 16);
-        rec.y = qlv | (qhv << 16);
-        rec.z = t.qhi[a] | (t.qlo[a] << 16);
-        rec.w = (uint32_t)load_rec(leaf + j).ref;
+        rec = grid_ref_pack(qlu, qhu, qlv, qhv, t.qlo[a], t.qhi[a], (uint32_t)load_rec(leaf + j).ref);
     }
     if (ncell > MAX_CELLS_PER_TRI) {
         uint32_t slot = atomicAdd(&bigCount[FILL ? 3 + a : a], 1u);

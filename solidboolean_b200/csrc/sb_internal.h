@@ -11,10 +11,10 @@
 #define SB_CLUSTER 8
 #endif
 
-// Axis-projected grids (sb_grid.cu).  One 16-bit quantiser per world axis;
+// Axis-projected grids (sb_grid.cu).  One 15-bit quantiser per world axis (sb_gridq.cuh);
 // grid a (rays along axis a) bins the two perpendicular dimensions u, v.
 struct GridParams {
-    double org[3], scl[3]; // q(x) = clamp(floor((x - org) * scl), 0, 65535)
+    double org[3], scl[3]; // q(x) = clamp(floor((x - org) * scl), 0, 32767)
     double lo[3], hi[3];   // mesh bounds
     int shiftU[3], shiftV[3]; // cell = q >> shift
     uint32_t nu[3];        // cells along u
@@ -56,7 +56,7 @@ struct MeshDev {
     uint32_t gridCellBits = 0;          // at most 2^bits cells per axis (allocation bound)
     GridParams *gridParams = nullptr;
     uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
-    uint4 *gridRefs = nullptr;          // {qlo_u|qhi_u<<16, qlo_v|qhi_v<<16, qhi_a|qlo_a<<16, triangle id}
+    uint4 *gridRefs = nullptr;          // grid_ref_pack (sb_gridq.cuh): quantised box + triangle id
     uint32_t gridRefCap = 0;            // entries allocated behind gridRefs
     uint4 *gridBigRefs = nullptr;       // 3 * gridBigCap: triangles covering too many cells
     uint32_t *gridBigCount = nullptr;   // [0..2] counts (count pass), [3..5] fill cursors, [6] total refs
@@ -102,26 +102,18 @@ struct ClassifyArgs {
     uint8_t *inside = nullptr;   // indexed by point index / original triangle id
     uint8_t *perAxis = nullptr;  // optional, 3 per point
 };
-// One pass of the classifier.  Full vote: axis0 = 0, naxes = 3.  Lazy vote (only
-// `inside` wanted): pass 1 = axes 0,1 over all points (axis0 = 0, naxes = 2), which
-// appends the points whose two votes disagree to the scratch's undecided list; pass 2
-// = axis 2 over that list (axis0 = 2, naxes = 1, list/listCount set).
-struct ClassifyPass {
-    int axis0 = 0, naxes = 3;
-    const uint32_t *list = nullptr;
-    uint32_t listCount = 0;
-};
-// scratch: sbk_classify_scratch_bytes(points in this pass, cap, naxes) bytes; cap =
-// capacity of the ray/triangle list; *candCount (device, zeroed by the caller)
-// receives the number of list entries (quantised-box matches) -- if it exceeds cap
-// the results are invalid and the pass must be repeated with a larger cap;
-// *exactCount accumulates the true candidates (exact box overlap); *undecidedCount
-// the length of the undecided list (naxes == 2 only).
-size_t sbk_classify_scratch_bytes(uint32_t points, unsigned long long cap, int naxes);
-uint32_t *sbk_classify_undecided_list(void *scratch, uint32_t points, unsigned long long cap, int naxes);
-cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, const ClassifyPass &pass,
-    void *scratch, unsigned long long cap, unsigned long long *candCount, unsigned long long *exactCount,
-    unsigned int *undecidedCount, LaunchCounter &lc);
+// One launch classifies all points (sb_classify.cu).  Lazy vote when only `inside` is
+// wanted: axes 0 and 1 for every point, axis 2 where the two disagree
+// (*undecidedCount counts those points); all three axes when perAxis is set.
+// bigKeys / bigCap: scratch (3 x bigCap int64) for rays with many quantised matches;
+// *bigNeeded (device, zeroed by the caller) receives the entries they asked for -- if
+// it exceeds bigCap the results are invalid and the call must be repeated with a
+// scratch of that size.  *exactCount accumulates the true candidates (exact box overlap).
+cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, long long *bigKeys,
+    unsigned long long bigCap, unsigned long long *bigNeeded, unsigned long long *exactCount, unsigned int *undecidedCount,
+    uint32_t poolLimit /* 0 = default; tests lower it to reach the general path */,
+    unsigned long long *trace /* dev: 4 words per CTA, or null */, LaunchCounter &lc);
+uint32_t sbk_classify_blocks(uint32_t points);
 
 size_t sbk_radix_workspace_words(size_t n);
 

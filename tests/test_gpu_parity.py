@@ -256,24 +256,48 @@ def test_explicit_points_vs_oracle(ctx, oracle):
         m.close()
 
 
-def test_many_layers_hit_list_overflow_path(ctx, oracle):
-    """A ray crossing > 16 distinct surface points takes the exact slow path."""
+@pytest.mark.parametrize("layers,pitch", [(24, 0.05), (90, 0.02)])
+def test_many_layers_hit_list_overflow_path(ctx, oracle, layers, pitch):
+    """Rays with more matches than the per-ray staging area take the warp-cooperative
+    path: 24 thin slabs stacked along x = 48 crossings for +x rays (keys held in shared
+    memory); 90 slabs = 180 crossings (more than 128 distinct keys: global scratch,
+    including the host's exact-size retry)."""
     parts_v, parts_t = [], []
     off = 0
-    for i in range(24):  # 24 nested thin slabs stacked along x -> 48 crossings for +x rays
+    for i in range(layers):
         v, t = meshgen.slab(2, 1.0, 0.01, center=(0, 0, 0))
         rot = np.array([[0, 0, 1], [0, 1, 0], [-1, 0, 0]], np.float64)  # slab normal along x
-        v = v @ rot.T + np.array([0.05 * i, 0, 0])
+        v = v @ rot.T + np.array([pitch * i, 0, 0])
         parts_v.append(v); parts_t.append(t + off); off += len(v)
     mesh = (np.concatenate(parts_v), np.concatenate(parts_t).astype(np.uint32))
     rng = np.random.default_rng(9)
     pts = np.concatenate([rng.uniform(-0.4, 0.4, (500, 3)) * [0, 1, 1] + [-1.0, 0, 0],
-                          rng.uniform(-0.6, 1.5, (500, 3))])
+                          rng.uniform(-0.6, 1.5, (500, 3)), rng.uniform(-0.6, 1.5, (100000 if layers > 50 else 0, 3))])
     m = ctx.mesh(*mesh)
     ins, per = m.classify(pts)
     oi, op, _ = oracle.classify(mesh, pts)
     assert np.array_equal(per, op) and np.array_equal(ins, oi)
     m.close()
+
+
+def test_general_ray_path_forced(oracle, monkeypatch):
+    """SB_CLASSIFY_POOL_LIMIT=2 sends every ray with more than two quantised matches through
+    the reference-by-reference warp path (normally only rays spanning several cells or
+    overflowing the staging pool): same flags, per-axis bits and candidate counts."""
+    monkeypatch.setenv("SB_CLASSIFY_POOL_LIMIT", "2")
+    c2 = sb.Context(0)
+    rng = np.random.default_rng(31)
+    for mesh in (meshgen.torus(64, 32, center=(0.013, 0.007, 0.011)), meshgen.icosphere(4)):
+        pts = np.concatenate([rng.uniform(-1.5, 1.5, (20000, 3)), oracle.centroids(*mesh)[:3000]])
+        m = c2.mesh(*mesh)
+        ins, per = m.classify(pts)
+        oi, op, ncand = oracle.classify(mesh, pts)
+        assert np.array_equal(per, op) and np.array_equal(ins, oi)
+        assert c2.classify_stats()[1] == ncand
+        lazy, _ = m.classify(pts, per_axis=False)
+        assert np.array_equal(lazy, oi)
+        m.close()
+    c2.close()
 
 
 def test_mixed_scale_mesh_big_triangle_list(ctx, oracle):
