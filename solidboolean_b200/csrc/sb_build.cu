@@ -1,18 +1,21 @@
 // Stage 1: everything SolidMesh::prepare() computes (reference src/solidmesh.cpp:
 // 42-76), rebuilt for the device:
 //   K2  bounds_pad    whole-mesh box (:64-72) + 32-byte padded vertex copy
-//   K1  tri_prepare   unit normals (:47-55), exact per-triangle boxes (:57-62),
-//                     Morton key of the box centre
+//   K1  tri_prepare   unit normals (:47-55), Morton key of the centre of the exact
+//                     per-triangle box (:57-62)
 //   K3  onesweep radix sort of (Morton key, triangle id)
-//   K1b leaf_gather   sorted leaf records + warp-shuffle reduction of every K
+//   K1b leaf_gather   exact boxes (:57-62) and face centroids in Morton order, straight
+//                     from the vertices; sorted leaf records + warp-shuffle reduction of every K
 //                     consecutive leaves into a cluster box (the bottom log2 K
-//                     levels of the bottom-up refit, done in registers)
+//                     levels of the bottom-up refit, done in registers); also the
+//                     quantised boxes and per-cell counts of the ray grids (sb_grid.cu)
 //   K4  tree_build    agglomerative bottom-up LBVH over the clusters: topology
 //                     and boxes in ONE pass with an atomic rendezvous per node
 // The reference's top-down mean-split tree (axisalignedboundingboxtree.cpp:27-141)
 // is not reproduced: the candidate-pair set only depends on the leaf boxes.
 #include "sb_internal.h"
 #include "sb_radix.cuh"
+#include "sb_gridq.cuh"
 
 namespace {
 
@@ -61,6 +64,23 @@ __global__ void __launch_bounds__(256) bounds_pad_kernel(const double *__restric
 }
 
 // ---- K1 ---------------------------------------------------------------------
+// AxisAlignedBoudingBox::update x3 from the +-DBL_MAX seeds, strict compares
+// (src/axisalignedboundingbox.h:31-41)
+__device__ __forceinline__ BoxD tri_box(const d3 &a, const d3 &b, const d3 &c)
+{
+    BoxD bx = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
+#define SB_UPD(v)                                   \
+    if (v.x > bx.hix) bx.hix = v.x;                 \
+    if (v.x < bx.lox) bx.lox = v.x;                 \
+    if (v.y > bx.hiy) bx.hiy = v.y;                 \
+    if (v.y < bx.loy) bx.loy = v.y;                 \
+    if (v.z > bx.hiz) bx.hiz = v.z;                 \
+    if (v.z < bx.loz) bx.loz = v.z;
+    SB_UPD(a) SB_UPD(b) SB_UPD(c)
+#undef SB_UPD
+    return bx;
+}
+
 __device__ __forceinline__ uint32_t expand10(uint32_t v)
 {
     v = (v * 0x00010001u) & 0xFF0000FFu;
@@ -79,9 +99,9 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 }
 
 __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
-    uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double2 *__restrict__ tbox,
-    double *__restrict__ normal, double *__restrict__ cent, uint32_t *__restrict__ mkey, uint32_t *__restrict__ order,
-    int *__restrict__ err, unsigned long long *__restrict__ extentSum)
+    uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double *__restrict__ normal,
+    uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
+    unsigned long long *__restrict__ extentSum)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // this triangle's box extents as 2^-24 fractions of the mesh extent (integers:
@@ -95,19 +115,9 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     }
     d3 a = load_vertex(vtx, i0), b = load_vertex(vtx, i1), c = load_vertex(vtx, i2);
 
-    // AxisAlignedBoudingBox::update x3 from the +-DBL_MAX seeds, strict compares
-    // (src/axisalignedboundingbox.h:31-41)
-    BoxD bx = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
-#define SB_UPD(v)                                   \
-    if (v.x > bx.hix) bx.hix = v.x;                 \
-    if (v.x < bx.lox) bx.lox = v.x;                 \
-    if (v.y > bx.hiy) bx.hiy = v.y;                 \
-    if (v.y < bx.loy) bx.loy = v.y;                 \
-    if (v.z > bx.hiz) bx.hiz = v.z;                 \
-    if (v.z < bx.loz) bx.loz = v.z;
-    SB_UPD(a) SB_UPD(b) SB_UPD(c)
-#undef SB_UPD
-    store_boxd(tbox + 3 * (size_t)i, bx);
+    // the triangle's box, here only for the Morton key and the grid resolution (the
+    // sorted copy that the queries read is formed by leaf_gather_kernel)
+    const BoxD bx = tri_box(a, b, c);
 
     // Vector3::normal (src/vector3.h:155-176)
     d3 ba = d3sub(b, a), ca = d3sub(c, a);
@@ -120,12 +130,6 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     normal[3 * (size_t)i] = n.x;
     normal[3 * (size_t)i + 1] = n.y;
     normal[3 * (size_t)i + 2] = n.z;
-    // face centroid exactly as decideGroupSide forms its query point:
-    // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
-    cent[3 * (size_t)i] = xdiv(xadd(xadd(a.x, b.x), c.x), 3.0);
-    cent[3 * (size_t)i + 1] = xdiv(xadd(xadd(a.y, b.y), c.y), 3.0);
-    cent[3 * (size_t)i + 2] = xdiv(xadd(xadd(a.z, b.z), c.z), 3.0);
-
     // 30-bit Morton key of the box centre inside the mesh box (ordering only)
     double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
     double ex = dkey_inv(bounds[3]) - blx, ey = dkey_inv(bounds[4]) - bly, ez = dkey_inv(bounds[5]) - blz;
@@ -165,10 +169,15 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
 
 // ---- K1b --------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__restrict__ sortedTri,
-    const uint32_t *__restrict__ sortedKey, const double2 *__restrict__ tbox, const double *__restrict__ cent,
-    uint32_t nT, uint32_t nTpad, Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, double *__restrict__ scent,
-    Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey)
+    const uint32_t *__restrict__ sortedKey, const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
+    uint32_t nT, uint32_t nV, uint32_t nTpad, Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, double *__restrict__ scent,
+    Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey, const GridParams *__restrict__ gp, uint4 *__restrict__ qbox,
+    uint32_t *__restrict__ gridE, uint32_t *__restrict__ gridBigCount)
 {
+    __shared__ GridParams g;
+    if (threadIdx.x < sizeof(GridParams) / 4)
+        reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(gp)[threadIdx.x];
+    __syncthreads();
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nTpad) // nTpad is a multiple of 32: whole warps leave together
         return;
@@ -177,12 +186,22 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
     int ref = -1;
     if (j < nT) {
         uint32_t t = sortedTri[j];
-        bd = load_boxd(tbox + 3 * (size_t)t);
+        uint32_t i0 = __ldg(tri + 3 * (size_t)t), i1 = __ldg(tri + 3 * (size_t)t + 1), i2 = __ldg(tri + 3 * (size_t)t + 2);
+        if (i0 >= nV || i1 >= nV || i2 >= nV) // flagged by tri_prepare_kernel, reported by the host
+            i0 = i1 = i2 = 0;
+        const d3 a = load_vertex(vtx, i0), b = load_vertex(vtx, i1), c = load_vertex(vtx, i2);
+        bd = tri_box(a, b, c); // exact box (reference `update` semantics), Morton order
         bf = enclose(bd);
         ref = (int)t;
-        scent[3 * (size_t)j] = __ldg(cent + 3 * (size_t)t);
-        scent[3 * (size_t)j + 1] = __ldg(cent + 3 * (size_t)t + 1);
-        scent[3 * (size_t)j + 2] = __ldg(cent + 3 * (size_t)t + 2);
+        // face centroid exactly as decideGroupSide forms its query point:
+        // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
+        scent[3 * (size_t)j] = xdiv(xadd(xadd(a.x, b.x), c.x), 3.0);
+        scent[3 * (size_t)j + 1] = xdiv(xadd(xadd(a.y, b.y), c.y), 3.0);
+        scent[3 * (size_t)j + 2] = xdiv(xadd(xadd(a.z, b.z), c.z), 3.0);
+        // ray grids (sb_grid.cu): the quantised box, and the count pass while it is in registers
+        const uint4 q = quantise_box(bd, g, t);
+        qbox[j] = q;
+        grid_count_tri(q, g, gridE, gridBigCount);
     }
     store_boxd(sbox + 3 * (size_t)j, bd);
     store_rec(leaf + j, bf, ref, (int)j);
@@ -256,13 +275,35 @@ __global__ void __launch_bounds__(256) tree_build_kernel(const Rec32 *__restrict
     }
 }
 
+// exact triangle boxes in ORIGINAL order (sb_mesh_triangle_boxes; the front end itself
+// only reads the Morton-ordered copy)
+__global__ void __launch_bounds__(256) tri_boxes_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
+    uint32_t nT, uint32_t nV, double2 *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nT)
+        return;
+    uint32_t i0 = tri[3 * (size_t)i], i1 = tri[3 * (size_t)i + 1], i2 = tri[3 * (size_t)i + 2];
+    if (i0 >= nV || i1 >= nV || i2 >= nV)
+        i0 = i1 = i2 = 0;
+    store_boxd(out + 3 * (size_t)i, tri_box(load_vertex(vtx, i0), load_vertex(vtx, i1), load_vertex(vtx, i2)));
+}
+
 } // namespace
+
+cudaError_t sbk_triangle_boxes(cudaStream_t s, const MeshDev &m, double2 *out, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    tri_boxes_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, out);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
 
 size_t sbk_radix_workspace_words(size_t n) { return sbradix::Workspace::words(sbradix::tiles_for(n)); }
 
-cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t radixWsWords, int smCount, LaunchCounter &lc)
+cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc)
 {
-    (void)radixWsWords;
     if (m.nT == 0)
         return cudaSuccess;
     // bounds seeds: min slots all-ones, max slots zero (order-encoded doubles)
@@ -275,8 +316,8 @@ cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t
     if (vb < 1)
         vb = 1;
     bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds);
-    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.tbox, m.normal, m.cent, m.mkey, m.order,
-        m.err, m.extentSum);
+    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.normal, m.mkey, m.order, m.err,
+        m.extentSum);
     lc.kernels += 2;
     sbradix::Workspace ws;
     ws.mem = radixWs;
@@ -284,8 +325,15 @@ cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t
     lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, 30, ws, smCount, &sk, &sv);
     m.sortedKey = sk;
     m.sortedTri = sv;
-    leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.tbox, m.cent, m.nT, m.nTpad,
-        m.leaf, m.sbox, m.scent, m.cbox, m.ckey);
+    return cudaGetLastError();
+}
+
+cudaError_t sbk_build_leaves(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.vtx, m.tri, m.nT, m.nV, m.nTpad,
+        m.leaf, m.sbox, m.scent, m.cbox, m.ckey, m.gridParams, m.qbox, m.gridE, m.gridBigCount);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -296,9 +296,9 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
         return o;
     };
     size_t oXyz = take(24 * nV), oTri = take(12 * nT), oVtx = take(32 * nV), oBounds = take(48);
-    size_t oTbox = take(48 * nT), oNormal = take(24 * nT), oCent = take(24 * nT), oScent = take(24 * (size_t)((nT + 31) / 32 * 32));
+    size_t oNormal = take(24 * nT), oScent = take(24 * (size_t)((nT + 31) / 32 * 32));
     size_t oKey = take(4 * nT), oKeyT = take(4 * nT), oOrd = take(4 * nT), oOrdT = take(4 * nT);
-    size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad);
+    size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad), oQbox = take(16 * (size_t)d.nTpad);
     size_t oCbox = take(32 * (size_t)d.M), oCkey = take(4 * (size_t)d.M + 4);
     size_t oNodes = take(64 * nI), oSlot = take(4 * nI), oRoot = take(8);
     {
@@ -323,9 +323,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.tri = (uint32_t *)(b + oTri);
     d.vtx = (double4 *)(b + oVtx);
     d.bounds = (unsigned long long *)(b + oBounds);
-    d.tbox = (double2 *)(b + oTbox);
     d.normal = (double *)(b + oNormal);
-    d.cent = (double *)(b + oCent);
     d.scent = (double *)(b + oScent);
     d.mkey = (uint32_t *)(b + oKey);
     d.mkeyTmp = (uint32_t *)(b + oKeyT);
@@ -333,6 +331,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.orderTmp = (uint32_t *)(b + oOrdT);
     d.leaf = (Rec32 *)(b + oLeaf);
     d.sbox = (double2 *)(b + oSbox);
+    d.qbox = (uint4 *)(b + oQbox);
     d.cbox = (Rec32 *)(b + oCbox);
     d.ckey = (uint32_t *)(b + oCkey);
     d.nodes = (Rec32 *)(b + oNodes);
@@ -602,7 +601,9 @@ int sb_mesh_build(sb_mesh *m)
     {
         StageTimer t(c, SB_STAGE_BUILD, st);
         SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, st));
-        SB_CUDA(sbk_build_mesh(st, m->d, m->radixWs, 0, c->smCount, c->lc));
+        SB_CUDA(sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc));
+        SB_CUDA(sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc));
+        SB_CUDA(sbk_build_leaves(st, m->d, c->lc)); // also counts the grid cells
         m->treeBuilt = false;
         if (m->treeWanted) { // known traversal target: LBVH right away, before the grids
             SB_CUDA(sbk_build_tree(st, m->d, c->lc));
@@ -610,7 +611,7 @@ int sb_mesh_build(sb_mesh *m)
         }
         // the intersection can start here, while the ray grids are still being built
         SB_CUDA(cudaEventRecord(m->leafReady, st));
-        SB_CUDA(sbk_grid_count(st, m->d, m->scanScratch, c->gridBeta, c->lc));
+        SB_CUDA(sbk_grid_scan(st, m->d, m->scanScratch, c->lc));
         if (m->d.nT && m->gridSized) {
             // Rebuild of the same (immutable) geometry: every step above is
             // deterministic, so the reference count equals the one the list was
@@ -736,7 +737,28 @@ static int mesh_download(const sb_mesh *m, void *dst, const void *src, size_t by
 }
 
 int sb_mesh_normals(const sb_mesh *m, double *out) { return mesh_download(m, out, m ? m->d.normal : nullptr, m ? 24 * (size_t)m->d.nT : 0); }
-int sb_mesh_triangle_boxes(const sb_mesh *m, double *out) { return mesh_download(m, out, m ? m->d.tbox : nullptr, m ? 48 * (size_t)m->d.nT : 0); }
+// The front end only keeps the Morton-ordered boxes; the original-order copy is formed on request.
+int sb_mesh_triangle_boxes(const sb_mesh *m, double *out)
+{
+    if (!m || !out)
+        return fail(SB_ERR_INVALID, "null mesh or output");
+    if (!m->built)
+        return fail(SB_ERR_INVALID, "mesh not built");
+    if (!m->d.nT)
+        return SB_OK;
+    sb_context *c = m->ctx;
+    DeviceGuard g(c->device);
+    use_mesh(c, m);
+    double2 *tmp = nullptr;
+    int r = alloc_async(c, &tmp, 3 * (size_t)m->d.nT, nullptr);
+    if (r)
+        return r;
+    SB_CUDA(sbk_triangle_boxes(c->stream, m->d, tmp, c->lc));
+    SB_CUDA(cudaMemcpyAsync(out, tmp, 48 * (size_t)m->d.nT, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(tmp, c->stream);
+    return SB_OK;
+}
 int sb_mesh_order(const sb_mesh *m, uint32_t *out) { return mesh_download(m, out, m ? m->d.sortedTri : nullptr, m ? 4 * (size_t)m->d.nT : 0); }
 
 int sb_mesh_bounds(const sb_mesh *m, double *out6)

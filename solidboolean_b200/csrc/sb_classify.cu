@@ -13,8 +13,8 @@
 //         16-byte references (sb_gridq.cuh: three subtractions and a mask per
 //         reference, integer only, slightly over-accepting).
 //  fill   a prefix sum over the warp's 64 rays lays their matches out ray by ray in a
-//         shared-memory pool (the first 8 matches of a ray were kept by the count
-//         pass; a ray with more walks its, now cached, list again).
+//         shared-memory pool; the rays with matches walk their (now cached) lists
+//         again and store the triangle ids.
 //  eval   one lane per staged (ray, triangle) ENTRY, dense, 32 at a time (chunks end
 //         on ray boundaries).  Exact double box test = the reference's candidate set
 //         (:55-63), then segment/plane hit + the two edge-normal sign tests
@@ -44,9 +44,6 @@ namespace {
 #ifndef SB_CLS_UNROLL
 #define SB_CLS_UNROLL 4 // references loaded per scan step (<= 8: allocation padding)
 #endif
-#ifndef SB_CLS_KEEP
-#define SB_CLS_KEEP 0   // the count pass keeps the first RCAP matches of a ray
-#endif
 #ifndef SB_CLS_NPREF
 #define SB_CLS_NPREF 0  // normals fetched before the exact box test
 #endif
@@ -55,16 +52,18 @@ namespace {
 #endif
 constexpr int CT = SB_CLS_CT; // threads per CTA
 constexpr int CW = CT / 32;   // warps per CTA
-constexpr int POOL = 1024;    // staged (ray, triangle) entries per warp
-constexpr int RCAP = 8;       // matches per ray kept during the count pass (more: the list is walked again)
-constexpr int KSM = 64;       // distinct keys of a long ray held in shared memory
-constexpr int KS = 128;       // ... of a big_ray ray (in the then idle pool)
+#ifndef SB_CLS_POOL
+#define SB_CLS_POOL 512
+#endif
+#ifndef SB_CLS_KSM
+#define SB_CLS_KSM 32
+#endif
+constexpr int POOL = SB_CLS_POOL; // staged (ray, triangle) entries per warp
+constexpr int KSM = SB_CLS_KSM; // distinct keys of a long ray held in shared memory
+constexpr int KS = POOL * 4 / 24; // ... of a big_ray ray (in the then idle pool)
 
 struct __align__(16) WarpStage {
     uint32_t tri[POOL];     // triangle ids, ray by ray
-#if SB_CLS_KEEP
-    uint32_t first[2][RCAP][32]; // [slot][k][lane]: the first matches of the lane's rays (conflict-free columns)
-#endif
     long long key[32][3];   // PositionKeys of the current chunk's hits
     long long list[KSM][3]; // distinct keys of the long ray being evaluated
     uint8_t owner[POOL];    // entry -> slot * 32 + owner lane
@@ -218,6 +217,30 @@ __device__ __forceinline__ bool eval_entry(const Target &T, const d3 &p, int axi
     return true;
 }
 
+// The same as a separately compiled function (its FP64 register pressure stays out of
+// the scan loops): bit 0 = hit, bit 1 = candidate; the keys of a hit go to key3[0..2].
+#ifndef SB_CLS_EVAL_CALL
+#define SB_CLS_EVAL_CALL 0
+#endif
+#if SB_CLS_EVAL_CALL
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+uint32_t eval_call(const Target &T, double px, double py, double pz, int axis, uint32_t f, long long *key3)
+{
+    long long k0 = 0, k1 = 0, k2 = 0;
+    bool isCand;
+    const d3 p = {px, py, pz};
+    const bool h = eval_entry(T, p, axis, f, k0, k1, k2, isCand);
+    if (h) {
+        key3[0] = k0;
+        key3[1] = k1;
+        key3[2] = k2;
+    }
+    return (h ? 1u : 0u) | (isCand ? 2u : 0u);
+}
+
 // A ray with more than one cell or more matches than the pool takes, traced by the
 // whole warp: 32 references per step, hits de-duplicated against the ray's key list
 // (the first KS keys in the idle pool, the rest in the global scratch).  n = its
@@ -273,9 +296,11 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
             if (ii < i1) {
                 const uint4 r = __ldg(src + ii);
                 if (ray_ref_match(rs.rq, r) && (!cellRule || first_cell(g, axis, rs, r, cu, cv))) {
-                    bool isCand;
-                    h = eval_entry(T, p, axis, r.w, k0, k1, k2, isCand);
-                    exact += isCand ? 1u : 0u;
+                    long long k[3] = {0, 0, 0};
+                    const uint32_t fl = eval_call(T, px, py, pz, axis, r.w, k);
+                    h = fl & 1u;
+                    exact += fl >> 1;
+                    k0 = k[0]; k1 = k[1]; k2 = k[2];
                 }
             }
             uint32_t hm = __ballot_sync(SB_FULL, h);
@@ -307,32 +332,54 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
     return make_uint2(count, __reduce_add_sync(SB_FULL, exact));
 }
 
-// the single cell list (+ the per-axis big list) of one ray, as seen by its lane
-struct RayScan {
-    RayQ rq;
-    uint32_t i0, i1; // cell list range in T.refs
-    uint32_t nBig;   // length of the axis's big list (0 when the ray cannot hit anything)
-    const uint4 *big;
-};
-
-// f(matched, triangle id) for every reference of the ray, in a fixed order
-template <typename F>
-__device__ __forceinline__ void for_refs(const Target &T, const RayScan &r, F &&f)
+// One ray's cell list (len references from src) + the per-axis big list, walked by its
+// lane: number of references whose quantised box the ray matches.
+__device__ __forceinline__ uint32_t scan_count(const uint4 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t qz, uint32_t len,
+    const uint4 *__restrict__ big, uint32_t nBig)
 {
-    // eight independent 16-byte loads in flight; a cell list is followed by at least
-    // seven more references (big lists + allocation padding), so i + 7 stays in bounds
-    for (uint32_t i = r.i0; i < r.i1; i += SB_CLS_UNROLL) {
+    const RayQ rq = {qx, qy, qz};
+    uint32_t m = 0;
+    // independent 16-byte loads in flight; a list is followed by at least seven more
+    // readable references (padding), so the last group stays in bounds
+    for (uint32_t i = 0; i < len; i += SB_CLS_UNROLL) {
         uint4 q[SB_CLS_UNROLL];
 #pragma unroll
         for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            q[k] = __ldg(T.refs + i + k);
+            q[k] = __ldg(src + i + k);
 #pragma unroll
         for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            f((i + k < r.i1) & ray_ref_match(r.rq, q[k]), q[k].w);
+            m += ((i + k < len) & ray_ref_match(rq, q[k])) ? 1u : 0u;
     }
-    for (uint32_t i = 0; i < r.nBig; ++i) {
-        const uint4 q = __ldg(r.big + i);
-        f(ray_ref_match(r.rq, q), q.w);
+    for (uint32_t i = 0; i < nBig; ++i)
+        m += ray_ref_match(rq, __ldg(big + i)) ? 1u : 0u;
+    return m;
+}
+
+// the same walk, storing the matching triangle ids (and their owner) from `pos` on
+__device__ __forceinline__ void scan_fill(const uint4 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t qz, uint32_t len,
+    const uint4 *__restrict__ big, uint32_t nBig, uint32_t *tri, uint8_t *owner, uint32_t pos, uint8_t rid)
+{
+    const RayQ rq = {qx, qy, qz};
+    for (uint32_t i = 0; i < len; i += SB_CLS_UNROLL) {
+        uint4 q[SB_CLS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SB_CLS_UNROLL; ++k)
+            q[k] = __ldg(src + i + k);
+#pragma unroll
+        for (int k = 0; k < SB_CLS_UNROLL; ++k)
+            if ((i + k < len) & ray_ref_match(rq, q[k])) {
+                tri[pos] = q[k].w;
+                owner[pos] = rid;
+                ++pos;
+            }
+    }
+    for (uint32_t i = 0; i < nBig; ++i) {
+        const uint4 q = __ldg(big + i);
+        if (ray_ref_match(rq, q)) {
+            tri[pos] = q.w;
+            owner[pos] = rid;
+            ++pos;
+        }
     }
 }
 
@@ -345,44 +392,40 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
     bool want, const d3 &p, int lane, uint32_t &exact)
 {
     // ---- count ----
-    RayScan rs[2];
-    uint32_t n[2];
-    bool legacy[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        rs[s].i0 = rs[s].i1 = rs[s].nBig = 0;
-        rs[s].big = nullptr;
-        rs[s].rq.x = rs[s].rq.y = rs[s].rq.z = 0;
-        legacy[s] = false;
-        if (want && s < nax) {
-            const RaySetup r = ray_setup(g, axis0 + s, p);
-            rs[s].rq = r.rq;
-            // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell;
-            // the others go the general way (big_ray)
-            legacy[s] = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
-            if (r.any && !legacy[s]) {
-                const uint32_t cell = g.cellBase[axis0 + s] + r.cv0 * g.nu[axis0 + s] + r.cu0;
-                rs[s].i0 = __ldg(T.E + cell + 1);
-                rs[s].i1 = __ldg(T.E + cell + 2);
-                rs[s].nBig = big_list_length(T, axis0 + s);
-                rs[s].big = T.bigRefs + (size_t)(axis0 + s) * T.bigCap;
-            }
+    // per slot s (ray along axis0 + s): packed ray, cell list range, big list
+    uint32_t qx0 = 0, qy0 = 0, qz0 = 0, a0 = 0, b0 = 0, nBig0 = 0;
+    uint32_t qx1 = 0, qy1 = 0, qz1 = 0, a1 = 0, b1 = 0, nBig1 = 0;
+    bool legacy0 = false, legacy1 = false;
+    if (want) {
+        const RaySetup r = ray_setup(g, axis0, p);
+        qx0 = r.rq.x; qy0 = r.rq.y; qz0 = r.rq.z;
+        // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell;
+        // the others go the general way (big_ray)
+        legacy0 = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
+        if (r.any && !legacy0) {
+            const uint32_t cell = g.cellBase[axis0] + r.cv0 * g.nu[axis0] + r.cu0;
+            a0 = __ldg(T.E + cell + 1);
+            b0 = __ldg(T.E + cell + 2);
+            nBig0 = big_list_length(T, axis0);
         }
     }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        uint32_t m = 0;
-        for_refs(T, rs[s], [&](bool hit, uint32_t f) {
-#if SB_CLS_KEEP
-            if (hit && m < RCAP)
-                W.first[s][m][lane] = f;
-#endif
-            m += hit ? 1u : 0u;
-        });
-        n[s] = m;
-        legacy[s] = legacy[s] || m > o.poolLimit;
+    if (want && nax > 1) {
+        const RaySetup r = ray_setup(g, axis0 + 1, p);
+        qx1 = r.rq.x; qy1 = r.rq.y; qz1 = r.rq.z;
+        legacy1 = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
+        if (r.any && !legacy1) {
+            const uint32_t cell = g.cellBase[axis0 + 1] + r.cv0 * g.nu[axis0 + 1] + r.cu0;
+            a1 = __ldg(T.E + cell + 1);
+            b1 = __ldg(T.E + cell + 2);
+            nBig1 = big_list_length(T, axis0 + 1);
+        }
     }
-    const uint32_t ns0 = legacy[0] ? 0u : n[0], ns1 = legacy[1] ? 0u : n[1];
+    const uint4 *big0 = T.bigRefs + (size_t)axis0 * T.bigCap, *big1 = T.bigRefs + (size_t)(axis0 + 1) * T.bigCap;
+    const uint32_t n0 = scan_count(T.refs + a0, qx0, qy0, qz0, b0 - a0, big0, nBig0);
+    const uint32_t n1 = scan_count(T.refs + a1, qx1, qy1, qz1, b1 - a1, big1, nBig1);
+    legacy0 = legacy0 || n0 > o.poolLimit;
+    legacy1 = legacy1 || n1 > o.poolLimit;
+    const uint32_t ns0 = legacy0 ? 0u : n0, ns1 = legacy1 ? 0u : n1;
     uint32_t incl0 = ns0, incl1 = ns1;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -403,33 +446,11 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
         const uint32_t w0 = (ns0 && off0 >= Wb && off0 + ns0 > Wb + POOL) ? off0 : total;
         const uint32_t w1 = (ns1 && off1 >= Wb && off1 + ns1 > Wb + POOL) ? off1 : total;
         const uint32_t We = __reduce_min_sync(SB_FULL, min(w0, w1));
-        // ---- fill ----
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const uint32_t nss = s ? ns1 : ns0, offs = s ? off1 : off0;
-            if (nss && offs >= Wb && offs < We) {
-                const uint32_t pos0 = offs - Wb;
-                const uint8_t rid = (uint8_t)(32 * s + lane);
-#if SB_CLS_KEEP
-                if (nss <= RCAP) {
-                    for (uint32_t k = 0; k < nss; ++k) {
-                        W.tri[pos0 + k] = W.first[s][k][lane];
-                        W.owner[pos0 + k] = rid;
-                    }
-                } else
-#endif
-                { // more matches than were kept: walk the (cached) list again
-                    uint32_t pos = pos0;
-                    for_refs(T, rs[s], [&](bool hit, uint32_t f) {
-                        if (hit) {
-                            W.tri[pos] = f;
-                            W.owner[pos] = rid;
-                        }
-                        pos += hit ? 1u : 0u;
-                    });
-                }
-            }
-        }
+        // ---- fill ---- (the rays with matches walk their, now cached, lists again)
+        if (ns0 && off0 >= Wb && off0 < We)
+            scan_fill(T.refs + a0, qx0, qy0, qz0, b0 - a0, big0, nBig0, W.tri, W.owner, off0 - Wb, (uint8_t)lane);
+        if (ns1 && off1 >= Wb && off1 < We)
+            scan_fill(T.refs + a1, qx1, qy1, qz1, b1 - a1, big1, nBig1, W.tri, W.owner, off1 - Wb, (uint8_t)(32 + lane));
         __syncwarp();
         // ---- eval ----
         for (uint32_t S = Wb; S < We;) {
@@ -461,15 +482,15 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
                     bool h = false;
                     long long k0 = 0, k1 = 0, k2 = 0;
                     if (c + lane < nl) {
-                        bool isCand;
-                        h = eval_entry(T, pb, axis0 + sl, W.tri[S - Wb + c + lane], k0, k1, k2, isCand);
-                        exact += isCand ? 1u : 0u;
+                        const uint32_t fl = eval_call(T, pb.x, pb.y, pb.z, axis0 + sl, W.tri[S - Wb + c + lane], &W.key[lane][0]);
+                        h = fl & 1u;
+                        exact += fl >> 1;
                     }
                     W.hit[lane] = h ? 1 : 0;
                     if (h) {
-                        W.key[lane][0] = k0;
-                        W.key[lane][1] = k1;
-                        W.key[lane][2] = k2;
+                        k0 = W.key[lane][0];
+                        k1 = W.key[lane][1];
+                        k2 = W.key[lane][2];
                     }
                     __syncwarp();
                     if (h)
@@ -516,14 +537,14 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
             bool h = false;
             long long k0 = 0, k1 = 0, k2 = 0;
             if (have) {
-                bool isCand;
-                h = eval_entry(T, pp, axis0 + sl, W.tri[S - Wb + lane], k0, k1, k2, isCand);
-                exact += isCand ? 1u : 0u;
+                const uint32_t fl = eval_call(T, pp.x, pp.y, pp.z, axis0 + sl, W.tri[S - Wb + lane], &W.key[lane][0]);
+                h = fl & 1u;
+                exact += fl >> 1;
                 W.hit[lane] = h ? 1 : 0;
                 if (h) {
-                    W.key[lane][0] = k0;
-                    W.key[lane][1] = k1;
-                    W.key[lane][2] = k2;
+                    k0 = W.key[lane][0];
+                    k1 = W.key[lane][1];
+                    k2 = W.key[lane][2];
                 }
             }
             __syncwarp();
@@ -547,11 +568,11 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
     // ---- rays that span several cells or overflow the pool ----
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        uint32_t bigMask = __ballot_sync(SB_FULL, legacy[s]);
+        uint32_t bigMask = __ballot_sync(SB_FULL, s ? legacy1 : legacy0);
         while (bigMask) {
             const int b = __ffs(bigMask) - 1;
             bigMask &= bigMask - 1;
-            const uint32_t nb = __shfl_sync(SB_FULL, n[s], b); // 0 for a ray of several cells: not counted yet
+            const uint32_t nb = __shfl_sync(SB_FULL, s ? n1 : n0, b); // 0 for a ray of several cells: not counted yet
             const uint2 d = big_ray(g, T, o, reinterpret_cast<long long *>(W.tri), axis0 + s, __shfl_sync(SB_FULL, p.x, b),
                 __shfl_sync(SB_FULL, p.y, b), __shfl_sync(SB_FULL, p.z, b), nb, lane);
             if (lane == b)

@@ -13,15 +13,15 @@
 // bounds and to ray bounds alike, so the quantised test can only over-accept; the
 // exact double test of the reference follows in the classifier.
 //
-// Build = count (atomics) -> in-place chained scan -> fill (atomics), three axes
-// in one pass each, triangles visited in Morton order so neighbouring threads
+// Build = count (atomics; done by the leaf kernel of sb_build.cu while the box is in
+// registers, together with the 15-bit quantised box it stores) -> in-place chained
+// scan -> fill (atomics), triangles visited in Morton order so neighbouring threads
 // hit neighbouring cells.
 #include "sb_internal.h"
 #include "sb_gridq.cuh"
 
 namespace {
 
-constexpr uint32_t MAX_CELLS_PER_TRI = 1024; // larger footprints go to the per-axis "big" list
 
 // Cell size = beta x mean triangle-box extent along each world axis, so a
 // triangle covers about (1 + 1/beta)^2 cells on every grid whatever the mesh's
@@ -71,55 +71,35 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
     *out = g;
 }
 
-struct TriCells {
-    uint32_t qlo[3], qhi[3];
-};
-
-__device__ __forceinline__ TriCells quantise_box(const BoxD &b, const GridParams &g)
-{
-    TriCells t;
-    t.qlo[0] = quant15(b.lox, g.org[0], g.scl[0]); t.qhi[0] = quant15(b.hix, g.org[0], g.scl[0]);
-    t.qlo[1] = quant15(b.loy, g.org[1], g.scl[1]); t.qhi[1] = quant15(b.hiy, g.org[1], g.scl[1]);
-    t.qlo[2] = quant15(b.loz, g.org[2], g.scl[2]); t.qhi[2] = quant15(b.hiz, g.org[2], g.scl[2]);
-    return t;
-}
-
-// One thread per (triangle, axis): three times the parallelism and a third of the
-// serial atomic chain of a per-triangle loop.  Triangles are visited in Morton
-// order, so neighbouring threads update neighbouring cells.
-template <bool FILL>
-__global__ void __launch_bounds__(256) grid_bin_kernel(const double2 *__restrict__ sbox, const Rec32 *__restrict__ leaf,
-    uint32_t nT, const GridParams *__restrict__ gp, uint32_t *__restrict__ E, uint4 *__restrict__ refs,
-    uint32_t refCap, uint4 *__restrict__ bigRefs, uint32_t *__restrict__ bigCount, uint32_t bigCap)
+// Fill pass: one thread per (triangle, axis) -- three times the parallelism and a third
+// of the serial atomic chain of a per-triangle loop.  Triangles are visited in Morton
+// order, so neighbouring threads update neighbouring cells.  The quantised boxes were
+// formed (and the cells counted) by the leaf kernel of sb_build.cu.
+__global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict__ qbox, uint32_t nT,
+    const GridParams *__restrict__ gp, uint32_t *__restrict__ E, uint4 *__restrict__ refs, uint32_t refCap,
+    uint4 *__restrict__ bigRefs, uint32_t *__restrict__ bigCount, uint32_t bigCap)
 {
     __shared__ GridParams g;
-    if (threadIdx.x == 0)
-        g = *gp;
+    if (threadIdx.x < sizeof(GridParams) / 4)
+        reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(gp)[threadIdx.x];
     __syncthreads();
     const uint32_t blocksPerAxis = (nT + 255) / 256;
     const int a = blockIdx.x / blocksPerAxis;
     const uint32_t j = (blockIdx.x % blocksPerAxis) * 256 + threadIdx.x;
     if (j >= nT)
         return;
-    BoxD b = load_boxd(sbox + 3 * (size_t)j);
-    TriCells t = quantise_box(b, g);
-    const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
-    const uint32_t qlu = t.qlo[u], qhu = t.qhi[u], qlv = t.qlo[v], qhv = t.qhi[v];
-    const uint32_t cu0 = qlu >> g.shiftU[a], cu1 = qhu >> g.shiftU[a];
-    const uint32_t cv0 = qlv >> g.shiftV[a], cv1 = qhv >> g.shiftV[a];
-    const uint32_t ncell = (cu1 - cu0 + 1) * (cv1 - cv0 + 1);
-    uint4 rec = make_uint4(0, 0, 0, 0);
-    if (FILL) {
-        rec = grid_ref_pack(qlu, qhu, qlv, qhv, t.qlo[a], t.qhi[a], (uint32_t)load_rec(leaf + j).ref);
-    }
-    if (ncell > MAX_CELLS_PER_TRI) {
-        uint32_t slot = atomicAdd(&bigCount[FILL ? 3 + a : a], 1u);
-        if (FILL && slot < bigCap)
+    const uint4 q = __ldg(qbox + j);
+    const GridFootprint f = grid_footprint(q, g, a);
+    const uint32_t cu0 = f.cu0, cu1 = f.cu1, cv0 = f.cv0, cv1 = f.cv1;
+    const uint4 rec = grid_ref_pack(f.qu & 0xffffu, f.qu >> 16, f.qv & 0xffffu, f.qv >> 16, f.qa & 0xffffu, f.qa >> 16, q.w);
+    if ((cu1 - cu0 + 1) * (cv1 - cv0 + 1) > SB_GRID_MAX_CELLS_PER_TRI) {
+        uint32_t slot = atomicAdd(&bigCount[3 + a], 1u);
+        if (slot < bigCap)
             bigRefs[(size_t)a * bigCap + slot] = rec;
         return;
     }
     const uint32_t base = g.cellBase[a], nu = g.nu[a];
-    if (FILL && cu1 - cu0 <= 1 && cv1 - cv0 <= 1) {
+    if (cu1 - cu0 <= 1 && cv1 - cv0 <= 1) {
         // common case (footprint at most 2 x 2 cells): all atomics are issued before the
         // first dependent store, so their round trips overlap instead of adding up
         const bool du = cu1 != cu0, dv = cv1 != cv0;
@@ -136,14 +116,9 @@ __global__ void __launch_bounds__(256) grid_bin_kernel(const double2 *__restrict
     }
     for (uint32_t cv = cv0; cv <= cv1; ++cv)
         for (uint32_t cu = cu0; cu <= cu1; ++cu) {
-            uint32_t cell = base + cv * nu + cu;
-            if (FILL) {
-                uint32_t pos = atomicSub(&E[cell + 1], 1u) - 1u; // fill each cell back to front
-                if (pos < refCap)
-                    refs[pos] = rec;
-            } else {
-                atomicAdd(&E[cell + 1], 1u);
-            }
+            uint32_t pos = atomicSub(&E[base + cv * nu + cu + 1], 1u) - 1u; // fill each cell back to front
+            if (pos < refCap)
+                refs[pos] = rec;
         }
 }
 
@@ -238,25 +213,33 @@ size_t sbk_grid_scan_status_words(uint32_t maxCells)
     return 2 * tiles + 4; // u64 status per tile + the tile counter
 }
 
-// Phase 1: parameters, per-cell counts, inclusive scan.  Afterwards
-// E[c + 1] = end of cell c and gridBigCount[6] = total number of references.
-cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc)
+// Phase 0 (before the leaf kernel, which counts): cleared counters + grid parameters.
+cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc)
 {
     if (m.nT == 0)
         return cudaSuccess;
     const uint32_t maxCells = 3u << m.gridCellBits;
     cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)maxCells + 2), s);
     cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
-    size_t statusWords = sbk_grid_scan_status_words(maxCells);
-    cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * statusWords, s);
+    cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * sbk_grid_scan_status_words(maxCells), s);
     grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, m.extentSum, m.nT, (int)m.gridCellBits, beta, m.gridParams);
-    grid_bin_kernel<false><<<3 * ((m.nT + 255) / 256), 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, nullptr, 0,
-        nullptr, m.gridBigCount, 0);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+// Phase 1 (after the leaf kernel): inclusive scan of the per-cell counts.  Afterwards
+// E[c + 1] = end of cell c and gridBigCount[6] = total number of references.
+cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    const uint32_t maxCells = 3u << m.gridCellBits;
+    size_t statusWords = sbk_grid_scan_status_words(maxCells);
     uint32_t tiles = (maxCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
     unsigned long long *status = reinterpret_cast<unsigned long long *>(scanScratch);
     uint32_t *counter = scanScratch + statusWords - 2;
     inclusive_scan_kernel<<<tiles, SCAN_THREADS, 0, s>>>(m.gridE, m.gridParams, status, counter, m.gridBigCount + 6);
-    lc.kernels += 3;
+    lc.kernels += 1;
     return cudaGetLastError();
 }
 
@@ -267,7 +250,7 @@ cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
 {
     if (m.nT == 0)
         return cudaSuccess;
-    grid_bin_kernel<true><<<3 * ((m.nT + 255) / 256), 256, 0, s>>>(m.sbox, m.leaf, m.nT, m.gridParams, m.gridE, m.gridRefs,
+    grid_fill_kernel<<<3 * ((m.nT + 255) / 256), 256, 0, s>>>(m.qbox, m.nT, m.gridParams, m.gridE, m.gridRefs,
         m.gridRefCap, m.gridBigRefs, m.gridBigCount, m.gridBigCap);
     lc.kernels += 1;
     return cudaGetLastError();

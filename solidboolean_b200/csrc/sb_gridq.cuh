@@ -14,6 +14,7 @@
 // the closed-interval test are 3 subtractions, 2 logic ops and one compare.
 #pragma once
 #include "sb_common.cuh"
+#include "sb_internal.h"
 
 #define SB_Q_MAX 32767u
 #define SB_Q_BITS 15
@@ -55,4 +56,56 @@ __device__ __forceinline__ RayQ ray_pack(uint32_t aU, uint32_t bU, uint32_t aV, 
 __device__ __forceinline__ bool ray_ref_match(const RayQ &q, const uint4 &r)
 {
     return (((q.x - r.x) & (q.y - r.y) & (q.z - r.z)) & SB_Q_GUARD) == SB_Q_GUARD;
+}
+
+// ---- binning (shared by the leaf kernel of sb_build.cu, which counts, and sb_grid.cu, which fills) ----
+#define SB_GRID_MAX_CELLS_PER_TRI 1024u // larger footprints go to the per-axis "big" list
+
+// quantised triangle box: one word per world axis, lo | hi << 16; .w = triangle id
+__device__ __forceinline__ uint4 quantise_box(const BoxD &b, const GridParams &g, uint32_t id)
+{
+    return make_uint4(quant15(b.lox, g.org[0], g.scl[0]) | (quant15(b.hix, g.org[0], g.scl[0]) << 16),
+                      quant15(b.loy, g.org[1], g.scl[1]) | (quant15(b.hiy, g.org[1], g.scl[1]) << 16),
+                      quant15(b.loz, g.org[2], g.scl[2]) | (quant15(b.hiz, g.org[2], g.scl[2]) << 16), id);
+}
+
+__device__ __forceinline__ uint32_t qbox_axis(const uint4 &q, int d) { return d == 0 ? q.x : d == 1 ? q.y : q.z; }
+
+// footprint of a quantised box on grid a (rays along axis a; u, v = the other two axes)
+struct GridFootprint {
+    uint32_t cu0, cu1, cv0, cv1;
+    uint32_t qu, qv, qa; // lo | hi << 16 along u, v, a
+};
+
+__device__ __forceinline__ GridFootprint grid_footprint(const uint4 &q, const GridParams &g, int a)
+{
+    GridFootprint f;
+    const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+    f.qu = qbox_axis(q, u);
+    f.qv = qbox_axis(q, v);
+    f.qa = qbox_axis(q, a);
+    f.cu0 = (f.qu & 0xffffu) >> g.shiftU[a];
+    f.cu1 = (f.qu >> 16) >> g.shiftU[a];
+    f.cv0 = (f.qv & 0xffffu) >> g.shiftV[a];
+    f.cv1 = (f.qv >> 16) >> g.shiftV[a];
+    return f;
+}
+
+// count pass for one triangle: +1 on every cell it covers on the three grids (E[c + 1]
+// = number of references of cell c), or on the axis's big-list counter
+__device__ __forceinline__ void grid_count_tri(const uint4 &q, const GridParams &g, uint32_t *__restrict__ E,
+    uint32_t *__restrict__ bigCount)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const GridFootprint f = grid_footprint(q, g, a);
+        if ((f.cu1 - f.cu0 + 1) * (f.cv1 - f.cv0 + 1) > SB_GRID_MAX_CELLS_PER_TRI) {
+            atomicAdd(&bigCount[a], 1u);
+            continue;
+        }
+        const uint32_t base = g.cellBase[a], nu = g.nu[a];
+        for (uint32_t cv = f.cv0; cv <= f.cv1; ++cv)
+            for (uint32_t cu = f.cu0; cu <= f.cu1; ++cu)
+                atomicAdd(&E[base + cv * nu + cu + 1], 1u);
+    }
 }

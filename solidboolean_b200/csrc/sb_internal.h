@@ -35,16 +35,15 @@ struct MeshDev {
     // derived (sb_mesh_build)
     double4 *vtx = nullptr;             // padded vertices
     unsigned long long *bounds = nullptr; // 6 order-encoded doubles: min xyz, max xyz
-    double2 *tbox = nullptr;            // 3*nT: exact triangle boxes, original order
     double *normal = nullptr;           // 3*nT, original order
-    double *cent = nullptr;             // 3*nT face centroids ((v0+v1)+v2)/3.0, original order
-    double *scent = nullptr;            // 3*nTpad the same in Morton order (classification queries)
+    double *scent = nullptr;            // 3*nTpad face centroids ((v0+v1)+v2)/3.0 in Morton order (classification queries)
     uint32_t *mkey = nullptr, *mkeyTmp = nullptr;   // Morton keys (sort ping-pong)
     uint32_t *order = nullptr, *orderTmp = nullptr; // triangle ids (sort ping-pong)
     uint32_t *sortedKey = nullptr;      // -> mkey or mkeyTmp after the sort
     uint32_t *sortedTri = nullptr;      // -> order or orderTmp: sorted position -> triangle id
     Rec32 *leaf = nullptr;              // nTpad sorted-triangle records (float box + id)
     double2 *sbox = nullptr;            // 3*nTpad exact boxes in sorted order
+    uint4 *qbox = nullptr;              // nTpad quantised boxes (sb_gridq.cuh) + triangle id, sorted order
     Rec32 *cbox = nullptr;              // M cluster boxes
     uint32_t *ckey = nullptr;           // M cluster keys
     Rec32 *nodes = nullptr;             // 2*(M-1) child records
@@ -69,8 +68,13 @@ struct LaunchCounter {
 };
 
 // sb_build.cu
-cudaError_t sbk_build_mesh(cudaStream_t s, MeshDev &m, uint32_t *radixWs, size_t radixWsWords, int smCount, LaunchCounter &lc);
+// sbk_build_sort: bounds, per-triangle data, Morton sort; sbk_build_leaves (after
+// sbk_grid_prepare): sorted leaves / boxes / centroids / clusters + quantised boxes and
+// the per-cell counts of the ray grids
+cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc);
+cudaError_t sbk_build_leaves(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
 cudaError_t sbk_build_tree(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
+cudaError_t sbk_triangle_boxes(cudaStream_t s, const MeshDev &m, double2 *out /* 3*nT, original order */, LaunchCounter &lc);
 
 // sb_broad.cu -- candidate keys: (((a << bitsB) | b) << 2), code bits zero
 cudaError_t sbk_broad_phase(cudaStream_t s, const MeshDev &A, const MeshDev &B, uint32_t groupBegin, uint32_t groupEnd,
@@ -119,5 +123,6 @@ size_t sbk_radix_workspace_words(size_t n);
 
 // sb_grid.cu
 size_t sbk_grid_scan_status_words(uint32_t maxCells);
-cudaError_t sbk_grid_count(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc);
+cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc);
+cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc);
 cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc);

@@ -8,10 +8,20 @@
 
 namespace sbradix {
 
-constexpr int THREADS = 256;
+#ifndef SB_RADIX_THREADS
+#define SB_RADIX_THREADS 512
+#endif
+#ifndef SB_RADIX_ITEMS
+#define SB_RADIX_ITEMS 8
+#endif
+// 512 threads x 8 keys: the same 4096-key tile as 256 x 16, but ~40 registers per thread,
+// so three CTAs fit an SM and all tiles of a 1M-key sort are resident at once (the
+// decoupled look-back never waits for a tile that has not been scheduled yet)
+constexpr int THREADS = SB_RADIX_THREADS; // >= 256: thread d < 256 owns digit d in the scan phases
 constexpr int WARPS = THREADS / 32;
-constexpr int ITEMS = 16;
-constexpr int TILE = THREADS * ITEMS; // 4096 keys per CTA
+constexpr int ITEMS = SB_RADIX_ITEMS;
+constexpr int TILE = THREADS * ITEMS; // keys per CTA
+static_assert(THREADS >= 256 && THREADS % 32 == 0, "one thread per digit");
 constexpr int MAX_PASSES = 8;
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
@@ -48,47 +58,41 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ 
     if (!s_last)
         return;
     __threadfence();
-    // exclusive scan of each pass's bins (thread t owns bins t*PER .. t*PER+PER-1)
-    constexpr int PER = RADIX / THREADS;
-    __shared__ uint32_t s_scan[THREADS];
+    // exclusive scan of each pass's bins (thread d < RADIX owns bin d)
+    static_assert(RADIX == 256, "one thread per digit");
+    __shared__ uint32_t s_scan[RADIX];
+    const bool own = threadIdx.x < RADIX;
     for (int p = 0; p < passes; ++p) {
-        uint32_t v[PER];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            v[i] = __ldcg(&hist[p * RADIX + threadIdx.x * PER + i]);
-            sum += v[i];
-        }
-        s_scan[threadIdx.x] = sum;
+        uint32_t v = own ? __ldcg(&hist[p * RADIX + threadIdx.x]) : 0u;
+        if (own)
+            s_scan[threadIdx.x] = v;
         __syncthreads();
-        for (int off = 1; off < THREADS; off <<= 1) {
-            uint32_t t = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+        for (int off = 1; off < RADIX; off <<= 1) {
+            uint32_t t = (own && (int)threadIdx.x >= off) ? s_scan[threadIdx.x - off] : 0;
             __syncthreads();
-            s_scan[threadIdx.x] += t;
+            if (own)
+                s_scan[threadIdx.x] += t;
             __syncthreads();
         }
-        uint32_t excl = s_scan[threadIdx.x] - sum;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            hist[p * RADIX + threadIdx.x * PER + i] = excl;
-            excl += v[i];
-        }
+        if (own)
+            hist[p * RADIX + threadIdx.x] = s_scan[threadIdx.x] - v;
         __syncthreads();
     }
 }
 
 template <typename KeyT, bool HAS_VALUES, int BITS>
-__global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restrict__ keysIn, KeyT *__restrict__ keysOut,
+__global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(const KeyT *__restrict__ keysIn, KeyT *__restrict__ keysOut,
     const uint32_t *__restrict__ valsIn, uint32_t *__restrict__ valsOut, uint32_t n, int shift,
     const uint32_t *__restrict__ digitBase /* [RADIX] exclusive */, volatile uint32_t *lookback /* [tiles][RADIX] */,
     uint32_t *__restrict__ tileCounter)
 {
     constexpr int RADIX = 1 << BITS;
-    constexpr int PER = RADIX / THREADS; // digits owned by one thread in the scan / look-back phase
-    __shared__ uint32_t s_warpHist[WARPS][RADIX];
+    static_assert(RADIX == 256, "one thread per digit");
+    __shared__ uint16_t s_warpHist[WARPS][RADIX]; // counts <= 32 * ITEMS, prefixes <= TILE
+    static_assert(TILE <= 65535, "16-bit per-warp digit counters");
     __shared__ uint32_t s_digitStart[RADIX];
     __shared__ uint32_t s_globalOff[RADIX];
-    __shared__ uint32_t s_scanTmp[WARPS];
+    __shared__ uint32_t s_scanTmp[RADIX / 32];
     __shared__ uint32_t s_tile;
     __shared__ __align__(16) unsigned char s_raw[TILE * sizeof(KeyT)];
     KeyT *s_keys = reinterpret_cast<KeyT *>(s_raw);
@@ -97,8 +101,8 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0)
         s_tile = atomicAdd(tileCounter, 1u);
-    for (int i = tid; i < WARPS * RADIX; i += THREADS)
-        (&s_warpHist[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * RADIX / 2; i += THREADS)
+        reinterpret_cast<uint32_t *>(&s_warpHist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t tileBase = tile * TILE;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
         uint32_t old = 0;
         if (lane == leader) {
             old = s_warpHist[warp][digit];
-            s_warpHist[warp][digit] = old + __popc(peers);
+            s_warpHist[warp][digit] = (uint16_t)(old + __popc(peers));
         }
         old = __shfl_sync(SB_FULL, old, leader);
         rank[i] = old + __popc(peers & ltMask);
@@ -131,35 +135,25 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
     }
     __syncthreads();
 
-    // thread t owns digits t*PER..: exclusive scan over the warps, tile aggregate, look-back
+    // thread d < RADIX owns digit d: exclusive scan over the warps, tile aggregate, look-back
     {
-        uint32_t sums[PER], excls[PER];
-        uint32_t mySum = 0;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int d = tid * PER + i;
-            uint32_t sum = 0;
+        const bool own = tid < RADIX;
+        uint32_t sum = 0, excl = 0;
+        if (own) {
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) {
-                uint32_t t = s_warpHist[w][d];
-                s_warpHist[w][d] = sum;
+                uint32_t t = s_warpHist[w][tid];
+                s_warpHist[w][tid] = (uint16_t)sum;
                 sum += t;
             }
-            sums[i] = sum;
-            mySum += sum;
             if (tile == 0)
-                lookback[d] = sum | FLAG_PREFIX;
+                lookback[tid] = sum | FLAG_PREFIX;
             else
-                lookback[tile * RADIX + d] = sum | FLAG_AGG;
-        }
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int d = tid * PER + i;
-            uint32_t excl = 0;
+                lookback[tile * RADIX + tid] = sum | FLAG_AGG;
             if (tile != 0) {
                 int t = (int)tile - 1;
                 while (true) {
-                    uint32_t v = lookback[t * RADIX + d];
+                    uint32_t v = lookback[t * RADIX + tid];
                     if (v & FLAG_PREFIX) {
                         excl += v & VALUE_MASK;
                         break;
@@ -169,33 +163,29 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
                         --t;
                     }
                 }
-                lookback[tile * RADIX + d] = (excl + sums[i]) | FLAG_PREFIX;
+                lookback[tile * RADIX + tid] = (excl + sum) | FLAG_PREFIX;
             }
-            excls[i] = excl;
         }
-        // block-wide exclusive scan of the per-thread digit totals
-        uint32_t incl = mySum;
+        // block-wide exclusive scan of the digit totals (warps 0..7 hold them)
+        uint32_t incl = sum;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
             if (lane >= off)
                 incl += t;
         }
-        if (lane == 31)
+        if (own && lane == 31)
             s_scanTmp[warp] = incl;
         __syncthreads();
-        uint32_t warpOff = 0;
+        if (own) {
+            uint32_t warpOff = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w)
-            if (w < warp)
-                warpOff += s_scanTmp[w];
-        uint32_t start = warpOff + incl - mySum;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int d = tid * PER + i;
-            s_digitStart[d] = start;
-            s_globalOff[d] = digitBase[d] + excls[i] - start;
-            start += sums[i];
+            for (int w = 0; w < RADIX / 32; ++w)
+                if (w < warp)
+                    warpOff += s_scanTmp[w];
+            const uint32_t start = warpOff + incl - sum;
+            s_digitStart[tid] = start;
+            s_globalOff[tid] = digitBase[tid] + excl - start;
         }
     }
     __syncthreads();
