@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
     const uint32_t *__restrict__ sortedKey, const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, uint32_t nTpad, Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, double *__restrict__ scent,
     Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey, const GridParams *__restrict__ gp, uint4 *__restrict__ qbox,
-    uint32_t *__restrict__ gridE, uint32_t *__restrict__ gridBigCount)
+    uint32_t *__restrict__ gridE, uint32_t *__restrict__ gridBigCount, int gridAxes)
 {
     __shared__ GridParams g;
     if (threadIdx.x < sizeof(GridParams) / 4)
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
         // ray grids (sb_grid.cu): the quantised box, and the count pass while it is in registers
         const uint4 q = quantise_box(bd, g, t);
         qbox[j] = q;
-        grid_count_tri(q, g, gridE, gridBigCount);
+        grid_count_tri(q, g, gridE, gridBigCount, gridAxes);
     }
     store_boxd(sbox + 3 * (size_t)j, bd);
     store_rec(leaf + j, bf, ref, (int)j);
@@ -333,7 +333,7 @@ cudaError_t sbk_build_leaves(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
     if (m.nT == 0)
         return cudaSuccess;
     leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.vtx, m.tri, m.nT, m.nV, m.nTpad,
-        m.leaf, m.sbox, m.scent, m.cbox, m.ckey, m.gridParams, m.qbox, m.gridE, m.gridBigCount);
+        m.leaf, m.sbox, m.scent, m.cbox, m.ckey, m.gridParams, m.qbox, m.gridE, m.gridBigCount, m.gridAxes);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -118,6 +118,7 @@ struct sb_mesh {
     uint32_t *hCounts = nullptr;     // pinned: [0] total refs, [1..3] big-list lengths
     uint32_t *hErr = nullptr;        // pinned: index-validation flag read back with the counts
     bool gridSized = false;          // reference list already sized by an earlier build
+    bool grid3Wanted = false;        // a vote (or a per-axis query) needed the third grid: builds include it from now on
     bool treeBuilt = false;          // LBVH topology built (lazily, on first use as a traversal target)
     bool treeWanted = false;         // the mesh has been a traversal target: rebuilds include the LBVH
 };
@@ -588,6 +589,69 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
     return SB_OK;
 }
 
+// First build (or first build with a third grid): the reference list is sized from the
+// counts (16-byte read-back on the mesh's stream), then filled.
+static int grid_size_and_fill(sb_mesh *m)
+{
+    sb_context *c = m->ctx;
+    cudaStream_t st = m->stream;
+    uint32_t *h = m->hCounts;
+    SB_CUDA(cudaMemcpyAsync(h, m->d.gridBigCount + 6, 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, st));
+    int *hErr = reinterpret_cast<int *>(m->hErr);
+    SB_CUDA(cudaMemcpyAsync(hErr, m->d.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (*hErr)
+        return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
+    size_t nRefs = h[0];
+    uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
+    for (int k = 0; k < 3; ++k)
+        m->d.gridBigN[k] = h[1 + k];
+    // + 8: the classifier reads whole groups of references
+    size_t bytes = 16 * (std::max<size_t>(nRefs, 1) + 3 * (size_t)std::max<uint32_t>(bigMax, 1) + 8);
+    if (m->gridArena)
+        cudaFreeAsync(m->gridArena, st);
+    SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, st));
+    m->gridArenaBytes = bytes;
+    m->d.gridRefs = static_cast<uint4 *>(m->gridArena);
+    m->d.gridRefCap = (uint32_t)std::max<size_t>(nRefs, 1);
+    m->d.gridBigRefs = m->d.gridRefs + std::max<size_t>(nRefs, 1);
+    m->d.gridBigCap = std::max<uint32_t>(bigMax, 1);
+    m->gridSized = true;
+    StageTimer t(c, SB_STAGE_BUILD, st);
+    SB_CUDA(sbk_grid_fill(st, m->d, c->lc));
+    return SB_OK;
+}
+
+// The third ray grid (rays along z) is only binned once something needs it: a point
+// whose first two votes disagree, or a per-axis query.  The mesh's grids are then built
+// again from the stored quantised boxes with all three axes (and every later
+// sb_mesh_build includes the third one).  Nothing may be reading the grids meanwhile.
+static int ensure_grid3(const sb_mesh *mc)
+{
+    sb_mesh *m = const_cast<sb_mesh *>(mc);
+    if (m->d.gridAxes == 3 || !m->d.nT)
+        return SB_OK;
+    sb_context *c = m->ctx;
+    for (int l = 0; l < 3; ++l)
+        SB_CUDA(cudaStreamSynchronize(c->lanes[l].stream));
+    cudaStream_t st = m->stream;
+    m->d.gridAxes = 3;
+    m->grid3Wanted = true;
+    m->gridSized = false;
+    {
+        StageTimer t(c, SB_STAGE_BUILD, st);
+        SB_CUDA(sbk_grid_recount(st, m->d, m->scanScratch, c->lc));
+        SB_CUDA(sbk_grid_scan(st, m->d, m->scanScratch, c->lc));
+    }
+    int r = grid_size_and_fill(m);
+    if (r)
+        return r;
+    SB_CUDA(cudaEventRecord(m->ready, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
 int sb_mesh_build(sb_mesh *m)
 {
     if (!m)
@@ -596,6 +660,9 @@ int sb_mesh_build(sb_mesh *m)
     DeviceGuard g(c->device);
     cudaStream_t st = m->stream;
     m->d.sortBeginBit = c->sortBeginBit;
+    if ((m->d.gridAxes == 3) != m->grid3Wanted)
+        m->gridSized = false; // the reference list was sized for another number of grids
+    m->d.gridAxes = m->grid3Wanted ? 3 : 2;
     // after whatever the context stream still does with this mesh's buffers
     order_after_context(c, m);
     {
@@ -620,30 +687,9 @@ int sb_mesh_build(sb_mesh *m)
         }
     }
     if (m->d.nT && !m->gridSized) {
-        // first build: the reference list is sized from the counts (16-byte read-back)
-        uint32_t *h = m->hCounts;
-        SB_CUDA(cudaMemcpyAsync(h, m->d.gridBigCount + 6, 4, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, st));
-        int *hErr = reinterpret_cast<int *>(m->hErr);
-        SB_CUDA(cudaMemcpyAsync(hErr, m->d.err, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        if (*hErr)
-            return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
-        size_t nRefs = h[0];
-        uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
-        for (int k = 0; k < 3; ++k)
-            m->d.gridBigN[k] = h[1 + k];
-        size_t bytes = 16 * (std::max<size_t>(nRefs, 1) + 3 * (size_t)std::max<uint32_t>(bigMax, 1) + 8); // + 8: the classifier reads
-                                                                                    // whole groups of 8 references
-        SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, st));
-        m->gridArenaBytes = bytes;
-        m->d.gridRefs = static_cast<uint4 *>(m->gridArena);
-        m->d.gridRefCap = (uint32_t)std::max<size_t>(nRefs, 1);
-        m->d.gridBigRefs = m->d.gridRefs + std::max<size_t>(nRefs, 1);
-        m->d.gridBigCap = std::max<uint32_t>(bigMax, 1);
-        m->gridSized = true;
-        StageTimer t(c, SB_STAGE_BUILD, st);
-        SB_CUDA(sbk_grid_fill(st, m->d, c->lc));
+        int r = grid_size_and_fill(m);
+        if (r)
+            return r;
     }
     SB_CUDA(cudaEventRecord(m->ready, st));
     m->built = true;
@@ -1195,27 +1241,51 @@ int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret
 // ---- classification --------------------------------------------------------------
 
 // One classification on a lane: launch enqueues the kernel and the counter read-back;
-// finish waits for the lane and repeats the call once, with the exact size, if the
-// scratch of the many-layer rays was too small.
+// finish waits for the lane, repeats the call once with the exact size if the scratch of
+// the many-layer rays was too small, and -- when the target had only its first two ray
+// grids and some points' two votes disagree -- has the third grid built and traces the
+// third ray of just those points in a second launch.
 struct ClassifyJob {
-    void *scratch = nullptr;
+    void *scratch = nullptr;      // [many-layer keys: 24 * cap][undecided list: 4 * points]
     unsigned long long cap = 0;
     uint32_t points = 0;
     int firstAxes = 2;
     bool launched = false;
+    bool second = false;          // this is the third-axis launch over the undecided list
+    void *firstScratch = nullptr; // keeps that list alive during the second launch
+    size_t firstKeyBytes = 0;     // offset of the list in firstScratch
+    uint32_t undecided = 0;
 };
 
-static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a,
+static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a0,
     ClassifyJob &job, unsigned long long forceCap = 0)
 {
-    job.points = a.end - a.begin;
-    job.firstAxes = a.perAxis ? 3 : 2; // without the per-axis bits the vote is lazy (third ray on demand)
+    ClassifyArgs a = a0;
+    if (a.perAxis) {
+        int r = ensure_grid3(target); // all three rays of every point
+        if (r)
+            return r;
+        cudaStreamWaitEvent(lane.stream, target->ready, 0);
+    }
+    if (!job.second) {
+        job.points = a.end - a.begin;
+        job.firstAxes = a.perAxis ? 3 : 2; // without the per-axis bits the vote is lazy (third ray on demand)
+    }
     job.cap = forceCap ? forceCap : std::max<unsigned long long>(1 << 16, lane.bigHint + lane.bigHint / 4);
-    SB_CUDA(cudaMallocAsync(&job.scratch, 24 * (size_t)job.cap, lane.stream));
+    const size_t keyBytes = align256(24 * (size_t)job.cap);
+    SB_CUDA(cudaMallocAsync(&job.scratch, keyBytes + 4 * (size_t)std::max<uint32_t>(job.points, 1), lane.stream));
     SB_CUDA(cudaMemsetAsync(lane.d, 0, sizeof(DeviceScalars), lane.stream));
+    if (job.second) {
+        a.list = reinterpret_cast<const uint32_t *>(static_cast<char *>(job.firstScratch) + job.firstKeyBytes);
+        a.listCount = job.undecided;
+        a.thirdAxisOnly = true;
+    } else {
+        a.undecidedList = reinterpret_cast<uint32_t *>(static_cast<char *>(job.scratch) + keyBytes);
+        job.firstKeyBytes = keyBytes;
+    }
     unsigned long long *trace = nullptr;
     const char *traceFile = getenv("SB_CLASSIFY_TRACE"); // dev: per-CTA timeline of every classification launch
-    const uint32_t traceBlocks = sbk_classify_blocks(job.points);
+    const uint32_t traceBlocks = sbk_classify_blocks(job.second ? job.undecided : job.points);
     if (traceFile)
         SB_CUDA(cudaMalloc(&trace, 32 * (size_t)traceBlocks));
     {
@@ -1245,26 +1315,59 @@ static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh 
 {
     if (!accumulateStats)
         c->lastRays = c->lastCands = 0;
-    for (int attempt = 0;; ++attempt) {
+    auto release = [&]() {
+        if (job.scratch)
+            cudaFreeAsync(job.scratch, lane.stream);
+        if (job.firstScratch)
+            cudaFreeAsync(job.firstScratch, lane.stream);
+        job.scratch = job.firstScratch = nullptr;
+    };
+    for (int attempt = 0;;) {
         SB_CUDA(cudaStreamSynchronize(lane.stream));
         const unsigned long long needed = lane.h->stats[1]; // scratch entries the many-layer rays asked for
         const uint32_t undecided = lane.h->overflowCount;
-        lane.bigHint = needed;
+        lane.bigHint = std::max(lane.bigHint, needed);
         if (getenv("SB_DEBUG"))
-            fprintf(stderr, "[sb] classify: points %u axes %d undecided %u exact candidates %llu big-ray entries %llu (cap %llu)\n",
-                job.points, job.firstAxes, undecided, (unsigned long long)lane.h->stats[0], needed, job.cap);
-        cudaFreeAsync(job.scratch, lane.stream);
-        job.scratch = nullptr;
-        if (needed > job.cap) { // scratch too small: repeat with the exact size
-            if (attempt)
+            fprintf(stderr, "[sb] classify%s: points %u axes %d undecided %u exact candidates %llu big-ray entries %llu (cap %llu) grids %d\n",
+                job.second ? " (third axis)" : "", job.second ? job.undecided : job.points, job.firstAxes, undecided,
+                (unsigned long long)lane.h->stats[0], needed, job.cap, target->d.gridAxes);
+        if (needed > job.cap) { // scratch too small: repeat this launch with the exact size
+            cudaFreeAsync(job.scratch, lane.stream);
+            job.scratch = nullptr;
+            if (attempt++) {
+                release();
                 return fail(SB_ERR_CAPACITY, "many-layer ray scratch overflow after retry (%llu > %llu)", needed, job.cap);
+            }
             int r = classify_launch(c, lane, target, a, job, needed);
-            if (r)
+            if (r) {
+                release();
                 return r;
+            }
             continue;
         }
-        c->lastRays += (unsigned long long)job.firstAxes * job.points + (job.firstAxes == 2 ? undecided : 0);
         c->lastCands += lane.h->stats[0]; // exact candidates
+        if (!job.second) {
+            c->lastRays += (unsigned long long)job.firstAxes * job.points + (job.firstAxes == 2 ? undecided : 0);
+            if (job.firstAxes == 2 && undecided && target->d.gridAxes == 2) {
+                // the kernel could not trace the third ray (no third grid yet): it listed the points
+                job.firstScratch = job.scratch;
+                job.scratch = nullptr;
+                job.undecided = undecided;
+                job.second = true;
+                attempt = 0;
+                int r = ensure_grid3(target);
+                if (!r) {
+                    cudaStreamWaitEvent(lane.stream, target->ready, 0);
+                    r = classify_launch(c, lane, target, a, job);
+                }
+                if (r) {
+                    release();
+                    return r;
+                }
+                continue;
+            }
+        }
+        release();
         return SB_OK;
     }
 }

@@ -29,6 +29,8 @@
 // exactly).  A ray whose box straddles a cell border or that has more matches than
 // the pool holds is traced reference by reference by the warp (big_ray).
 // Majority: (float)insideCount / totalCount > 0.5 with totalCount == 3 (:508).
+// A target starts with the grids of axes 0 and 1 only; if a vote needs the third ray
+// and that grid does not exist yet, the points are listed for a second launch (sb_capi.cu).
 #include "sb_internal.h"
 #include "sb_gridq.cuh"
 #include "sb_raytri.cuh"
@@ -106,6 +108,7 @@ struct Target {
     const uint4 *bigRefs;
     uint32_t bigCap;
     uint32_t bigN0, bigN1, bigN2;
+    int naxes;                 // ray grids the target has (2: the third is built on demand, see ensure_grid3)
     const double4 *vtx;
     const uint32_t *tri;
     const double *normal;
@@ -118,6 +121,7 @@ struct Query {
     uint32_t nT;
     uint32_t begin;            // first point / sorted position
     uint32_t count;            // points in this launch
+    const uint32_t *list;      // optional: the launch's points as indices relative to `begin`
 };
 
 struct Out {
@@ -128,6 +132,8 @@ struct Out {
     unsigned long long *bigNeeded;  // entries the many-layer rays asked for (> bigCap: repeat)
     unsigned long long *exactCount; // true candidates (exact box overlap), roofline accounting
     unsigned int *undecidedCount;   // points whose first two votes disagreed
+    uint32_t *undecidedList;   // ... listed here (relative to `begin`) when the target has no third grid yet
+    int thirdOnly;             // second launch: only the third ray, of the listed points; its vote decides
     uint32_t poolLimit;        // rays with more matches go through big_ray (<= POOL; smaller only in tests)
     unsigned long long *trace; // dev: per CTA {sm id, start ns, end ns, entries evaluated} (SB_CLASSIFY_TRACE), or null
 };
@@ -601,10 +607,11 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
     const uint32_t j = blockIdx.x * CT + threadIdx.x;
 
     d3 p = {0, 0, 0};
-    uint32_t outIndex = 0;
+    uint32_t outIndex = 0, local = 0;
     bool active = j < q.count;
     if (active) {
-        const uint32_t idx = q.begin + j;
+        local = q.list ? __ldg(q.list + j) : j;
+        const uint32_t idx = q.begin + local;
         if (q.pts) {
             p = {q.pts[3 * (size_t)idx], q.pts[3 * (size_t)idx + 1], q.pts[3 * (size_t)idx + 2]};
             outIndex = idx;
@@ -619,13 +626,19 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
     }
 
     uint32_t votes = 0, exact = 0;
-    bool undecided = false;
-    for (int round = 0; round < 2; ++round) {
+    bool undecided = false, deferred = false;
+    // second launch (thirdOnly): votes 0 and 1 of the listed points disagreed, so only round 1
+    // (axis 2) runs and its vote is the majority
+    for (int round = o.thirdOnly ? 1 : 0; round < 2; ++round) {
         bool want = active;
-        if (round == 1 && !o.perAxis) {
+        if (round == 1 && !o.perAxis && !o.thirdOnly) {
             // lazy majority: the third ray only where the first two disagree
             undecided = active && (((votes >> 1) ^ votes) & 1u);
             want = undecided;
+            if (T.naxes < 3) { // no third grid yet: the host has it built and launches again for these points
+                deferred = true;
+                break;
+            }
         }
         if (!__any_sync(SB_FULL, want))
             continue;
@@ -639,17 +652,24 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
             o.perAxis[3 * (size_t)outIndex + 2] = (votes >> 2) & 1u;
             in = __popc(votes) >= 2; // (float)insideCount / totalCount > 0.5 (:508)
         } else {
-            in = undecided ? ((votes >> 2) & 1u) != 0 : (votes & 1u) != 0;
+            in = (undecided || o.thirdOnly) ? ((votes >> 2) & 1u) != 0 : (votes & 1u) != 0;
         }
-        o.inside[outIndex] = in ? 1 : 0;
+        if (!(deferred && undecided))
+            o.inside[outIndex] = in ? 1 : 0;
     }
     const uint32_t ex = __reduce_add_sync(SB_FULL, exact);
     const uint32_t um = __ballot_sync(SB_FULL, undecided);
+    unsigned int ubase = 0;
     if (lane == 0) {
         if (ex)
             atomicAdd(o.exactCount, (unsigned long long)ex);
         if (um)
-            atomicAdd(o.undecidedCount, (unsigned int)__popc(um));
+            ubase = atomicAdd(o.undecidedCount, (unsigned int)__popc(um));
+    }
+    if (deferred && um) {
+        ubase = __shfl_sync(SB_FULL, ubase, 0);
+        if (undecided)
+            o.undecidedList[ubase + __popc(um & lanemask_lt())] = local;
     }
     if (o.trace) { // dev instrumentation
         if (lane == 0 && ex)
@@ -684,7 +704,10 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     q.sortedTri = qm ? qm->sortedTri : nullptr;
     q.nT = qm ? qm->nT : 0;
     q.begin = a.begin;
-    q.count = a.end - a.begin;
+    q.count = a.list ? a.listCount : a.end - a.begin;
+    q.list = a.list;
+    if (q.count == 0)
+        return cudaSuccess;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;
@@ -694,6 +717,7 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     T.bigN0 = target.gridBigN[0];
     T.bigN1 = target.gridBigN[1];
     T.bigN2 = target.gridBigN[2];
+    T.naxes = target.gridAxes;
     T.vtx = target.vtx;
     T.tri = target.tri;
     T.normal = target.normal;
@@ -705,6 +729,8 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     o.bigNeeded = bigNeeded;
     o.exactCount = exactCount;
     o.undecidedCount = undecidedCount;
+    o.undecidedList = a.undecidedList;
+    o.thirdOnly = a.thirdAxisOnly ? 1 : 0;
     o.trace = trace;
     o.poolLimit = poolLimit ? (poolLimit < (uint32_t)POOL ? poolLimit : (uint32_t)POOL) : (uint32_t)POOL;
     if (trace)

@@ -122,6 +122,20 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
         }
 }
 
+// Count pass on its own (the leaf kernel normally does it): used when a mesh built with
+// two grids needs the third one after all.
+__global__ void __launch_bounds__(256) grid_count_kernel(const uint4 *__restrict__ qbox, uint32_t nT,
+    const GridParams *__restrict__ gp, uint32_t *__restrict__ E, uint32_t *__restrict__ bigCount, int naxes)
+{
+    __shared__ GridParams g;
+    if (threadIdx.x < sizeof(GridParams) / 4)
+        reinterpret_cast<uint32_t *>(&g)[threadIdx.x] = reinterpret_cast<const uint32_t *>(gp)[threadIdx.x];
+    __syncthreads();
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j < nT)
+        grid_count_tri(__ldg(qbox + j), g, E, bigCount, naxes);
+}
+
 // In-place inclusive scan of a u32 array (single pass, chained tiles with
 // decoupled look-back -- same protocol as the radix sort's digit offsets).
 constexpr int SCAN_THREADS = 256;
@@ -176,15 +190,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
             status[0] = (unsigned long long)total | SCAN_PREFIX;
         } else {
             status[tile] = (unsigned long long)total | SCAN_AGG;
+            // LOOK predecessors per round trip (the tiles are resident together, the walk can be long)
+            constexpr int LOOK = 8;
             int t = (int)tile - 1;
-            while (true) {
-                unsigned long long s = status[t];
-                if (s & SCAN_PREFIX) {
-                    excl += s & SCAN_MASK;
-                    break;
+            bool done = false;
+            while (!done) {
+                unsigned long long s[LOOK];
+#pragma unroll
+                for (int k = 0; k < LOOK; ++k) {
+                    s[k] = SCAN_PREFIX + 0ull; // before the first tile: an empty prefix
+                    if (t - k >= 0)
+                        s[k] = status[t - k];
                 }
-                if (s & SCAN_AGG) {
-                    excl += s & SCAN_MASK;
+#pragma unroll
+                for (int k = 0; k < LOOK; ++k) {
+                    if (done || s[k] == 0)
+                        break; // not published yet: look again from here
+                    excl += s[k] & SCAN_MASK;
+                    done = (s[k] & SCAN_PREFIX) != 0;
                     --t;
                 }
             }
@@ -227,6 +250,19 @@ cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, 
     return cudaGetLastError();
 }
 
+cudaError_t sbk_grid_recount(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    const uint32_t maxCells = 3u << m.gridCellBits;
+    cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)maxCells + 2), s);
+    cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
+    cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * sbk_grid_scan_status_words(maxCells), s);
+    grid_count_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.qbox, m.nT, m.gridParams, m.gridE, m.gridBigCount, m.gridAxes);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
 // Phase 1 (after the leaf kernel): inclusive scan of the per-cell counts.  Afterwards
 // E[c + 1] = end of cell c and gridBigCount[6] = total number of references.
 cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc)
@@ -250,7 +286,7 @@ cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
 {
     if (m.nT == 0)
         return cudaSuccess;
-    grid_fill_kernel<<<3 * ((m.nT + 255) / 256), 256, 0, s>>>(m.qbox, m.nT, m.gridParams, m.gridE, m.gridRefs,
+    grid_fill_kernel<<<m.gridAxes * ((m.nT + 255) / 256), 256, 0, s>>>(m.qbox, m.nT, m.gridParams, m.gridE, m.gridRefs,
         m.gridRefCap, m.gridBigRefs, m.gridBigCount, m.gridBigCap);
     lc.kernels += 1;
     return cudaGetLastError();

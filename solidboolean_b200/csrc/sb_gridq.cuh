@@ -91,13 +91,15 @@ __device__ __forceinline__ GridFootprint grid_footprint(const uint4 &q, const Gr
     return f;
 }
 
-// count pass for one triangle: +1 on every cell it covers on the three grids (E[c + 1]
-// = number of references of cell c), or on the axis's big-list counter
+// count pass for one triangle: +1 on every cell it covers on the first `naxes` grids
+// (E[c + 1] = number of references of cell c), or on the axis's big-list counter
 __device__ __forceinline__ void grid_count_tri(const uint4 &q, const GridParams &g, uint32_t *__restrict__ E,
-    uint32_t *__restrict__ bigCount)
+    uint32_t *__restrict__ bigCount, int naxes)
 {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
+        if (a >= naxes)
+            break;
         const GridFootprint f = grid_footprint(q, g, a);
         if ((f.cu1 - f.cu0 + 1) * (f.cv1 - f.cv0 + 1) > SB_GRID_MAX_CELLS_PER_TRI) {
             atomicAdd(&bigCount[a], 1u);

@@ -53,6 +53,7 @@ struct MeshDev {
     // ray grids
     unsigned long long *extentSum = nullptr; // 32 x 3 partial sums of triangle-box extents (2^-24 of the mesh extent)
     uint32_t gridCellBits = 0;          // at most 2^bits cells per axis (allocation bound)
+    int gridAxes = 2;                   // grids actually binned: axes 0..gridAxes-1 (the third one only once a vote needed it)
     GridParams *gridParams = nullptr;
     uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
     uint4 *gridRefs = nullptr;          // grid_ref_pack (sb_gridq.cuh): quantised box + triangle id
@@ -104,7 +105,14 @@ struct ClassifyArgs {
     const MeshDev *queryMesh = nullptr;
     uint32_t begin = 0, end = 0; // point range (explicit) or sorted-position range (faces)
     uint8_t *inside = nullptr;   // indexed by point index / original triangle id
-    uint8_t *perAxis = nullptr;  // optional, 3 per point
+    uint8_t *perAxis = nullptr;  // optional, 3 per point (needs all three grids of the target)
+    // target with two grids only: points whose two votes disagree are appended (as indices
+    // relative to `begin`) to undecidedList; a second launch with list / listCount /
+    // thirdAxisOnly set traces their third ray once the target's third grid exists
+    uint32_t *undecidedList = nullptr;
+    const uint32_t *list = nullptr;
+    uint32_t listCount = 0;
+    bool thirdAxisOnly = false;
 };
 // One launch classifies all points (sb_classify.cu).  Lazy vote when only `inside` is
 // wanted: axes 0 and 1 for every point, axis 2 where the two disagree
@@ -125,4 +133,6 @@ size_t sbk_radix_workspace_words(size_t n);
 size_t sbk_grid_scan_status_words(uint32_t maxCells);
 cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc);
 cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc);
+// counts again from the stored quantised boxes, for m.gridAxes axes (a mesh built with two grids gets its third)
+cudaError_t sbk_grid_recount(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc);
 cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc);

@@ -151,15 +151,25 @@ __global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(const KeyT *__rest
             else
                 lookback[tile * RADIX + tid] = sum | FLAG_AGG;
             if (tile != 0) {
+                // decoupled look-back, LOOK predecessors per round trip (all tiles of a sort are
+                // resident, so the walk back to the nearest published prefix can be long)
+                constexpr int LOOK = 8;
                 int t = (int)tile - 1;
-                while (true) {
-                    uint32_t v = lookback[t * RADIX + tid];
-                    if (v & FLAG_PREFIX) {
-                        excl += v & VALUE_MASK;
-                        break;
+                bool done = false;
+                while (!done) {
+                    uint32_t v[LOOK];
+#pragma unroll
+                    for (int k = 0; k < LOOK; ++k) {
+                        v[k] = FLAG_PREFIX + 0u; // before the first tile: an empty prefix
+                        if (t - k >= 0)
+                            v[k] = lookback[(t - k) * RADIX + tid];
                     }
-                    if (v & FLAG_AGG) {
-                        excl += v & VALUE_MASK;
+#pragma unroll
+                    for (int k = 0; k < LOOK; ++k) {
+                        if (done || v[k] == 0)
+                            break; // not published yet: look again from here
+                        excl += v[k] & VALUE_MASK;
+                        done = (v[k] & FLAG_PREFIX) != 0;
                         --t;
                     }
                 }

@@ -254,6 +254,18 @@ def test_explicit_points_vs_oracle(ctx, oracle):
         rays, _ = ctx.classify_stats()
         assert rays == 2 * len(pts) + int((op[:, 0] != op[:, 1]).sum())
         m.close()
+        # a fresh mesh has the ray grids of axes 0 and 1 only: the lazy vote lists the undecided
+        # points, the third grid is built on demand and a second launch traces their third ray
+        m2 = ctx.mesh(*mesh)
+        lazy2, _ = m2.classify(pts, per_axis=False)
+        assert np.array_equal(lazy2, oi)
+        rays2, cands2 = ctx.classify_stats()
+        assert rays2 == rays
+        # rebuilt meshes keep the third grid: same answer through the single-launch path
+        m2.build()
+        lazy3, _ = m2.classify(pts, per_axis=False)
+        assert np.array_equal(lazy3, oi) and ctx.classify_stats() == (rays2, cands2)
+        m2.close()
 
 
 @pytest.mark.parametrize("layers,pitch", [(24, 0.05), (90, 0.02)])
