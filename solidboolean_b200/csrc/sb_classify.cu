@@ -70,6 +70,11 @@ struct __align__(16) WarpStage {
     long long list[KSM][3]; // distinct keys of the long ray being evaluated
     uint8_t owner[POOL];    // entry -> slot * 32 + owner lane
     uint8_t hit[32];
+    // per-lane state that lives here rather than in registers (the FP64 evaluation needs
+    // them all; what does not fit is spilled to local memory, which misses L1 half of the
+    // time at this footprint): the points, and per slot the packed ray + its cell list range
+    double px[32], py[32], pz[32];
+    uint32_t ray[2][5][32]; // [slot][qx, qy, qz, list begin, list end][lane]
 };
 static_assert(KS * 24 <= POOL * 4, "big_ray keeps its keys in the pool");
 
@@ -395,8 +400,9 @@ __device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32 ? 0xff
 // of the lanes that `want` them.  Returns bit s set when the ray along axis0 + s
 // crosses an odd number of distinct surface points (:89).
 __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Target &T, const Out &o, WarpStage &W, int axis0, int nax,
-    bool want, const d3 &p, int lane, uint32_t &exact)
+    bool want, int lane, uint32_t &exact)
 {
+    const d3 p = {W.px[lane], W.py[lane], W.pz[lane]};
     // ---- count ----
     // per slot s (ray along axis0 + s): packed ray, cell list range, big list
     uint32_t qx0 = 0, qy0 = 0, qz0 = 0, a0 = 0, b0 = 0, nBig0 = 0;
@@ -429,6 +435,8 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
     const uint4 *big0 = T.bigRefs + (size_t)axis0 * T.bigCap, *big1 = T.bigRefs + (size_t)(axis0 + 1) * T.bigCap;
     const uint32_t n0 = scan_count(T.refs + a0, qx0, qy0, qz0, b0 - a0, big0, nBig0);
     const uint32_t n1 = scan_count(T.refs + a1, qx1, qy1, qz1, b1 - a1, big1, nBig1);
+    W.ray[0][0][lane] = qx0; W.ray[0][1][lane] = qy0; W.ray[0][2][lane] = qz0; W.ray[0][3][lane] = a0; W.ray[0][4][lane] = b0;
+    W.ray[1][0][lane] = qx1; W.ray[1][1][lane] = qy1; W.ray[1][2][lane] = qz1; W.ray[1][3][lane] = a1; W.ray[1][4][lane] = b1;
     legacy0 = legacy0 || n0 > o.poolLimit;
     legacy1 = legacy1 || n1 > o.poolLimit;
     const uint32_t ns0 = legacy0 ? 0u : n0, ns1 = legacy1 ? 0u : n1;
@@ -453,10 +461,17 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
         const uint32_t w1 = (ns1 && off1 >= Wb && off1 + ns1 > Wb + POOL) ? off1 : total;
         const uint32_t We = __reduce_min_sync(SB_FULL, min(w0, w1));
         // ---- fill ---- (the rays with matches walk their, now cached, lists again)
-        if (ns0 && off0 >= Wb && off0 < We)
-            scan_fill(T.refs + a0, qx0, qy0, qz0, b0 - a0, big0, nBig0, W.tri, W.owner, off0 - Wb, (uint8_t)lane);
-        if (ns1 && off1 >= Wb && off1 < We)
-            scan_fill(T.refs + a1, qx1, qy1, qz1, b1 - a1, big1, nBig1, W.tri, W.owner, off1 - Wb, (uint8_t)(32 + lane));
+        if (ns0 && off0 >= Wb && off0 < We) {
+            const uint32_t fa = W.ray[0][3][lane], fb = W.ray[0][4][lane];
+            scan_fill(T.refs + fa, W.ray[0][0][lane], W.ray[0][1][lane], W.ray[0][2][lane], fb - fa,
+                T.bigRefs + (size_t)axis0 * T.bigCap, big_list_length(T, axis0), W.tri, W.owner, off0 - Wb, (uint8_t)lane);
+        }
+        if (ns1 && off1 >= Wb && off1 < We) {
+            const uint32_t fa = W.ray[1][3][lane], fb = W.ray[1][4][lane];
+            scan_fill(T.refs + fa, W.ray[1][0][lane], W.ray[1][1][lane], W.ray[1][2][lane], fb - fa,
+                T.bigRefs + (size_t)(axis0 + 1) * T.bigCap, big_list_length(T, axis0 + 1), W.tri, W.owner, off1 - Wb,
+                (uint8_t)(32 + lane));
+        }
         __syncwarp();
         // ---- eval ----
         for (uint32_t S = Wb; S < We;) {
@@ -472,7 +487,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
                 const int sl = m0 ? 0 : 1;
                 const int b = __ffs(m0 ? m0 : m1) - 1;
                 const uint32_t nl = __shfl_sync(SB_FULL, sl ? ns1 : ns0, b);
-                const d3 pb = {__shfl_sync(SB_FULL, p.x, b), __shfl_sync(SB_FULL, p.y, b), __shfl_sync(SB_FULL, p.z, b)};
+                const d3 pb = {W.px[b], W.py[b], W.pz[b]};
                 long long *gl = nullptr;
                 bool ok = true;
                 if (nl > KSM) {
@@ -539,7 +554,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
             const uint32_t ridPrev = __shfl_up_sync(SB_FULL, rid, 1);
             const uint32_t heads = __ballot_sync(SB_FULL, have && (lane == 0 || rid != ridPrev));
             const int segStart = 31 - __clz(heads & lelane);
-            const d3 pp = {__shfl_sync(SB_FULL, p.x, ow), __shfl_sync(SB_FULL, p.y, ow), __shfl_sync(SB_FULL, p.z, ow)};
+            const d3 pp = {W.px[ow], W.py[ow], W.pz[ow]};
             bool h = false;
             long long k0 = 0, k1 = 0, k2 = 0;
             if (have) {
@@ -579,8 +594,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
             const int b = __ffs(bigMask) - 1;
             bigMask &= bigMask - 1;
             const uint32_t nb = __shfl_sync(SB_FULL, s ? n1 : n0, b); // 0 for a ray of several cells: not counted yet
-            const uint2 d = big_ray(g, T, o, reinterpret_cast<long long *>(W.tri), axis0 + s, __shfl_sync(SB_FULL, p.x, b),
-                __shfl_sync(SB_FULL, p.y, b), __shfl_sync(SB_FULL, p.z, b), nb, lane);
+            const uint2 d = big_ray(g, T, o, reinterpret_cast<long long *>(W.tri), axis0 + s, W.px[b], W.py[b], W.pz[b], nb, lane);
             if (lane == b)
                 parity |= (d.x & 1u) << s;
             if (lane == 0)
@@ -625,6 +639,10 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
         }
     }
 
+    W.px[lane] = p.x;
+    W.py[lane] = p.y;
+    W.pz[lane] = p.z;
+    __syncwarp();
     uint32_t votes = 0, exact = 0;
     bool undecided = false, deferred = false;
     // second launch (thirdOnly): votes 0 and 1 of the listed points disagreed, so only round 1
@@ -642,7 +660,7 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
         }
         if (!__any_sync(SB_FULL, want))
             continue;
-        votes |= trace_round(g, T, o, W, 2 * round, 2 - round, want, p, lane, exact) << (2 * round);
+        votes |= trace_round(g, T, o, W, 2 * round, 2 - round, want, lane, exact) << (2 * round);
     }
     if (active) {
         bool in;
