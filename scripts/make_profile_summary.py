@@ -22,13 +22,12 @@ keys = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
         ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
         ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 %"),
         ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
-        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_sb")]
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_sb"),
+        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 pipe %")]
 lines = []
 cls_bytes = 0.0
-ray_rows = [r for r in rows[2:] if "ray_" in col(r, "Kernel Name")]
-while ray_rows and "ray_scan" not in col(ray_rows[0], "Kernel Name"):
-    ray_rows.pop(0)          # the capture window may start in the middle of a step
-ray_rows = ray_rows[:6]      # one step = 2 directions x (scan, hit, finish)
+ray_rows = [r for r in rows[2:] if "classify_kernel" in col(r, "Kernel Name")]
+ray_rows = ray_rows[:2]      # one step = 2 directions, one launch each
 for r in ray_rows:
     cls_bytes += tobytes(col(r, "dram__bytes_read.sum"), units[hdr.index("dram__bytes_read.sum")])
     cls_bytes += tobytes(col(r, "dram__bytes_write.sum"), units[hdr.index("dram__bytes_write.sum")])
@@ -46,7 +45,7 @@ for r in rows[2:]:
     lines.append("| %s | %s |" % (name[:48], " | ".join(vals)))
 # the capture holds ONE serial step: 2 x (scan, hit, finish) [+ lazy second passes]
 json.dump({"config": "c3", "classify_dram_bytes_per_step": int(cls_bytes),
-           "how": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the ray_scan/ray_hit/ray_finish launches of one step, "
+           "how": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the two classify_kernel launches of one step, "
                   "ncu --set full --clock-control none, scripts/stage_times.py c3 --serial (profiles/r01_ncu_summary.md)"},
           open(out_json, "w"), indent=1)
 # launch list
@@ -65,16 +64,16 @@ with open(out_md, "w") as f:
             "compare SHARES, never absolutes; bench values are never taken from these runs.\n\n")
     f.write("## Launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (raw list: profiles/r01_launches_bench.csv;\n"
-            "3 resident steps + 5 host-buffer steps; torch kernels = L2 flush / result copies)\n\n")
+            "3 resident steps + 5 host-buffer steps + fp64 probe; torch kernels = L2 flush / result copies)\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write("| %s | %d | %.1f | %.1f%% |\n" % (k, len(v), sum(v), 100 * sum(v) / tot))
     f.write("| **all** | %d | %.1f | 100%% |\n\n" % (sum(len(v) for v in agg.values()), tot))
     f.write("## `ncu --set full --clock-control none --import-source on`, one serial step (`scripts/stage_times.py c3 2 --serial`, 2nd iteration)\n")
-    f.write("order = execution order: build(A) kernels, build(B) kernels, broad phase, hit-key sort, classify A-in-B (scan/hit/finish), classify B-in-A\n\n")
+    f.write("order = execution order: build(A) kernels, build(B) kernels, broad phase, predicate, hit-key sort, classify A-in-B, classify B-in-A\n\n")
     f.write("| kernel | " + " | ".join(n for _, n in keys) + " |\n|---|" + "---:|" * len(keys) + "\n")
     f.write("\n".join(lines) + "\n\n")
-    f.write("Classification kernels, DRAM bytes per step (sum over ray_* launches): **%.0f MB** vs %.0f MB algorithmic\n"
+    f.write("Classification kernel, DRAM bytes per step (two launches): **%.0f MB** vs %.0f MB algorithmic\n"
             "(SURVEY 8d: 25Q + 104 nT + 108 C with Q = 2,359,296, C = 7.21 M exact candidates under the lazy vote) -> profiles/traffic.json\n"
             % (cls_bytes / 1e6, (25 * 2359296 + 104 * 2359296 + 108 * 7.21e6) / 1e6))
 print(open(out_md).read()[:3000])

@@ -292,6 +292,40 @@ def test_many_layers_hit_list_overflow_path(ctx, oracle, layers, pitch):
     m.close()
 
 
+def test_rays_on_cell_borders(ctx, oracle):
+    """Points whose DBL_EPSILON-wide ray box straddles a border of the target's ray-grid cells
+    (the box then spans two cells): the general warp path, 'first cell only' rule included."""
+    mesh = meshgen.torus(96, 48, center=(0.013, 0.007, 0.011))
+    m = ctx.mesh(*mesh)
+    gi = m.grid_info()
+    lo, hi = mesh[0].min(0), mesh[0].max(0)
+    ext = hi - lo
+    scl = 32767.999 / ext                      # the device's quantiser (sb_gridq.cuh), same IEEE operations
+    rng = np.random.default_rng(77)
+    pts = []
+    straddling = 0
+    for d, cells in ((1, gi["nu"][0]), (2, gi["nv"][0]), (0, gi["nu"][1])):   # y and z borders (x rays), x borders (y rays)
+        shift = 15 - int(np.log2(cells))
+        for k in rng.integers(1, cells, 300):
+            xb = lo[d] + (int(k) << shift) / scl[d]
+            for j in range(-4, 5):
+                x = xb
+                for _ in range(abs(j)):
+                    x = np.nextafter(x, np.inf if j > 0 else -np.inf)
+                p = rng.uniform(lo - 0.1, hi + 0.1)
+                p[d] = x
+                q0 = int(np.floor((x - lo[d]) * scl[d])); q1 = int(np.floor(((x + 2.220446049250313e-16) - lo[d]) * scl[d]))
+                straddling += (q0 >> shift) != (q1 >> shift)
+                pts.append(p)
+    pts = np.array(pts)
+    assert straddling > 50
+    ins, per = m.classify(pts)
+    oi, op, ncand = oracle.classify(mesh, pts)
+    assert np.array_equal(per, op) and np.array_equal(ins, oi)
+    assert ctx.classify_stats()[1] == ncand
+    m.close()
+
+
 def test_general_ray_path_forced(oracle, monkeypatch):
     """SB_CLASSIFY_POOL_LIMIT=2 sends every ray with more than two quantised matches through
     the reference-by-reference warp path (normally only rays spanning several cells or
