@@ -59,6 +59,10 @@ int sb_context_device(const sb_context *ctx);
  * the AxisAlignedBoudingBoxTree build (:74-75, axisalignedboundingboxtree.cpp:
  * 27-141), the latter as a Morton-code LBVH over clusters of triangles. */
 
+/* A mesh holds at most 2^SB_MAX_TRIANGLE_BITS - 1 triangles (the ray-grid references keep
+ * the triangle id in 25 bits) and 2^31 - 1 vertices; larger inputs fail with SB_ERR_INVALID. */
+#define SB_MAX_TRIANGLE_BITS 25
+
 /* Host buffers in, copy + build enqueued; returns after the build completed. */
 int sb_mesh_create(sb_context *ctx, const double *xyz, size_t nV,
                    const uint32_t *tri, size_t nT, sb_mesh **out);
@@ -103,7 +107,7 @@ int sb_mesh_bvh_leaves(const sb_mesh *mesh, void *out_records /* padded nT * 32 
 typedef struct sb_grid_info {
     uint32_t nu[3], nv[3];
     uint32_t total_cells;
-    uint32_t total_refs;    /* 16-byte references over the three grids */
+    uint32_t total_refs;    /* 8-byte references over the grids built so far (the third on demand) */
     uint32_t big[3];        /* triangles kept on the per-axis "big" list */
     float mean_extent[3];   /* mean triangle-box extent per world axis */
 } sb_grid_info;

@@ -278,7 +278,7 @@ int alloc_async(sb_context *c, T **p, size_t count, std::vector<void *> *owned)
 
 int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
 {
-    if (nV >= (1ull << 31) || nT >= (1ull << 30))
+    if (nV >= (1ull << 31) || nT >= (1ull << SB_MAX_TRIANGLE_BITS))
         return fail(SB_ERR_INVALID, "mesh too large: %zu vertices, %zu triangles", nV, nT);
     sb_mesh *m = new (std::nothrow) sb_mesh;
     if (!m)
@@ -607,15 +607,16 @@ static int grid_size_and_fill(sb_mesh *m)
     uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
     for (int k = 0; k < 3; ++k)
         m->d.gridBigN[k] = h[1 + k];
-    // + 8: the classifier reads whole groups of references
-    size_t bytes = 16 * (std::max<size_t>(nRefs, 1) + 3 * (size_t)std::max<uint32_t>(bigMax, 1) + 8);
+    // [8-byte references: nRefs + 8 (the classifier reads whole groups)][16-byte big lists: 3 x bigMax]
+    const size_t refBytes = align256(8 * (std::max<size_t>(nRefs, 1) + 8));
+    size_t bytes = refBytes + 16 * 3 * (size_t)std::max<uint32_t>(bigMax, 1);
     if (m->gridArena)
         cudaFreeAsync(m->gridArena, st);
     SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, st));
     m->gridArenaBytes = bytes;
-    m->d.gridRefs = static_cast<uint4 *>(m->gridArena);
+    m->d.gridRefs = static_cast<uint2 *>(m->gridArena);
     m->d.gridRefCap = (uint32_t)std::max<size_t>(nRefs, 1);
-    m->d.gridBigRefs = m->d.gridRefs + std::max<size_t>(nRefs, 1);
+    m->d.gridBigRefs = reinterpret_cast<uint4 *>(static_cast<char *>(m->gridArena) + refBytes);
     m->d.gridBigCap = std::max<uint32_t>(bigMax, 1);
     m->gridSized = true;
     StageTimer t(c, SB_STAGE_BUILD, st);

@@ -74,7 +74,7 @@ struct __align__(16) WarpStage {
     // them all; what does not fit is spilled to local memory, which misses L1 half of the
     // time at this footprint): the points, and per slot the packed ray + its cell list range
     double px[32], py[32], pz[32];
-    uint32_t ray[2][5][32]; // [slot][qx, qy, qz, list begin, list end][lane]
+    uint32_t ray[2][4][32]; // [slot][packed ray x, y, list begin, list end][lane]
 };
 static_assert(KS * 24 <= POOL * 4, "big_ray keeps its keys in the pool");
 
@@ -109,8 +109,8 @@ __device__ __forceinline__ double comp(const BoxD &b, int d, bool hi)
 struct Target {
     const GridParams *gp;
     const uint32_t *E;
-    const uint4 *refs;
-    const uint4 *bigRefs;
+    const uint2 *refs;      // cell lists: 8-byte cell-relative references (sb_gridq.cuh)
+    const uint4 *bigRefs;   // per-axis big lists: 16-byte absolute references
     uint32_t bigCap;
     uint32_t bigN0, bigN1, bigN2;
     int naxes;                 // ray grids the target has (2: the third is built on demand, see ensure_grid3)
@@ -144,9 +144,9 @@ struct Out {
 };
 
 struct RaySetup {
-    RayQ rq;
-    uint32_t cu0, cu1, cv0, cv1;
-    bool any; // the ray box overlaps the mesh box
+    uint32_t aU, bU, aV, bV, aA; // the ray box, 15-bit quantised: [aU,bU] x [aV,bV] across, from aA along the axis
+    uint32_t cu0, cu1, cv0, cv1; // the cells it touches
+    bool any;                    // the ray box overlaps the mesh box
 };
 
 __device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, const d3 &p)
@@ -157,23 +157,23 @@ __device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, con
     const BoxD meshBox = {g.lo[0], g.lo[1], g.lo[2], g.hi[0], g.hi[1], g.hi[2]};
     rs.any = overlap_d(meshBox, myD); // otherwise no triangle box can overlap the ray box
     const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
-    const uint32_t aU = quant15(comp(myD, u, false), g.org[u], g.scl[u]);
-    const uint32_t bU = quant15(comp(myD, u, true), g.org[u], g.scl[u]);
-    const uint32_t aV = quant15(comp(myD, v, false), g.org[v], g.scl[v]);
-    const uint32_t bV = quant15(comp(myD, v, true), g.org[v], g.scl[v]);
-    const uint32_t aA = quant15(comp(myD, axis, false), g.org[axis], g.scl[axis]);
-    rs.rq = ray_pack(aU, bU, aV, bV, aA);
+    rs.aU = quant15(comp(myD, u, false), g.org[u], g.scl[u]);
+    rs.bU = quant15(comp(myD, u, true), g.org[u], g.scl[u]);
+    rs.aV = quant15(comp(myD, v, false), g.org[v], g.scl[v]);
+    rs.bV = quant15(comp(myD, v, true), g.org[v], g.scl[v]);
+    rs.aA = quant15(comp(myD, axis, false), g.org[axis], g.scl[axis]);
     const int su = g.shiftU[axis], sv = g.shiftV[axis];
-    rs.cu0 = aU >> su; rs.cu1 = bU >> su;
-    rs.cv0 = aV >> sv; rs.cv1 = bV >> sv;
+    rs.cu0 = rs.aU >> su; rs.cu1 = rs.bU >> su;
+    rs.cv0 = rs.aV >> sv; rs.cv1 = rs.bV >> sv;
     return rs;
 }
 
-// a triangle spanning several of the ray's cells is taken in the first of them only
-__device__ __forceinline__ bool first_cell(const GridParams &g, int axis, const RaySetup &rs, const uint4 &r, uint32_t cu,
-    uint32_t cv)
+// the ray as seen from cell (cu, cv): its box clipped to the cell, cell-relative
+__device__ __forceinline__ CellRay ray_in_cell(const GridParams &g, int axis, const RaySetup &rs, uint32_t cu, uint32_t cv)
 {
-    return max(grid_ref_lo_u(r) >> g.shiftU[axis], rs.cu0) == cu && max(grid_ref_lo_v(r) >> g.shiftV[axis], rs.cv0) == cv;
+    const int su = g.shiftU[axis], sv = g.shiftV[axis];
+    const uint32_t u0 = cu << su, u1 = u0 + (1u << su) - 1u, v0 = cv << sv, v1 = v0 + (1u << sv) - 1u;
+    return cell_ray_pack(max(rs.aU, u0), min(rs.bU, u1), max(rs.aV, v0), min(rs.bV, v1), rs.aA, cu, cv, su, sv);
 }
 
 __device__ __forceinline__ uint32_t big_list_length(const Target &T, int axis)
@@ -265,23 +265,36 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
     if (!rs.any)
         return make_uint2(0, 0);
     const uint32_t cbase = g.cellBase[axis], nu = g.nu[axis];
-    const bool multi = rs.cu0 != rs.cu1 || rs.cv0 != rs.cv1;
     const uint4 *bigList = T.bigRefs + (size_t)axis * T.bigCap;
     const uint32_t nBig = big_list_length(T, axis);
-    // visit(source, i0, i1, cellRule, cu, cv) for each reference range of the ray
+    const RayQ rqAbs = ray_pack(rs.aU, rs.bU, rs.aV, rs.bV, rs.aA);
+    // visit(probe, count) for each reference range of the ray; probe(i, id) = does reference i
+    // of the range match (a triangle spanning several of the ray's cells is taken in the
+    // first of them only: not if it also covers the previous cell of the ray's range)
     auto ranges = [&](auto &&visit) {
         for (uint32_t cv = rs.cv0; cv <= rs.cv1; ++cv)
             for (uint32_t cu = rs.cu0; cu <= rs.cu1; ++cu) {
                 const uint32_t cell = cbase + cv * nu + cu;
-                visit(T.refs, __ldg(T.E + cell + 1), __ldg(T.E + cell + 2), multi, cu, cv);
+                const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2);
+                const CellRay cq = ray_in_cell(g, axis, rs, cu, cv);
+                const bool firstU = cu == rs.cu0, firstV = cv == rs.cv0;
+                visit([&](uint32_t i, uint32_t &id) {
+                    const uint2 r = __ldg(T.refs + i0 + i);
+                    id = cell_ref_id(r);
+                    return cell_ref_match(cq, r) && (firstU || !cell_ref_ext_u(r)) && (firstV || !cell_ref_ext_v(r));
+                }, i1 - i0);
             }
-        visit(bigList, 0u, nBig, false, 0u, 0u);
+        visit([&](uint32_t i, uint32_t &id) {
+            const uint4 r = __ldg(bigList + i);
+            id = r.w;
+            return ray_ref_match(rqAbs, r);
+        }, nBig);
     };
     if (n == 0) { // count the matches (bounds the number of distinct keys)
-        ranges([&](const uint4 *src, uint32_t i0, uint32_t i1, bool cellRule, uint32_t cu, uint32_t cv) {
-            for (uint32_t i = i0 + lane; i < i1; i += 32) {
-                const uint4 r = __ldg(src + i);
-                n += (ray_ref_match(rs.rq, r) && (!cellRule || first_cell(g, axis, rs, r, cu, cv))) ? 1u : 0u;
+        ranges([&](auto &&probe, uint32_t len) {
+            for (uint32_t i = lane; i < len; i += 32) {
+                uint32_t id;
+                n += probe(i, id) ? 1u : 0u;
             }
         });
         n = __reduce_add_sync(SB_FULL, n);
@@ -299,20 +312,17 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
         gkeys = o.bigKeys + 3 * base;
     }
     uint32_t count = 0, exact = 0; // distinct hit keys so far (<= n)
-    ranges([&](const uint4 *src, uint32_t i0, uint32_t i1, bool cellRule, uint32_t cu, uint32_t cv) {
-        for (uint32_t i = i0; i < i1; i += 32) {
-            const uint32_t ii = i + lane;
+    ranges([&](auto &&probe, uint32_t len) {
+        for (uint32_t i = 0; i < len; i += 32) {
             bool h = false;
             long long k0 = 0, k1 = 0, k2 = 0;
-            if (ii < i1) {
-                const uint4 r = __ldg(src + ii);
-                if (ray_ref_match(rs.rq, r) && (!cellRule || first_cell(g, axis, rs, r, cu, cv))) {
-                    long long k[3] = {0, 0, 0};
-                    const uint32_t fl = eval_call(T, px, py, pz, axis, r.w, k);
-                    h = fl & 1u;
-                    exact += fl >> 1;
-                    k0 = k[0]; k1 = k[1]; k2 = k[2];
-                }
+            uint32_t id = 0;
+            if (i + lane < len && probe(i + lane, id)) {
+                long long k[3] = {0, 0, 0};
+                const uint32_t fl = eval_call(T, px, py, pz, axis, id, k);
+                h = fl & 1u;
+                exact += fl >> 1;
+                k0 = k[0]; k1 = k[1]; k2 = k[2];
             }
             uint32_t hm = __ballot_sync(SB_FULL, h);
             while (hm) {
@@ -343,47 +353,59 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
     return make_uint2(count, __reduce_add_sync(SB_FULL, exact));
 }
 
-// One ray's cell list (len references from src) + the per-axis big list, walked by its
-// lane: number of references whose quantised box the ray matches.
-__device__ __forceinline__ uint32_t scan_count(const uint4 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t qz, uint32_t len,
-    const uint4 *__restrict__ big, uint32_t nBig)
+// One ray's cell list (len 8-byte references from src), walked by its lane: number of
+// references whose quantised box the ray matches.
+__device__ __forceinline__ uint32_t scan_count(const uint2 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t len)
 {
-    const RayQ rq = {qx, qy, qz};
+    const CellRay rq = {qx, qy};
     uint32_t m = 0;
-    // independent 16-byte loads in flight; a list is followed by at least seven more
-    // readable references (padding), so the last group stays in bounds
+    // independent loads in flight; a list is followed by at least seven more readable
+    // references (padding), so the last group stays in bounds
     for (uint32_t i = 0; i < len; i += SB_CLS_UNROLL) {
-        uint4 q[SB_CLS_UNROLL];
+        uint2 q[SB_CLS_UNROLL];
 #pragma unroll
         for (int k = 0; k < SB_CLS_UNROLL; ++k)
             q[k] = __ldg(src + i + k);
 #pragma unroll
         for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            m += ((i + k < len) & ray_ref_match(rq, q[k])) ? 1u : 0u;
+            m += ((i + k < len) & cell_ref_match(rq, q[k])) ? 1u : 0u;
     }
+    return m;
+}
+
+// the same walk, storing the matching triangle ids (and their owner) from `pos` on
+__device__ __forceinline__ uint32_t scan_fill(const uint2 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t len, uint32_t *tri,
+    uint8_t *owner, uint32_t pos, uint8_t rid)
+{
+    const CellRay rq = {qx, qy};
+    for (uint32_t i = 0; i < len; i += SB_CLS_UNROLL) {
+        uint2 q[SB_CLS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SB_CLS_UNROLL; ++k)
+            q[k] = __ldg(src + i + k);
+#pragma unroll
+        for (int k = 0; k < SB_CLS_UNROLL; ++k)
+            if ((i + k < len) & cell_ref_match(rq, q[k])) {
+                tri[pos] = cell_ref_id(q[k]);
+                owner[pos] = rid;
+                ++pos;
+            }
+    }
+    return pos;
+}
+
+// the per-axis big list (triangles covering too many cells; usually empty): absolute references
+__device__ __forceinline__ uint32_t big_count(const uint4 *__restrict__ big, uint32_t nBig, const RayQ &rq)
+{
+    uint32_t m = 0;
     for (uint32_t i = 0; i < nBig; ++i)
         m += ray_ref_match(rq, __ldg(big + i)) ? 1u : 0u;
     return m;
 }
 
-// the same walk, storing the matching triangle ids (and their owner) from `pos` on
-__device__ __forceinline__ void scan_fill(const uint4 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t qz, uint32_t len,
-    const uint4 *__restrict__ big, uint32_t nBig, uint32_t *tri, uint8_t *owner, uint32_t pos, uint8_t rid)
+__device__ __forceinline__ void big_fill(const uint4 *__restrict__ big, uint32_t nBig, const RayQ &rq, uint32_t *tri,
+    uint8_t *owner, uint32_t pos, uint8_t rid)
 {
-    const RayQ rq = {qx, qy, qz};
-    for (uint32_t i = 0; i < len; i += SB_CLS_UNROLL) {
-        uint4 q[SB_CLS_UNROLL];
-#pragma unroll
-        for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            q[k] = __ldg(src + i + k);
-#pragma unroll
-        for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            if ((i + k < len) & ray_ref_match(rq, q[k])) {
-                tri[pos] = q[k].w;
-                owner[pos] = rid;
-                ++pos;
-            }
-    }
     for (uint32_t i = 0; i < nBig; ++i) {
         const uint4 q = __ldg(big + i);
         if (ray_ref_match(rq, q)) {
@@ -404,39 +426,44 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
 {
     const d3 p = {W.px[lane], W.py[lane], W.pz[lane]};
     // ---- count ----
-    // per slot s (ray along axis0 + s): packed ray, cell list range, big list
-    uint32_t qx0 = 0, qy0 = 0, qz0 = 0, a0 = 0, b0 = 0, nBig0 = 0;
-    uint32_t qx1 = 0, qy1 = 0, qz1 = 0, a1 = 0, b1 = 0, nBig1 = 0;
+    // per slot s (ray along axis0 + s): cell-relative packed ray, cell list range
+    uint32_t qx0 = 0, qy0 = 0, a0 = 0, b0 = 0, n0 = 0;
+    uint32_t qx1 = 0, qy1 = 0, a1 = 0, b1 = 0, n1 = 0;
     bool legacy0 = false, legacy1 = false;
     if (want) {
         const RaySetup r = ray_setup(g, axis0, p);
-        qx0 = r.rq.x; qy0 = r.rq.y; qz0 = r.rq.z;
         // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell;
         // the others go the general way (big_ray)
         legacy0 = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
         if (r.any && !legacy0) {
+            const CellRay cq = ray_in_cell(g, axis0, r, r.cu0, r.cv0);
+            qx0 = cq.x; qy0 = cq.y;
             const uint32_t cell = g.cellBase[axis0] + r.cv0 * g.nu[axis0] + r.cu0;
             a0 = __ldg(T.E + cell + 1);
             b0 = __ldg(T.E + cell + 2);
-            nBig0 = big_list_length(T, axis0);
+            const uint32_t nBig = big_list_length(T, axis0);
+            if (nBig)
+                n0 = big_count(T.bigRefs + (size_t)axis0 * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA));
         }
     }
     if (want && nax > 1) {
         const RaySetup r = ray_setup(g, axis0 + 1, p);
-        qx1 = r.rq.x; qy1 = r.rq.y; qz1 = r.rq.z;
         legacy1 = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
         if (r.any && !legacy1) {
+            const CellRay cq = ray_in_cell(g, axis0 + 1, r, r.cu0, r.cv0);
+            qx1 = cq.x; qy1 = cq.y;
             const uint32_t cell = g.cellBase[axis0 + 1] + r.cv0 * g.nu[axis0 + 1] + r.cu0;
             a1 = __ldg(T.E + cell + 1);
             b1 = __ldg(T.E + cell + 2);
-            nBig1 = big_list_length(T, axis0 + 1);
+            const uint32_t nBig = big_list_length(T, axis0 + 1);
+            if (nBig)
+                n1 = big_count(T.bigRefs + (size_t)(axis0 + 1) * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA));
         }
     }
-    const uint4 *big0 = T.bigRefs + (size_t)axis0 * T.bigCap, *big1 = T.bigRefs + (size_t)(axis0 + 1) * T.bigCap;
-    const uint32_t n0 = scan_count(T.refs + a0, qx0, qy0, qz0, b0 - a0, big0, nBig0);
-    const uint32_t n1 = scan_count(T.refs + a1, qx1, qy1, qz1, b1 - a1, big1, nBig1);
-    W.ray[0][0][lane] = qx0; W.ray[0][1][lane] = qy0; W.ray[0][2][lane] = qz0; W.ray[0][3][lane] = a0; W.ray[0][4][lane] = b0;
-    W.ray[1][0][lane] = qx1; W.ray[1][1][lane] = qy1; W.ray[1][2][lane] = qz1; W.ray[1][3][lane] = a1; W.ray[1][4][lane] = b1;
+    n0 += scan_count(T.refs + a0, qx0, qy0, b0 - a0);
+    n1 += scan_count(T.refs + a1, qx1, qy1, b1 - a1);
+    W.ray[0][0][lane] = qx0; W.ray[0][1][lane] = qy0; W.ray[0][2][lane] = a0; W.ray[0][3][lane] = b0;
+    W.ray[1][0][lane] = qx1; W.ray[1][1][lane] = qy1; W.ray[1][2][lane] = a1; W.ray[1][3][lane] = b1;
     legacy0 = legacy0 || n0 > o.poolLimit;
     legacy1 = legacy1 || n1 > o.poolLimit;
     const uint32_t ns0 = legacy0 ? 0u : n0, ns1 = legacy1 ? 0u : n1;
@@ -461,16 +488,19 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
         const uint32_t w1 = (ns1 && off1 >= Wb && off1 + ns1 > Wb + POOL) ? off1 : total;
         const uint32_t We = __reduce_min_sync(SB_FULL, min(w0, w1));
         // ---- fill ---- (the rays with matches walk their, now cached, lists again)
-        if (ns0 && off0 >= Wb && off0 < We) {
-            const uint32_t fa = W.ray[0][3][lane], fb = W.ray[0][4][lane];
-            scan_fill(T.refs + fa, W.ray[0][0][lane], W.ray[0][1][lane], W.ray[0][2][lane], fb - fa,
-                T.bigRefs + (size_t)axis0 * T.bigCap, big_list_length(T, axis0), W.tri, W.owner, off0 - Wb, (uint8_t)lane);
-        }
-        if (ns1 && off1 >= Wb && off1 < We) {
-            const uint32_t fa = W.ray[1][3][lane], fb = W.ray[1][4][lane];
-            scan_fill(T.refs + fa, W.ray[1][0][lane], W.ray[1][1][lane], W.ray[1][2][lane], fb - fa,
-                T.bigRefs + (size_t)(axis0 + 1) * T.bigCap, big_list_length(T, axis0 + 1), W.tri, W.owner, off1 - Wb,
-                (uint8_t)(32 + lane));
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t nss = s ? ns1 : ns0, offs = s ? off1 : off0;
+            if (nss && offs >= Wb && offs < We) {
+                const uint32_t fa = W.ray[s][2][lane], fb = W.ray[s][3][lane];
+                const uint8_t rid = (uint8_t)(32 * s + lane);
+                const uint32_t pos = scan_fill(T.refs + fa, W.ray[s][0][lane], W.ray[s][1][lane], fb - fa, W.tri, W.owner, offs - Wb, rid);
+                const uint32_t nBig = big_list_length(T, axis0 + s);
+                if (nBig) { // same order as counted: the cell list, then the big list
+                    const RaySetup r = ray_setup(g, axis0 + s, p);
+                    big_fill(T.bigRefs + (size_t)(axis0 + s) * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA), W.tri, W.owner, pos, rid);
+                }
+            }
         }
         __syncwarp();
         // ---- eval ----

@@ -6,7 +6,7 @@
 // perpendicular to the ray plus a half-line test along it.  For every mesh and
 // every axis we therefore bin the triangles' boxes into a 2-D grid over the two
 // perpendicular dimensions (CSR layout: per-cell ranges into one array of
-// 16-byte references).  A ray then reads ONE cell list instead of walking a tree.
+// 8-byte cell-relative references).  A ray then reads ONE cell list instead of walking a tree.
 //
 // Exactness: cells and the 15-bit coordinates inside a reference are produced by
 // one monotone quantiser per world axis (sb_gridq.cuh), applied to triangle
@@ -76,7 +76,7 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
 // order, so neighbouring threads update neighbouring cells.  The quantised boxes were
 // formed (and the cells counted) by the leaf kernel of sb_build.cu.
 __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict__ qbox, uint32_t nT,
-    const GridParams *__restrict__ gp, uint32_t *__restrict__ E, uint4 *__restrict__ refs, uint32_t refCap,
+    const GridParams *__restrict__ gp, uint32_t *__restrict__ E, uint2 *__restrict__ refs, uint32_t refCap,
     uint4 *__restrict__ bigRefs, uint32_t *__restrict__ bigCount, uint32_t bigCap)
 {
     __shared__ GridParams g;
@@ -91,14 +91,19 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
     const uint4 q = __ldg(qbox + j);
     const GridFootprint f = grid_footprint(q, g, a);
     const uint32_t cu0 = f.cu0, cu1 = f.cu1, cv0 = f.cv0, cv1 = f.cv1;
-    const uint4 rec = grid_ref_pack(f.qu & 0xffffu, f.qu >> 16, f.qv & 0xffffu, f.qv >> 16, f.qa & 0xffffu, f.qa >> 16, q.w);
+    const uint32_t qlu = f.qu & 0xffffu, qhu = f.qu >> 16, qlv = f.qv & 0xffffu, qhv = f.qv >> 16, qla = f.qa & 0xffffu, qha = f.qa >> 16;
     if ((cu1 - cu0 + 1) * (cv1 - cv0 + 1) > SB_GRID_MAX_CELLS_PER_TRI) {
         uint32_t slot = atomicAdd(&bigCount[3 + a], 1u);
         if (slot < bigCap)
-            bigRefs[(size_t)a * bigCap + slot] = rec;
+            bigRefs[(size_t)a * bigCap + slot] = grid_ref_pack(qlu, qhu, qlv, qhv, qla, qha, q.w);
         return;
     }
     const uint32_t base = g.cellBase[a], nu = g.nu[a];
+    const int su = g.shiftU[a], sv = g.shiftV[a];
+    // the reference of this triangle in cell (cu, cv): its box clipped to the cell, cell-relative
+    auto ref_in = [&](uint32_t cu, uint32_t cv) {
+        return cell_ref_pack(qlu, qhu, qlv, qhv, qha, cu, cv, su, sv, cu > cu0, cv > cv0, q.w);
+    };
     if (cu1 - cu0 <= 1 && cv1 - cv0 <= 1) {
         // common case (footprint at most 2 x 2 cells): all atomics are issued before the
         // first dependent store, so their round trips overlap instead of adding up
@@ -108,17 +113,17 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
         if (du) p10 = atomicSub(&E[c00 + 2], 1u) - 1u;
         if (dv) p01 = atomicSub(&E[c00 + nu + 1], 1u) - 1u;
         if (du && dv) p11 = atomicSub(&E[c00 + nu + 2], 1u) - 1u;
-        if (p00 < refCap) refs[p00] = rec;
-        if (du && p10 < refCap) refs[p10] = rec;
-        if (dv && p01 < refCap) refs[p01] = rec;
-        if (du && dv && p11 < refCap) refs[p11] = rec;
+        if (p00 < refCap) refs[p00] = ref_in(cu0, cv0);
+        if (du && p10 < refCap) refs[p10] = ref_in(cu1, cv0);
+        if (dv && p01 < refCap) refs[p01] = ref_in(cu0, cv1);
+        if (du && dv && p11 < refCap) refs[p11] = ref_in(cu1, cv1);
         return;
     }
     for (uint32_t cv = cv0; cv <= cv1; ++cv)
         for (uint32_t cu = cu0; cu <= cu1; ++cu) {
             uint32_t pos = atomicSub(&E[base + cv * nu + cu + 1], 1u) - 1u; // fill each cell back to front
             if (pos < refCap)
-                refs[pos] = rec;
+                refs[pos] = ref_in(cu, cv);
         }
 }
 

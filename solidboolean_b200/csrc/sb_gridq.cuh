@@ -58,6 +58,69 @@ __device__ __forceinline__ bool ray_ref_match(const RayQ &q, const uint4 &r)
     return (((q.x - r.x) & (q.y - r.y) & (q.z - r.z)) & SB_Q_GUARD) == SB_Q_GUARD;
 }
 
+// ---- 8-byte cell-relative references ------------------------------------------------
+// Inside the list of ONE cell only the part of a triangle's box that lies in that cell
+// matters, so the reference stores it relative to the cell, 5 bits per bound (the 15-bit
+// coordinate minus the cell origin, shifted down to 32 steps per cell: still monotone, still
+// only over-accepting), the far depth bound in 12 bits, and the triangle id in the
+// remaining 25 bits:
+//   x: [lo_u:5 g][31-hi_u:5 g][lo_v:5 g][31-hi_v:5 g][extU][extV][id >> 19 : 6]
+//   y: [4095-hi_a:12 g][id & 0x7ffff : 19]
+// (g = guard bit, zero in a reference, set in a ray).  extU / extV: the triangle also
+// covers the cell before this one along u / v -- what the "first cell only" rule of rays
+// that span several cells needs.  Half the bytes of the absolute 16-byte form in the grid
+// fill and in every list walk; triangles on the per-axis big lists keep the 16-byte form.
+#define SB_CELLREF_ID_BITS 25
+#define SB_R_UV_GUARD 0x00820820u // bits 5, 11, 17, 23
+#define SB_R_D_GUARD 0x00001000u  // bit 12 of .y
+#define SB_R_ALL (SB_R_UV_GUARD | (SB_R_D_GUARD << 12))
+
+// position of a 15-bit coordinate inside its cell, in 1/32 (or finer cells: exact) steps
+__device__ __forceinline__ uint32_t cell_rel5(uint32_t q, uint32_t cell, int shift)
+{
+    const uint32_t r = q - (cell << shift);
+    return shift > 5 ? r >> (shift - 5) : r;
+}
+
+__device__ __forceinline__ uint2 cell_ref_pack(uint32_t qlu, uint32_t qhu, uint32_t qlv, uint32_t qhv, uint32_t qha,
+    uint32_t cu, uint32_t cv, int shiftU, int shiftV, bool extU, bool extV, uint32_t id)
+{
+    const uint32_t su = cu << shiftU, eu = su + (1u << shiftU) - 1u, sv = cv << shiftV, ev = sv + (1u << shiftV) - 1u;
+    const uint32_t lu = cell_rel5(max(qlu, su), cu, shiftU), hu = cell_rel5(min(qhu, eu), cu, shiftU);
+    const uint32_t lv = cell_rel5(max(qlv, sv), cv, shiftV), hv = cell_rel5(min(qhv, ev), cv, shiftV);
+    uint2 r;
+    r.x = lu | ((31u - hu) << 6) | (lv << 12) | ((31u - hv) << 18) | ((extU ? 1u : 0u) << 24) | ((extV ? 1u : 0u) << 25) |
+          ((id >> 19) << 26);
+    r.y = (4095u - (qha >> 3)) | ((id & 0x7ffffu) << 13);
+    return r;
+}
+
+__device__ __forceinline__ uint32_t cell_ref_id(const uint2 &r) { return ((r.x >> 26) << 19) | (r.y >> 13); }
+__device__ __forceinline__ bool cell_ref_ext_u(const uint2 &r) { return (r.x >> 24) & 1u; }
+__device__ __forceinline__ bool cell_ref_ext_v(const uint2 &r) { return (r.x >> 25) & 1u; }
+
+// a ray in cell (cu, cv): [aU,bU] x [aV,bV] across (15-bit, inside the cell), starting at aA along the axis
+struct CellRay {
+    uint32_t x, y;
+};
+
+__device__ __forceinline__ CellRay cell_ray_pack(uint32_t aU, uint32_t bU, uint32_t aV, uint32_t bV, uint32_t aA, uint32_t cu,
+    uint32_t cv, int shiftU, int shiftV)
+{
+    CellRay q;
+    q.x = cell_rel5(bU, cu, shiftU) | ((31u - cell_rel5(aU, cu, shiftU)) << 6) | (cell_rel5(bV, cv, shiftV) << 12) |
+          ((31u - cell_rel5(aV, cv, shiftV)) << 18) | SB_R_UV_GUARD;
+    q.y = (4095u - (aA >> 3)) | SB_R_D_GUARD;
+    return q;
+}
+
+// lo_u <= bU && hi_u >= aU && lo_v <= bV && hi_v >= aV && hi_a >= aA: no field of (ray - ref)
+// borrows from its neighbour, and a guard bit survives exactly where ref <= ray
+__device__ __forceinline__ bool cell_ref_match(const CellRay &q, const uint2 &r)
+{
+    return (((q.x - r.x) & SB_R_UV_GUARD) | (((q.y - r.y) & SB_R_D_GUARD) << 12)) == SB_R_ALL;
+}
+
 // ---- binning (shared by the leaf kernel of sb_build.cu, which counts, and sb_grid.cu, which fills) ----
 #define SB_GRID_MAX_CELLS_PER_TRI 1024u // larger footprints go to the per-axis "big" list
 

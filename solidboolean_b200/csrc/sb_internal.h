@@ -56,9 +56,9 @@ struct MeshDev {
     int gridAxes = 2;                   // grids actually binned: axes 0..gridAxes-1 (the third one only once a vote needed it)
     GridParams *gridParams = nullptr;
     uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
-    uint4 *gridRefs = nullptr;          // grid_ref_pack (sb_gridq.cuh): quantised box + triangle id
+    uint2 *gridRefs = nullptr;          // cell_ref_pack (sb_gridq.cuh): cell-relative quantised box + triangle id
     uint32_t gridRefCap = 0;            // entries allocated behind gridRefs
-    uint4 *gridBigRefs = nullptr;       // 3 * gridBigCap: triangles covering too many cells
+    uint4 *gridBigRefs = nullptr;       // 3 * gridBigCap: triangles covering too many cells (grid_ref_pack, absolute)
     uint32_t *gridBigCount = nullptr;   // [0..2] counts (count pass), [3..5] fill cursors, [6] total refs
     uint32_t gridBigCap = 0;
     uint32_t gridBigN[3] = {0, 0, 0};   // host copy of the big-list lengths
