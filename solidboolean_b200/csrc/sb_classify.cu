@@ -44,7 +44,7 @@ namespace {
 #define SB_CLS_MINB 6
 #endif
 #ifndef SB_CLS_UNROLL
-#define SB_CLS_UNROLL 4 // references loaded per scan step (<= 8: allocation padding)
+#define SB_CLS_UNROLL 8 // references loaded per scan step (<= 8: allocation padding)
 #endif
 #ifndef SB_CLS_NPREF
 #define SB_CLS_NPREF 0  // normals fetched before the exact box test
