@@ -64,13 +64,17 @@ with open(out_md, "w") as f:
             "compare SHARES, never absolutes; bench values are never taken from these runs.\n\n")
     f.write("## Launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (raw list: profiles/r01_launches_bench.csv;\n"
-            "3 resident steps + 5 host-buffer steps + fp64 probe; torch kernels = L2 flush / result copies)\n\n")
+            "3 resident steps + 5 host-buffer steps; fp64_peak_kernel = the FP64 issue-rate microbenchmark of the bench line; torch kernels = L2 flush / result copies)\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write("| %s | %d | %.1f | %.1f%% |\n" % (k, len(v), sum(v), 100 * sum(v) / tot))
     f.write("| **all** | %d | %.1f | 100%% |\n\n" % (sum(len(v) for v in agg.values()), tot))
-    f.write("## `ncu --set full --clock-control none --import-source on`, one serial step (`scripts/stage_times.py c3 2 --serial`, 2nd iteration)\n")
-    f.write("order = execution order: build(A) kernels, build(B) kernels, broad phase, predicate, hit-key sort, classify A-in-B, classify B-in-A\n\n")
+    f.write("## Per-kernel counters of one serial step (`scripts/stage_times.py c3 2 --serial`, 35 consecutive launches)\n")
+    f.write("`ncu --section SpeedOfLight,MemoryWorkloadAnalysis,ComputeWorkloadAnalysis,Occupancy,LaunchStats,WarpStateStats,SchedulerStats,InstructionStats`\n"
+            "`+ dram / L1-pipe / fp64 / local-memory metrics, --clock-control none`; execution order (the window may start inside a step):\n"
+            "build(A), build(B), broad phase, predicate, hit-key sort, classify A-in-B, classify B-in-A; torch kernels = the script's own result checks.\n"
+            "`L1 pipe %` = l1tex__data_pipe_lsu_wavefronts (the busiest unit of the classifier).  The source-level capture of the classifier\n"
+            "(`--set full --import-source on`) is summarised in profiles/r01_classify_lines.md.\n\n")
     f.write("| kernel | " + " | ".join(n for _, n in keys) + " |\n|---|" + "---:|" * len(keys) + "\n")
     f.write("\n".join(lines) + "\n\n")
     f.write("Classification kernel, DRAM bytes per step (two launches): **%.0f MB** vs %.0f MB algorithmic\n"
