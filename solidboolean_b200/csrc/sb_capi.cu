@@ -98,6 +98,8 @@ struct sb_context {
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
     int sortBeginBit = 0;            // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT)
     uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
+    size_t grid3EagerBelow = 65536;  // SB_GRID3_EAGER_BELOW: meshes with fewer triangles get their third ray grid right away
+                                     // (launch-bound sizes: binning it costs nothing, building it later costs host round trips)
 };
 
 struct sb_mesh {
@@ -284,6 +286,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     if (!m)
         return fail(SB_ERR_NOMEM, "out of host memory");
     m->ctx = ctx;
+    m->grid3Wanted = nT < ctx->grid3EagerBelow;
     MeshDev &d = m->d;
     d.nV = (uint32_t)nV;
     d.nT = (uint32_t)nT;
@@ -411,6 +414,8 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaEventRecord(c->t0, c->stream));
     if (const char *e = getenv("SB_SORT_BEGIN_BIT"))
         c->sortBeginBit = std::max(0, std::min(atoi(e), 24));
+    if (const char *e = getenv("SB_GRID3_EAGER_BELOW"))
+        c->grid3EagerBelow = (size_t)std::max(0ll, atoll(e));
     if (const char *e = getenv("SB_CLASSIFY_POOL_LIMIT"))
         c->classifyPoolLimit = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("SB_GRID_BETA")) {

@@ -235,7 +235,9 @@ def test_invalid_arguments(ctx):
     m.close()
 
 
-def test_explicit_points_vs_oracle(ctx, oracle):
+def test_explicit_points_vs_oracle(oracle, monkeypatch):
+    monkeypatch.setenv("SB_GRID3_EAGER_BELOW", "0")   # small meshes too start with two ray grids (see below)
+    ctx = sb.Context(0)
     rng = np.random.default_rng(5)
     for mesh in (meshgen.icosphere(4), meshgen.torus(64, 32, center=(0.013, 0.007, 0.011)),
                  meshgen.slab(16, 1.0, 0.3, tilt=0.2)):
@@ -266,6 +268,7 @@ def test_explicit_points_vs_oracle(ctx, oracle):
         lazy3, _ = m2.classify(pts, per_axis=False)
         assert np.array_equal(lazy3, oi) and ctx.classify_stats() == (rays2, cands2)
         m2.close()
+    ctx.close()
 
 
 @pytest.mark.parametrize("layers,pitch", [(24, 0.05), (90, 0.02)])
@@ -507,6 +510,35 @@ def test_config_c2_vs_oracle(ctx, oracle):
     ia, pa = ma.classify_faces_against(mb)
     oi, op, _ = oracle.classify(b, oracle.centroids(*a))
     assert np.array_equal(pa, op) and np.array_equal(ia, oi)
+    x.close(); ma.close(); mb.close()
+
+
+@pytest.mark.slow
+def test_config_c4_dense_pairs_properties(ctx, oracle):
+    """BASELINE config 4 proxy: near-coincident icospheres k=7, 327,680 x2 triangles,
+    2.26 M candidate pairs -- the predicate-heavy case.  Full candidate / hit / segment equality
+    with the oracle, sampled classification."""
+    import torch
+    a, b = meshgen.config_c4()
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    da = torch.zeros(len(a[1]), dtype=torch.uint8, device="cuda")
+    db = torch.zeros(len(b[1]), dtype=torch.uint8, device="cuda")
+    x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+    ab, code = x.candidates()
+    hab, seg = x.hits()
+    ref = oracle.candidate_pairs(a, b)
+    assert len(ref) > 2_000_000 and np.array_equal(ab, ref)
+    ret, cop, hit, oseg = oracle.predicate_pairs(a, b, ab)
+    assert np.array_equal(code, (ret | (cop << 1)).astype(np.uint8))
+    assert np.array_equal(hab, ab[hit.astype(bool)]) and seg.tobytes() == oseg[hit.astype(bool)].tobytes()
+    assert int(sum(x.path_counts())) == len(ab)      # every pair left the predicate through one of its five exits
+    ia, ib = da.cpu().numpy(), db.cpu().numpy()
+    rng = np.random.default_rng(14)
+    sa = rng.choice(len(a[1]), 20000, replace=False)
+    sb_ = rng.choice(len(b[1]), 20000, replace=False)
+    oa, _, _ = oracle.classify(b, oracle.centroids(*a)[sa])
+    ob, _, _ = oracle.classify(a, oracle.centroids(*b)[sb_])
+    assert np.array_equal(ia[sa], oa) and np.array_equal(ib[sb_], ob)
     x.close(); ma.close(); mb.close()
 
 
