@@ -1,5 +1,6 @@
-// The quantiser shared by the ray-grid build (sb_grid.cu) and the classifier
-// (sb_classify.cu), and the 16-byte grid reference built from it.
+// The quantiser shared by the ray-grid build (sb_grid.cu, leaf kernel of sb_build.cu) and
+// the classifier (sb_classify.cu), and the grid references built from it: the absolute
+// 16-byte form (per-axis big lists) and the 8-byte cell-relative form (cell lists).
 //
 // One monotone 15-bit quantiser per world axis, q(x) = clamp(floor((x - org) * scl),
 // 0, 32767), is applied to triangle bounds and to ray bounds alike.  Monotonicity
@@ -35,8 +36,6 @@ __device__ __forceinline__ uint4 grid_ref_pack(uint32_t qlu, uint32_t qhu, uint3
     return make_uint4(qlu | ((SB_Q_MAX - qhu) << 16), qlv | ((SB_Q_MAX - qhv) << 16), (SB_Q_MAX - qha) | (qla << 16), id);
 }
 
-__device__ __forceinline__ uint32_t grid_ref_lo_u(const uint4 &r) { return r.x & SB_Q_MAX; }
-__device__ __forceinline__ uint32_t grid_ref_lo_v(const uint4 &r) { return r.y & SB_Q_MAX; }
 
 // a ray: [aU,bU] x [aV,bV] across (almost always one point), starting at aA along the axis
 struct RayQ {
