@@ -50,7 +50,7 @@ namespace {
 #define SB_CLS_NPREF 0  // normals fetched before the exact box test
 #endif
 #ifndef SB_CLS_RBOX
-#define SB_CLS_RBOX 0   // ray box shortcut for finite points
+#define SB_CLS_RBOX 1   // ray box shortcut for finite points
 #endif
 constexpr int CT = SB_CLS_CT; // threads per CTA
 constexpr int CW = CT / 32;   // warps per CTA
@@ -275,7 +275,7 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
         for (uint32_t cv = rs.cv0; cv <= rs.cv1; ++cv)
             for (uint32_t cu = rs.cu0; cu <= rs.cu1; ++cu) {
                 const uint32_t cell = cbase + cv * nu + cu;
-                const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2);
+                const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2) & ~1u;
                 const CellRay cq = ray_in_cell(g, axis, rs, cu, cv);
                 const bool firstU = cu == rs.cu0, firstV = cv == rs.cv0;
                 visit([&](uint32_t i, uint32_t &id) {
@@ -353,43 +353,52 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
     return make_uint2(count, __reduce_add_sync(SB_FULL, exact));
 }
 
-// One ray's cell list (len 8-byte references from src), walked by its lane: number of
-// references whose quantised box the ray matches.
-__device__ __forceinline__ uint32_t scan_count(const uint2 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t len)
+// One ray's cell list, references [a, b) of refs (b even, sb_grid.cu), walked by its lane in
+// aligned 16-byte PAIRS: number of references whose quantised box the ray matches.
+__device__ __forceinline__ uint32_t scan_count(const uint2 *__restrict__ refs, uint32_t qx, uint32_t qy, uint32_t a, uint32_t b)
 {
     const CellRay rq = {qx, qy};
     uint32_t m = 0;
-    // independent loads in flight; a list is followed by at least seven more readable
+    // independent loads in flight; the lists are followed by at least eight more readable
     // references (padding), so the last group stays in bounds
-    for (uint32_t i = 0; i < len; i += SB_CLS_UNROLL) {
-        uint2 q[SB_CLS_UNROLL];
+    for (uint32_t i = a & ~1u; i < b; i += SB_CLS_UNROLL) {
+        uint4 q[SB_CLS_UNROLL / 2];
 #pragma unroll
-        for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            q[k] = __ldg(src + i + k);
+        for (int k = 0; k < SB_CLS_UNROLL / 2; ++k)
+            q[k] = __ldg(reinterpret_cast<const uint4 *>(refs + i) + k);
 #pragma unroll
-        for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            m += ((i + k < len) & cell_ref_match(rq, q[k])) ? 1u : 0u;
+        for (int k = 0; k < SB_CLS_UNROLL / 2; ++k) {
+            m += ((i + 2 * k >= a) & (i + 2 * k < b) & cell_ref_match(rq, make_uint2(q[k].x, q[k].y))) ? 1u : 0u;
+            m += ((i + 2 * k + 1 < b) & cell_ref_match(rq, make_uint2(q[k].z, q[k].w))) ? 1u : 0u;
+        }
     }
     return m;
 }
 
 // the same walk, storing the matching triangle ids (and their owner) from `pos` on
-__device__ __forceinline__ uint32_t scan_fill(const uint2 *__restrict__ src, uint32_t qx, uint32_t qy, uint32_t len, uint32_t *tri,
-    uint8_t *owner, uint32_t pos, uint8_t rid)
+__device__ __forceinline__ uint32_t scan_fill(const uint2 *__restrict__ refs, uint32_t qx, uint32_t qy, uint32_t a, uint32_t b,
+    uint32_t *tri, uint8_t *owner, uint32_t pos, uint8_t rid)
 {
     const CellRay rq = {qx, qy};
-    for (uint32_t i = 0; i < len; i += SB_CLS_UNROLL) {
-        uint2 q[SB_CLS_UNROLL];
+    for (uint32_t i = a & ~1u; i < b; i += SB_CLS_UNROLL) {
+        uint4 q[SB_CLS_UNROLL / 2];
 #pragma unroll
-        for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            q[k] = __ldg(src + i + k);
+        for (int k = 0; k < SB_CLS_UNROLL / 2; ++k)
+            q[k] = __ldg(reinterpret_cast<const uint4 *>(refs + i) + k);
 #pragma unroll
-        for (int k = 0; k < SB_CLS_UNROLL; ++k)
-            if ((i + k < len) & cell_ref_match(rq, q[k])) {
-                tri[pos] = cell_ref_id(q[k]);
+        for (int k = 0; k < SB_CLS_UNROLL / 2; ++k) {
+            const uint2 r0 = make_uint2(q[k].x, q[k].y), r1 = make_uint2(q[k].z, q[k].w);
+            if ((i + 2 * k >= a) & (i + 2 * k < b) & cell_ref_match(rq, r0)) {
+                tri[pos] = cell_ref_id(r0);
                 owner[pos] = rid;
                 ++pos;
             }
+            if ((i + 2 * k + 1 < b) & cell_ref_match(rq, r1)) {
+                tri[pos] = cell_ref_id(r1);
+                owner[pos] = rid;
+                ++pos;
+            }
+        }
     }
     return pos;
 }
@@ -440,7 +449,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
             qx0 = cq.x; qy0 = cq.y;
             const uint32_t cell = g.cellBase[axis0] + r.cv0 * g.nu[axis0] + r.cu0;
             a0 = __ldg(T.E + cell + 1);
-            b0 = __ldg(T.E + cell + 2);
+            b0 = __ldg(T.E + cell + 2) & ~1u; // the next cell's share may begin with an unused slot
             const uint32_t nBig = big_list_length(T, axis0);
             if (nBig)
                 n0 = big_count(T.bigRefs + (size_t)axis0 * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA));
@@ -454,14 +463,14 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
             qx1 = cq.x; qy1 = cq.y;
             const uint32_t cell = g.cellBase[axis0 + 1] + r.cv0 * g.nu[axis0 + 1] + r.cu0;
             a1 = __ldg(T.E + cell + 1);
-            b1 = __ldg(T.E + cell + 2);
+            b1 = __ldg(T.E + cell + 2) & ~1u;
             const uint32_t nBig = big_list_length(T, axis0 + 1);
             if (nBig)
                 n1 = big_count(T.bigRefs + (size_t)(axis0 + 1) * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA));
         }
     }
-    n0 += scan_count(T.refs + a0, qx0, qy0, b0 - a0);
-    n1 += scan_count(T.refs + a1, qx1, qy1, b1 - a1);
+    n0 += scan_count(T.refs, qx0, qy0, a0, b0);
+    n1 += scan_count(T.refs, qx1, qy1, a1, b1);
     W.ray[0][0][lane] = qx0; W.ray[0][1][lane] = qy0; W.ray[0][2][lane] = a0; W.ray[0][3][lane] = b0;
     W.ray[1][0][lane] = qx1; W.ray[1][1][lane] = qy1; W.ray[1][2][lane] = a1; W.ray[1][3][lane] = b1;
     legacy0 = legacy0 || n0 > o.poolLimit;
@@ -494,7 +503,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
             if (nss && offs >= Wb && offs < We) {
                 const uint32_t fa = W.ray[s][2][lane], fb = W.ray[s][3][lane];
                 const uint8_t rid = (uint8_t)(32 * s + lane);
-                const uint32_t pos = scan_fill(T.refs + fa, W.ray[s][0][lane], W.ray[s][1][lane], fb - fa, W.tri, W.owner, offs - Wb, rid);
+                const uint32_t pos = scan_fill(T.refs, W.ray[s][0][lane], W.ray[s][1][lane], fa, fb, W.tri, W.owner, offs - Wb, rid);
                 const uint32_t nBig = big_list_length(T, axis0 + s);
                 if (nBig) { // same order as counted: the cell list, then the big list
                     const RaySetup r = ray_setup(g, axis0 + s, p);

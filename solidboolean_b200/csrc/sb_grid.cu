@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
     uint32_t sum = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        v[i] = base + i < n ? data[base + i] : 0u;
+        // every cell's share is rounded up to an even number of references: the ends (and the
+        // 16-byte pairs the classifier loads) stay aligned; a list with an odd count starts
+        // one slot after its share does
+        v[i] = base + i < n ? ((data[base + i] + 1u) & ~1u) : 0u;
         sum += v[i];
         v[i] = sum; // inclusive within the thread
     }
@@ -285,8 +288,10 @@ cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, Lau
 }
 
 // Phase 2 (after the caller sized refs / bigRefs from the counts): every
-// E[c + 1] turns from the END of cell c into its START as the cell is filled
-// back to front; E[totalCells + 1] (written by the scan) closes the last cell.
+// E[c + 1] turns from the (even) END of cell c into its START as the cell is filled
+// back to front; E[totalCells + 1] (written by the scan) closes the last cell.  The
+// list of cell c is then [E[c + 1], E[c + 2] & ~1): the share of the next cell may begin
+// with an unused slot.
 cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
 {
     if (m.nT == 0)
