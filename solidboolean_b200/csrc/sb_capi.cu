@@ -113,6 +113,8 @@ struct sb_mesh {
     // consumers on the context stream wait for `ready`
     cudaStream_t stream = nullptr;
     cudaEvent_t ready = nullptr;     // everything built (incl. the ray grids)
+    cudaStream_t treeStream = nullptr; // the (latency-bound) LBVH kernel runs here, beside the grid scan / fill
+    cudaEvent_t leavesDone = nullptr;  // leaf kernel finished (orders treeStream behind the mesh stream)
     cudaEvent_t leafReady = nullptr; // sorted leaves / boxes / centroids (+ LBVH when wanted): all the
                                      // intersection needs, recorded before the grids are built
     uint32_t *radixWs = nullptr;     // in the arena
@@ -354,6 +356,8 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
     if (cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prioHigh) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&m->treeStream, cudaStreamNonBlocking, prioHigh) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->leavesDone, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->leafReady, cudaEventDisableTiming) != cudaSuccess) {
         cudaFreeAsync(m->arena, ctx->stream);
         delete m;
@@ -678,12 +682,22 @@ int sb_mesh_build(sb_mesh *m)
         SB_CUDA(sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc));
         SB_CUDA(sbk_build_leaves(st, m->d, c->lc)); // also counts the grid cells
         m->treeBuilt = false;
-        if (m->treeWanted) { // known traversal target: LBVH right away, before the grids
-            SB_CUDA(sbk_build_tree(st, m->d, c->lc));
+        if (m->treeWanted) {
+            // known traversal target: the LBVH right away, on its own stream -- one
+            // latency-bound kernel (an atomic rendezvous per level) next to the
+            // bandwidth-bound grid scan / fill of the same mesh
+            SB_CUDA(cudaEventRecord(m->leavesDone, st));
+            SB_CUDA(cudaStreamWaitEvent(m->treeStream, m->leavesDone, 0));
+            {
+                StageTimer tt(c, SB_STAGE_BUILD, m->treeStream);
+                SB_CUDA(sbk_build_tree(m->treeStream, m->d, c->lc));
+            }
             m->treeBuilt = true;
+            // the intersection can start here, while the ray grids are still being built
+            SB_CUDA(cudaEventRecord(m->leafReady, m->treeStream));
+        } else {
+            SB_CUDA(cudaEventRecord(m->leafReady, st));
         }
-        // the intersection can start here, while the ray grids are still being built
-        SB_CUDA(cudaEventRecord(m->leafReady, st));
         SB_CUDA(sbk_grid_scan(st, m->d, m->scanScratch, c->lc));
         if (m->d.nT && m->gridSized) {
             // Rebuild of the same (immutable) geometry: every step above is
@@ -697,6 +711,8 @@ int sb_mesh_build(sb_mesh *m)
         if (r)
             return r;
     }
+    if (m->treeBuilt && m->d.nT)
+        SB_CUDA(cudaStreamWaitEvent(st, m->leafReady, 0)); // `ready` covers the LBVH too
     SB_CUDA(cudaEventRecord(m->ready, st));
     m->built = true;
     return SB_OK;
@@ -761,6 +777,8 @@ void sb_mesh_destroy(sb_mesh *m)
         if (m->gridArena)
             cudaFreeAsync(m->gridArena, m->stream);
         cudaStreamDestroy(m->stream); // deferred by the runtime until the stream drains
+        if (m->treeStream)
+            cudaStreamDestroy(m->treeStream);
     } else {
         cudaFreeAsync(m->arena, m->ctx->stream);
     }
@@ -768,6 +786,8 @@ void sb_mesh_destroy(sb_mesh *m)
         cudaEventDestroy(m->ready);
     if (m->leafReady)
         cudaEventDestroy(m->leafReady);
+    if (m->leavesDone)
+        cudaEventDestroy(m->leavesDone);
     delete m;
 }
 
