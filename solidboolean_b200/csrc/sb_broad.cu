@@ -24,8 +24,8 @@ struct BroadShared {
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
     const Rec32 *__restrict__ leafA, const double2 *__restrict__ sboxA, uint32_t groupBegin, uint32_t groupEnd,
     const Rec32 *__restrict__ nodesB, const Rec32 *__restrict__ leafB, const double2 *__restrict__ sboxB,
-    const int *__restrict__ rootB, unsigned bitsB, unsigned long long *__restrict__ outKeys,
-    unsigned long long capacity, unsigned long long *__restrict__ outCount)
+    const int *__restrict__ rootB, const unsigned long long *__restrict__ boundsB, unsigned bitsB,
+    unsigned long long *__restrict__ outKeys, unsigned long long capacity, unsigned long long *__restrict__ outCount)
 {
     __shared__ BroadShared sh[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -38,6 +38,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
     const uint32_t j = group * 32 + lane;
     Rec32 me = load_rec(leafA + j);
     const BoxF myF = {me.lox, me.loy, me.loz, me.hix, me.hiy, me.hiz};
+    // groups whose box misses B's bounding box altogether (most of a mesh, usually) leave
+    // before they touch their exact boxes or B's tree
+    BoxF all = myF; // padding lanes hold an empty box and never match
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        BoxF o = shfl_xor_box(all, off);
+        merge_f(all, o);
+    }
+    {
+        const BoxD bb = {dkey_inv(__ldg(boundsB)), dkey_inv(__ldg(boundsB + 1)), dkey_inv(__ldg(boundsB + 2)),
+                         dkey_inv(__ldg(boundsB + 3)), dkey_inv(__ldg(boundsB + 4)), dkey_inv(__ldg(boundsB + 5))};
+        const BoxF bf = enclose(bb); // conservative: rounded outwards
+        if (!overlap_f(all, bf.lox, bf.loy, bf.loz, bf.hix, bf.hiy, bf.hiz))
+            return;
+    }
     const BoxD myD = load_boxd(sboxA + 3 * (size_t)j);
     const unsigned long long myA = (unsigned long long)(uint32_t)me.ref;
     sbtrav::BvhView bvh = {nodesB, leafB, __ldg(rootB)};
@@ -56,12 +71,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
 
     // surface-area measure of a query box (0 for an empty one); the pad keeps
     // flat boxes from measuring zero
-    BoxF all = myF; // padding lanes hold an empty box and never match
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        BoxF o = shfl_xor_box(all, off);
-        merge_f(all, o);
-    }
     const float pad = 0.015625f * fmaxf(fmaxf(all.hix - all.lox, all.hiy - all.loy), all.hiz - all.loz);
     auto measure = [pad](const BoxF &b) {
         float ex = b.hix - b.lox, ey = b.hiy - b.loy, ez = b.hiz - b.loz;
@@ -105,7 +114,7 @@ cudaError_t sbk_broad_phase(cudaStream_t s, const MeshDev &A, const MeshDev &B, 
     uint32_t groups = groupEnd - groupBegin;
     uint32_t blocks = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     broad_phase_kernel<<<blocks, WARPS_PER_CTA * 32, 0, s>>>(A.leaf, A.sbox, groupBegin, groupEnd, B.nodes, B.leaf, B.sbox,
-        B.root, bitsB, outKeys, capacity, outCount);
+        B.root, B.bounds, bitsB, outKeys, capacity, outCount);
     lc.kernels += 1;
     return cudaGetLastError();
 }
