@@ -96,7 +96,7 @@ struct sb_context {
     uint32_t *scanScratch = nullptr; // grid-build scan status words
     size_t scanScratchWords = 0;
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
-    int sortBeginBit = 0;            // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT)
+    int sortBeginBit = -1;           // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT); -1 = by mesh size
     uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
     size_t grid3EagerBelow = 65536;  // SB_GRID3_EAGER_BELOW: meshes with fewer triangles get their third ray grid right away
                                      // (launch-bound sizes: binning it costs nothing, building it later costs host round trips)
@@ -669,7 +669,18 @@ int sb_mesh_build(sb_mesh *m)
     sb_context *c = m->ctx;
     DeviceGuard g(c->device);
     cudaStream_t st = m->stream;
-    m->d.sortBeginBit = c->sortBeginBit;
+    if (c->sortBeginBit >= 0) {
+        m->d.sortBeginBit = c->sortBeginBit;
+    } else {
+        // The order only has to be spatially coherent: 8 or more Morton cells per triangle are
+        // plenty (ties keep their input order), so a 1M-triangle mesh sorts 24 of the 30 bits
+        // -- three 8-bit passes instead of four -- and a 5K-triangle mesh two.
+        int want = 3;
+        while (want < 30 && ((size_t)1 << (want - 3)) < m->d.nT)
+            ++want;
+        const int passes = std::min(4, (want + 7) / 8);
+        m->d.sortBeginBit = std::max(0, 30 - 8 * passes);
+    }
     if ((m->d.gridAxes == 3) != m->grid3Wanted)
         m->gridSized = false; // the reference list was sized for another number of grids
     m->d.gridAxes = m->grid3Wanted ? 3 : 2;
