@@ -295,6 +295,24 @@ def test_many_layers_hit_list_overflow_path(ctx, oracle, layers, pitch):
     m.close()
 
 
+def test_extreme_query_points(ctx, oracle):
+    """Non-finite and huge query coordinates (NaN, +-inf, +-DBL_MAX, 1e300, denormals, -0.0): the
+    ray-box shortcut's general branch and the quantiser's clamps against the reference's arithmetic."""
+    mesh = meshgen.icosphere(3)
+    m = ctx.mesh(*mesh)
+    big = np.finfo(np.float64).max
+    specials = [np.nan, np.inf, -np.inf, big, -big, 1e300, -1e300, 5e-324, -5e-324, -0.0, 0.0, 0.5, -0.5, 2.0]
+    pts = np.array([(x, y, z) for x in specials for y in specials for z in (0.0, 0.25, np.nan, -np.inf, big)], np.float64)
+    with np.errstate(all="ignore"):
+        oi, op, ncand = oracle.classify(mesh, pts)
+    ins, per = m.classify(pts)
+    assert np.array_equal(per, op) and np.array_equal(ins, oi)
+    assert ctx.classify_stats()[1] == ncand
+    lazy, _ = m.classify(pts, per_axis=False)
+    assert np.array_equal(lazy, oi)
+    m.close()
+
+
 def test_rays_on_cell_borders(ctx, oracle):
     """Points whose DBL_EPSILON-wide ray box straddles a border of the target's ray-grid cells
     (the box then spans two cells): the general warp path, 'first cell only' rule included."""
