@@ -365,10 +365,12 @@ class Isect:
         _check(self.lib.sb_isect_face_flags(self.h, _ptr(fa), _ptr(fb)))
         return fa, fb
 
-    def device_ptrs(self):
+    def device_ptrs(self, candidates=True):
+        """Device pointers of the results.  candidates=False leaves the candidate keys alone (asking
+        for them orders the full candidate list on the device, which is otherwise done lazily)."""
         ck, ha, hs, fa, fb = _vp(), _vp(), _vp(), _vp(), _vp()
         bits = C.c_uint(0)
-        _check(self.lib.sb_isect_device_ptrs(self.h, C.byref(ck), C.byref(bits), C.byref(ha), C.byref(hs),
-                                             C.byref(fa), C.byref(fb)))
+        _check(self.lib.sb_isect_device_ptrs(self.h, C.byref(ck) if candidates else None, C.byref(bits), C.byref(ha),
+                                             C.byref(hs), C.byref(fa), C.byref(fb)))
         return dict(cand_keys=ck.value or 0, bits_b=bits.value, hit_ab=ha.value or 0, hit_seg=hs.value or 0,
                     flags_a=fa.value or 0, flags_b=fb.value or 0)
