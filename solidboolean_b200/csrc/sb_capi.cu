@@ -98,6 +98,7 @@ struct sb_context {
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
     int sortBeginBit = -1;           // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT); -1 = by mesh size
     uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
+    bool useGraphs = true;           // SB_GRAPHS=0: rebuilds enqueue their kernels one by one
     size_t grid3EagerBelow = 65536;  // SB_GRID3_EAGER_BELOW: meshes with fewer triangles get their third ray grid right away
                                      // (launch-bound sizes: binning it costs nothing, building it later costs host round trips)
 };
@@ -123,6 +124,11 @@ struct sb_mesh {
     uint32_t *hErr = nullptr;        // pinned: index-validation flag read back with the counts
     bool gridSized = false;          // reference list already sized by an earlier build
     bool grid3Wanted = false;        // a vote (or a per-axis query) needed the third grid: builds include it from now on
+    // A REbuild (same immutable geometry, reference list already sized) is a fixed sequence of
+    // ~20 launches and memsets on two streams: captured once, replayed as one CUDA graph.
+    cudaGraphExec_t buildGraph = nullptr;
+    unsigned graphSig = 0;           // what the capture depended on: grids, LBVH wanted, sorted bits
+    uint64_t graphKernels = 0;       // kernels in the graph (launch accounting)
     bool treeBuilt = false;          // LBVH topology built (lazily, on first use as a traversal target)
     bool treeWanted = false;         // the mesh has been a traversal target: rebuilds include the LBVH
 };
@@ -418,6 +424,8 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaEventRecord(c->t0, c->stream));
     if (const char *e = getenv("SB_SORT_BEGIN_BIT"))
         c->sortBeginBit = std::max(0, std::min(atoi(e), 24));
+    if (const char *e = getenv("SB_GRAPHS"))
+        c->useGraphs = atoi(e) != 0;
     if (const char *e = getenv("SB_GRID3_EAGER_BELOW"))
         c->grid3EagerBelow = (size_t)std::max(0ll, atoll(e));
     if (const char *e = getenv("SB_CLASSIFY_POOL_LIMIT"))
@@ -686,6 +694,57 @@ int sb_mesh_build(sb_mesh *m)
     m->d.gridAxes = m->grid3Wanted ? 3 : 2;
     // after whatever the context stream still does with this mesh's buffers
     order_after_context(c, m);
+    if (c->useGraphs && m->d.nT && m->gridSized) {
+        const unsigned sig = (unsigned)m->d.gridAxes | (m->treeWanted ? 4u : 0u) | ((unsigned)m->d.sortBeginBit << 3);
+        if (m->buildGraph && m->graphSig != sig) {
+            cudaGraphExecDestroy(m->buildGraph);
+            m->buildGraph = nullptr;
+        }
+        if (!m->buildGraph) {
+            const uint64_t k0 = c->lc.kernels;
+            SB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            cudaError_t e = cudaMemsetAsync(m->d.root, 0, 8, st);
+            if (e == cudaSuccess) e = sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc);
+            if (e == cudaSuccess) e = sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc);
+            if (e == cudaSuccess) e = sbk_build_leaves(st, m->d, c->lc);
+            if (e == cudaSuccess && m->treeWanted) { // fork: the LBVH beside the grid scan / fill
+                e = cudaEventRecord(m->leavesDone, st);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(m->treeStream, m->leavesDone, 0);
+                if (e == cudaSuccess) e = sbk_build_tree(m->treeStream, m->d, c->lc);
+                if (e == cudaSuccess) e = cudaEventRecord(m->leavesDone, m->treeStream);
+            }
+            if (e == cudaSuccess) e = sbk_grid_scan(st, m->d, m->scanScratch, c->lc);
+            if (e == cudaSuccess) e = sbk_grid_fill(st, m->d, c->lc);
+            if (e == cudaSuccess && m->treeWanted)
+                e = cudaStreamWaitEvent(st, m->leavesDone, 0); // join
+            cudaGraph_t graph = nullptr;
+            cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+            m->graphKernels = c->lc.kernels - k0;
+            c->lc.kernels = k0;
+            if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
+                if (graph)
+                    cudaGraphDestroy(graph);
+                return fail(SB_ERR_CUDA, "build graph capture: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+            }
+            e = cudaGraphInstantiate(&m->buildGraph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                m->buildGraph = nullptr;
+                return fail(SB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+            }
+            m->graphSig = sig;
+        }
+        {
+            StageTimer t(c, SB_STAGE_BUILD, st);
+            SB_CUDA(cudaGraphLaunch(m->buildGraph, st));
+        }
+        c->lc.kernels += m->graphKernels;
+        m->treeBuilt = m->treeWanted;
+        SB_CUDA(cudaEventRecord(m->leafReady, st));
+        SB_CUDA(cudaEventRecord(m->ready, st));
+        m->built = true;
+        return SB_OK;
+    }
     {
         StageTimer t(c, SB_STAGE_BUILD, st);
         SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, st));
@@ -799,6 +858,8 @@ void sb_mesh_destroy(sb_mesh *m)
         cudaEventDestroy(m->leafReady);
     if (m->leavesDone)
         cudaEventDestroy(m->leavesDone);
+    if (m->buildGraph)
+        cudaGraphExecDestroy(m->buildGraph);
     delete m;
 }
 
