@@ -116,8 +116,8 @@ struct sb_mesh {
     cudaEvent_t ready = nullptr;     // everything built (incl. the ray grids)
     cudaStream_t treeStream = nullptr; // the (latency-bound) LBVH kernel runs here, beside the grid scan / fill
     cudaEvent_t leavesDone = nullptr;  // leaf kernel finished (orders treeStream behind the mesh stream)
-    cudaEvent_t leafReady = nullptr; // sorted leaves / boxes / centroids (+ LBVH when wanted): all the
-                                     // intersection needs, recorded before the grids are built
+    cudaEvent_t leafReady = nullptr; // sorted leaves / boxes / centroids: all a QUERY mesh needs,
+                                     // recorded before the grids (and the LBVH) are built
     uint32_t *radixWs = nullptr;     // in the arena
     uint32_t *scanScratch = nullptr; // in the arena
     uint32_t *hCounts = nullptr;     // pinned: [0] total refs, [1..3] big-list lengths
@@ -126,7 +126,8 @@ struct sb_mesh {
     bool grid3Wanted = false;        // a vote (or a per-axis query) needed the third grid: builds include it from now on
     // A REbuild (same immutable geometry, reference list already sized) is a fixed sequence of
     // ~20 launches and memsets on two streams: captured once, replayed as one CUDA graph.
-    cudaGraphExec_t buildGraph = nullptr;
+    cudaGraphExec_t buildGraph = nullptr;  // sort .. leaves (then leafReady is recorded)
+    cudaGraphExec_t gridGraph = nullptr;   // {grid scan -> fill} beside {LBVH}
     unsigned graphSig = 0;           // what the capture depended on: grids, LBVH wanted, sorted bits
     uint64_t graphKernels = 0;       // kernels in the graph (launch accounting)
     bool treeBuilt = false;          // LBVH topology built (lazily, on first use as a traversal target)
@@ -406,7 +407,13 @@ int sb_context_create(int device, sb_context **out)
     cudaDeviceProp prop;
     SB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->smCount = prop.multiProcessorCount;
-    SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // Priorities: the intersection stages on the context stream are short and the host waits
+    // for their counts twice, the two classification launches are long and saturate every
+    // SM: with equal priorities the broad phase only got its CTAs once the classifiers had
+    // dispatched all of theirs, and the whole intersection ran as a tail after them.
+    int prioLow = 0, prioHigh = 0;
+    cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
+    SB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prioHigh));
     SB_CUDA(cudaMalloc(&c->dScalars, 512));
     SB_CUDA(cudaMallocHost(&c->hScalars, 512));
     SB_CUDA(cudaMallocHost(&c->hPool, 256 * 32));
@@ -416,7 +423,7 @@ int sb_context_create(int device, sb_context **out)
         if (l == 0)
             c->lanes[l].stream = c->stream;
         else
-            SB_CUDA(cudaStreamCreateWithFlags(&c->lanes[l].stream, cudaStreamNonBlocking));
+            SB_CUDA(cudaStreamCreateWithPriority(&c->lanes[l].stream, cudaStreamNonBlocking, prioLow));
         SB_CUDA(cudaEventCreateWithFlags(&c->lanes[l].done, cudaEventDisableTiming));
     }
     SB_CUDA(cudaEventCreate(&c->t0));
@@ -506,8 +513,11 @@ static int drain_spans(sb_context *c)
     std::vector<std::pair<float, float>> iv[SB_STAGE_COUNT];
     for (auto &s : c->spans) {
         float a = 0, b = 0;
-        if (cudaEventElapsedTime(&a, c->t0, s.a) == cudaSuccess && cudaEventElapsedTime(&b, c->t0, s.b) == cudaSuccess)
+        if (cudaEventElapsedTime(&a, c->t0, s.a) == cudaSuccess && cudaEventElapsedTime(&b, c->t0, s.b) == cudaSuccess) {
             iv[s.stage].push_back({a, b});
+            if (getenv("SB_DEBUG_SPANS")) // dev: the timeline of the stage spans since the last reset
+                fprintf(stderr, "[sb] span stage %d: %.4f .. %.4f ms\n", s.stage, a, b);
+        }
         c->freeEvents.push_back(s.a);
         c->freeEvents.push_back(s.b);
     }
@@ -698,49 +708,75 @@ int sb_mesh_build(sb_mesh *m)
         const unsigned sig = (unsigned)m->d.gridAxes | (m->treeWanted ? 4u : 0u) | ((unsigned)m->d.sortBeginBit << 3);
         if (m->buildGraph && m->graphSig != sig) {
             cudaGraphExecDestroy(m->buildGraph);
-            m->buildGraph = nullptr;
+            cudaGraphExecDestroy(m->gridGraph);
+            m->buildGraph = m->gridGraph = nullptr;
         }
         if (!m->buildGraph) {
             const uint64_t k0 = c->lc.kernels;
-            SB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            cudaError_t e = cudaMemsetAsync(m->d.root, 0, 8, st);
-            if (e == cudaSuccess) e = sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc);
-            if (e == cudaSuccess) e = sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc);
-            if (e == cudaSuccess) e = sbk_build_leaves(st, m->d, c->lc);
-            if (e == cudaSuccess && m->treeWanted) { // fork: the LBVH beside the grid scan / fill
-                e = cudaEventRecord(m->leavesDone, st);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(m->treeStream, m->leavesDone, 0);
-                if (e == cudaSuccess) e = sbk_build_tree(m->treeStream, m->d, c->lc);
-                if (e == cudaSuccess) e = cudaEventRecord(m->leavesDone, m->treeStream);
-            }
-            if (e == cudaSuccess) e = sbk_grid_scan(st, m->d, m->scanScratch, c->lc);
-            if (e == cudaSuccess) e = sbk_grid_fill(st, m->d, c->lc);
-            if (e == cudaSuccess && m->treeWanted)
-                e = cudaStreamWaitEvent(st, m->leavesDone, 0); // join
-            cudaGraph_t graph = nullptr;
-            cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+            // two graphs, so that the event the classification queries of OTHER streams wait
+            // for (sorted centroids ready) can be recorded between them
+            auto capture = [&](cudaGraphExec_t *exec, auto &&enqueue) -> int {
+                SB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+                cudaError_t e = enqueue();
+                cudaGraph_t graph = nullptr;
+                cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+                if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
+                    if (graph)
+                        cudaGraphDestroy(graph);
+                    return fail(SB_ERR_CUDA, "build graph capture: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+                }
+                e = cudaGraphInstantiate(exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) {
+                    *exec = nullptr;
+                    return fail(SB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+                }
+                return SB_OK;
+            };
+            int r = capture(&m->buildGraph, [&]() {
+                cudaError_t e = cudaMemsetAsync(m->d.root, 0, 8, st);
+                if (e == cudaSuccess) e = sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc);
+                if (e == cudaSuccess) e = sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc);
+                if (e == cudaSuccess) e = sbk_build_leaves(st, m->d, c->lc);
+                return e;
+            });
+            if (!r)
+                r = capture(&m->gridGraph, [&]() {
+                    cudaError_t e = cudaSuccess;
+                    if (m->treeWanted) { // fork: the LBVH beside the grid scan / fill
+                        e = cudaEventRecord(m->leavesDone, st);
+                        if (e == cudaSuccess) e = cudaStreamWaitEvent(m->treeStream, m->leavesDone, 0);
+                        if (e == cudaSuccess) e = sbk_build_tree(m->treeStream, m->d, c->lc);
+                        if (e == cudaSuccess) e = cudaEventRecord(m->leavesDone, m->treeStream);
+                    }
+                    if (e == cudaSuccess) e = sbk_grid_scan(st, m->d, m->scanScratch, c->lc);
+                    if (e == cudaSuccess) e = sbk_grid_fill(st, m->d, c->lc);
+                    if (e == cudaSuccess && m->treeWanted)
+                        e = cudaStreamWaitEvent(st, m->leavesDone, 0); // join
+                    return e;
+                });
             m->graphKernels = c->lc.kernels - k0;
             c->lc.kernels = k0;
-            if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
-                if (graph)
-                    cudaGraphDestroy(graph);
-                return fail(SB_ERR_CUDA, "build graph capture: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
-            }
-            e = cudaGraphInstantiate(&m->buildGraph, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) {
-                m->buildGraph = nullptr;
-                return fail(SB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+            if (r) {
+                if (m->buildGraph)
+                    cudaGraphExecDestroy(m->buildGraph);
+                m->buildGraph = m->gridGraph = nullptr;
+                return r;
             }
             m->graphSig = sig;
         }
         {
             StageTimer t(c, SB_STAGE_BUILD, st);
             SB_CUDA(cudaGraphLaunch(m->buildGraph, st));
+            SB_CUDA(cudaGraphLaunch(m->gridGraph, st));
         }
+        // Recorded at the END of a rebuild on purpose: letting the other mesh's face queries
+        // start as soon as the sorted centroids exist (between the two graphs) was measured
+        // slower -- the two long classification launches then no longer run side by side and
+        // the later one ends with its tail alone (1.32 -> 1.37 ms/step at 1M+1M).
+        SB_CUDA(cudaEventRecord(m->leafReady, st));
         c->lc.kernels += m->graphKernels;
         m->treeBuilt = m->treeWanted;
-        SB_CUDA(cudaEventRecord(m->leafReady, st));
         SB_CUDA(cudaEventRecord(m->ready, st));
         m->built = true;
         return SB_OK;
@@ -752,21 +788,20 @@ int sb_mesh_build(sb_mesh *m)
         SB_CUDA(sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc));
         SB_CUDA(sbk_build_leaves(st, m->d, c->lc)); // also counts the grid cells
         m->treeBuilt = false;
+        // classification queries of this mesh's faces can start here (sorted centroids)
+        SB_CUDA(cudaEventRecord(m->leafReady, st));
         if (m->treeWanted) {
             // known traversal target: the LBVH right away, on its own stream -- one
             // latency-bound kernel (an atomic rendezvous per level) next to the
-            // bandwidth-bound grid scan / fill of the same mesh
+            // bandwidth-bound grid scan / fill of the same mesh; `ready` covers it
             SB_CUDA(cudaEventRecord(m->leavesDone, st));
             SB_CUDA(cudaStreamWaitEvent(m->treeStream, m->leavesDone, 0));
             {
                 StageTimer tt(c, SB_STAGE_BUILD, m->treeStream);
                 SB_CUDA(sbk_build_tree(m->treeStream, m->d, c->lc));
             }
+            SB_CUDA(cudaEventRecord(m->leavesDone, m->treeStream));
             m->treeBuilt = true;
-            // the intersection can start here, while the ray grids are still being built
-            SB_CUDA(cudaEventRecord(m->leafReady, m->treeStream));
-        } else {
-            SB_CUDA(cudaEventRecord(m->leafReady, st));
         }
         SB_CUDA(sbk_grid_scan(st, m->d, m->scanScratch, c->lc));
         if (m->d.nT && m->gridSized) {
@@ -782,7 +817,7 @@ int sb_mesh_build(sb_mesh *m)
             return r;
     }
     if (m->treeBuilt && m->d.nT)
-        SB_CUDA(cudaStreamWaitEvent(st, m->leafReady, 0)); // `ready` covers the LBVH too
+        SB_CUDA(cudaStreamWaitEvent(st, m->leavesDone, 0)); // `ready` covers the LBVH too
     SB_CUDA(cudaEventRecord(m->ready, st));
     m->built = true;
     return SB_OK;
@@ -860,6 +895,8 @@ void sb_mesh_destroy(sb_mesh *m)
         cudaEventDestroy(m->leavesDone);
     if (m->buildGraph)
         cudaGraphExecDestroy(m->buildGraph);
+    if (m->gridGraph)
+        cudaGraphExecDestroy(m->gridGraph);
     delete m;
 }
 
@@ -1022,8 +1059,8 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         if (rt)
             return rt;
     }
-    use_mesh_leaves(c, A); // the grids are not read here: the broad phase may overlap their build
-    use_mesh_leaves(c, B);
+    use_mesh_leaves(c, A); // the query side reads the sorted leaves only: may overlap A's grid build
+    use_mesh(c, B);        // the target's LBVH is finished together with its grids
     sb_isect *x = new (std::nothrow) sb_isect;
     if (!x)
         return fail(SB_ERR_NOMEM, "out of host memory");
