@@ -68,7 +68,9 @@ int sb_mesh_create(sb_context *ctx, const double *xyz, size_t nV,
                    const uint32_t *tri, size_t nT, sb_mesh **out);
 /* Split form used for device-resident timing: upload copies the geometry to the
  * device (no build), build (re)builds every derived array from the resident
- * geometry.  build is asynchronous on the context stream. */
+ * geometry.  build is asynchronous (each mesh has its own stream); an invalid mesh
+ * (triangle index out of range) is reported by build or, at the latest, by the first
+ * call that uses the mesh. */
 int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV,
                    const uint32_t *tri, size_t nT, sb_mesh **out);
 int sb_mesh_build(sb_mesh *mesh);

@@ -123,6 +123,9 @@ struct sb_mesh {
     uint32_t *hCounts = nullptr;     // pinned: [0] total refs, [1..3] big-list lengths
     uint32_t *hErr = nullptr;        // pinned: index-validation flag read back with the counts
     bool gridSized = false;          // reference list already sized by an earlier build
+    bool gridPending = false;        // first build: counts on their way to the host, list not yet sized / filled
+                                     // (mesh_finish completes it at the first use, so that the host does not
+                                     // wait for one mesh before it has enqueued the next one's build)
     bool grid3Wanted = false;        // a vote (or a per-axis query) needed the third grid: builds include it from now on
     // A REbuild (same immutable geometry, reference list already sized) is a fixed sequence of
     // ~20 launches and memsets on two streams: captured once, replayed as one CUDA graph.
@@ -618,15 +621,27 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
 
 // First build (or first build with a third grid): the reference list is sized from the
 // counts (16-byte read-back on the mesh's stream), then filled.
-static int grid_size_and_fill(sb_mesh *m)
+static int grid_counts_readback(sb_mesh *m)
 {
-    sb_context *c = m->ctx;
     cudaStream_t st = m->stream;
     uint32_t *h = m->hCounts;
     SB_CUDA(cudaMemcpyAsync(h, m->d.gridBigCount + 6, 4, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaMemcpyAsync(h + 1, m->d.gridBigCount, 12, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(m->hErr, m->d.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return SB_OK;
+}
+
+static int grid_size_and_fill(sb_mesh *m, bool readback = true)
+{
+    sb_context *c = m->ctx;
+    cudaStream_t st = m->stream;
+    uint32_t *h = m->hCounts;
+    if (readback) {
+        int r = grid_counts_readback(m);
+        if (r)
+            return r;
+    }
     int *hErr = reinterpret_cast<int *>(m->hErr);
-    SB_CUDA(cudaMemcpyAsync(hErr, m->d.err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     if (*hErr)
         return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
@@ -651,6 +666,26 @@ static int grid_size_and_fill(sb_mesh *m)
     return SB_OK;
 }
 
+// Completes a first build whose reference list is still to be sized and filled.
+static int mesh_finish(const sb_mesh *mc)
+{
+    sb_mesh *m = const_cast<sb_mesh *>(mc);
+    if (!m || !m->gridPending)
+        return SB_OK;
+    m->gridPending = false;
+    DeviceGuard g(m->ctx->device);
+    int r = grid_size_and_fill(m, false);
+    if (r) {
+        m->built = false;
+        return r;
+    }
+    cudaStream_t st = m->stream;
+    if (m->treeBuilt && m->d.nT)
+        SB_CUDA(cudaStreamWaitEvent(st, m->leavesDone, 0)); // `ready` covers the LBVH too
+    SB_CUDA(cudaEventRecord(m->ready, st));
+    return SB_OK;
+}
+
 // The third ray grid (rays along z) is only binned once something needs it: a point
 // whose first two votes disagree, or a per-axis query.  The mesh's grids are then built
 // again from the stored quantised boxes with all three axes (and every later
@@ -660,6 +695,11 @@ static int ensure_grid3(const sb_mesh *mc)
     sb_mesh *m = const_cast<sb_mesh *>(mc);
     if (m->d.gridAxes == 3 || !m->d.nT)
         return SB_OK;
+    {
+        int rf = mesh_finish(m);
+        if (rf)
+            return rf;
+    }
     sb_context *c = m->ctx;
     for (int l = 0; l < 3; ++l)
         SB_CUDA(cudaStreamSynchronize(c->lanes[l].stream));
@@ -687,6 +727,7 @@ int sb_mesh_build(sb_mesh *m)
     sb_context *c = m->ctx;
     DeviceGuard g(c->device);
     cudaStream_t st = m->stream;
+    m->gridPending = false; // an unfinished first build is simply redone
     if (c->sortBeginBit >= 0) {
         m->d.sortBeginBit = c->sortBeginBit;
     } else {
@@ -812,9 +853,14 @@ int sb_mesh_build(sb_mesh *m)
         }
     }
     if (m->d.nT && !m->gridSized) {
-        int r = grid_size_and_fill(m);
+        // first build: the list has to be sized from the counts.  They are sent to the host
+        // here; the rest (size, fill, `ready`) happens at the first use of the mesh
+        int r = grid_counts_readback(m);
         if (r)
             return r;
+        m->gridPending = true;
+        m->built = true;
+        return SB_OK;
     }
     if (m->treeBuilt && m->d.nT)
         SB_CUDA(cudaStreamWaitEvent(st, m->leavesDone, 0)); // `ready` covers the LBVH too
@@ -829,6 +875,11 @@ static int ensure_tree(const sb_mesh *mc)
     sb_mesh *m = const_cast<sb_mesh *>(mc);
     if (m->treeBuilt)
         return SB_OK;
+    {
+        int rf = mesh_finish(m);
+        if (rf)
+            return rf;
+    }
     sb_context *c = m->ctx;
     {
         StageTimer t(c, SB_STAGE_BUILD, m->stream);
@@ -843,6 +894,11 @@ static int ensure_tree(const sb_mesh *mc)
 
 static int mesh_check(sb_mesh *m)
 {
+    {
+        int rf = mesh_finish(m);
+        if (rf)
+            return rf;
+    }
     sb_context *c = m->ctx;
     int err = 0;
     use_mesh(c, m);
@@ -909,6 +965,11 @@ static int mesh_download(const sb_mesh *m, void *dst, const void *src, size_t by
         return fail(SB_ERR_INVALID, "null mesh or output");
     if (!m->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rf = mesh_finish(m);
+        if (rf)
+            return rf;
+    }
     DeviceGuard g(m->ctx->device);
     use_mesh(m->ctx, m);
     if (bytes)
@@ -927,6 +988,11 @@ int sb_mesh_triangle_boxes(const sb_mesh *m, double *out)
         return fail(SB_ERR_INVALID, "mesh not built");
     if (!m->d.nT)
         return SB_OK;
+    {
+        int rf = mesh_finish(m);
+        if (rf)
+            return rf;
+    }
     sb_context *c = m->ctx;
     DeviceGuard g(c->device);
     use_mesh(c, m);
@@ -1000,6 +1066,11 @@ int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
     memset(out, 0, sizeof(*out));
     if (!m->d.nT)
         return SB_OK;
+    {
+        int rf = mesh_finish(m);
+        if (rf)
+            return rf;
+    }
     GridParams g;
     int r = mesh_download(m, &g, m->d.gridParams, sizeof(g));
     if (r)
@@ -1046,6 +1117,13 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         return fail(SB_ERR_INVALID, "meshes belong to different contexts");
     if (!A->built || !B->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rf = mesh_finish(A);
+        if (!rf)
+            rf = mesh_finish(B);
+        if (rf)
+            return rf;
+    }
     if (end > A->d.nT)
         end = A->d.nT;
     if (begin > end)
@@ -1522,6 +1600,11 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
         return fail(SB_ERR_INVALID, "null argument");
     if (!target->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rf = mesh_finish(target);
+        if (rf)
+            return rf;
+    }
     if (Q >= (1ull << 31))
         return fail(SB_ERR_INVALID, "too many points");
     if (!Q)
@@ -1568,6 +1651,13 @@ static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size
         return fail(SB_ERR_INVALID, "meshes belong to different contexts");
     if (!query->built || !target->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rf = mesh_finish(query);
+        if (!rf)
+            rf = mesh_finish(target);
+        if (rf)
+            return rf;
+    }
     sb_context *c = query->ctx;
     use_mesh(c, query);
     use_mesh(c, target);
@@ -1641,6 +1731,13 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
         return fail(SB_ERR_INVALID, "meshes belong to different contexts");
     if (!A->built || !B->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rf = mesh_finish(A);
+        if (!rf)
+            rf = mesh_finish(B);
+        if (rf)
+            return rf;
+    }
     sb_context *c = A->ctx;
     DeviceGuard g(c->device);
     aEnd = std::min<size_t>(aEnd, A->d.nT);

@@ -225,9 +225,10 @@ def test_invalid_arguments(ctx):
     xyz = np.zeros((3, 3))
     with pytest.raises(sb.SolidBooleanError, match="out of range"):
         ctx.mesh(xyz, np.array([[0, 1, 3]], np.uint32))
-    bad = ctx.mesh(xyz, np.array([[0, 1, 2], [0, 7, 2]], np.uint32), build=False)   # split upload/build path
-    with pytest.raises(sb.SolidBooleanError, match="out of range"):
-        bad.build()
+    bad = ctx.mesh(xyz, np.array([[0, 1, 2], [0, 7, 2]], np.uint32), build=False)   # split upload/build path:
+    with pytest.raises(sb.SolidBooleanError, match="out of range"):                   # the build is asynchronous, the
+        bad.build()                                                                   # error surfaces at the latest
+        bad.normals()                                                                 # with the first use of the mesh
     bad.close()
     m = ctx.mesh(*meshgen.icosphere(1))
     with pytest.raises(sb.SolidBooleanError, match="multiple of 32"):
