@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4"])
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c4k8"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -55,11 +55,13 @@ def parse_args():
 
 def workload(name):
     from solidboolean_b200 import meshgen
-    a, b = {"c2": meshgen.config_c2, "c3": meshgen.config_c3, "c4": meshgen.config_c4}[name]()
+    a, b = {"c2": meshgen.config_c2, "c3": meshgen.config_c3, "c4": meshgen.config_c4,
+            "c4k8": lambda: meshgen.config_c4(k=8)}[name]()
     desc = {
         "c2": "two offset icospheres k=6, 81,920 + 81,920 triangles (BASELINE configs[1])",
         "c3": "icosphere k=8 (1,310,720 tris) vs torus 1024x512 (1,048,576 tris), BASELINE configs[2] = the 1M+1M config the metric is quoted on",
         "c4": "near-coincident icospheres k=7, 327,680 x2 triangles, ~2.3M candidate pairs (BASELINE configs[3] proxy)",
+        "c4k8": "near-coincident icospheres k=8, 1,310,720 x2 triangles, ~8.2M candidate pairs (BASELINE configs[3] at its stated size)",
     }[name]
     return a, b, desc
 

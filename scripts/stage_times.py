@@ -8,7 +8,8 @@ from solidboolean_b200 import meshgen
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 t0 = time.time()
-a, b = {"c2": meshgen.config_c2, "c3": meshgen.config_c3, "c4": meshgen.config_c4}[cfg]()
+a, b = {"c2": meshgen.config_c2, "c3": meshgen.config_c3, "c4": meshgen.config_c4,
+        "c4k8": lambda: meshgen.config_c4(k=8)}[cfg]()   # c4k8: 1,310,720 x2 near-coincident, ~9 M candidate pairs
 print("gen %.2fs  A %d tris  B %d tris" % (time.time() - t0, len(a[1]), len(b[1])), flush=True)
 import torch
 ctx = sb.Context(0)
