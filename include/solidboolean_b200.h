@@ -38,6 +38,7 @@ extern "C" {
 typedef struct sb_context sb_context;
 typedef struct sb_mesh sb_mesh;
 typedef struct sb_isect sb_isect;
+typedef struct sb_uncut sb_uncut;
 
 /* Thread-local message of the last failing call ("" if none). */
 const char *sb_last_error(void);
@@ -163,6 +164,42 @@ int sb_fp64_peak(sb_context *ctx, double *nofma_gflops, double *fma_gflops);
 int sb_tri_tri_batch(sb_context *ctx, const double *tris18, size_t n,
                      int32_t *ret, int32_t *coplanar, double *seg6);
 
+/* ---- uncut triangles + half-edge map: replaces SolidBoolean::addUnintersectedTriangles
+ * (src/solidboolean.cpp:250-286, called at :411-421) and answers the half-edge lookups of
+ * buildFaceGroups (:205-224) -- SURVEY 8f row 2.
+ * Every face of the mesh that is not cut becomes new triangle `triangle_offset + rank` (rank =
+ * its position among the uncut faces, original order = the reference's m_newTriangles order)
+ * with vertex ids shifted by vertex_offset (= m_newVertices.size() before the call, :253); its
+ * half-edges are keyed (first << 32) | second (makeHalfEdgeKey, src/solidboolean.h:75-78).
+ * vertex_offset + nV must fit 32 bits.
+ * Error behaviour as the reference: a repeated half-edge does not fail the call; *ok = 0 and the
+ * object holds exactly what the reference leaves behind when it returns false -- the triangles up
+ * to and including the offending one, the half-edges inserted before the refused insertion. */
+
+/* Cut faces = the faces the intersection touched (m_firstIntersectedFaces for which = 0,
+ * m_secondIntersectedFaces for which = 1, src/solidboolean.cpp:318-319); no host round trip of
+ * the flags. */
+int sb_isect_uncut(const sb_isect *isect, int which, size_t vertex_offset, size_t triangle_offset,
+                   sb_uncut **out);
+/* Same with an explicit per-face flag array (host, nT bytes, non-zero = cut; NULL = keep all). */
+int sb_mesh_uncut(const sb_mesh *mesh, const uint8_t *cut_flags, size_t vertex_offset,
+                  size_t triangle_offset, sb_uncut **out);
+void sb_uncut_destroy(sb_uncut *u);
+/* n_triangles new triangles, n_half_edges map entries, *ok = the reference's return value. */
+int sb_uncut_counts(const sb_uncut *u, size_t *n_triangles, size_t *n_half_edges, int *ok);
+/* face: original face id per new triangle; tri3 (optional): its shifted index triple. */
+int sb_uncut_triangles(const sb_uncut *u, uint32_t *face, uint32_t *tri3);
+/* The map, sorted by key: keys[n_half_edges], owner[n_half_edges] (new triangle index). */
+int sb_uncut_half_edges(const sb_uncut *u, uint64_t *keys, uint32_t *owner);
+/* adj3[3 j + k] = owner of the half-edge opposite to edge k (vertices k, k+1 mod 3) of new
+ * triangle j, or -1 if the map has none (the neighbour is a cut face or the mesh is open). */
+int sb_uncut_adjacency(const sb_uncut *u, int32_t *adj3);
+/* Device pointers of the same arrays (valid until sb_uncut_destroy) for device-side consumers;
+ * any out pointer may be NULL.  After a repeated half-edge (*ok == 0) they hold the untruncated
+ * arrays of ALL uncut faces. */
+int sb_uncut_device_ptrs(const sb_uncut *u, void **face, void **tri3, void **keys, void **owner,
+                         void **adj3);
+
 /* ---- classification: replaces SolidBoolean::isPointInMesh
  * (src/solidboolean.cpp:48-92) as driven by decideGroupSide (:482-510): three
  * rays (g_testAxisList :31-35) per point, PositionKey de-duplication
@@ -207,7 +244,8 @@ enum {
     SB_STAGE_NARROW = 2,   /* hit / candidate sorts + gather */
     SB_STAGE_CLASSIFY = 3, /* ray classification */
     SB_STAGE_PREDICATE = 4,/* the tri/tri predicate kernel alone (FP64 roofline) */
-    SB_STAGE_COUNT = 5
+    SB_STAGE_HALFEDGE = 5, /* uncut-triangle compaction, half-edge sort, adjacency */
+    SB_STAGE_COUNT = 6
 };
 int sb_context_enable_timing(sb_context *ctx, int enable);
 int sb_context_reset_timing(sb_context *ctx);

@@ -24,6 +24,7 @@ _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _i8p = np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 
 
 def build(force: bool = False) -> None:
@@ -76,6 +77,10 @@ class Oracle:
                                    C.POINTER(C.c_uint64)]
         L.sbo_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
         L.sbo_fnv1a64.restype = C.c_uint64
+        L.sbo_uncut_half_edges.argtypes = [_u32p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint64, _u32p,
+                                           C.POINTER(C.c_size_t), _u64p, _u32p, C.POINTER(C.c_size_t)]
+        L.sbo_uncut_half_edges.restype = C.c_int
+        L.sbo_uncut_adjacency.argtypes = [_u32p, _u32p, C.c_size_t, C.c_uint64, _u64p, _u32p, C.c_size_t, _i32p]
 
     # -- predicate ---------------------------------------------------------
     def tri_tri_batch(self, tris18):
@@ -133,6 +138,29 @@ class Oracle:
         if n:
             self.lib.sbo_predicate_pairs(xa, ta, xb, tb, pairs, n, ret, cop, hit, seg)
         return ret, cop, hit, seg
+
+    # -- uncut triangles + half-edge map -----------------------------------
+    def uncut_half_edges(self, tri, cut=None, vertex_offset=0, triangle_offset=0):
+        """addUnintersectedTriangles (src/solidboolean.cpp:250-286) for one mesh.
+        -> dict(ok, face [n], keys [m] ascending, owner [m], adj [n,3])"""
+        tri = _u32(tri).reshape(-1, 3)
+        nT = tri.shape[0]
+        cutp = None
+        if cut is not None:
+            cut = np.ascontiguousarray(cut, dtype=np.uint8)
+            assert cut.shape[0] == nT
+            cutp = cut.ctypes.data_as(C.c_void_p)
+        face = np.zeros(max(nT, 1), np.uint32)
+        keys = np.zeros(max(3 * nT, 1), np.uint64)
+        owner = np.zeros(max(3 * nT, 1), np.uint32)
+        n, m = C.c_size_t(0), C.c_size_t(0)
+        ok = self.lib.sbo_uncut_half_edges(tri, nT, cutp, vertex_offset, triangle_offset, face, C.byref(n),
+                                           keys, owner, C.byref(m))
+        face, keys, owner = face[:n.value].copy(), keys[:m.value].copy(), owner[:m.value].copy()
+        adj = np.full((n.value, 3), -1, np.int32)
+        if n.value:
+            self.lib.sbo_uncut_adjacency(tri, face, n.value, vertex_offset, keys, owner, m.value, adj)
+        return dict(ok=bool(ok), face=face, keys=keys, owner=owner, adj=adj)
 
     # -- classification -----------------------------------------------------
     def classify(self, target_mesh, pts):
@@ -195,6 +223,11 @@ class Ref:
         L.ref_op_result_triangles.argtypes = [vp, C.c_int, _u32p]
         L.ref_op_group_count.argtypes = [vp, C.c_int]
         L.ref_op_group_count.restype = C.c_size_t
+        if hasattr(L, "ref_op_uncut"):
+            L.ref_op_uncut.argtypes = [vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int]
+            L.ref_op_uncut.restype = C.c_int
+            L.ref_op_uncut_fetch.argtypes = [vp, C.c_int, _u64p, _u32p]
+            L.ref_op_uncut_lookup.argtypes = [vp, C.c_int, _u64p, C.c_size_t, _i32p]
         if hasattr(L, "ref_load_obj"):
             L.ref_load_obj.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p,
                                        C.POINTER(C.c_size_t)]
@@ -319,6 +352,37 @@ class RefOp:
                 res[name] = t
             res["groups"] = (self.ref.lib.ref_op_group_count(self.h, 0), self.ref.lib.ref_op_group_count(self.h, 1))
         return res
+
+    def uncut(self, cut_a=None, cut_b=None):
+        """The reference's addUnintersectedTriangles for both meshes, as combine() calls them.
+        -> [dict(ok, n_triangles (m_newTriangles.size() after the call), keys, owner)] x 2, triangles"""
+        def ptr(c):
+            if c is None:
+                return None, None
+            c = np.ascontiguousarray(c, dtype=np.uint8)
+            return c, c.ctypes.data_as(C.c_void_p)
+        ka, pa = ptr(cut_a)
+        kb, pb = ptr(cut_b)
+        ntri = (C.c_size_t * 2)()
+        nkeys = (C.c_size_t * 2)()
+        res = self.ref.lib.ref_op_uncut(self.h, pa, pb, ntri, nkeys, 1)
+        out = []
+        for w in range(2):
+            keys = np.zeros(max(nkeys[w], 1), np.uint64)
+            owner = np.zeros(max(nkeys[w], 1), np.uint32)
+            self.ref.lib.ref_op_uncut_fetch(self.h, w, keys, owner)
+            out.append(dict(ok=bool(res >> w & 1), n_triangles=int(ntri[w]), keys=keys[:nkeys[w]], owner=owner[:nkeys[w]]))
+        tris = np.zeros((max(ntri[1], 1), 3), np.uint32)
+        if ntri[1]:
+            self.ref.lib.ref_op_result_triangles(self.h, 0, tris)
+        return out, tris[:ntri[1]]
+
+    def uncut_lookup(self, which, from_to):
+        ft = np.ascontiguousarray(from_to, dtype=np.uint64).reshape(-1, 2)
+        out = np.zeros(ft.shape[0], np.int32)
+        if ft.shape[0]:
+            self.ref.lib.ref_op_uncut_lookup(self.h, which, ft, ft.shape[0], out)
+        return out
 
     def close(self):
         if self.h:

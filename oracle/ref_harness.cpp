@@ -14,6 +14,7 @@
 //   SolidBoolean::intersectTwoFaces             src/solidboolean.cpp:103-122
 //   SolidBoolean::isPointInMesh                 src/solidboolean.cpp:48-92
 //   SolidBoolean::combine / fetch*              src/solidboolean.cpp:288-565
+//   SolidBoolean::addUnintersectedTriangles     src/solidboolean.cpp:250-286
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -67,6 +68,8 @@ struct RefOp {
     bool combined = false;
     bool combineOk = false;
     std::vector<std::vector<size_t>> fetched[3];
+    // ref_op_uncut: the two half-edge maps, flattened and sorted by key
+    std::vector<std::pair<uint64_t, size_t>> halfEdges[2];
 };
 
 // Silence the reference's std::cout chatter (failure messages) on request.
@@ -370,5 +373,63 @@ int ref_load_obj(const char *path, double *xyz, size_t *nV, uint32_t *tri, size_
     return 1;
 }
 #endif
+
+// addUnintersectedTriangles for both meshes on a FRESH SolidBoolean, in the order combine()
+// calls them (src/solidboolean.cpp:411-421): first mesh with vertex offset 0, then the second
+// behind it.  cutA / cutB: per-face bytes (non-zero = the face is in usedFaces).
+// nTri[0] / nTri[1] = m_newTriangles.size() after the first / second call, nKeys = map sizes.
+// Returns bit 0 = first call's result, bit 1 = second call's.
+int ref_op_uncut(void *h, const uint8_t *cutA, const uint8_t *cutB, size_t *nTri, size_t *nKeys, int quiet)
+{
+    RefOp *o = (RefOp *)h;
+    SolidBoolean fresh(&o->a->mesh, &o->b->mesh);
+    std::unordered_set<size_t> used[2];
+    for (size_t i = 0; i < o->a->triangles.size(); ++i)
+        if (cutA && cutA[i])
+            used[0].insert(i);
+    for (size_t i = 0; i < o->b->triangles.size(); ++i)
+        if (cutB && cutB[i])
+            used[1].insert(i);
+    std::unordered_map<uint64_t, size_t> maps[2];
+    int result = 0;
+    {
+        CoutSilencer *s = quiet ? new CoutSilencer : nullptr;
+        if (fresh.addUnintersectedTriangles(&o->a->mesh, used[0], &maps[0]))
+            result |= 1;
+        nTri[0] = fresh.m_newTriangles.size();
+        if (fresh.addUnintersectedTriangles(&o->b->mesh, used[1], &maps[1]))
+            result |= 2;
+        nTri[1] = fresh.m_newTriangles.size();
+        delete s;
+    }
+    o->fetched[0] = fresh.m_newTriangles; // reuse the triple store for ref_op_result_triangles(h, 0, ..)
+    for (int w = 0; w < 2; ++w) {
+        o->halfEdges[w].assign(maps[w].begin(), maps[w].end());
+        std::sort(o->halfEdges[w].begin(), o->halfEdges[w].end());
+        nKeys[w] = o->halfEdges[w].size();
+    }
+    return result;
+}
+
+void ref_op_uncut_fetch(void *h, int which, uint64_t *keys, uint32_t *owner)
+{
+    RefOp *o = (RefOp *)h;
+    for (size_t i = 0; i < o->halfEdges[which].size(); ++i) {
+        keys[i] = o->halfEdges[which][i].first;
+        owner[i] = (uint32_t)o->halfEdges[which][i].second;
+    }
+}
+
+// buildFaceGroups' neighbour lookup (src/solidboolean.cpp:205-224) against the map kept by
+// ref_op_uncut: the owner of half-edge (from, to), or -1.
+void ref_op_uncut_lookup(void *h, int which, const uint64_t *fromTo, size_t n, int32_t *out)
+{
+    RefOp *o = (RefOp *)h;
+    std::unordered_map<uint64_t, size_t> m(o->halfEdges[which].begin(), o->halfEdges[which].end());
+    for (size_t i = 0; i < n; ++i) {
+        auto it = m.find(SolidBoolean::makeHalfEdgeKey(fromTo[2 * i], fromTo[2 * i + 1]));
+        out[i] = it == m.end() ? -1 : (int32_t)it->second;
+    }
+}
 
 } // extern "C"

@@ -766,3 +766,107 @@ uint64_t sbo_fnv1a64(const void *data, size_t n)
     }
     return h;
 }
+
+/* ---- uncut triangles + half-edge map -------------------------------
+ * SolidBoolean::addUnintersectedTriangles (src/solidboolean.cpp:250-286): every triangle of
+ * `mesh` that is not in usedFaces is appended to m_newTriangles with its vertex ids shifted
+ * by the number of vertices already in m_newVertices (:254, :265-269), and its three
+ * half-edges (0,1), (1,2), (2,0) are inserted into an unordered_map keyed by
+ * makeHalfEdgeKey(first, second) = (first << 32) | second (src/solidboolean.h:75-78) with the
+ * new triangle's index as value (:271-282).  The FIRST insertion that meets an existing key
+ * makes the function return false at once: the offending triangle is already in
+ * m_newTriangles, its earlier half-edges are in the map, nothing after it is visited.
+ *
+ * The map's iteration order is unspecified, so the contents are returned SORTED BY KEY.
+ *   cut            nT bytes (non-zero = in usedFaces) or NULL
+ *   outFace        original face id of new triangle k            (capacity nT)
+ *   outKeys/Owner  half-edge keys ascending + their triangle      (capacity 3 nT)
+ * Returns 1 like the reference's `true`, 0 after a repeated half-edge. */
+typedef struct {
+    uint64_t key;
+    uint32_t owner;
+} he_entry;
+
+static int cmp_he(const void *pa, const void *pb)
+{
+    const he_entry *a = (const he_entry *)pa, *b = (const he_entry *)pb;
+    return a->key < b->key ? -1 : a->key > b->key;
+}
+
+static inline uint64_t he_hash(uint64_t k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    return k;
+}
+
+int sbo_uncut_half_edges(const uint32_t *tri, size_t nT, const uint8_t *cut, uint64_t vertexOffset,
+    uint64_t triangleOffset, uint32_t *outFace, size_t *nTriOut, uint64_t *outKeys, uint32_t *outOwner,
+    size_t *nKeysOut)
+{
+    size_t cap = 16;
+    while (cap < 6 * nT + 16)
+        cap <<= 1;
+    uint64_t *slots = (uint64_t *)malloc(cap * sizeof(uint64_t)); /* open addressing; key + 1 so that 0 = empty */
+    he_entry *ent = (he_entry *)malloc((3 * nT + 1) * sizeof(he_entry));
+    memset(slots, 0, cap * sizeof(uint64_t));
+    size_t nTri = 0, nKeys = 0;
+    int ok = 1;
+    for (size_t i = 0; i < nT && ok; ++i) {
+        if (cut && cut[i])
+            continue; /* :261-262 */
+        uint64_t v[3] = {tri[3 * i] + vertexOffset, tri[3 * i + 1] + vertexOffset, tri[3 * i + 2] + vertexOffset};
+        uint64_t index = triangleOffset + nTri; /* :264 newInsertedIndex */
+        outFace[nTri++] = (uint32_t)i;          /* :265 push_back */
+        for (int k = 0; k < 3; ++k) {
+            uint64_t key = (v[k] << 32) | v[(k + 1) % 3];
+            size_t h = (size_t)he_hash(key) & (cap - 1);
+            while (slots[h] && slots[h] != key + 1)
+                h = (h + 1) & (cap - 1);
+            if (slots[h]) { /* :271-282 insert(...).second == false */
+                ok = 0;
+                break;
+            }
+            slots[h] = key + 1;
+            ent[nKeys].key = key;
+            ent[nKeys].owner = (uint32_t)index;
+            ++nKeys;
+        }
+    }
+    qsort(ent, nKeys, sizeof(he_entry), cmp_he);
+    for (size_t j = 0; j < nKeys; ++j) {
+        outKeys[j] = ent[j].key;
+        outOwner[j] = ent[j].owner;
+    }
+    *nTriOut = nTri;
+    *nKeysOut = nKeys;
+    free(slots);
+    free(ent);
+    return ok;
+}
+
+/* What buildFaceGroups asks the half-edge map (src/solidboolean.cpp:205-224): for edge k of a
+ * triangle (from, to) the triangle on the other side = halfEdges.find(key(to, from)).  For new
+ * triangle j (face outFace[j], vertex ids shifted by vertexOffset) adj[3 j + k] = that owner,
+ * or -1 when the map holds no such half-edge.  keys sorted ascending (as returned above). */
+void sbo_uncut_adjacency(const uint32_t *tri, const uint32_t *face, size_t nTri, uint64_t vertexOffset,
+    const uint64_t *keys, const uint32_t *owner, size_t nKeys, int32_t *adj)
+{
+    for (size_t j = 0; j < nTri; ++j) {
+        const uint32_t *t = tri + 3 * (size_t)face[j];
+        for (int k = 0; k < 3; ++k) {
+            uint64_t from = t[k] + vertexOffset, to = t[(k + 1) % 3] + vertexOffset;
+            uint64_t want = (to << 32) | from;
+            size_t lo = 0, hi = nKeys;
+            while (lo < hi) {
+                size_t mid = (lo + hi) / 2;
+                if (keys[mid] < want)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            adj[3 * j + k] = (lo < nKeys && keys[lo] == want) ? (int32_t)owner[lo] : -1;
+        }
+    }
+}

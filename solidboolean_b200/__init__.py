@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(HERE, "lib", "libsolidboolean_b200.so")  # override: dev builds
 
-STAGES = ("build", "broad", "narrow", "classify", "predicate")
+STAGES = ("build", "broad", "narrow", "classify", "predicate", "halfedge")
 ISECT_NO_SORT = 1
 
 
@@ -75,6 +75,15 @@ ABI = {
     "sb_isect_path_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "sb_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sb_tri_tri_batch": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "sb_isect_uncut": (C.c_int, [_vp, C.c_int, _sz, _sz, C.POINTER(_vp)]),
+    "sb_mesh_uncut": (C.c_int, [_vp, _vp, _sz, _sz, C.POINTER(_vp)]),
+    "sb_uncut_destroy": (None, [_vp]),
+    "sb_uncut_counts": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(C.c_int)]),
+    "sb_uncut_triangles": (C.c_int, [_vp, _vp, _vp]),
+    "sb_uncut_half_edges": (C.c_int, [_vp, _vp, _vp]),
+    "sb_uncut_adjacency": (C.c_int, [_vp, _vp]),
+    "sb_uncut_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                       C.POINTER(_vp)]),
     "sb_classify": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "sb_classify_faces": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sb_classify_faces_device": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
@@ -293,6 +302,17 @@ class Mesh:
         _check(self.lib.sb_classify_faces(self.h, target.h, _ptr(inside), _ptr(axes)))
         return inside, axes
 
+    def uncut(self, cut_flags=None, vertex_offset=0, triangle_offset=0) -> "Uncut":
+        """sb_mesh_uncut: addUnintersectedTriangles with an explicit per-face cut mask."""
+        cf = None
+        if cut_flags is not None:
+            cf = np.ascontiguousarray(cut_flags, dtype=np.uint8)
+            if cf.shape[0] != self.num_triangles:
+                raise ValueError("cut_flags must hold one byte per triangle")
+        h = _vp()
+        _check(self.lib.sb_mesh_uncut(self.h, _ptr(cf), vertex_offset, triangle_offset, C.byref(h)))
+        return Uncut(self, h)
+
     def classify_faces_device(self, target: "Mesh", d_inside_ptr: int, begin=0, end=None):
         end = self.num_triangles if end is None else end
         _check(self.lib.sb_classify_faces_device(self.h, target.h, begin, end, _vp(d_inside_ptr)))
@@ -365,6 +385,12 @@ class Isect:
         _check(self.lib.sb_isect_face_flags(self.h, _ptr(fa), _ptr(fb)))
         return fa, fb
 
+    def uncut(self, which: int, vertex_offset=0, triangle_offset=0) -> "Uncut":
+        """sb_isect_uncut: the faces of mesh `which` the intersection left alone + their half-edge map."""
+        h = _vp()
+        _check(self.lib.sb_isect_uncut(self.h, which, vertex_offset, triangle_offset, C.byref(h)))
+        return Uncut(self.a if which == 0 else self.b, h)
+
     def device_ptrs(self, candidates=True):
         """Device pointers of the results.  candidates=False leaves the candidate keys alone (asking
         for them orders the full candidate list on the device, which is otherwise done lazily)."""
@@ -374,3 +400,51 @@ class Isect:
                                              C.byref(hs), C.byref(fa), C.byref(fb)))
         return dict(cand_keys=ck.value or 0, bits_b=bits.value, hit_ab=ha.value or 0, hit_seg=hs.value or 0,
                     flags_a=fa.value or 0, flags_b=fb.value or 0)
+
+
+class Uncut:
+    """Uncut triangles + half-edge map of one mesh (sb_uncut): what
+    SolidBoolean::addUnintersectedTriangles leaves behind (reference src/solidboolean.cpp:250-286)."""
+
+    def __init__(self, mesh: Mesh, h):
+        self.mesh, self.lib, self.h = mesh, mesh.lib, h
+        nt, nh, ok = _sz(0), _sz(0), C.c_int(0)
+        _check(self.lib.sb_uncut_counts(h, C.byref(nt), C.byref(nh), C.byref(ok)))
+        self.num_triangles, self.num_half_edges, self.ok = int(nt.value), int(nh.value), bool(ok.value)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.mesh.ctx, "h", None):
+            self.lib.sb_uncut_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def triangles(self):
+        """-> face [n] (original face id of each new triangle), tri3 [n,3] (shifted index triples)"""
+        face = np.zeros(self.num_triangles, np.uint32)
+        tri3 = np.zeros((self.num_triangles, 3), np.uint32)
+        _check(self.lib.sb_uncut_triangles(self.h, _ptr(face), _ptr(tri3)))
+        return face, tri3
+
+    def half_edges(self):
+        """-> keys [m] ascending ((first << 32) | second), owner [m] (new triangle index)"""
+        keys = np.zeros(self.num_half_edges, np.uint64)
+        owner = np.zeros(self.num_half_edges, np.uint32)
+        _check(self.lib.sb_uncut_half_edges(self.h, _ptr(keys), _ptr(owner)))
+        return keys, owner
+
+    def adjacency(self):
+        """-> adj [n,3]: triangle across edge k of new triangle j, or -1"""
+        adj = np.full((self.num_triangles, 3), -1, np.int32)
+        if self.num_triangles:
+            _check(self.lib.sb_uncut_adjacency(self.h, _ptr(adj)))
+        return adj
+
+    def device_ptrs(self):
+        p = [_vp() for _ in range(5)]
+        _check(self.lib.sb_uncut_device_ptrs(self.h, *[C.byref(x) for x in p]))
+        return dict(zip(("face", "tri3", "keys", "owner", "adj"), [x.value or 0 for x in p]))

@@ -51,6 +51,8 @@ struct DeviceScalars { // device counters of one lane (128-byte slots)
     int err;
     int pad;
     unsigned long long paths[5]; // predicate exit histogram (TriTriPath)
+    unsigned int uncutTotal;     // sb_*_uncut: uncut faces
+    unsigned int heRepeat;       // ... first refused half-edge insertion (ordinal), UINT_MAX = none
 };
 static_assert(sizeof(DeviceScalars) <= 128, "lane slot too small");
 
@@ -69,7 +71,7 @@ struct sb_context {
     };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> freeEvents;
-    float acc[SB_STAGE_COUNT] = {0, 0, 0, 0};
+    float acc[SB_STAGE_COUNT] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t t0 = nullptr;      // timing reference (recorded at reset)
     cudaEvent_t orderEvent = nullptr; // orders per-mesh streams behind the context stream
     // scratch
@@ -151,6 +153,22 @@ struct sb_isect {
     std::vector<void *> owned; // stream-ordered allocations to release
     bool candSorted = false;   // candidates are ordered lazily, when somebody asks for them
     bool noSort = false;
+};
+
+// Result of sb_*_uncut (sb_halfedge.cu): all arrays device-resident, sized for the nTri uncut faces.
+struct sb_uncut {
+    sb_context *ctx = nullptr;
+    const sb_mesh *mesh = nullptr;
+    uint32_t nTri = 0;            // uncut faces
+    uint32_t vertexOffset = 0, triangleOffset = 0;
+    uint32_t repeatOrd = 0xffffffffu; // ordinal (3 * rank + edge) of the first refused insertion
+    uint32_t *face = nullptr;     // nTri
+    uint32_t *tri3 = nullptr;     // 3 nTri shifted index triples
+    unsigned long long *keys = nullptr; // 3 nTri reference-format keys, ascending
+    uint32_t *owner = nullptr;    // 3 nTri
+    uint32_t *ords = nullptr;     // 3 nTri insertion ordinal of each sorted entry
+    int32_t *adj = nullptr;       // 3 nTri, indexed by ordinal
+    std::vector<void *> owned;
 };
 
 namespace {
@@ -1414,6 +1432,249 @@ int sb_isect_device_ptrs(const sb_isect *xc, void **cand_keys, unsigned *bits_b,
     if (hit_seg) *hit_seg = x->hitSeg;
     if (flagsA) *flagsA = x->flagsA;
     if (flagsB) *flagsB = x->flagsB;
+    return SB_OK;
+}
+
+// ---- uncut triangles + half-edge map (sb_halfedge.cu) ---------------------------------
+
+void sb_uncut_destroy(sb_uncut *u)
+{
+    if (!u)
+        return;
+    DeviceGuard g(u->ctx->device);
+    for (void *p : u->owned)
+        cudaFreeAsync(p, u->ctx->stream);
+    delete u;
+}
+
+// dCut: device flags (nT bytes, 8-byte aligned) or null; everything on the context stream
+static int uncut_run(const sb_mesh *mesh, const uint8_t *dCut, size_t vertexOffset, size_t triangleOffset, sb_uncut **out)
+{
+    sb_context *c = mesh->ctx;
+    const MeshDev &d = mesh->d;
+    if (vertexOffset + d.nV > 0xffffffffull || triangleOffset + d.nT > 0x7fffffffull)
+        return fail(SB_ERR_INVALID, "vertex / triangle offset out of the 32-bit index range");
+    sb_uncut *u = new (std::nothrow) sb_uncut;
+    if (!u)
+        return fail(SB_ERR_NOMEM, "out of host memory");
+    u->ctx = c;
+    u->mesh = mesh;
+    u->vertexOffset = (uint32_t)vertexOffset;
+    u->triangleOffset = (uint32_t)triangleOffset;
+    int r = SB_OK;
+    auto bail = [&](int code) {
+        sb_uncut_destroy(u);
+        return code;
+    };
+#define SB_TRY(expr)          \
+    do {                      \
+        r = (expr);           \
+        if (r)                \
+            return bail(r);   \
+    } while (0)
+#define SB_CUDA_X(expr)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return bail(fail(SB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+    StageTimer timer(c, SB_STAGE_HALFEDGE);
+    uint32_t *tileScratch = nullptr;
+    SB_TRY(alloc_async(c, &tileScratch, sbk_uncut_tiles(d.nT), &u->owned));
+    SB_CUDA_X(cudaMemsetAsync(&c->dScalars->heRepeat, 0xff, sizeof(unsigned int), c->stream));
+    SB_CUDA_X(sbk_uncut_count(c->stream, dCut, d.nT, tileScratch, &c->dScalars->uncutTotal, c->lc));
+    // the number of uncut faces sizes everything that follows (one 128-byte read-back)
+    SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA_X(cudaStreamSynchronize(c->stream));
+    u->nTri = c->hScalars->uncutTotal;
+    const size_t n = 3 * (size_t)u->nTri;
+    if (n) {
+        const unsigned bitsV = bits_for(vertexOffset + d.nV);
+        unsigned long long *k0 = nullptr, *k1 = nullptr, *sk = nullptr;
+        uint32_t *o0 = nullptr, *o1 = nullptr, *so = nullptr;
+        SB_TRY(alloc_async(c, &u->face, u->nTri, &u->owned));
+        SB_TRY(alloc_async(c, &u->tri3, n, &u->owned));
+        SB_TRY(alloc_async(c, &k0, n, &u->owned));
+        SB_TRY(alloc_async(c, &k1, n, &u->owned));
+        SB_TRY(alloc_async(c, &o0, n, &u->owned));
+        SB_TRY(alloc_async(c, &o1, n, &u->owned));
+        SB_TRY(alloc_async(c, &u->owner, n, &u->owned));
+        SB_TRY(alloc_async(c, &u->adj, n, &u->owned));
+        SB_TRY(ensure_radix_ws(c, n));
+        SB_CUDA_X(sbk_uncut_emit(c->stream, dCut, d.tri, d.nT, tileScratch, u->vertexOffset, bitsV, u->face, u->tri3, k0, o0,
+            c->lc));
+        SB_CUDA_X(sbk_sort_keys(c->stream, k0, k1, o0, o1, n, 0, (int)(2 * bitsV), c->radixWs, c->smCount, &sk, &so, c->lc));
+        // the reference-format keys go to whichever key buffer the sort left free
+        u->keys = sk == k0 ? k1 : k0;
+        u->ords = so;
+        SB_CUDA_X(sbk_halfedge_link(c->stream, sk, so, (uint32_t)n, bitsV, u->triangleOffset, u->keys, u->owner, u->adj,
+            &c->dScalars->heRepeat, c->lc));
+        SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA_X(cudaStreamSynchronize(c->stream));
+        u->repeatOrd = c->hScalars->heRepeat;
+    }
+#undef SB_TRY
+#undef SB_CUDA_X
+    *out = u;
+    return SB_OK;
+}
+
+int sb_isect_uncut(const sb_isect *x, int which, size_t vertex_offset, size_t triangle_offset, sb_uncut **out)
+{
+    if (!x || !out || (which != 0 && which != 1))
+        return fail(SB_ERR_INVALID, "null isect / out, or which not 0 / 1");
+    *out = nullptr;
+    DeviceGuard g(x->ctx->device);
+    return uncut_run(which == 0 ? x->A : x->B, which == 0 ? x->flagsA : x->flagsB, vertex_offset, triangle_offset, out);
+}
+
+int sb_mesh_uncut(const sb_mesh *mesh, const uint8_t *cut_flags, size_t vertex_offset, size_t triangle_offset, sb_uncut **out)
+{
+    if (!mesh || !out)
+        return fail(SB_ERR_INVALID, "null mesh or out");
+    *out = nullptr;
+    sb_context *c = mesh->ctx;
+    DeviceGuard g(c->device);
+    use_mesh(c, mesh); // the geometry upload ran on the mesh stream
+    uint8_t *dCut = nullptr;
+    if (cut_flags && mesh->d.nT) {
+        int r = alloc_async(c, &dCut, mesh->d.nT, nullptr);
+        if (r)
+            return r;
+        SB_CUDA(cudaMemcpyAsync(dCut, cut_flags, mesh->d.nT, cudaMemcpyHostToDevice, c->stream));
+    }
+    int r = uncut_run(mesh, dCut, vertex_offset, triangle_offset, out);
+    if (dCut)
+        cudaFreeAsync(dCut, c->stream);
+    return r;
+}
+
+// what the reference leaves behind: everything, or the state at the refused insertion
+static inline size_t uncut_tri_count(const sb_uncut *u) { return u->repeatOrd == 0xffffffffu ? u->nTri : u->repeatOrd / 3 + 1; }
+
+int sb_uncut_counts(const sb_uncut *u, size_t *n_triangles, size_t *n_half_edges, int *ok)
+{
+    if (!u)
+        return fail(SB_ERR_INVALID, "uncut is null");
+    const bool good = u->repeatOrd == 0xffffffffu;
+    if (n_triangles)
+        *n_triangles = uncut_tri_count(u);
+    if (n_half_edges)
+        *n_half_edges = good ? 3 * (size_t)u->nTri : u->repeatOrd;
+    if (ok)
+        *ok = good ? 1 : 0;
+    return SB_OK;
+}
+
+int sb_uncut_triangles(const sb_uncut *u, uint32_t *face, uint32_t *tri3)
+{
+    if (!u)
+        return fail(SB_ERR_INVALID, "uncut is null");
+    sb_context *c = u->ctx;
+    DeviceGuard g(c->device);
+    const size_t n = uncut_tri_count(u);
+    if (!n)
+        return SB_OK;
+    if (face)
+        SB_CUDA(cudaMemcpyAsync(face, u->face, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (tri3)
+        SB_CUDA(cudaMemcpyAsync(tri3, u->tri3, 12 * n, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+// Rare path (the reference returned false): the arrays hold all uncut faces; keep the entries
+// inserted before the refused one.  Host-side filter of the downloaded arrays, order preserved.
+static int uncut_truncated(const sb_uncut *u, std::vector<unsigned long long> &keys, std::vector<uint32_t> &owner)
+{
+    sb_context *c = u->ctx;
+    const size_t n = 3 * (size_t)u->nTri;
+    std::vector<unsigned long long> k(n);
+    std::vector<uint32_t> o(n), ord(n);
+    SB_CUDA(cudaMemcpyAsync(k.data(), u->keys, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaMemcpyAsync(o.data(), u->owner, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaMemcpyAsync(ord.data(), u->ords, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    keys.clear();
+    owner.clear();
+    for (size_t i = 0; i < n; ++i)
+        if (ord[i] < u->repeatOrd) {
+            keys.push_back(k[i]);
+            owner.push_back(o[i]);
+        }
+    return SB_OK;
+}
+
+int sb_uncut_half_edges(const sb_uncut *u, uint64_t *keys, uint32_t *owner)
+{
+    if (!u)
+        return fail(SB_ERR_INVALID, "uncut is null");
+    sb_context *c = u->ctx;
+    DeviceGuard g(c->device);
+    const size_t n = 3 * (size_t)u->nTri;
+    if (!n)
+        return SB_OK;
+    if (u->repeatOrd != 0xffffffffu) {
+        std::vector<unsigned long long> k;
+        std::vector<uint32_t> o;
+        int r = uncut_truncated(u, k, o);
+        if (r)
+            return r;
+        if (keys && !k.empty())
+            memcpy(keys, k.data(), 8 * k.size());
+        if (owner && !o.empty())
+            memcpy(owner, o.data(), 4 * o.size());
+        return SB_OK;
+    }
+    if (keys)
+        SB_CUDA(cudaMemcpyAsync(keys, u->keys, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (owner)
+        SB_CUDA(cudaMemcpyAsync(owner, u->owner, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_uncut_adjacency(const sb_uncut *u, int32_t *adj3)
+{
+    if (!u || !adj3)
+        return fail(SB_ERR_INVALID, "null uncut or output");
+    sb_context *c = u->ctx;
+    DeviceGuard g(c->device);
+    if (!u->nTri)
+        return SB_OK;
+    if (u->repeatOrd != 0xffffffffu) {
+        // look the opposite half-edges up in the truncated map, as buildFaceGroups would
+        std::vector<unsigned long long> k;
+        std::vector<uint32_t> o;
+        int r = uncut_truncated(u, k, o);
+        if (r)
+            return r;
+        const size_t nt = uncut_tri_count(u);
+        std::vector<uint32_t> t(3 * nt);
+        SB_CUDA(cudaMemcpyAsync(t.data(), u->tri3, 12 * nt, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t j = 0; j < nt; ++j)
+            for (int e = 0; e < 3; ++e) {
+                unsigned long long want = ((unsigned long long)t[3 * j + (e + 1) % 3] << 32) | t[3 * j + e];
+                auto it = std::lower_bound(k.begin(), k.end(), want);
+                adj3[3 * j + e] = (it != k.end() && *it == want) ? (int32_t)o[it - k.begin()] : -1;
+            }
+        return SB_OK;
+    }
+    SB_CUDA(cudaMemcpyAsync(adj3, u->adj, 12 * (size_t)u->nTri, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_uncut_device_ptrs(const sb_uncut *u, void **face, void **tri3, void **keys, void **owner, void **adj3)
+{
+    if (!u)
+        return fail(SB_ERR_INVALID, "uncut is null");
+    if (face) *face = u->face;
+    if (tri3) *tri3 = u->tri3;
+    if (keys) *keys = u->keys;
+    if (owner) *owner = u->owner;
+    if (adj3) *adj3 = u->adj;
     return SB_OK;
 }
 

@@ -97,6 +97,17 @@ cudaError_t sbk_sort_keys(cudaStream_t s, unsigned long long *keys, unsigned lon
     uint32_t *valsTmp, size_t n, int beginBit, int endBit, uint32_t *radixWs, int smCount,
     unsigned long long **outKeys, uint32_t **outVals, LaunchCounter &lc);
 
+// sb_halfedge.cu -- uncut triangles + half-edge map (SolidBoolean::addUnintersectedTriangles)
+uint32_t sbk_uncut_tiles(uint32_t nT);
+cudaError_t sbk_uncut_count(cudaStream_t s, const uint8_t *cut /* nT bytes or null */, uint32_t nT, uint32_t *tileScratch,
+    uint32_t *total, LaunchCounter &lc);
+cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *tri, uint32_t nT, const uint32_t *tileScratch,
+    uint32_t vertexOffset, unsigned bitsV, uint32_t *face, uint32_t *tri3, unsigned long long *keys, uint32_t *ords,
+    LaunchCounter &lc);
+cudaError_t sbk_halfedge_link(cudaStream_t s, const unsigned long long *sortedKeys, const uint32_t *sortedOrds, uint32_t n,
+    unsigned bitsV, uint32_t triangleOffset, unsigned long long *refKeys, uint32_t *owner, int32_t *adj,
+    uint32_t *firstRepeat, LaunchCounter &lc);
+
 // sb_classify.cu
 struct ClassifyArgs {
     // query points: either explicit (pts != null, AoS 3*Q, processed in given order)

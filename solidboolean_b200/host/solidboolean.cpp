@@ -46,34 +46,80 @@ size_t SolidBoolean::weldPoint(const Vector3 &p)
     return ins.first->second;
 }
 
+void SolidBoolean::HalfEdgeMap::adopt(std::vector<uint64_t> &&sortedKeys, std::vector<uint32_t> &&owners)
+{
+    m_keys = std::move(sortedKeys);
+    m_owners = std::move(owners);
+    m_added.clear();
+}
+
+bool SolidBoolean::HalfEdgeMap::find(uint64_t key, size_t &triangle) const
+{
+    auto it = std::lower_bound(m_keys.begin(), m_keys.end(), key);
+    if (it != m_keys.end() && *it == key) {
+        triangle = m_owners[it - m_keys.begin()];
+        return true;
+    }
+    auto added = m_added.find(key);
+    if (added == m_added.end())
+        return false;
+    triangle = added->second;
+    return true;
+}
+
+bool SolidBoolean::HalfEdgeMap::insert(uint64_t key, size_t triangle)
+{
+    size_t existing;
+    if (find(key, existing))
+        return false;
+    m_added.insert({key, triangle});
+    return true;
+}
+
 bool SolidBoolean::appendTriangle(size_t a, size_t b, size_t c, HalfEdgeMap &halfEdges)
 {
     size_t index = m_newTriangles.size();
     m_newTriangles.push_back({a, b, c});
     bool ok = true;
-    ok &= halfEdges.insert({halfEdgeKey(a, b), index}).second;
-    ok &= halfEdges.insert({halfEdgeKey(b, c), index}).second;
-    ok &= halfEdges.insert({halfEdgeKey(c, a), index}).second;
+    ok &= halfEdges.insert(halfEdgeKey(a, b), index);
+    ok &= halfEdges.insert(halfEdgeKey(b, c), index);
+    ok &= halfEdges.insert(halfEdgeKey(c, a), index);
     return ok;
 }
 
-// triangles the intersection does not touch are taken over as they are
-// (reference addUnintersectedTriangles, src/solidboolean.cpp:250-286)
-bool SolidBoolean::copyUncutTriangles(const SolidMesh *mesh, const std::unordered_set<size_t> &cut, size_t vertexOffset,
-    HalfEdgeMap &halfEdges)
+// Triangles the intersection does not touch are taken over as they are (reference
+// addUnintersectedTriangles, src/solidboolean.cpp:250-286).  GPU: sb_isect_uncut compacts
+// them, sorts their half-edge keys and reports a repeated half-edge exactly where the
+// reference's map insert would have refused it.
+bool SolidBoolean::copyUncutTriangles(const void *isect, int which, size_t vertexOffset, HalfEdgeMap &halfEdges)
 {
-    const auto &triangles = *mesh->triangles();
-    bool ok = true;
-    for (size_t i = 0; i < triangles.size(); ++i) {
-        if (cut.count(i))
-            continue;
-        const auto &t = triangles[i];
-        if (!appendTriangle(t[0] + vertexOffset, t[1] + vertexOffset, t[2] + vertexOffset, halfEdges)) {
-            std::cout << "Found repeated halfedge:" << t[0] + vertexOffset << "," << t[1] + vertexOffset << std::endl;
-            ok = false;
-        }
+    sb_uncut *uncut = nullptr;
+    if (sb_isect_uncut(static_cast<const sb_isect *>(isect), which, vertexOffset, m_newTriangles.size(), &uncut) != SB_OK) {
+        std::cout << "addUnintersectedTriangles failed: " << sb_last_error() << std::endl;
+        return false;
     }
-    return ok;
+    size_t triangleCount = 0, halfEdgeCount = 0;
+    int ok = 0;
+    sb_uncut_counts(uncut, &triangleCount, &halfEdgeCount, &ok);
+    std::vector<uint32_t> triples(3 * triangleCount), owners(halfEdgeCount);
+    std::vector<uint64_t> keys(halfEdgeCount);
+    int rc = sb_uncut_triangles(uncut, nullptr, triples.data());
+    if (rc == SB_OK)
+        rc = sb_uncut_half_edges(uncut, keys.data(), owners.data());
+    sb_uncut_destroy(uncut);
+    if (rc != SB_OK) {
+        std::cout << "addUnintersectedTriangles failed: " << sb_last_error() << std::endl;
+        return false;
+    }
+    m_newTriangles.reserve(m_newTriangles.size() + triangleCount);
+    for (size_t i = 0; i < triangleCount; ++i)
+        m_newTriangles.push_back({triples[3 * i], triples[3 * i + 1], triples[3 * i + 2]});
+    if (!ok && triangleCount) {
+        const auto &last = m_newTriangles.back();
+        std::cout << "Found repeated halfedge:" << last[0] << "," << last[1] << std::endl;
+    }
+    halfEdges.adopt(std::move(keys), std::move(owners));
+    return ok != 0;
 }
 
 // reference reTriangulate lambda, src/solidboolean.cpp:352-407
@@ -176,9 +222,9 @@ void SolidBoolean::growFaceGroups(const std::vector<std::vector<size_t>> &loops,
             for (int side = 0; side < 2; ++side) {
                 uint64_t key = side == 0 ? halfEdgeKey(a, b) : halfEdgeKey(b, a);
                 fence.insert({key, groupIndex + side});
-                auto he = halfEdges.find(key);
-                if (he != halfEdges.end())
-                    queue.push_back({he->second, groupIndex + side});
+                size_t owner;
+                if (halfEdges.find(key, owner))
+                    queue.push_back({owner, groupIndex + side});
             }
         }
         groupIndex += 2;
@@ -197,9 +243,9 @@ void SolidBoolean::growFaceGroups(const std::vector<std::vector<size_t>> &loops,
                 size_t a = t[i], b = t[(i + 1) % 3];
                 if (!fence.insert({halfEdgeKey(a, b), item.second}).second)
                     continue;
-                auto opposite = halfEdges.find(halfEdgeKey(b, a));
-                if (opposite != halfEdges.end())
-                    queue.push_back({opposite->second, item.second});
+                size_t opposite;
+                if (halfEdges.find(halfEdgeKey(b, a), opposite))
+                    queue.push_back({opposite, item.second});
             }
         }
     };
@@ -274,19 +320,16 @@ bool SolidBoolean::combine()
     m_hitPairs.resize(2 * hitCount);
     m_hitSegments.resize(6 * hitCount);
     int rc = sb_isect_hits(isect, m_hitPairs.data(), m_hitSegments.data());
-    sb_isect_destroy(isect);
     if (rc != SB_OK) {
+        sb_isect_destroy(isect);
         std::cout << "combine failed: " << sb_last_error() << std::endl;
         return false;
     }
     std::map<size_t, CutTriangle> firstCuts, secondCuts; // ordered: deterministic output
-    std::unordered_set<size_t> firstCutFaces, secondCutFaces;
     for (size_t h = 0; h < hitCount; ++h) {
         size_t a = m_hitPairs[2 * h], b = m_hitPairs[2 * h + 1];
         const double *s = &m_hitSegments[6 * h];
         Vector3 source(s[0], s[1], s[2]), target(s[3], s[4], s[5]);
-        firstCutFaces.insert(a);
-        secondCutFaces.insert(b);
         firstCuts[a].addSegment(source, target);
         secondCuts[b].addSegment(source, target);
     }
@@ -300,13 +343,14 @@ bool SolidBoolean::combine()
     m_newVertices.insert(m_newVertices.end(), m_secondMesh->vertices()->begin(), m_secondMesh->vertices()->end());
     HalfEdgeMap firstHalfEdges, secondHalfEdges;
     size_t firstStart = m_newTriangles.size();
-    if (!copyUncutTriangles(m_firstMesh, firstCutFaces, 0, firstHalfEdges))
+    if (!copyUncutTriangles(isect, 0, 0, firstHalfEdges))
         std::cout << "Add first mesh remaining triangles failed" << std::endl;
     size_t firstCount = m_newTriangles.size() - firstStart;
     size_t secondStart = m_newTriangles.size();
-    if (!copyUncutTriangles(m_secondMesh, secondCutFaces, firstVertexCount, secondHalfEdges))
+    if (!copyUncutTriangles(isect, 1, firstVertexCount, secondHalfEdges))
         std::cout << "Add second mesh remaining triangles failed" << std::endl;
     size_t secondCount = m_newTriangles.size() - secondStart;
+    sb_isect_destroy(isect);
     benchEnd_addUnintersectedTriangles = now();
 
     benchBegin_reTriangulate = now();

@@ -52,13 +52,26 @@ private:
         size_t addPoint(const Vector3 &p);
         void addSegment(const Vector3 &a, const Vector3 &b);
     };
-    typedef std::unordered_map<uint64_t, size_t> HalfEdgeMap;
+    // half-edge (from << 32 | to) -> triangle.  The uncut triangles' entries arrive from the GPU
+    // as one array sorted by key (sb_uncut_half_edges: lookup = binary search); the pieces of
+    // retriangulated faces are added on the host behind it.
+    class HalfEdgeMap
+    {
+    public:
+        void adopt(std::vector<uint64_t> &&sortedKeys, std::vector<uint32_t> &&owners);
+        bool insert(uint64_t key, size_t triangle); // false: the half-edge already exists
+        bool find(uint64_t key, size_t &triangle) const;
+    private:
+        std::vector<uint64_t> m_keys;
+        std::vector<uint32_t> m_owners;
+        std::unordered_map<uint64_t, size_t> m_added;
+    };
     typedef std::unordered_map<size_t, std::unordered_set<size_t>> EdgeGraph;
 
     static uint64_t halfEdgeKey(size_t from, size_t to) { return ((uint64_t)from << 32) | (uint64_t)to; }
     size_t weldPoint(const Vector3 &p);
     bool appendTriangle(size_t a, size_t b, size_t c, HalfEdgeMap &halfEdges);
-    bool copyUncutTriangles(const SolidMesh *mesh, const std::unordered_set<size_t> &cut, size_t vertexOffset, HalfEdgeMap &halfEdges);
+    bool copyUncutTriangles(const void *isect, int which, size_t vertexOffset, HalfEdgeMap &halfEdges);
     bool retriangulateCutTriangles(const std::map<size_t, CutTriangle> &cuts, const SolidMesh *mesh, size_t vertexOffset,
         HalfEdgeMap &halfEdges, EdgeGraph &loopEdges);
     bool traceLoops(const EdgeGraph &edges, std::vector<std::vector<size_t>> &loops);

@@ -74,3 +74,42 @@ def load_synthetic(golden_synthetic, name):
     out = {k: golden_synthetic[name + "__" + k] for k in
            ("pairs", "ret", "coplanar", "hit", "seg_hits", "inside_a", "per_axis_a", "inside_b", "per_axis_b")}
     return a, b, out
+
+
+def uncut_inputs():
+    """name -> (mesh a, mesh b, cut flags a, cut flags b): the bundled cases and the synthetic
+    pairs with the faces their (golden) hit pairs touch, plus crafted meshes."""
+    from solidboolean_b200 import meshgen
+    cases = np.load(os.path.join(GOLDEN, "cases.npz"))
+    syn = np.load(os.path.join(GOLDEN, "synthetic.npz"))
+    out = {}
+
+    def flags(n, ids):
+        f = np.zeros(n, np.uint8)
+        f[ids] = 1
+        return f
+
+    for case in CASES:
+        k = case.replace("-", "_")
+        a = (cases[k + "__xyz_a"].astype(np.float64), cases[k + "__tri_a"])
+        b = (cases[k + "__xyz_b"].astype(np.float64), cases[k + "__tri_b"])
+        hp = cases[k + "__pairs"][cases[k + "__hit"].astype(bool)]
+        out[case] = (a, b, flags(len(a[1]), hp[:, 0]), flags(len(b[1]), hp[:, 1]))
+    for name, make in synthetic_specs().items():
+        a, b = make()
+        hp = syn[name + "__pairs"][syn[name + "__hit"].astype(bool)]
+        out[name] = (a, b, flags(len(a[1]), hp[:, 0]), flags(len(b[1]), hp[:, 1]))
+    # crafted: a triangle present twice (the reference stops at the copy), an open sheet, a
+    # flipped triangle (its half-edges repeat its neighbours'), nothing cut, everything cut
+    ico = meshgen.icosphere(2)
+    tor = meshgen.torus(16, 8)
+    dup = (ico[0], np.concatenate([ico[1][:40], ico[1][7:8], ico[1][40:]]))
+    out["repeat_first"] = (dup, tor, None, None)
+    out["repeat_second"] = (tor, dup, None, flags(len(dup[1]), [3, 4, 5]))
+    flipped = ico[1].copy()
+    flipped[100] = flipped[100][::-1]
+    out["flipped_face"] = ((ico[0], flipped), tor, flags(len(flipped), [0, 1]), None)
+    sheet = meshgen.slab(6, 1.0, 0.2)
+    out["open_sheet"] = ((sheet[0], sheet[1][: len(sheet[1]) // 3]), tor, None, flags(len(tor[1]), np.arange(0, len(tor[1]), 5)))
+    out["all_cut"] = (ico, tor, np.ones(len(ico[1]), np.uint8), np.ones(len(tor[1]), np.uint8))
+    return out

@@ -19,6 +19,8 @@ void sbo_predicate_pairs(const double *xyzA, const uint32_t *triA, const double 
     const uint32_t *pairs, size_t n, int8_t *ret, int8_t *coplanar, uint8_t *hit, double *seg);
 void sbo_classify(const double *xyz, const uint32_t *tri, size_t nT, const double *pts, size_t q, uint8_t *inside,
     uint8_t *perAxis, uint64_t *candCount);
+int sbo_uncut_half_edges(const uint32_t *tri, size_t nT, const uint8_t *cut, uint64_t vertexOffset, uint64_t triangleOffset,
+    uint32_t *outFace, size_t *nTriOut, uint64_t *outKeys, uint32_t *outOwner, size_t *nKeysOut);
 }
 
 struct sb_context { int dummy; };
@@ -27,9 +29,15 @@ struct sb_mesh {
     std::vector<uint32_t> tri;
 };
 struct sb_isect {
+    const sb_mesh *A = nullptr, *B = nullptr;
     size_t nCand = 0;
     std::vector<uint32_t> hitAB;
     std::vector<double> hitSeg;
+};
+struct sb_uncut {
+    int ok = 1;
+    std::vector<uint32_t> face, tri3, owner;
+    std::vector<uint64_t> keys;
 };
 
 extern "C" {
@@ -64,6 +72,8 @@ int sb_intersect(const sb_mesh *A, const sb_mesh *B, unsigned, sb_isect **out)
         sbo_predicate_pairs(A->xyz.data(), A->tri.data(), B->xyz.data(), B->tri.data(), pairs, n, nullptr, nullptr,
             hit.data(), seg.data());
     sb_isect *x = new sb_isect;
+    x->A = A;
+    x->B = B;
     x->nCand = n;
     for (size_t i = 0; i < n; ++i)
         if (hit[i]) {
@@ -86,6 +96,49 @@ int sb_isect_hits(const sb_isect *x, uint32_t *ab, double *seg)
 {
     if (ab && !x->hitAB.empty()) std::memcpy(ab, x->hitAB.data(), 4 * x->hitAB.size());
     if (seg && !x->hitSeg.empty()) std::memcpy(seg, x->hitSeg.data(), 8 * x->hitSeg.size());
+    return SB_OK;
+}
+int sb_isect_uncut(const sb_isect *x, int which, size_t vertexOffset, size_t triangleOffset, sb_uncut **out)
+{
+    const sb_mesh *m = which == 0 ? x->A : x->B;
+    size_t nT = m->tri.size() / 3;
+    std::vector<uint8_t> cut(nT + 1, 0);
+    for (size_t h = 0; h < x->hitAB.size() / 2; ++h)
+        cut[x->hitAB[2 * h + which]] = 1;
+    sb_uncut *u = new sb_uncut;
+    u->face.resize(nT + 1);
+    u->keys.resize(3 * nT + 1);
+    u->owner.resize(3 * nT + 1);
+    size_t nTri = 0, nKeys = 0;
+    u->ok = sbo_uncut_half_edges(m->tri.data(), nT, cut.data(), vertexOffset, triangleOffset, u->face.data(), &nTri,
+        u->keys.data(), u->owner.data(), &nKeys);
+    u->face.resize(nTri);
+    u->keys.resize(nKeys);
+    u->owner.resize(nKeys);
+    for (size_t j = 0; j < nTri; ++j)
+        for (int k = 0; k < 3; ++k)
+            u->tri3.push_back(m->tri[3 * (size_t)u->face[j] + k] + (uint32_t)vertexOffset);
+    *out = u;
+    return SB_OK;
+}
+void sb_uncut_destroy(sb_uncut *u) { delete u; }
+int sb_uncut_counts(const sb_uncut *u, size_t *nTri, size_t *nKeys, int *ok)
+{
+    if (nTri) *nTri = u->face.size();
+    if (nKeys) *nKeys = u->keys.size();
+    if (ok) *ok = u->ok;
+    return SB_OK;
+}
+int sb_uncut_triangles(const sb_uncut *u, uint32_t *face, uint32_t *tri3)
+{
+    if (face && !u->face.empty()) std::memcpy(face, u->face.data(), 4 * u->face.size());
+    if (tri3 && !u->tri3.empty()) std::memcpy(tri3, u->tri3.data(), 4 * u->tri3.size());
+    return SB_OK;
+}
+int sb_uncut_half_edges(const sb_uncut *u, uint64_t *keys, uint32_t *owner)
+{
+    if (keys && !u->keys.empty()) std::memcpy(keys, u->keys.data(), 8 * u->keys.size());
+    if (owner && !u->owner.empty()) std::memcpy(owner, u->owner.data(), 4 * u->owner.size());
     return SB_OK;
 }
 int sb_classify(const sb_mesh *t, const double *pts, size_t Q, uint8_t *inside, uint8_t *per_axis)

@@ -1,0 +1,142 @@
+"""GPU (B200): uncut triangles + half-edge map (sb_isect_uncut / sb_mesh_uncut) against the
+oracle restatement of SolidBoolean::addUnintersectedTriangles (reference
+src/solidboolean.cpp:250-286) and the committed reference fixtures (tests/golden/uncut.json).
+Index work: everything bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import solidboolean_b200 as sb
+from conftest import GOLDEN, uncut_inputs
+from oracle import fnv1a64
+from solidboolean_b200 import meshgen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sb.Context(0)
+    yield c
+    c.close()
+
+
+def _h(a, dt):
+    return "%016x" % fnv1a64(np.ascontiguousarray(a).astype(dt).tobytes())
+
+
+def check_uncut(u, ref, tri, vertex_offset):
+    """u: sb.Uncut; ref: oracle.uncut_half_edges(...) of the same inputs."""
+    assert (u.ok, u.num_triangles, u.num_half_edges) == (ref["ok"], len(ref["face"]), len(ref["keys"]))
+    face, tri3 = u.triangles()
+    assert np.array_equal(face, ref["face"])
+    assert np.array_equal(tri3, np.asarray(tri, np.uint32)[ref["face"]] + np.uint32(vertex_offset))
+    keys, owner = u.half_edges()
+    assert np.array_equal(keys, ref["keys"]) and np.array_equal(owner, ref["owner"])
+    assert np.array_equal(u.adjacency(), ref["adj"])
+    return keys, owner
+
+
+def test_uncut_fixtures_vs_reference_and_oracle(ctx, oracle):
+    with open(os.path.join(GOLDEN, "uncut.json")) as f:
+        golden = json.load(f)
+    for name, (a, b, ca, cb) in uncut_inputs().items():
+        ma, mb = ctx.mesh(*a, build=False), ctx.mesh(*b, build=False)   # the geometry is all this stage reads
+        ua = ma.uncut(ca, 0, 0)
+        ub = mb.uncut(cb, len(a[0]), ua.num_triangles)
+        ra = oracle.uncut_half_edges(a[1], ca, 0, 0)
+        rb = oracle.uncut_half_edges(b[1], cb, len(a[0]), len(ra["face"]))
+        g = golden[name]
+        for u, r, m, voff, gg in ((ua, ra, a, 0, g["a"]), (ub, rb, b, len(a[0]), g["b"])):
+            keys, owner = check_uncut(u, r, m[1], voff)
+            # ... and straight against the numbers the unmodified reference produced
+            assert (u.ok, u.num_triangles, u.num_half_edges) == (gg["ok"], gg["n_triangles"], gg["n_half_edges"]), name
+            assert (_h(keys, "<u8"), _h(owner, "<u4")) == (gg["keys_hash"], gg["owner_hash"]), name
+            assert _h(u.adjacency(), "<i4") == gg["adj_hash"], name
+        ua.close(); ub.close(); ma.close(); mb.close()
+
+
+def test_uncut_from_intersection_flags(ctx, oracle):
+    """sb_isect_uncut takes the cut faces from the intersection's own device flags
+    (m_firstIntersectedFaces / m_secondIntersectedFaces, reference src/solidboolean.cpp:318-319)."""
+    a, b = meshgen.config_c2()
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x = ma.intersect(mb)
+    fa, fb = x.face_flags()
+    hab, _ = x.hits()
+    assert int(fa.sum()) == len(np.unique(hab[:, 0])) and int(fb.sum()) == len(np.unique(hab[:, 1]))
+    ua = x.uncut(0, 0, 0)
+    ub = x.uncut(1, len(a[0]), ua.num_triangles)
+    ra = oracle.uncut_half_edges(a[1], fa, 0, 0)
+    rb = oracle.uncut_half_edges(b[1], fb, len(a[0]), len(ra["face"]))
+    check_uncut(ua, ra, a[1], 0)
+    check_uncut(ub, rb, b[1], len(a[0]))
+    assert ua.num_triangles == len(a[1]) - int(fa.sum())
+    # closed manifold input: the only missing neighbours are the cut faces
+    adj = ua.adjacency()
+    t = a[1]
+    cut_neighbours = 0
+    he = {}
+    for f in np.flatnonzero(fa):
+        for k in range(3):
+            he[(int(t[f, k]), int(t[f, (k + 1) % 3]))] = f
+    face, _ = ua.triangles()
+    for j in np.flatnonzero((adj < 0).any(axis=1)):
+        for k in range(3):
+            if adj[j, k] < 0:
+                assert (int(t[face[j], (k + 1) % 3]), int(t[face[j], k])) in he
+                cut_neighbours += 1
+    assert cut_neighbours == int((adj < 0).sum())
+    ua.close(); ub.close(); x.close(); ma.close(); mb.close()
+
+
+def test_uncut_edge_cases(ctx, oracle):
+    # empty mesh, one triangle, ragged sizes around the 2048-face tile and the 8-face word
+    tor = meshgen.torus(64, 33)
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 7, 8, 9, 2047, 2048, 2049, 4100, len(tor[1])):
+        tri = tor[1][:n]
+        m = ctx.mesh(tor[0], tri, build=False)
+        for cut in (None, (rng.random(n) < 0.5).astype(np.uint8), np.ones(n, np.uint8)):
+            u = m.uncut(cut, 5, 17)
+            check_uncut(u, oracle.uncut_half_edges(tri, cut, 5, 17), tri, 5)
+            u.close()
+        m.close()
+    # vertex offsets close to the 32-bit limit (33 key bits per half: an 8-pass sort)
+    m = ctx.mesh(*tor, build=False)
+    off = (1 << 32) - len(tor[0])
+    u = m.uncut(None, off, 0)
+    keys, owner = u.half_edges()
+    r = oracle.uncut_half_edges(tor[1], None, off, 0)
+    assert np.array_equal(keys, r["keys"]) and np.array_equal(owner, r["owner"]) and np.array_equal(u.adjacency(), r["adj"])
+    u.close()
+    with pytest.raises(sb.SolidBooleanError):
+        m.uncut(None, off + 1, 0)
+    m.close()
+
+
+@pytest.mark.slow
+def test_uncut_config_c3_full_size(ctx, oracle):
+    """BASELINE config 3 (1,310,720 + 1,048,576 triangles): the whole map against the oracle,
+    plus the properties a closed manifold must show."""
+    a, b = meshgen.config_c3()
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x = ma.intersect(mb)
+    fa, fb = x.face_flags()
+    ua = x.uncut(0, 0, 0)
+    ub = x.uncut(1, len(a[0]), ua.num_triangles)
+    ra = oracle.uncut_half_edges(a[1], fa, 0, 0)
+    rb = oracle.uncut_half_edges(b[1], fb, len(a[0]), len(ra["face"]))
+    for u, r, m, voff in ((ua, ra, a, 0), (ub, rb, b, len(a[0]))):
+        keys, owner = check_uncut(u, r, m[1], voff)
+        assert u.ok and np.all(np.diff(keys.astype(np.uint64)) > 0)          # sorted, no repeated half-edge
+        adj = u.adjacency()
+        # symmetry: my neighbour across an edge has me as a neighbour
+        base = u.half_edges()[1].min() if u.num_half_edges else 0
+        j, k = np.nonzero(adj >= 0)
+        back = adj[adj[j, k] - base]
+        assert np.all((back == (j + base)[:, None]).any(axis=1))
+    assert int((ua.adjacency() < 0).sum()) > 0 and ua.num_triangles + int(fa.sum()) == len(a[1])
+    ua.close(); ub.close(); x.close(); ma.close(); mb.close()

@@ -112,3 +112,65 @@ def test_oracle_vs_live_reference_mesh(oracle):
     i0, p0, _ = op.classify(1, pts)
     i1, p1, _ = oracle.classify(b, pts)
     assert np.array_equal(i0, i1) and np.array_equal(p0, p1)
+
+
+# ---- uncut triangles + half-edge map ---------------------------------
+
+def _h(a, dt):
+    return "%016x" % fnv1a64(np.ascontiguousarray(a).astype(dt).tobytes())
+
+
+def oracle_uncut_pair(oracle, a, b, ca, cb):
+    """Both meshes as combine() chains them (reference src/solidboolean.cpp:411-421): the second
+    mesh's vertices sit behind the first's, its triangles behind the first's uncut ones."""
+    ra = oracle.uncut_half_edges(a[1], ca, 0, 0)
+    rb = oracle.uncut_half_edges(b[1], cb, len(a[0]), len(ra["face"]))
+    return ra, rb
+
+
+@pytest.fixture(scope="module")
+def uncut_golden():
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "uncut.json")) as f:
+        return json.load(f)
+
+
+def test_uncut_half_edges_match_reference_fixtures(oracle, uncut_golden):
+    from conftest import uncut_inputs
+    inputs = uncut_inputs()
+    assert sorted(inputs) == sorted(uncut_golden)
+    for name, (a, b, ca, cb) in inputs.items():
+        ra, rb = oracle_uncut_pair(oracle, a, b, ca, cb)
+        tris = np.concatenate([a[1][ra["face"]], b[1][rb["face"]] + len(a[0])]).astype(np.uint32)
+        g = uncut_golden[name]
+        assert _h(tris, "<u4") == g["triangles_hash"], name
+        for r, gg in ((ra, g["a"]), (rb, g["b"])):
+            assert (r["ok"], len(r["face"]), len(r["keys"])) == (gg["ok"], gg["n_triangles"], gg["n_half_edges"]), name
+            assert _h(r["keys"], "<u8") == gg["keys_hash"], name
+            assert _h(r["owner"], "<u4") == gg["owner_hash"], name
+            assert _h(r["adj"], "<i4") == gg["adj_hash"], name
+            assert int((r["adj"] < 0).sum()) == gg["boundary_edges"], name
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built")
+def test_uncut_half_edges_match_live_reference(oracle):
+    from solidboolean_b200 import meshgen
+    rng = np.random.default_rng(5)
+    a = meshgen.icosphere(4)
+    b = meshgen.torus(40, 20, center=(0.2, 0.0, 0.1))
+    R = Ref.get()
+    op = R.op(R.mesh(*a), R.mesh(*b))
+    for trial in range(3):
+        ca = (rng.random(len(a[1])) < 0.1 * trial).astype(np.uint8)
+        cb = (rng.random(len(b[1])) < 0.3).astype(np.uint8)
+        (ra, rb), tris = op.uncut(ca, cb)
+        oa, ob = oracle_uncut_pair(oracle, a, b, ca, cb)
+        for r, o in ((ra, oa), (rb, ob)):
+            assert r["ok"] and o["ok"]
+            assert np.array_equal(r["keys"], o["keys"]) and np.array_equal(r["owner"], o["owner"])
+        assert np.array_equal(tris, np.concatenate([a[1][oa["face"]], b[1][ob["face"]] + len(a[0])]))
+        t = a[1][oa["face"]].astype(np.uint64)
+        ft = np.stack([np.stack([t[:, (k + 1) % 3], t[:, k]], -1) for k in range(3)], 1).reshape(-1, 2)
+        assert np.array_equal(op.uncut_lookup(0, ft).reshape(-1, 3), oa["adj"])
