@@ -194,6 +194,12 @@ int sb_uncut_half_edges(const sb_uncut *u, uint64_t *keys, uint32_t *owner);
 /* adj3[3 j + k] = owner of the half-edge opposite to edge k (vertices k, k+1 mod 3) of new
  * triangle j, or -1 if the map has none (the neighbour is a cut face or the mesh is open). */
 int sb_uncut_adjacency(const sb_uncut *u, int32_t *adj3);
+/* Face groups of the uncut triangles -- the flood fill of SolidBoolean::buildFaceGroups
+ * (src/solidboolean.cpp:167-239) where no intersection loop fences it (:229-238), as connected
+ * components of the adjacency above (lock-free union-find on the device): label[j] = lowest new
+ * triangle index of j's component, i.e. the triangle the reference's loop over ascending indices
+ * opens that group with; *n_components = number of groups.  SURVEY 8f row 3.  label may be NULL. */
+int sb_uncut_components(const sb_uncut *u, uint32_t *label, size_t *n_components);
 /* Device pointers of the same arrays (valid until sb_uncut_destroy) for device-side consumers;
  * any out pointer may be NULL.  After a repeated half-edge (*ok == 0) they hold the untruncated
  * arrays of ALL uncut faces. */

@@ -81,6 +81,8 @@ class Oracle:
                                            C.POINTER(C.c_size_t), _u64p, _u32p, C.POINTER(C.c_size_t)]
         L.sbo_uncut_half_edges.restype = C.c_int
         L.sbo_uncut_adjacency.argtypes = [_u32p, _u32p, C.c_size_t, C.c_uint64, _u64p, _u32p, C.c_size_t, _i32p]
+        L.sbo_uncut_components.argtypes = [_i32p, C.c_size_t, C.c_uint64, _u32p]
+        L.sbo_uncut_components.restype = C.c_size_t
 
     # -- predicate ---------------------------------------------------------
     def tri_tri_batch(self, tris18):
@@ -160,7 +162,9 @@ class Oracle:
         adj = np.full((n.value, 3), -1, np.int32)
         if n.value:
             self.lib.sbo_uncut_adjacency(tri, face, n.value, vertex_offset, keys, owner, m.value, adj)
-        return dict(ok=bool(ok), face=face, keys=keys, owner=owner, adj=adj)
+        label = np.zeros(n.value, np.uint32)
+        comps = self.lib.sbo_uncut_components(adj, n.value, triangle_offset, label) if n.value else 0
+        return dict(ok=bool(ok), face=face, keys=keys, owner=owner, adj=adj, label=label, components=int(comps))
 
     # -- classification -----------------------------------------------------
     def classify(self, target_mesh, pts):
@@ -228,6 +232,10 @@ class Ref:
             L.ref_op_uncut.restype = C.c_int
             L.ref_op_uncut_fetch.argtypes = [vp, C.c_int, _u64p, _u32p]
             L.ref_op_uncut_lookup.argtypes = [vp, C.c_int, _u64p, C.c_size_t, _i32p]
+            L.ref_op_uncut_groups.argtypes = [vp, C.c_int, _u32p]
+            L.ref_op_uncut_groups.restype = C.c_size_t
+            L.ref_op_uncut_ms.argtypes = [vp, C.c_int, C.c_int]
+            L.ref_op_uncut_ms.restype = C.c_double
         if hasattr(L, "ref_load_obj"):
             L.ref_load_obj.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p,
                                        C.POINTER(C.c_size_t)]
@@ -376,6 +384,16 @@ class RefOp:
         if ntri[1]:
             self.ref.lib.ref_op_result_triangles(self.h, 0, tris)
         return out, tris[:ntri[1]]
+
+    def uncut_groups(self, which, n):
+        """buildFaceGroups without loops over the state left by uncut(): -> label [n], group count"""
+        label = np.zeros(max(n, 1), np.uint32)
+        g = self.ref.lib.ref_op_uncut_groups(self.h, which, label)
+        return label[:n], int(g)
+
+    def uncut_ms(self, what, which):
+        """ms inside the reference's addUnintersectedTriangles (what=0) / buildFaceGroups (what=1)"""
+        return float(self.ref.lib.ref_op_uncut_ms(self.h, what, which))
 
     def uncut_lookup(self, which, from_to):
         ft = np.ascontiguousarray(from_to, dtype=np.uint64).reshape(-1, 2)

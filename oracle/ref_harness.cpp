@@ -70,6 +70,9 @@ struct RefOp {
     std::vector<std::vector<size_t>> fetched[3];
     // ref_op_uncut: the two half-edge maps, flattened and sorted by key
     std::vector<std::pair<uint64_t, size_t>> halfEdges[2];
+    size_t uncutEnd[2] = {0, 0}; // m_newTriangles.size() after each addUnintersectedTriangles call
+    double uncutMs[2] = {0, 0};  // time inside addUnintersectedTriangles / buildFaceGroups alone
+    double groupsMs[2] = {0, 0};
 };
 
 // Silence the reference's std::cout chatter (failure messages) on request.
@@ -394,14 +397,20 @@ int ref_op_uncut(void *h, const uint8_t *cutA, const uint8_t *cutB, size_t *nTri
     int result = 0;
     {
         CoutSilencer *s = quiet ? new CoutSilencer : nullptr;
+        auto t0 = Clock::now();
         if (fresh.addUnintersectedTriangles(&o->a->mesh, used[0], &maps[0]))
             result |= 1;
+        o->uncutMs[0] = msSince(t0);
         nTri[0] = fresh.m_newTriangles.size();
+        t0 = Clock::now();
         if (fresh.addUnintersectedTriangles(&o->b->mesh, used[1], &maps[1]))
             result |= 2;
+        o->uncutMs[1] = msSince(t0);
         nTri[1] = fresh.m_newTriangles.size();
         delete s;
     }
+    o->uncutEnd[0] = nTri[0];
+    o->uncutEnd[1] = nTri[1];
     o->fetched[0] = fresh.m_newTriangles; // reuse the triple store for ref_op_result_triangles(h, 0, ..)
     for (int w = 0; w < 2; ++w) {
         o->halfEdges[w].assign(maps[w].begin(), maps[w].end());
@@ -430,6 +439,34 @@ void ref_op_uncut_lookup(void *h, int which, const uint64_t *fromTo, size_t n, i
         auto it = m.find(SolidBoolean::makeHalfEdgeKey(fromTo[2 * i], fromTo[2 * i + 1]));
         out[i] = it == m.end() ? -1 : (int32_t)it->second;
     }
+}
+
+// buildFaceGroups (src/solidboolean.cpp:167-239) over the triangles and the half-edge map kept
+// by ref_op_uncut, with NO intersection loops: the flood of :229-238 alone.  label[j] = first
+// triangle of the group that new triangle (start + j) landed in; returns the number of groups.
+size_t ref_op_uncut_groups(void *h, int which, uint32_t *label)
+{
+    RefOp *o = (RefOp *)h;
+    SolidBoolean fresh(&o->a->mesh, &o->b->mesh);
+    std::unordered_map<uint64_t, size_t> m(o->halfEdges[which].begin(), o->halfEdges[which].end());
+    std::vector<std::vector<size_t>> none, groups;
+    size_t start = which == 0 ? 0 : o->uncutEnd[0];
+    size_t count = o->uncutEnd[which] - start;
+    auto t0 = Clock::now();
+    fresh.buildFaceGroups(none, m, o->fetched[0], start, count, groups);
+    o->groupsMs[which] = msSince(t0);
+    for (const auto &g : groups)
+        for (size_t t : g)
+            label[t - start] = (uint32_t)g[0];
+    return groups.size();
+}
+
+// milliseconds spent inside the reference's own functions by the last ref_op_uncut /
+// ref_op_uncut_groups: what = 0 addUnintersectedTriangles, 1 buildFaceGroups
+double ref_op_uncut_ms(void *h, int what, int which)
+{
+    RefOp *o = (RefOp *)h;
+    return what == 0 ? o->uncutMs[which] : o->groupsMs[which];
 }
 
 } // extern "C"

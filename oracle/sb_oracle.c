@@ -870,3 +870,45 @@ void sbo_uncut_adjacency(const uint32_t *tri, const uint32_t *face, size_t nTri,
         }
     }
 }
+
+/* ---- face groups of the untouched triangles ------------------------
+ * SolidBoolean::buildFaceGroups (src/solidboolean.cpp:167-239) floods the triangles through
+ * the half-edge map: from triangle t, edge (i, j) leads to halfEdges.find(key(j, i)) (:216-221)
+ * unless that half-edge is fenced by an intersection loop.  With no loops in the way the
+ * groups it opens at :229-238 are the connected components of the adjacency relation above,
+ * opened in ascending order of their lowest triangle index.  label[j] = lowest new-triangle
+ * index of j's component (adj as returned by sbo_uncut_adjacency, indices carry
+ * triangleOffset).  Returns the number of components. */
+size_t sbo_uncut_components(const int32_t *adj, size_t nTri, uint64_t triangleOffset, uint32_t *label)
+{
+    size_t *stack = (size_t *)malloc((nTri + 1) * sizeof(size_t));
+    uint8_t *seen = (uint8_t *)calloc(nTri + 1, 1);
+    size_t comps = 0;
+    for (size_t s = 0; s < nTri; ++s) {
+        if (seen[s])
+            continue;
+        ++comps;
+        size_t top = 0;
+        stack[top++] = s;
+        seen[s] = 1;
+        while (top) {
+            size_t t = stack[--top];
+            label[t] = (uint32_t)(triangleOffset + s);
+            for (int k = 0; k < 3; ++k) {
+                int32_t o = adj[3 * t + k];
+                if (o < 0)
+                    continue;
+                size_t u = (size_t)((uint64_t)o - triangleOffset);
+                /* forward only, like the reference's flood; the relation is symmetric unless a
+                 * repeated half-edge truncated the map (then the order of the seeds matters) */
+                if (u < nTri && !seen[u]) {
+                    seen[u] = 1;
+                    stack[top++] = u;
+                }
+            }
+        }
+    }
+    free(stack);
+    free(seen);
+    return comps;
+}

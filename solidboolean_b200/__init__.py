@@ -82,6 +82,7 @@ ABI = {
     "sb_uncut_triangles": (C.c_int, [_vp, _vp, _vp]),
     "sb_uncut_half_edges": (C.c_int, [_vp, _vp, _vp]),
     "sb_uncut_adjacency": (C.c_int, [_vp, _vp]),
+    "sb_uncut_components": (C.c_int, [_vp, _vp, C.POINTER(_sz)]),
     "sb_uncut_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                        C.POINTER(_vp)]),
     "sb_classify": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
@@ -443,6 +444,13 @@ class Uncut:
         if self.num_triangles:
             _check(self.lib.sb_uncut_adjacency(self.h, _ptr(adj)))
         return adj
+
+    def components(self):
+        """-> label [n] (lowest new triangle index of each triangle's face group), group count"""
+        label = np.zeros(self.num_triangles, np.uint32)
+        n = _sz(0)
+        _check(self.lib.sb_uncut_components(self.h, _ptr(label), C.byref(n)))
+        return label, int(n.value)
 
     def device_ptrs(self):
         p = [_vp() for _ in range(5)]

@@ -53,6 +53,7 @@ struct DeviceScalars { // device counters of one lane (128-byte slots)
     unsigned long long paths[5]; // predicate exit histogram (TriTriPath)
     unsigned int uncutTotal;     // sb_*_uncut: uncut faces
     unsigned int heRepeat;       // ... first refused half-edge insertion (ordinal), UINT_MAX = none
+    unsigned int ccCount;        // sb_uncut_components: components
 };
 static_assert(sizeof(DeviceScalars) <= 128, "lane slot too small");
 
@@ -168,6 +169,8 @@ struct sb_uncut {
     uint32_t *owner = nullptr;    // 3 nTri
     uint32_t *ords = nullptr;     // 3 nTri insertion ordinal of each sorted entry
     int32_t *adj = nullptr;       // 3 nTri, indexed by ordinal
+    uint32_t *label = nullptr;    // nTri component labels (sb_uncut_components, on first request)
+    size_t nComponents = 0;
     std::vector<void *> owned;
 };
 
@@ -1452,7 +1455,7 @@ static int uncut_run(const sb_mesh *mesh, const uint8_t *dCut, size_t vertexOffs
 {
     sb_context *c = mesh->ctx;
     const MeshDev &d = mesh->d;
-    if (vertexOffset + d.nV > 0xffffffffull || triangleOffset + d.nT > 0x7fffffffull)
+    if (vertexOffset + d.nV > 0x100000000ull || triangleOffset + d.nT > 0x7fffffffull)
         return fail(SB_ERR_INVALID, "vertex / triangle offset out of the 32-bit index range");
     sb_uncut *u = new (std::nothrow) sb_uncut;
     if (!u)
@@ -1663,6 +1666,80 @@ int sb_uncut_adjacency(const sb_uncut *u, int32_t *adj3)
     }
     SB_CUDA(cudaMemcpyAsync(adj3, u->adj, 12 * (size_t)u->nTri, cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_uncut_components(const sb_uncut *uc, uint32_t *label, size_t *n_components)
+{
+    sb_uncut *u = const_cast<sb_uncut *>(uc);
+    if (!u)
+        return fail(SB_ERR_INVALID, "uncut is null");
+    sb_context *c = u->ctx;
+    DeviceGuard g(c->device);
+    if (n_components)
+        *n_components = 0;
+    if (!u->nTri)
+        return SB_OK;
+    if (u->repeatOrd != 0xffffffffu) {
+        // Rare path (the reference returned false): the truncated map is not symmetric, so the
+        // groups depend on the order of the reference's flood -- repeat it on the host:
+        // ascending seeds, forward lookups only (src/solidboolean.cpp:205-238).
+        const size_t nt = uncut_tri_count(u);
+        std::vector<int32_t> adj(3 * nt);
+        int r = sb_uncut_adjacency(u, adj.data());
+        if (r)
+            return r;
+        std::vector<uint32_t> lab(nt, 0xffffffffu), stack;
+        size_t comps = 0;
+        for (size_t s = 0; s < nt; ++s) {
+            if (lab[s] != 0xffffffffu)
+                continue;
+            ++comps;
+            lab[s] = u->triangleOffset + (uint32_t)s;
+            stack.assign(1, (uint32_t)s);
+            while (!stack.empty()) {
+                uint32_t t = stack.back();
+                stack.pop_back();
+                for (int k = 0; k < 3; ++k) {
+                    int32_t o = adj[3 * (size_t)t + k];
+                    if (o < 0)
+                        continue;
+                    uint32_t j = (uint32_t)o - u->triangleOffset;
+                    if (j < nt && lab[j] == 0xffffffffu) {
+                        lab[j] = u->triangleOffset + (uint32_t)s;
+                        stack.push_back(j);
+                    }
+                }
+            }
+        }
+        if (label)
+            memcpy(label, lab.data(), 4 * nt);
+        if (n_components)
+            *n_components = comps;
+        return SB_OK;
+    }
+    if (!u->label) {
+        StageTimer timer(c, SB_STAGE_HALFEDGE);
+        uint32_t *parent = nullptr;
+        int r = alloc_async(c, &u->label, u->nTri, &u->owned);
+        if (!r)
+            r = alloc_async(c, &parent, u->nTri, nullptr);
+        if (r)
+            return r;
+        SB_CUDA(cudaMemsetAsync(&c->dScalars->ccCount, 0, sizeof(unsigned int), c->stream));
+        SB_CUDA(sbk_uncut_components(c->stream, u->adj, u->nTri, u->triangleOffset, parent, u->label, &c->dScalars->ccCount,
+            c->lc));
+        cudaFreeAsync(parent, c->stream);
+        SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        u->nComponents = c->hScalars->ccCount;
+    }
+    if (label) {
+        SB_CUDA(cudaMemcpyAsync(label, u->label, 4 * (size_t)u->nTri, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (n_components)
+        *n_components = u->nComponents;
     return SB_OK;
 }
 

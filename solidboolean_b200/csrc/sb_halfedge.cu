@@ -198,7 +198,91 @@ __global__ void __launch_bounds__(256) halfedge_link_kernel(const unsigned long 
     adj[ord] = other;
 }
 
+// ---- connected components of the uncut triangles -----------------------------------------
+// buildFaceGroups' flood (reference src/solidboolean.cpp:229-238) without the queue: lock-free
+// union-find over the adjacency array.  A root only ever gets a SMALLER root as parent, so
+// every component ends up rooted at its lowest triangle index -- the triangle the reference's
+// loop over ascending indices would have opened the group with -- whatever the thread order.
+__device__ __forceinline__ uint32_t cc_find(uint32_t *parent, uint32_t x)
+{
+    uint32_t p = __ldcg(parent + x);
+    while (p != x) {
+        const uint32_t g = __ldcg(parent + p);
+        if (g != p)
+            parent[x] = g; // path halving: any ancestor is a valid parent
+        x = p;
+        p = g;
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(256) cc_init_kernel(uint32_t *__restrict__ parent, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        parent[i] = i;
+}
+
+__global__ void __launch_bounds__(256) cc_hook_kernel(const int32_t *__restrict__ adj, uint32_t n, uint32_t triangleOffset,
+    uint32_t *parent)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int32_t o = __ldg(adj + 3 * (size_t)i + k);
+        if (o < 0)
+            continue;
+        const uint32_t j = (uint32_t)o - triangleOffset;
+        if (j >= i)
+            continue; // every edge once (the relation is symmetric), from its larger end
+        uint32_t a = cc_find(parent, i), b = cc_find(parent, j);
+        while (a != b) {
+            if (a < b) {
+                const uint32_t t = a;
+                a = b;
+                b = t;
+            }
+            const uint32_t old = atomicCAS(parent + a, a, b); // hang the larger root under the smaller
+            if (old == a)
+                break;
+            a = cc_find(parent, old);
+            b = cc_find(parent, b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cc_label_kernel(uint32_t *parent, uint32_t n, uint32_t triangleOffset,
+    uint32_t *__restrict__ label, uint32_t *__restrict__ count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    uint32_t r = 0;
+    if (live) {
+        r = cc_find(parent, i);
+        label[i] = r + triangleOffset;
+    }
+    const unsigned roots = __ballot_sync(SB_FULL, live && r == i);
+    if ((threadIdx.x & 31) == 0 && roots)
+        atomicAdd(count, __popc(roots));
+}
+
 } // namespace
+
+// parent: n words of scratch; label: n; *count (device, zeroed by the caller) += components
+cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *parent,
+    uint32_t *label, uint32_t *count, LaunchCounter &lc)
+{
+    if (n == 0)
+        return cudaSuccess;
+    const uint32_t blocks = (n + 255) / 256;
+    cc_init_kernel<<<blocks, 256, 0, s>>>(parent, n);
+    cc_hook_kernel<<<blocks, 256, 0, s>>>(adj, n, triangleOffset, parent);
+    cc_label_kernel<<<blocks, 256, 0, s>>>(parent, n, triangleOffset, label, count);
+    lc.kernels += 3;
+    return cudaGetLastError();
+}
 
 uint32_t sbk_uncut_tiles(uint32_t nT) { return (nT + HE_TILE - 1) / HE_TILE; }
 

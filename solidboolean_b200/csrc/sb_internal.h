@@ -107,6 +107,8 @@ cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *t
 cudaError_t sbk_halfedge_link(cudaStream_t s, const unsigned long long *sortedKeys, const uint32_t *sortedOrds, uint32_t n,
     unsigned bitsV, uint32_t triangleOffset, unsigned long long *refKeys, uint32_t *owner, int32_t *adj,
     uint32_t *firstRepeat, LaunchCounter &lc);
+cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *parent,
+    uint32_t *label, uint32_t *count, LaunchCounter &lc);
 
 // sb_classify.cu
 struct ClassifyArgs {

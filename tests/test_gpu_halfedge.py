@@ -36,6 +36,8 @@ def check_uncut(u, ref, tri, vertex_offset):
     keys, owner = u.half_edges()
     assert np.array_equal(keys, ref["keys"]) and np.array_equal(owner, ref["owner"])
     assert np.array_equal(u.adjacency(), ref["adj"])
+    label, groups = u.components()
+    assert groups == ref["components"] and np.array_equal(label, ref["label"])
     return keys, owner
 
 
@@ -55,6 +57,8 @@ def test_uncut_fixtures_vs_reference_and_oracle(ctx, oracle):
             assert (u.ok, u.num_triangles, u.num_half_edges) == (gg["ok"], gg["n_triangles"], gg["n_half_edges"]), name
             assert (_h(keys, "<u8"), _h(owner, "<u4")) == (gg["keys_hash"], gg["owner_hash"]), name
             assert _h(u.adjacency(), "<i4") == gg["adj_hash"], name
+            label, groups = u.components()
+            assert (groups, _h(label, "<u4")) == (gg["groups"], gg["label_hash"]), name
         ua.close(); ub.close(); ma.close(); mb.close()
 
 
@@ -111,6 +115,7 @@ def test_uncut_edge_cases(ctx, oracle):
     keys, owner = u.half_edges()
     r = oracle.uncut_half_edges(tor[1], None, off, 0)
     assert np.array_equal(keys, r["keys"]) and np.array_equal(owner, r["owner"]) and np.array_equal(u.adjacency(), r["adj"])
+    assert np.array_equal(u.components()[0], r["label"])
     u.close()
     with pytest.raises(sb.SolidBooleanError):
         m.uncut(None, off + 1, 0)

@@ -152,6 +152,7 @@ def test_uncut_half_edges_match_reference_fixtures(oracle, uncut_golden):
             assert _h(r["owner"], "<u4") == gg["owner_hash"], name
             assert _h(r["adj"], "<i4") == gg["adj_hash"], name
             assert int((r["adj"] < 0).sum()) == gg["boundary_edges"], name
+            assert (r["components"], _h(r["label"], "<u4")) == (gg["groups"], gg["label_hash"]), name
 
 
 @pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built")
@@ -174,3 +175,6 @@ def test_uncut_half_edges_match_live_reference(oracle):
         t = a[1][oa["face"]].astype(np.uint64)
         ft = np.stack([np.stack([t[:, (k + 1) % 3], t[:, k]], -1) for k in range(3)], 1).reshape(-1, 2)
         assert np.array_equal(op.uncut_lookup(0, ft).reshape(-1, 3), oa["adj"])
+        for w, o in ((0, oa), (1, ob)):
+            label, groups = op.uncut_groups(w, len(o["face"]))
+            assert groups == o["components"] and np.array_equal(label, o["label"])
