@@ -1,5 +1,7 @@
 #include "solidboolean.h"
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 #include <deque>
 #include <iostream>
 #include "retriangulator.h"
@@ -79,7 +81,7 @@ bool SolidBoolean::HalfEdgeMap::insert(uint64_t key, size_t triangle)
 bool SolidBoolean::appendTriangle(size_t a, size_t b, size_t c, HalfEdgeMap &halfEdges)
 {
     size_t index = m_newTriangles.size();
-    m_newTriangles.push_back({a, b, c});
+    m_newTriangles.push_back({{a, b, c}});
     bool ok = true;
     ok &= halfEdges.insert(halfEdgeKey(a, b), index);
     ok &= halfEdges.insert(halfEdgeKey(b, c), index);
@@ -91,7 +93,8 @@ bool SolidBoolean::appendTriangle(size_t a, size_t b, size_t c, HalfEdgeMap &hal
 // addUnintersectedTriangles, src/solidboolean.cpp:250-286).  GPU: sb_isect_uncut compacts
 // them, sorts their half-edge keys and reports a repeated half-edge exactly where the
 // reference's map insert would have refused it.
-bool SolidBoolean::copyUncutTriangles(const void *isect, int which, size_t vertexOffset, HalfEdgeMap &halfEdges)
+bool SolidBoolean::copyUncutTriangles(const void *isect, int which, size_t vertexOffset, HalfEdgeMap &halfEdges,
+    UncutTopology &topology)
 {
     sb_uncut *uncut = nullptr;
     if (sb_isect_uncut(static_cast<const sb_isect *>(isect), which, vertexOffset, m_newTriangles.size(), &uncut) != SB_OK) {
@@ -106,6 +109,21 @@ bool SolidBoolean::copyUncutTriangles(const void *isect, int which, size_t verte
     int rc = sb_uncut_triangles(uncut, nullptr, triples.data());
     if (rc == SB_OK)
         rc = sb_uncut_half_edges(uncut, keys.data(), owners.data());
+    topology.first = m_newTriangles.size();
+    topology.count = triangleCount;
+    topology.grouped = false;
+    // SB_HOST_FLOOD=legacy: triangle-by-triangle flood through the half-edge map, as the reference
+    // does it (comparison / debugging)
+    static const bool legacyFlood = [] { const char *e = std::getenv("SB_HOST_FLOOD"); return e && std::string(e) == "legacy"; }();
+    if (rc == SB_OK && ok && triangleCount && !legacyFlood) {
+        // face groups + neighbours of the uncut triangles, computed on the GPU
+        topology.label.resize(triangleCount);
+        topology.adjacency.resize(3 * triangleCount);
+        rc = sb_uncut_components(uncut, topology.label.data(), nullptr);
+        if (rc == SB_OK)
+            rc = sb_uncut_adjacency(uncut, topology.adjacency.data());
+        topology.grouped = rc == SB_OK;
+    }
     sb_uncut_destroy(uncut);
     if (rc != SB_OK) {
         std::cout << "addUnintersectedTriangles failed: " << sb_last_error() << std::endl;
@@ -113,7 +131,7 @@ bool SolidBoolean::copyUncutTriangles(const void *isect, int which, size_t verte
     }
     m_newTriangles.reserve(m_newTriangles.size() + triangleCount);
     for (size_t i = 0; i < triangleCount; ++i)
-        m_newTriangles.push_back({triples[3 * i], triples[3 * i + 1], triples[3 * i + 2]});
+        m_newTriangles.push_back({{triples[3 * i], triples[3 * i + 1], triples[3 * i + 2]}});
     if (!ok && triangleCount) {
         const auto &last = m_newTriangles.back();
         std::cout << "Found repeated halfedge:" << last[0] << "," << last[1] << std::endl;
@@ -210,9 +228,35 @@ bool SolidBoolean::traceLoops(const EdgeGraph &edges, std::vector<std::vector<si
 // loops: loop k seeds group 2k on the side of its forward half-edges and group
 // 2k+1 on the other side; triangles no loop reaches form further groups
 // (reference buildFaceGroups, src/solidboolean.cpp:167-239).
+//
+// The uncut triangles arrive pre-grouped from the GPU (sb_uncut_components): no loop runs through
+// them, so a fill that reaches one of them takes its whole component at once and carries on
+// through the component's open edges (adjacency -1: a retriangulated face lies there).  The host
+// flood proper only walks the retriangulated pieces.  Where two seeds reach the same region the
+// reference splits it between their groups along the meeting front of its queue; here the first
+// seed to arrive takes the component whole -- the two groups lie on the same side of every loop,
+// so the triangles each operation keeps are the same.
 void SolidBoolean::growFaceGroups(const std::vector<std::vector<size_t>> &loops, const HalfEdgeMap &halfEdges,
-    size_t firstTriangle, size_t triangleCount, std::vector<std::vector<size_t>> &groups)
+    const UncutTopology &uncut, size_t firstTriangle, size_t triangleCount, std::vector<std::vector<size_t>> &groups)
 {
+    // members of every uncut component, ascending (counting sort by label)
+    const bool grouped = uncut.grouped && uncut.count > 0;
+    std::vector<uint32_t> memberStart, members;
+    std::vector<uint8_t> claimed;
+    if (grouped) {
+        memberStart.assign(uncut.count + 1, 0);
+        for (size_t i = 0; i < uncut.count; ++i)
+            ++memberStart[uncut.label[i] - uncut.first + 1];
+        for (size_t i = 0; i < uncut.count; ++i)
+            memberStart[i + 1] += memberStart[i];
+        members.resize(uncut.count);
+        std::vector<uint32_t> cursor(memberStart.begin(), memberStart.end() - 1);
+        for (size_t i = 0; i < uncut.count; ++i)
+            members[cursor[uncut.label[i] - uncut.first]++] = (uint32_t)i;
+        claimed.assign(uncut.count, 0);
+    }
+    auto isGroupedUncut = [&](size_t t) { return grouped && t >= uncut.first && t < uncut.first + uncut.count; };
+
     std::unordered_map<uint64_t, size_t> fence; // half-edges a fill must not cross again
     std::deque<std::pair<size_t, size_t>> queue;
     size_t groupIndex = 0;
@@ -230,11 +274,35 @@ void SolidBoolean::growFaceGroups(const std::vector<std::vector<size_t>> &loops,
         groupIndex += 2;
     }
     groups.assign(groupIndex, std::vector<size_t>());
-    std::unordered_set<size_t> visited;
+    std::unordered_set<size_t> visited; // retriangulated pieces (and everything when the GPU groups are missing)
     auto drain = [&]() {
         while (!queue.empty()) {
             auto item = queue.front();
             queue.pop_front();
+            if (isGroupedUncut(item.first)) {
+                const size_t root = uncut.label[item.first - uncut.first] - uncut.first;
+                if (claimed[root])
+                    continue;
+                claimed[root] = 1;
+                auto &group = groups[item.second];
+                group.reserve(group.size() + (memberStart[root + 1] - memberStart[root]));
+                for (uint32_t m = memberStart[root]; m < memberStart[root + 1]; ++m) {
+                    const size_t local = members[m], tri = uncut.first + local;
+                    group.push_back(tri);
+                    for (size_t i = 0; i < 3; ++i) {
+                        if (uncut.adjacency[3 * local + i] >= 0)
+                            continue; // the neighbour is in this component
+                        const auto &t = m_newTriangles[tri];
+                        size_t a = t[i], b = t[(i + 1) % 3];
+                        if (!fence.insert({halfEdgeKey(a, b), item.second}).second)
+                            continue;
+                        size_t opposite;
+                        if (halfEdges.find(halfEdgeKey(b, a), opposite))
+                            queue.push_back({opposite, item.second});
+                    }
+                }
+                continue;
+            }
             if (!visited.insert(item.first).second)
                 continue;
             groups[item.second].push_back(item.first);
@@ -251,7 +319,10 @@ void SolidBoolean::growFaceGroups(const std::vector<std::vector<size_t>> &loops,
     };
     drain();
     for (size_t t = firstTriangle; t < firstTriangle + triangleCount; ++t) {
-        if (visited.count(t))
+        if (isGroupedUncut(t)) {
+            if (claimed[uncut.label[t - uncut.first] - uncut.first]) // labels are the lowest member: seen first
+                continue;
+        } else if (visited.count(t))
             continue;
         groups.push_back(std::vector<size_t>());
         queue.push_back({t, groupIndex++});
@@ -342,12 +413,13 @@ bool SolidBoolean::combine()
     m_newVertices.insert(m_newVertices.end(), m_firstMesh->vertices()->begin(), m_firstMesh->vertices()->end());
     m_newVertices.insert(m_newVertices.end(), m_secondMesh->vertices()->begin(), m_secondMesh->vertices()->end());
     HalfEdgeMap firstHalfEdges, secondHalfEdges;
+    UncutTopology firstUncut, secondUncut;
     size_t firstStart = m_newTriangles.size();
-    if (!copyUncutTriangles(isect, 0, 0, firstHalfEdges))
+    if (!copyUncutTriangles(isect, 0, 0, firstHalfEdges, firstUncut))
         std::cout << "Add first mesh remaining triangles failed" << std::endl;
     size_t firstCount = m_newTriangles.size() - firstStart;
     size_t secondStart = m_newTriangles.size();
-    if (!copyUncutTriangles(isect, 1, firstVertexCount, secondHalfEdges))
+    if (!copyUncutTriangles(isect, 1, firstVertexCount, secondHalfEdges, secondUncut))
         std::cout << "Add second mesh remaining triangles failed" << std::endl;
     size_t secondCount = m_newTriangles.size() - secondStart;
     sb_isect_destroy(isect);
@@ -374,8 +446,8 @@ bool SolidBoolean::combine()
     benchEnd_buildPolygonsFromEdges = now();
 
     benchBegin_buildFaceGroups = now();
-    growFaceGroups(loops, firstHalfEdges, firstStart, firstCount, m_firstGroups);
-    growFaceGroups(loops, secondHalfEdges, secondStart, secondCount, m_secondGroups);
+    growFaceGroups(loops, firstHalfEdges, firstUncut, firstStart, firstCount, m_firstGroups);
+    growFaceGroups(loops, secondHalfEdges, secondUncut, secondStart, secondCount, m_secondGroups);
     benchEnd_buildFaceGroups = now();
 
     // ---- GPU: inside/outside of every group ----
@@ -392,11 +464,11 @@ void SolidBoolean::fetchUnion(std::vector<std::vector<size_t>> &resultTriangles)
     for (size_t g = 0; g < m_firstGroups.size(); ++g)
         if (!m_firstGroupInside[g])
             for (size_t t : m_firstGroups[g])
-                resultTriangles.push_back(m_newTriangles[t]);
+                resultTriangles.push_back({m_newTriangles[t][0], m_newTriangles[t][1], m_newTriangles[t][2]});
     for (size_t g = 0; g < m_secondGroups.size(); ++g)
         if (!m_secondGroupInside[g])
             for (size_t t : m_secondGroups[g])
-                resultTriangles.push_back(m_newTriangles[t]);
+                resultTriangles.push_back({m_newTriangles[t][0], m_newTriangles[t][1], m_newTriangles[t][2]});
 }
 
 void SolidBoolean::fetchDiff(std::vector<std::vector<size_t>> &resultTriangles)
@@ -404,7 +476,7 @@ void SolidBoolean::fetchDiff(std::vector<std::vector<size_t>> &resultTriangles)
     for (size_t g = 0; g < m_firstGroups.size(); ++g)
         if (!m_firstGroupInside[g])
             for (size_t t : m_firstGroups[g])
-                resultTriangles.push_back(m_newTriangles[t]);
+                resultTriangles.push_back({m_newTriangles[t][0], m_newTriangles[t][1], m_newTriangles[t][2]});
     for (size_t g = 0; g < m_secondGroups.size(); ++g)
         if (m_secondGroupInside[g])
             for (size_t t : m_secondGroups[g]) { // the cavity wall faces inward: reverse the winding
@@ -418,9 +490,9 @@ void SolidBoolean::fetchIntersect(std::vector<std::vector<size_t>> &resultTriang
     for (size_t g = 0; g < m_firstGroups.size(); ++g)
         if (m_firstGroupInside[g])
             for (size_t t : m_firstGroups[g])
-                resultTriangles.push_back(m_newTriangles[t]);
+                resultTriangles.push_back({m_newTriangles[t][0], m_newTriangles[t][1], m_newTriangles[t][2]});
     for (size_t g = 0; g < m_secondGroups.size(); ++g)
         if (m_secondGroupInside[g])
             for (size_t t : m_secondGroups[g])
-                resultTriangles.push_back(m_newTriangles[t]);
+                resultTriangles.push_back({m_newTriangles[t][0], m_newTriangles[t][1], m_newTriangles[t][2]});
 }

@@ -7,6 +7,7 @@
 // message on std::cout, combine() returns false, no exceptions.
 #ifndef SOLID_BOOLEAN_H
 #define SOLID_BOOLEAN_H
+#include <array>
 #include <chrono>
 #include <cstdint>
 #include <map>
@@ -67,16 +68,25 @@ private:
         std::unordered_map<uint64_t, size_t> m_added;
     };
     typedef std::unordered_map<size_t, std::unordered_set<size_t>> EdgeGraph;
+    // The uncut triangles of one mesh as the GPU hands them over (sb_uncut_*): new triangles
+    // [first, first + count), for each its face group among the uncut triangles (label = lowest
+    // triangle of the group) and the triangle across each edge (-1: a cut face lies there).
+    struct UncutTopology {
+        size_t first = 0, count = 0;
+        bool grouped = false; // labels / adjacency valid (false after a repeated half-edge)
+        std::vector<uint32_t> label;
+        std::vector<int32_t> adjacency;
+    };
 
     static uint64_t halfEdgeKey(size_t from, size_t to) { return ((uint64_t)from << 32) | (uint64_t)to; }
     size_t weldPoint(const Vector3 &p);
     bool appendTriangle(size_t a, size_t b, size_t c, HalfEdgeMap &halfEdges);
-    bool copyUncutTriangles(const void *isect, int which, size_t vertexOffset, HalfEdgeMap &halfEdges);
+    bool copyUncutTriangles(const void *isect, int which, size_t vertexOffset, HalfEdgeMap &halfEdges, UncutTopology &topology);
     bool retriangulateCutTriangles(const std::map<size_t, CutTriangle> &cuts, const SolidMesh *mesh, size_t vertexOffset,
         HalfEdgeMap &halfEdges, EdgeGraph &loopEdges);
     bool traceLoops(const EdgeGraph &edges, std::vector<std::vector<size_t>> &loops);
-    void growFaceGroups(const std::vector<std::vector<size_t>> &loops, const HalfEdgeMap &halfEdges, size_t firstTriangle,
-        size_t triangleCount, std::vector<std::vector<size_t>> &groups);
+    void growFaceGroups(const std::vector<std::vector<size_t>> &loops, const HalfEdgeMap &halfEdges, const UncutTopology &uncut,
+        size_t firstTriangle, size_t triangleCount, std::vector<std::vector<size_t>> &groups);
     bool classifyGroups(const std::vector<std::vector<size_t>> &groups, const SolidMesh *against, std::vector<bool> &inside);
 
     const SolidMesh *m_firstMesh = nullptr;
@@ -85,7 +95,7 @@ private:
     std::vector<uint32_t> m_hitPairs;  // 2 per intersecting pair, sorted by (first, second)
     std::vector<double> m_hitSegments; // 6 per intersecting pair
     std::vector<Vector3> m_newVertices;
-    std::vector<std::vector<size_t>> m_newTriangles;
+    std::vector<std::array<size_t, 3>> m_newTriangles; // flat triples; fetch* turns them into the reference's vectors
     std::map<PositionKey, size_t> m_weldMap;
     std::vector<std::vector<size_t>> m_firstGroups, m_secondGroups;
     std::vector<bool> m_firstGroupInside, m_secondGroupInside;

@@ -21,6 +21,9 @@ void sbo_classify(const double *xyz, const uint32_t *tri, size_t nT, const doubl
     uint8_t *perAxis, uint64_t *candCount);
 int sbo_uncut_half_edges(const uint32_t *tri, size_t nT, const uint8_t *cut, uint64_t vertexOffset, uint64_t triangleOffset,
     uint32_t *outFace, size_t *nTriOut, uint64_t *outKeys, uint32_t *outOwner, size_t *nKeysOut);
+void sbo_uncut_adjacency(const uint32_t *tri, const uint32_t *face, size_t nTri, uint64_t vertexOffset,
+    const uint64_t *keys, const uint32_t *owner, size_t nKeys, int32_t *adj);
+size_t sbo_uncut_components(const int32_t *adj, size_t nTri, uint64_t triangleOffset, uint32_t *label);
 }
 
 struct sb_context { int dummy; };
@@ -35,6 +38,8 @@ struct sb_isect {
     std::vector<double> hitSeg;
 };
 struct sb_uncut {
+    const sb_mesh *mesh = nullptr;
+    uint64_t vertexOffset = 0, triangleOffset = 0;
     int ok = 1;
     std::vector<uint32_t> face, tri3, owner;
     std::vector<uint64_t> keys;
@@ -106,6 +111,9 @@ int sb_isect_uncut(const sb_isect *x, int which, size_t vertexOffset, size_t tri
     for (size_t h = 0; h < x->hitAB.size() / 2; ++h)
         cut[x->hitAB[2 * h + which]] = 1;
     sb_uncut *u = new sb_uncut;
+    u->mesh = m;
+    u->vertexOffset = vertexOffset;
+    u->triangleOffset = triangleOffset;
     u->face.resize(nT + 1);
     u->keys.resize(3 * nT + 1);
     u->owner.resize(3 * nT + 1);
@@ -139,6 +147,23 @@ int sb_uncut_half_edges(const sb_uncut *u, uint64_t *keys, uint32_t *owner)
 {
     if (keys && !u->keys.empty()) std::memcpy(keys, u->keys.data(), 8 * u->keys.size());
     if (owner && !u->owner.empty()) std::memcpy(owner, u->owner.data(), 4 * u->owner.size());
+    return SB_OK;
+}
+int sb_uncut_adjacency(const sb_uncut *u, int32_t *adj3)
+{
+    if (!u->face.empty())
+        sbo_uncut_adjacency(u->mesh->tri.data(), u->face.data(), u->face.size(), u->vertexOffset, u->keys.data(),
+            u->owner.data(), u->keys.size(), adj3);
+    return SB_OK;
+}
+int sb_uncut_components(const sb_uncut *u, uint32_t *label, size_t *n)
+{
+    std::vector<int32_t> adj(3 * u->face.size() + 3);
+    sb_uncut_adjacency(u, adj.data());
+    std::vector<uint32_t> lab(u->face.size() + 1);
+    size_t c = sbo_uncut_components(adj.data(), u->face.size(), u->triangleOffset, lab.data());
+    if (label && !u->face.empty()) std::memcpy(label, lab.data(), 4 * u->face.size());
+    if (n) *n = c;
     return SB_OK;
 }
 int sb_classify(const sb_mesh *t, const double *pts, size_t Q, uint8_t *inside, uint8_t *per_axis)
