@@ -524,6 +524,11 @@ def run_ours(args):
                             "note": "shard of rank 0" if world > 1 else "whole workload"}
         except Exception as e:  # the microbenchmark must never break the bench line
             line["fp64"] = {"error": str(e)}
+        if world == 1:
+            try:
+                line["next_rows"] = next_rows(sb, ctx, ma, mb, a, b, not args.no_cpu_baseline)
+            except Exception as e:  # evidence for the widened rows, never allowed to break the bench line
+                line["next_rows"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             sec, Href, detail = cpu_reference_step(a, b, 32768, threads)
@@ -544,6 +549,63 @@ def run_ours(args):
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(0)  # skip interpreter teardown: CUDA objects of two runtimes have no defined order there
+
+
+def next_rows(sb, ctx, ma, mb, a, b, with_cpu):
+    """SURVEY 8f rows 2-3, outside the timed step: uncut triangles + half-edge map
+    (addUnintersectedTriangles, reference src/solidboolean.cpp:250-286) and the face groups of the
+    uncut triangles (the flood of buildFaceGroups, :229-238) on the device, device time from the
+    library's stage events; beside them the reference's own two functions on one host core."""
+    ctx.enable_timing(True)
+    ma.build(); mb.build()
+    x = ma.intersect(mb)
+    best = None
+    for _ in range(4):
+        ctx.reset_timing()
+        ua = x.uncut(0, 0, 0)
+        ub = x.uncut(1, len(a[0]), ua.num_triangles)
+        he_ms = ctx.timing()[0]["halfedge"]
+        ctx.reset_timing()
+        ga, gb = ua.components()[1], ub.components()[1]
+        cc_ms = ctx.timing()[0]["halfedge"]
+        rec = {"halfedge_ms": round(he_ms, 4), "components_ms": round(cc_ms, 4),
+               "uncut_triangles": [ua.num_triangles, ub.num_triangles], "face_groups": [ga, gb], "ok": [ua.ok, ub.ok]}
+        if best is None or he_ms + cc_ms < best["halfedge_ms"] + best["components_ms"]:
+            best = rec
+        keep = (ua.half_edges(), ub.half_edges(), ua.components()[0], ub.components()[0]) if with_cpu and _ == 3 else None
+        ua.close(); ub.close()
+    fa, fb = x.face_flags()
+    x.close()
+    ctx.enable_timing(False)
+
+    def bits_for(n):
+        k = 1
+        while (1 << k) < n:
+            k += 1
+        return k
+    total = 0
+    for m, voff, n in ((a, 0, best["uncut_triangles"][0]), (b, len(a[0]), best["uncut_triangles"][1])):
+        passes = (2 * bits_for(voff + len(m[0])) + 7) // 8
+        total += 13 * len(m[1]) + 16 * n + 36 * n + 72 * n * passes + 84 * n     # DESIGN section 4
+    best["halfedge_algorithmic_bytes"] = total
+    best["halfedge_gbs_algorithmic"] = round(total / (best["halfedge_ms"] * 1e-3) / 1e9, 1) if best["halfedge_ms"] > 0 else None
+    if with_cpu:
+        from oracle import Ref
+        if Ref.available():
+            R = Ref.get()
+            op = R.op(R.mesh(*a), R.mesh(*b))
+            (ra, rb), _t = op.uncut(fa, fb)
+            la, _ga = op.uncut_groups(0, best["uncut_triangles"][0])
+            lb, _gb = op.uncut_groups(1, best["uncut_triangles"][1])
+            (ka, oa), (kb, ob), ca, cb = keep
+            best["reference_cpu"] = {
+                "cores": 1, "addUnintersectedTriangles_ms": round(op.uncut_ms(0, 0) + op.uncut_ms(0, 1), 1),
+                "buildFaceGroups_ms": round(op.uncut_ms(1, 0) + op.uncut_ms(1, 1), 1),
+                "identical": bool(np.array_equal(ra["keys"], ka) and np.array_equal(ra["owner"], oa)
+                                  and np.array_equal(rb["keys"], kb) and np.array_equal(rb["owner"], ob)
+                                  and np.array_equal(la, ca) and np.array_equal(lb, cb))}
+            op.close()
+    return best
 
 
 def _as_tensor(torch, ptr, shape, dtype, dev):

@@ -1485,6 +1485,7 @@ static int uncut_run(const sb_mesh *mesh, const uint8_t *dCut, size_t vertexOffs
     uint32_t *tileScratch = nullptr;
     SB_TRY(alloc_async(c, &tileScratch, sbk_uncut_tiles(d.nT), &u->owned));
     SB_CUDA_X(cudaMemsetAsync(&c->dScalars->heRepeat, 0xff, sizeof(unsigned int), c->stream));
+    SB_CUDA_X(cudaMemsetAsync(&c->dScalars->err, 0, sizeof(int), c->stream));
     SB_CUDA_X(sbk_uncut_count(c->stream, dCut, d.nT, tileScratch, &c->dScalars->uncutTotal, c->lc));
     // the number of uncut faces sizes everything that follows (one 128-byte read-back)
     SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -1492,7 +1493,7 @@ static int uncut_run(const sb_mesh *mesh, const uint8_t *dCut, size_t vertexOffs
     u->nTri = c->hScalars->uncutTotal;
     const size_t n = 3 * (size_t)u->nTri;
     if (n) {
-        const unsigned bitsV = bits_for(vertexOffset + d.nV);
+        const unsigned bitsV = bits_for(d.nV); // keys are sorted on the mesh's own vertex ids
         unsigned long long *k0 = nullptr, *k1 = nullptr, *sk = nullptr;
         uint32_t *o0 = nullptr, *o1 = nullptr, *so = nullptr;
         SB_TRY(alloc_async(c, &u->face, u->nTri, &u->owned));
@@ -1504,17 +1505,21 @@ static int uncut_run(const sb_mesh *mesh, const uint8_t *dCut, size_t vertexOffs
         SB_TRY(alloc_async(c, &u->owner, n, &u->owned));
         SB_TRY(alloc_async(c, &u->adj, n, &u->owned));
         SB_TRY(ensure_radix_ws(c, n));
-        SB_CUDA_X(sbk_uncut_emit(c->stream, dCut, d.tri, d.nT, tileScratch, u->vertexOffset, bitsV, u->face, u->tri3, k0, o0,
+        SB_CUDA_X(sbk_uncut_emit(c->stream, dCut, d.tri, d.nT, d.nV, &c->dScalars->err, tileScratch, u->vertexOffset, bitsV, u->face, u->tri3, k0, o0,
             c->lc));
         SB_CUDA_X(sbk_sort_keys(c->stream, k0, k1, o0, o1, n, 0, (int)(2 * bitsV), c->radixWs, c->smCount, &sk, &so, c->lc));
         // the reference-format keys go to whichever key buffer the sort left free
         u->keys = sk == k0 ? k1 : k0;
         u->ords = so;
-        SB_CUDA_X(sbk_halfedge_link(c->stream, sk, so, (uint32_t)n, bitsV, u->triangleOffset, u->keys, u->owner, u->adj,
-            &c->dScalars->heRepeat, c->lc));
+        uint32_t *vstart = nullptr;
+        SB_TRY(alloc_async(c, &vstart, d.nV, &u->owned));
+        SB_CUDA_X(sbk_halfedge_link(c->stream, sk, so, (uint32_t)n, bitsV, d.nV, vstart, u->vertexOffset, u->triangleOffset,
+            u->keys, u->owner, u->adj, &c->dScalars->heRepeat, c->lc));
         SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA_X(cudaStreamSynchronize(c->stream));
         u->repeatOrd = c->hScalars->heRepeat;
+        if (c->hScalars->err)
+            return bail(fail(SB_ERR_INVALID, "triangle index out of range"));
     }
 #undef SB_TRY
 #undef SB_CUDA_X
@@ -1723,7 +1728,7 @@ int sb_uncut_components(const sb_uncut *uc, uint32_t *label, size_t *n_component
         uint32_t *parent = nullptr;
         int r = alloc_async(c, &u->label, u->nTri, &u->owned);
         if (!r)
-            r = alloc_async(c, &parent, u->nTri, nullptr);
+            r = alloc_async(c, &parent, 2 * (size_t)u->nTri, nullptr);
         if (r)
             return r;
         SB_CUDA(cudaMemsetAsync(&c->dScalars->ccCount, 0, sizeof(unsigned int), c->stream));

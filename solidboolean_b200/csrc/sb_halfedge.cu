@@ -115,59 +115,90 @@ __global__ void __launch_bounds__(1024) uncut_scan_kernel(uint32_t *__restrict__
 }
 
 // New triangle `rank` = original face i: the face id, the shifted index triple, and its three
-// keys with the reference's insertion ordinal 3 * rank + k as value.  Keys are packed as
-// (first << bitsV) | second (same order as the reference's (first << 32) | second, fewer
-// radix passes).
+// keys with the reference's insertion ordinal 3 * rank + k as value.  Keys are packed from the
+// mesh's own vertex ids as (first << bitsV) | second, bitsV = bits of nV: same order as the
+// reference's ((first + offset) << 32) | (second + offset), fewer radix passes.
+// Faces are taken in stripes (item s of thread t = face tile + s * 256 + t): neighbouring threads
+// read neighbouring triples and, ranks being prefix counts in face order, write neighbouring
+// records.
 __global__ void __launch_bounds__(HE_THREADS) uncut_emit_kernel(const uint8_t *__restrict__ cut,
-    const uint32_t *__restrict__ tri, uint32_t nT, const uint32_t *__restrict__ tileOffset, uint32_t vertexOffset,
-    unsigned bitsV, uint32_t *__restrict__ face, uint32_t *__restrict__ tri3, unsigned long long *__restrict__ keys,
-    uint32_t *__restrict__ ords)
+    const uint32_t *__restrict__ tri, uint32_t nT, uint32_t nV, int *__restrict__ err,
+    const uint32_t *__restrict__ tileOffset, uint32_t vertexOffset, unsigned bitsV, uint32_t *__restrict__ face,
+    uint32_t *__restrict__ tri3, unsigned long long *__restrict__ keys, uint32_t *__restrict__ ords)
 {
-    __shared__ uint32_t s_warp[HE_THREADS / 32];
+    constexpr int WARPS = HE_THREADS / 32;
+    __shared__ uint32_t s_cnt[HE_ITEMS * WARPS]; // uncut faces per (stripe, warp), then their exclusive scan
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t base = blockIdx.x * HE_TILE + threadIdx.x * HE_ITEMS;
-    const uint32_t mask = uncut_mask8(cut, base, nT);
-    const uint32_t mine = __popc(mask);
-    uint32_t incl = mine;
+    const uint32_t tile = blockIdx.x * HE_TILE;
+    uint32_t before[HE_ITEMS]; // uncut faces of this warp's stripe segment below this lane
+    uint32_t keep = 0;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
-        if (lane >= off)
-            incl += t;
+    for (int s = 0; s < HE_ITEMS; ++s) {
+        const uint32_t f = tile + s * HE_THREADS + threadIdx.x;
+        const bool uncut = f < nT && !(cut && __ldg(cut + f));
+        const unsigned b = __ballot_sync(SB_FULL, uncut);
+        before[s] = __popc(b & lanemask_lt());
+        keep |= (uncut ? 1u : 0u) << s;
+        if (lane == 0)
+            s_cnt[s * WARPS + warp] = __popc(b);
     }
-    if (lane == 31)
-        s_warp[warp] = incl;
     __syncthreads();
-    uint32_t rank = tileOffset[blockIdx.x] + incl - mine;
-    for (int w = 0; w < warp; ++w)
-        rank += s_warp[w];
+    if (threadIdx.x < 32) { // exclusive scan of the 64 counts (two per lane), in face order
+        const uint32_t c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        uint32_t incl = c0 + c1;
 #pragma unroll
-    for (int i = 0; i < HE_ITEMS; ++i) {
-        if (!(mask >> i & 1u))
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(SB_FULL, incl, off);
+            if (lane >= off)
+                incl += t;
+        }
+        s_cnt[2 * lane] = incl - c0 - c1;
+        s_cnt[2 * lane + 1] = incl - c1;
+    }
+    __syncthreads();
+    const uint32_t tileRank = tileOffset[blockIdx.x];
+#pragma unroll
+    for (int s = 0; s < HE_ITEMS; ++s) {
+        if (!(keep >> s & 1u))
             continue;
-        const uint32_t f = base + i;
-        const uint32_t v0 = __ldg(tri + 3 * (size_t)f) + vertexOffset, v1 = __ldg(tri + 3 * (size_t)f + 1) + vertexOffset,
-                       v2 = __ldg(tri + 3 * (size_t)f + 2) + vertexOffset;
+        const uint32_t f = tile + s * HE_THREADS + threadIdx.x;
+        const uint32_t rank = tileRank + s_cnt[s * WARPS + warp] + before[s];
+        uint32_t v0 = __ldg(tri + 3 * (size_t)f), v1 = __ldg(tri + 3 * (size_t)f + 1), v2 = __ldg(tri + 3 * (size_t)f + 2);
+        if (v0 >= nV || v1 >= nV || v2 >= nV) { // the packed keys and the vertex index only hold ids below nV:
+            *err = 1;                           // reported as SB_ERR_INVALID by the host
+            v0 = v1 = v2 = 0;
+        }
         face[rank] = f;
         const size_t o = 3 * (size_t)rank;
-        tri3[o] = v0;
-        tri3[o + 1] = v1;
-        tri3[o + 2] = v2;
+        tri3[o] = v0 + vertexOffset;
+        tri3[o + 1] = v1 + vertexOffset;
+        tri3[o + 2] = v2 + vertexOffset;
         keys[o] = ((unsigned long long)v0 << bitsV) | v1;
         keys[o + 1] = ((unsigned long long)v1 << bitsV) | v2;
         keys[o + 2] = ((unsigned long long)v2 << bitsV) | v0;
         ords[o] = (uint32_t)o;
         ords[o + 1] = (uint32_t)o + 1;
         ords[o + 2] = (uint32_t)o + 2;
-        ++rank;
     }
+}
+
+// First sorted entry of every vertex that starts a half-edge (vstart was filled with 0xff).
+__global__ void __launch_bounds__(256) halfedge_vstart_kernel(const unsigned long long *__restrict__ keys, uint32_t n,
+    unsigned bitsV, uint32_t *__restrict__ vstart)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n)
+        return;
+    const uint32_t first = (uint32_t)(__ldg(keys + p) >> bitsV);
+    if (p == 0 || (uint32_t)(__ldg(keys + p - 1) >> bitsV) != first)
+        vstart[first] = p;
 }
 
 // One thread per sorted half-edge.
 __global__ void __launch_bounds__(256) halfedge_link_kernel(const unsigned long long *__restrict__ keys,
-    const uint32_t *__restrict__ ords, uint32_t n, unsigned bitsV, uint32_t triangleOffset,
-    unsigned long long *__restrict__ refKeys, uint32_t *__restrict__ owner, int32_t *__restrict__ adj,
-    uint32_t *__restrict__ firstRepeat)
+    const uint32_t *__restrict__ ords, uint32_t n, unsigned bitsV, uint32_t vertexOffset, uint32_t triangleOffset,
+    const uint32_t *__restrict__ vstart, unsigned long long *__restrict__ refKeys, uint32_t *__restrict__ owner,
+    int32_t *__restrict__ adj, uint32_t *__restrict__ firstRepeat)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n)
@@ -180,29 +211,69 @@ __global__ void __launch_bounds__(256) halfedge_link_kernel(const unsigned long 
         atomicMin(firstRepeat, ord);
     const unsigned long long lowMask = (1ull << bitsV) - 1ull;
     const unsigned long long from = key >> bitsV, to = key & lowMask;
-    refKeys[p] = (from << 32) | to;
+    refKeys[p] = ((from + vertexOffset) << 32) | (to + vertexOffset);
     owner[p] = triangleOffset + ord / 3u;
-    // the opposite half-edge (to, from): lower bound in the sorted keys
+    // the opposite half-edge (to, from) sits among the entries that start at `to`: a handful
+    // (the vertex's valence), walked from their first one; a vertex with a huge fan falls back
+    // to a binary search of the rest
     const unsigned long long want = (to << bitsV) | from;
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(keys + mid) < want)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
     int32_t other = -1;
-    if (lo < n && __ldg(keys + lo) == want)
-        other = (int32_t)(triangleOffset + __ldg(ords + lo) / 3u);
+    uint32_t q = __ldg(vstart + to);
+    if (q != 0xffffffffu) {
+        int steps = 0;
+        while (q < n && __ldg(keys + q) < want && ++steps < 16)
+            ++q;
+        if (steps == 16) {
+            uint32_t lo = q, hi = n;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (__ldg(keys + mid) < want)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            q = lo;
+        }
+        if (q < n && __ldg(keys + q) == want)
+            other = (int32_t)(triangleOffset + __ldg(ords + q) / 3u);
+    }
     adj[ord] = other;
 }
 
 // ---- connected components of the uncut triangles -----------------------------------------
 // buildFaceGroups' flood (reference src/solidboolean.cpp:229-238) without the queue: lock-free
-// union-find over the adjacency array.  A root only ever gets a SMALLER root as parent, so
-// every component ends up rooted at its lowest triangle index -- the triangle the reference's
-// loop over ascending indices would have opened the group with -- whatever the thread order.
+// union-find over the adjacency array, label = lowest triangle index of the component -- the
+// triangle the reference's loop over ascending indices opens the group with -- whatever the
+// thread order.
+//
+// Uncut triangles keep the mesh's own order, in which neighbours sit close together (strips,
+// subdivision patches) -- or not at all.  Hanging the larger INDEX under the smaller one grows
+// paths, not trees (i under i - 1 under i - 2 ...), and a find that walks such a path is a chain
+// of dependent L2 round trips.
+//   pass 1  cc_tile   union-find by index inside tiles of CC_TILE consecutive triangles, in
+//                     shared memory: the long paths are walked at shared-memory latency; every
+//                     triangle leaves pointing at its tile root (lowest member in the tile)
+//   pass 2  cc_hook   edges that leave a tile, on the global array, linking by a hashed
+//                     priority instead of the index: random linking keeps the trees of tile
+//                     roots O(log) deep
+//   pass 3  cc_min    the lowest tile root of every tree (atomicMin at the tree's root)
+//   pass 4  cc_label  label = that minimum; roots counted
+constexpr int CC_TILE = 1024;
+constexpr int CC_THREADS = 256;
+
+// a bijection of the 32-bit ids (murmur3's finaliser) whose order looks random: tile roots are
+// mostly multiples of the tile size, and a multiplicative hash keeps long monotone runs along
+// arithmetic progressions of them -- exactly the paths the random linking is there to avoid
+__device__ __forceinline__ uint32_t cc_prio(uint32_t x)
+{
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+
 __device__ __forceinline__ uint32_t cc_find(uint32_t *parent, uint32_t x)
 {
     uint32_t p = __ldcg(parent + x);
@@ -216,35 +287,98 @@ __device__ __forceinline__ uint32_t cc_find(uint32_t *parent, uint32_t x)
     return x;
 }
 
-__global__ void __launch_bounds__(256) cc_init_kernel(uint32_t *__restrict__ parent, uint32_t n)
+__device__ __forceinline__ uint32_t cc_find_s(volatile uint32_t *sp, uint32_t x)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n)
-        parent[i] = i;
+    uint32_t p = sp[x];
+    while (p != x) {
+        const uint32_t g = sp[p];
+        if (g != p)
+            sp[x] = g;
+        x = p;
+        p = g;
+    }
+    return x;
 }
 
+__global__ void __launch_bounds__(CC_THREADS) cc_tile_kernel(const int32_t *__restrict__ adj, uint32_t n,
+    uint32_t triangleOffset, uint32_t *__restrict__ parent, uint32_t *__restrict__ tileRoot)
+{
+    __shared__ uint32_t sp[CC_TILE];
+    const uint32_t tileStart = blockIdx.x * CC_TILE;
+    for (uint32_t l = threadIdx.x; l < CC_TILE; l += CC_THREADS)
+        sp[l] = l;
+    __syncthreads();
+    for (uint32_t l = threadIdx.x; l < CC_TILE; l += CC_THREADS) {
+        const uint32_t i = tileStart + l;
+        if (i >= n)
+            break;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int32_t o = __ldg(adj + 3 * (size_t)i + k);
+            if (o < 0)
+                continue;
+            const uint32_t j = (uint32_t)o - triangleOffset;
+            if (j >= i || j < tileStart)
+                continue; // each edge once, from its larger end; other tiles: pass 2
+            uint32_t a = cc_find_s(sp, l), b = cc_find_s(sp, j - tileStart);
+            while (a != b) {
+                if (a < b) {
+                    const uint32_t t = a;
+                    a = b;
+                    b = t;
+                }
+                const uint32_t old = atomicCAS(sp + a, a, b); // the larger index under the smaller
+                if (old == a)
+                    break;
+                a = cc_find_s(sp, old);
+                b = cc_find_s(sp, b);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t l = threadIdx.x; l < CC_TILE; l += CC_THREADS)
+        if (tileStart + l < n) {
+            const uint32_t r = tileStart + cc_find_s(sp, l);
+            parent[tileStart + l] = r;
+            tileRoot[tileStart + l] = r;
+        }
+}
+
+// Pass 2: the edges that leave a tile towards lower indices.  Each joins two TILE roots, both
+// known from pass 1 without a find; where the face order is spatially coherent the 32
+// consecutive triangles of a warp mostly cross into the same neighbouring patch, so one lane per
+// distinct pair does the union.  (Face orders without locality -- e.g. a subdivision that emits
+// all first children, then all second children -- leave ~n tile roots: then this pass is a plain
+// global union-find, ~0.35 ns per link, bound by the compare-and-swap rate of L2.)
 __global__ void __launch_bounds__(256) cc_hook_kernel(const int32_t *__restrict__ adj, uint32_t n, uint32_t triangleOffset,
-    uint32_t *parent)
+    const uint32_t *__restrict__ tileRoot, uint32_t *parent)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
+    const bool live = i < n;
+    const uint32_t tileStart = i & ~(uint32_t)(CC_TILE - 1);
+    const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int32_t o = __ldg(adj + 3 * (size_t)i + k);
-        if (o < 0)
+        unsigned long long pair = ~0ull - lane; // no edge: a key nobody shares (bit 63 set; tile roots are below 2^31)
+        if (live) {
+            const int32_t o = __ldg(adj + 3 * (size_t)i + k);
+            if (o >= 0) {
+                const uint32_t j = (uint32_t)o - triangleOffset;
+                if (j < tileStart)
+                    pair = ((unsigned long long)__ldg(tileRoot + i) << 32) | __ldg(tileRoot + j);
+            }
+        }
+        const unsigned same = __match_any_sync(SB_FULL, pair);
+        if ((pair >> 63) || lane != (uint32_t)(__ffs(same) - 1))
             continue;
-        const uint32_t j = (uint32_t)o - triangleOffset;
-        if (j >= i)
-            continue; // every edge once (the relation is symmetric), from its larger end
-        uint32_t a = cc_find(parent, i), b = cc_find(parent, j);
+        uint32_t a = cc_find(parent, (uint32_t)(pair >> 32)), b = cc_find(parent, (uint32_t)pair);
         while (a != b) {
-            if (a < b) {
+            if (cc_prio(a) < cc_prio(b)) {
                 const uint32_t t = a;
                 a = b;
                 b = t;
             }
-            const uint32_t old = atomicCAS(parent + a, a, b); // hang the larger root under the smaller
+            const uint32_t old = atomicCAS(parent + a, a, b); // the root of larger priority value under the other
             if (old == a)
                 break;
             a = cc_find(parent, old);
@@ -253,15 +387,28 @@ __global__ void __launch_bounds__(256) cc_hook_kernel(const int32_t *__restrict_
     }
 }
 
+// every tile root reports itself to the root of its tree; minIdx was filled with 0xff.  Blocks
+// start in ascending order, so after the first few reports the rest only read and leave.
+__global__ void __launch_bounds__(256) cc_min_kernel(uint32_t *parent, const uint32_t *__restrict__ tileRoot, uint32_t n,
+    uint32_t *minIdx)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && __ldg(tileRoot + i) == i) {
+        uint32_t *slot = minIdx + cc_find(parent, i);
+        if (i < __ldcg(slot))
+            atomicMin(slot, i);
+    }
+}
+
 __global__ void __launch_bounds__(256) cc_label_kernel(uint32_t *parent, uint32_t n, uint32_t triangleOffset,
-    uint32_t *__restrict__ label, uint32_t *__restrict__ count)
+    const uint32_t *minIdx, uint32_t *__restrict__ label, uint32_t *__restrict__ count)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     uint32_t r = 0;
     if (live) {
         r = cc_find(parent, i);
-        label[i] = r + triangleOffset;
+        label[i] = __ldcg(minIdx + r) + triangleOffset;
     }
     const unsigned roots = __ballot_sync(SB_FULL, live && r == i);
     if ((threadIdx.x & 31) == 0 && roots)
@@ -270,17 +417,20 @@ __global__ void __launch_bounds__(256) cc_label_kernel(uint32_t *parent, uint32_
 
 } // namespace
 
-// parent: n words of scratch; label: n; *count (device, zeroed by the caller) += components
-cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *parent,
+// scratch: 2 n words; label: n; *count (device, zeroed by the caller) += components
+cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *scratch,
     uint32_t *label, uint32_t *count, LaunchCounter &lc)
 {
     if (n == 0)
         return cudaSuccess;
     const uint32_t blocks = (n + 255) / 256;
-    cc_init_kernel<<<blocks, 256, 0, s>>>(parent, n);
-    cc_hook_kernel<<<blocks, 256, 0, s>>>(adj, n, triangleOffset, parent);
-    cc_label_kernel<<<blocks, 256, 0, s>>>(parent, n, triangleOffset, label, count);
-    lc.kernels += 3;
+    uint32_t *parent = scratch, *minIdx = scratch + n;
+    cudaMemsetAsync(minIdx, 0xff, sizeof(uint32_t) * (size_t)n, s);
+    cc_tile_kernel<<<(n + CC_TILE - 1) / CC_TILE, CC_THREADS, 0, s>>>(adj, n, triangleOffset, parent, label /* tile roots */);
+    cc_hook_kernel<<<blocks, 256, 0, s>>>(adj, n, triangleOffset, label, parent);
+    cc_min_kernel<<<blocks, 256, 0, s>>>(parent, label, n, minIdx);
+    cc_label_kernel<<<blocks, 256, 0, s>>>(parent, n, triangleOffset, minIdx, label, count);
+    lc.kernels += 4;
     return cudaGetLastError();
 }
 
@@ -300,26 +450,30 @@ cudaError_t sbk_uncut_count(cudaStream_t s, const uint8_t *cut, uint32_t nT, uin
     return cudaGetLastError();
 }
 
-cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *tri, uint32_t nT, const uint32_t *tileScratch,
-    uint32_t vertexOffset, unsigned bitsV, uint32_t *face, uint32_t *tri3, unsigned long long *keys, uint32_t *ords,
+cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *tri, uint32_t nT, uint32_t nV, int *err,
+    const uint32_t *tileScratch, uint32_t vertexOffset, unsigned bitsV, uint32_t *face, uint32_t *tri3, unsigned long long *keys, uint32_t *ords,
     LaunchCounter &lc)
 {
     const uint32_t tiles = sbk_uncut_tiles(nT);
     if (tiles == 0)
         return cudaSuccess;
-    uncut_emit_kernel<<<tiles, HE_THREADS, 0, s>>>(cut, tri, nT, tileScratch, vertexOffset, bitsV, face, tri3, keys, ords);
+    uncut_emit_kernel<<<tiles, HE_THREADS, 0, s>>>(cut, tri, nT, nV, err, tileScratch, vertexOffset, bitsV, face, tri3, keys,
+        ords);
     lc.kernels += 1;
     return cudaGetLastError();
 }
 
+// vstart: nV words of scratch
 cudaError_t sbk_halfedge_link(cudaStream_t s, const unsigned long long *sortedKeys, const uint32_t *sortedOrds, uint32_t n,
-    unsigned bitsV, uint32_t triangleOffset, unsigned long long *refKeys, uint32_t *owner, int32_t *adj,
+    unsigned bitsV, uint32_t nV, uint32_t *vstart, uint32_t vertexOffset, uint32_t triangleOffset, unsigned long long *refKeys, uint32_t *owner, int32_t *adj,
     uint32_t *firstRepeat, LaunchCounter &lc)
 {
     if (n == 0)
         return cudaSuccess;
-    halfedge_link_kernel<<<(n + 255) / 256, 256, 0, s>>>(sortedKeys, sortedOrds, n, bitsV, triangleOffset, refKeys, owner, adj,
-        firstRepeat);
-    lc.kernels += 1;
+    cudaMemsetAsync(vstart, 0xff, sizeof(uint32_t) * (size_t)nV, s);
+    halfedge_vstart_kernel<<<(n + 255) / 256, 256, 0, s>>>(sortedKeys, n, bitsV, vstart);
+    halfedge_link_kernel<<<(n + 255) / 256, 256, 0, s>>>(sortedKeys, sortedOrds, n, bitsV, vertexOffset, triangleOffset, vstart,
+        refKeys, owner, adj, firstRepeat);
+    lc.kernels += 2;
     return cudaGetLastError();
 }

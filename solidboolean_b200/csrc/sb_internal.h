@@ -101,13 +101,13 @@ cudaError_t sbk_sort_keys(cudaStream_t s, unsigned long long *keys, unsigned lon
 uint32_t sbk_uncut_tiles(uint32_t nT);
 cudaError_t sbk_uncut_count(cudaStream_t s, const uint8_t *cut /* nT bytes or null */, uint32_t nT, uint32_t *tileScratch,
     uint32_t *total, LaunchCounter &lc);
-cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *tri, uint32_t nT, const uint32_t *tileScratch,
-    uint32_t vertexOffset, unsigned bitsV, uint32_t *face, uint32_t *tri3, unsigned long long *keys, uint32_t *ords,
+cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *tri, uint32_t nT, uint32_t nV, int *err,
+    const uint32_t *tileScratch, uint32_t vertexOffset, unsigned bitsV, uint32_t *face, uint32_t *tri3, unsigned long long *keys, uint32_t *ords,
     LaunchCounter &lc);
 cudaError_t sbk_halfedge_link(cudaStream_t s, const unsigned long long *sortedKeys, const uint32_t *sortedOrds, uint32_t n,
-    unsigned bitsV, uint32_t triangleOffset, unsigned long long *refKeys, uint32_t *owner, int32_t *adj,
-    uint32_t *firstRepeat, LaunchCounter &lc);
-cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *parent,
+    unsigned bitsV, uint32_t nV, uint32_t *vstart /* nV words of scratch */, uint32_t vertexOffset, uint32_t triangleOffset,
+    unsigned long long *refKeys, uint32_t *owner, int32_t *adj, uint32_t *firstRepeat, LaunchCounter &lc);
+cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *scratch /* 2 n */,
     uint32_t *label, uint32_t *count, LaunchCounter &lc);
 
 // sb_classify.cu

@@ -145,3 +145,13 @@ def test_uncut_config_c3_full_size(ctx, oracle):
         assert np.all((back == (j + base)[:, None]).any(axis=1))
     assert int((ua.adjacency() < 0).sum()) > 0 and ua.num_triangles + int(fa.sum()) == len(a[1])
     ua.close(); ub.close(); x.close(); ma.close(); mb.close()
+
+
+def test_uncut_rejects_out_of_range_indices(ctx):
+    tor = meshgen.torus(16, 8)
+    bad = tor[1].copy()
+    bad[5, 1] = len(tor[0]) + 3
+    m = ctx.mesh(tor[0], bad, build=False)
+    with pytest.raises(sb.SolidBooleanError):
+        m.uncut(None, 0, 0)
+    m.close()

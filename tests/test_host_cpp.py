@@ -195,11 +195,10 @@ def test_drop_in_classes_config_c3_gpu(real_lib):
     assert (res["P"], res["H"]) == (36125, 9606)
     v = res["vertices"]
     for name in ("union", "diff", "intersect"):
-        # Known limit of the host retriangulation at this tessellation (the
-        # reference's absolute-epsilon attach test): a few dozen of ~4 M half-edges end up without
-        # a partner (T-junctions where a segment end was snapped onto an edge whose other face is
-        # not split).  The triangle-by-triangle flood of the reference gives the same count
-        # (SB_HOST_FLOOD=legacy), so it is not an effect of the GPU face groups.
+        # Known limit: where the curve passes through a mesh vertex the cut
+        # faces around it get a new point ~4e-7 away from that vertex while the face it only touches
+        # keeps the original vertex; the reference's algorithm never welds the two, so a few dozen of
+        # ~4 M half-edges have no partner.  Same count with SB_HOST_FLOOD=legacy.
         t = res[name].astype(np.int64)
         he = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
         keys = he[:, 0] << 32 | he[:, 1]
