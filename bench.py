@@ -259,6 +259,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its banner / debug lines to stdout by default: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not os.path.exists(sb.LIB_PATH):
         if local == 0:

@@ -1726,14 +1726,19 @@ int sb_uncut_components(const sb_uncut *uc, uint32_t *label, size_t *n_component
     if (!u->label) {
         StageTimer timer(c, SB_STAGE_HALFEDGE);
         uint32_t *parent = nullptr;
+        // union-find in the mesh's Morton order when it has one (spatially coherent tiles)
+        const MeshDev &d = u->mesh->d;
+        const bool ordered = u->mesh->built && d.sortedTri && !std::getenv("SB_CC_FACE_ORDER");
+        if (ordered)
+            use_mesh_leaves(c, u->mesh);
         int r = alloc_async(c, &u->label, u->nTri, &u->owned);
         if (!r)
-            r = alloc_async(c, &parent, 2 * (size_t)u->nTri, nullptr);
+            r = alloc_async(c, &parent, sbk_uncut_components_scratch(u->nTri, d.nT, ordered), nullptr);
         if (r)
             return r;
         SB_CUDA(cudaMemsetAsync(&c->dScalars->ccCount, 0, sizeof(unsigned int), c->stream));
-        SB_CUDA(sbk_uncut_components(c->stream, u->adj, u->nTri, u->triangleOffset, parent, u->label, &c->dScalars->ccCount,
-            c->lc));
+        SB_CUDA(sbk_uncut_components(c->stream, u->adj, u->nTri, u->triangleOffset, ordered ? d.sortedTri : nullptr, u->face, d.nT,
+            parent, u->label, &c->dScalars->ccCount, c->lc));
         cudaFreeAsync(parent, c->stream);
         SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA(cudaStreamSynchronize(c->stream));

@@ -246,20 +246,24 @@ __global__ void __launch_bounds__(256) halfedge_link_kernel(const unsigned long 
 // triangle the reference's loop over ascending indices opens the group with -- whatever the
 // thread order.
 //
-// Uncut triangles keep the mesh's own order, in which neighbours sit close together (strips,
-// subdivision patches) -- or not at all.  Hanging the larger INDEX under the smaller one grows
-// paths, not trees (i under i - 1 under i - 2 ...), and a find that walks such a path is a chain
-// of dependent L2 round trips.
-//   pass 1  cc_tile   union-find by index inside tiles of CC_TILE consecutive triangles, in
-//                     shared memory: the long paths are walked at shared-memory latency; every
-//                     triangle leaves pointing at its tile root (lowest member in the tile)
-//   pass 2  cc_hook   edges that leave a tile, on the global array, linking by a hashed
-//                     priority instead of the index: random linking keeps the trees of tile
-//                     roots O(log) deep
-//   pass 3  cc_min    the lowest tile root of every tree (atomicMin at the tree's root)
+// The NODES of the union-find are not the new triangles but positions in a spatially coherent
+// order: the mesh's Morton order when it has been built (pos2new / new2pos translate; cut faces
+// are isolated nodes), else the face order itself.  Face orders as they come have no locality
+// to speak of (a subdivision emits all first children, then all second ones; a grid all lower
+// triangles, then all upper ones), and without locality every link is an L2 compare-and-swap
+// on a tree whose finds are chains of dependent L2 loads.
+//   pass 1  cc_tile   union-find inside tiles of CC_TILE consecutive nodes, in shared memory;
+//                     every node leaves pointing at its tile root, which also carries the
+//                     lowest NEW TRIANGLE index of its tile component
+//   pass 2  cc_hook   edges that leave a tile, on the global array, one lane per distinct
+//                     (tile root, tile root) pair of a warp, linking by a hashed priority
+//                     instead of the position: random linking keeps the trees O(log) deep
+//                     (linking by index grows paths: i under i - 1 under i - 2 ...)
+//   pass 3  cc_min    the lowest triangle index of every tree (atomicMin at the tree's root)
 //   pass 4  cc_label  label = that minimum; roots counted
 constexpr int CC_TILE = 1024;
 constexpr int CC_THREADS = 256;
+constexpr uint32_t CC_NONE = 0xffffffffu;
 
 // a bijection of the 32-bit ids (murmur3's finaliser) whose order looks random: tile roots are
 // mostly multiples of the tile size, and a multiplicative hash keeps long monotone runs along
@@ -300,34 +304,68 @@ __device__ __forceinline__ uint32_t cc_find_s(volatile uint32_t *sp, uint32_t x)
     return x;
 }
 
-__global__ void __launch_bounds__(CC_THREADS) cc_tile_kernel(const int32_t *__restrict__ adj, uint32_t n,
-    uint32_t triangleOffset, uint32_t *__restrict__ parent, uint32_t *__restrict__ tileRoot)
+// node order = face order: position p is new triangle p
+__global__ void __launch_bounds__(256) cc_identity_kernel(uint32_t n, uint32_t *__restrict__ pos2new, uint32_t *__restrict__ new2pos)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        pos2new[i] = i;
+        new2pos[i] = i;
+    }
+}
+
+// node order = the mesh's Morton order.  faceRank (filled with 0xff): original face -> new triangle.
+__global__ void __launch_bounds__(256) cc_rank_kernel(const uint32_t *__restrict__ face, uint32_t nTri, uint32_t *__restrict__ faceRank)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nTri)
+        faceRank[__ldg(face + r)] = r;
+}
+
+__global__ void __launch_bounds__(256) cc_order_kernel(const uint32_t *__restrict__ sortedTri, const uint32_t *__restrict__ faceRank,
+    uint32_t nT, uint32_t *__restrict__ pos2new, uint32_t *__restrict__ new2pos)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nT)
+        return;
+    const uint32_t r = __ldg(faceRank + __ldg(sortedTri + p));
+    pos2new[p] = r;
+    if (r != CC_NONE)
+        new2pos[r] = p;
+}
+
+__global__ void __launch_bounds__(CC_THREADS) cc_tile_kernel(const int32_t *__restrict__ adj, uint32_t nodes,
+    uint32_t triangleOffset, const uint32_t *__restrict__ pos2new, const uint32_t *__restrict__ new2pos,
+    uint32_t *__restrict__ parent, uint32_t *__restrict__ tileRoot, uint32_t *__restrict__ minIdx)
 {
     __shared__ uint32_t sp[CC_TILE];
+    __shared__ uint32_t smin[CC_TILE];
     const uint32_t tileStart = blockIdx.x * CC_TILE;
-    for (uint32_t l = threadIdx.x; l < CC_TILE; l += CC_THREADS)
+    for (uint32_t l = threadIdx.x; l < CC_TILE; l += CC_THREADS) {
         sp[l] = l;
+        smin[l] = tileStart + l < nodes ? __ldg(pos2new + tileStart + l) : CC_NONE;
+    }
     __syncthreads();
     for (uint32_t l = threadIdx.x; l < CC_TILE; l += CC_THREADS) {
-        const uint32_t i = tileStart + l;
-        if (i >= n)
-            break;
+        const uint32_t r = smin[l]; // still this node's own triangle: the minima are formed after the next barrier
+        if (r == CC_NONE)
+            continue;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const int32_t o = __ldg(adj + 3 * (size_t)i + k);
+            const int32_t o = __ldg(adj + 3 * (size_t)r + k);
             if (o < 0)
                 continue;
-            const uint32_t j = (uint32_t)o - triangleOffset;
-            if (j >= i || j < tileStart)
-                continue; // each edge once, from its larger end; other tiles: pass 2
-            uint32_t a = cc_find_s(sp, l), b = cc_find_s(sp, j - tileStart);
+            const uint32_t q = __ldg(new2pos + ((uint32_t)o - triangleOffset));
+            if (q >= tileStart + l || q < tileStart)
+                continue; // each edge once, from its later end; other tiles: pass 2
+            uint32_t a = cc_find_s(sp, l), b = cc_find_s(sp, q - tileStart);
             while (a != b) {
-                if (a < b) {
+                if (cc_prio(a) < cc_prio(b)) {
                     const uint32_t t = a;
                     a = b;
                     b = t;
                 }
-                const uint32_t old = atomicCAS(sp + a, a, b); // the larger index under the smaller
+                const uint32_t old = atomicCAS(sp + a, a, b); // random linking here too: shallow trees
                 if (old == a)
                     break;
                 a = cc_find_s(sp, old);
@@ -336,36 +374,47 @@ __global__ void __launch_bounds__(CC_THREADS) cc_tile_kernel(const int32_t *__re
         }
     }
     __syncthreads();
-    for (uint32_t l = threadIdx.x; l < CC_TILE; l += CC_THREADS)
-        if (tileStart + l < n) {
-            const uint32_t r = tileStart + cc_find_s(sp, l);
-            parent[tileStart + l] = r;
-            tileRoot[tileStart + l] = r;
+    uint32_t root[CC_TILE / CC_THREADS], mine[CC_TILE / CC_THREADS];
+#pragma unroll
+    for (int s = 0; s < CC_TILE / CC_THREADS; ++s) {
+        const uint32_t l = threadIdx.x + s * CC_THREADS;
+        root[s] = cc_find_s(sp, l);
+        mine[s] = smin[l];
+    }
+    __syncthreads(); // everybody holds its own triangle: smin may now turn into the per-root minima
+#pragma unroll
+    for (int s = 0; s < CC_TILE / CC_THREADS; ++s)
+        if (mine[s] != CC_NONE && root[s] != threadIdx.x + s * CC_THREADS)
+            atomicMin(smin + root[s], mine[s]);
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < CC_TILE / CC_THREADS; ++s) {
+        const uint32_t l = threadIdx.x + s * CC_THREADS;
+        if (tileStart + l < nodes) {
+            parent[tileStart + l] = tileStart + root[s];
+            tileRoot[tileStart + l] = tileStart + root[s];
+            minIdx[tileStart + l] = root[s] == l ? smin[l] : CC_NONE;
         }
+    }
 }
 
-// Pass 2: the edges that leave a tile towards lower indices.  Each joins two TILE roots, both
-// known from pass 1 without a find; where the face order is spatially coherent the 32
-// consecutive triangles of a warp mostly cross into the same neighbouring patch, so one lane per
-// distinct pair does the union.  (Face orders without locality -- e.g. a subdivision that emits
-// all first children, then all second children -- leave ~n tile roots: then this pass is a plain
-// global union-find, ~0.35 ns per link, bound by the compare-and-swap rate of L2.)
-__global__ void __launch_bounds__(256) cc_hook_kernel(const int32_t *__restrict__ adj, uint32_t n, uint32_t triangleOffset,
-    const uint32_t *__restrict__ tileRoot, uint32_t *parent)
+__global__ void __launch_bounds__(256) cc_hook_kernel(const int32_t *__restrict__ adj, uint32_t nodes, uint32_t triangleOffset,
+    const uint32_t *__restrict__ pos2new, const uint32_t *__restrict__ new2pos, const uint32_t *__restrict__ tileRoot,
+    uint32_t *parent)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    const uint32_t tileStart = i & ~(uint32_t)(CC_TILE - 1);
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = p < nodes ? __ldg(pos2new + p) : CC_NONE;
+    const uint32_t tileStart = p & ~(uint32_t)(CC_TILE - 1);
     const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        unsigned long long pair = ~0ull - lane; // no edge: a key nobody shares (bit 63 set; tile roots are below 2^31)
-        if (live) {
-            const int32_t o = __ldg(adj + 3 * (size_t)i + k);
+        unsigned long long pair = ~0ull - lane; // no edge: a key nobody shares (bit 63 set; positions are below 2^31)
+        if (r != CC_NONE) {
+            const int32_t o = __ldg(adj + 3 * (size_t)r + k);
             if (o >= 0) {
-                const uint32_t j = (uint32_t)o - triangleOffset;
-                if (j < tileStart)
-                    pair = ((unsigned long long)__ldg(tileRoot + i) << 32) | __ldg(tileRoot + j);
+                const uint32_t q = __ldg(new2pos + ((uint32_t)o - triangleOffset));
+                if (q < tileStart)
+                    pair = ((unsigned long long)__ldg(tileRoot + p) << 32) | __ldg(tileRoot + q);
             }
         }
         const unsigned same = __match_any_sync(SB_FULL, pair);
@@ -387,49 +436,72 @@ __global__ void __launch_bounds__(256) cc_hook_kernel(const int32_t *__restrict_
     }
 }
 
-// every tile root reports itself to the root of its tree; minIdx was filled with 0xff.  Blocks
-// start in ascending order, so after the first few reports the rest only read and leave.
-__global__ void __launch_bounds__(256) cc_min_kernel(uint32_t *parent, const uint32_t *__restrict__ tileRoot, uint32_t n,
+// every tile root that is not the root of its tree hands its minimum up (its own slot is
+// written by nobody else); most only read and leave once a low index has arrived
+__global__ void __launch_bounds__(256) cc_min_kernel(uint32_t *parent, const uint32_t *__restrict__ tileRoot, uint32_t nodes,
     uint32_t *minIdx)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && __ldg(tileRoot + i) == i) {
-        uint32_t *slot = minIdx + cc_find(parent, i);
-        if (i < __ldcg(slot))
-            atomicMin(slot, i);
-    }
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nodes || __ldg(tileRoot + p) != p)
+        return;
+    const uint32_t root = cc_find(parent, p);
+    if (root == p)
+        return;
+    const uint32_t v = __ldcg(minIdx + p);
+    if (v < __ldcg(minIdx + root))
+        atomicMin(minIdx + root, v);
 }
 
-__global__ void __launch_bounds__(256) cc_label_kernel(uint32_t *parent, uint32_t n, uint32_t triangleOffset,
-    const uint32_t *minIdx, uint32_t *__restrict__ label, uint32_t *__restrict__ count)
+__global__ void __launch_bounds__(256) cc_label_kernel(uint32_t *parent, uint32_t nodes, uint32_t triangleOffset,
+    const uint32_t *__restrict__ pos2new, const uint32_t *minIdx, uint32_t *__restrict__ label, uint32_t *__restrict__ count)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    uint32_t r = 0;
-    if (live) {
-        r = cc_find(parent, i);
-        label[i] = __ldcg(minIdx + r) + triangleOffset;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = p < nodes ? __ldg(pos2new + p) : CC_NONE;
+    uint32_t root = CC_NONE;
+    if (r != CC_NONE) {
+        root = cc_find(parent, p);
+        label[r] = __ldcg(minIdx + root) + triangleOffset;
     }
-    const unsigned roots = __ballot_sync(SB_FULL, live && r == i);
+    const unsigned roots = __ballot_sync(SB_FULL, r != CC_NONE && root == p);
     if ((threadIdx.x & 31) == 0 && roots)
         atomicAdd(count, __popc(roots));
 }
 
 } // namespace
 
-// scratch: 2 n words; label: n; *count (device, zeroed by the caller) += components
-cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *scratch,
-    uint32_t *label, uint32_t *count, LaunchCounter &lc)
+// Words of scratch sbk_uncut_components needs.
+size_t sbk_uncut_components_scratch(uint32_t nTri, uint32_t nT, bool ordered)
 {
-    if (n == 0)
+    const size_t nodes = ordered ? nT : nTri;
+    return 4 * nodes + nTri + (ordered ? nT : 0);
+}
+
+// sortedTri: the mesh's Morton order (sorted position -> face, nT entries) or null; face: new
+// triangle -> face; label: nTri; *count (device, zeroed by the caller) += components
+cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t nTri, uint32_t triangleOffset,
+    const uint32_t *sortedTri, const uint32_t *face, uint32_t nT, uint32_t *scratch, uint32_t *label, uint32_t *count,
+    LaunchCounter &lc)
+{
+    if (nTri == 0)
         return cudaSuccess;
-    const uint32_t blocks = (n + 255) / 256;
-    uint32_t *parent = scratch, *minIdx = scratch + n;
-    cudaMemsetAsync(minIdx, 0xff, sizeof(uint32_t) * (size_t)n, s);
-    cc_tile_kernel<<<(n + CC_TILE - 1) / CC_TILE, CC_THREADS, 0, s>>>(adj, n, triangleOffset, parent, label /* tile roots */);
-    cc_hook_kernel<<<blocks, 256, 0, s>>>(adj, n, triangleOffset, label, parent);
-    cc_min_kernel<<<blocks, 256, 0, s>>>(parent, label, n, minIdx);
-    cc_label_kernel<<<blocks, 256, 0, s>>>(parent, n, triangleOffset, minIdx, label, count);
+    const uint32_t nodes = sortedTri ? nT : nTri;
+    uint32_t *parent = scratch, *minIdx = parent + nodes, *tileRoot = minIdx + nodes, *pos2new = tileRoot + nodes,
+             *new2pos = pos2new + nodes, *faceRank = new2pos + nTri;
+    if (sortedTri) {
+        cudaMemsetAsync(faceRank, 0xff, sizeof(uint32_t) * (size_t)nT, s);
+        cc_rank_kernel<<<(nTri + 255) / 256, 256, 0, s>>>(face, nTri, faceRank);
+        cc_order_kernel<<<(nT + 255) / 256, 256, 0, s>>>(sortedTri, faceRank, nT, pos2new, new2pos);
+        lc.kernels += 2;
+    } else {
+        cc_identity_kernel<<<(nTri + 255) / 256, 256, 0, s>>>(nTri, pos2new, new2pos);
+        lc.kernels += 1;
+    }
+    const uint32_t blocks = (nodes + 255) / 256;
+    cc_tile_kernel<<<(nodes + CC_TILE - 1) / CC_TILE, CC_THREADS, 0, s>>>(adj, nodes, triangleOffset, pos2new, new2pos, parent,
+        tileRoot, minIdx);
+    cc_hook_kernel<<<blocks, 256, 0, s>>>(adj, nodes, triangleOffset, pos2new, new2pos, tileRoot, parent);
+    cc_min_kernel<<<blocks, 256, 0, s>>>(parent, tileRoot, nodes, minIdx);
+    cc_label_kernel<<<blocks, 256, 0, s>>>(parent, nodes, triangleOffset, pos2new, minIdx, label, count);
     lc.kernels += 4;
     return cudaGetLastError();
 }

@@ -107,7 +107,9 @@ cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *t
 cudaError_t sbk_halfedge_link(cudaStream_t s, const unsigned long long *sortedKeys, const uint32_t *sortedOrds, uint32_t n,
     unsigned bitsV, uint32_t nV, uint32_t *vstart /* nV words of scratch */, uint32_t vertexOffset, uint32_t triangleOffset,
     unsigned long long *refKeys, uint32_t *owner, int32_t *adj, uint32_t *firstRepeat, LaunchCounter &lc);
-cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t n, uint32_t triangleOffset, uint32_t *scratch /* 2 n */,
+size_t sbk_uncut_components_scratch(uint32_t nTri, uint32_t nT, bool ordered);
+cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t nTri, uint32_t triangleOffset,
+    const uint32_t *sortedTri /* Morton order of the mesh, or null */, const uint32_t *face, uint32_t nT, uint32_t *scratch,
     uint32_t *label, uint32_t *count, LaunchCounter &lc);
 
 // sb_classify.cu
