@@ -1736,12 +1736,19 @@ int sb_uncut_components(const sb_uncut *uc, uint32_t *label, size_t *n_component
             r = alloc_async(c, &parent, sbk_uncut_components_scratch(u->nTri, d.nT, ordered), nullptr);
         if (r)
             return r;
-        SB_CUDA(cudaMemsetAsync(&c->dScalars->ccCount, 0, sizeof(unsigned int), c->stream));
-        SB_CUDA(sbk_uncut_components(c->stream, u->adj, u->nTri, u->triangleOffset, ordered ? d.sortedTri : nullptr, u->face, d.nT,
-            parent, u->label, &c->dScalars->ccCount, c->lc));
-        cudaFreeAsync(parent, c->stream);
-        SB_CUDA(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
-        SB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaError_t e = cudaMemsetAsync(&c->dScalars->ccCount, 0, sizeof(unsigned int), c->stream);
+        if (e == cudaSuccess)
+            e = sbk_uncut_components(c->stream, u->adj, u->nTri, u->triangleOffset, ordered ? d.sortedTri : nullptr, u->face,
+                d.nT, parent, u->label, &c->dScalars->ccCount, c->lc);
+        cudaFreeAsync(parent, c->stream); // stream-ordered: released once the kernels above are through
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            u->label = nullptr; // (stays in `owned`) computed again by the next request
+            return fail(SB_ERR_CUDA, "components: %s", cudaGetErrorString(e));
+        }
         u->nComponents = c->hScalars->ccCount;
     }
     if (label) {

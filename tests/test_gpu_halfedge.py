@@ -155,3 +155,35 @@ def test_uncut_rejects_out_of_range_indices(ctx):
     with pytest.raises(sb.SolidBooleanError):
         m.uncut(None, 0, 0)
     m.close()
+
+
+@pytest.mark.slow
+def test_uncut_config_c4_many_fragments(ctx, oracle):
+    """BASELINE config 4 proxy (near-coincident icospheres, 327,680 x 2): a large share of the
+    faces is cut, the uncut rest falls apart into many face groups."""
+    a, b = meshgen.config_c4()
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x = ma.intersect(mb)
+    fa, fb = x.face_flags()
+    assert int(fa.sum()) > 1000 and int(fb.sum()) > 1000
+    ua = x.uncut(0, 0, 0)
+    ub = x.uncut(1, len(a[0]), ua.num_triangles)
+    ra = oracle.uncut_half_edges(a[1], fa, 0, 0)
+    rb = oracle.uncut_half_edges(b[1], fb, len(a[0]), len(ra["face"]))
+    check_uncut(ua, ra, a[1], 0)
+    check_uncut(ub, rb, b[1], len(a[0]))
+    ua.close(); ub.close()
+    # ... and with a random third of the faces cut: thousands of fragments, single triangles included,
+    # through both node orders of the union-find (Morton order of the built mesh / face order)
+    rng = np.random.default_rng(21)
+    cut = (rng.random(len(a[1])) < 0.35).astype(np.uint8)
+    r = oracle.uncut_half_edges(a[1], cut, 7, 3)
+    assert r["components"] > 1000
+    u = ma.uncut(cut, 7, 3)
+    check_uncut(u, r, a[1], 7)
+    u.close()
+    raw = ctx.mesh(*a, build=False)
+    u = raw.uncut(cut, 7, 3)
+    check_uncut(u, r, a[1], 7)
+    u.close(); raw.close()
+    x.close(); ma.close(); mb.close()
