@@ -8,12 +8,5 @@ timeout 600 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_c3.json 2> 
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -c 400 gpurun_out/bench_reference.json
 SB_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -c 300 gpurun_out/ncu_bench.log
-timeout 300 python scripts/halfedge_times.py c3 5 > gpurun_out/halfedge_c3.log 2>&1; tail -1 gpurun_out/halfedge_c3.log
-timeout 200 python scripts/halfedge_times.py c2 5 --no-ref > gpurun_out/halfedge_c2.log 2>&1; tail -1 gpurun_out/halfedge_c2.log
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_halfedge.csv \
-    python scripts/halfedge_times.py c3 2 --no-ref > gpurun_out/ncu_halfedge.log 2>&1
-timeout 600 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section Occupancy --section WarpStateStats --section LaunchStats \
-    --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,lts__t_requests_srcunit_tex_op_atom_dot_cas.sum \
-    --clock-control none -k regex:"uncut|halfedge|cc_|onesweep_kernel<unsigned long|hist_kernel<unsigned long" -c 40 -o gpurun_out/halfedge_kernels -f \
-    python scripts/halfedge_times.py c3 1 --no-ref > gpurun_out/ncu_halfedge_kernels.log 2>&1; tail -1 gpurun_out/ncu_halfedge_kernels.log
 timeout 300 python scripts/combine_times.py c3 3 > gpurun_out/combine_c3.log 2>&1; tail -2 gpurun_out/combine_c3.log | cut -c1-400
+bash scripts/gpu_halfedge_check.sh

@@ -1494,27 +1494,36 @@ static int uncut_run(const sb_mesh *mesh, const uint8_t *dCut, size_t vertexOffs
     const size_t n = 3 * (size_t)u->nTri;
     if (n) {
         const unsigned bitsV = bits_for(d.nV); // keys are sorted on the mesh's own vertex ids
+        // one 8-byte record per half-edge when key and ordinal fit 64 bits together (they do up to
+        // ~2 M vertices x 4 M uncut triangles): keys-only sort, a third less traffic per pass
+        unsigned bitsO = bits_for(n);
+        if (2 * bitsV + bitsO > 64 || std::getenv("SB_HE_PAIR_SORT"))
+            bitsO = 0;
         unsigned long long *k0 = nullptr, *k1 = nullptr, *sk = nullptr;
-        uint32_t *o0 = nullptr, *o1 = nullptr, *so = nullptr;
+        uint32_t *o0 = nullptr, *o1 = nullptr, *so = nullptr, *vstart = nullptr;
         SB_TRY(alloc_async(c, &u->face, u->nTri, &u->owned));
         SB_TRY(alloc_async(c, &u->tri3, n, &u->owned));
         SB_TRY(alloc_async(c, &k0, n, &u->owned));
         SB_TRY(alloc_async(c, &k1, n, &u->owned));
-        SB_TRY(alloc_async(c, &o0, n, &u->owned));
-        SB_TRY(alloc_async(c, &o1, n, &u->owned));
+        SB_TRY(alloc_async(c, &o0, n, &u->owned)); // sort values, or the unpacked ordinals of the sorted entries
+        if (!bitsO)
+            SB_TRY(alloc_async(c, &o1, n, &u->owned));
         SB_TRY(alloc_async(c, &u->owner, n, &u->owned));
         SB_TRY(alloc_async(c, &u->adj, n, &u->owned));
+        SB_TRY(alloc_async(c, &vstart, d.nV, &u->owned));
         SB_TRY(ensure_radix_ws(c, n));
-        SB_CUDA_X(sbk_uncut_emit(c->stream, dCut, d.tri, d.nT, d.nV, &c->dScalars->err, tileScratch, u->vertexOffset, bitsV, u->face, u->tri3, k0, o0,
-            c->lc));
-        SB_CUDA_X(sbk_sort_keys(c->stream, k0, k1, o0, o1, n, 0, (int)(2 * bitsV), c->radixWs, c->smCount, &sk, &so, c->lc));
+        SB_CUDA_X(sbk_uncut_emit(c->stream, dCut, d.tri, d.nT, d.nV, &c->dScalars->err, tileScratch, u->vertexOffset, bitsV, bitsO,
+            u->face, u->tri3, k0, o0, c->lc));
+        if (bitsO)
+            SB_CUDA_X(sbk_sort_keys(c->stream, k0, k1, nullptr, nullptr, n, (int)bitsO, (int)(bitsO + 2 * bitsV), c->radixWs,
+                c->smCount, &sk, nullptr, c->lc));
+        else
+            SB_CUDA_X(sbk_sort_keys(c->stream, k0, k1, o0, o1, n, 0, (int)(2 * bitsV), c->radixWs, c->smCount, &sk, &so, c->lc));
         // the reference-format keys go to whichever key buffer the sort left free
         u->keys = sk == k0 ? k1 : k0;
-        u->ords = so;
-        uint32_t *vstart = nullptr;
-        SB_TRY(alloc_async(c, &vstart, d.nV, &u->owned));
-        SB_CUDA_X(sbk_halfedge_link(c->stream, sk, so, (uint32_t)n, bitsV, d.nV, vstart, u->vertexOffset, u->triangleOffset,
-            u->keys, u->owner, u->adj, &c->dScalars->heRepeat, c->lc));
+        u->ords = bitsO ? o0 : so;
+        SB_CUDA_X(sbk_halfedge_link(c->stream, sk, so, (uint32_t)n, bitsV, bitsO, d.nV, vstart, u->vertexOffset, u->triangleOffset,
+            u->keys, u->owner, u->adj, bitsO ? o0 : nullptr, &c->dScalars->heRepeat, c->lc));
         SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA_X(cudaStreamSynchronize(c->stream));
         u->repeatOrd = c->hScalars->heRepeat;

@@ -120,11 +120,15 @@ __global__ void __launch_bounds__(1024) uncut_scan_kernel(uint32_t *__restrict__
 // reference's ((first + offset) << 32) | (second + offset), fewer radix passes.
 // Faces are taken in stripes (item s of thread t = face tile + s * 256 + t): neighbouring threads
 // read neighbouring triples and, ranks being prefix counts in face order, write neighbouring
-// records.
+// records.  bitsO > 0: the ordinal rides in the low bitsO bits of the key word (one 8-byte
+// record per half-edge, a keys-only sort on the bits above it -- the ordinals ascend in emission
+// order, so an LSD sort of the upper bits alone leaves equal keys in insertion order); bitsO == 0
+// (key and ordinal do not fit 64 bits together): separate ordinal array, (key, value) sort.
 __global__ void __launch_bounds__(HE_THREADS) uncut_emit_kernel(const uint8_t *__restrict__ cut,
     const uint32_t *__restrict__ tri, uint32_t nT, uint32_t nV, int *__restrict__ err,
-    const uint32_t *__restrict__ tileOffset, uint32_t vertexOffset, unsigned bitsV, uint32_t *__restrict__ face,
-    uint32_t *__restrict__ tri3, unsigned long long *__restrict__ keys, uint32_t *__restrict__ ords)
+    const uint32_t *__restrict__ tileOffset, uint32_t vertexOffset, unsigned bitsV, unsigned bitsO,
+    uint32_t *__restrict__ face, uint32_t *__restrict__ tri3, unsigned long long *__restrict__ keys,
+    uint32_t *__restrict__ ords)
 {
     constexpr int WARPS = HE_THREADS / 32;
     __shared__ uint32_t s_cnt[HE_ITEMS * WARPS]; // uncut faces per (stripe, warp), then their exclusive scan
@@ -173,41 +177,55 @@ __global__ void __launch_bounds__(HE_THREADS) uncut_emit_kernel(const uint8_t *_
         tri3[o] = v0 + vertexOffset;
         tri3[o + 1] = v1 + vertexOffset;
         tri3[o + 2] = v2 + vertexOffset;
-        keys[o] = ((unsigned long long)v0 << bitsV) | v1;
-        keys[o + 1] = ((unsigned long long)v1 << bitsV) | v2;
-        keys[o + 2] = ((unsigned long long)v2 << bitsV) | v0;
-        ords[o] = (uint32_t)o;
-        ords[o + 1] = (uint32_t)o + 1;
-        ords[o + 2] = (uint32_t)o + 2;
+        const unsigned long long k0 = ((unsigned long long)v0 << bitsV) | v1, k1 = ((unsigned long long)v1 << bitsV) | v2,
+                                 k2 = ((unsigned long long)v2 << bitsV) | v0;
+        if (bitsO) {
+            keys[o] = (k0 << bitsO) | o;
+            keys[o + 1] = (k1 << bitsO) | (o + 1);
+            keys[o + 2] = (k2 << bitsO) | (o + 2);
+        } else {
+            keys[o] = k0;
+            keys[o + 1] = k1;
+            keys[o + 2] = k2;
+            ords[o] = (uint32_t)o;
+            ords[o + 1] = (uint32_t)o + 1;
+            ords[o + 2] = (uint32_t)o + 2;
+        }
     }
 }
 
 // First sorted entry of every vertex that starts a half-edge (vstart was filled with 0xff).
 __global__ void __launch_bounds__(256) halfedge_vstart_kernel(const unsigned long long *__restrict__ keys, uint32_t n,
-    unsigned bitsV, uint32_t *__restrict__ vstart)
+    unsigned bitsV, unsigned bitsO, uint32_t *__restrict__ vstart)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n)
         return;
-    const uint32_t first = (uint32_t)(__ldg(keys + p) >> bitsV);
-    if (p == 0 || (uint32_t)(__ldg(keys + p - 1) >> bitsV) != first)
+    const uint32_t first = (uint32_t)(__ldg(keys + p) >> (bitsV + bitsO));
+    if (p == 0 || (uint32_t)(__ldg(keys + p - 1) >> (bitsV + bitsO)) != first)
         vstart[first] = p;
 }
 
-// One thread per sorted half-edge.
+// One thread per sorted half-edge.  ords: the sorted ordinals (bitsO == 0) or null; ordOut
+// (bitsO > 0): receives them, unpacked.
 __global__ void __launch_bounds__(256) halfedge_link_kernel(const unsigned long long *__restrict__ keys,
-    const uint32_t *__restrict__ ords, uint32_t n, unsigned bitsV, uint32_t vertexOffset, uint32_t triangleOffset,
-    const uint32_t *__restrict__ vstart, unsigned long long *__restrict__ refKeys, uint32_t *__restrict__ owner,
-    int32_t *__restrict__ adj, uint32_t *__restrict__ firstRepeat)
+    const uint32_t *__restrict__ ords, uint32_t n, unsigned bitsV, unsigned bitsO, uint32_t vertexOffset,
+    uint32_t triangleOffset, const uint32_t *__restrict__ vstart, unsigned long long *__restrict__ refKeys,
+    uint32_t *__restrict__ owner, int32_t *__restrict__ adj, uint32_t *__restrict__ ordOut,
+    uint32_t *__restrict__ firstRepeat)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n)
         return;
-    const unsigned long long key = __ldg(keys + p);
-    const uint32_t ord = __ldg(ords + p);
+    const unsigned long long ordMask = (1ull << bitsO) - 1ull;
+    const unsigned long long word = __ldg(keys + p);
+    const unsigned long long key = word >> bitsO;
+    const uint32_t ord = bitsO ? (uint32_t)(word & ordMask) : __ldg(ords + p);
+    if (bitsO)
+        ordOut[p] = ord;
     // the sort is stable and the ordinals ascend in emission order: of two equal keys the
     // later entry is the insertion the reference's map refuses
-    if (p > 0 && __ldg(keys + p - 1) == key)
+    if (p > 0 && (__ldg(keys + p - 1) >> bitsO) == key)
         atomicMin(firstRepeat, ord);
     const unsigned long long lowMask = (1ull << bitsV) - 1ull;
     const unsigned long long from = key >> bitsV, to = key & lowMask;
@@ -221,21 +239,24 @@ __global__ void __launch_bounds__(256) halfedge_link_kernel(const unsigned long 
     uint32_t q = __ldg(vstart + to);
     if (q != 0xffffffffu) {
         int steps = 0;
-        while (q < n && __ldg(keys + q) < want && ++steps < 16)
+        while (q < n && (__ldg(keys + q) >> bitsO) < want && ++steps < 16)
             ++q;
         if (steps == 16) {
             uint32_t lo = q, hi = n;
             while (lo < hi) {
                 const uint32_t mid = lo + ((hi - lo) >> 1);
-                if (__ldg(keys + mid) < want)
+                if ((__ldg(keys + mid) >> bitsO) < want)
                     lo = mid + 1;
                 else
                     hi = mid;
             }
             q = lo;
         }
-        if (q < n && __ldg(keys + q) == want)
-            other = (int32_t)(triangleOffset + __ldg(ords + q) / 3u);
+        if (q < n) {
+            const unsigned long long w = __ldg(keys + q);
+            if ((w >> bitsO) == want)
+                other = (int32_t)(triangleOffset + (bitsO ? (uint32_t)(w & ordMask) : __ldg(ords + q)) / 3u);
+        }
     }
     adj[ord] = other;
 }
@@ -523,29 +544,29 @@ cudaError_t sbk_uncut_count(cudaStream_t s, const uint8_t *cut, uint32_t nT, uin
 }
 
 cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *tri, uint32_t nT, uint32_t nV, int *err,
-    const uint32_t *tileScratch, uint32_t vertexOffset, unsigned bitsV, uint32_t *face, uint32_t *tri3, unsigned long long *keys, uint32_t *ords,
-    LaunchCounter &lc)
+    const uint32_t *tileScratch, uint32_t vertexOffset, unsigned bitsV, unsigned bitsO, uint32_t *face, uint32_t *tri3,
+    unsigned long long *keys, uint32_t *ords, LaunchCounter &lc)
 {
     const uint32_t tiles = sbk_uncut_tiles(nT);
     if (tiles == 0)
         return cudaSuccess;
-    uncut_emit_kernel<<<tiles, HE_THREADS, 0, s>>>(cut, tri, nT, nV, err, tileScratch, vertexOffset, bitsV, face, tri3, keys,
-        ords);
+    uncut_emit_kernel<<<tiles, HE_THREADS, 0, s>>>(cut, tri, nT, nV, err, tileScratch, vertexOffset, bitsV, bitsO, face, tri3,
+        keys, ords);
     lc.kernels += 1;
     return cudaGetLastError();
 }
 
 // vstart: nV words of scratch
 cudaError_t sbk_halfedge_link(cudaStream_t s, const unsigned long long *sortedKeys, const uint32_t *sortedOrds, uint32_t n,
-    unsigned bitsV, uint32_t nV, uint32_t *vstart, uint32_t vertexOffset, uint32_t triangleOffset, unsigned long long *refKeys, uint32_t *owner, int32_t *adj,
-    uint32_t *firstRepeat, LaunchCounter &lc)
+    unsigned bitsV, unsigned bitsO, uint32_t nV, uint32_t *vstart, uint32_t vertexOffset, uint32_t triangleOffset,
+    unsigned long long *refKeys, uint32_t *owner, int32_t *adj, uint32_t *ordOut, uint32_t *firstRepeat, LaunchCounter &lc)
 {
     if (n == 0)
         return cudaSuccess;
     cudaMemsetAsync(vstart, 0xff, sizeof(uint32_t) * (size_t)nV, s);
-    halfedge_vstart_kernel<<<(n + 255) / 256, 256, 0, s>>>(sortedKeys, n, bitsV, vstart);
-    halfedge_link_kernel<<<(n + 255) / 256, 256, 0, s>>>(sortedKeys, sortedOrds, n, bitsV, vertexOffset, triangleOffset, vstart,
-        refKeys, owner, adj, firstRepeat);
+    halfedge_vstart_kernel<<<(n + 255) / 256, 256, 0, s>>>(sortedKeys, n, bitsV, bitsO, vstart);
+    halfedge_link_kernel<<<(n + 255) / 256, 256, 0, s>>>(sortedKeys, sortedOrds, n, bitsV, bitsO, vertexOffset, triangleOffset,
+        vstart, refKeys, owner, adj, ordOut, firstRepeat);
     lc.kernels += 2;
     return cudaGetLastError();
 }

@@ -101,12 +101,15 @@ cudaError_t sbk_sort_keys(cudaStream_t s, unsigned long long *keys, unsigned lon
 uint32_t sbk_uncut_tiles(uint32_t nT);
 cudaError_t sbk_uncut_count(cudaStream_t s, const uint8_t *cut /* nT bytes or null */, uint32_t nT, uint32_t *tileScratch,
     uint32_t *total, LaunchCounter &lc);
+// bitsO > 0: ordinal packed into the low bits of the key word (keys-only sort on the bits above), ords unused;
+// bitsO == 0: separate ordinal array (key, value sort)
 cudaError_t sbk_uncut_emit(cudaStream_t s, const uint8_t *cut, const uint32_t *tri, uint32_t nT, uint32_t nV, int *err,
-    const uint32_t *tileScratch, uint32_t vertexOffset, unsigned bitsV, uint32_t *face, uint32_t *tri3, unsigned long long *keys, uint32_t *ords,
-    LaunchCounter &lc);
+    const uint32_t *tileScratch, uint32_t vertexOffset, unsigned bitsV, unsigned bitsO, uint32_t *face, uint32_t *tri3,
+    unsigned long long *keys, uint32_t *ords, LaunchCounter &lc);
 cudaError_t sbk_halfedge_link(cudaStream_t s, const unsigned long long *sortedKeys, const uint32_t *sortedOrds, uint32_t n,
-    unsigned bitsV, uint32_t nV, uint32_t *vstart /* nV words of scratch */, uint32_t vertexOffset, uint32_t triangleOffset,
-    unsigned long long *refKeys, uint32_t *owner, int32_t *adj, uint32_t *firstRepeat, LaunchCounter &lc);
+    unsigned bitsV, unsigned bitsO, uint32_t nV, uint32_t *vstart /* nV words of scratch */, uint32_t vertexOffset,
+    uint32_t triangleOffset, unsigned long long *refKeys, uint32_t *owner, int32_t *adj, uint32_t *ordOut /* bitsO > 0 */,
+    uint32_t *firstRepeat, LaunchCounter &lc);
 size_t sbk_uncut_components_scratch(uint32_t nTri, uint32_t nT, bool ordered);
 cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t nTri, uint32_t triangleOffset,
     const uint32_t *sortedTri /* Morton order of the mesh, or null */, const uint32_t *face, uint32_t nT, uint32_t *scratch,
