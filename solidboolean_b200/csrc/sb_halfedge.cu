@@ -282,8 +282,14 @@ __global__ void __launch_bounds__(256) halfedge_link_kernel(const unsigned long 
 //                     (linking by index grows paths: i under i - 1 under i - 2 ...)
 //   pass 3  cc_min    the lowest triangle index of every tree (atomicMin at the tree's root)
 //   pass 4  cc_label  label = that minimum; roots counted
-constexpr int CC_TILE = 1024;
-constexpr int CC_THREADS = 256;
+#ifndef SB_CC_TILE
+#define SB_CC_TILE 256 // measured at C3 / C2: 1024 x 256 threads 0.48 / 0.25 ms, 256 x 256 0.40 / 0.16, 64 x 64 0.48 / 0.27
+#endif
+#ifndef SB_CC_THREADS
+#define SB_CC_THREADS 256
+#endif
+constexpr int CC_TILE = SB_CC_TILE;       // nodes per shared-memory tile (power of two)
+constexpr int CC_THREADS = SB_CC_THREADS; // threads per tile
 constexpr uint32_t CC_NONE = 0xffffffffu;
 
 // a bijection of the 32-bit ids (murmur3's finaliser) whose order looks random: tile roots are
