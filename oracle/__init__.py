@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libsboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsbref.so")
+HOOK_SO = os.path.join(HERE, "_ref", "libsbref_hook.so")
 
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
@@ -83,6 +84,8 @@ class Oracle:
         L.sbo_uncut_adjacency.argtypes = [_u32p, _u32p, C.c_size_t, C.c_uint64, _u64p, _u32p, C.c_size_t, _i32p]
         L.sbo_uncut_components.argtypes = [_i32p, C.c_size_t, C.c_uint64, _u32p]
         L.sbo_uncut_components.restype = C.c_size_t
+        L.sbo_cut_contexts.argtypes = [_u32p, _f64p, C.c_size_t, C.c_int, _u32p, _u32p, _f64p, _u32p, _u32p]
+        L.sbo_cut_contexts.restype = C.c_size_t
 
     # -- predicate ---------------------------------------------------------
     def tri_tri_batch(self, tris18):
@@ -165,6 +168,22 @@ class Oracle:
         label = np.zeros(n.value, np.uint32)
         comps = self.lib.sbo_uncut_components(adj, n.value, triangle_offset, label) if n.value else 0
         return dict(ok=bool(ok), face=face, keys=keys, owner=owner, adj=adj, label=label, components=int(comps))
+
+    # -- per-triangle intersection contexts ---------------------------------
+    def cut_contexts(self, hits, seg, which):
+        """The pair-loop body of combine() (src/solidboolean.cpp:296-339) over `hits` in the given order.
+        -> dict(tri [c], point_start [c+1], points [p,3], edge_start [c+1], edges [e,2])"""
+        hits = _u32(hits).reshape(-1, 2)
+        seg = _f64(seg).reshape(-1, 6)
+        n = hits.shape[0]
+        tri = np.zeros(max(n, 1), np.uint32)
+        ps = np.zeros(n + 1, np.uint32)
+        es = np.zeros(n + 1, np.uint32)
+        pts = np.zeros((max(2 * n, 1), 3), np.float64)
+        edges = np.zeros((max(n, 1), 2), np.uint32)
+        c = self.lib.sbo_cut_contexts(hits, seg, n, which, tri, ps, pts, es, edges) if n else 0
+        return dict(tri=tri[:c].copy(), point_start=ps[:c + 1].copy(), points=pts[:ps[c]].copy(),
+                    edge_start=es[:c + 1].copy(), edges=edges[:es[c]].copy())
 
     # -- classification -----------------------------------------------------
     def classify(self, target_mesh, pts):

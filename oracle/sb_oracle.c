@@ -912,3 +912,98 @@ size_t sbo_uncut_components(const int32_t *adj, size_t nTri, uint64_t triangleOf
     free(seen);
     return comps;
 }
+
+/* ---- per-triangle intersection contexts -----------------------------
+ * The body of the pair loop of SolidBoolean::combine (src/solidboolean.cpp:296-339): for every
+ * intersecting pair, in the order of the pair list, the segment's two end points are entered
+ * into the context of the first mesh's triangle and into the context of the second mesh's
+ * triangle.  A context de-duplicates its points by PositionKey (addIntersectedPoint, :305-310:
+ * std::map insert, the FIRST position with a key is kept, indices in first-seen order) and keeps
+ * the undirected neighbour relation between the two (3 + index) numbers of a segment unless they
+ * are the same point (:323-328 / :332-337).
+ *
+ * hits: nHit pairs in the order the loop sees them (the CUDA path: ascending (a, b)); seg: 6
+ * doubles per hit.  which = 0: contexts of the first mesh's triangles, 1: of the second's.
+ * Output, contexts in ascending triangle id:
+ *   cutTri[c]                          triangle id
+ *   pointStart[c] .. pointStart[c+1]   its points in `points` (3 doubles each), first-seen order
+ *   edgeStart[c] .. edgeStart[c+1]     its relations in `edges` (2 x uint32, lower number first,
+ *                                      ascending): the flattened neighborMap
+ * Capacities: cutTri nHit, pointStart/edgeStart nHit + 1, points 6 nHit doubles, edges 2 nHit.
+ * Returns the number of contexts. */
+typedef struct {
+    uint32_t tri, hit;
+} ctx_ref;
+
+static int cmp_ctx_ref(const void *pa, const void *pb)
+{
+    const ctx_ref *a = (const ctx_ref *)pa, *b = (const ctx_ref *)pb;
+    if (a->tri != b->tri)
+        return a->tri < b->tri ? -1 : 1;
+    return a->hit < b->hit ? -1 : a->hit > b->hit; /* the loop's order inside a triangle */
+}
+
+static int cmp_edge(const void *pa, const void *pb)
+{
+    const uint32_t *a = (const uint32_t *)pa, *b = (const uint32_t *)pb;
+    if (a[0] != b[0])
+        return a[0] < b[0] ? -1 : 1;
+    return a[1] < b[1] ? -1 : a[1] > b[1];
+}
+
+size_t sbo_cut_contexts(const uint32_t *hits, const double *seg, size_t nHit, int which, uint32_t *cutTri,
+    uint32_t *pointStart, double *points, uint32_t *edgeStart, uint32_t *edges)
+{
+    ctx_ref *order = (ctx_ref *)malloc((nHit + 1) * sizeof(ctx_ref));
+    pkey *keys = (pkey *)malloc((2 * nHit + 2) * sizeof(pkey));
+    for (size_t h = 0; h < nHit; ++h) {
+        order[h].tri = hits[2 * h + which];
+        order[h].hit = (uint32_t)h;
+    }
+    qsort(order, nHit, sizeof(ctx_ref), cmp_ctx_ref);
+    size_t nCtx = 0, nPts = 0, nEdges = 0;
+    pointStart[0] = 0;
+    edgeStart[0] = 0;
+    for (size_t i = 0; i < nHit;) {
+        size_t j = i;
+        const size_t p0 = nPts, e0 = nEdges;
+        while (j < nHit && order[j].tri == order[i].tri) {
+            uint32_t idx[2];
+            for (int s = 0; s < 2; ++s) {
+                const double *p = seg + 6 * (size_t)order[j].hit + 3 * s;
+                pkey k = {to_key(p[0]), to_key(p[1]), to_key(p[2])};
+                size_t q = p0;
+                while (q < nPts && !pkey_eq(&keys[q], &k))
+                    ++q;
+                if (q == nPts) { /* insertResult.second: a new point */
+                    keys[nPts] = k;
+                    points[3 * nPts] = p[0];
+                    points[3 * nPts + 1] = p[1];
+                    points[3 * nPts + 2] = p[2];
+                    ++nPts;
+                }
+                idx[s] = 3 + (uint32_t)(q - p0);
+            }
+            if (idx[0] != idx[1]) {
+                uint32_t lo = idx[0] < idx[1] ? idx[0] : idx[1], hi = idx[0] < idx[1] ? idx[1] : idx[0];
+                size_t q = e0;
+                while (q < nEdges && !(edges[2 * q] == lo && edges[2 * q + 1] == hi))
+                    ++q;
+                if (q == nEdges) {
+                    edges[2 * nEdges] = lo;
+                    edges[2 * nEdges + 1] = hi;
+                    ++nEdges;
+                }
+            }
+            ++j;
+        }
+        qsort(edges + 2 * e0, nEdges - e0, 2 * sizeof(uint32_t), cmp_edge);
+        cutTri[nCtx++] = order[i].tri;
+        pointStart[nCtx] = (uint32_t)nPts;
+        edgeStart[nCtx] = (uint32_t)nEdges;
+        i = j;
+    }
+    free(order);
+    free(keys);
+    return nCtx;
+}

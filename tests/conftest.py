@@ -113,3 +113,18 @@ def uncut_inputs():
     out["open_sheet"] = ((sheet[0], sheet[1][: len(sheet[1]) // 3]), tor, None, flags(len(tor[1]), np.arange(0, len(tor[1]), 5)))
     out["all_cut"] = (ico, tor, np.ones(len(ico[1]), np.uint8), np.ones(len(tor[1]), np.uint8))
     return out
+
+
+def check_contexts_against(o, cap_get, side):
+    """o: Oracle.cut_contexts-style dict (tri ascending, CSR points / edges) of ALL contexts;
+    cap_get(key): the reference's captured arrays of one side ("tri", "point_start", ...), possibly a
+    subset (combine() stopped early).  Points bit for bit, edges exactly."""
+    tri = cap_get("tri")
+    idx = np.searchsorted(o["tri"], tri)
+    assert np.all(idx < max(len(o["tri"]), 1)) or len(tri) == 0
+    assert np.array_equal(o["tri"][idx], tri), side + ": context triangles differ"
+    ps, pts, es, ed = cap_get("point_start"), cap_get("points"), cap_get("edge_start"), cap_get("edges")
+    for j, i in enumerate(idx):
+        mine = o["points"][o["point_start"][i]:o["point_start"][i + 1]]
+        assert mine.tobytes() == pts[ps[j]:ps[j + 1]].tobytes(), (side, int(tri[j]), "points")
+        assert np.array_equal(o["edges"][o["edge_start"][i]:o["edge_start"][i + 1]], ed[es[j]:es[j + 1]]), (side, int(tri[j]), "edges")

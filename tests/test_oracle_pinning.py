@@ -178,3 +178,50 @@ def test_uncut_half_edges_match_live_reference(oracle):
         for w, o in ((0, oa), (1, ob)):
             label, groups = op.uncut_groups(w, len(o["face"]))
             assert groups == o["components"] and np.array_equal(label, o["label"])
+
+
+# ---- per-triangle intersection contexts ------------------------------
+
+def _context_inputs(golden_cases, golden_synthetic):
+    out = {c: load_case(golden_cases, c) for c in CASES}
+    out.update({n: load_synthetic(golden_synthetic, n) for n in sorted(synthetic_specs())})
+    return out
+
+
+def test_cut_contexts_match_reference_fixtures(oracle, golden_cases, golden_synthetic):
+    """tests/golden/contexts.npz = what the unmodified reference's own pair loop built, observed at
+    ReTriangulator::setEdges (oracle/ref_hook.cpp), pair list ascending."""
+    import os
+    from conftest import GOLDEN, check_contexts_against
+    fx = np.load(os.path.join(GOLDEN, "contexts.npz"))
+    total = 0
+    for name, (a, b, out) in _context_inputs(golden_cases, golden_synthetic).items():
+        hits = out["pairs"][out["hit"].astype(bool)]
+        key = name.replace("-", "_")
+        for w, s in enumerate("ab"):
+            o = oracle.cut_contexts(hits, out["seg_hits"], w)
+            assert np.array_equal(o["tri"], np.unique(hits[:, w]))
+            check_contexts_against(o, lambda k: fx["%s__%s_%s" % (key, s, k)], name + ":" + s)
+            total += len(fx["%s__%s_tri" % (key, s)])
+    assert total > 1500      # 1,558 contexts of the reference in the fixture
+
+
+@pytest.mark.skipif(not (Ref.available() and __import__("os").path.exists(__import__("oracle").HOOK_SO)),
+                    reason="oracle/_ref (reference + hook) not built")
+def test_cut_contexts_match_live_reference(oracle):
+    from conftest import check_contexts_against
+    from oracle.ref_contexts import capture
+    from solidboolean_b200 import meshgen
+    a = meshgen.icosphere(3, round_to_float=True)
+    b = meshgen.torus(24, 12, center=(0.31, 0.02, 0.05))
+    cap = capture(a, b, True)
+    assert cap["ok"][0] == 1 and len(cap["hits"]) > 50
+    assert np.all(np.diff(cap["hits"][:, 0].astype(np.int64) << 32 | cap["hits"][:, 1]) > 0)   # the loop saw ascending pairs
+    for w, s in enumerate("ab"):
+        o = oracle.cut_contexts(cap["hits"], cap["seg"], w)
+        assert len(cap[s + "_tri"]) == len(o["tri"])
+        check_contexts_against(o, lambda k: cap[s + "_" + k], s)
+    # the reference's own (tree-traversal) order gives the same context SETS for this input,
+    # but not necessarily the same point numbering: only the sorted run is the contract
+    cap2 = capture(a, b, False)
+    assert sorted(map(tuple, cap2["hits"].tolist())) == list(map(tuple, cap["hits"].tolist()))
