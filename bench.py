@@ -554,7 +554,8 @@ def run_ours(args):
 
 
 def next_rows(sb, ctx, ma, mb, a, b, with_cpu):
-    """SURVEY 8f rows 2-3, outside the timed step: uncut triangles + half-edge map
+    """SURVEY 8f rows 1-3, outside the timed step: the per-triangle intersection contexts (the
+    pair-loop body of combine(), :296-339), uncut triangles + half-edge map
     (addUnintersectedTriangles, reference src/solidboolean.cpp:250-286) and the face groups of the
     uncut triangles (the flood of buildFaceGroups, :229-238) on the device, device time from the
     library's stage events; beside them the reference's own two functions on one host core."""
@@ -576,7 +577,15 @@ def next_rows(sb, ctx, ma, mb, a, b, with_cpu):
             best = rec
         keep = (ua.half_edges(), ub.half_edges(), ua.components()[0], ub.components()[0]) if with_cpu and _ == 3 else None
         ua.close(); ub.close()
+        # row 1: the per-triangle intersection contexts of both meshes (the pair-loop body of combine())
+        ctx.reset_timing()
+        cuts = [x.contexts(w) for w in (0, 1)]
+        rec["contexts_ms"] = round(ctx.timing()[0]["contexts"], 4)
+        rec["contexts"] = [len(c["tri"]) for c in cuts]
+        if best is not rec and rec["contexts_ms"] < best.get("contexts_ms", 1e9):
+            best["contexts_ms"], best["contexts"] = rec["contexts_ms"], rec["contexts"]
     fa, fb = x.face_flags()
+    x_hits = x.hits()
     x.close()
     ctx.enable_timing(False)
 
@@ -600,7 +609,17 @@ def next_rows(sb, ctx, ma, mb, a, b, with_cpu):
             la, _ga = op.uncut_groups(0, best["uncut_triangles"][0])
             lb, _gb = op.uncut_groups(1, best["uncut_triangles"][1])
             (ka, oa), (kb, ob), ca, cb = keep
+            from oracle import Oracle
+            hab, hseg = x_hits
+            t0 = time.perf_counter()
+            oc = [Oracle.get().cut_contexts(hab, hseg, w) for w in (0, 1)]
+            port_ms = (time.perf_counter() - t0) * 1e3
+            same_ctx = all(np.array_equal(d[k], o[k]) for d, o in zip(cuts, oc) for k in ("tri", "point_start", "edge_start", "edges")) \
+                and all(d["points"].tobytes() == o["points"].tobytes() for d, o in zip(cuts, oc))
+            comb = op.combine()     # the reference's own time-points around its pair loop (predicate included; it may fail later on)
             best["reference_cpu"] = {
+                "pair_loop_stage_ms": round(float(comb["stage_ms"][1]), 1), "contexts_oracle_port_ms": round(port_ms, 2),
+                "contexts_identical_to_oracle": bool(same_ctx),
                 "cores": 1, "addUnintersectedTriangles_ms": round(op.uncut_ms(0, 0) + op.uncut_ms(0, 1), 1),
                 "buildFaceGroups_ms": round(op.uncut_ms(1, 0) + op.uncut_ms(1, 1), 1),
                 "identical": bool(np.array_equal(ra["keys"], ka) and np.array_equal(ra["owner"], oa)

@@ -39,6 +39,7 @@ typedef struct sb_context sb_context;
 typedef struct sb_mesh sb_mesh;
 typedef struct sb_isect sb_isect;
 typedef struct sb_uncut sb_uncut;
+typedef struct sb_cuts sb_cuts;
 
 /* Thread-local message of the last failing call ("" if none). */
 const char *sb_last_error(void);
@@ -164,6 +165,28 @@ int sb_fp64_peak(sb_context *ctx, double *nofma_gflops, double *fma_gflops);
 int sb_tri_tri_batch(sb_context *ctx, const double *tris18, size_t n,
                      int32_t *ret, int32_t *coplanar, double *seg6);
 
+/* ---- per-triangle intersection contexts: replaces the body of the pair loop of
+ * SolidBoolean::combine (src/solidboolean.cpp:296-339; addIntersectedPoint :305-310, the neighbour
+ * bookkeeping :321-339) -- SURVEY 8f row 1.
+ * One context per triangle of mesh `which` (0 = first, 1 = second) that takes part in an
+ * intersecting pair: its points = the segment end points de-duplicated by PositionKey
+ * (src/positionkey.cpp:32-54), the FIRST position seen with a key kept, in first-seen order; its
+ * relations = the undirected pairs of point numbers (3 + index, as the reference numbers them
+ * behind the triangle's own corners) that a segment joins, coinciding ends dropped.  "Seen" refers
+ * to the pair list in ascending (first, second) order, i.e. the hits as sb_isect_hits returns them
+ * (the reference's own list is in the order of its tree traversal; its loop body is the same).
+ * Contexts come in ascending triangle id; the relations of a context in ascending (low, high). */
+int sb_isect_contexts(const sb_isect *isect, int which, sb_cuts **out);
+void sb_cuts_destroy(sb_cuts *cuts);
+int sb_cuts_counts(const sb_cuts *cuts, size_t *n_contexts, size_t *n_points, size_t *n_relations);
+/* tri[n_contexts]; point_start / relation_start [n_contexts + 1] (CSR); points 3 doubles each;
+ * relations 2 uint32 each.  Any pointer may be NULL. */
+int sb_cuts_fetch(const sb_cuts *cuts, uint32_t *tri, uint32_t *point_start, double *points,
+                  uint32_t *relation_start, uint32_t *relations);
+/* Device pointers of the same arrays (valid until sb_cuts_destroy). */
+int sb_cuts_device_ptrs(const sb_cuts *cuts, void **tri, void **point_start, void **points,
+                        void **relation_start, void **relations);
+
 /* ---- uncut triangles + half-edge map: replaces SolidBoolean::addUnintersectedTriangles
  * (src/solidboolean.cpp:250-286, called at :411-421) and answers the half-edge lookups of
  * buildFaceGroups (:205-224) -- SURVEY 8f row 2.
@@ -250,8 +273,9 @@ enum {
     SB_STAGE_NARROW = 2,   /* hit / candidate sorts + gather */
     SB_STAGE_CLASSIFY = 3, /* ray classification */
     SB_STAGE_PREDICATE = 4,/* the tri/tri predicate kernel alone (FP64 roofline) */
-    SB_STAGE_HALFEDGE = 5, /* uncut-triangle compaction, half-edge sort, adjacency */
-    SB_STAGE_COUNT = 6
+    SB_STAGE_HALFEDGE = 5, /* uncut-triangle compaction, half-edge sort, adjacency, face groups */
+    SB_STAGE_CONTEXTS = 6, /* per-triangle intersection contexts */
+    SB_STAGE_COUNT = 7
 };
 int sb_context_enable_timing(sb_context *ctx, int enable);
 int sb_context_reset_timing(sb_context *ctx);

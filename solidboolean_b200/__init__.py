@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(HERE, "lib", "libsolidboolean_b200.so")  # override: dev builds
 
-STAGES = ("build", "broad", "narrow", "classify", "predicate", "halfedge")
+STAGES = ("build", "broad", "narrow", "classify", "predicate", "halfedge", "contexts")
 ISECT_NO_SORT = 1
 
 
@@ -75,6 +75,11 @@ ABI = {
     "sb_isect_path_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "sb_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sb_tri_tri_batch": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "sb_isect_contexts": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "sb_cuts_destroy": (None, [_vp]),
+    "sb_cuts_counts": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "sb_cuts_fetch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_cuts_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "sb_isect_uncut": (C.c_int, [_vp, C.c_int, _sz, _sz, C.POINTER(_vp)]),
     "sb_mesh_uncut": (C.c_int, [_vp, _vp, _sz, _sz, C.POINTER(_vp)]),
     "sb_uncut_destroy": (None, [_vp]),
@@ -385,6 +390,25 @@ class Isect:
         fb = np.zeros(self.b.num_triangles, np.uint8)
         _check(self.lib.sb_isect_face_flags(self.h, _ptr(fa), _ptr(fb)))
         return fa, fb
+
+    def contexts(self, which: int):
+        """sb_isect_contexts: the per-triangle intersection contexts of mesh `which` (the pair-loop
+        body of combine(), reference src/solidboolean.cpp:296-339), hits in ascending (a, b) order.
+        -> dict(tri [c], point_start [c+1], points [p,3], edge_start [c+1], edges [e,2])"""
+        h = _vp()
+        _check(self.lib.sb_isect_contexts(self.h, which, C.byref(h)))
+        try:
+            nc, npts, ne = _sz(0), _sz(0), _sz(0)
+            _check(self.lib.sb_cuts_counts(h, C.byref(nc), C.byref(npts), C.byref(ne)))
+            tri = np.zeros(nc.value, np.uint32)
+            ps = np.zeros(nc.value + 1, np.uint32)
+            es = np.zeros(nc.value + 1, np.uint32)
+            pts = np.zeros((npts.value, 3), np.float64)
+            edges = np.zeros((ne.value, 2), np.uint32)
+            _check(self.lib.sb_cuts_fetch(h, _ptr(tri), _ptr(ps), _ptr(pts), _ptr(es), _ptr(edges)))
+        finally:
+            self.lib.sb_cuts_destroy(h)
+        return dict(tri=tri, point_start=ps, points=pts, edge_start=es, edges=edges)
 
     def uncut(self, which: int, vertex_offset=0, triangle_offset=0) -> "Uncut":
         """sb_isect_uncut: the faces of mesh `which` the intersection left alone + their half-edge map."""

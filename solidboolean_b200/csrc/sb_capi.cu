@@ -54,6 +54,7 @@ struct DeviceScalars { // device counters of one lane (128-byte slots)
     unsigned int uncutTotal;     // sb_*_uncut: uncut faces
     unsigned int heRepeat;       // ... first refused half-edge insertion (ordinal), UINT_MAX = none
     unsigned int ccCount;        // sb_uncut_components: components
+    unsigned int cuts[3];        // sb_isect_contexts: contexts, points, relations
 };
 static_assert(sizeof(DeviceScalars) <= 128, "lane slot too small");
 
@@ -72,7 +73,7 @@ struct sb_context {
     };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> freeEvents;
-    float acc[SB_STAGE_COUNT] = {0, 0, 0, 0, 0, 0};
+    float acc[SB_STAGE_COUNT] = {0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t t0 = nullptr;      // timing reference (recorded at reset)
     cudaEvent_t orderEvent = nullptr; // orders per-mesh streams behind the context stream
     // scratch
@@ -171,6 +172,15 @@ struct sb_uncut {
     int32_t *adj = nullptr;       // 3 nTri, indexed by ordinal
     uint32_t *label = nullptr;    // nTri component labels (sb_uncut_components, on first request)
     size_t nComponents = 0;
+    std::vector<void *> owned;
+};
+
+// Result of sb_isect_contexts (sb_cuts.cu), device-resident.
+struct sb_cuts {
+    sb_context *ctx = nullptr;
+    size_t nCtx = 0, nPoints = 0, nEdges = 0;
+    uint32_t *tri = nullptr, *pointStart = nullptr, *edgeStart = nullptr, *edges = nullptr;
+    double *points = nullptr;
     std::vector<void *> owned;
 };
 
@@ -1778,6 +1788,115 @@ int sb_uncut_device_ptrs(const sb_uncut *u, void **face, void **tri3, void **key
     if (keys) *keys = u->keys;
     if (owner) *owner = u->owner;
     if (adj3) *adj3 = u->adj;
+    return SB_OK;
+}
+
+// ---- per-triangle intersection contexts (sb_cuts.cu) ------------------------------------
+
+void sb_cuts_destroy(sb_cuts *k)
+{
+    if (!k)
+        return;
+    DeviceGuard g(k->ctx->device);
+    for (void *p : k->owned)
+        cudaFreeAsync(p, k->ctx->stream);
+    delete k;
+}
+
+int sb_isect_contexts(const sb_isect *x, int which, sb_cuts **out)
+{
+    if (!x || !out || (which != 0 && which != 1))
+        return fail(SB_ERR_INVALID, "null isect / out, or which not 0 / 1");
+    *out = nullptr;
+    if (x->noSort)
+        return fail(SB_ERR_INVALID, "contexts need the hits in ascending order (SB_ISECT_NO_SORT was set)");
+    sb_context *c = x->ctx;
+    DeviceGuard g(c->device);
+    sb_cuts *k = new (std::nothrow) sb_cuts;
+    if (!k)
+        return fail(SB_ERR_NOMEM, "out of host memory");
+    k->ctx = c;
+    const size_t n = x->nHit;
+    if (n == 0) {
+        *out = k;
+        return SB_OK;
+    }
+    int r = SB_OK;
+    uint32_t *scratch = nullptr;
+    auto bail = [&](int code) {
+        if (scratch)
+            cudaFreeAsync(scratch, c->stream);
+        sb_cuts_destroy(k);
+        return code;
+    };
+    StageTimer timer(c, SB_STAGE_CONTEXTS);
+    if ((r = alloc_async(c, &k->tri, n, &k->owned)) || (r = alloc_async(c, &k->pointStart, n + 1, &k->owned)) ||
+        (r = alloc_async(c, &k->edgeStart, n + 1, &k->owned)) || (r = alloc_async(c, &k->points, 6 * n, &k->owned)) ||
+        (r = alloc_async(c, &k->edges, 2 * n, &k->owned)) || (r = alloc_async(c, &scratch, sbk_cut_contexts_scratch(n), nullptr)) ||
+        (r = ensure_radix_ws(c, n)))
+        return bail(r);
+    cudaError_t e = sbk_cut_contexts(c->stream, x->hitAB, reinterpret_cast<const double *>(x->hitSeg), (uint32_t)n, which,
+        which == 0 ? x->bitsA : x->bitsB, scratch, c->radixWs, c->smCount, k->tri, k->pointStart, k->points, k->edgeStart, k->edges,
+        c->dScalars->cuts, c->lc);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+        return bail(fail(SB_ERR_CUDA, "contexts: %s", cudaGetErrorString(e)));
+    cudaFreeAsync(scratch, c->stream);
+    k->nCtx = c->hScalars->cuts[0];
+    k->nPoints = c->hScalars->cuts[1];
+    k->nEdges = c->hScalars->cuts[2];
+    *out = k;
+    return SB_OK;
+}
+
+int sb_cuts_counts(const sb_cuts *k, size_t *n_contexts, size_t *n_points, size_t *n_relations)
+{
+    if (!k)
+        return fail(SB_ERR_INVALID, "cuts is null");
+    if (n_contexts) *n_contexts = k->nCtx;
+    if (n_points) *n_points = k->nPoints;
+    if (n_relations) *n_relations = k->nEdges;
+    return SB_OK;
+}
+
+int sb_cuts_fetch(const sb_cuts *k, uint32_t *tri, uint32_t *point_start, double *points, uint32_t *relation_start,
+    uint32_t *relations)
+{
+    if (!k)
+        return fail(SB_ERR_INVALID, "cuts is null");
+    sb_context *c = k->ctx;
+    DeviceGuard g(c->device);
+    if (!k->nCtx) {
+        if (point_start) point_start[0] = 0;
+        if (relation_start) relation_start[0] = 0;
+        return SB_OK;
+    }
+    if (tri)
+        SB_CUDA(cudaMemcpyAsync(tri, k->tri, 4 * k->nCtx, cudaMemcpyDeviceToHost, c->stream));
+    if (point_start)
+        SB_CUDA(cudaMemcpyAsync(point_start, k->pointStart, 4 * (k->nCtx + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (points && k->nPoints)
+        SB_CUDA(cudaMemcpyAsync(points, k->points, 24 * k->nPoints, cudaMemcpyDeviceToHost, c->stream));
+    if (relation_start)
+        SB_CUDA(cudaMemcpyAsync(relation_start, k->edgeStart, 4 * (k->nCtx + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (relations && k->nEdges)
+        SB_CUDA(cudaMemcpyAsync(relations, k->edges, 8 * k->nEdges, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_cuts_device_ptrs(const sb_cuts *k, void **tri, void **point_start, void **points, void **relation_start, void **relations)
+{
+    if (!k)
+        return fail(SB_ERR_INVALID, "cuts is null");
+    if (tri) *tri = k->tri;
+    if (point_start) *point_start = k->pointStart;
+    if (points) *points = k->points;
+    if (relation_start) *relation_start = k->edgeStart;
+    if (relations) *relations = k->edges;
     return SB_OK;
 }
 

@@ -115,6 +115,13 @@ cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t nT
     const uint32_t *sortedTri /* Morton order of the mesh, or null */, const uint32_t *face, uint32_t nT, uint32_t *scratch,
     uint32_t *label, uint32_t *count, LaunchCounter &lc);
 
+// sb_cuts.cu -- per-triangle intersection contexts (the pair-loop body of SolidBoolean::combine)
+size_t sbk_cut_contexts_scratch(size_t nHits); // 4-byte words
+cudaError_t sbk_cut_contexts(cudaStream_t s, const uint32_t *hitAB, const double *seg, uint32_t n, int which, unsigned bitsTri,
+    uint32_t *scratch, uint32_t *radixWs, int smCount, uint32_t *cutTri /* n */, uint32_t *pointStart /* n + 1 */,
+    double *points /* 6 n */, uint32_t *edgeStart /* n + 1 */, uint32_t *edges /* 2 n */, uint32_t *counts /* dev: 3 */,
+    LaunchCounter &lc);
+
 // sb_classify.cu
 struct ClassifyArgs {
     // query points: either explicit (pts != null, AoS 3*Q, processed in given order)

@@ -21,25 +21,6 @@ SolidBoolean::~SolidBoolean() {}
 
 const std::vector<Vector3> &SolidBoolean::resultVertices() { return m_newVertices; }
 
-// ---- per-triangle cut bookkeeping (reference src/solidboolean.cpp:296-311, 321-339)
-
-size_t SolidBoolean::CutTriangle::addPoint(const Vector3 &p)
-{
-    auto ins = lookup.insert({PositionKey(p), points.size()});
-    if (ins.second)
-        points.push_back(p);
-    return ins.first->second;
-}
-
-void SolidBoolean::CutTriangle::addSegment(const Vector3 &a, const Vector3 &b)
-{
-    size_t ia = 3 + addPoint(a), ib = 3 + addPoint(b);
-    if (ia == ib)
-        return;
-    neighbors[ia].insert(ib);
-    neighbors[ib].insert(ia);
-}
-
 size_t SolidBoolean::weldPoint(const Vector3 &p)
 {
     auto ins = m_weldMap.insert({PositionKey(p), m_newVertices.size()});
@@ -396,13 +377,38 @@ bool SolidBoolean::combine()
         std::cout << "combine failed: " << sb_last_error() << std::endl;
         return false;
     }
+    // ---- GPU: the per-triangle contexts the reference builds in the body of its pair loop
+    // (src/solidboolean.cpp:296-339): welded points in first-seen order + the relations between them
     std::map<size_t, CutTriangle> firstCuts, secondCuts; // ordered: deterministic output
-    for (size_t h = 0; h < hitCount; ++h) {
-        size_t a = m_hitPairs[2 * h], b = m_hitPairs[2 * h + 1];
-        const double *s = &m_hitSegments[6 * h];
-        Vector3 source(s[0], s[1], s[2]), target(s[3], s[4], s[5]);
-        firstCuts[a].addSegment(source, target);
-        secondCuts[b].addSegment(source, target);
+    for (int which = 0; which < 2; ++which) {
+        sb_cuts *contexts = nullptr;
+        if (sb_isect_contexts(isect, which, &contexts) != SB_OK) {
+            sb_isect_destroy(isect);
+            std::cout << "combine failed: " << sb_last_error() << std::endl;
+            return false;
+        }
+        size_t contextCount = 0, pointCount = 0, relationCount = 0;
+        sb_cuts_counts(contexts, &contextCount, &pointCount, &relationCount);
+        std::vector<uint32_t> triangle(contextCount), pointStart(contextCount + 1), relationStart(contextCount + 1),
+            relations(2 * relationCount);
+        std::vector<double> points(3 * pointCount);
+        rc = sb_cuts_fetch(contexts, triangle.data(), pointStart.data(), points.data(), relationStart.data(), relations.data());
+        sb_cuts_destroy(contexts);
+        if (rc != SB_OK) {
+            sb_isect_destroy(isect);
+            std::cout << "combine failed: " << sb_last_error() << std::endl;
+            return false;
+        }
+        auto &cuts = which == 0 ? firstCuts : secondCuts;
+        for (size_t c = 0; c < contextCount; ++c) {
+            CutTriangle &cut = cuts[triangle[c]];
+            for (size_t p = pointStart[c]; p < pointStart[c + 1]; ++p)
+                cut.points.push_back(Vector3(points[3 * p], points[3 * p + 1], points[3 * p + 2]));
+            for (size_t r = relationStart[c]; r < relationStart[c + 1]; ++r) {
+                cut.neighbors[relations[2 * r]].insert(relations[2 * r + 1]);
+                cut.neighbors[relations[2 * r + 1]].insert(relations[2 * r]);
+            }
+        }
     }
     benchEnd_processPotentialIntersectedPairs = now();
 

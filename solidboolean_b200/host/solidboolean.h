@@ -46,12 +46,11 @@ public:
     size_t intersectingPairCount() const { return m_hitPairs.size() / 2; }
 
 private:
-    struct CutTriangle { // per intersected triangle: welded local points + segments between them
+    // per intersected triangle: welded local points + the relations between them, as the GPU builds
+    // them (sb_isect_contexts = the reference's IntersectedContext, src/solidboolean.cpp:296-339)
+    struct CutTriangle {
         std::vector<Vector3> points;
-        std::map<PositionKey, size_t> lookup;
         std::unordered_map<size_t, std::unordered_set<size_t>> neighbors; // indices are 3 + local point
-        size_t addPoint(const Vector3 &p);
-        void addSegment(const Vector3 &a, const Vector3 &b);
     };
     // half-edge (from << 32 | to) -> triangle.  The uncut triangles' entries arrive from the GPU
     // as one array sorted by key (sb_uncut_half_edges: lookup = binary search); the pieces of

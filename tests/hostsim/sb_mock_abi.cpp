@@ -24,6 +24,8 @@ int sbo_uncut_half_edges(const uint32_t *tri, size_t nT, const uint8_t *cut, uin
 void sbo_uncut_adjacency(const uint32_t *tri, const uint32_t *face, size_t nTri, uint64_t vertexOffset,
     const uint64_t *keys, const uint32_t *owner, size_t nKeys, int32_t *adj);
 size_t sbo_uncut_components(const int32_t *adj, size_t nTri, uint64_t triangleOffset, uint32_t *label);
+size_t sbo_cut_contexts(const uint32_t *hits, const double *seg, size_t nHit, int which, uint32_t *cutTri,
+    uint32_t *pointStart, double *points, uint32_t *edgeStart, uint32_t *edges);
 }
 
 struct sb_context { int dummy; };
@@ -36,6 +38,10 @@ struct sb_isect {
     size_t nCand = 0;
     std::vector<uint32_t> hitAB;
     std::vector<double> hitSeg;
+};
+struct sb_cuts {
+    std::vector<uint32_t> tri, pointStart, edgeStart, edges;
+    std::vector<double> points;
 };
 struct sb_uncut {
     const sb_mesh *mesh = nullptr;
@@ -101,6 +107,41 @@ int sb_isect_hits(const sb_isect *x, uint32_t *ab, double *seg)
 {
     if (ab && !x->hitAB.empty()) std::memcpy(ab, x->hitAB.data(), 4 * x->hitAB.size());
     if (seg && !x->hitSeg.empty()) std::memcpy(seg, x->hitSeg.data(), 8 * x->hitSeg.size());
+    return SB_OK;
+}
+int sb_isect_contexts(const sb_isect *x, int which, sb_cuts **out)
+{
+    size_t n = x->hitAB.size() / 2;
+    sb_cuts *k = new sb_cuts;
+    k->tri.resize(n + 1);
+    k->pointStart.assign(n + 1, 0);
+    k->edgeStart.assign(n + 1, 0);
+    k->points.resize(6 * n + 1);
+    k->edges.resize(2 * n + 1);
+    size_t c = n ? sbo_cut_contexts(x->hitAB.data(), x->hitSeg.data(), n, which, k->tri.data(), k->pointStart.data(),
+                       k->points.data(), k->edgeStart.data(), k->edges.data())
+                 : 0;
+    k->tri.resize(c);
+    k->pointStart.resize(c + 1);
+    k->edgeStart.resize(c + 1);
+    *out = k;
+    return SB_OK;
+}
+void sb_cuts_destroy(sb_cuts *k) { delete k; }
+int sb_cuts_counts(const sb_cuts *k, size_t *nc, size_t *np, size_t *ne)
+{
+    if (nc) *nc = k->tri.size();
+    if (np) *np = k->pointStart.back();
+    if (ne) *ne = k->edgeStart.back();
+    return SB_OK;
+}
+int sb_cuts_fetch(const sb_cuts *k, uint32_t *tri, uint32_t *ps, double *points, uint32_t *es, uint32_t *edges)
+{
+    if (tri && !k->tri.empty()) std::memcpy(tri, k->tri.data(), 4 * k->tri.size());
+    if (ps) std::memcpy(ps, k->pointStart.data(), 4 * k->pointStart.size());
+    if (es) std::memcpy(es, k->edgeStart.data(), 4 * k->edgeStart.size());
+    if (points && k->pointStart.back()) std::memcpy(points, k->points.data(), 24 * (size_t)k->pointStart.back());
+    if (edges && k->edgeStart.back()) std::memcpy(edges, k->edges.data(), 8 * (size_t)k->edgeStart.back());
     return SB_OK;
 }
 int sb_isect_uncut(const sb_isect *x, int which, size_t vertexOffset, size_t triangleOffset, sb_uncut **out)
