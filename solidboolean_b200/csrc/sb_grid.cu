@@ -20,6 +20,10 @@
 #include "sb_internal.h"
 #include "sb_gridq.cuh"
 
+#ifndef SB_FILL_AGG
+#define SB_FILL_AGG 0 // warp-aggregated slot claims in the fill pass (measured: see DESIGN section 4)
+#endif
+
 namespace {
 
 
@@ -109,10 +113,28 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
         // first dependent store, so their round trips overlap instead of adding up
         const bool du = cu1 != cu0, dv = cv1 != cv0;
         const uint32_t c00 = base + cv0 * nu + cu0;
+#if SB_FILL_AGG
+        // Morton-neighbouring triangles mostly land in the same cells: one atomic per distinct cell
+        // of the warp, the lanes that share it take consecutive slots below the returned end
+        const unsigned act = __activemask();
+        const uint32_t lane = threadIdx.x & 31, below = lanemask_lt();
+        auto claim = [&](bool want, uint32_t cell) {
+            const unsigned peers = __match_any_sync(act, want ? cell : 0xffffffffu - lane);
+            const int leader = __ffs(peers) - 1;
+            uint32_t end = 0;
+            if (want && (int)lane == leader)
+                end = atomicSub(&E[cell], (uint32_t)__popc(peers));
+            end = __shfl_sync(act, end, leader);
+            return end - 1u - (uint32_t)__popc(peers & below);
+        };
+        const uint32_t p00 = claim(true, c00 + 1), p10 = claim(du, c00 + 2), p01 = claim(dv, c00 + nu + 1),
+                       p11 = claim(du && dv, c00 + nu + 2);
+#else
         uint32_t p00 = atomicSub(&E[c00 + 1], 1u) - 1u, p10 = 0, p01 = 0, p11 = 0;
         if (du) p10 = atomicSub(&E[c00 + 2], 1u) - 1u;
         if (dv) p01 = atomicSub(&E[c00 + nu + 1], 1u) - 1u;
         if (du && dv) p11 = atomicSub(&E[c00 + nu + 2], 1u) - 1u;
+#endif
         if (p00 < refCap) refs[p00] = ref_in(cu0, cv0);
         if (du && p10 < refCap) refs[p10] = ref_in(cu1, cv0);
         if (dv && p01 < refCap) refs[p01] = ref_in(cu0, cv1);
