@@ -21,7 +21,7 @@
 #include "sb_gridq.cuh"
 
 #ifndef SB_FILL_AGG
-#define SB_FILL_AGG 0 // warp-aggregated slot claims in the fill pass (measured: see DESIGN section 4)
+#define SB_FILL_AGG 1 // warp-aggregated slot claims in the fill pass (build 0.562 -> 0.544 ms at C3)
 #endif
 
 namespace {

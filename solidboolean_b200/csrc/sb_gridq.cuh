@@ -122,6 +122,9 @@ __device__ __forceinline__ bool cell_ref_match(const CellRay &q, const uint2 &r)
 
 // ---- binning (shared by the leaf kernel of sb_build.cu, which counts, and sb_grid.cu, which fills) ----
 #define SB_GRID_MAX_CELLS_PER_TRI 1024u // larger footprints go to the per-axis "big" list
+#ifndef SB_COUNT_AGG
+#define SB_COUNT_AGG 1 // warp-aggregated cell counts in the leaf kernel (build 0.548 -> 0.534 ms at C3)
+#endif
 
 // quantised triangle box: one word per world axis, lo | hi << 16; .w = triangle id
 __device__ __forceinline__ uint4 quantise_box(const BoxD &b, const GridParams &g, uint32_t id)
@@ -168,6 +171,25 @@ __device__ __forceinline__ void grid_count_tri(const uint4 &q, const GridParams 
             continue;
         }
         const uint32_t base = g.cellBase[a], nu = g.nu[a];
+#if SB_COUNT_AGG
+        if (f.cu1 - f.cu0 <= 1 && f.cv1 - f.cv0 <= 1) {
+            // common case: one atomic per distinct cell of the warp's lanes that took this path
+            const unsigned act = __activemask();
+            const uint32_t lane = threadIdx.x & 31;
+            const bool du = f.cu1 != f.cu0, dv = f.cv1 != f.cv0;
+            const uint32_t c00 = base + f.cv0 * nu + f.cu0;
+            auto bump = [&](bool want, uint32_t cell) {
+                const unsigned peers = __match_any_sync(act, want ? cell : 0xffffffffu - lane);
+                if (want && (int)lane == __ffs(peers) - 1)
+                    atomicAdd(&E[cell], (uint32_t)__popc(peers));
+            };
+            bump(true, c00 + 1);
+            bump(du, c00 + 2);
+            bump(dv, c00 + nu + 1);
+            bump(du && dv, c00 + nu + 2);
+            continue;
+        }
+#endif
         for (uint32_t cv = f.cv0; cv <= f.cv1; ++cv)
             for (uint32_t cu = f.cu0; cu <= f.cu1; ++cu)
                 atomicAdd(&E[base + cv * nu + cu + 1], 1u);
