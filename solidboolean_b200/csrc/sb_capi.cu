@@ -449,6 +449,7 @@ int sb_context_create(int device, sb_context **out)
     cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
     SB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prioHigh));
     SB_CUDA(cudaMalloc(&c->dScalars, 512));
+    SB_CUDA(cudaMemset(c->dScalars, 0, 512)); // the counter blocks are read back whole
     SB_CUDA(cudaMallocHost(&c->hScalars, 512));
     SB_CUDA(cudaMallocHost(&c->hPool, 256 * 32));
     for (int l = 0; l < 3; ++l) {
