@@ -77,3 +77,23 @@ def test_contexts_config_c3_and_c4(ctx, oracle):
     devs = check_pair(ctx, oracle, *meshgen.config_c3(), "c3")
     assert sum(len(d["tri"]) for d in devs) > 5000
     check_pair(ctx, oracle, *meshgen.config_c4(), "c4")
+
+
+def test_contexts_and_uncut_reject_bad_arguments(ctx):
+    import ctypes as C
+    a, b = meshgen.icosphere(2), meshgen.icosphere(2, center=(0.4, 0.1, 0.0))
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    x = ma.intersect(mb)
+    lib, h = x.lib, sb._vp()
+    assert lib.sb_isect_contexts(None, 0, C.byref(h)) == 1          # SB_ERR_INVALID
+    assert lib.sb_isect_contexts(x.h, 2, C.byref(h)) == 1
+    assert lib.sb_isect_contexts(x.h, 0, None) == 1
+    assert lib.sb_isect_uncut(x.h, 5, 0, 0, C.byref(h)) == 1
+    assert lib.sb_mesh_uncut(None, None, 0, 0, C.byref(h)) == 1
+    assert lib.sb_uncut_counts(None, None, None, None) == 1 and lib.sb_cuts_counts(None, None, None, None) == 1
+    assert b"null" in lib.sb_last_error() or b"cuts" in lib.sb_last_error()
+    # hits left in emission order: "first seen" would not be defined
+    y = ma.intersect(mb, flags=1)                                    # SB_ISECT_NO_SORT
+    assert lib.sb_isect_contexts(y.h, 0, C.byref(h)) == 1
+    assert b"ascending" in lib.sb_last_error()
+    y.close(); x.close(); ma.close(); mb.close()
