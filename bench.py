@@ -258,9 +258,12 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    # Native libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner
+    # there): stdout is kept for the ONE JSON line -- everything else of this process goes to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its banner / debug lines to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not os.path.exists(sb.LIB_PATH):
         if local == 0:
@@ -537,7 +540,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": Href / sec, "unit": UNIT, "cores": threads, "kind": detail["kind"],
                                     "sample": sample_description(detail, threads), "front_end_ms": sec * 1e3,
                                     "H": Href, "P": detail["P"]}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     # release everything that was used on the library's stream while that stream is alive
     # (torch's pinned-memory allocator records an event on the stream a block was used on)
     torch.cuda.synchronize()
