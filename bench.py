@@ -291,8 +291,11 @@ def run_ours(args):
 
     dev = torch.device("cuda", local)
     # one buffer for both flag arrays: a single NCCL collective exchanges them
-    flagsAB = torch.zeros(nA + nB, dtype=torch.uint8, device=dev)
-    flagsA, flagsB = flagsAB[:nA], flagsAB[nA:]
+    # (padded to whole 32-bit words: the collective sums int32 lanes -- every byte is written by exactly
+    # one rank, so no carry ever crosses a byte -- which NCCL reduces with its fast paths, unlike uint8)
+    flagsAB = torch.zeros((nA + nB + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+    flagsAB32 = flagsAB.view(torch.int32)
+    flagsA, flagsB = flagsAB[:nA], flagsAB[nA:nA + nB]
     assert flagsB.data_ptr() == flagsAB.data_ptr() + nA
     l2_flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -304,48 +307,45 @@ def run_ours(args):
         per-rank record {nCand, nHit, hit pairs, hit segments} straight from the library's
         device buffers, and ONE all_reduce over both per-face flag arrays (every face is
         classified by exactly one rank, so summing the byte masks is the gather).
-        No host round trip: the header goes up from pinned memory, and this rank only
-        looks at the other ranks' counts (a 16 x world byte read-back) when its own hit
-        count says the padding may have to grow.  Returns global (P, H) when it looked,
-        else this rank's share with a note -- the caller sums the shares after the loop."""
+        No host round trip in the steady state: sb_isect_pack_device writes the record, and the
+        other ranks' counts are only read back (16 x world bytes) while the padding is still being
+        sized (the first steps) -- afterwards the caller reads them once, after the timed region."""
         while True:
             cap = hit_cap[0]
             rec = 16 + 8 * cap + 48 * cap                     # header + int32[cap,2] + float64[cap,6]
             if xbuf.get("cap") != cap:
                 xbuf.update(cap=cap, mine=torch.zeros(rec, dtype=torch.uint8, device=dev),
-                            everyone=torch.empty(world * rec, dtype=torch.uint8, device=dev),
-                            hdr=torch.zeros(2, dtype=torch.int64).pin_memory())
-            mine, everyone, hdr = xbuf["mine"], xbuf["everyone"], xbuf["hdr"]
-            hdr[0], hdr[1] = x.num_candidates, x.num_hits
-            mine[:16].view(torch.int64).copy_(hdr, non_blocking=True)
-            n = min(x.num_hits, cap)
-            if n:
-                ptrs = x.device_ptrs(candidates=False)   # the hit records only: the candidate list stays unsorted
-                mine[16:16 + 8 * n].view(torch.int32).copy_(_as_tensor(torch, ptrs["hit_ab"], (2 * n,), torch.int32, dev))
-                mine[16 + 8 * cap:16 + 8 * cap + 48 * n].view(torch.float64).copy_(
-                    _as_tensor(torch, ptrs["hit_seg"], (6 * n,), torch.float64, dev))
+                            everyone=torch.empty(world * rec, dtype=torch.uint8, device=dev))
+            mine, everyone = xbuf["mine"], xbuf["everyone"]
+            # header + hit pairs + segments straight from the library's device buffers (three async copies
+            # enqueued by one C call: the step is host-bound here, every Python-level op counts)
+            x.pack_device(mine.data_ptr(), cap)
             dist.all_gather_into_tensor(everyone, mine)
-            # every rank must take the same decision: the maximum hit count decides
-            cnt = everyone.view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2)
             if xbuf.get("checked") == cap:
                 # steady state (the same workload as the step that sized the padding, which
                 # left head room): no read-back -- and no rank-local decision, every rank
                 # must issue the same collectives; the counts stay on the device and the
-                # caller verifies them after the timed region
-                xbuf["cnt"] = cnt
+                # caller reads them after the timed region
                 break
+            # every rank must take the same decision: the maximum hit count decides
+            cnt = everyone.view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2)
             cnt = cnt.cpu()
             if int(cnt[:, 1].max()) <= cap // 2:
                 xbuf["checked"] = cap
-                xbuf["cnt"] = cnt
                 break
             hit_cap[0] = int(cnt[:, 1].max()) * 3 + 64   # some rank is close to the padding: once more, with room
-        dist.all_reduce(flagsAB)
+        dist.all_reduce(flagsAB32)
         gathered["hits"] = everyone
-        c = xbuf["cnt"]
-        return c[:, 0].sum(), c[:, 1].sum()       # tensors (device or host): read after the timed region
+        xbuf["rec"] = rec
+        return None, None                         # the counts are read from the gathered records after the timed region
 
     gathered = {}
+
+    def gathered_counts():
+        """Global (P, H, largest per-rank H) from the records of the last exchange (outside the timed region)."""
+        rec = xbuf["rec"]
+        cnt = gathered["hits"].view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2).cpu()
+        return int(cnt[:, 0].sum()), int(cnt[:, 1].sum()), int(cnt[:, 1].max())
 
     # ---------------- resident loop: `value` ----------------
     ma = ctx.mesh(a[0], a[1], build=False)
@@ -409,9 +409,10 @@ def run_ours(args):
         return float(t.item()) / steps, res, clocks
 
     ms_step, (P, H), clocks = timed_loop(resident_step, args.steps, args.warmup, True)
-    P, H = int(P), int(H)
     if world > 1:
-        assert int(xbuf["cnt"].cpu()[:, 1].max()) <= hit_cap[0], "hit padding overflow in the exchange"
+        P, H, hmax = gathered_counts()
+        assert hmax <= hit_cap[0], "hit padding overflow in the exchange"
+    P, H = int(P), int(H)
     stage_ms, launches = ctx.timing()
     stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
     stage_by_rank = None
@@ -456,6 +457,8 @@ def run_ours(args):
 
     ctx.enable_timing(False)
     e2e_ms, (P2, H2), _ = timed_loop(e2e_step, max(3, args.steps // 2), 2, False)
+    if world > 1:
+        P2, H2, _ = gathered_counts()
     P2, H2 = int(P2), int(H2)
     sampler.stop()
     h2d = 24 * (nVA + nVB) + 12 * (nA + nB)
@@ -546,7 +549,7 @@ def run_ours(args):
     # (torch's pinned-memory allocator records an event on the stream a block was used on)
     torch.cuda.synchronize()
     gathered.clear()
-    del out_in_a_t, out_in_b_t, flagsA, flagsB, flagsAB, l2_flush, pin
+    del out_in_a_t, out_in_b_t, flagsA, flagsB, flagsAB, flagsAB32, l2_flush, pin
     ma.close(); mb.close()
     torch.cuda.synchronize()
     if world > 1:

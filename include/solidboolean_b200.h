@@ -151,6 +151,12 @@ int sb_isect_face_flags(const sb_isect *isect, uint8_t *flagsA, uint8_t *flagsB)
 int sb_isect_device_ptrs(const sb_isect *isect, void **cand_keys, unsigned *bits_b,
                          void **hit_ab, void **hit_seg, void **flagsA, void **flagsB);
 
+/* The per-rank record of the multi-GPU exchange, written into a caller-owned DEVICE buffer
+ * of 16 + 56 * cap bytes on the context stream, no host round trip:
+ *   uint64 nCand, uint64 nHit | uint32 hit pairs [cap][2] | double segments [cap][6]
+ * (the first min(nHit, cap) hits; the rest of the buffer is left as it is). */
+int sb_isect_pack_device(const sb_isect *isect, void *d_record, size_t cap);
+
 /* How the candidate pairs left the predicate (flop accounting): out5 =
  * {rejected at plane(T2) test, rejected at plane(T1) test, coplanar 2-D test,
  *  rejected at the interval test, segment constructed}. */

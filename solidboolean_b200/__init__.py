@@ -72,6 +72,7 @@ ABI = {
     "sb_isect_face_flags": (C.c_int, [_vp, _vp, _vp]),
     "sb_isect_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint), C.POINTER(_vp),
                                        C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sb_isect_pack_device": (C.c_int, [_vp, _vp, _sz]),
     "sb_isect_path_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "sb_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sb_tri_tri_batch": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
@@ -415,6 +416,10 @@ class Isect:
         h = _vp()
         _check(self.lib.sb_isect_uncut(self.h, which, vertex_offset, triangle_offset, C.byref(h)))
         return Uncut(self.a if which == 0 else self.b, h)
+
+    def pack_device(self, d_record: int, cap: int):
+        """sb_isect_pack_device: {nCand, nHit, hit pairs, segments} into a device buffer of 16 + 56 cap bytes."""
+        _check(self.lib.sb_isect_pack_device(self.h, _vp(d_record), cap))
 
     def device_ptrs(self, candidates=True):
         """Device pointers of the results.  candidates=False leaves the candidate keys alone (asking

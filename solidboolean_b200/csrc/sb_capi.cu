@@ -1901,6 +1901,24 @@ int sb_cuts_device_ptrs(const sb_cuts *k, void **tri, void **point_start, void *
     return SB_OK;
 }
 
+int sb_isect_pack_device(const sb_isect *x, void *d_record, size_t cap)
+{
+    if (!x || !d_record)
+        return fail(SB_ERR_INVALID, "null isect or record");
+    sb_context *c = x->ctx;
+    DeviceGuard g(c->device);
+    char *rec = static_cast<char *>(d_record);
+    const unsigned long long header[2] = {x->nCand, x->nHit};
+    // 16 bytes from the stack: copied into the driver's staging at enqueue time
+    SB_CUDA(cudaMemcpyAsync(rec, header, sizeof(header), cudaMemcpyHostToDevice, c->stream));
+    const size_t n = std::min(x->nHit, cap);
+    if (n) {
+        SB_CUDA(cudaMemcpyAsync(rec + 16, x->hitAB, 8 * n, cudaMemcpyDeviceToDevice, c->stream));
+        SB_CUDA(cudaMemcpyAsync(rec + 16 + 8 * cap, x->hitSeg, 48 * n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return SB_OK;
+}
+
 int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret, int32_t *coplanar, double *seg6)
 {
     if (!c || (n && (!tris18 || !ret || !coplanar || !seg6)))
