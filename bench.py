@@ -433,6 +433,8 @@ def run_ours(args):
     out_in_a_t = torch.zeros(nA, dtype=torch.uint8).pin_memory()
     out_in_b_t = torch.zeros(nB, dtype=torch.uint8).pin_memory()
 
+    host_hits = {}   # pinned landing buffers of the e2e loop, grown on demand
+
     def e2e_step():
         with torch.cuda.stream(ext):
             # host buffers in through the C ABI: sb_mesh_upload (H2D) for both meshes first,
@@ -447,11 +449,16 @@ def run_ours(args):
                 Pg, Hg = gather_results(x)
             else:
                 Pg, Hg = x.num_candidates, x.num_hits
-            if rank == 0:  # results back to the host: hit pairs + segments, per-face flags
-                x.hits()
+            if rank == 0:  # results back to the host: per-face flags, hit pairs + segments -- all into PINNED
+                # buffers (the C ABI takes any host pointer; pageable ones make the copies staged and slow),
+                # flag copies enqueued first so that the one synchronisation inside sb_isect_hits covers all
                 out_in_a_t.copy_(flagsA, non_blocking=True)
                 out_in_b_t.copy_(flagsB, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                if host_hits.get("cap", -1) < x.num_hits:
+                    cap = x.num_hits * 3 // 2 + 64
+                    host_hits.update(cap=cap, ab=torch.zeros(2 * cap, dtype=torch.int32).pin_memory(),
+                                     seg=torch.zeros(6 * cap, dtype=torch.float64).pin_memory())
+                sb._check(x.lib.sb_isect_hits(x.h, host_hits["ab"].data_ptr(), host_hits["seg"].data_ptr()))
             x.close(); xa.close(); xb.close()
         return Pg, Hg
 
@@ -549,6 +556,7 @@ def run_ours(args):
     # (torch's pinned-memory allocator records an event on the stream a block was used on)
     torch.cuda.synchronize()
     gathered.clear()
+    host_hits.clear()
     del out_in_a_t, out_in_b_t, flagsA, flagsB, flagsAB, flagsAB32, l2_flush, pin
     ma.close(); mb.close()
     torch.cuda.synchronize()
