@@ -181,7 +181,9 @@ int sb_tri_tri_batch(sb_context *ctx, const double *tris18, size_t n,
  * behind the triangle's own corners) that a segment joins, coinciding ends dropped.  "Seen" refers
  * to the pair list in ascending (first, second) order, i.e. the hits as sb_isect_hits returns them
  * (the reference's own list is in the order of its tree traversal; its loop body is the same).
- * Contexts come in ascending triangle id; the relations of a context in ascending (low, high). */
+ * Contexts come in ascending triangle id; the relations of a context in ascending (low, high).
+ * An sb_isect made by sb_intersect_range / sb_front_end_range holds one shard's pairs: its contexts
+ * cover those pairs only (the second mesh's triangles may then appear in several shards). */
 int sb_isect_contexts(const sb_isect *isect, int which, sb_cuts **out);
 void sb_cuts_destroy(sb_cuts *cuts);
 int sb_cuts_counts(const sb_cuts *cuts, size_t *n_contexts, size_t *n_points, size_t *n_relations);
