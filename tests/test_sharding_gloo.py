@@ -48,7 +48,11 @@ def _worker(rank, world, port, out):
     flags_b[torch.from_numpy(mine_b)] = torch.from_numpy(ib)
     # ---- the exchange step (same protocol as bench.py::gather_results): one all_gather of
     # a packed per-rank record {nCand, nHit, pairs, segments}, one all_reduce over both flag arrays ----
-    flags_ab = torch.cat([flags_a, flags_b])
+    # (record layout = what sb_isect_pack_device writes; the flag bytes are reduced on int32 lanes over a
+    # buffer padded to whole words: every byte has one owner, so no carry crosses a byte)
+    flags_ab = torch.zeros((nA + nB + 15) // 16 * 16, dtype=torch.uint8)
+    flags_ab[:nA] = flags_a
+    flags_ab[nA:nA + nB] = flags_b
     cap = 8                                   # deliberately too small: exercises the regrow-and-repeat path
     while True:
         rec = 16 + 8 * cap + 48 * cap
@@ -64,8 +68,8 @@ def _worker(rank, world, port, out):
         if int(counts_all[:, 1].max()) <= cap:
             break
         cap = int(counts_all[:, 1].max()) * 3 // 2 + 64
-    dist.all_reduce(flags_ab)
-    flags_a, flags_b = flags_ab[:nA], flags_ab[nA:]
+    dist.all_reduce(flags_ab.view(torch.int32))
+    flags_a, flags_b = flags_ab[:nA], flags_ab[nA:nA + nB]
     ev = everyone.view(world, rec)
     gab = np.concatenate([ev[r, 16:16 + 8 * int(counts_all[r, 1])].contiguous().view(torch.int32).view(-1, 2).numpy()
                           for r in range(world)])
