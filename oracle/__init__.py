@@ -84,6 +84,9 @@ class Oracle:
         L.sbo_uncut_adjacency.argtypes = [_u32p, _u32p, C.c_size_t, C.c_uint64, _u64p, _u32p, C.c_size_t, _i32p]
         L.sbo_uncut_components.argtypes = [_i32p, C.c_size_t, C.c_uint64, _u32p]
         L.sbo_uncut_components.restype = C.c_size_t
+        L.sbo_face_groups.argtypes = [_u32p, C.c_size_t, _u64p, _u32p, C.c_size_t, _u32p, _u32p, C.c_size_t, C.c_size_t,
+                                      C.c_size_t, _u32p, _u32p, C.POINTER(C.c_size_t)]
+        L.sbo_face_groups.restype = C.c_size_t
         L.sbo_cut_contexts.argtypes = [_u32p, _f64p, C.c_size_t, C.c_int, _u32p, _u32p, _f64p, _u32p, _u32p]
         L.sbo_cut_contexts.restype = C.c_size_t
 
@@ -169,6 +172,22 @@ class Oracle:
         comps = self.lib.sbo_uncut_components(adj, n.value, triangle_offset, label) if n.value else 0
         return dict(ok=bool(ok), face=face, keys=keys, owner=owner, adj=adj, label=label, components=int(comps))
 
+    # -- buildFaceGroups with loops -------------------------------------------
+    def face_groups(self, tri, keys, owner, loops, remaining_start, remaining_count):
+        """SolidBoolean::buildFaceGroups (src/solidboolean.cpp:167-239) on explicit inputs.
+        loops: list of vertex cycles. -> group [nTri] (0xffffffff = unreached), order (assignment order), n_groups"""
+        tri = _u32(tri).reshape(-1, 3)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        owner = _u32(owner)
+        ls = np.cumsum([0] + [len(l) for l in loops]).astype(np.uint32)
+        lv = _u32(np.concatenate([np.asarray(l, np.uint32) for l in loops])) if loops else np.zeros(1, np.uint32)
+        group = np.zeros(max(len(tri), 1), np.uint32)
+        order = np.zeros(max(len(tri), 1), np.uint32)
+        n = C.c_size_t(0)
+        g = self.lib.sbo_face_groups(tri, len(tri), keys, owner, len(keys), ls, lv, len(loops), remaining_start,
+                                     remaining_count, group, order, C.byref(n))
+        return group[:len(tri)], order[:n.value], int(g)
+
     # -- per-triangle intersection contexts ---------------------------------
     def cut_contexts(self, hits, seg, which):
         """The pair-loop body of combine() (src/solidboolean.cpp:296-339) over `hits` in the given order.
@@ -253,6 +272,9 @@ class Ref:
             L.ref_op_uncut_lookup.argtypes = [vp, C.c_int, _u64p, C.c_size_t, _i32p]
             L.ref_op_uncut_groups.argtypes = [vp, C.c_int, _u32p]
             L.ref_op_uncut_groups.restype = C.c_size_t
+            L.ref_face_groups.argtypes = [_u32p, C.c_size_t, _u64p, _u32p, C.c_size_t, _u32p, _u32p, C.c_size_t, C.c_size_t,
+                                          C.c_size_t, _u32p, _u32p]
+            L.ref_face_groups.restype = C.c_size_t
             L.ref_op_uncut_ms.argtypes = [vp, C.c_int, C.c_int]
             L.ref_op_uncut_ms.restype = C.c_double
         if hasattr(L, "ref_load_obj"):
@@ -279,6 +301,20 @@ class Ref:
         self.lib.ref_load_obj(path.encode(), xyz.ctypes.data_as(C.c_void_p), C.byref(nv),
                               tri.ctypes.data_as(C.c_void_p), C.byref(nt))
         return xyz, tri
+
+    def face_groups(self, tri, keys, owner, loops, remaining_start, remaining_count):
+        """The reference's private buildFaceGroups on explicit inputs (same signature as Oracle.face_groups)."""
+        tri = _u32(tri).reshape(-1, 3)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        owner = _u32(owner)
+        ls = np.cumsum([0] + [len(l) for l in loops]).astype(np.uint32)
+        lv = _u32(np.concatenate([np.asarray(l, np.uint32) for l in loops])) if loops else np.zeros(1, np.uint32)
+        group = np.zeros(max(len(tri), 1), np.uint32)
+        order = np.zeros(max(len(tri), 1), np.uint32)
+        g = self.lib.ref_face_groups(tri, len(tri), keys, owner, len(keys), ls, lv, len(loops), remaining_start,
+                                     remaining_count, group, order)
+        n = int((group[:len(tri)] != 0xffffffff).sum())
+        return group[:len(tri)], order[:n], int(g)
 
     def mesh(self, xyz, tri) -> "RefMesh":
         return RefMesh(self, xyz, tri)

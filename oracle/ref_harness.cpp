@@ -461,6 +461,38 @@ size_t ref_op_uncut_groups(void *h, int which, uint32_t *label)
     return groups.size();
 }
 
+// buildFaceGroups (src/solidboolean.cpp:167-239) on explicit inputs: triangles (3 ids each), a
+// half-edge map (keys / owner), intersection loops (CSR of vertex cycles), the range of "remaining"
+// triangles.  group[t] = index of the group triangle t landed in (0xffffffff: none); order = the
+// groups' members concatenated group by group.  Returns the number of groups.
+size_t ref_face_groups(const uint32_t *tri, size_t nTri, const uint64_t *keys, const uint32_t *owner, size_t nKeys,
+    const uint32_t *loopStart, const uint32_t *loopVerts, size_t nLoops, size_t remainingStart, size_t remainingCount,
+    uint32_t *group, uint32_t *order)
+{
+    std::vector<Vector3> noVertices;
+    std::vector<std::vector<size_t>> noTriangles;
+    SolidMesh ma, mb;
+    SolidBoolean fresh(&ma, &mb);
+    std::vector<std::vector<size_t>> triangles(nTri), loops(nLoops), groups;
+    for (size_t t = 0; t < nTri; ++t)
+        triangles[t] = {tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]};
+    for (size_t k = 0; k < nLoops; ++k)
+        loops[k].assign(loopVerts + loopStart[k], loopVerts + loopStart[k + 1]);
+    std::unordered_map<uint64_t, size_t> map;
+    for (size_t i = 0; i < nKeys; ++i)
+        map.insert({keys[i], owner[i]});
+    fresh.buildFaceGroups(loops, map, triangles, remainingStart, remainingCount, groups);
+    for (size_t t = 0; t < nTri; ++t)
+        group[t] = 0xffffffffu;
+    size_t at = 0;
+    for (size_t g = 0; g < groups.size(); ++g)
+        for (size_t t : groups[g]) {
+            group[t] = (uint32_t)g;
+            order[at++] = (uint32_t)t;
+        }
+    return groups.size();
+}
+
 // milliseconds spent inside the reference's own functions by the last ref_op_uncut /
 // ref_op_uncut_groups: what = 0 addUnintersectedTriangles, 1 buildFaceGroups
 double ref_op_uncut_ms(void *h, int what, int which)

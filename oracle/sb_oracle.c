@@ -1007,3 +1007,130 @@ size_t sbo_cut_contexts(const uint32_t *hits, const double *seg, size_t nHit, in
     free(keys);
     return nCtx;
 }
+
+/* ---- buildFaceGroups with intersection loops (the part that is still on the host)
+ * SolidBoolean::buildFaceGroups (src/solidboolean.cpp:167-239), restated with its queue order:
+ * loop k (a closed vertex cycle) fences its half-edges and seeds group 2k through the triangle on
+ * half-edge (v_i, v_i+1) and group 2k+1 through the one on (v_i+1, v_i) (:176-196); the queue is
+ * drained first-in first-out, a triangle joins the group of the entry that reaches it first, and an
+ * edge is crossed through halfEdges.find(key(j, i)) unless key(i, j) is already in the fence map
+ * (:201-224); triangles of [remainingStart, remainingStart + remainingCount) no seed reached open
+ * further groups in ascending order (:229-238).
+ *   tri        3 vertex ids per triangle (all triangles the map can name)
+ *   keys/owner the half-edge map, ascending keys ((first << 32) | second)
+ *   loopStart  CSR over loopVerts, nLoops + 1 entries
+ * group[t] = group index of triangle t, or 0xffffffff if nothing reached it; order[] = the triangles
+ * in the order they were assigned (the concatenation of the reference's groups is a stable sort of it
+ * by group).  Returns the number of groups. */
+static int he_find(const uint64_t *keys, const uint32_t *owner, size_t n, uint64_t want, uint32_t *out)
+{
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (keys[mid] < want)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo < n && keys[lo] == want) {
+        *out = owner[lo];
+        return 1;
+    }
+    return 0;
+}
+
+typedef struct {
+    uint64_t *slot; /* key + 1, 0 = empty */
+    size_t cap;
+} u64set;
+
+static int u64set_insert(u64set *s, uint64_t key) /* 1 = newly inserted */
+{
+    size_t h = (size_t)he_hash(key) & (s->cap - 1);
+    while (s->slot[h] && s->slot[h] != key + 1)
+        h = (h + 1) & (s->cap - 1);
+    if (s->slot[h])
+        return 0;
+    s->slot[h] = key + 1;
+    return 1;
+}
+
+static int u64set_has(const u64set *s, uint64_t key)
+{
+    size_t h = (size_t)he_hash(key) & (s->cap - 1);
+    while (s->slot[h] && s->slot[h] != key + 1)
+        h = (h + 1) & (s->cap - 1);
+    return s->slot[h] != 0;
+}
+
+size_t sbo_face_groups(const uint32_t *tri, size_t nTri, const uint64_t *keys, const uint32_t *owner, size_t nKeys,
+    const uint32_t *loopStart, const uint32_t *loopVerts, size_t nLoops, size_t remainingStart, size_t remainingCount,
+    uint32_t *group, uint32_t *order, size_t *nOrdered)
+{
+    size_t nLoopEdges = loopStart[nLoops];
+    u64set fence;
+    fence.cap = 16;
+    while (fence.cap < 2 * (3 * nTri + 2 * nLoopEdges) + 16)
+        fence.cap <<= 1;
+    fence.slot = (uint64_t *)calloc(fence.cap, sizeof(uint64_t));
+    /* FIFO of (triangle, group) */
+    size_t qcap = 4 * nTri + 2 * nLoopEdges + 16, qh = 0, qt = 0; /* <= 3 per processed triangle + the seeds */
+    uint32_t *qTri = (uint32_t *)malloc(qcap * sizeof(uint32_t)), *qGrp = (uint32_t *)malloc(qcap * sizeof(uint32_t));
+    for (size_t t = 0; t < nTri; ++t)
+        group[t] = 0xffffffffu;
+    size_t groups = 0, done = 0;
+    for (size_t k = 0; k < nLoops; ++k) {
+        size_t n = loopStart[k + 1] - loopStart[k];
+        const uint32_t *v = loopVerts + loopStart[k];
+        for (size_t i = 0; i < n; ++i) {
+            size_t j = (i + 1) % n;
+            uint64_t fwd = ((uint64_t)v[i] << 32) | v[j], back = ((uint64_t)v[j] << 32) | v[i];
+            uint32_t o;
+            u64set_insert(&fence, fwd); /* :181 */
+            if (he_find(keys, owner, nKeys, fwd, &o)) {
+                qTri[qt] = o;
+                qGrp[qt++] = (uint32_t)groups;
+            }
+            u64set_insert(&fence, back); /* :189 */
+            if (he_find(keys, owner, nKeys, back, &o)) {
+                qTri[qt] = o;
+                qGrp[qt++] = (uint32_t)groups + 1;
+            }
+        }
+        groups += 2;
+    }
+    size_t next = remainingStart;
+    for (;;) {
+        while (qh < qt) { /* processQueue, :201-226 */
+            uint32_t t = qTri[qh], g = qGrp[qh];
+            ++qh;
+            if (group[t] != 0xffffffffu)
+                continue;
+            group[t] = g;
+            order[done++] = t;
+            for (int i = 0; i < 3; ++i) {
+                int j = (i + 1) % 3;
+                uint64_t e = ((uint64_t)tri[3 * (size_t)t + i] << 32) | tri[3 * (size_t)t + j];
+                if (u64set_has(&fence, e))
+                    continue;
+                u64set_insert(&fence, e);
+                uint32_t o;
+                if (he_find(keys, owner, nKeys, ((uint64_t)tri[3 * (size_t)t + j] << 32) | tri[3 * (size_t)t + i], &o)) {
+                    qTri[qt] = o;
+                    qGrp[qt++] = g;
+                }
+            }
+        }
+        while (next < remainingStart + remainingCount && group[next] != 0xffffffffu)
+            ++next;
+        if (next >= remainingStart + remainingCount)
+            break;
+        qTri[qt] = (uint32_t)next; /* :232-236 */
+        qGrp[qt++] = (uint32_t)groups++;
+    }
+    *nOrdered = done;
+    free(fence.slot);
+    free(qTri);
+    free(qGrp);
+    return groups;
+}

@@ -225,3 +225,72 @@ def test_cut_contexts_match_live_reference(oracle):
     # but not necessarily the same point numbering: only the sorted run is the contract
     cap2 = capture(a, b, False)
     assert sorted(map(tuple, cap2["hits"].tolist())) == list(map(tuple, cap["hits"].tolist()))
+
+
+# ---- buildFaceGroups with loops (the part still on the host) ------------------
+
+def _boundary_loops(tri, sel):
+    """Closed vertex cycles along the mesh edges that separate the selected triangles from the rest."""
+    he = {}
+    for t in np.flatnonzero(sel):
+        for k in range(3):
+            he[(int(tri[t, k]), int(tri[t, (k + 1) % 3]))] = t
+    nxt = {u: v for (u, v) in he if (v, u) not in he}
+    loops, seen = [], set()
+    for s in sorted(nxt):
+        if s in seen:
+            continue
+        loop, c = [], s
+        while c not in seen:
+            seen.add(c)
+            loop.append(c)
+            c = nxt[c]
+        loops.append(loop)
+    return loops
+
+
+def _group_cases():
+    from solidboolean_b200 import meshgen
+    for name, (v, t) in {"ico3": meshgen.icosphere(3), "torus": meshgen.torus(24, 12)}.items():
+        cen = v[t].mean(axis=1)
+        for sel_name, sel in {"z>0": cen[:, 2] > 0.0, "x>0.3": cen[:, 0] > 0.3, "caps": np.abs(cen[:, 2]) > 0.2}.items():
+            yield name + ":" + sel_name, t, sel, _boundary_loops(t, sel)
+
+
+def test_face_groups_with_loops_split_where_the_loops_run(oracle):
+    for name, t, sel, loops in _group_cases():
+        r = oracle.uncut_half_edges(t, None, 0, 0)
+        group, order, n = oracle.face_groups(t, r["keys"], r["owner"], loops, 0, len(t))
+        assert n == 2 * len(loops) and len(order) == len(t) and np.all(group != 0xffffffff), name
+        # loop k runs with the selected triangles on its left: they land in the even groups
+        assert np.all((group[sel] % 2) == 0) and np.all((group[~sel] % 2) == 1), name
+        # with a third of the faces missing from the map the flood stops there: leftovers open new groups
+        cut = (np.arange(len(t)) % 3 == 0).astype(np.uint8)
+        rc = oracle.uncut_half_edges(t, cut, 0, 0)
+        tri_new = t[rc["face"]]
+        g2, o2, n2 = oracle.face_groups(tri_new, rc["keys"], rc["owner"], [], 0, len(tri_new))
+        assert n2 == rc["components"] and len(o2) == len(tri_new), name
+        first = {}
+        for tt in o2:
+            first.setdefault(int(g2[tt]), int(tt))
+        assert np.array_equal(np.array([first[int(g)] for g in g2], np.uint32), rc["label"]), name
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built")
+def test_face_groups_with_loops_match_live_reference(oracle):
+    R = Ref.get()
+    for name, t, sel, loops in _group_cases():
+        r = oracle.uncut_half_edges(t, None, 0, 0)
+        for start, count in ((0, len(t)), (0, 0), (len(t) // 2, len(t) // 3)):
+            og, oo, on = oracle.face_groups(t, r["keys"], r["owner"], loops, start, count)
+            rg, ro, rn = R.face_groups(t, r["keys"], r["owner"], loops, start, count)
+            assert on == rn and np.array_equal(og, rg), (name, start, count)
+            # the reference's groups, concatenated = the oracle's assignment order, stably sorted by group
+            assert np.array_equal(oo[np.argsort(og[oo], kind="stable")], ro), (name, start, count)
+        # a map with holes (cut faces) and no loops: leftover groups only
+        cut = (np.arange(len(t)) % 3 == 0).astype(np.uint8)
+        rc = oracle.uncut_half_edges(t, cut, 0, 0)
+        tri_new = t[rc["face"]]
+        og, oo, on = oracle.face_groups(tri_new, rc["keys"], rc["owner"], [], 0, len(tri_new))
+        rg, ro, rn = R.face_groups(tri_new, rc["keys"], rc["owner"], [], 0, len(tri_new))
+        assert on == rn and np.array_equal(og, rg) and np.array_equal(oo[np.argsort(og[oo], kind="stable")], ro), name
