@@ -552,20 +552,32 @@ def run_ours(args):
                                     "H": Href, "P": detail["P"]}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    # release everything that was used on the library's stream while that stream is alive
-    # (torch's pinned-memory allocator records an event on the stream a block was used on)
+    # Orderly teardown, then a NORMAL interpreter exit (exit hooks must run: the driver records the
+    # shared objects this process mapped from one).  Everything that was used on the library's stream
+    # is released while that stream is alive -- torch's caching allocators record events on the stream
+    # a block was used on -- and only then is the context destroyed.
     torch.cuda.synchronize()
     gathered.clear()
     host_hits.clear()
+    xbuf.clear()
     del out_in_a_t, out_in_b_t, flagsA, flagsB, flagsAB, flagsAB32, l2_flush, pin
     ma.close(); mb.close()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    del ext
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    try:
+        torch._C._host_emptyCache()       # pinned-host cache: its blocks remember the library's stream
+    except Exception:
+        pass
+    torch.cuda.synchronize()
+    ctx.close()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)  # skip interpreter teardown: CUDA objects of two runtimes have no defined order there
 
 
 def next_rows(sb, ctx, ma, mb, a, b, with_cpu):
