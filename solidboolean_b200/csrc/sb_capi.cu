@@ -55,6 +55,7 @@ struct DeviceScalars { // device counters of one lane (128-byte slots)
     unsigned int heRepeat;       // ... first refused half-edge insertion (ordinal), UINT_MAX = none
     unsigned int ccCount;        // sb_uncut_components: components
     unsigned int cuts[3];        // sb_isect_contexts: contexts, points, relations
+    unsigned int legacyCount;    // classification: points the balanced kernel left to the general one
 };
 static_assert(sizeof(DeviceScalars) <= 128, "lane slot too small");
 
@@ -102,6 +103,7 @@ struct sb_context {
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
     int sortBeginBit = -1;           // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT); -1 = by mesh size
     uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
+    bool classifyBalanced = true;    // SB_CLASSIFY_V2=0: every launch uses the general kernel (sb_classify.cu)
     bool useGraphs = true;           // SB_GRAPHS=0: rebuilds enqueue their kernels one by one
     size_t grid3EagerBelow = 65536;  // SB_GRID3_EAGER_BELOW: meshes with fewer triangles get their third ray grid right away
                                      // (launch-bound sizes: binning it costs nothing, building it later costs host round trips)
@@ -472,6 +474,8 @@ int sb_context_create(int device, sb_context **out)
         c->grid3EagerBelow = (size_t)std::max(0ll, atoll(e));
     if (const char *e = getenv("SB_CLASSIFY_POOL_LIMIT"))
         c->classifyPoolLimit = (uint32_t)std::max(0, atoi(e));
+    if (const char *e = getenv("SB_CLASSIFY_V2"))
+        c->classifyBalanced = atoi(e) != 0;
     if (const char *e = getenv("SB_GRID_BETA")) {
         float b = (float)atof(e);
         if (b > 0.01f && b < 100.0f)
@@ -1961,7 +1965,7 @@ int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret
 // grids and some points' two votes disagree -- has the third grid built and traces the
 // third ray of just those points in a second launch.
 struct ClassifyJob {
-    void *scratch = nullptr;      // [many-layer keys: 24 * cap][undecided list: 4 * points]
+    void *scratch = nullptr;      // [many-layer keys: 24 * cap][undecided list: 4 * points][legacy list: 4 * points]
     unsigned long long cap = 0;
     uint32_t points = 0;
     int firstAxes = 2;
@@ -1970,7 +1974,23 @@ struct ClassifyJob {
     void *firstScratch = nullptr; // keeps that list alive during the second launch
     size_t firstKeyBytes = 0;     // offset of the list in firstScratch
     uint32_t undecided = 0;
+    bool balanced = false;        // the first launch used the balanced kernel (sb_classify2.cu) ...
+    bool legacyPass = false;      // ... and this is the general kernel's launch over the points it left (same scratch,
+    uint32_t legacy = 0;          //     counters carried on)
+    bool noBalanced = false;      // after a failed legacy pass: everything through the general kernel
 };
+
+// can the balanced kernel take this launch?  (no per-axis big lists on the grids it may trace)
+static bool classify_balanced_ok(const sb_context *c, const sb_mesh *target, const ClassifyArgs &a)
+{
+    if (!c->classifyBalanced || c->classifyPoolLimit || a.list || a.thirdAxisOnly)
+        return false;
+    const int axes = a.perAxis ? 3 : target->d.gridAxes;
+    for (int k = 0; k < axes; ++k)
+        if (target->d.gridBigN[k])
+            return false;
+    return true;
+}
 
 static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a0,
     ClassifyJob &job, unsigned long long forceCap = 0)
@@ -1982,31 +2002,47 @@ static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh 
             return r;
         cudaStreamWaitEvent(lane.stream, target->ready, 0);
     }
-    if (!job.second) {
+    if (!job.second && !job.legacyPass) {
         job.points = a.end - a.begin;
         job.firstAxes = a.perAxis ? 3 : 2; // without the per-axis bits the vote is lazy (third ray on demand)
     }
-    job.cap = forceCap ? forceCap : std::max<unsigned long long>(1 << 16, lane.bigHint + lane.bigHint / 4);
-    const size_t keyBytes = align256(24 * (size_t)job.cap);
-    SB_CUDA(cudaMallocAsync(&job.scratch, keyBytes + 4 * (size_t)std::max<uint32_t>(job.points, 1), lane.stream));
-    SB_CUDA(cudaMemsetAsync(lane.d, 0, sizeof(DeviceScalars), lane.stream));
+    const size_t listBytes = align256(4 * (size_t)std::max<uint32_t>(job.points, 1));
+    if (!job.legacyPass) {
+        job.cap = forceCap ? forceCap : std::max<unsigned long long>(1 << 16, lane.bigHint + lane.bigHint / 4);
+        const size_t keyBytes = align256(24 * (size_t)job.cap);
+        SB_CUDA(cudaMallocAsync(&job.scratch, keyBytes + 2 * listBytes, lane.stream));
+        SB_CUDA(cudaMemsetAsync(lane.d, 0, sizeof(DeviceScalars), lane.stream));
+        if (!job.second)
+            job.firstKeyBytes = keyBytes;
+    }
+    char *const firstBase = static_cast<char *>(job.second ? job.firstScratch : job.scratch);
+    uint32_t *const undecidedList = reinterpret_cast<uint32_t *>(firstBase + job.firstKeyBytes);
+    uint32_t *const legacyList = reinterpret_cast<uint32_t *>(firstBase + job.firstKeyBytes + listBytes);
     if (job.second) {
-        a.list = reinterpret_cast<const uint32_t *>(static_cast<char *>(job.firstScratch) + job.firstKeyBytes);
+        a.list = undecidedList;
         a.listCount = job.undecided;
         a.thirdAxisOnly = true;
     } else {
-        a.undecidedList = reinterpret_cast<uint32_t *>(static_cast<char *>(job.scratch) + keyBytes);
-        job.firstKeyBytes = keyBytes;
+        a.undecidedList = undecidedList;
+        if (job.legacyPass) {
+            a.list = legacyList;
+            a.listCount = job.legacy;
+        }
     }
+    job.balanced = !job.second && !job.legacyPass && !job.noBalanced && classify_balanced_ok(c, target, a);
     unsigned long long *trace = nullptr;
-    const char *traceFile = getenv("SB_CLASSIFY_TRACE"); // dev: per-CTA timeline of every classification launch
-    const uint32_t traceBlocks = sbk_classify_blocks(job.second ? job.undecided : job.points);
+    const char *traceFile = job.balanced ? nullptr : getenv("SB_CLASSIFY_TRACE"); // dev: per-CTA timeline of the general kernel's launches
+    const uint32_t traceBlocks = sbk_classify_blocks(job.second ? job.undecided : job.legacyPass ? job.legacy : job.points);
     if (traceFile)
         SB_CUDA(cudaMalloc(&trace, 32 * (size_t)traceBlocks));
     {
         StageTimer t(c, SB_STAGE_CLASSIFY, lane.stream);
-        SB_CUDA(sbk_classify(lane.stream, target->d, a, static_cast<long long *>(job.scratch), job.cap, &lane.d->stats[1],
-            &lane.d->stats[0], &lane.d->overflowCount, c->classifyPoolLimit, trace, c->lc));
+        if (job.balanced)
+            SB_CUDA(sbk_classify2(lane.stream, target->d, a, &lane.d->stats[0], &lane.d->overflowCount, &lane.d->legacyCount,
+                legacyList, c->lc));
+        else
+            SB_CUDA(sbk_classify(lane.stream, target->d, a, static_cast<long long *>(job.scratch), job.cap, &lane.d->stats[1],
+                &lane.d->stats[0], &lane.d->overflowCount, c->classifyPoolLimit, trace, c->lc));
     }
     if (trace) {
         std::vector<unsigned long long> h(4 * (size_t)traceBlocks);
@@ -2043,10 +2079,23 @@ static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh 
         const uint32_t undecided = lane.h->overflowCount;
         lane.bigHint = std::max(lane.bigHint, needed);
         if (getenv("SB_DEBUG"))
-            fprintf(stderr, "[sb] classify%s: points %u axes %d undecided %u exact candidates %llu big-ray entries %llu (cap %llu) grids %d\n",
-                job.second ? " (third axis)" : "", job.second ? job.undecided : job.points, job.firstAxes, undecided,
-                (unsigned long long)lane.h->stats[0], needed, job.cap, target->d.gridAxes);
-        if (needed > job.cap) { // scratch too small: repeat this launch with the exact size
+            fprintf(stderr, "[sb] classify%s%s: points %u axes %d undecided %u exact candidates %llu big-ray entries %llu (cap %llu) grids %d left to the general kernel %u\n",
+                job.second ? " (third axis)" : job.legacyPass ? " (general kernel over the listed points)" : "",
+                job.balanced ? " [balanced kernel]" : "", job.second ? job.undecided : job.legacyPass ? job.legacy : job.points,
+                job.firstAxes, undecided, (unsigned long long)lane.h->stats[0], needed, job.cap, target->d.gridAxes,
+                lane.h->legacyCount);
+        if (needed > job.cap) { // scratch too small: repeat with the exact size
+            if (job.legacyPass) {
+                // the lists live in the same allocation: start over, everything through the general kernel
+                release();
+                job = ClassifyJob();
+                job.noBalanced = true;
+                attempt = 0;
+                int r = classify_launch(c, lane, target, a, job, needed);
+                if (r)
+                    return r;
+                continue;
+            }
             cudaFreeAsync(job.scratch, lane.stream);
             job.scratch = nullptr;
             if (attempt++) {
@@ -2054,6 +2103,18 @@ static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh 
                 return fail(SB_ERR_CAPACITY, "many-layer ray scratch overflow after retry (%llu > %llu)", needed, job.cap);
             }
             int r = classify_launch(c, lane, target, a, job, needed);
+            if (r) {
+                release();
+                return r;
+            }
+            continue;
+        }
+        if (job.balanced && lane.h->legacyCount) {
+            // points the balanced kernel does not cover (ray box over several cells, more than 32 matches on
+            // a ray): the general kernel classifies them, counters and the undecided list carried on
+            job.legacy = lane.h->legacyCount;
+            job.legacyPass = true;
+            int r = classify_launch(c, lane, target, a, job);
             if (r) {
                 release();
                 return r;
@@ -2069,6 +2130,7 @@ static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh 
                 job.scratch = nullptr;
                 job.undecided = undecided;
                 job.second = true;
+                job.legacyPass = false;
                 attempt = 0;
                 int r = ensure_grid3(target);
                 if (!r) {

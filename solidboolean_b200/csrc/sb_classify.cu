@@ -31,9 +31,7 @@
 // Majority: (float)insideCount / totalCount > 0.5 with totalCount == 3 (:508).
 // A target starts with the grids of axes 0 and 1 only; if a vote needs the third ray
 // and that grid does not exist yet, the points are listed for a second launch (sb_capi.cu).
-#include "sb_internal.h"
-#include "sb_gridq.cuh"
-#include "sb_raytri.cuh"
+#include "sb_classify.cuh"
 
 namespace {
 
@@ -45,12 +43,6 @@ namespace {
 #endif
 #ifndef SB_CLS_UNROLL
 #define SB_CLS_UNROLL 8 // references loaded per scan step (<= 8: allocation padding)
-#endif
-#ifndef SB_CLS_NPREF
-#define SB_CLS_NPREF 0  // normals fetched before the exact box test
-#endif
-#ifndef SB_CLS_RBOX
-#define SB_CLS_RBOX 1   // ray box shortcut for finite points
 #endif
 constexpr int CT = SB_CLS_CT; // threads per CTA
 constexpr int CW = CT / 32;   // warps per CTA
@@ -77,156 +69,6 @@ struct __align__(16) WarpStage {
     uint32_t ray[2][4][32]; // [slot][packed ray x, y, list begin, list end][lane]
 };
 static_assert(KS * 24 <= POOL * 4, "big_ray keeps its keys in the pool");
-
-#define SB_BOX_UPD(b, v)                          \
-    if (v.x > b.hix) b.hix = v.x;                 \
-    if (v.x < b.lox) b.lox = v.x;                 \
-    if (v.y > b.hiy) b.hiy = v.y;                 \
-    if (v.y < b.loy) b.loy = v.y;                 \
-    if (v.z > b.hiz) b.hiz = v.z;                 \
-    if (v.z < b.loz) b.loz = v.z;
-
-__device__ __forceinline__ BoxD ray_box(const d3 &p, const d3 &e)
-{
-    // box.update(testPosition); box.update(testEnd)  (src/solidboolean.cpp:55-58).
-    // For a point with |coordinates| < DBL_MAX the updates leave lo = p and hi = e: the
-    // first one stores p in both (-DBL_MAX < p < DBL_MAX), and e = p + (DBL_MAX or
-    // DBL_EPSILON) >= p (rounding is monotone; +inf compares greater) only ever raises hi.
-#if SB_CLS_RBOX
-    if (fabs(p.x) < DBL_MAX && fabs(p.y) < DBL_MAX && fabs(p.z) < DBL_MAX)
-        return {p.x, p.y, p.z, e.x, e.y, e.z};
-#endif
-    BoxD b = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
-    SB_BOX_UPD(b, p) SB_BOX_UPD(b, e)
-    return b;
-}
-
-__device__ __forceinline__ double comp(const BoxD &b, int d, bool hi)
-{
-    return d == 0 ? (hi ? b.hix : b.lox) : d == 1 ? (hi ? b.hiy : b.loy) : (hi ? b.hiz : b.loz);
-}
-
-struct Target {
-    const GridParams *gp;
-    const uint32_t *E;
-    const uint2 *refs;      // cell lists: 8-byte cell-relative references (sb_gridq.cuh)
-    const uint4 *bigRefs;   // per-axis big lists: 16-byte absolute references
-    uint32_t bigCap;
-    uint32_t bigN0, bigN1, bigN2;
-    int naxes;                 // ray grids the target has (2: the third is built on demand, see ensure_grid3)
-    const double4 *vtx;
-    const uint32_t *tri;
-    const double *normal;
-};
-
-struct Query {
-    const double *pts;         // explicit points (AoS), or null
-    const double *scent;       // faces mode: query mesh centroids in Morton order ...
-    const uint32_t *sortedTri; // ... and sorted position -> triangle id
-    uint32_t nT;
-    uint32_t begin;            // first point / sorted position
-    uint32_t count;            // points in this launch
-    const uint32_t *list;      // optional: the launch's points as indices relative to `begin`
-};
-
-struct Out {
-    uint8_t *inside;           // indexed by point index / original triangle id
-    uint8_t *perAxis;          // optional, 3 per point: all three rays are traced
-    long long *bigKeys;        // scratch of the many-layer rays, 3 x bigCap
-    unsigned long long bigCap;
-    unsigned long long *bigNeeded;  // entries the many-layer rays asked for (> bigCap: repeat)
-    unsigned long long *exactCount; // true candidates (exact box overlap), roofline accounting
-    unsigned int *undecidedCount;   // points whose first two votes disagreed
-    uint32_t *undecidedList;   // ... listed here (relative to `begin`) when the target has no third grid yet
-    int thirdOnly;             // second launch: only the third ray, of the listed points; its vote decides
-    uint32_t poolLimit;        // rays with more matches go through big_ray (<= POOL; smaller only in tests)
-    unsigned long long *trace; // dev: per CTA {sm id, start ns, end ns, entries evaluated} (SB_CLASSIFY_TRACE), or null
-};
-
-struct RaySetup {
-    uint32_t aU, bU, aV, bV, aA; // the ray box, 15-bit quantised: [aU,bU] x [aV,bV] across, from aA along the axis
-    uint32_t cu0, cu1, cv0, cv1; // the cells it touches
-    bool any;                    // the ray box overlaps the mesh box
-};
-
-__device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, const d3 &p)
-{
-    RaySetup rs;
-    const d3 e = ray_end(p, axis);
-    const BoxD myD = ray_box(p, e);
-    const BoxD meshBox = {g.lo[0], g.lo[1], g.lo[2], g.hi[0], g.hi[1], g.hi[2]};
-    rs.any = overlap_d(meshBox, myD); // otherwise no triangle box can overlap the ray box
-    const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
-    rs.aU = quant15(comp(myD, u, false), g.org[u], g.scl[u]);
-    rs.bU = quant15(comp(myD, u, true), g.org[u], g.scl[u]);
-    rs.aV = quant15(comp(myD, v, false), g.org[v], g.scl[v]);
-    rs.bV = quant15(comp(myD, v, true), g.org[v], g.scl[v]);
-    rs.aA = quant15(comp(myD, axis, false), g.org[axis], g.scl[axis]);
-    const int su = g.shiftU[axis], sv = g.shiftV[axis];
-    rs.cu0 = rs.aU >> su; rs.cu1 = rs.bU >> su;
-    rs.cv0 = rs.aV >> sv; rs.cv1 = rs.bV >> sv;
-    return rs;
-}
-
-// the ray as seen from cell (cu, cv): its box clipped to the cell, cell-relative
-__device__ __forceinline__ CellRay ray_in_cell(const GridParams &g, int axis, const RaySetup &rs, uint32_t cu, uint32_t cv)
-{
-    const int su = g.shiftU[axis], sv = g.shiftV[axis];
-    const uint32_t u0 = cu << su, u1 = u0 + (1u << su) - 1u, v0 = cv << sv, v1 = v0 + (1u << sv) - 1u;
-    return cell_ray_pack(max(rs.aU, u0), min(rs.bU, u1), max(rs.aV, v0), min(rs.bV, v1), rs.aA, cu, cv, su, sv);
-}
-
-__device__ __forceinline__ uint32_t big_list_length(const Target &T, int axis)
-{
-    return axis == 0 ? T.bigN0 : axis == 1 ? T.bigN1 : T.bigN2;
-}
-
-// triangle box .intersectWith(ray box) (axisalignedboundingbox.h:95-105) without forming
-// the triangle box: AxisAlignedBoudingBox::update (:31-41) leaves lo = min(DBL_MAX,
-// {c : c < DBL_MAX}) and hi = max(-DBL_MAX, {c : c > -DBL_MAX}) over the vertex
-// coordinates c (NaN never updates), so
-//     lo <= X  <=>  DBL_MAX <= X || c0 <= X || c1 <= X || c2 <= X
-//     hi >= Y  <=>  -DBL_MAX >= Y || c0 >= Y || c1 >= Y || c2 >= Y
-// (a c >= DBL_MAX that satisfies c <= X implies DBL_MAX <= X; mirrored for hi).
-// Bitwise operators: 24 predicate-setting compares, no branches.
-__device__ __forceinline__ bool tri_box_overlaps(const d3 &t0, const d3 &t1, const d3 &t2, const BoxD &rb)
-{
-    return ((DBL_MAX <= rb.hix) | (t0.x <= rb.hix) | (t1.x <= rb.hix) | (t2.x <= rb.hix)) &
-           ((-DBL_MAX >= rb.lox) | (t0.x >= rb.lox) | (t1.x >= rb.lox) | (t2.x >= rb.lox)) &
-           ((DBL_MAX <= rb.hiy) | (t0.y <= rb.hiy) | (t1.y <= rb.hiy) | (t2.y <= rb.hiy)) &
-           ((-DBL_MAX >= rb.loy) | (t0.y >= rb.loy) | (t1.y >= rb.loy) | (t2.y >= rb.loy)) &
-           ((DBL_MAX <= rb.hiz) | (t0.z <= rb.hiz) | (t1.z <= rb.hiz) | (t2.z <= rb.hiz)) &
-           ((-DBL_MAX >= rb.loz) | (t0.z >= rb.loz) | (t1.z >= rb.loz) | (t2.z >= rb.loz));
-}
-
-// One (ray, triangle) entry: is it a candidate of the reference (triangle box
-// .intersectWith(ray box), exact doubles, :55-63), and does the reference insert
-// PositionKey(hit) for it (:66-87)?
-__device__ __forceinline__ bool eval_entry(const Target &T, const d3 &p, int axis, uint32_t f, long long &k0, long long &k1,
-    long long &k2, bool &isCand)
-{
-    const d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
-    const d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
-    const d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
-#if SB_CLS_NPREF
-    // fetched before the box test decides (one round trip less; 98 % of the entries pass)
-    const d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
-#endif
-    const d3 e = ray_end(p, axis);
-    isCand = tri_box_overlaps(t0, t1, t2, ray_box(p, e));
-    if (!isCand)
-        return false;
-#if !SB_CLS_NPREF
-    const d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
-#endif
-    d3 hit = {0, 0, 0};
-    if (!ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit))
-        return false;
-    k0 = position_key(hit.x);
-    k1 = position_key(hit.y);
-    k2 = position_key(hit.z);
-    return true;
-}
 
 // The same as a separately compiled function (its FP64 register pressure stays out of
 // the scan loops): bit 0 = hit, bit 1 = candidate; the keys of a hit go to key3[0..2].
@@ -778,7 +620,7 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     T.vtx = target.vtx;
     T.tri = target.tri;
     T.normal = target.normal;
-    Out o;
+    Out o = {};
     o.inside = a.inside;
     o.perAxis = a.perAxis;
     o.bigKeys = bigKeys;

@@ -151,6 +151,12 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     uint32_t poolLimit /* 0 = default; tests lower it to reach the general path */,
     unsigned long long *trace /* dev: 4 words per CTA, or null */, LaunchCounter &lc);
 uint32_t sbk_classify_blocks(uint32_t points);
+// The balanced single-walk kernel (sb_classify2.cu) for targets without per-axis big lists and
+// launches without a point list: same outputs; points it leaves to the general kernel (a ray box
+// over several cells, more than 32 matches on a ray) are counted in *legacyCount and listed
+// (relative to a.begin) in legacyList, for a second launch of sbk_classify over that list.
+cudaError_t sbk_classify2(cudaStream_t s, const MeshDev &target, const ClassifyArgs &a, unsigned long long *exactCount,
+    unsigned int *undecidedCount, unsigned int *legacyCount, uint32_t *legacyList, LaunchCounter &lc);
 
 size_t sbk_radix_workspace_words(size_t n);
 

@@ -272,12 +272,14 @@ def test_explicit_points_vs_oracle(oracle, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize("layers,pitch", [(24, 0.05), (90, 0.02)])
+@pytest.mark.parametrize("layers,pitch", [(24, 0.05), (90, 0.02), (40, 1e-7), (70, 3e-6)])
 def test_many_layers_hit_list_overflow_path(ctx, oracle, layers, pitch):
     """Rays with more matches than the per-ray staging area take the warp-cooperative
     path: 24 thin slabs stacked along x = 48 crossings for +x rays (keys held in shared
     memory); 90 slabs = 180 crossings (more than 128 distinct keys: global scratch,
-    including the host's exact-size retry)."""
+    including the host's exact-size retry).  40 slabs 1e-7 apart = 80 matches per ray but two distinct
+    PositionKeys, 70 slabs 3e-6 apart = runs of equal keys: the balanced kernel's several-chunk rays
+    (sb_classify2.cu) with their short key list."""
     parts_v, parts_t = [], []
     off = 0
     for i in range(layers):
