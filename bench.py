@@ -84,7 +84,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -133,12 +133,18 @@ class ClockSampler:
 # CPU reference (oracle/_ref = the unmodified reference; else the C port)
 
 def cpu_reference_step(a, b, sample_points, threads):
-    """One bounded pass of the reference front end on the host.  Returns
-    (seconds scaled to the full workload, H, detail dict)."""
+    """One pass of the reference front end on the host: prepare() of both meshes, the broad
+    phase, the predicate loop and isPointInMesh on the face centroids (sample_points = None:
+    ALL of them, nothing extrapolated; a number: that many, spread evenly, and the time scaled).
+    Returns (seconds, H, detail dict); detail["measured_s"] is what the clock saw."""
     from oracle import Oracle, Ref
     nA, nB = len(a[1]), len(b[1])
     Q = nA + nB
+    full = sample_points is None or sample_points >= Q
     rng = np.random.default_rng(0)
+
+    def pick(n, share):
+        return np.arange(n) if full else rng.choice(n, size=min(n, max(1, share)), replace=False)
     if Ref.available():
         R = Ref.get()
         out = [None, None]
@@ -158,20 +164,29 @@ def cpu_reference_step(a, b, sample_points, threads):
         ret, cop, hit, seg, ms_pred = op.predicate(pairs)
         t_pred = ms_pred / 1e3
         H = int(hit.sum())
-        # classification on a bounded sample of the face centroids, spread over host threads
+        # isPointInMesh on the face centroids (3 axes each), spread over the host threads
         ca, cb = ma.centroids(), mb.centroids()
-        sa = rng.choice(nA, size=min(nA, sample_points * nA // Q), replace=False)
-        sb_ = rng.choice(nB, size=min(nB, sample_points * nB // Q), replace=False)
+        sa = pick(nA, (sample_points or 0) * nA // Q)
+        sb_ = pick(nB, (sample_points or 0) * nB // Q)
         jobs = [(1, chunk) for chunk in np.array_split(ca[sa], threads)] + \
                [(0, chunk) for chunk in np.array_split(cb[sb_], threads)]
+        inside = [0, 0]
+        parts = [[None] * threads, [None] * threads]   # per-face flags, chunk by chunk (full runs: compared with the GPU's)
+
+        def work(k, j):
+            flags = op.classify(j[0], j[1])[0]
+            parts[1 - j[0]][k % threads] = flags
         t0 = time.perf_counter()
-        ws = [threading.Thread(target=lambda j=j: op.classify(j[0], j[1])) for j in jobs if len(j[1])]
+        ws = [threading.Thread(target=work, args=(k, j)) for k, j in enumerate(jobs) if len(j[1])]
         for i in range(0, len(ws), threads):
             [w.start() for w in ws[i:i + threads]]
             [w.join() for w in ws[i:i + threads]]
         t_cls_sample = time.perf_counter() - t0
         n_sample = len(sa) + len(sb_)
         kind = "reference"
+        flags_ab = [np.concatenate([x for x in parts[k] if x is not None]) if any(x is not None for x in parts[k])
+                    else np.zeros(0, np.uint8) for k in (0, 1)]
+        inside = [int(flags_ab[0].sum()), int(flags_ab[1].sum())]
         op.close(); ma.close(); mb.close()
     else:
         O = Oracle.get()
@@ -186,18 +201,34 @@ def cpu_reference_step(a, b, sample_points, threads):
         t_pred = time.perf_counter() - t0
         H = int(hit.sum())
         ca, cb = O.centroids(*a), O.centroids(*b)
-        sa = rng.choice(nA, size=min(nA, sample_points * nA // Q), replace=False)
-        sb_ = rng.choice(nB, size=min(nB, sample_points * nB // Q), replace=False)
+        sa = pick(nA, (sample_points or 0) * nA // Q)
+        sb_ = pick(nB, (sample_points or 0) * nB // Q)
+        jobs = [(b, 0, chunk) for chunk in np.array_split(ca[sa], threads)] + \
+               [(a, 1, chunk) for chunk in np.array_split(cb[sb_], threads)]
+        parts = [[None] * threads, [None] * threads]
+
+        def work(k, j):
+            parts[j[1]][k % threads] = O.classify(j[0], j[2])[0]
         t0 = time.perf_counter()
-        O.classify(b, ca[sa]); O.classify(a, cb[sb_])
+        ws = [threading.Thread(target=work, args=(k, j)) for k, j in enumerate(jobs) if len(j[2])]
+        for i in range(0, len(ws), threads):
+            [w.start() for w in ws[i:i + threads]]
+            [w.join() for w in ws[i:i + threads]]
         t_cls_sample = time.perf_counter() - t0
         n_sample = len(sa) + len(sb_)
         kind = "port"
+        flags_ab = [np.concatenate([x for x in parts[k] if x is not None]) if any(x is not None for x in parts[k])
+                    else np.zeros(0, np.uint8) for k in (0, 1)]
+        inside = [int(flags_ab[0].sum()), int(flags_ab[1].sum())]
     t_cls = t_cls_sample * (Q / max(n_sample, 1))
+    measured = t_prepare + t_search + t_pred + t_cls_sample
     total = t_prepare + t_search + t_pred + t_cls
     detail = dict(kind=kind, prepare_s=t_prepare, search_s=t_search, predicate_s=t_pred,
-                  classify_sample_s=t_cls_sample, classify_scaled_s=t_cls, sample_points=n_sample, H=H,
-                  P=int(len(pairs)))
+                  classify_measured_s=t_cls_sample, classify_points=n_sample, classify_points_total=Q,
+                  extrapolated_s=total - measured, measured_s=measured, H=H, P=int(len(pairs)),
+                  inside_a=inside[0] if full else None, inside_b=inside[1] if full else None)
+    detail["_flags"] = flags_ab if full else None        # numpy arrays, for the caller's comparison (never serialised)
+    detail["_hits"] = (pairs[hit.astype(bool)], seg[hit.astype(bool)])
     return total, H, detail
 
 
@@ -209,8 +240,19 @@ def host_threads():
 
 
 def sample_description(detail, threads):
-    return ("full prepare() x2 (2 threads) + full broad phase + full predicate loop; isPointInMesh on %d of the "
-            "face centroids x 3 axes over %d threads, scaled to all faces" % (detail["sample_points"], threads))
+    if detail["classify_points"] >= detail["classify_points_total"]:
+        return ("the whole workload, nothing extrapolated: prepare() x2 (2 threads) + broad phase + predicate loop + "
+                "isPointInMesh on all %d face centroids x 3 axes over %d threads" % (detail["classify_points_total"], threads))
+    return ("full prepare() x2 (2 threads) + full broad phase + full predicate loop; isPointInMesh on %d of the %d "
+            "face centroids x 3 axes over %d threads, scaled to all faces" % (detail["classify_points"],
+                                                                            detail["classify_points_total"], threads))
+
+
+def config_dict(desc, name, nA, nB):
+    """The same `config` object in both arms (the driver compares them)."""
+    return {"workload": desc, "name": name, "tris_a": int(nA), "tris_b": int(nB),
+            "l2": "512 MiB buffer written between timed steps (L2 flush)",
+            "parallelism": "A-range + query shards over the ranks, acceleration structures replicated"}
 
 
 def run_reference(args):
@@ -219,10 +261,9 @@ def run_reference(args):
         return
     a, b, desc = workload(args.config)
     threads = host_threads()
-    sample = 65536
     times, H, detail = [], 0, None
     for i in range(args.warmup + args.steps):
-        t, H, detail = cpu_reference_step(a, b, sample, threads)
+        t, H, detail = cpu_reference_step(a, b, None, threads)   # every step is the whole workload, measured
         if i >= args.warmup:
             times.append(t)
     sec = float(np.mean(times))
@@ -231,11 +272,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "name": args.config, "tris_a": int(len(a[1])), "tris_b": int(len(b[1]))},
+        "config": config_dict(desc, args.config, len(a[1]), len(b[1])),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": detail["kind"],
                          "sample": sample_description(detail, threads)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "front_end_ms": sec * 1e3, "detail": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in detail.items()},
+        "front_end_ms": sec * 1e3, "detail": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in detail.items() if not k.startswith("_")},
     }
     print(json.dumps(line), flush=True)
 
@@ -480,7 +521,9 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         # classification bytes = 25 Q + 104 nTarget + 108 C, both launches of a step
-        cls_bytes = 25 * (nA + nB) + 104 * (nA + nB) + 108 * cands_total
+        # (N > 1: per GPU -- rank 0's own query shard and candidates against its own kernel time and ONE GPU's peak)
+        q_local = (a1 - a0) + (b1 - b0)
+        cls_bytes = 25 * q_local + 104 * (nA + nB) + 108 * (cands if world > 1 else cands_total)
         cls_ms = stage_ms["classify"]
         traffic = None
         try:  # DRAM bytes of the classification kernels of one step, from the committed ncu --set full capture
@@ -500,9 +543,7 @@ def run_ours(args):
             "metric": METRIC, "value": H / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "name": args.config, "tris_a": nA, "tris_b": nB,
-                       "l2": "512 MiB buffer written between timed steps (L2 flush)",
-                       "parallelism": "A-range + query shards x%d, LBVHs replicated" % world},
+            "config": config_dict(desc, args.config, nA, nB),
             "front_end_ms": ms_step,
             "candidate_pairs": P, "intersecting_pairs": H, "inside_a": insideA, "inside_b": insideB,
             "candidate_pairs_per_s": P / (ms_step * 1e-3),
@@ -512,7 +553,7 @@ def run_ours(args):
             **({"stage_ms_by_rank": stage_by_rank} if stage_by_rank else {}),
             "stage_gbs_algorithmic": {"build": gbs(build_bytes, stage_ms["build"]), "broad": gbs(broad_bytes, stage_ms["broad"]),
                                       "narrow": gbs(narrow_bytes, stage_ms["narrow"]), "classify": gbs(cls_bytes, cls_ms)},
-            "roofline": {"bound": "hbm", "kernel": "classification: classify_kernel, both directions (2 launches/step)", "achieved": round(achieved, 1),
+            "roofline": {"bound": "hbm", "kernel": "classification: classify2_kernel, both directions (2 launches/step)" + (", rank 0's shard" if world > 1 else ""), "achieved": round(achieved, 1),
                          "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": cls_bytes,
                          "kernel_ms_per_step": round(cls_ms, 4)},
@@ -546,10 +587,27 @@ def run_ours(args):
                 line["next_rows"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            sec, Href, detail = cpu_reference_step(a, b, 32768, threads)
+            sec, Href, detail = cpu_reference_step(a, b, None, threads)
             line["cpu_baseline"] = {"value": Href / sec, "unit": UNIT, "cores": threads, "kind": detail["kind"],
                                     "sample": sample_description(detail, threads), "front_end_ms": sec * 1e3,
-                                    "H": Href, "P": detail["P"]}
+                                    "measured_ms": detail["measured_s"] * 1e3, "extrapolated_ms": detail["extrapolated_s"] * 1e3,
+                                    "H": Href, "P": detail["P"], "inside_a": detail["inside_a"], "inside_b": detail["inside_b"]}
+            # the whole workload was run on the CPU: compare everything the e2e step brought back with it
+            try:
+                fa, fb = detail["_flags"]
+                rab, rseg = detail["_hits"]
+                order = np.lexsort((rab[:, 1], rab[:, 0]))
+                gab = host_hits["ab"][:2 * H2].numpy().reshape(-1, 2).astype(np.uint32)
+                gseg = host_hits["seg"][:6 * H2].numpy().reshape(-1, 6)
+                line["parity_vs_cpu"] = {
+                    "what": "results of the last host-buffer step against the CPU baseline run above (all faces, all pairs)",
+                    "candidate_pairs_equal": bool(P2 == detail["P"]),
+                    "hit_pairs_identical": bool(np.array_equal(gab, rab[order].astype(np.uint32))),
+                    "segments_bit_identical": bool(gseg.tobytes() == np.ascontiguousarray(rseg[order]).tobytes()),
+                    "flags_a_identical": bool(np.array_equal(out_in_a_t.numpy(), fa)),
+                    "flags_b_identical": bool(np.array_equal(out_in_b_t.numpy(), fb))}
+            except Exception as e:
+                line["parity_vs_cpu"] = {"error": str(e)}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     # Orderly teardown, then a NORMAL interpreter exit (exit hooks must run: the driver records the
