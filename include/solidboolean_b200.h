@@ -258,6 +258,29 @@ int sb_classify_faces(const sb_mesh *query, const sb_mesh *target,
 int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target,
                              size_t begin, size_t end, void *d_inside);
 
+/* ---- batches of small booleans (BASELINE configs[4]: 1,000 x 5K-triangle jobs; SURVEY 8e "C5") --------
+ * The reference runs one SolidBoolean per call (test/main.cpp:92-103); a 5K-triangle mesh cannot fill a
+ * B200.  A BATCH MESH holds the meshes of n_jobs independent jobs end to end and goes through the same
+ * entry points as a single mesh -- sb_mesh_build, sb_intersect, sb_classify_faces(_device), sb_front_end:
+ * ONE sort, ONE leaf / grid build, ONE front-end launch sequence for all jobs.  Job j of batch A only ever
+ * meets job j of batch B.  The jobs may (and usually do) overlap in space: inside the library the job
+ * number leads the Morton key and moves the conservative float boxes / quantised grid coordinates onto a
+ * 32 x 32 x 32 lattice; every exact test reads the real coordinates, so results are those of n_jobs
+ * separate calls.
+ *   xyz            AoS vertices of all jobs, job after job; vertex_start[n_jobs + 1] (first entry 0)
+ *   tri            index triples of all jobs, JOB-LOCAL vertex indices; triangle_start[n_jobs + 1]
+ *   lattice_pitch  >= 4 x the largest |coordinate| over BOTH batches of a pair (a power of two is a
+ *                  good choice); both batches must be made with the same value.  Checked at build time.
+ * Results are batch-global: triangle a of job j has index triangle_start[j] + a in hit / candidate pairs
+ * and in the per-face flag arrays.  sb_batch_job_ranges splits the (sorted) hit list by job.
+ * At most 1024 jobs per batch; explicit-point classification (sb_classify) is not offered for batches. */
+int sb_batch_upload(sb_context *ctx, size_t n_jobs, const double *xyz, const size_t *vertex_start,
+                    const uint32_t *tri, const size_t *triangle_start, double lattice_pitch, sb_mesh **out);
+int sb_batch_info(const sb_mesh *m, size_t *n_jobs, size_t *vertex_start /* n_jobs + 1, or NULL */,
+                  size_t *triangle_start /* n_jobs + 1, or NULL */);
+/* hits of job j = entries [hit_start[j], hit_start[j + 1]) of sb_isect_hits; hit_start holds n_jobs + 1 */
+int sb_batch_job_ranges(const sb_isect *x, size_t *hit_start);
+
 /* ---- the whole front end of one boolean in one call ------------------------------
  * sb_intersect(A, B) on the context stream, overlapped with the classification of
  * A's faces against B and of B's faces against A on two internal streams (what

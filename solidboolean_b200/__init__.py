@@ -51,6 +51,9 @@ ABI = {
     "sb_context_device": (C.c_int, [_vp]),
     "sb_mesh_create": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_vp)]),
     "sb_mesh_upload": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_vp)]),
+    "sb_batch_upload": (C.c_int, [_vp, _sz, _vp, _vp, _vp, _vp, C.c_double, C.POINTER(_vp)]),
+    "sb_batch_info": (C.c_int, [_vp, C.POINTER(_sz), _vp, _vp]),
+    "sb_batch_job_ranges": (C.c_int, [_vp, _vp]),
     "sb_mesh_build": (C.c_int, [_vp]),
     "sb_mesh_destroy": (None, [_vp]),
     "sb_mesh_num_triangles": (_sz, [_vp]),
@@ -224,6 +227,36 @@ class Mesh:
         self.h = h
         return self
 
+    @classmethod
+    def batch(cls, ctx: Context, jobs, lattice_pitch: float, build=True):
+        """sb_batch_upload: `jobs` = sequence of (xyz, tri) small meshes (job-local indices), laid end to
+        end into ONE batch mesh.  lattice_pitch >= 4 x the largest |coordinate| of both batches of a pair
+        (`batch_pitch` computes it)."""
+        xs = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3) for x, _ in jobs]
+        ts = [np.ascontiguousarray(t, dtype=np.uint32).reshape(-1, 3) for _, t in jobs]
+        return cls.batch_arrays(ctx, np.concatenate(xs) if xs else np.zeros((0, 3)),
+                                np.concatenate([[0], np.cumsum([len(x) for x in xs])]),
+                                np.concatenate(ts) if ts else np.zeros((0, 3), np.uint32),
+                                np.concatenate([[0], np.cumsum([len(t) for t in ts])]), lattice_pitch, build)
+
+    @classmethod
+    def batch_arrays(cls, ctx: Context, xyz, vertex_start, tri, triangle_start, lattice_pitch: float, build=True):
+        """The same from already concatenated arrays (+ their n_jobs + 1 start offsets)."""
+        self = cls.__new__(cls)
+        self.ctx, self.lib = ctx, ctx.lib
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        self.tri = np.ascontiguousarray(tri, dtype=np.uint32).reshape(-1, 3)
+        self.vertex_start = np.ascontiguousarray(vertex_start, dtype=np.uint64)
+        self.triangle_start = np.ascontiguousarray(triangle_start, dtype=np.uint64)
+        h = _vp()
+        _check(self.lib.sb_batch_upload(ctx.h, len(self.vertex_start) - 1, _ptr(self.xyz), _ptr(self.vertex_start),
+                                        _ptr(self.tri), _ptr(self.triangle_start), float(lattice_pitch), C.byref(h)))
+        self.h = h
+        if build:
+            self.build()
+            ctx.synchronize()
+        return self
+
     def build(self):
         _check(self.lib.sb_mesh_build(self.h))
 
@@ -325,6 +358,17 @@ class Mesh:
         _check(self.lib.sb_classify_faces_device(self.h, target.h, begin, end, _vp(d_inside_ptr)))
 
 
+def batch_pitch(*arrays) -> float:
+    """A lattice pitch for sb_batch_upload: the power of two >= 4 x the largest |coordinate| of the given arrays."""
+    m = max((float(np.abs(a).max()) for a in arrays if np.size(a)), default=1.0)
+    p = 1.0
+    while p < 4.0 * m:
+        p *= 2.0
+    while p * 0.5 >= 4.0 * m and p > 1e-300:
+        p *= 0.5
+    return p
+
+
 class Isect:
     """Candidate pairs + intersecting pairs of two meshes (sb_isect)."""
 
@@ -379,6 +423,14 @@ class Isect:
         seg = np.zeros((self.num_hits, 6), np.float64)
         _check(self.lib.sb_isect_hits(self.h, _ptr(ab), _ptr(seg)))
         return ab, seg
+
+    def job_ranges(self):
+        """Batch meshes: hits of job j = rows [r[j], r[j + 1]) of hits() (sb_batch_job_ranges)."""
+        n = _sz(0)
+        _check(self.lib.sb_batch_info(self.a.h, C.byref(n), None, None))
+        out = np.zeros(n.value + 1, np.uint64)
+        _check(self.lib.sb_batch_job_ranges(self.h, _ptr(out)))
+        return out.astype(np.int64)
 
     def path_counts(self):
         """Predicate exit histogram: plane2 reject, plane1 reject, coplanar, interval reject, segment."""

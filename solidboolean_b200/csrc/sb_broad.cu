@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
         BoxF o = shfl_xor_box(all, off);
         merge_f(all, o);
     }
-    {
+    if (boundsB) { // (batch meshes: the float boxes live on the job lattice, the bounds do not)
         const BoxD bb = {dkey_inv(__ldg(boundsB)), dkey_inv(__ldg(boundsB + 1)), dkey_inv(__ldg(boundsB + 2)),
                          dkey_inv(__ldg(boundsB + 3)), dkey_inv(__ldg(boundsB + 4)), dkey_inv(__ldg(boundsB + 5))};
         const BoxF bf = enclose(bb); // conservative: rounded outwards
@@ -114,7 +114,7 @@ cudaError_t sbk_broad_phase(cudaStream_t s, const MeshDev &A, const MeshDev &B, 
     uint32_t groups = groupEnd - groupBegin;
     uint32_t blocks = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     broad_phase_kernel<<<blocks, WARPS_PER_CTA * 32, 0, s>>>(A.leaf, A.sbox, groupBegin, groupEnd, B.nodes, B.leaf, B.sbox,
-        B.root, B.bounds, bitsB, outKeys, capacity, outCount);
+        B.root, B.triJob ? nullptr : B.bounds, bitsB, outKeys, capacity, outCount);
     lc.kernels += 1;
     return cudaGetLastError();
 }

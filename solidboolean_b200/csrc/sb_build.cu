@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double *__restrict__ normal,
     uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
-    unsigned long long *__restrict__ extentSum)
+    unsigned long long *__restrict__ extentSum, const uint16_t *__restrict__ triJob)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // this triangle's box extents as 2^-24 fractions of the mesh extent (integers:
@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     uint32_t qx = quant10(0.5 * (bx.lox + bx.hix), blx, ix);
     uint32_t qy = quant10(0.5 * (bx.loy + bx.hiy), bly, iy);
     uint32_t qz = quant10(0.5 * (bx.loz + bx.hiz), blz, iz);
-    mkey[i] = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
+    const uint32_t morton = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
+    // batch mesh: the job leads the key (12 bits), 20 Morton bits follow -- every job is one run of the order
+    mkey[i] = triJob ? ((uint32_t)triJob[i] << 20) | (morton >> 10) : morton;
     order[i] = i;
     sx = (unsigned int)fmin(fmax((bx.hix - bx.lox) * ix * 16777216.0, 0.0), 16777216.0); // NaN -> 0
     sy = (unsigned int)fmin(fmax((bx.hiy - bx.loy) * iy * 16777216.0, 0.0), 16777216.0);
@@ -172,7 +174,8 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
     const uint32_t *__restrict__ sortedKey, const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, uint32_t nTpad, Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, double *__restrict__ scent,
     Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey, const GridParams *__restrict__ gp, uint4 *__restrict__ qbox,
-    uint32_t *__restrict__ gridE, uint32_t *__restrict__ gridBigCount, int gridAxes)
+    uint32_t *__restrict__ gridE, uint32_t *__restrict__ gridBigCount, int gridAxes, const uint16_t *__restrict__ triJob,
+    double latPitch)
 {
     __shared__ GridParams g;
     if (threadIdx.x < sizeof(GridParams) / 4)
@@ -192,6 +195,15 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
         const d3 a = load_vertex(vtx, i0), b = load_vertex(vtx, i1), c = load_vertex(vtx, i2);
         bd = tri_box(a, b, c); // exact box (reference `update` semantics), Morton order
         bf = enclose(bd);
+        uint32_t job = 0;
+        if (triJob) {
+            // batch mesh: the conservative float box moves to the job's lattice position (rounded outwards
+            // after the shift); only these floats are moved, the exact box below stays where it is
+            job = triJob[t];
+            const double ox = latPitch * lattice3(job, 0), oy = latPitch * lattice3(job, 1), oz = latPitch * lattice3(job, 2);
+            bf = {__double2float_rd(bd.lox + ox), __double2float_rd(bd.loy + oy), __double2float_rd(bd.loz + oz),
+                  __double2float_ru(bd.hix + ox), __double2float_ru(bd.hiy + oy), __double2float_ru(bd.hiz + oz)};
+        }
         ref = (int)t;
         // face centroid exactly as decideGroupSide forms its query point:
         // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
         scent[3 * (size_t)j + 1] = xdiv(xadd(xadd(a.y, b.y), c.y), 3.0);
         scent[3 * (size_t)j + 2] = xdiv(xadd(xadd(a.z, b.z), c.z), 3.0);
         // ray grids (sb_grid.cu): the quantised box, and the count pass while it is in registers
-        const uint4 q = quantise_box(bd, g, t);
+        const uint4 q = quantise_box(bd, g, t, job);
         qbox[j] = q;
         grid_count_tri(q, g, gridE, gridBigCount, gridAxes);
     }
@@ -289,7 +301,44 @@ __global__ void __launch_bounds__(256) tri_boxes_kernel(const double4 *__restric
     store_boxd(out + 3 * (size_t)i, tri_box(load_vertex(vtx, i0), load_vertex(vtx, i1), load_vertex(vtx, i2)));
 }
 
+// batch upload: job-local vertex indices -> batch-global ones, job of every triangle
+__global__ void __launch_bounds__(256) batch_fixup_kernel(uint32_t *__restrict__ tri, uint32_t nT,
+    const uint32_t *__restrict__ triStart, const uint32_t *__restrict__ vtxStart, uint32_t nJobs, uint16_t *__restrict__ triJob,
+    int *__restrict__ err)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nT)
+        return;
+    uint32_t lo = 0, hi = nJobs; // last job whose first triangle is <= t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(triStart + mid) <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const uint32_t v0 = __ldg(vtxStart + lo), nv = __ldg(vtxStart + lo + 1) - v0;
+    triJob[t] = (uint16_t)lo;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint32_t i = tri[3 * (size_t)t + k];
+        if (i >= nv) { // reported as SB_ERR_INVALID by the first build
+            *err = 1;
+            i = 0;
+        }
+        tri[3 * (size_t)t + k] = v0 + i;
+    }
+}
+
 } // namespace
+
+cudaError_t sbk_batch_fixup(cudaStream_t s, uint32_t *tri, uint32_t nT, const uint32_t *triStart, const uint32_t *vtxStart,
+    uint32_t nJobs, uint16_t *triJob, int *err, LaunchCounter &lc)
+{
+    batch_fixup_kernel<<<(nT + 255) / 256, 256, 0, s>>>(tri, nT, triStart, vtxStart, nJobs, triJob, err);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
 
 cudaError_t sbk_triangle_boxes(cudaStream_t s, const MeshDev &m, double2 *out, LaunchCounter &lc)
 {
@@ -317,12 +366,12 @@ cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int sm
         vb = 1;
     bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds);
     tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.normal, m.mkey, m.order, m.err,
-        m.extentSum);
+        m.extentSum, m.triJob);
     lc.kernels += 2;
     sbradix::Workspace ws;
     ws.mem = radixWs;
     uint32_t *sk = nullptr, *sv = nullptr;
-    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, 30, ws, smCount, &sk, &sv);
+    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, m.triJob ? 32 : 30, ws, smCount, &sk, &sv);
     m.sortedKey = sk;
     m.sortedTri = sv;
     return cudaGetLastError();
@@ -333,7 +382,7 @@ cudaError_t sbk_build_leaves(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
     if (m.nT == 0)
         return cudaSuccess;
     leaf_gather_kernel<<<(m.nTpad + 255) / 256, 256, 0, s>>>(m.sortedTri, m.sortedKey, m.vtx, m.tri, m.nT, m.nV, m.nTpad,
-        m.leaf, m.sbox, m.scent, m.cbox, m.ckey, m.gridParams, m.qbox, m.gridE, m.gridBigCount, m.gridAxes);
+        m.leaf, m.sbox, m.scent, m.cbox, m.ckey, m.gridParams, m.qbox, m.gridE, m.gridBigCount, m.gridAxes, m.triJob, m.latPitch);
     lc.kernels += 1;
     return cudaGetLastError();
 }

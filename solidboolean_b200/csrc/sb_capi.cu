@@ -43,6 +43,8 @@ unsigned bits_for(size_t n)
     return b;
 }
 
+constexpr size_t SB_BATCH_MAX_JOBS_HOST = 1024; // = SB_BATCH_MAX_JOBS of sb_gridq.cuh (the 32 x 32 job lattice)
+
 struct DeviceScalars { // device counters of one lane (128-byte slots)
     unsigned long long pairCount;
     unsigned long long stats[2];
@@ -139,6 +141,8 @@ struct sb_mesh {
     cudaGraphExec_t gridGraph = nullptr;   // {grid scan -> fill} beside {LBVH}
     unsigned graphSig = 0;           // what the capture depended on: grids, LBVH wanted, sorted bits
     uint64_t graphKernels = 0;       // kernels in the graph (launch accounting)
+    std::vector<uint32_t> jobTriStart, jobVtxStart; // batch mesh (sb_batch_upload): n_jobs + 1 each, else empty
+    uint32_t *dJobStart = nullptr;   // ... and their device copy: [triangle starts][vertex starts] (in the arena)
     bool treeBuilt = false;          // LBVH topology built (lazily, on first use as a traversal target)
     bool treeWanted = false;         // the mesh has been a traversal target: rebuilds include the LBVH
 };
@@ -323,7 +327,7 @@ int alloc_async(sb_context *c, T **p, size_t count, std::vector<void *> *owned)
     return SB_OK;
 }
 
-int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
+int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJobs = 0)
 {
     if (nV >= (1ull << 31) || nT >= (1ull << SB_MAX_TRIANGLE_BITS))
         return fail(SB_ERR_INVALID, "mesh too large: %zu vertices, %zu triangles", nV, nT);
@@ -355,8 +359,11 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
         // actual resolution from the mean triangle extent, sb_grid.cu)
         double lg = nT ? std::log2((double)nT) + 1.0 : 0.0;
         int bits = (int)std::floor(lg + 0.5);
+        if (nJobs) // batch mesh: every job has its own block of cells on the 32 x 32 lattice, most of them sparsely used
+            bits = std::max(bits + 2, 12);
         d.gridCellBits = (uint32_t)std::max(0, std::min(bits, 26));
     }
+    size_t oTriJob = take(nJobs ? 2 * nT : 0), oJobStart = take(nJobs ? 8 * (nJobs + 1) : 0);
     size_t oRadix = take(4 * sbk_radix_workspace_words(nT));
     size_t oScan = take(4 * sbk_grid_scan_status_words(3u << d.gridCellBits));
     size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32 + 96 * 8);
@@ -391,6 +398,11 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out)
     d.gridE = (uint32_t *)(b + oGridE);
     d.gridBigCount = (uint32_t *)(b + oGridBig);
     d.extentSum = (unsigned long long *)(d.gridBigCount + 8);
+    if (nJobs) {
+        d.triJob = (const uint16_t *)(b + oTriJob);
+        d.nJobs = (uint32_t)nJobs;
+        m->dJobStart = (uint32_t *)(b + oJobStart);
+    }
     m->radixWs = (uint32_t *)(b + oRadix);
     m->scanScratch = (uint32_t *)(b + oScan);
     // builds are on the critical path of everything that follows: highest priority, so
@@ -655,6 +667,93 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
     return SB_OK;
 }
 
+// ---- batch meshes ---------------------------------------------------------------------
+int sb_batch_upload(sb_context *ctx, size_t n_jobs, const double *xyz, const size_t *vertex_start, const uint32_t *tri,
+    const size_t *triangle_start, double lattice_pitch, sb_mesh **out)
+{
+    if (!ctx || !out)
+        return fail(SB_ERR_INVALID, "null context or out");
+    *out = nullptr;
+    if (!n_jobs || n_jobs > SB_BATCH_MAX_JOBS_HOST)
+        return fail(SB_ERR_INVALID, "a batch holds 1 .. %u jobs", (unsigned)SB_BATCH_MAX_JOBS_HOST);
+    if (!vertex_start || !triangle_start || vertex_start[0] || triangle_start[0])
+        return fail(SB_ERR_INVALID, "job start arrays must begin with 0");
+    for (size_t j = 0; j < n_jobs; ++j)
+        if (vertex_start[j + 1] < vertex_start[j] || triangle_start[j + 1] < triangle_start[j])
+            return fail(SB_ERR_INVALID, "job start arrays must not decrease (job %zu)", j);
+    const size_t nV = vertex_start[n_jobs], nT = triangle_start[n_jobs];
+    if ((nV && !xyz) || (nT && !tri))
+        return fail(SB_ERR_INVALID, "null geometry pointer");
+    if (nT && !nV)
+        return fail(SB_ERR_INVALID, "triangles without vertices");
+    if (!(lattice_pitch > 0.0) || !(lattice_pitch < 1.0e30))
+        return fail(SB_ERR_INVALID, "lattice_pitch must be a positive number (>= 4 x the largest |coordinate| of both batches)");
+    DeviceGuard g(ctx->device);
+    sb_mesh *m = nullptr;
+    int r = mesh_alloc(ctx, nV, nT, &m, n_jobs);
+    if (r)
+        return r;
+    m->d.latPitch = lattice_pitch;
+    m->jobTriStart.resize(n_jobs + 1);
+    m->jobVtxStart.resize(n_jobs + 1);
+    for (size_t j = 0; j <= n_jobs; ++j) {
+        m->jobTriStart[j] = (uint32_t)triangle_start[j];
+        m->jobVtxStart[j] = (uint32_t)vertex_start[j];
+    }
+    cudaError_t e = cudaSuccess;
+    if (nV)
+        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess && nT)
+        e = cudaMemcpyAsync(m->d.tri, tri, 12 * nT, cudaMemcpyHostToDevice, m->stream);
+    // (the vectors outlive the copies: the stream is synchronised before the mesh can be destroyed)
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(m->dJobStart, m->jobTriStart.data(), 4 * (n_jobs + 1), cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(m->dJobStart + n_jobs + 1, m->jobVtxStart.data(), 4 * (n_jobs + 1), cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(m->d.root, 0, 8, m->stream); // clears the error flag the fix-up may raise
+    if (e == cudaSuccess && nT)
+        e = sbk_batch_fixup(m->stream, m->d.tri, (uint32_t)nT, m->dJobStart, m->dJobStart + n_jobs + 1, (uint32_t)n_jobs,
+            const_cast<uint16_t *>(m->d.triJob), m->d.err, ctx->lc);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(m->ready, m->stream);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(m->leafReady, m->stream);
+    if (e != cudaSuccess) {
+        sb_mesh_destroy(m);
+        return fail(SB_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return SB_OK;
+}
+
+int sb_batch_info(const sb_mesh *m, size_t *n_jobs, size_t *vertex_start, size_t *triangle_start)
+{
+    if (!m)
+        return fail(SB_ERR_INVALID, "mesh is null");
+    const size_t J = m->d.nJobs;
+    if (n_jobs)
+        *n_jobs = J;
+    for (size_t j = 0; J && j <= J; ++j) {
+        if (vertex_start)
+            vertex_start[j] = m->jobVtxStart[j];
+        if (triangle_start)
+            triangle_start[j] = m->jobTriStart[j];
+    }
+    return SB_OK;
+}
+
+// device error flag of a build -> message (bit 0: index check; bit 1: batch lattice pitch)
+static int mesh_error(const sb_mesh *m, int err)
+{
+    if (err & 2)
+        return fail(SB_ERR_INVALID, "lattice_pitch %g is too small: it must be at least 4 x the largest |coordinate| of the batch",
+            m->d.latPitch);
+    if (m->d.triJob)
+        return fail(SB_ERR_INVALID, "triangle index out of range (>= the vertex count of its job)");
+    return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
+}
+
 // First build (or first build with a third grid): the reference list is sized from the
 // counts (16-byte read-back on the mesh's stream), then filled.
 static int grid_counts_readback(sb_mesh *m)
@@ -680,7 +779,7 @@ static int grid_size_and_fill(sb_mesh *m, bool readback = true)
     int *hErr = reinterpret_cast<int *>(m->hErr);
     SB_CUDA(cudaStreamSynchronize(st));
     if (*hErr)
-        return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
+        return mesh_error(m, *hErr);
     size_t nRefs = h[0];
     uint32_t bigMax = std::max(h[1], std::max(h[2], h[3]));
     for (int k = 0; k < 3; ++k)
@@ -766,6 +865,8 @@ int sb_mesh_build(sb_mesh *m)
     m->gridPending = false; // an unfinished first build is simply redone
     if (c->sortBeginBit >= 0) {
         m->d.sortBeginBit = c->sortBeginBit;
+    } else if (m->d.triJob) {
+        m->d.sortBeginBit = 8; // batch: 12 job bits + the 12 leading Morton bits = three passes
     } else {
         // The order only has to be spatially coherent: 8 or more Morton cells per triangle are
         // plenty (ties keep their input order), so a 1M-triangle mesh sorts 24 of the 30 bits
@@ -811,7 +912,7 @@ int sb_mesh_build(sb_mesh *m)
                 return SB_OK;
             };
             int r = capture(&m->buildGraph, [&]() {
-                cudaError_t e = cudaMemsetAsync(m->d.root, 0, 8, st);
+                cudaError_t e = cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st); // (batch: the upload's index check stays)
                 if (e == cudaSuccess) e = sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc);
                 if (e == cudaSuccess) e = sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc);
                 if (e == cudaSuccess) e = sbk_build_leaves(st, m->d, c->lc);
@@ -860,7 +961,7 @@ int sb_mesh_build(sb_mesh *m)
     }
     {
         StageTimer t(c, SB_STAGE_BUILD, st);
-        SB_CUDA(cudaMemsetAsync(m->d.root, 0, 8, st));
+        SB_CUDA(cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st));
         SB_CUDA(sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc));
         SB_CUDA(sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc));
         SB_CUDA(sbk_build_leaves(st, m->d, c->lc)); // also counts the grid cells
@@ -942,7 +1043,7 @@ static int mesh_check(sb_mesh *m)
     SB_CUDA(cudaStreamSynchronize(c->stream));
     err = c->hScalars->err;
     if (err)
-        return fail(SB_ERR_INVALID, "triangle index out of range (>= %u vertices)", m->d.nV);
+        return mesh_error(m, err);
     return SB_OK;
 }
 
@@ -1132,6 +1233,20 @@ int sb_mesh_grid_info(const sb_mesh *m, sb_grid_info *out)
     return SB_OK;
 }
 
+// batch meshes only meet batch meshes of the same shape (job j of one against job j of the other)
+static int batch_pair_check(const sb_mesh *A, const sb_mesh *B)
+{
+    if (!A->d.triJob && !B->d.triJob)
+        return SB_OK;
+    if (!A->d.triJob || !B->d.triJob)
+        return fail(SB_ERR_INVALID, "a batch mesh can only be combined with another batch mesh");
+    if (A->d.nJobs != B->d.nJobs)
+        return fail(SB_ERR_INVALID, "batch meshes with different job counts (%u, %u)", A->d.nJobs, B->d.nJobs);
+    if (A->d.latPitch != B->d.latPitch)
+        return fail(SB_ERR_INVALID, "batch meshes with different lattice pitches (%g, %g)", A->d.latPitch, B->d.latPitch);
+    return SB_OK;
+}
+
 // ---- intersection -----------------------------------------------------------------
 
 void sb_isect_destroy(sb_isect *x)
@@ -1166,6 +1281,11 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         begin = end;
     if (begin % 32)
         return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
+    {
+        int rb = batch_pair_check(A, B);
+        if (rb)
+            return rb;
+    }
     sb_context *c = A->ctx;
     DeviceGuard g(c->device);
     {
@@ -1415,6 +1535,33 @@ int sb_isect_hits(const sb_isect *x, uint32_t *ab, double *seg)
     if (seg)
         SB_CUDA(cudaMemcpyAsync(seg, x->hitSeg, 48 * x->nHit, cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_batch_job_ranges(const sb_isect *x, size_t *hit_start)
+{
+    if (!x || !hit_start)
+        return fail(SB_ERR_INVALID, "null argument");
+    const sb_mesh *A = x->A;
+    if (!A || !A->d.triJob)
+        return fail(SB_ERR_INVALID, "not the intersection of two batch meshes");
+    if (x->noSort)
+        return fail(SB_ERR_INVALID, "hits were left unsorted (SB_ISECT_NO_SORT)");
+    const size_t J = A->d.nJobs, H = x->nHit;
+    std::vector<uint32_t> ab(2 * std::max<size_t>(H, 1));
+    if (H) {
+        DeviceGuard g(x->ctx->device);
+        SB_CUDA(cudaMemcpyAsync(ab.data(), x->hitAB, 8 * H, cudaMemcpyDeviceToHost, x->ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(x->ctx->stream));
+    }
+    // the hits ascend in (a, b) and a job's triangles are one index range: one sweep
+    size_t k = 0;
+    for (size_t j = 0; j <= J; ++j) {
+        while (k < H && ab[2 * k] < A->jobTriStart[j])
+            ++k;
+        hit_start[j] = k;
+    }
+    hit_start[J] = H;
     return SB_OK;
 }
 
@@ -2164,6 +2311,8 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
         return fail(SB_ERR_INVALID, "null argument");
     if (!target->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    if (target->d.triJob)
+        return fail(SB_ERR_INVALID, "explicit query points cannot be classified against a batch mesh (they belong to no job)");
     {
         int rf = mesh_finish(target);
         if (rf)
@@ -2215,6 +2364,11 @@ static int classify_faces_impl(const sb_mesh *query, const sb_mesh *target, size
         return fail(SB_ERR_INVALID, "meshes belong to different contexts");
     if (!query->built || !target->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rb = batch_pair_check(query, target);
+        if (rb)
+            return rb;
+    }
     {
         int rf = mesh_finish(query);
         if (!rf)
@@ -2295,6 +2449,11 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
         return fail(SB_ERR_INVALID, "meshes belong to different contexts");
     if (!A->built || !B->built)
         return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rb = batch_pair_check(A, B);
+        if (rb)
+            return rb;
+    }
     {
         int rf = mesh_finish(A);
         if (!rf)

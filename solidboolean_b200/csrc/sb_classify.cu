@@ -100,10 +100,10 @@ uint32_t eval_call(const Target &T, double px, double py, double pz, int axis, u
 // number of quantised matches, 0 if not known.  Returns {distinct hit keys, exact
 // candidates seen}.
 __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, const Out &o, long long *skeys, int axis, double px,
-    double py, double pz, uint32_t n, int lane)
+    double py, double pz, uint32_t job, uint32_t n, int lane)
 {
     const d3 p = {px, py, pz};
-    const RaySetup rs = ray_setup(g, axis, p);
+    const RaySetup rs = ray_setup(g, axis, p, job);
     if (!rs.any)
         return make_uint2(0, 0);
     const uint32_t cbase = g.cellBase[axis], nu = g.nu[axis];
@@ -273,7 +273,7 @@ __device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32 ? 0xff
 // of the lanes that `want` them.  Returns bit s set when the ray along axis0 + s
 // crosses an odd number of distinct surface points (:89).
 __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Target &T, const Out &o, WarpStage &W, int axis0, int nax,
-    bool want, int lane, uint32_t &exact)
+    bool want, int lane, uint32_t job, uint32_t &exact)
 {
     const d3 p = {W.px[lane], W.py[lane], W.pz[lane]};
     // ---- count ----
@@ -282,7 +282,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
     uint32_t qx1 = 0, qy1 = 0, a1 = 0, b1 = 0, n1 = 0;
     bool legacy0 = false, legacy1 = false;
     if (want) {
-        const RaySetup r = ray_setup(g, axis0, p);
+        const RaySetup r = ray_setup(g, axis0, p, job);
         // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell;
         // the others go the general way (big_ray)
         legacy0 = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
@@ -298,7 +298,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
         }
     }
     if (want && nax > 1) {
-        const RaySetup r = ray_setup(g, axis0 + 1, p);
+        const RaySetup r = ray_setup(g, axis0 + 1, p, job);
         legacy1 = r.any && (r.cu0 != r.cu1 || r.cv0 != r.cv1);
         if (r.any && !legacy1) {
             const CellRay cq = ray_in_cell(g, axis0 + 1, r, r.cu0, r.cv0);
@@ -348,7 +348,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
                 const uint32_t pos = scan_fill(T.refs, W.ray[s][0][lane], W.ray[s][1][lane], fa, fb, W.tri, W.owner, offs - Wb, rid);
                 const uint32_t nBig = big_list_length(T, axis0 + s);
                 if (nBig) { // same order as counted: the cell list, then the big list
-                    const RaySetup r = ray_setup(g, axis0 + s, p);
+                    const RaySetup r = ray_setup(g, axis0 + s, p, job);
                     big_fill(T.bigRefs + (size_t)(axis0 + s) * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA), W.tri, W.owner, pos, rid);
                 }
             }
@@ -475,7 +475,8 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
             const int b = __ffs(bigMask) - 1;
             bigMask &= bigMask - 1;
             const uint32_t nb = __shfl_sync(SB_FULL, s ? n1 : n0, b); // 0 for a ray of several cells: not counted yet
-            const uint2 d = big_ray(g, T, o, reinterpret_cast<long long *>(W.tri), axis0 + s, W.px[b], W.py[b], W.pz[b], nb, lane);
+            const uint2 d = big_ray(g, T, o, reinterpret_cast<long long *>(W.tri), axis0 + s, W.px[b], W.py[b], W.pz[b],
+                __shfl_sync(SB_FULL, job, b), nb, lane);
             if (lane == b)
                 parity |= (d.x & 1u) << s;
             if (lane == 0)
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
     const uint32_t j = blockIdx.x * CT + threadIdx.x;
 
     d3 p = {0, 0, 0};
-    uint32_t outIndex = 0, local = 0;
+    uint32_t outIndex = 0, local = 0, job = 0;
     bool active = j < q.count;
     if (active) {
         local = q.list ? __ldg(q.list + j) : j;
@@ -515,6 +516,8 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
             // formed at build time and stored in Morton order
             p = {__ldg(q.scent + 3 * (size_t)idx), __ldg(q.scent + 3 * (size_t)idx + 1), __ldg(q.scent + 3 * (size_t)idx + 2)};
             outIndex = __ldg(q.sortedTri + idx);
+            if (q.triJob)
+                job = q.triJob[outIndex];
         } else {
             active = false; // padding of the sorted order
         }
@@ -541,7 +544,7 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
         }
         if (!__any_sync(SB_FULL, want))
             continue;
-        votes |= trace_round(g, T, o, W, 2 * round, 2 - round, want, lane, exact) << (2 * round);
+        votes |= trace_round(g, T, o, W, 2 * round, 2 - round, want, lane, job, exact) << (2 * round);
     }
     if (active) {
         bool in;
@@ -605,6 +608,7 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     q.begin = a.begin;
     q.count = a.list ? a.listCount : a.end - a.begin;
     q.list = a.list;
+    q.triJob = qm ? qm->triJob : nullptr;
     if (q.count == 0)
         return cudaSuccess;
     Target T;

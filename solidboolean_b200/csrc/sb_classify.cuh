@@ -66,6 +66,7 @@ struct Query {
     uint32_t begin;            // first point / sorted position
     uint32_t count;            // points in this launch
     const uint32_t *list;      // optional: the launch's points as indices relative to `begin`
+    const uint16_t *triJob;    // batch meshes (faces mode): job of each query face, or null
 };
 
 struct Out {
@@ -90,7 +91,7 @@ struct RaySetup {
     bool any;                    // the ray box overlaps the mesh box
 };
 
-__device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, const d3 &p)
+__device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, const d3 &p, uint32_t job = 0)
 {
     RaySetup rs;
     const d3 e = ray_end(p, axis);
@@ -98,11 +99,11 @@ __device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, con
     const BoxD meshBox = {g.lo[0], g.lo[1], g.lo[2], g.hi[0], g.hi[1], g.hi[2]};
     rs.any = overlap_d(meshBox, myD); // otherwise no triangle box can overlap the ray box
     const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
-    rs.aU = quant15(comp(myD, u, false), g.org[u], g.scl[u]);
-    rs.bU = quant15(comp(myD, u, true), g.org[u], g.scl[u]);
-    rs.aV = quant15(comp(myD, v, false), g.org[v], g.scl[v]);
-    rs.bV = quant15(comp(myD, v, true), g.org[v], g.scl[v]);
-    rs.aA = quant15(comp(myD, axis, false), g.org[axis], g.scl[axis]);
+    rs.aU = quant_axis(comp(myD, u, false), g, u, job);
+    rs.bU = quant_axis(comp(myD, u, true), g, u, job);
+    rs.aV = quant_axis(comp(myD, v, false), g, v, job);
+    rs.bV = quant_axis(comp(myD, v, true), g, v, job);
+    rs.aA = quant_axis(comp(myD, axis, false), g, axis, job);
     const int su = g.shiftU[axis], sv = g.shiftV[axis];
     rs.cu0 = rs.aU >> su; rs.cu1 = rs.bU >> su;
     rs.cv0 = rs.aV >> sv; rs.cv1 = rs.bV >> sv;

@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t prefix_max_bytes(uint32_t x)
 // number of distinct surface points (:89); lanes whose point needs the general kernel get
 // their bit in `legacy`.
 __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Target &T, Stage2 &W, int axis0, int nax, bool want,
-    int lane, uint32_t &exact, uint32_t &legacy)
+    int lane, uint32_t job, uint32_t &exact, uint32_t &legacy)
 {
     const d3 p = {W.px[lane], W.py[lane], W.pz[lane]};
     // ---- setup: packed ray, cell list, pairs ----
@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         if (s < nax && want) {
-            const RaySetup r = ray_setup(g, axis0 + s, p);
+            const RaySetup r = ray_setup(g, axis0 + s, p, job);
             if (r.any) {
                 // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell
                 if (r.cu0 != r.cu1 || r.cv0 != r.cv1) {
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(CT2, SB_CLS2_MINB) classify2_kernel(const __gr
     const uint32_t j = blockIdx.x * CT2 + threadIdx.x;
 
     d3 p = {0, 0, 0};
-    uint32_t outIndex = 0;
+    uint32_t outIndex = 0, job = 0;
     bool active = j < q.count;
     if (active) {
         const uint32_t idx = q.begin + j;
@@ -335,6 +335,8 @@ __global__ void __launch_bounds__(CT2, SB_CLS2_MINB) classify2_kernel(const __gr
             // formed at build time and stored in Morton order
             p = {__ldg(q.scent + 3 * (size_t)idx), __ldg(q.scent + 3 * (size_t)idx + 1), __ldg(q.scent + 3 * (size_t)idx + 2)};
             outIndex = __ldg(q.sortedTri + idx);
+            if (q.triJob)
+                job = q.triJob[outIndex];
         } else {
             active = false; // padding of the sorted order
         }
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(CT2, SB_CLS2_MINB) classify2_kernel(const __gr
         }
         if (!__any_sync(SB_FULL, want))
             continue;
-        votes |= trace_round2(g, T, W, 2 * round, 2 - round, want, lane, exact, legacy) << (2 * round);
+        votes |= trace_round2(g, T, W, 2 * round, 2 - round, want, lane, job, exact, legacy) << (2 * round);
     }
     const bool mine = (legacy >> lane) & 1u; // the general kernel classifies this point (and counts its candidates)
     if (mine) {
@@ -418,6 +420,7 @@ cudaError_t sbk_classify2(cudaStream_t s, const MeshDev &target, const ClassifyA
     q.begin = a.begin;
     q.count = a.end - a.begin;
     q.list = nullptr;
+    q.triJob = qm ? qm->triJob : nullptr;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;

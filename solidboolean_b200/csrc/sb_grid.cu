@@ -33,35 +33,43 @@ namespace {
 // is a shift of the 15-bit coordinate.  maxBits bounds cells per axis (allocation).
 __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds,
     const unsigned long long *__restrict__ extentSum,
-    uint32_t nT, int maxBits, float beta, GridParams *out)
+    uint32_t nT, int maxBits, float beta, int batch, double latPitch, int *err, GridParams *out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
     GridParams g;
+    // batch mesh: 10 job-local bits per axis under 5 lattice bits (sb_gridq.cuh); a cell never spans two jobs
+    g.latShift = batch ? SB_BATCH_LAT_SHIFT : 0;
+    g.qmax = batch ? 1023.0 : 32767.0;
+    const int localBits = batch ? SB_BATCH_LAT_SHIFT : SB_Q_BITS, latBits = batch ? SB_Q_BITS - SB_BATCH_LAT_SHIFT : 0;
     int bitsWanted[3];
     for (int d = 0; d < 3; ++d) {
         double lo = dkey_inv(bounds[d]), hi = dkey_inv(bounds[3 + d]);
         double ext = hi - lo;
         g.org[d] = lo;
         // hi maps to 32767.99..; finite and > 0 extents only
-        g.scl[d] = (ext > 0.0 && ext < 1.0e300) ? 32767.999 / ext : 0.0;
+        g.scl[d] = (ext > 0.0 && ext < 1.0e300) ? (g.qmax + 0.999) / ext : 0.0;
         g.lo[d] = lo;
         g.hi[d] = hi;
+        // batch: jobs one lattice step apart must not meet, whatever their place inside [-M, M]
+        if (batch && !(4.0 * fmax(fabs(lo), fabs(hi)) <= latPitch))
+            atomicOr(err, 2);
         unsigned long long isum = 0; // fixed point: 2^-24 fractions of the mesh extent
         for (int k = 0; k < 32; ++k)
             isum += extentSum[3 * k + d];
         double mean = nT ? (double)isum / 16777216.0 * ext / (double)nT : 0.0;
         double cells = (ext > 0.0 && mean > 0.0) ? ext / ((double)beta * mean) : 1.0;
         int b = (int)floor(log2(fmax(cells, 1.0)) + 0.5);
-        bitsWanted[d] = max(0, min(b, SB_Q_BITS));
+        bitsWanted[d] = max(0, min(b, localBits)) + latBits;
     }
     uint32_t base = 0;
     for (int a = 0; a < 3; ++a) {
         int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
         int ku = bitsWanted[u], kv = bitsWanted[v];
         while (ku + kv > maxBits) { // shrink the finer dimension first
-            if (ku >= kv && ku > 0) --ku;
-            else if (kv > 0) --kv;
+            if (ku >= kv && ku > latBits) --ku;
+            else if (kv > latBits) --kv;
+            else if (ku > latBits) --ku;
             else break;
         }
         g.shiftU[a] = SB_Q_BITS - ku;
@@ -71,7 +79,6 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
         base += 1u << (ku + kv);
     }
     g.totalCells = base;
-    g.pad = 0;
     *out = g;
 }
 
@@ -275,7 +282,7 @@ cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, 
     cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)maxCells + 2), s);
     cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
     cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * sbk_grid_scan_status_words(maxCells), s);
-    grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, m.extentSum, m.nT, (int)m.gridCellBits, beta, m.gridParams);
+    grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, m.extentSum, m.nT, (int)m.gridCellBits, beta, m.triJob ? 1 : 0, m.latPitch, m.err, m.gridParams);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -21,11 +21,29 @@
 #define SB_Q_BITS 15
 #define SB_Q_GUARD 0x80008000u
 
-__device__ __forceinline__ uint32_t quant15(double x, double org, double scl)
+__device__ __forceinline__ uint32_t quant15(double x, double org, double scl, double qmax = 32767.0)
 {
     double t = floor((x - org) * scl);
-    t = fmin(fmax(t, 0.0), 32767.0); // NaN -> 0
+    t = fmin(fmax(t, 0.0), qmax); // NaN -> 0
     return (uint32_t)t;
+}
+
+// Batch meshes: position of job j on a 32 x 32 x 32 lattice, chosen so that ANY two of the three
+// coordinates identify the job (z = x + y mod 32) -- each ray grid bins two of them, so the jobs
+// (at most 1024) never share a cell; the float boxes of the LBVH use all three.
+#define SB_BATCH_MAX_JOBS 1024u
+#define SB_BATCH_LAT_SHIFT 10
+__host__ __device__ __forceinline__ uint32_t lattice3(uint32_t job, int d)
+{
+    const uint32_t lx = (job >> 5) & 31u, ly = job & 31u;
+    return d == 0 ? lx : d == 1 ? ly : ((lx + ly) & 31u);
+}
+
+// quantised coordinate along world axis d of a point of job `job` (plain meshes: job 0, latShift 0)
+__device__ __forceinline__ uint32_t quant_axis(double x, const GridParams &g, int d, uint32_t job)
+{
+    const uint32_t q = quant15(x, g.org[d], g.scl[d], g.qmax);
+    return g.latShift ? q + (lattice3(job, d) << g.latShift) : q;
 }
 
 // reference of a triangle whose quantised box is [qlu,qhu] x [qlv,qhv] across the ray
@@ -127,11 +145,11 @@ __device__ __forceinline__ bool cell_ref_match(const CellRay &q, const uint2 &r)
 #endif
 
 // quantised triangle box: one word per world axis, lo | hi << 16; .w = triangle id
-__device__ __forceinline__ uint4 quantise_box(const BoxD &b, const GridParams &g, uint32_t id)
+__device__ __forceinline__ uint4 quantise_box(const BoxD &b, const GridParams &g, uint32_t id, uint32_t job = 0)
 {
-    return make_uint4(quant15(b.lox, g.org[0], g.scl[0]) | (quant15(b.hix, g.org[0], g.scl[0]) << 16),
-                      quant15(b.loy, g.org[1], g.scl[1]) | (quant15(b.hiy, g.org[1], g.scl[1]) << 16),
-                      quant15(b.loz, g.org[2], g.scl[2]) | (quant15(b.hiz, g.org[2], g.scl[2]) << 16), id);
+    return make_uint4(quant_axis(b.lox, g, 0, job) | (quant_axis(b.hix, g, 0, job) << 16),
+                      quant_axis(b.loy, g, 1, job) | (quant_axis(b.hiy, g, 1, job) << 16),
+                      quant_axis(b.loz, g, 2, job) | (quant_axis(b.hiz, g, 2, job) << 16), id);
 }
 
 __device__ __forceinline__ uint32_t qbox_axis(const uint4 &q, int d) { return d == 0 ? q.x : d == 1 ? q.y : q.z; }

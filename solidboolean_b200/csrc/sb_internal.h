@@ -20,7 +20,9 @@ struct GridParams {
     uint32_t nu[3];        // cells along u
     uint32_t cellBase[3];  // first cell of axis a in the concatenated cell space
     uint32_t totalCells;
-    uint32_t pad;
+    uint32_t latShift;     // 0: plain mesh.  Batch mesh (sb_batch_upload): quantised coordinates are job-local in the bits
+                           // below latShift (10), the job's lattice position (sb_gridq.cuh lattice3) sits above them
+    double qmax;           // clamp of the job-local part: 32767 (plain) or 1023 (batch)
 };
 
 // Device-resident mesh (all pointers are device pointers).
@@ -62,6 +64,14 @@ struct MeshDev {
     uint32_t *gridBigCount = nullptr;   // [0..2] counts (count pass), [3..5] fill cursors, [6] total refs
     uint32_t gridBigCap = 0;
     uint32_t gridBigN[3] = {0, 0, 0};   // host copy of the big-list lengths
+    // batch mesh (sb_batch_upload): many independent small meshes ("jobs") laid end to end.  Triangle and vertex
+    // indices are global; the jobs overlap in space, so every spatial structure keeps them apart by a VIRTUAL
+    // translation that never touches the doubles: the job number leads the Morton key, the conservative float
+    // boxes of the LBVH are shifted by latPitch x lattice3(job), the quantised coordinates of the ray grids by
+    // lattice3(job) << 10.  Exact tests read the real coordinates.
+    const uint16_t *triJob = nullptr;   // nT: job of each triangle (original order), or null
+    uint32_t nJobs = 0;
+    double latPitch = 0.0;
 };
 
 struct LaunchCounter {
@@ -75,6 +85,8 @@ struct LaunchCounter {
 cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc);
 cudaError_t sbk_build_leaves(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
 cudaError_t sbk_build_tree(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
+cudaError_t sbk_batch_fixup(cudaStream_t s, uint32_t *tri, uint32_t nT, const uint32_t *triStart, const uint32_t *vtxStart,
+    uint32_t nJobs, uint16_t *triJob, int *err, LaunchCounter &lc);
 cudaError_t sbk_triangle_boxes(cudaStream_t s, const MeshDev &m, double2 *out /* 3*nT, original order */, LaunchCounter &lc);
 
 // sb_broad.cu -- candidate keys: (((a << bitsB) | b) << 2), code bits zero
