@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c4k8"])
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c4k8", "c5"])
+    ap.add_argument("--jobs", type=int, default=1000, help="c5: number of 5K+5K-triangle jobs in the batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -638,6 +639,311 @@ def run_ours(args):
     sys.stderr.flush()
 
 
+# ----------------------------------------------------------------------------
+# BASELINE configs[4] ("C5"): a batch of 1,000 small booleans (icosphere k=4 pairs, 5,120 + 5,120
+# triangles, seeded offsets), jobs dealt job_id mod N over the GPUs, no collective.
+# On every rank the jobs form ONE batch mesh per side (sb_batch_upload): one sort, one leaf / grid
+# build and one front-end launch sequence for all of them.
+
+C5_DESC = "batch of %d boolean front ends, icosphere k=4 pairs (5,120 + 5,120 triangles each, seeded offsets), BASELINE configs[4]"
+
+
+def c5_jobs(n_jobs, rank=0, world=1):
+    from solidboolean_b200 import meshgen
+    ids = list(range(rank, n_jobs, world))
+    return ids, [meshgen.config_c5_job(j) for j in ids]
+
+
+def c5_reference_jobs(jobs, threads):
+    """The reference (one SolidBoolean front end per job: prepare x2, search, predicate loop,
+    isPointInMesh on every face centroid) over all host cores, one job per thread at a time.
+    -> (seconds, total hits, per-job results)."""
+    from oracle import Oracle, Ref
+    use_ref = Ref.available()
+    out = [None] * len(jobs)
+
+    def one(k):
+        a, b = jobs[k]
+        if use_ref:
+            R = Ref.get()
+            ma, mb = R.mesh(*a), R.mesh(*b)
+            op = R.op(ma, mb)
+            pairs = op.search()
+            ret, cop, hit, seg, _ = op.predicate(pairs)
+            fa = op.classify(1, ma.centroids())[0]
+            fb = op.classify(0, mb.centroids())[0]
+            op.close(); ma.close(); mb.close()
+        else:
+            O = Oracle.get()
+            pairs = O.candidate_pairs(a, b)
+            ret, cop, hit, seg = O.predicate_pairs(a, b, pairs)
+            fa = O.classify(b, O.centroids(*a))[0]
+            fb = O.classify(a, O.centroids(*b))[0]
+        h = hit.astype(bool)
+        order = np.lexsort((pairs[h][:, 1], pairs[h][:, 0]))
+        out[k] = (len(pairs), pairs[h][order], seg[h][order], fa, fb)
+
+    def worker(t):
+        for k in range(t, len(jobs), threads):
+            one(k)
+    t0 = time.perf_counter()
+    ws = [threading.Thread(target=worker, args=(t,)) for t in range(threads)]
+    [w.start() for w in ws]
+    [w.join() for w in ws]
+    sec = time.perf_counter() - t0
+    return sec, sum(len(r[1]) for r in out), out, ("reference" if use_ref else "port")
+
+
+def c5_config(n_jobs):
+    return {"workload": C5_DESC % n_jobs, "name": "c5", "jobs": n_jobs, "tris_a": 5120 * n_jobs, "tris_b": 5120 * n_jobs,
+            "l2": "512 MiB buffer written between timed steps (L2 flush)",
+            "parallelism": "jobs dealt job_id mod N over the ranks, one batch mesh per side and rank, no collective"}
+
+
+def run_reference_c5(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = host_threads()
+    # a bounded sample per step: 4 jobs per host thread, scaled to the whole batch by the job count
+    sample = min(args.jobs, 4 * threads)
+    _, jobs = c5_jobs(sample)
+    times, H = [], 0
+    for i in range(args.warmup + args.steps):
+        sec, H, _, kind = c5_reference_jobs(jobs, threads)
+        if i >= args.warmup:
+            times.append(sec)
+    sec = float(np.mean(times)) * args.jobs / sample
+    Hs = H * args.jobs / sample
+    val = Hs / sec
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": c5_config(args.jobs),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "%d of the %d jobs per step (4 per host thread), each job the reference's whole front end; "
+                                       "time and hits scaled by the job count" % (sample, args.jobs)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ms_per_job": sec * 1e3 / args.jobs, "jobs_per_s": args.jobs / sec}
+    print(json.dumps(line), flush=True)
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    import solidboolean_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ids, jobs = c5_jobs(args.jobs, rank, world)
+    J = len(jobs)
+    ctx = sb.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    def work():
+        # the batch as a caller hands it over: concatenated arrays + start offsets, in pinned host memory
+        def cat(side):
+            xs = [j[side][0] for j in jobs]
+            ts = [j[side][1] for j in jobs]
+            return (np.concatenate(xs), np.concatenate([[0], np.cumsum([len(x) for x in xs])]).astype(np.uint64),
+                    np.concatenate(ts), np.concatenate([[0], np.cumsum([len(t) for t in ts])]).astype(np.uint64))
+        hostA, hostB = cat(0), cat(1)
+        pitch = sb.batch_pitch(hostA[0], hostB[0])
+        if world > 1:   # one pitch for the whole run (any rank's value would do for its own batches; kept equal for the record)
+            t = torch.tensor([pitch], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pitch = float(t.item())
+        pinned = [[torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (h[0], h[2].view(np.int32))] for h in (hostA, hostB)]
+        nA, nB = len(hostA[2]), len(hostB[2])
+        nVA, nVB = len(hostA[0]), len(hostB[0])
+        flagsA = torch.zeros(nA, dtype=torch.uint8, device=dev)
+        flagsB = torch.zeros(nB, dtype=torch.uint8, device=dev)
+        l2_flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+        def make(side, build):
+            h, pin = (hostA, hostB)[side], pinned[side]
+            return sb.Mesh.batch_arrays(ctx, pin[0].numpy(), h[1], pin[1].numpy().view(np.uint32), h[3], pitch, build=build)
+        A, B = make(0, False), make(1, False)
+        ctx.synchronize()
+        ctx.enable_timing(True)
+        stats = [0, 0]
+
+        def resident_step():
+            with torch.cuda.stream(ext):
+                A.build(); B.build()
+                x = sb.Isect.front_end(A, B, flagsA.data_ptr(), flagsB.data_ptr())
+                stats[0], stats[1] = ctx.classify_stats()
+                P, H = x.num_candidates, x.num_hits
+                x.close()
+            return P, H
+
+        def timed_loop(step_fn, steps, warmup, device_timed):
+            for _ in range(warmup):
+                res = step_fn()
+            torch.cuda.synchronize()
+            ctx.reset_timing()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            total_ms = 0.0
+            t_begin = time.monotonic()
+            for _ in range(steps):
+                with torch.cuda.stream(ext):
+                    l2_flush.zero_()
+                torch.cuda.synchronize()
+                if device_timed:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(ext)
+                    res = step_fn()
+                    e1.record(ext)
+                    e1.synchronize()
+                    total_ms += e0.elapsed_time(e1)
+                else:
+                    t0 = time.perf_counter()
+                    res = step_fn()
+                    torch.cuda.synchronize()
+                    total_ms += (time.perf_counter() - t0) * 1e3
+            clocks = sampler.summary(t_begin, time.monotonic())
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / steps, res, clocks
+
+        ms_step, (P, H), clocks = timed_loop(resident_step, args.steps, args.warmup, True)
+        stage_ms, launches = ctx.timing()
+        stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+        rays, cands = stats
+
+        # host-buffer loop: upload of the rank's whole batch, builds, front end, everything back to the host
+        out_a = torch.zeros(nA, dtype=torch.uint8).pin_memory()
+        out_b = torch.zeros(nB, dtype=torch.uint8).pin_memory()
+        host_hits = {}
+        last = {}
+
+        def e2e_step():
+            with torch.cuda.stream(ext):
+                xa, xb = make(0, False), make(1, False)
+                xa.build(); xb.build()
+                x = sb.Isect.front_end(xa, xb, flagsA.data_ptr(), flagsB.data_ptr())
+                out_a.copy_(flagsA, non_blocking=True)
+                out_b.copy_(flagsB, non_blocking=True)
+                if host_hits.get("cap", -1) < x.num_hits:
+                    cap = x.num_hits * 3 // 2 + 64
+                    host_hits.update(cap=cap, ab=torch.zeros(2 * cap, dtype=torch.int32).pin_memory(),
+                                     seg=torch.zeros(6 * cap, dtype=torch.float64).pin_memory())
+                sb._check(x.lib.sb_isect_hits(x.h, host_hits["ab"].data_ptr(), host_hits["seg"].data_ptr()))
+                last["ranges"] = x.job_ranges()
+                res = (x.num_candidates, x.num_hits)
+                x.close(); xa.close(); xb.close()
+            return res
+
+        ctx.enable_timing(False)
+        e2e_ms, (P2, H2), _ = timed_loop(e2e_step, max(3, args.steps // 2), 2, False)
+        sampler.stop()
+        tot = torch.tensor([P, H, P2, H2, rays, cands, J], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        Pg, Hg, P2g, H2g, rays_g, cands_g, Jg = [int(v) for v in tot.tolist()]
+
+        # parity: jobs of this rank against the CPU (the reference where it was built, else the port), all fields
+        want = max(1, (64 + world - 1) // world)
+        sample = list(range(0, J, max(1, J // want)))[:want] if not args.no_cpu_baseline else []
+        ok, checked = True, 0
+        if sample:
+            _, _, refs, kind = c5_reference_jobs([jobs[k] for k in sample], host_threads())
+            r = last["ranges"]
+            gab = host_hits["ab"][:2 * H2].numpy().reshape(-1, 2).astype(np.int64)
+            gseg = host_hits["seg"][:6 * H2].numpy().reshape(-1, 6)
+            ta, tb = hostA[3].astype(np.int64), hostB[3].astype(np.int64)
+            fa, fb = out_a.numpy(), out_b.numpy()
+            for k, ref in zip(sample, refs):
+                mine = gab[r[k]:r[k + 1]] - [ta[k], tb[k]]
+                ok = ok and np.array_equal(mine, ref[1].astype(np.int64)) and gseg[r[k]:r[k + 1]].tobytes() == ref[2].tobytes() \
+                    and np.array_equal(fa[ta[k]:ta[k + 1]], ref[3]) and np.array_equal(fb[tb[k]:tb[k + 1]], ref[4])
+                checked += 1
+        par = torch.tensor([1 if ok else 0, checked], dtype=torch.int64, device=dev)
+        if world > 1:
+            okt = par[:1].clone()
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            dist.all_reduce(par[1:])
+            par[0] = okt[0]
+        if rank == 0:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+            cls_bytes = 25 * (nA + nB) + 104 * (nA + nB) + 108 * cands    # SURVEY 8d, rank 0's batch
+            cls_ms = stage_ms["classify"]
+            achieved = cls_bytes / (cls_ms * 1e-3) / 1e9 if cls_ms > 0 else 0.0
+            n_jobs = Jg
+            line = {
+                "metric": METRIC, "value": Hg / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": c5_config(n_jobs),
+                "jobs": n_jobs, "ms_per_job": ms_step / n_jobs, "jobs_per_s": n_jobs / (ms_step * 1e-3),
+                "candidate_pairs": Pg, "intersecting_pairs": Hg,
+                "triangles_per_s": 10240 * n_jobs / (ms_step * 1e-3),
+                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+                "roofline": {"bound": "hbm", "kernel": "classification of rank 0's batch: classify2_kernel, both directions",
+                             "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+                             "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
+                             "algorithmic_bytes_per_step": cls_bytes, "kernel_ms_per_step": round(cls_ms, 4)},
+                "e2e": {"value": H2g / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "ms_per_job": e2e_ms / n_jobs,
+                        "h2d_bytes_per_step": 24 * (nVA + nVB) + 12 * (nA + nB) + 16 * (J + 1) * 2,
+                        "d2h_bytes_per_step": (nA + nB) + 56 * int(H2) + 64, "bytes_are": "rank 0's share"},
+                "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+                "parity": {"jobs_checked": int(par[1]), "identical": bool(int(par[0])),
+                           "what": "hit pairs, segments (bit for bit) and per-face flags of the sampled jobs against the CPU, from the last host-buffer step"},
+                "clocks": clocks,
+            }
+            if world == 1 and not args.no_cpu_baseline:
+                threads = host_threads()
+                ns = min(J, 4 * threads)
+                sec, Hs, _, kind = c5_reference_jobs(jobs[:ns], threads)
+                line["cpu_baseline"] = {"value": Hs / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                                        "sample": "%d of the %d jobs (4 per host thread), each the reference's whole front end" % (ns, n_jobs),
+                                        "ms_per_job": sec * 1e3 / ns, "jobs_per_s": ns / sec}
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        torch.cuda.synchronize()
+        A.close(); B.close()
+
+    # everything that lives in pinned or device memory is a local of work(): it is gone (and, after the
+    # collection below, really freed) before the caches are emptied and the library's streams destroyed
+    work()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    del ext
+    gc.collect()
+    torch.cuda.empty_cache()
+    try:
+        torch._C._host_emptyCache()
+    except Exception:
+        pass
+    torch.cuda.synchronize()
+    ctx.close()
+    sys.stdout.flush()
+    sys.stderr.flush()
+
+
 def next_rows(sb, ctx, ma, mb, a, b, with_cpu):
     """SURVEY 8f rows 1-3, outside the timed step: the per-triangle intersection contexts (the
     pair-loop body of combine(), :296-339), uncut triangles + half-edge map
@@ -731,7 +1037,9 @@ def _as_tensor(torch, ptr, shape, dtype, dev):
 
 if __name__ == "__main__":
     args = parse_args()
-    if args.impl == "reference":
+    if args.config == "c5":
+        (run_reference_c5 if args.impl == "reference" else run_c5)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
