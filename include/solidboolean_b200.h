@@ -258,6 +258,28 @@ int sb_classify_faces(const sb_mesh *query, const sb_mesh *target,
 int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target,
                              size_t begin, size_t end, void *d_inside);
 
+/* ---- multi-GPU shards (north_star: "mesh A's query triangles shard naturally") ---------
+ * One process per GPU.  Every rank uploads (or receives) the geometry of both meshes -- sb_mesh_upload,
+ * no build -- and makes a shard for its rank.  sb_shard_front_end then does the rank's share of one
+ * front end: the faces of A and of B are dealt to the ranks by the z of their centroid (n equally
+ * populated slabs, borders computed on the device, identical on every rank); the rank selects from both
+ * meshes the triangles its queries can meet (the two lazy test rays run along x and y, so a slab is
+ * closed under them), builds LBVH + ray grids over that selection only, and runs broad phase, predicate
+ * and both classifications for its own faces.  Results use the triangle ids of the uploaded meshes:
+ * the isect holds the rank's hit pairs (sorted) and segments -- sb_isect_counts / sb_isect_hits /
+ * sb_isect_pack_device; candidates, contexts and uncut triangles are not offered on a shard's isect --
+ * and d_insideA / d_insideB (caller-owned device arrays of nT(A) / nT(B) bytes) receive the flags of the
+ * rank's own faces, the other bytes are left alone.  Summing the flag arrays and concatenating the hit
+ * lists of all ranks gives the single-GPU result (the union over ranks is exact: every face belongs to
+ * one rank).  A point whose first two votes disagree needs its third ray, along z, through the whole
+ * target: the rank then builds the whole meshes and classifies its faces again (rare; counted). */
+typedef struct sb_shard sb_shard;
+int sb_shard_create(const sb_mesh *A, const sb_mesh *B, int rank, int n_ranks, sb_shard **out);
+int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB);
+int sb_shard_info(const sb_shard *s, size_t *selected_a, size_t *selected_b, double *z_lo, double *z_hi,
+                  uint64_t *fallbacks);
+void sb_shard_destroy(sb_shard *s);
+
 /* ---- batches of small booleans (BASELINE configs[4]: 1,000 x 5K-triangle jobs; SURVEY 8e "C5") --------
  * The reference runs one SolidBoolean per call (test/main.cpp:92-103); a 5K-triangle mesh cannot fill a
  * B200.  A BATCH MESH holds the meshes of n_jobs independent jobs end to end and goes through the same

@@ -54,6 +54,11 @@ ABI = {
     "sb_batch_upload": (C.c_int, [_vp, _sz, _vp, _vp, _vp, _vp, C.c_double, C.POINTER(_vp)]),
     "sb_batch_info": (C.c_int, [_vp, C.POINTER(_sz), _vp, _vp]),
     "sb_batch_job_ranges": (C.c_int, [_vp, _vp]),
+    "sb_shard_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "sb_shard_front_end": (C.c_int, [_vp, C.c_uint, C.POINTER(_vp), _vp, _vp]),
+    "sb_shard_info": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_uint64)]),
+    "sb_shard_destroy": (None, [_vp]),
     "sb_mesh_build": (C.c_int, [_vp]),
     "sb_mesh_destroy": (None, [_vp]),
     "sb_mesh_num_triangles": (_sz, [_vp]),
@@ -356,6 +361,44 @@ class Mesh:
     def classify_faces_device(self, target: "Mesh", d_inside_ptr: int, begin=0, end=None):
         end = self.num_triangles if end is None else end
         _check(self.lib.sb_classify_faces_device(self.h, target.h, begin, end, _vp(d_inside_ptr)))
+
+
+class Shard:
+    """One rank's share of a multi-GPU front end (sb_shard): `a`, `b` = uploaded meshes (build=False is enough)."""
+
+    def __init__(self, a: Mesh, b: Mesh, rank: int, n_ranks: int):
+        self.a, self.b, self.lib = a, b, a.lib
+        h = _vp()
+        _check(self.lib.sb_shard_create(a.h, b.h, rank, n_ranks, C.byref(h)))
+        self.h = h
+
+    def front_end(self, d_inside_a: int, d_inside_b: int, flags=0) -> "Isect":
+        x = Isect.__new__(Isect)
+        x.a, x.b, x.lib = self.a, self.b, self.lib
+        h = _vp()
+        _check(self.lib.sb_shard_front_end(self.h, flags, C.byref(h), _vp(d_inside_a), _vp(d_inside_b)))
+        x.h = h
+        nc, nh = _sz(0), _sz(0)
+        _check(self.lib.sb_isect_counts(h, C.byref(nc), C.byref(nh)))
+        x.num_candidates, x.num_hits = int(nc.value), int(nh.value)
+        return x
+
+    def info(self):
+        sa, sb_, lo, hi, fb = _sz(0), _sz(0), C.c_double(0), C.c_double(0), C.c_uint64(0)
+        _check(self.lib.sb_shard_info(self.h, C.byref(sa), C.byref(sb_), C.byref(lo), C.byref(hi), C.byref(fb)))
+        return dict(selected_a=int(sa.value), selected_b=int(sb_.value), z_lo=float(lo.value), z_hi=float(hi.value),
+                    fallbacks=int(fb.value))
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.a.ctx, "h", None):
+            self.lib.sb_shard_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def batch_pitch(*arrays) -> float:

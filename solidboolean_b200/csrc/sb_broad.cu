@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
     const Rec32 *__restrict__ leafA, const double2 *__restrict__ sboxA, uint32_t groupBegin, uint32_t groupEnd,
     const Rec32 *__restrict__ nodesB, const Rec32 *__restrict__ leafB, const double2 *__restrict__ sboxB,
     const int *__restrict__ rootB, const unsigned long long *__restrict__ boundsB, unsigned bitsB,
-    unsigned long long *__restrict__ outKeys, unsigned long long capacity, unsigned long long *__restrict__ outCount)
+    unsigned long long *__restrict__ outKeys, unsigned long long capacity, unsigned long long *__restrict__ outCount,
+    const double *__restrict__ scentA, double ownLo, double ownHi, int ownMode /* 0 off, 1 [lo, hi), 2 [lo, hi] */)
 {
     __shared__ BroadShared sh[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -37,7 +38,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) broad_phase_kernel(
 
     const uint32_t j = group * 32 + lane;
     Rec32 me = load_rec(leafA + j);
-    const BoxF myF = {me.lox, me.loy, me.loz, me.hix, me.hiy, me.hiz};
+    BoxF myF = {me.lox, me.loy, me.loz, me.hix, me.hiy, me.hiz};
+    if (ownMode) {
+        // multi-GPU selection: only the faces whose centroid lies in this rank's slab ask (sb_shard.cu);
+        // the others -- and NaN -- hold an empty box like the padding lanes
+        const double cz = scentA[3 * (size_t)j + 2];
+        if (!(me.ref >= 0 && cz >= ownLo && (ownMode == 2 ? cz <= ownHi : cz < ownHi)))
+            myF = empty_boxf();
+    }
     // groups whose box misses B's bounding box altogether (most of a mesh, usually) leave
     // before they touch their exact boxes or B's tree
     BoxF all = myF; // padding lanes hold an empty box and never match
@@ -114,7 +122,8 @@ cudaError_t sbk_broad_phase(cudaStream_t s, const MeshDev &A, const MeshDev &B, 
     uint32_t groups = groupEnd - groupBegin;
     uint32_t blocks = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     broad_phase_kernel<<<blocks, WARPS_PER_CTA * 32, 0, s>>>(A.leaf, A.sbox, groupBegin, groupEnd, B.nodes, B.leaf, B.sbox,
-        B.root, B.triJob ? nullptr : B.bounds, bitsB, outKeys, capacity, outCount);
+        B.root, B.triJob ? nullptr : B.bounds, bitsB, outKeys, capacity, outCount, A.scent, A.ownLo, A.ownHi,
+        A.ownFilter ? (A.ownClosed ? 2 : 1) : 0);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -351,20 +351,33 @@ cudaError_t sbk_triangle_boxes(cudaStream_t s, const MeshDev &m, double2 *out, L
 
 size_t sbk_radix_workspace_words(size_t n) { return sbradix::Workspace::words(sbradix::tiles_for(n)); }
 
-cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc)
+// whole-mesh box + padded vertex copy (K2)
+cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounter &lc)
 {
-    if (m.nT == 0)
-        return cudaSuccess;
     // bounds seeds: min slots all-ones, max slots zero (order-encoded doubles)
     cudaMemsetAsync(m.bounds, 0xff, 3 * sizeof(unsigned long long), s);
     cudaMemsetAsync(m.bounds + 3, 0x00, 3 * sizeof(unsigned long long), s);
-    cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(unsigned long long), s);
     int vb = (int)((m.nV + 255) / 256);
     if (vb > smCount * 8)
         vb = smCount * 8;
     if (vb < 1)
         vb = 1;
     bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(unsigned long long), s);
+    if (!m.sharedVtx) { // (a multi-GPU selection reads its parent's padded vertices and bounds)
+        cudaError_t eb = sbk_bounds_pad(s, m, smCount, lc);
+        if (eb != cudaSuccess)
+            return eb;
+        lc.kernels -= 1;
+    }
     tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.normal, m.mkey, m.order, m.err,
         m.extentSum, m.triJob);
     lc.kernels += 2;

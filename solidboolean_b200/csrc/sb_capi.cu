@@ -105,6 +105,7 @@ struct sb_context {
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
     int sortBeginBit = -1;           // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT); -1 = by mesh size
     uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
+    uint64_t shardUndecided = 0;     // points of a multi-GPU selection whose first two votes disagreed (need the whole target)
     bool classifyBalanced = true;    // SB_CLASSIFY_V2=0: every launch uses the general kernel (sb_classify.cu)
     bool useGraphs = true;           // SB_GRAPHS=0: rebuilds enqueue their kernels one by one
     size_t grid3EagerBelow = 65536;  // SB_GRID3_EAGER_BELOW: meshes with fewer triangles get their third ray grid right away
@@ -327,7 +328,7 @@ int alloc_async(sb_context *c, T **p, size_t count, std::vector<void *> *owned)
     return SB_OK;
 }
 
-int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJobs = 0)
+int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJobs = 0, const sb_mesh *vertexParent = nullptr)
 {
     if (nV >= (1ull << 31) || nT >= (1ull << SB_MAX_TRIANGLE_BITS))
         return fail(SB_ERR_INVALID, "mesh too large: %zu vertices, %zu triangles", nV, nT);
@@ -348,7 +349,8 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
         off += align256(std::max<size_t>(bytes, 16));
         return o;
     };
-    size_t oXyz = take(24 * nV), oTri = take(12 * nT), oVtx = take(32 * nV), oBounds = take(48);
+    // (a multi-GPU selection reads the vertices, padded vertices and bounds of its parent)
+    size_t oXyz = take(vertexParent ? 0 : 24 * nV), oTri = take(12 * nT), oVtx = take(vertexParent ? 0 : 32 * nV), oBounds = take(48);
     size_t oNormal = take(24 * nT), oScent = take(24 * (size_t)((nT + 31) / 32 * 32));
     size_t oKey = take(4 * nT), oKeyT = take(4 * nT), oOrd = take(4 * nT), oOrdT = take(4 * nT);
     size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad), oQbox = take(16 * (size_t)d.nTpad);
@@ -398,6 +400,13 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
     d.gridE = (uint32_t *)(b + oGridE);
     d.gridBigCount = (uint32_t *)(b + oGridBig);
     d.extentSum = (unsigned long long *)(d.gridBigCount + 8);
+    if (vertexParent) {
+        d.xyz = vertexParent->d.xyz;
+        d.vtx = vertexParent->d.vtx;
+        d.bounds = vertexParent->d.bounds;
+        d.sharedVtx = true;
+        m->grid3Wanted = false; // its third ray would need the whole parent (sb_shard.cu)
+    }
     if (nJobs) {
         d.triJob = (const uint16_t *)(b + oTriJob);
         d.nJobs = (uint32_t)nJobs;
@@ -877,6 +886,8 @@ int sb_mesh_build(sb_mesh *m)
         const int passes = std::min(4, (want + 7) / 8);
         m->d.sortBeginBit = std::max(0, 30 - 8 * passes);
     }
+    if (m->d.sharedVtx)
+        m->grid3Wanted = false;
     if ((m->d.gridAxes == 3) != m->grid3Wanted)
         m->gridSized = false; // the reference list was sized for another number of grids
     m->d.gridAxes = m->grid3Wanted ? 3 : 2;
@@ -2271,7 +2282,11 @@ static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh 
         c->lastCands += lane.h->stats[0]; // exact candidates
         if (!job.second) {
             c->lastRays += (unsigned long long)job.firstAxes * job.points + (job.firstAxes == 2 ? undecided : 0);
-            if (job.firstAxes == 2 && undecided && target->d.gridAxes == 2) {
+            if (job.firstAxes == 2 && undecided && target->d.sharedVtx) {
+                // a multi-GPU selection holds the part of the target the first two rays can meet; the third
+                // ray needs all of it: the caller (sb_shard_front_end) classifies against the whole meshes
+                c->shardUndecided += undecided;
+            } else if (job.firstAxes == 2 && undecided && target->d.gridAxes == 2) {
                 // the kernel could not trace the third ray (no third grid yet): it listed the points
                 job.firstScratch = job.scratch;
                 job.scratch = nullptr;
@@ -2487,8 +2502,9 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
         const ClassifyArgs &q = l == 1 ? qa : qb;
         if (q.end > q.begin && target->d.nT)
             r = classify_launch(c, lane, target, q, l == 1 ? ja : jb);
-        else if (q.end > q.begin) // empty target: nothing is inside it
-            cudaMemsetAsync(q.inside, 0, q.queryMesh->nT, lane.stream);
+        else if (q.end > q.begin && !q.queryMesh->origFace) // empty target: nothing is inside it
+            cudaMemsetAsync(q.inside, 0, q.queryMesh->nT, lane.stream); // (a multi-GPU selection writes its own faces only;
+                                                                        //  the caller's array starts out cleared)
     }
     // broad + narrow phase on the context stream meanwhile
     int ri = r ? r : sb_intersect_range(A, B, aBegin, aEnd, flags, out);
@@ -2518,6 +2534,213 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
 int sb_front_end(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
 {
     return sb_front_end_range(A, B, 0, A ? A->d.nT : 0, 0, B ? B->d.nT : 0, flags, out, d_insideA, d_insideB);
+}
+
+// ---- multi-GPU shards (sb_shard.cu) --------------------------------------------------------
+
+struct sb_shard {
+    sb_context *ctx = nullptr;
+    const sb_mesh *parent[2] = {nullptr, nullptr};
+    int rank = 0, n = 1;
+    void *arena = nullptr;
+    double *zinfo[2] = {nullptr, nullptr};
+    uint32_t *tiles[2] = {nullptr, nullptr};
+    uint32_t *hist = nullptr;
+    unsigned long long *tallest = nullptr;
+    double *cuts = nullptr;     // n + 2
+    uint32_t *totals = nullptr; // 2
+    void *hPinned = nullptr;    // [cuts: n + 2 doubles][totals: 2 words]
+    sb_mesh *sub[2] = {nullptr, nullptr};
+    uint32_t *face[2] = {nullptr, nullptr};
+    uint64_t fallbacks = 0;
+};
+
+int sb_shard_create(const sb_mesh *A, const sb_mesh *B, int rank, int n_ranks, sb_shard **out)
+{
+    if (!A || !B || !out)
+        return fail(SB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (A->ctx != B->ctx)
+        return fail(SB_ERR_INVALID, "meshes belong to different contexts");
+    if (n_ranks < 1 || n_ranks > 1000 || rank < 0 || rank >= n_ranks)
+        return fail(SB_ERR_INVALID, "rank %d of %d", rank, n_ranks);
+    if (A->d.triJob || B->d.triJob || A->d.sharedVtx || B->d.sharedVtx)
+        return fail(SB_ERR_INVALID, "shards are made of plain meshes");
+    sb_context *c = A->ctx;
+    DeviceGuard g(c->device);
+    sb_shard *s = new (std::nothrow) sb_shard;
+    if (!s)
+        return fail(SB_ERR_NOMEM, "out of host memory");
+    s->ctx = c;
+    s->parent[0] = A;
+    s->parent[1] = B;
+    s->rank = rank;
+    s->n = n_ranks;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align256(std::max<size_t>(bytes, 16));
+        return o;
+    };
+    size_t oZ[2], oT[2];
+    for (int k = 0; k < 2; ++k) {
+        oZ[k] = take(24 * (size_t)s->parent[k]->d.nT);
+        oT[k] = take(4 * (sbk_shard_tiles(s->parent[k]->d.nT) + 1));
+    }
+    const size_t oHist = take(4 * sbk_shard_hist_words()), oTall = take(8), oCuts = take(8 * ((size_t)n_ranks + 2)), oTot = take(8);
+    cudaError_t e = cudaMallocAsync(&s->arena, off, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMallocHost(&s->hPinned, 8 * ((size_t)n_ranks + 2) + 8);
+    if (e != cudaSuccess) {
+        if (s->arena)
+            cudaFreeAsync(s->arena, c->stream);
+        delete s;
+        return fail(e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, "shard scratch: %s", cudaGetErrorString(e));
+    }
+    memset(s->hPinned, 0, 8 * ((size_t)n_ranks + 2) + 8);
+    char *b = static_cast<char *>(s->arena);
+    for (int k = 0; k < 2; ++k) {
+        s->zinfo[k] = (double *)(b + oZ[k]);
+        s->tiles[k] = (uint32_t *)(b + oT[k]);
+    }
+    s->hist = (uint32_t *)(b + oHist);
+    s->tallest = (unsigned long long *)(b + oTall);
+    s->cuts = (double *)(b + oCuts);
+    s->totals = (uint32_t *)(b + oTot);
+    *out = s;
+    return SB_OK;
+}
+
+void sb_shard_destroy(sb_shard *s)
+{
+    if (!s)
+        return;
+    DeviceGuard g(s->ctx->device);
+    for (int k = 0; k < 2; ++k) {
+        if (s->sub[k])
+            sb_mesh_destroy(s->sub[k]);
+        if (s->face[k])
+            cudaFreeAsync(s->face[k], s->ctx->stream);
+    }
+    cudaFreeAsync(s->arena, s->ctx->stream);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFreeHost(s->hPinned);
+    delete s;
+}
+
+int sb_shard_info(const sb_shard *s, size_t *selected_a, size_t *selected_b, double *z_lo, double *z_hi, uint64_t *fallbacks)
+{
+    if (!s)
+        return fail(SB_ERR_INVALID, "shard is null");
+    if (selected_a)
+        *selected_a = s->sub[0] ? s->sub[0]->d.nT : 0;
+    if (selected_b)
+        *selected_b = s->sub[1] ? s->sub[1]->d.nT : 0;
+    const double *hc = static_cast<const double *>(s->hPinned);
+    if (z_lo)
+        *z_lo = hc[s->rank];
+    if (z_hi)
+        *z_hi = hc[s->rank + 1];
+    if (fallbacks)
+        *fallbacks = s->fallbacks;
+    return SB_OK;
+}
+
+int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
+{
+    if (!s || !out || !d_insideA || !d_insideB)
+        return fail(SB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    sb_context *c = s->ctx;
+    DeviceGuard g(c->device);
+    cudaStream_t st = c->stream;
+    const int n = s->n, rank = s->rank;
+    double *hCuts = static_cast<double *>(s->hPinned);
+    uint32_t *hTot = reinterpret_cast<uint32_t *>(hCuts + n + 2);
+    // ---- plan: padded vertices + bounds of the parents, z ranges, slab borders, selection sizes ----
+    {
+        StageTimer t(c, SB_STAGE_BUILD, st);
+        for (int k = 0; k < 2; ++k) {
+            sb_mesh *p = const_cast<sb_mesh *>(s->parent[k]);
+            use_mesh(c, p); // uploads (and earlier builds) of the parent happen on its own stream
+            SB_CUDA(sbk_bounds_pad(st, p->d, c->smCount, c->lc));
+        }
+        SB_CUDA(cudaMemsetAsync(s->hist, 0, 4 * sbk_shard_hist_words(), st));
+        SB_CUDA(cudaMemsetAsync(s->tallest, 0, 8, st));
+        for (int k = 0; k < 2; ++k)
+            SB_CUDA(sbk_shard_tri_z(st, s->parent[k]->d, s->parent[0]->d.bounds, s->parent[1]->d.bounds, s->zinfo[k], s->hist,
+                s->tallest, c->smCount, c->lc));
+        SB_CUDA(sbk_shard_plan(st, s->hist, s->parent[0]->d.bounds, s->parent[1]->d.bounds, s->tallest, n, s->cuts, c->lc));
+        for (int k = 0; k < 2; ++k)
+            SB_CUDA(sbk_shard_count(st, s->zinfo[k], s->parent[k]->d.nT, s->cuts, rank, n, s->tiles[k], s->totals + k, c->lc));
+    }
+    SB_CUDA(cudaMemcpyAsync(hCuts, s->cuts, 8 * ((size_t)n + 2), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(hTot, s->totals, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    // ---- the two selections: ordinary meshes over the chosen triangles ----
+    for (int k = 0; k < 2; ++k) {
+        const sb_mesh *p = s->parent[k];
+        const uint32_t want = hTot[k];
+        if (!s->sub[k] || s->sub[k]->d.nT != want) {
+            if (s->sub[k])
+                sb_mesh_destroy(s->sub[k]);
+            s->sub[k] = nullptr;
+            if (s->face[k])
+                cudaFreeAsync(s->face[k], st);
+            s->face[k] = nullptr;
+            int r = mesh_alloc(c, p->d.nV, want, &s->sub[k], 0, p);
+            if (r)
+                return r;
+            r = alloc_async(c, &s->face[k], std::max<uint32_t>(want, 1), nullptr);
+            if (r)
+                return r;
+        }
+        sb_mesh *m = s->sub[k];
+        m->d.origFace = s->face[k];
+        m->d.ownFilter = true;
+        m->d.ownLo = hCuts[rank];
+        m->d.ownHi = hCuts[rank + 1];
+        m->d.ownClosed = rank == n - 1;
+        {
+            StageTimer t(c, SB_STAGE_BUILD, st);
+            SB_CUDA(sbk_shard_emit(st, s->zinfo[k], p->d.tri, p->d.nT, s->cuts, rank, n, s->tiles[k], want, m->d.tri, s->face[k], c->lc));
+        }
+        int r = sb_mesh_build(m);
+        if (r)
+            return r;
+    }
+    // ---- front end over the selections; flags land at the parents' triangle ids ----
+    c->shardUndecided = 0;
+    int r = sb_front_end_range(s->sub[0], s->sub[1], 0, s->sub[0]->d.nT, 0, s->sub[1]->d.nT, flags, out, d_insideA, d_insideB);
+    if (r)
+        return r;
+    sb_isect *x = *out;
+    if (x->nHit)
+        SB_CUDA(sbk_shard_remap_hits(st, x->hitAB, (uint32_t)x->nHit, s->face[0], s->face[1], c->lc));
+    if (c->shardUndecided) {
+        // some points' first two votes disagree: their third ray (along z) leaves the slab.  Rare (C3: none):
+        // this rank's faces are classified again against the WHOLE meshes, built here on demand.
+        ++s->fallbacks;
+        sb_mesh *P[2] = {const_cast<sb_mesh *>(s->parent[0]), const_cast<sb_mesh *>(s->parent[1])};
+        for (int k = 0; k < 2 && !r; ++k) {
+            P[k]->d.ownFilter = false;
+            r = sb_mesh_build(P[k]);
+        }
+        for (int k = 0; k < 2 && !r; ++k) {
+            P[k]->d.ownFilter = true;
+            P[k]->d.ownLo = hCuts[rank];
+            P[k]->d.ownHi = hCuts[rank + 1];
+            P[k]->d.ownClosed = rank == n - 1;
+            r = sb_classify_faces_device(P[k], P[1 - k], 0, P[k]->d.nT, k == 0 ? d_insideA : d_insideB);
+            P[k]->d.ownFilter = false;
+        }
+        if (r) {
+            sb_isect_destroy(x);
+            *out = nullptr;
+            return r;
+        }
+    }
+    return SB_OK;
 }
 
 } // extern "C"

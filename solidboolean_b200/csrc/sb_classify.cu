@@ -518,6 +518,10 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
             outIndex = __ldg(q.sortedTri + idx);
             if (q.triJob)
                 job = q.triJob[outIndex];
+            if (q.ownMode && !(p.z >= q.ownLo && (q.ownMode == 2 ? p.z <= q.ownHi : p.z < q.ownHi)))
+                active = false; // another rank's face (sb_shard.cu)
+            if (q.origFace)
+                outIndex = __ldg(q.origFace + outIndex);
         } else {
             active = false; // padding of the sorted order
         }
@@ -609,6 +613,10 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     q.count = a.list ? a.listCount : a.end - a.begin;
     q.list = a.list;
     q.triJob = qm ? qm->triJob : nullptr;
+    q.origFace = qm ? qm->origFace : nullptr;
+    q.ownMode = qm && qm->ownFilter ? (qm->ownClosed ? 2 : 1) : 0;
+    q.ownLo = qm ? qm->ownLo : 0.0;
+    q.ownHi = qm ? qm->ownHi : 0.0;
     if (q.count == 0)
         return cudaSuccess;
     Target T;

@@ -67,6 +67,9 @@ struct Query {
     uint32_t count;            // points in this launch
     const uint32_t *list;      // optional: the launch's points as indices relative to `begin`
     const uint16_t *triJob;    // batch meshes (faces mode): job of each query face, or null
+    const uint32_t *origFace;  // multi-GPU selection (faces mode): query face -> the parent's triangle id (output index), or null
+    int ownMode;               // ... and only the faces with centroid z in [ownLo, ownHi) (2: <= ownHi) are classified
+    double ownLo, ownHi;
 };
 
 struct Out {

@@ -337,6 +337,10 @@ __global__ void __launch_bounds__(CT2, SB_CLS2_MINB) classify2_kernel(const __gr
             outIndex = __ldg(q.sortedTri + idx);
             if (q.triJob)
                 job = q.triJob[outIndex];
+            if (q.ownMode && !(p.z >= q.ownLo && (q.ownMode == 2 ? p.z <= q.ownHi : p.z < q.ownHi)))
+                active = false; // another rank's face (sb_shard.cu)
+            if (q.origFace)
+                outIndex = __ldg(q.origFace + outIndex);
         } else {
             active = false; // padding of the sorted order
         }
@@ -421,6 +425,10 @@ cudaError_t sbk_classify2(cudaStream_t s, const MeshDev &target, const ClassifyA
     q.count = a.end - a.begin;
     q.list = nullptr;
     q.triJob = qm ? qm->triJob : nullptr;
+    q.origFace = qm ? qm->origFace : nullptr;
+    q.ownMode = qm && qm->ownFilter ? (qm->ownClosed ? 2 : 1) : 0;
+    q.ownLo = qm ? qm->ownLo : 0.0;
+    q.ownHi = qm ? qm->ownHi : 0.0;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;

@@ -69,6 +69,14 @@ struct MeshDev {
     // translation that never touches the doubles: the job number leads the Morton key, the conservative float
     // boxes of the LBVH are shifted by latPitch x lattice3(job), the quantised coordinates of the ray grids by
     // lattice3(job) << 10.  Exact tests read the real coordinates.
+    // multi-GPU selection (sb_shard.cu): an ordinary mesh over the triangles a rank needs, sharing the parent's
+    // vertices; origFace maps its triangle numbers back; as a QUERY mesh only the faces whose centroid z lies
+    // in [ownLo, ownHi) (ownClosed: <= ownHi) take part -- each face of the parent belongs to one rank
+    bool sharedVtx = false;             // vtx / bounds belong to the parent (built there): the build skips them
+    const uint32_t *origFace = nullptr; // nT, ascending, or null
+    bool ownFilter = false;
+    double ownLo = 0.0, ownHi = 0.0;
+    bool ownClosed = false;
     const uint16_t *triJob = nullptr;   // nT: job of each triangle (original order), or null
     uint32_t nJobs = 0;
     double latPitch = 0.0;
@@ -133,6 +141,20 @@ cudaError_t sbk_cut_contexts(cudaStream_t s, const uint32_t *hitAB, const double
     uint32_t *scratch, uint32_t *radixWs, int smCount, uint32_t *cutTri /* n */, uint32_t *pointStart /* n + 1 */,
     double *points /* 6 n */, uint32_t *edgeStart /* n + 1 */, uint32_t *edges /* 2 n */, uint32_t *counts /* dev: 3 */,
     LaunchCounter &lc);
+
+// sb_shard.cu -- multi-GPU selection
+size_t sbk_shard_tiles(uint32_t nT);
+size_t sbk_shard_hist_words();
+cudaError_t sbk_shard_tri_z(cudaStream_t s, const MeshDev &m, const unsigned long long *boundsA, const unsigned long long *boundsB,
+    double *zinfo, uint32_t *hist, unsigned long long *tallest, int smCount, LaunchCounter &lc);
+cudaError_t sbk_shard_plan(cudaStream_t s, const uint32_t *hist, const unsigned long long *boundsA, const unsigned long long *boundsB,
+    const unsigned long long *tallest, int n, double *cuts /* n + 2 */, LaunchCounter &lc);
+cudaError_t sbk_shard_count(cudaStream_t s, const double *zinfo, uint32_t nT, const double *cuts, int rank, int n, uint32_t *tileCount,
+    uint32_t *total, LaunchCounter &lc);
+cudaError_t sbk_shard_emit(cudaStream_t s, const double *zinfo, const uint32_t *tri, uint32_t nT, const double *cuts, int rank, int n,
+    const uint32_t *tileStart, uint32_t cap, uint32_t *outTri, uint32_t *outFace, LaunchCounter &lc);
+cudaError_t sbk_shard_remap_hits(cudaStream_t s, uint32_t *ab, uint32_t n, const uint32_t *faceA, const uint32_t *faceB, LaunchCounter &lc);
+cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounter &lc);
 
 // sb_classify.cu
 struct ClassifyArgs {
