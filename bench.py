@@ -253,7 +253,7 @@ def config_dict(desc, name, nA, nB):
     """The same `config` object in both arms (the driver compares them)."""
     return {"workload": desc, "name": name, "tris_a": int(nA), "tris_b": int(nB),
             "l2": "512 MiB buffer written between timed steps (L2 flush)",
-            "parallelism": "A-range + query shards over the ranks, acceleration structures replicated"}
+            "parallelism": "N > 1: the faces of both meshes dealt to the ranks by centroid z, every rank builds only what its slab can meet"}
 
 
 def run_reference(args):
@@ -332,61 +332,52 @@ def run_ours(args):
     b0, b1 = cutsB[rank], cutsB[rank + 1]
 
     dev = torch.device("cuda", local)
-    # one buffer for both flag arrays: a single NCCL collective exchanges them
-    # (padded to whole 32-bit words: the collective sums int32 lanes -- every byte is written by exactly
-    # one rank, so no carry ever crosses a byte -- which NCCL reduces with its fast paths, unlike uint8)
-    flagsAB = torch.zeros((nA + nB + 15) // 16 * 16, dtype=torch.uint8, device=dev)
-    flagsAB32 = flagsAB.view(torch.int32)
-    flagsA, flagsB = flagsAB[:nA], flagsAB[nA:nA + nB]
-    assert flagsB.data_ptr() == flagsAB.data_ptr() + nA
+    # ONE buffer and ONE collective per step: [flags of A | flags of B | world x packed hit record].  Every byte
+    # is written by exactly one rank (a face belongs to one rank, a record slot to its rank) and starts
+    # out zero, so an all_reduce(sum) over int32 lanes IS the gather -- no carry ever crosses a byte.
+    flag_bytes = (nA + nB + 15) // 16 * 16
     l2_flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    hit_cap = [4096]  # padded hit capacity per rank; grows to fit (a retry costs one extra exchange)
+    xbuf = {}         # exchange buffer, re-made when the padding grows
+    gathered = {}
 
-    hit_cap = [4096]  # padded hit capacity per rank; grows to fit (a retry costs one extra gather)
-    xbuf = {}         # exchange buffers, reused from step to step (re-made when the padding grows)
+    def make_xbuf():
+        cap = hit_cap[0]
+        rec = (16 + 8 * cap + 48 * cap + 15) // 16 * 16       # header + int32[cap,2] + float64[cap,6]
+        buf = torch.zeros(flag_bytes + (world * rec if world > 1 else 0), dtype=torch.uint8, device=dev)
+        xbuf.update(cap=cap, rec=rec, buf=buf, buf32=buf.view(torch.int32), checked=None)
+        gathered["hits"] = buf[flag_bytes:]
+    make_xbuf()
+
+    def flags_views():
+        buf = xbuf["buf"]
+        return buf[:nA], buf[nA:nA + nB]
+    flagsA, flagsB = flags_views()
 
     def gather_results(x):
-        """NCCL exchange of the shard results: ONE all_gather of a packed
-        per-rank record {nCand, nHit, hit pairs, hit segments} straight from the library's
-        device buffers, and ONE all_reduce over both per-face flag arrays (every face is
-        classified by exactly one rank, so summing the byte masks is the gather).
-        No host round trip in the steady state: sb_isect_pack_device writes the record, and the
-        other ranks' counts are only read back (16 x world bytes) while the padding is still being
-        sized (the first steps) -- afterwards the caller reads them once, after the timed region."""
+        """The exchange of the shard results: sb_isect_pack_device writes this rank's record
+        {nCand, nHit, hit pairs, segments} straight from the library's device buffers into its slot, and one
+        NCCL all_reduce over the whole buffer hands every rank all flags and all records.  No host round
+        trip in the steady state: the counts are only read back while the padding is still being sized."""
         while True:
-            cap = hit_cap[0]
-            rec = 16 + 8 * cap + 48 * cap                     # header + int32[cap,2] + float64[cap,6]
-            if xbuf.get("cap") != cap:
-                xbuf.update(cap=cap, mine=torch.zeros(rec, dtype=torch.uint8, device=dev),
-                            everyone=torch.empty(world * rec, dtype=torch.uint8, device=dev))
-            mine, everyone = xbuf["mine"], xbuf["everyone"]
-            # header + hit pairs + segments straight from the library's device buffers (three async copies
-            # enqueued by one C call: the step is host-bound here, every Python-level op counts)
-            x.pack_device(mine.data_ptr(), cap)
-            dist.all_gather_into_tensor(everyone, mine)
-            if xbuf.get("checked") == cap:
-                # steady state (the same workload as the step that sized the padding, which
-                # left head room): no read-back -- and no rank-local decision, every rank
-                # must issue the same collectives; the counts stay on the device and the
-                # caller reads them after the timed region
+            cap, rec = xbuf["cap"], xbuf["rec"]
+            x.pack_device(xbuf["buf"].data_ptr() + flag_bytes + rank * rec, cap)
+            dist.all_reduce(xbuf["buf32"])
+            if xbuf["checked"] == cap:
                 break
-            # every rank must take the same decision: the maximum hit count decides
-            cnt = everyone.view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2)
-            cnt = cnt.cpu()
+            cnt = xbuf["buf"][flag_bytes:].view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2).cpu()
             if int(cnt[:, 1].max()) <= cap // 2:
                 xbuf["checked"] = cap
                 break
-            hit_cap[0] = int(cnt[:, 1].max()) * 3 + 64   # some rank is close to the padding: once more, with room
-        dist.all_reduce(flagsAB32)
-        gathered["hits"] = everyone
-        xbuf["rec"] = rec
-        return None, None                         # the counts are read from the gathered records after the timed region
-
-    gathered = {}
+            # some rank is close to the padding: once more, with room (every rank takes the same decision)
+            hit_cap[0] = int(cnt[:, 1].max()) * 3 + 64
+            return "again"
+        return None
 
     def gathered_counts():
         """Global (P, H, largest per-rank H) from the records of the last exchange (outside the timed region)."""
         rec = xbuf["rec"]
-        cnt = gathered["hits"].view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2).cpu()
+        cnt = xbuf["buf"][flag_bytes:].view(world, rec)[:, :16].contiguous().view(torch.int64).view(world, 2).cpu()
         return int(cnt[:, 0].sum()), int(cnt[:, 1].sum()), int(cnt[:, 1].max())
 
     # ---------------- resident loop: `value` ----------------
@@ -398,21 +389,30 @@ def run_ours(args):
     rays_cands = [0, 0]
     paths = [0, 0, 0, 0, 0]
 
+    shard = sb.Shard(ma, mb, rank, world) if world > 1 else None
+
     def resident_step():
         with torch.cuda.stream(ext):
-            if world > 1:
-                flagsAB.zero_()
-            ma.build(); mb.build()          # concurrent: each mesh builds on its own stream
-            # sb_front_end_range: intersection on the context stream, the two
-            # classification directions overlapped on internal streams
-            x = sb.Isect.front_end(ma, mb, flagsA.data_ptr(), flagsB.data_ptr(), a_range=(a0, a1), b_range=(b0, b1))
-            rays_cands[0], rays_cands[1] = ctx.classify_stats()
-            if world > 1:
-                P, H = gather_results(x)
-            else:
+            while True:
+                if world > 1:
+                    # sb_shard_front_end: this rank's slab of faces -- selection, build of the selected triangles
+                    # only, broad phase, predicate, both classifications; flags of its own faces into the zeroed buffer
+                    xbuf["buf"].zero_()
+                    fa, fb = flags_views()
+                    x = shard.front_end(fa.data_ptr(), fb.data_ptr())
+                else:
+                    ma.build(); mb.build()          # concurrent: each mesh builds on its own stream
+                    # sb_front_end: intersection on the context stream, the two
+                    # classification directions overlapped on internal streams
+                    x = sb.Isect.front_end(ma, mb, flagsA.data_ptr(), flagsB.data_ptr())
+                rays_cands[0], rays_cands[1] = ctx.classify_stats()
+                again = gather_results(x) if world > 1 else None
                 P, H = x.num_candidates, x.num_hits
-            paths[:] = x.path_counts()
-            x.close()
+                paths[:] = x.path_counts()
+                x.close()
+                if again is None:
+                    break
+                make_xbuf()                          # the padding grew: same step once more
         return P, H
 
     def timed_loop(step_fn, steps, warmup, device_timed):
@@ -462,7 +462,37 @@ def run_ours(args):
         stage_by_rank = [None] * world
         dist.all_gather_object(stage_by_rank, {k: round(v, 4) for k, v in stage_ms.items()})
     launches_per_step = launches / args.steps
+    flagsA, flagsB = flags_views()
     insideA, insideB = int(flagsA.sum().item()), int(flagsB.sum().item())
+    mg_parity, shard_info = None, None
+    if world > 1:
+        shard_info = [None] * world
+        dist.all_gather_object(shard_info, shard.info())
+        if rank == 0:
+            # the gathered bytes against the single-GPU output of the same run (outside the timed region)
+            rec = xbuf["rec"]
+            ev = gathered["hits"].view(world, rec).cpu().numpy()
+            parts_ab, parts_seg = [], []
+            for r in range(world):
+                nh = int(ev[r, 8:16].view(np.int64)[0])
+                parts_ab.append(ev[r, 16:16 + 8 * nh].view(np.uint32).reshape(-1, 2))
+                parts_seg.append(ev[r, 16 + 8 * hit_cap[0]:16 + 8 * hit_cap[0] + 48 * nh].view(np.float64).reshape(-1, 6))
+            gab, gseg = np.concatenate(parts_ab), np.concatenate(parts_seg)
+            order = np.lexsort((gab[:, 1], gab[:, 0]))
+            got_flags = xbuf["buf"][:nA + nB].cpu().numpy()
+            with torch.cuda.stream(ext):
+                ma.build(); mb.build()
+                one = torch.zeros(nA + nB, dtype=torch.uint8, device=dev)
+                x1 = sb.Isect.front_end(ma, mb, one.data_ptr(), one.data_ptr() + nA)
+                h1, s1 = x1.hits()
+                p1 = x1.num_candidates
+                x1.close()
+            mg_parity = {"what": "hit pairs + segments gathered from all ranks (sorted) and the summed per-face flags against the "
+                                 "single-GPU front end run by rank 0 in the same process",
+                         "candidate_pairs_equal": bool(p1 == P), "hit_pairs_identical": bool(np.array_equal(gab[order], h1)),
+                         "segments_bit_identical": bool(gseg[order].tobytes() == s1.tobytes()),
+                         "flags_identical": bool(np.array_equal(got_flags, one.cpu().numpy()))}
+            del one
     rays, cands = rays_cands
     if world > 1:
         rc = torch.tensor([rays, cands], dtype=torch.int64, device=dev)
@@ -477,31 +507,66 @@ def run_ours(args):
 
     host_hits = {}   # pinned landing buffers of the e2e loop, grown on demand
 
+    # N > 1: every rank uploads 1/N of the geometry bytes; the rest arrives over NVLink (one all_gather)
+    geo_sizes = [24 * nVA, 24 * nVB, 12 * nA, 12 * nB]
+    geo_off = [0, geo_sizes[0], geo_sizes[0] + geo_sizes[1], geo_sizes[0] + geo_sizes[1] + geo_sizes[2]]
+    geo_total = sum(geo_sizes)
+    geo_slice = ((geo_total + world - 1) // world + 255) // 256 * 256
+    geo_host = geo_dev = None
+    if world > 1:
+        geo_host = torch.zeros(geo_slice * world, dtype=torch.uint8).pin_memory()
+        for off, t in zip(geo_off, (pin[0], pin[2], pin[1], pin[3])):
+            flat = t.view(-1).view(torch.uint8)
+            geo_host[off:off + flat.numel()].copy_(flat)
+        geo_dev = torch.empty(geo_slice * world, dtype=torch.uint8, device=dev)
+
     def e2e_step():
         with torch.cuda.stream(ext):
-            # host buffers in through the C ABI: sb_mesh_upload (H2D) for both meshes first,
-            # so that B's copy overlaps A's build; then sb_mesh_build for each
-            xa = sb.Mesh.from_pointers(ctx, pin[0].data_ptr(), nVA, pin[1].data_ptr(), nA, build=False, keep=pin)
-            xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=False, keep=pin)
-            xa.build(); xb.build()
             if world > 1:
-                flagsAB.zero_()
-            x = sb.Isect.front_end(xa, xb, flagsA.data_ptr(), flagsB.data_ptr(), a_range=(a0, a1), b_range=(b0, b1))
-            if world > 1:
-                Pg, Hg = gather_results(x)
+                mine = geo_dev[rank * geo_slice:(rank + 1) * geo_slice]
+                mine.copy_(geo_host[rank * geo_slice:(rank + 1) * geo_slice], non_blocking=True)   # H2D of this rank's share
+                dist.all_gather_into_tensor(geo_dev, mine)
+                base = geo_dev.data_ptr()
+                # the step's geometry into the rank's two meshes (sb_mesh_update, device to device); the shard bound
+                # to them sizes its launches from the previous step and lets the device confirm the plan
+                ma.update(base + geo_off[0], base + geo_off[2], on_device=True)
+                mb.update(base + geo_off[1], base + geo_off[3], on_device=True)
+                xa = xb = sh = None
+                xbuf["buf"].zero_()
+                fa, fb = flags_views()
+                x = shard.front_end(fa.data_ptr(), fb.data_ptr())
+                assert gather_results(x) is None, "the hit padding was sized by the resident loop"
+                Pg, Hg = x.num_candidates, x.num_hits
             else:
+                # host buffers in through the C ABI: sb_mesh_upload (H2D) for both meshes first,
+                # so that B's copy overlaps A's build; then sb_mesh_build for each
+                xa = sb.Mesh.from_pointers(ctx, pin[0].data_ptr(), nVA, pin[1].data_ptr(), nA, build=False, keep=pin)
+                xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=False, keep=pin)
+                xa.build(); xb.build()
+                sh = None
+                fa, fb = flags_views()
+                x = sb.Isect.front_end(xa, xb, fa.data_ptr(), fb.data_ptr())
                 Pg, Hg = x.num_candidates, x.num_hits
             if rank == 0:  # results back to the host: per-face flags, hit pairs + segments -- all into PINNED
                 # buffers (the C ABI takes any host pointer; pageable ones make the copies staged and slow),
                 # flag copies enqueued first so that the one synchronisation inside sb_isect_hits covers all
-                out_in_a_t.copy_(flagsA, non_blocking=True)
-                out_in_b_t.copy_(flagsB, non_blocking=True)
+                out_in_a_t.copy_(fa, non_blocking=True)
+                out_in_b_t.copy_(fb, non_blocking=True)
                 if host_hits.get("cap", -1) < x.num_hits:
                     cap = x.num_hits * 3 // 2 + 64
                     host_hits.update(cap=cap, ab=torch.zeros(2 * cap, dtype=torch.int32).pin_memory(),
                                      seg=torch.zeros(6 * cap, dtype=torch.float64).pin_memory())
-                sb._check(x.lib.sb_isect_hits(x.h, host_hits["ab"].data_ptr(), host_hits["seg"].data_ptr()))
-            x.close(); xa.close(); xb.close()
+                if world > 1:
+                    # rank 0 reads every rank's record (hit pairs + segments) out of the gathered buffer
+                    if host_hits.get("rec") != xbuf["rec"] * world:
+                        host_hits.update(rec=xbuf["rec"] * world, all=torch.zeros(xbuf["rec"] * world, dtype=torch.uint8).pin_memory())
+                    host_hits["all"].copy_(gathered["hits"], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                else:
+                    sb._check(x.lib.sb_isect_hits(x.h, host_hits["ab"].data_ptr(), host_hits["seg"].data_ptr()))
+            x.close()
+            if xa is not None:
+                xa.close(); xb.close()
         return Pg, Hg
 
     ctx.enable_timing(False)
@@ -510,8 +575,8 @@ def run_ours(args):
         P2, H2, _ = gathered_counts()
     P2, H2 = int(P2), int(H2)
     sampler.stop()
-    h2d = 24 * (nVA + nVB) + 12 * (nA + nB)
-    d2h = (nA + nB) + 56 * H + 64
+    h2d = 24 * (nVA + nVB) + 12 * (nA + nB) if world == 1 else geo_slice   # per rank
+    d2h = (nA + nB) + 56 * H + 64 if world == 1 else (nA + nB) + xbuf["rec"] * world
 
     if rank == 0:
         peaks = {}
@@ -523,7 +588,7 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         # classification bytes = 25 Q + 104 nTarget + 108 C, both launches of a step
         # (N > 1: per GPU -- rank 0's own query shard and candidates against its own kernel time and ONE GPU's peak)
-        q_local = (a1 - a0) + (b1 - b0)
+        q_local = (a1 - a0) + (b1 - b0) if world == 1 else (nA + nB) // world
         cls_bytes = 25 * q_local + 104 * (nA + nB) + 108 * (cands if world > 1 else cands_total)
         cls_ms = stage_ms["classify"]
         traffic = None
@@ -545,6 +610,11 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(desc, args.config, nA, nB),
+            **({"multi_gpu": {"scheme": "faces dealt by centroid z (sb_shard_*): every rank selects and builds only the triangles its "
+                                        "slab can meet; one all_gather of the packed hit records + one all_reduce of the flag bytes",
+                              "shards": shard_info, "parity_vs_single_gpu": mg_parity,
+                              "e2e_upload": "each rank copies 1/N of the geometry bytes from pinned host memory, one all_gather over "
+                                            "NVLink hands everybody the rest"}} if world > 1 else {}),
             "front_end_ms": ms_step,
             "candidate_pairs": P, "intersecting_pairs": H, "inside_a": insideA, "inside_b": insideB,
             "candidate_pairs_per_s": P / (ms_step * 1e-3),
@@ -619,7 +689,10 @@ def run_ours(args):
     gathered.clear()
     host_hits.clear()
     xbuf.clear()
-    del out_in_a_t, out_in_b_t, flagsA, flagsB, flagsAB, flagsAB32, l2_flush, pin
+    if shard is not None:
+        shard.close()
+    del geo_host, geo_dev
+    del out_in_a_t, out_in_b_t, flagsA, flagsB, l2_flush, pin
     ma.close(); mb.close()
     torch.cuda.synchronize()
     if world > 1:

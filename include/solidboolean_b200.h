@@ -258,6 +258,18 @@ int sb_classify_faces(const sb_mesh *query, const sb_mesh *target,
 int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target,
                              size_t begin, size_t end, void *d_inside);
 
+/* sb_mesh_upload for geometry that already lives on this device (same layouts; e.g. gathered from the
+ * other ranks over NVLink): one device-to-device copy, ordered after the work enqueued on the context
+ * stream so far. */
+int sb_mesh_upload_device(sb_context *ctx, const void *d_xyz, size_t nV, const void *d_tri, size_t nT,
+                          sb_mesh **out);
+
+/* New coordinates (and / or index triples) of the SAME counts into an existing mesh -- the next frame of a
+ * deforming mesh, or the next of a stream of same-sized inputs; NULL leaves that array as it is.  on_device:
+ * the pointers are device pointers.  What was built from the old geometry is stale until sb_mesh_build;
+ * a shard bound to the mesh stays valid (its next sb_shard_front_end plans again if the slabs moved). */
+int sb_mesh_update(sb_mesh *m, const void *xyz, const void *tri, int on_device);
+
 /* ---- multi-GPU shards (north_star: "mesh A's query triangles shard naturally") ---------
  * One process per GPU.  Every rank uploads (or receives) the geometry of both meshes -- sb_mesh_upload,
  * no build -- and makes a shard for its rank.  sb_shard_front_end then does the rank's share of one
@@ -328,7 +340,8 @@ enum {
     SB_STAGE_PREDICATE = 4,/* the tri/tri predicate kernel alone (FP64 roofline) */
     SB_STAGE_HALFEDGE = 5, /* uncut-triangle compaction, half-edge sort, adjacency, face groups */
     SB_STAGE_CONTEXTS = 6, /* per-triangle intersection contexts */
-    SB_STAGE_COUNT = 7
+    SB_STAGE_SHARD = 7,    /* multi-GPU: padded vertices / bounds of the parents, slab plan, selection */
+    SB_STAGE_COUNT = 8
 };
 int sb_context_enable_timing(sb_context *ctx, int enable);
 int sb_context_reset_timing(sb_context *ctx);

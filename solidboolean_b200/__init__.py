@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(HERE, "lib", "libsolidboolean_b200.so")  # override: dev builds
 
-STAGES = ("build", "broad", "narrow", "classify", "predicate", "halfedge", "contexts")
+STAGES = ("build", "broad", "narrow", "classify", "predicate", "halfedge", "contexts", "shard")
 ISECT_NO_SORT = 1
 
 
@@ -59,6 +59,8 @@ ABI = {
     "sb_shard_info": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_uint64)]),
     "sb_shard_destroy": (None, [_vp]),
+    "sb_mesh_upload_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_vp)]),
+    "sb_mesh_update": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "sb_mesh_build": (C.c_int, [_vp]),
     "sb_mesh_destroy": (None, [_vp]),
     "sb_mesh_num_triangles": (_sz, [_vp]),
@@ -233,6 +235,18 @@ class Mesh:
         return self
 
     @classmethod
+    def from_device(cls, ctx: Context, d_xyz: int, nV: int, d_tri: int, nT: int, keep=None):
+        """sb_mesh_upload_device: geometry already on this device (no build)."""
+        self = cls.__new__(cls)
+        self.ctx, self.lib = ctx, ctx.lib
+        self.xyz = self.tri = None
+        self._keep = keep
+        h = _vp()
+        _check(self.lib.sb_mesh_upload_device(ctx.h, _vp(d_xyz), nV, _vp(d_tri), nT, C.byref(h)))
+        self.h = h
+        return self
+
+    @classmethod
     def batch(cls, ctx: Context, jobs, lattice_pitch: float, build=True):
         """sb_batch_upload: `jobs` = sequence of (xyz, tri) small meshes (job-local indices), laid end to
         end into ONE batch mesh.  lattice_pitch >= 4 x the largest |coordinate| of both batches of a pair
@@ -261,6 +275,11 @@ class Mesh:
             self.build()
             ctx.synchronize()
         return self
+
+    def update(self, xyz_ptr: int, tri_ptr: int, on_device=False):
+        """sb_mesh_update: same-sized geometry into this mesh (raw pointers; 0 = keep)."""
+        _check(self.lib.sb_mesh_update(self.h, _vp(xyz_ptr) if xyz_ptr else None, _vp(tri_ptr) if tri_ptr else None,
+                                       1 if on_device else 0))
 
     def build(self):
         _check(self.lib.sb_mesh_build(self.h))

@@ -24,7 +24,7 @@ static_assert(K == 1 || K == 2 || K == 4 || K == 8 || K == 16 || K == 32, "clust
 
 // ---- K2 ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bounds_pad_kernel(const double *__restrict__ xyz, uint32_t nV,
-    double4 *__restrict__ vtx, unsigned long long *__restrict__ bounds)
+    double4 *__restrict__ vtx, unsigned long long *__restrict__ bounds, float2 *__restrict__ zf)
 {
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nV; i += gridDim.x * blockDim.x) {
@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) bounds_pad_kernel(const double *__restric
         double2 *o = reinterpret_cast<double2 *>(vtx + i);
         o[0] = make_double2(x, y);
         o[1] = make_double2(z, 0.0);
+        if (zf) // multi-GPU planning (sb_shard.cu): z as a float bracket, a table dense enough to stay in cache
+            zf[i] = make_float2(__double2float_rd(z), __double2float_ru(z));
         lo[0] = fmin(lo[0], x); hi[0] = fmax(hi[0], x);
         lo[1] = fmin(lo[1], y); hi[1] = fmax(hi[1], y);
         lo[2] = fmin(lo[2], z); hi[2] = fmax(hi[2], z);
@@ -352,7 +354,7 @@ cudaError_t sbk_triangle_boxes(cudaStream_t s, const MeshDev &m, double2 *out, L
 size_t sbk_radix_workspace_words(size_t n) { return sbradix::Workspace::words(sbradix::tiles_for(n)); }
 
 // whole-mesh box + padded vertex copy (K2)
-cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounter &lc)
+cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounter &lc, float2 *zf)
 {
     // bounds seeds: min slots all-ones, max slots zero (order-encoded doubles)
     cudaMemsetAsync(m.bounds, 0xff, 3 * sizeof(unsigned long long), s);
@@ -362,7 +364,7 @@ cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounte
         vb = smCount * 8;
     if (vb < 1)
         vb = 1;
-    bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds);
+    bounds_pad_kernel<<<vb, 256, 0, s>>>(m.xyz, m.nV, m.vtx, m.bounds, zf);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -76,7 +76,7 @@ struct sb_context {
     };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> freeEvents;
-    float acc[SB_STAGE_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    float acc[SB_STAGE_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t t0 = nullptr;      // timing reference (recorded at reset)
     cudaEvent_t orderEvent = nullptr; // orders per-mesh streams behind the context stream
     // scratch
@@ -105,6 +105,7 @@ struct sb_context {
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
     int sortBeginBit = -1;           // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT); -1 = by mesh size
     uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
+    std::vector<void *> shardPinned;  // pinned read-back blocks of destroyed shards, reused (cudaMallocHost is slow)
     uint64_t shardUndecided = 0;     // points of a multi-GPU selection whose first two votes disagreed (need the whole target)
     bool classifyBalanced = true;    // SB_CLASSIFY_V2=0: every launch uses the general kernel (sb_classify.cu)
     bool useGraphs = true;           // SB_GRAPHS=0: rebuilds enqueue their kernels one by one
@@ -528,6 +529,8 @@ void sb_context_destroy(sb_context *c)
     cudaFree(c->dScalars);
     cudaFreeHost(c->hScalars);
     cudaFreeHost(c->hPool);
+    for (void *q : c->shardPinned)
+        cudaFreeHost(q);
     for (int l = 0; l < 3; ++l) {
         if (l && c->lanes[l].stream) {
             cudaStreamSynchronize(c->lanes[l].stream);
@@ -673,6 +676,62 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
         return fail(SB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
     }
     *out = m;
+    return SB_OK;
+}
+
+// geometry that is already on the device (e.g. received from another GPU): copied into the mesh on its stream,
+// ordered after everything the caller has enqueued on the context stream so far
+int sb_mesh_upload_device(sb_context *ctx, const void *d_xyz, size_t nV, const void *d_tri, size_t nT, sb_mesh **out)
+{
+    if (!ctx || !out)
+        return fail(SB_ERR_INVALID, "null context or out");
+    *out = nullptr;
+    if ((nV && !d_xyz) || (nT && !d_tri))
+        return fail(SB_ERR_INVALID, "null geometry pointer");
+    if (nT && !nV)
+        return fail(SB_ERR_INVALID, "triangles without vertices");
+    DeviceGuard g(ctx->device);
+    sb_mesh *m = nullptr;
+    int r = mesh_alloc(ctx, nV, nT, &m); // (the mesh stream waits for the context stream here)
+    if (r)
+        return r;
+    cudaError_t e = cudaSuccess;
+    if (nV)
+        e = cudaMemcpyAsync(m->d.xyz, d_xyz, 24 * nV, cudaMemcpyDeviceToDevice, m->stream);
+    if (e == cudaSuccess && nT)
+        e = cudaMemcpyAsync(m->d.tri, d_tri, 12 * nT, cudaMemcpyDeviceToDevice, m->stream);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(m->ready, m->stream);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(m->leafReady, m->stream);
+    if (e != cudaSuccess) {
+        sb_mesh_destroy(m);
+        return fail(SB_ERR_CUDA, "device upload: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return SB_OK;
+}
+
+// new coordinates / index triples of the SAME sizes into an existing mesh (a deforming mesh, or the next frame of
+// a stream of same-sized inputs): everything built from the old geometry is stale until the next sb_mesh_build
+int sb_mesh_update(sb_mesh *m, const void *xyz, const void *tri, int on_device)
+{
+    if (!m)
+        return fail(SB_ERR_INVALID, "mesh is null");
+    if (m->d.triJob || m->d.sharedVtx)
+        return fail(SB_ERR_INVALID, "only plain meshes can be updated");
+    sb_context *c = m->ctx;
+    DeviceGuard g(c->device);
+    order_after_context(c, m);
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (xyz && m->d.nV)
+        SB_CUDA(cudaMemcpyAsync(m->d.xyz, xyz, 24 * (size_t)m->d.nV, kind, m->stream));
+    if (tri && m->d.nT)
+        SB_CUDA(cudaMemcpyAsync(m->d.tri, tri, 12 * (size_t)m->d.nT, kind, m->stream));
+    m->built = false;
+    m->gridPending = false;
+    SB_CUDA(cudaEventRecord(m->ready, m->stream));
+    SB_CUDA(cudaEventRecord(m->leafReady, m->stream));
     return SB_OK;
 }
 
@@ -2543,16 +2602,22 @@ struct sb_shard {
     const sb_mesh *parent[2] = {nullptr, nullptr};
     int rank = 0, n = 1;
     void *arena = nullptr;
-    double *zinfo[2] = {nullptr, nullptr};
+    float2 *zr[2] = {nullptr, nullptr};  // per triangle: box z range (floats rounded outwards)
+    float2 *zf[2] = {nullptr, nullptr};  // per vertex: z rounded down / up
     uint32_t *tiles[2] = {nullptr, nullptr};
-    uint32_t *hist = nullptr;
-    unsigned long long *tallest = nullptr;
+    uint32_t *hist = nullptr;   // histogram + tallest box
     double *cuts = nullptr;     // n + 2
-    uint32_t *totals = nullptr; // 2
-    void *hPinned = nullptr;    // [cuts: n + 2 doubles][totals: 2 words]
+    uint32_t *totals = nullptr; // [selection sizes: 2][mismatch flag]
+    void *hPinned = nullptr;    // [cuts: n + 2 doubles][totals: 2 words][mismatch]
     sb_mesh *sub[2] = {nullptr, nullptr};
     uint32_t *face[2] = {nullptr, nullptr};
-    uint64_t fallbacks = 0;
+    cudaEvent_t padded[2] = {nullptr, nullptr};
+    // what the last completed call found: a repeated call over the same geometry sizes its launches from it
+    // and lets the device confirm (no host round trip in the middle of the step)
+    bool planValid = false;
+    std::vector<double> lastCuts;
+    uint32_t lastTotals[2] = {0, 0};
+    uint64_t fallbacks = 0, replans = 0;
 };
 
 int sb_shard_create(const sb_mesh *A, const sb_mesh *B, int rank, int n_ranks, sb_shard **out)
@@ -2582,29 +2647,44 @@ int sb_shard_create(const sb_mesh *A, const sb_mesh *B, int rank, int n_ranks, s
         off += align256(std::max<size_t>(bytes, 16));
         return o;
     };
-    size_t oZ[2], oT[2];
+    size_t oZ[2], oT[2], oF[2];
     for (int k = 0; k < 2; ++k) {
-        oZ[k] = take(24 * (size_t)s->parent[k]->d.nT);
+        oF[k] = take(8 * (size_t)s->parent[k]->d.nV);
+        oZ[k] = take(8 * (size_t)s->parent[k]->d.nT);
         oT[k] = take(4 * (sbk_shard_tiles(s->parent[k]->d.nT) + 1));
     }
-    const size_t oHist = take(4 * sbk_shard_hist_words()), oTall = take(8), oCuts = take(8 * ((size_t)n_ranks + 2)), oTot = take(8);
+    const size_t oHist = take(4 * sbk_shard_hist_words() + 8), oCuts = take(8 * ((size_t)n_ranks + 2)), oTot = take(16);
+    const size_t pinnedBytes = 8 * (1000 + 2) + 16; // (n_ranks <= 1000: one size, so that the blocks can be reused)
     cudaError_t e = cudaMallocAsync(&s->arena, off, c->stream);
-    if (e == cudaSuccess)
-        e = cudaMallocHost(&s->hPinned, 8 * ((size_t)n_ranks + 2) + 8);
+    if (e == cudaSuccess) {
+        if (!c->shardPinned.empty()) {
+            s->hPinned = c->shardPinned.back();
+            c->shardPinned.pop_back();
+        } else {
+            e = cudaMallocHost(&s->hPinned, pinnedBytes);
+        }
+    }
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+        e = cudaEventCreateWithFlags(&s->padded[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         if (s->arena)
             cudaFreeAsync(s->arena, c->stream);
+        if (s->hPinned)
+            cudaFreeHost(s->hPinned);
+        for (int k = 0; k < 2; ++k)
+            if (s->padded[k])
+                cudaEventDestroy(s->padded[k]);
         delete s;
         return fail(e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA, "shard scratch: %s", cudaGetErrorString(e));
     }
-    memset(s->hPinned, 0, 8 * ((size_t)n_ranks + 2) + 8);
+    memset(s->hPinned, 0, pinnedBytes);
     char *b = static_cast<char *>(s->arena);
     for (int k = 0; k < 2; ++k) {
-        s->zinfo[k] = (double *)(b + oZ[k]);
+        s->zr[k] = (float2 *)(b + oZ[k]);
+        s->zf[k] = (float2 *)(b + oF[k]);
         s->tiles[k] = (uint32_t *)(b + oT[k]);
     }
     s->hist = (uint32_t *)(b + oHist);
-    s->tallest = (unsigned long long *)(b + oTall);
     s->cuts = (double *)(b + oCuts);
     s->totals = (uint32_t *)(b + oTot);
     *out = s;
@@ -2623,8 +2703,10 @@ void sb_shard_destroy(sb_shard *s)
             cudaFreeAsync(s->face[k], s->ctx->stream);
     }
     cudaFreeAsync(s->arena, s->ctx->stream);
-    cudaStreamSynchronize(s->ctx->stream);
-    cudaFreeHost(s->hPinned);
+    cudaStreamSynchronize(s->ctx->stream); // the read-backs into the pinned block are done
+    s->ctx->shardPinned.push_back(s->hPinned);
+    for (int k = 0; k < 2; ++k)
+        cudaEventDestroy(s->padded[k]);
     delete s;
 }
 
@@ -2636,51 +2718,58 @@ int sb_shard_info(const sb_shard *s, size_t *selected_a, size_t *selected_b, dou
         *selected_a = s->sub[0] ? s->sub[0]->d.nT : 0;
     if (selected_b)
         *selected_b = s->sub[1] ? s->sub[1]->d.nT : 0;
-    const double *hc = static_cast<const double *>(s->hPinned);
     if (z_lo)
-        *z_lo = hc[s->rank];
+        *z_lo = s->planValid ? s->lastCuts[s->rank] : 0.0;
     if (z_hi)
-        *z_hi = hc[s->rank + 1];
+        *z_hi = s->planValid ? s->lastCuts[s->rank + 1] : 0.0;
     if (fallbacks)
         *fallbacks = s->fallbacks;
     return SB_OK;
 }
 
-int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
+// one attempt: speculative = sizes and slab borders of the last call, confirmed by the device afterwards
+static int shard_attempt(sb_shard *s, bool speculative, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB, bool *confirmed)
 {
-    if (!s || !out || !d_insideA || !d_insideB)
-        return fail(SB_ERR_INVALID, "null argument");
-    *out = nullptr;
     sb_context *c = s->ctx;
-    DeviceGuard g(c->device);
     cudaStream_t st = c->stream;
     const int n = s->n, rank = s->rank;
     double *hCuts = static_cast<double *>(s->hPinned);
     uint32_t *hTot = reinterpret_cast<uint32_t *>(hCuts + n + 2);
-    // ---- plan: padded vertices + bounds of the parents, z ranges, slab borders, selection sizes ----
+    const MeshDev &A = s->parent[0]->d, &B = s->parent[1]->d;
+    *confirmed = true;
+    // ---- plan: padded vertices + bounds of the parents (each on its own stream), z ranges, slab borders, sizes ----
     {
-        StageTimer t(c, SB_STAGE_BUILD, st);
         for (int k = 0; k < 2; ++k) {
             sb_mesh *p = const_cast<sb_mesh *>(s->parent[k]);
-            use_mesh(c, p); // uploads (and earlier builds) of the parent happen on its own stream
-            SB_CUDA(sbk_bounds_pad(st, p->d, c->smCount, c->lc));
+            order_after_context(c, p);
+            {
+                StageTimer t(c, SB_STAGE_SHARD, p->stream);
+                SB_CUDA(sbk_bounds_pad(p->stream, p->d, c->smCount, c->lc, s->zf[k]));
+            }
+            SB_CUDA(cudaEventRecord(s->padded[k], p->stream));
         }
-        SB_CUDA(cudaMemsetAsync(s->hist, 0, 4 * sbk_shard_hist_words(), st));
-        SB_CUDA(cudaMemsetAsync(s->tallest, 0, 8, st));
         for (int k = 0; k < 2; ++k)
-            SB_CUDA(sbk_shard_tri_z(st, s->parent[k]->d, s->parent[0]->d.bounds, s->parent[1]->d.bounds, s->zinfo[k], s->hist,
-                s->tallest, c->smCount, c->lc));
-        SB_CUDA(sbk_shard_plan(st, s->hist, s->parent[0]->d.bounds, s->parent[1]->d.bounds, s->tallest, n, s->cuts, c->lc));
-        for (int k = 0; k < 2; ++k)
-            SB_CUDA(sbk_shard_count(st, s->zinfo[k], s->parent[k]->d.nT, s->cuts, rank, n, s->tiles[k], s->totals + k, c->lc));
+            SB_CUDA(cudaStreamWaitEvent(st, s->padded[k], 0));
+        StageTimer t(c, SB_STAGE_SHARD, st);
+        SB_CUDA(sbk_shard_plan(st, A, B, s->zf, s->zr, s->tiles, s->hist, n, s->cuts, c->smCount, c->lc));
+        SB_CUDA(cudaMemsetAsync(s->totals, 0, 12, st));
+        SB_CUDA(sbk_shard_count(st, A, B, s->zr, s->tiles, s->cuts, rank, n, s->totals, speculative ? s->lastTotals : nullptr,
+            s->totals + 2, c->lc));
     }
     SB_CUDA(cudaMemcpyAsync(hCuts, s->cuts, 8 * ((size_t)n + 2), cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaMemcpyAsync(hTot, s->totals, 8, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CUDA(cudaMemcpyAsync(hTot, s->totals, 12, cudaMemcpyDeviceToHost, st));
+    if (!speculative) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        s->lastCuts.assign(hCuts, hCuts + n + 2);
+        s->lastTotals[0] = hTot[0];
+        s->lastTotals[1] = hTot[1];
+        s->planValid = true;
+    }
     // ---- the two selections: ordinary meshes over the chosen triangles ----
+    uint32_t *outTri[2], *outFace[2];
     for (int k = 0; k < 2; ++k) {
         const sb_mesh *p = s->parent[k];
-        const uint32_t want = hTot[k];
+        const uint32_t want = s->lastTotals[k];
         if (!s->sub[k] || s->sub[k]->d.nT != want) {
             if (s->sub[k])
                 sb_mesh_destroy(s->sub[k]);
@@ -2698,14 +2787,18 @@ int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insi
         sb_mesh *m = s->sub[k];
         m->d.origFace = s->face[k];
         m->d.ownFilter = true;
-        m->d.ownLo = hCuts[rank];
-        m->d.ownHi = hCuts[rank + 1];
+        m->d.ownLo = s->lastCuts[rank];
+        m->d.ownHi = s->lastCuts[rank + 1];
         m->d.ownClosed = rank == n - 1;
-        {
-            StageTimer t(c, SB_STAGE_BUILD, st);
-            SB_CUDA(sbk_shard_emit(st, s->zinfo[k], p->d.tri, p->d.nT, s->cuts, rank, n, s->tiles[k], want, m->d.tri, s->face[k], c->lc));
-        }
-        int r = sb_mesh_build(m);
+        outTri[k] = m->d.tri;
+        outFace[k] = s->face[k];
+    }
+    {
+        StageTimer t(c, SB_STAGE_SHARD, st);
+        SB_CUDA(sbk_shard_emit(st, A, B, s->zr, s->tiles, s->cuts, rank, n, s->lastTotals, outTri, outFace, c->lc));
+    }
+    for (int k = 0; k < 2; ++k) {
+        int r = sb_mesh_build(s->sub[k]);
         if (r)
             return r;
     }
@@ -2715,8 +2808,41 @@ int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insi
     if (r)
         return r;
     sb_isect *x = *out;
+    if (speculative) {
+        // the front end has waited for the context stream since the copies above were enqueued
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (hTot[2] || memcmp(hCuts, s->lastCuts.data(), 8 * ((size_t)n + 2)) != 0) {
+            *confirmed = false; // the geometry changed under the same handles: plan again, for real
+            sb_isect_destroy(x);
+            *out = nullptr;
+            return SB_OK;
+        }
+    }
     if (x->nHit)
         SB_CUDA(sbk_shard_remap_hits(st, x->hitAB, (uint32_t)x->nHit, s->face[0], s->face[1], c->lc));
+    return SB_OK;
+}
+
+int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
+{
+    if (!s || !out || !d_insideA || !d_insideB)
+        return fail(SB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    sb_context *c = s->ctx;
+    DeviceGuard g(c->device);
+    const int n = s->n, rank = s->rank;
+    bool confirmed = true;
+    const bool speculate = s->planValid && s->sub[0] && s->sub[1] && !getenv("SB_SHARD_NO_SPECULATION");
+    int r = shard_attempt(s, speculate, flags, out, d_insideA, d_insideB, &confirmed);
+    if (!r && !confirmed) {
+        ++s->replans;
+        // (flags the discarded attempt wrote for faces that are not this rank's any more are the caller's to clear:
+        //  the arrays are zeroed per step; a changed plan under unchanged handles means the caller rewrote the geometry)
+        r = shard_attempt(s, false, flags, out, d_insideA, d_insideB, &confirmed);
+    }
+    if (r)
+        return r;
+    sb_isect *x = *out;
     if (c->shardUndecided) {
         // some points' first two votes disagree: their third ray (along z) leaves the slab.  Rare (C3: none):
         // this rank's faces are classified again against the WHOLE meshes, built here on demand.
@@ -2728,8 +2854,8 @@ int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insi
         }
         for (int k = 0; k < 2 && !r; ++k) {
             P[k]->d.ownFilter = true;
-            P[k]->d.ownLo = hCuts[rank];
-            P[k]->d.ownHi = hCuts[rank + 1];
+            P[k]->d.ownLo = s->lastCuts[rank];
+            P[k]->d.ownHi = s->lastCuts[rank + 1];
             P[k]->d.ownClosed = rank == n - 1;
             r = sb_classify_faces_device(P[k], P[1 - k], 0, P[k]->d.nT, k == 0 ? d_insideA : d_insideB);
             P[k]->d.ownFilter = false;

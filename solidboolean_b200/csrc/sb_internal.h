@@ -142,19 +142,18 @@ cudaError_t sbk_cut_contexts(cudaStream_t s, const uint32_t *hitAB, const double
     double *points /* 6 n */, uint32_t *edgeStart /* n + 1 */, uint32_t *edges /* 2 n */, uint32_t *counts /* dev: 3 */,
     LaunchCounter &lc);
 
-// sb_shard.cu -- multi-GPU selection
+// sb_shard.cu -- multi-GPU selection (every pass covers both parents in one launch)
 size_t sbk_shard_tiles(uint32_t nT);
 size_t sbk_shard_hist_words();
-cudaError_t sbk_shard_tri_z(cudaStream_t s, const MeshDev &m, const unsigned long long *boundsA, const unsigned long long *boundsB,
-    double *zinfo, uint32_t *hist, unsigned long long *tallest, int smCount, LaunchCounter &lc);
-cudaError_t sbk_shard_plan(cudaStream_t s, const uint32_t *hist, const unsigned long long *boundsA, const unsigned long long *boundsB,
-    const unsigned long long *tallest, int n, double *cuts /* n + 2 */, LaunchCounter &lc);
-cudaError_t sbk_shard_count(cudaStream_t s, const double *zinfo, uint32_t nT, const double *cuts, int rank, int n, uint32_t *tileCount,
-    uint32_t *total, LaunchCounter &lc);
-cudaError_t sbk_shard_emit(cudaStream_t s, const double *zinfo, const uint32_t *tri, uint32_t nT, const double *cuts, int rank, int n,
-    const uint32_t *tileStart, uint32_t cap, uint32_t *outTri, uint32_t *outFace, LaunchCounter &lc);
+cudaError_t sbk_shard_plan(cudaStream_t s, const MeshDev &A, const MeshDev &B, float2 *const zf[2] /* per vertex, from sbk_bounds_pad */,
+    float2 *const zr[2], uint32_t *const tiles[2], uint32_t *hist, int n, double *cuts /* n + 2 */, int smCount, LaunchCounter &lc);
+cudaError_t sbk_shard_count(cudaStream_t s, const MeshDev &A, const MeshDev &B, float2 *const zr[2], uint32_t *const tiles[2],
+    const double *cuts, int rank, int n, uint32_t *totals, const uint32_t *expect, uint32_t *mismatch, LaunchCounter &lc);
+cudaError_t sbk_shard_emit(cudaStream_t s, const MeshDev &A, const MeshDev &B, float2 *const zr[2], uint32_t *const tiles[2],
+    const double *cuts, int rank, int n, const uint32_t cap[2], uint32_t *const outTri[2], uint32_t *const outFace[2],
+    LaunchCounter &lc);
 cudaError_t sbk_shard_remap_hits(cudaStream_t s, uint32_t *ab, uint32_t n, const uint32_t *faceA, const uint32_t *faceB, LaunchCounter &lc);
-cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounter &lc);
+cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounter &lc, float2 *zf = nullptr /* nV, optional */);
 
 // sb_classify.cu
 struct ClassifyArgs {
