@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 }
 
 __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
-    uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double *__restrict__ normal,
+    uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double4 *__restrict__ nrm4,
     uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
     unsigned long long *__restrict__ extentSum, const uint16_t *__restrict__ triJob)
 {
@@ -129,9 +129,8 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
     d3 n = {0.0, 0.0, 0.0};
     if (!(fabs(len) <= 2.2204460492503131e-16))
         n = {xdiv(cr.x, len), xdiv(cr.y, len), xdiv(cr.z, len)};
-    normal[3 * (size_t)i] = n.x;
-    normal[3 * (size_t)i + 1] = n.y;
-    normal[3 * (size_t)i + 2] = n.z;
+    stg256(nrm4 + i, n.x, n.y, n.z,
+        __longlong_as_double((long long)(nV <= (1u << SB_PACKED_IDX_BITS) ? pack_tri_idx(i0, i1, i2) : SB_PACKED_IDX_NONE)));
     // 30-bit Morton key of the box centre inside the mesh box (ordering only)
     double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
     double ex = dkey_inv(bounds[3]) - blx, ey = dkey_inv(bounds[4]) - bly, ez = dkey_inv(bounds[5]) - blz;
@@ -380,7 +379,7 @@ cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int sm
             return eb;
         lc.kernels -= 1;
     }
-    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.normal, m.mkey, m.order, m.err,
+    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.nrm4, m.mkey, m.order, m.err,
         m.extentSum, m.triJob);
     lc.kernels += 2;
     sbradix::Workspace ws;

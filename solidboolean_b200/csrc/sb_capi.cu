@@ -352,7 +352,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
     };
     // (a multi-GPU selection reads the vertices, padded vertices and bounds of its parent)
     size_t oXyz = take(vertexParent ? 0 : 24 * nV), oTri = take(12 * nT), oVtx = take(vertexParent ? 0 : 32 * nV), oBounds = take(48);
-    size_t oNormal = take(24 * nT), oScent = take(24 * (size_t)((nT + 31) / 32 * 32));
+    size_t oNormal = take(32 * nT), oScent = take(24 * (size_t)((nT + 31) / 32 * 32));
     size_t oKey = take(4 * nT), oKeyT = take(4 * nT), oOrd = take(4 * nT), oOrdT = take(4 * nT);
     size_t oLeaf = take(32 * (size_t)d.nTpad), oSbox = take(48 * (size_t)d.nTpad), oQbox = take(16 * (size_t)d.nTpad);
     size_t oCbox = take(32 * (size_t)d.M), oCkey = take(4 * (size_t)d.M + 4);
@@ -382,7 +382,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
     d.tri = (uint32_t *)(b + oTri);
     d.vtx = (double4 *)(b + oVtx);
     d.bounds = (unsigned long long *)(b + oBounds);
-    d.normal = (double *)(b + oNormal);
+    d.nrm4 = (double4 *)(b + oNormal);
     d.scent = (double *)(b + oScent);
     d.mkey = (uint32_t *)(b + oKey);
     d.mkeyTmp = (uint32_t *)(b + oKeyT);
@@ -1185,7 +1185,25 @@ static int mesh_download(const sb_mesh *m, void *dst, const void *src, size_t by
     return SB_OK;
 }
 
-int sb_mesh_normals(const sb_mesh *m, double *out) { return mesh_download(m, out, m ? m->d.normal : nullptr, m ? 24 * (size_t)m->d.nT : 0); }
+// The device keeps the normals in 32-byte records (normal + packed vertex indices, sb_common.cuh): a strided copy drops the fourth word.
+int sb_mesh_normals(const sb_mesh *m, double *out)
+{
+    if (!m || !out)
+        return fail(SB_ERR_INVALID, "null mesh or output");
+    if (!m->built)
+        return fail(SB_ERR_INVALID, "mesh not built");
+    {
+        int rf = mesh_finish(m);
+        if (rf)
+            return rf;
+    }
+    DeviceGuard g(m->ctx->device);
+    use_mesh(m->ctx, m);
+    if (m->d.nT)
+        SB_CUDA(cudaMemcpy2DAsync(out, 24, m->d.nrm4, 32, 24, m->d.nT, cudaMemcpyDeviceToHost, m->ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return SB_OK;
+}
 // The front end only keeps the Morton-ordered boxes; the original-order copy is formed on request.
 int sb_mesh_triangle_boxes(const sb_mesh *m, double *out)
 {

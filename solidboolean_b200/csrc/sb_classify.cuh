@@ -8,9 +8,6 @@
 #include "sb_gridq.cuh"
 #include "sb_raytri.cuh"
 
-#ifndef SB_CLS_NPREF
-#define SB_CLS_NPREF 0  // normals fetched before the exact box test
-#endif
 #ifndef SB_CLS_RBOX
 #define SB_CLS_RBOX 1   // ray box shortcut for finite points
 #endif
@@ -55,7 +52,8 @@ struct Target {
     int naxes;                 // ray grids the target has (2: the third is built on demand, see ensure_grid3)
     const double4 *vtx;
     const uint32_t *tri;
-    const double *normal;
+    bool packedIdx;            // nrm4[].w holds the vertex indices (meshes of at most 2^21 vertices)
+    const double4 *nrm4;       // per triangle: unit normal + packed vertex indices (sb_common.cuh)
 };
 
 struct Query {
@@ -113,6 +111,27 @@ __device__ __forceinline__ RaySetup ray_setup(const GridParams &g, int axis, con
     return rs;
 }
 
+// The same for a point with finite coordinates and a compile-time axis (sb_classify2.cu): the ray
+// box is lo = p, hi = p + axis vector (see ray_box), nothing else is formed.
+template <int AXIS>
+__device__ __forceinline__ RaySetup ray_setup_finite(const GridParams &g, const d3 &p, uint32_t job)
+{
+    constexpr int u = AXIS == 0 ? 1 : 0, v = AXIS == 2 ? 1 : 2;
+    const double pu = u == 0 ? p.x : p.y, pv = v == 1 ? p.y : p.z, pa = AXIS == 0 ? p.x : AXIS == 1 ? p.y : p.z;
+    const double eu = xadd(pu, SB_DBL_EPSILON), ev = xadd(pv, SB_DBL_EPSILON), ea = xadd(pa, SB_DBL_MAX);
+    RaySetup rs;
+    rs.any = (g.lo[u] <= eu) & (g.hi[u] >= pu) & (g.lo[v] <= ev) & (g.hi[v] >= pv) & (g.lo[AXIS] <= ea) & (g.hi[AXIS] >= pa);
+    rs.aU = quant_axis(pu, g, u, job);
+    rs.bU = quant_axis(eu, g, u, job);
+    rs.aV = quant_axis(pv, g, v, job);
+    rs.bV = quant_axis(ev, g, v, job);
+    rs.aA = quant_axis(pa, g, AXIS, job);
+    const int su = g.shiftU[AXIS], sv = g.shiftV[AXIS];
+    rs.cu0 = rs.aU >> su; rs.cu1 = rs.bU >> su;
+    rs.cv0 = rs.aV >> sv; rs.cv1 = rs.bV >> sv;
+    return rs;
+}
+
 // the ray as seen from cell (cu, cv): its box clipped to the cell, cell-relative
 __device__ __forceinline__ CellRay ray_in_cell(const GridParams &g, int axis, const RaySetup &rs, uint32_t cu, uint32_t cv)
 {
@@ -133,37 +152,99 @@ __device__ __forceinline__ uint32_t big_list_length(const Target &T, int axis)
 //     lo <= X  <=>  DBL_MAX <= X || c0 <= X || c1 <= X || c2 <= X
 //     hi >= Y  <=>  -DBL_MAX >= Y || c0 >= Y || c1 >= Y || c2 >= Y
 // (a c >= DBL_MAX that satisfies c <= X implies DBL_MAX <= X; mirrored for hi).
-// Bitwise operators: 24 predicate-setting compares, no branches.
+// 24 predicate-setting compares chained in PTX (setp.le.or / setp.ge.or), no branches.  Written
+// in C the compiler turns every row into a NaN-proofed DSETP.MIN/MAX + select sequence (158
+// instructions with the moves around them, a quarter of the evaluation step).
+#ifndef SB_CLS_BOXASM
+#define SB_CLS_BOXASM 1
+#endif
 __device__ __forceinline__ bool tri_box_overlaps(const d3 &t0, const d3 &t1, const d3 &t2, const BoxD &rb)
 {
+#if SB_CLS_BOXASM && defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{\n\t"
+        ".reg .pred a, b;\n\t"
+        "setp.le.f64 a, %19, %4;\n\t"       // DBL_MAX <= hix
+        "setp.le.or.f64 a, %1, %4, a;\n\t"
+        "setp.le.or.f64 a, %7, %4, a;\n\t"
+        "setp.le.or.f64 a, %13, %4, a;\n\t"
+        "setp.ge.f64 b, %20, %5;\n\t"       // -DBL_MAX >= lox
+        "setp.ge.or.f64 b, %1, %5, b;\n\t"
+        "setp.ge.or.f64 b, %7, %5, b;\n\t"
+        "setp.ge.or.f64 b, %13, %5, b;\n\t"
+        "and.pred a, a, b;\n\t"
+        "setp.le.f64 b, %19, %6;\n\t"       // y
+        "setp.le.or.f64 b, %2, %6, b;\n\t"
+        "setp.le.or.f64 b, %8, %6, b;\n\t"
+        "setp.le.or.f64 b, %14, %6, b;\n\t"
+        "and.pred a, a, b;\n\t"
+        "setp.ge.f64 b, %20, %10;\n\t"
+        "setp.ge.or.f64 b, %2, %10, b;\n\t"
+        "setp.ge.or.f64 b, %8, %10, b;\n\t"
+        "setp.ge.or.f64 b, %14, %10, b;\n\t"
+        "and.pred a, a, b;\n\t"
+        "setp.le.f64 b, %19, %11;\n\t"      // z
+        "setp.le.or.f64 b, %3, %11, b;\n\t"
+        "setp.le.or.f64 b, %9, %11, b;\n\t"
+        "setp.le.or.f64 b, %15, %11, b;\n\t"
+        "and.pred a, a, b;\n\t"
+        "setp.ge.f64 b, %20, %12;\n\t"
+        "setp.ge.or.f64 b, %3, %12, b;\n\t"
+        "setp.ge.or.f64 b, %9, %12, b;\n\t"
+        "setp.ge.or.f64 b, %15, %12, b;\n\t"
+        "and.pred a, a, b;\n\t"
+        "selp.u32 %0, 1, 0, a;\n\t"
+        "}"
+        : "=r"(r)
+        : "d"(t0.x), "d"(t0.y), "d"(t0.z),           // 1 2 3
+          "d"(rb.hix), "d"(rb.lox), "d"(rb.hiy),     // 4 5 6
+          "d"(t1.x), "d"(t1.y), "d"(t1.z),           // 7 8 9
+          "d"(rb.loy), "d"(rb.hiz), "d"(rb.loz),     // 10 11 12
+          "d"(t2.x), "d"(t2.y), "d"(t2.z),           // 13 14 15
+          "d"(0.0), "d"(0.0), "d"(0.0),              // 16 17 18 (unused)
+          "d"(DBL_MAX), "d"(-DBL_MAX));              // 19 20
+    return r != 0;
+#else
     return ((DBL_MAX <= rb.hix) | (t0.x <= rb.hix) | (t1.x <= rb.hix) | (t2.x <= rb.hix)) &
            ((-DBL_MAX >= rb.lox) | (t0.x >= rb.lox) | (t1.x >= rb.lox) | (t2.x >= rb.lox)) &
            ((DBL_MAX <= rb.hiy) | (t0.y <= rb.hiy) | (t1.y <= rb.hiy) | (t2.y <= rb.hiy)) &
            ((-DBL_MAX >= rb.loy) | (t0.y >= rb.loy) | (t1.y >= rb.loy) | (t2.y >= rb.loy)) &
            ((DBL_MAX <= rb.hiz) | (t0.z <= rb.hiz) | (t1.z <= rb.hiz) | (t2.z <= rb.hiz)) &
            ((-DBL_MAX >= rb.loz) | (t0.z >= rb.loz) | (t1.z >= rb.loz) | (t2.z >= rb.loz));
+#endif
 }
 
 // One (ray, triangle) entry: is it a candidate of the reference (triangle box
 // .intersectWith(ray box), exact doubles, :55-63), and does the reference insert
 // PositionKey(hit) for it (:66-87)?
+// FINITE: the caller vouches for |coordinates of p| < DBL_MAX (ray box = {p, e}, see ray_box)
+template <bool FINITE = false>
 __device__ __forceinline__ bool eval_entry(const Target &T, const d3 &p, int axis, uint32_t f, long long &k0, long long &k1,
     long long &k2, bool &isCand)
 {
-    const d3 t0 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f));
-    const d3 t1 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 1));
-    const d3 t2 = load_vertex(T.vtx, __ldg(T.tri + 3 * (size_t)f + 2));
-#if SB_CLS_NPREF
-    // fetched before the box test decides (one round trip less; 98 % of the entries pass)
-    const d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
-#endif
+    // first round trip: the triangle's record = normal + packed vertex indices (one 256-bit gather) ...
+    const double4 rec = ldg256(T.nrm4 + f);
+    uint32_t i0, i1, i2;
+    if (T.packedIdx) {
+        const unsigned long long w = (unsigned long long)__double_as_longlong(rec.w);
+        constexpr uint32_t m = (1u << SB_PACKED_IDX_BITS) - 1u;
+        i0 = (uint32_t)w & m;
+        i1 = (uint32_t)(w >> SB_PACKED_IDX_BITS) & m;
+        i2 = (uint32_t)(w >> (2 * SB_PACKED_IDX_BITS)) & m;
+    } else {
+        i0 = __ldg(T.tri + 3 * (size_t)f);
+        i1 = __ldg(T.tri + 3 * (size_t)f + 1);
+        i2 = __ldg(T.tri + 3 * (size_t)f + 2);
+    }
+    // ... second: its three vertices (one 256-bit gather each)
+    const d3 t0 = load_vertex(T.vtx, i0);
+    const d3 t1 = load_vertex(T.vtx, i1);
+    const d3 t2 = load_vertex(T.vtx, i2);
+    const d3 nrm = {rec.x, rec.y, rec.z};
     const d3 e = ray_end(p, axis);
-    isCand = tri_box_overlaps(t0, t1, t2, ray_box(p, e));
+    isCand = tri_box_overlaps(t0, t1, t2, FINITE ? BoxD{p.x, p.y, p.z, e.x, e.y, e.z} : ray_box(p, e));
     if (!isCand)
         return false;
-#if !SB_CLS_NPREF
-    const d3 nrm = {__ldg(T.normal + 3 * (size_t)f), __ldg(T.normal + 3 * (size_t)f + 1), __ldg(T.normal + 3 * (size_t)f + 2)};
-#endif
     d3 hit = {0, 0, 0};
     if (!ray_tri_hit_filtered(p, e, t0, t1, t2, nrm, hit))
         return false;

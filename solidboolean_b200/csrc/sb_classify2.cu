@@ -38,6 +38,9 @@ namespace {
 #ifndef SB_CLS2_MINB
 #define SB_CLS2_MINB 6
 #endif
+#ifndef SB_CLS2_FULLCHUNKS
+#define SB_CLS2_FULLCHUNKS 1   // evaluation steps wait for 32 entries (except in a round's last window)
+#endif
 constexpr int CT2 = SB_CLS2_CT;
 constexpr int CW2 = CT2 / 32;
 constexpr int WINP = 256;             // pairs per window (one owner byte each)
@@ -75,37 +78,45 @@ __device__ __forceinline__ uint32_t prefix_max_bytes(uint32_t x)
     return __vmaxu4(x, x << 16);
 }
 
+// The ray of point p along AXIS: its packed box (rx, ry), where its cell list starts (ra) and how many
+// 16-byte pairs it spans (np).  Returns true when the ray box straddles a cell border (general kernel).
+template <int AXIS>
+__device__ __forceinline__ bool setup_slot(const GridParams &g, const Target &T, const d3 &p, uint32_t job, uint32_t &rx,
+    uint32_t &ry, uint32_t &ra, uint32_t &np)
+{
+    const RaySetup r = ray_setup_finite<AXIS>(g, p, job);
+    if (!r.any)
+        return false;
+    // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell
+    if (r.cu0 != r.cu1 || r.cv0 != r.cv1)
+        return true;
+    const CellRay cq = ray_in_cell(g, AXIS, r, r.cu0, r.cv0);
+    const uint32_t cell = g.cellBase[AXIS] + r.cv0 * g.nu[AXIS] + r.cu0;
+    const uint32_t a = __ldg(T.E + cell + 1);
+    const uint32_t b = __ldg(T.E + cell + 2) & ~1u; // the next cell's share may begin with an unused slot
+    rx = cq.x;
+    ry = cq.y;
+    ra = a;
+    np = b > a ? (b - (a & ~1u)) >> 1 : 0u;
+    return false;
+}
+
 // One round for the warp's points: rays along axis0 .. axis0 + nax - 1 (nax = 1 or 2) of the
 // lanes that `want` them.  Returns bit s set when the ray along axis0 + s crosses an odd
 // number of distinct surface points (:89); lanes whose point needs the general kernel get
 // their bit in `legacy`.
-__device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Target &T, Stage2 &W, int axis0, int nax, bool want,
+template <int axis0, int nax>
+__device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Target &T, Stage2 &W, bool want,
     int lane, uint32_t job, uint32_t &exact, uint32_t &legacy)
 {
     const d3 p = {W.px[lane], W.py[lane], W.pz[lane]};
     // ---- setup: packed ray, cell list, pairs ----
     uint32_t np[2] = {0, 0}, rx[2] = {0, 0}, ry[2] = {0, 0}, ra[2] = {0, 0};
     bool multi = false;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (s < nax && want) {
-            const RaySetup r = ray_setup(g, axis0 + s, p, job);
-            if (r.any) {
-                // a ray box is a point widened by DBL_EPSILON: it almost always sits in ONE cell
-                if (r.cu0 != r.cu1 || r.cv0 != r.cv1) {
-                    multi = true;
-                } else {
-                    const CellRay cq = ray_in_cell(g, axis0 + s, r, r.cu0, r.cv0);
-                    const uint32_t cell = g.cellBase[axis0 + s] + r.cv0 * g.nu[axis0 + s] + r.cu0;
-                    const uint32_t a = __ldg(T.E + cell + 1);
-                    const uint32_t b = __ldg(T.E + cell + 2) & ~1u; // the next cell's share may begin with an unused slot
-                    rx[s] = cq.x;
-                    ry[s] = cq.y;
-                    ra[s] = a;
-                    np[s] = b > a ? (b - (a & ~1u)) >> 1 : 0u;
-                }
-            }
-        }
+    if (want) {
+        multi |= setup_slot<axis0>(g, T, p, job, rx[0], ry[0], ra[0], np[0]);
+        if (nax > 1)
+            multi |= setup_slot<(axis0 + 1) % 3>(g, T, p, job, rx[1], ry[1], ra[1], np[1]);
     }
     const uint32_t multiMask = __ballot_sync(SB_FULL, multi);
     legacy |= multiMask;
@@ -206,7 +217,13 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
         // ---- eval ----
         uint32_t S = 0;
         carry = 0;
+        const bool lastWindow = w0 + WINP >= total;
         while (S < pos) {
+            if (SB_CLS2_FULLCHUNKS && !lastWindow && pos - S < 32u) {
+                // not enough for a full step: these entries wait at the front of the pool for the next window's
+                carry = pos - S;
+                break;
+            }
             const uint32_t e = S + lane;
             const bool inPool = e < pos;
             const uint32_t o = inPool ? (uint32_t)W.owner[e] : 0x100u;
@@ -238,7 +255,7 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
             if (have) {
                 const int ow = rid & 31;
                 const d3 pp = {W.px[ow], W.py[ow], W.pz[ow]};
-                h = eval_entry(T, pp, axis0 + (int)(rid >> 5), W.tri[e], k0, k1, k2, isCand);
+                h = eval_entry<true>(T, pp, axis0 + (int)(rid >> 5), W.tri[e], k0, k1, k2, isCand);
                 if (h) {
                     W.key[lane][0] = k0;
                     W.key[lane][1] = k1;
@@ -349,7 +366,10 @@ __global__ void __launch_bounds__(CT2, SB_CLS2_MINB) classify2_kernel(const __gr
     W.py[lane] = p.y;
     W.pz[lane] = p.z;
     __syncwarp();
-    uint32_t votes = 0, exact = 0, legacy = 0;
+    // a point with an infinite or NaN coordinate goes to the general kernel: the rounds below form the ray box
+    // as lo = p, hi = p + axis vector, which needs |p| < DBL_MAX (ray_box in sb_classify.cuh)
+    const bool finite = fabs(p.x) < DBL_MAX && fabs(p.y) < DBL_MAX && fabs(p.z) < DBL_MAX;
+    uint32_t votes = 0, exact = 0, legacy = __ballot_sync(SB_FULL, active && !finite);
     bool undecided = false, deferred = false;
     for (int round = 0; round < 2; ++round) {
         bool want = active && !((legacy >> lane) & 1u);
@@ -364,7 +384,10 @@ __global__ void __launch_bounds__(CT2, SB_CLS2_MINB) classify2_kernel(const __gr
         }
         if (!__any_sync(SB_FULL, want))
             continue;
-        votes |= trace_round2(g, T, W, 2 * round, 2 - round, want, lane, job, exact, legacy) << (2 * round);
+        if (round == 0)
+            votes |= trace_round2<0, 2>(g, T, W, want, lane, job, exact, legacy);
+        else
+            votes |= trace_round2<2, 1>(g, T, W, want, lane, job, exact, legacy) << 2;
     }
     const bool mine = (legacy >> lane) & 1u; // the general kernel classifies this point (and counts its candidates)
     if (mine) {
@@ -439,7 +462,8 @@ cudaError_t sbk_classify2(cudaStream_t s, const MeshDev &target, const ClassifyA
     T.naxes = target.gridAxes;
     T.vtx = target.vtx;
     T.tri = target.tri;
-    T.normal = target.normal;
+    T.nrm4 = target.nrm4;
+    T.packedIdx = target.nV <= (1u << SB_PACKED_IDX_BITS);
     Out o = {};
     o.inside = a.inside;
     o.perAxis = a.perAxis;

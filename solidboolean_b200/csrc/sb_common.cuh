@@ -114,11 +114,35 @@ __device__ __forceinline__ BoxF shfl_xor_box(const BoxF &b, int mask)
 }
 
 // vertices are stored padded to double4 (one 32-B sector each, two 128-bit loads)
+// One 256-bit read-only load (sm_100: LDG.E.256) of a 32-byte aligned record: one instruction, one
+// L1 tag lookup per lane where two 128-bit loads cost two -- gathers are bound by those lookups.
+__device__ __forceinline__ double4 ldg256(const double4 *p)
+{
+    double4 r;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(double4 *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __device__ __forceinline__ d3 load_vertex(const double4 *v, uint32_t i)
 {
-    const double2 *p = reinterpret_cast<const double2 *>(v + i);
-    double2 a = __ldg(p), b = __ldg(p + 1);
-    return {a.x, a.y, b.x};
+    const double4 a = ldg256(v + i);
+    return {a.x, a.y, a.z};
+}
+
+// Per-triangle record of the classifier (sb_build.cu writes it, sb_classify*.cu read it): the unit normal
+// (SolidMesh::prepare, src/solidmesh.cpp:47-55) and, in the fourth word, the triangle's three vertex indices,
+// 21 bits each -- ONE 256-bit gather instead of three index loads followed by three normal loads, and one
+// dependent round trip less.  Meshes with more than 2^21 vertices leave the word all ones and the kernels
+// read the index triple from `tri`.
+#define SB_PACKED_IDX_BITS 21
+#define SB_PACKED_IDX_NONE 0xffffffffffffffffull
+__device__ __forceinline__ unsigned long long pack_tri_idx(uint32_t i0, uint32_t i1, uint32_t i2)
+{
+    return (unsigned long long)i0 | ((unsigned long long)i1 << SB_PACKED_IDX_BITS) | ((unsigned long long)i2 << (2 * SB_PACKED_IDX_BITS));
 }
 
 __device__ __forceinline__ uint32_t lanemask_lt()

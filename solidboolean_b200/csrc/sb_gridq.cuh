@@ -23,9 +23,10 @@
 
 __device__ __forceinline__ uint32_t quant15(double x, double org, double scl, double qmax = 32767.0)
 {
-    double t = floor((x - org) * scl);
-    t = fmin(fmax(t, 0.0), qmax); // NaN -> 0
-    return (uint32_t)t;
+    // floor, clamp to [0, qmax], NaN -> 0: cvt.rmi.s32.f64 floors, saturates and turns NaN into 0, the
+    // clamp is then two integer min/max (the fmin/fmax form costs a dozen NaN-proofing selects)
+    const int t = __double2int_rd((x - org) * scl);
+    return (uint32_t)min(max(t, 0), (int)qmax);
 }
 
 // Batch meshes: position of job j on a 32 x 32 x 32 lattice, chosen so that ANY two of the three

@@ -37,7 +37,7 @@ struct MeshDev {
     // derived (sb_mesh_build)
     double4 *vtx = nullptr;             // padded vertices
     unsigned long long *bounds = nullptr; // 6 order-encoded doubles: min xyz, max xyz
-    double *normal = nullptr;           // 3*nT, original order
+    double4 *nrm4 = nullptr;            // nT, original order: unit normal + packed vertex indices (sb_common.cuh pack_tri_idx)
     double *scent = nullptr;            // 3*nTpad face centroids ((v0+v1)+v2)/3.0 in Morton order (classification queries)
     uint32_t *mkey = nullptr, *mkeyTmp = nullptr;   // Morton keys (sort ping-pong)
     uint32_t *order = nullptr, *orderTmp = nullptr; // triangle ids (sort ping-pong)
