@@ -19,6 +19,9 @@
 
 namespace {
 
+#ifndef SB_LEAF_STAGE
+#define SB_LEAF_STAGE 0 // boxes / centroids staged through shared memory for 256-bit stores: measured SLOWER (95 -> 110 us at 1.3M triangles)
+#endif
 constexpr int K = SB_CLUSTER;
 static_assert(K == 1 || K == 2 || K == 4 || K == 8 || K == 16 || K == 32, "cluster size must divide the warp");
 
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
     BoxD bd = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
     BoxF bf = empty_boxf();
     int ref = -1;
+    d3 cen = {0.0, 0.0, 0.0};
     if (j < nT) {
         uint32_t t = sortedTri[j];
         uint32_t i0 = __ldg(tri + 3 * (size_t)t), i1 = __ldg(tri + 3 * (size_t)t + 1), i2 = __ldg(tri + 3 * (size_t)t + 2);
@@ -208,15 +212,51 @@ __global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__rest
         ref = (int)t;
         // face centroid exactly as decideGroupSide forms its query point:
         // (v0 + v1 + v2) / 3.0  (src/solidboolean.cpp:497-499)
-        scent[3 * (size_t)j] = xdiv(xadd(xadd(a.x, b.x), c.x), 3.0);
-        scent[3 * (size_t)j + 1] = xdiv(xadd(xadd(a.y, b.y), c.y), 3.0);
-        scent[3 * (size_t)j + 2] = xdiv(xadd(xadd(a.z, b.z), c.z), 3.0);
+        cen = {xdiv(xadd(xadd(a.x, b.x), c.x), 3.0), xdiv(xadd(xadd(a.y, b.y), c.y), 3.0), xdiv(xadd(xadd(a.z, b.z), c.z), 3.0)};
         // ray grids (sb_grid.cu): the quantised box, and the count pass while it is in registers
         const uint4 q = quantise_box(bd, g, t, job);
         qbox[j] = q;
+#ifndef SB_EXP_NOCOUNT
         grid_count_tri(q, g, gridE, gridBigCount, gridAxes);
+#endif
     }
+#if SB_LEAF_STAGE
+    // The 48-byte boxes and 24-byte centroids of a warp are 1536 + 768 contiguous bytes: staged through shared
+    // memory and written as 256-bit stores, whole lines at a time (per-lane stores of 16 / 8 bytes at those
+    // strides touched 21 sectors per request).  The padding lanes write an empty box and a zero centroid.
+    {
+        __shared__ __align__(32) double s_stage[8][32 * 9];
+        const int lane = threadIdx.x & 31;
+        double *sb = s_stage[threadIdx.x >> 5], *sc = sb + 32 * 6;
+        sb[6 * lane] = bd.lox; sb[6 * lane + 1] = bd.loy; sb[6 * lane + 2] = bd.loz; // store_boxd order
+        sb[6 * lane + 3] = bd.hix; sb[6 * lane + 4] = bd.hiy; sb[6 * lane + 5] = bd.hiz;
+        sc[3 * lane] = cen.x; sc[3 * lane + 1] = cen.y; sc[3 * lane + 2] = cen.z;
+        __syncwarp();
+        const uint32_t j0 = j - lane; // multiple of 32
+        double4 *db = reinterpret_cast<double4 *>(sbox + 3 * (size_t)j0), *dc = reinterpret_cast<double4 *>(scent + 3 * (size_t)j0);
+        const double4 *s4 = reinterpret_cast<const double4 *>(sb);
+        double4 q = s4[lane];
+        stg256(db + lane, q.x, q.y, q.z, q.w);
+        if (lane < 16) {
+            q = s4[32 + lane];
+            stg256(db + 32 + lane, q.x, q.y, q.z, q.w);
+        } else if (lane < 16 + 24) {
+            q = s4[48 + lane - 16]; // centroids: 24 records of 32 bytes, lanes 16..31 take the first 16 ...
+            stg256(dc + lane - 16, q.x, q.y, q.z, q.w);
+        }
+        if (lane < 8) { // ... lanes 0..7 the rest
+            q = s4[48 + 16 + lane];
+            stg256(dc + 16 + lane, q.x, q.y, q.z, q.w);
+        }
+    }
+#else
     store_boxd(sbox + 3 * (size_t)j, bd);
+    if (j < nT) {
+        scent[3 * (size_t)j] = cen.x;
+        scent[3 * (size_t)j + 1] = cen.y;
+        scent[3 * (size_t)j + 2] = cen.z;
+    }
+#endif
     store_rec(leaf + j, bf, ref, (int)j);
     // segmented (width K) min/max reduction in registers
     BoxF cb = bf;

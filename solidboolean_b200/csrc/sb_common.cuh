@@ -27,38 +27,48 @@ struct BoxD {
     double lox, loy, loz, hix, hiy, hiz;
 };
 
+// one 256-bit load per record (sm_100: LDG.E.256)
 __device__ __forceinline__ Rec32 load_rec(const Rec32 *p)
 {
-    const float4 *q = reinterpret_cast<const float4 *>(p);
-    float4 a = __ldg(q);
-    float4 b = __ldg(q + 1);
     Rec32 r;
-    r.lox = a.x; r.loy = a.y; r.loz = a.z; r.hix = a.w;
-    r.hiy = b.x; r.hiz = b.y;
-    r.ref = __float_as_int(b.z);
-    r.aux = __float_as_int(b.w);
+    float fr, fa;
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(r.lox), "=f"(r.loy), "=f"(r.loz), "=f"(r.hix), "=f"(r.hiy), "=f"(r.hiz), "=f"(fr), "=f"(fa)
+        : "l"(p));
+    r.ref = __float_as_int(fr);
+    r.aux = __float_as_int(fa);
     return r;
 }
 
 // coherent (L2) load, for data written earlier in the same kernel by another thread
 __device__ __forceinline__ Rec32 load_rec_cg(const Rec32 *p)
 {
-    const float4 *q = reinterpret_cast<const float4 *>(p);
-    float4 a = __ldcg(q);
-    float4 b = __ldcg(q + 1);
     Rec32 r;
-    r.lox = a.x; r.loy = a.y; r.loz = a.z; r.hix = a.w;
-    r.hiy = b.x; r.hiz = b.y;
-    r.ref = __float_as_int(b.z);
-    r.aux = __float_as_int(b.w);
+    float fr, fa;
+    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.lox), "=f"(r.loy), "=f"(r.loz), "=f"(r.hix), "=f"(r.hiy), "=f"(r.hiz), "=f"(fr), "=f"(fa)
+                 : "l"(p)
+                 : "memory");
+    r.ref = __float_as_int(fr);
+    r.aux = __float_as_int(fa);
     return r;
 }
 
+#ifndef SB_REC256
+#define SB_REC256 0 // 256-bit record stores measured slightly slower than two 128-bit ones (leaf kernel +5 us)
+#endif
 __device__ __forceinline__ void store_rec(Rec32 *p, const BoxF &b, int ref, int aux)
 {
+#if !SB_REC256
     float4 *q = reinterpret_cast<float4 *>(p);
     q[0] = make_float4(b.lox, b.loy, b.loz, b.hix);
     q[1] = make_float4(b.hiy, b.hiz, __int_as_float(ref), __int_as_float(aux));
+    return;
+#endif
+    // one 256-bit store per record (sm_100): a warp writing consecutive records fills whole 128-byte lines
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(b.lox), "f"(b.loy), "f"(b.loz), "f"(b.hix),
+                 "f"(b.hiy), "f"(b.hiz), "f"(__int_as_float(ref)), "f"(__int_as_float(aux))
+                 : "memory");
 }
 
 // closed-interval overlap, written with the same comparisons as

@@ -172,8 +172,16 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const uint4 *__restrict
 
 // In-place inclusive scan of a u32 array (single pass, chained tiles with
 // decoupled look-back -- same protocol as the radix sort's digit offsets).
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+#ifndef SB_SCAN_THREADS
+#define SB_SCAN_THREADS 512
+#endif
+#ifndef SB_SCAN_ITEMS
+#define SB_SCAN_ITEMS 16
+#endif
+// 8192 cells per tile: the look-back chain of a 2M-cell grid is 256 tiles long (it was 1024 with 2048-cell
+// tiles, and the chain -- not the 8 MB of traffic -- set the kernel's 23 us)
+constexpr int SCAN_THREADS = SB_SCAN_THREADS;
+constexpr int SCAN_ITEMS = SB_SCAN_ITEMS;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_PREFIX = 2ull << 62, SCAN_MASK = (1ull << 62) - 1;
 
@@ -195,13 +203,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
     const uint32_t base = tile * SCAN_TILE + tid * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t sum = 0;
+    static_assert(SCAN_ITEMS % 4 == 0, "128-bit loads");
+    const bool whole = base + SCAN_ITEMS <= n; // (the array is only allocated up to the cell bound + 2)
+    if (whole) {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i += 4) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(data + base + i);
+            v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            v[i] = base + i < n ? data[base + i] : 0xffffffffu; // (+1 & ~1 -> 0)
+    }
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         // every cell's share is rounded up to an even number of references: the ends (and the
         // 16-byte pairs the classifier loads) stay aligned; a list with an odd count starts
         // one slot after its share does
-        v[i] = base + i < n ? ((data[base + i] + 1u) & ~1u) : 0u;
-        sum += v[i];
+        sum += (v[i] + 1u) & ~1u;
         v[i] = sum; // inclusive within the thread
     }
     uint32_t incl = sum;
@@ -254,15 +274,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
     }
     __syncthreads();
     const uint32_t off = (uint32_t)s_excl + warpOff + incl - sum;
+    if (whole) {
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < n) {
-            data[base + i] = off + v[i];
-            if (base + i == n - 1) { // E[totalCells] = number of references
-                data[n] = off + v[i]; // E[totalCells + 1]: end of the last cell after the fill
-                *totalOut = off + v[i];
-            }
-        }
+        for (int i = 0; i < SCAN_ITEMS; i += 4)
+            *reinterpret_cast<uint4 *>(data + base + i) = make_uint4(off + v[i], off + v[i + 1], off + v[i + 2], off + v[i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i < n)
+                data[base + i] = off + v[i];
+    }
+    if (base < n && n - 1 - base < SCAN_ITEMS) { // this thread holds E[totalCells] = number of references
+        uint32_t last = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i == n - 1)
+                last = off + v[i];
+        data[n] = last; // E[totalCells + 1]: end of the last cell after the fill
+        *totalOut = last;
+    }
 }
 
 } // namespace
