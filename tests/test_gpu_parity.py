@@ -1,6 +1,7 @@
 """GPU (B200): the CUDA path, called through the C ABI, against the oracle and
 the committed reference fixtures.  Bit-exact for pairs, codes, flags; segments
 are compared bit-for-bit too (north_star allows 1e-12 relative, we get 0)."""
+import os
 import numpy as np
 import pytest
 
@@ -608,3 +609,55 @@ def test_config_c3_full_size_properties(ctx, oracle):
     full, per = ma.classify_faces_against(mb)
     assert np.array_equal(full, ia) and np.array_equal((per.sum(axis=1) >= 2).astype(np.uint8), ia)
     x.close(); ma.close(); mb.close()
+
+
+def _fullsize_pins(name):
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.json")) as f:
+        return json.load(f)[name]
+
+
+def _hash(a):
+    from oracle import fnv1a64
+    return "%016x" % fnv1a64(np.ascontiguousarray(a).tobytes())
+
+
+def _check_against_fullsize_pins(ctx, name, a, b):
+    """EVERY output of the front end at full size against the unmodified reference
+    (tests/golden/fullsize.json, written by tests/golden/make_fullsize.py from oracle/_ref over all
+    faces): sorted candidate pairs, per-pair (ret, coplanar), hit pairs, segments bit for bit,
+    per-face flags and per-axis bits of all faces of both meshes."""
+    import torch
+    pin = _fullsize_pins(name)
+    assert (len(a[1]), len(b[1])) == (pin["tris_a"], pin["tris_b"])
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    da = torch.zeros(len(a[1]), dtype=torch.uint8, device="cuda")
+    db = torch.zeros(len(b[1]), dtype=torch.uint8, device="cuda")
+    x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+    assert (x.num_candidates, x.num_hits) == (pin["n_pairs"], pin["n_hits"])
+    ab, code = x.candidates()
+    hab, seg = x.hits()
+    assert _hash(ab.astype("<u8")) == pin["pairs"]
+    assert _hash(code.astype(np.uint8)) == pin["codes"]
+    assert _hash(hab.astype("<u8")) == pin["hits"]
+    assert _hash(seg.astype("<f8")) == pin["seg"]
+    ia, ib = da.cpu().numpy(), db.cpu().numpy()
+    assert (int(ia.sum()), int(ib.sum())) == (pin["inside_a_count"], pin["inside_b_count"])
+    assert _hash(ia) == pin["inside_a"] and _hash(ib) == pin["inside_b"]       # lazy vote, all faces
+    fa, pa = ma.classify_faces_against(mb)                                          # all three rays, all faces
+    fb, pb = mb.classify_faces_against(ma)
+    assert _hash(pa.astype(np.uint8)) == pin["per_axis_a"] and _hash(pb.astype(np.uint8)) == pin["per_axis_b"]
+    assert np.array_equal(fa, ia) and np.array_equal(fb, ib)
+    x.close(); ma.close(); mb.close()
+
+
+@pytest.mark.slow
+def test_config_c3_every_output_vs_reference_pins(ctx):
+    _check_against_fullsize_pins(ctx, "c3", *meshgen.config_c3())
+
+
+@pytest.mark.slow
+def test_config_c4_stated_size_vs_reference_pins(ctx):
+    """BASELINE config 4 at its stated size: near-coincident icospheres k=8, 1,310,720 x2 triangles,
+    8,238,598 candidate pairs."""
+    _check_against_fullsize_pins(ctx, "c4k8", *meshgen.config_c4(k=8))

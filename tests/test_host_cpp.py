@@ -210,3 +210,65 @@ def test_drop_in_classes_config_c3_gpu(real_lib):
     vd = meshgen.signed_volume(v, res["diff"])
     assert abs(vu + vi - (va + vb)) < 1e-6 and abs(vd + vi - va) < 1e-6
     assert 0 < vi < min(va, vb)
+
+
+def _write_obj(path, xyz, tri):
+    with open(path, "w") as f:
+        for v in xyz:
+            f.write("v %.9g %.9g %.9g\n" % (v[0], v[1], v[2]))   # 9 digits: the float the reference's loader parsed
+        for t in tri:
+            f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
+
+
+def _read_obj(path):
+    v, t = [], []
+    with open(path) as f:
+        for line in f:
+            p = line.split()
+            if not p:
+                continue
+            if p[0] == "v":
+                v.append([float(x) for x in p[1:4]])
+            elif p[0] == "f":
+                t.append([int(x.split("/")[0]) - 1 for x in p[1:4]])
+    return np.array(v, np.float64), np.array(t, np.int64)
+
+
+@pytest.mark.gpu
+def test_reference_main_cpp_unchanged_runs_on_the_gpu(tmp_path, golden_cases, golden_json):
+    """BASELINE config 1: the reference's own test/main.cpp, compiled UNCHANGED against the drop-in
+    headers (solidboolean_b200/host/Makefile `refmain`, built where the reference tree is present;
+    the binary travels with the snapshot), executed on the GPU box.  It loads
+    ../../cases/addax-and-meerkat/{a,b}.obj, runs prepare() x2 + combine() + the three fetch* and
+    writes debug-merged-result.obj (union, diff at x-2, intersect at x+2).  The OBJ pair is rewritten
+    from the committed fixture (the reference tree does not exist on the GPU box); the result is
+    compared with the reference's own run as a SOLID: summed volume of the three results, and
+    every result closed."""
+    exe = os.path.join(HOST, "test-solidboolean")
+    if not os.path.exists(exe):
+        pytest.skip("test-solidboolean not built (needs the reference tree at build time)")
+    a, b, _ = load_case(golden_cases, "addax-and-meerkat")
+    case_dir = tmp_path / "cases" / "addax-and-meerkat"
+    run_dir = tmp_path / "build" / "run"
+    case_dir.mkdir(parents=True); run_dir.mkdir(parents=True)
+    _write_obj(case_dir / "a.obj", *a)
+    _write_obj(case_dir / "b.obj", *b)
+    r = subprocess.run([exe], cwd=run_dir, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
+    assert "Duration:" in r.stdout and "searchPotentialIntersectedPairs:" in r.stdout
+    v, t = _read_obj(run_dir / "debug-merged-result.obj")
+    meta = golden_json["cases"]["addax-and-meerkat"]
+    assert len(v) == 3 * meta["result_vertices"]          # the result vertex array, once per operation
+    # split the merged file back into the three results by their vertex blocks
+    nv = meta["result_vertices"]
+    block = t[:, 0] // nv
+    total = 0.0
+    for k, name in enumerate(("union", "diff", "intersect")):
+        tk = t[block == k] - k * nv
+        assert len(tk) > 0 and np.all((t[block == k] // nv) == k)
+        assert meshgen.is_closed_manifold(tk.astype(np.uint32)), name
+        vol = meshgen.signed_volume(v[k * nv:(k + 1) * nv], tk)
+        ref = meta["volume_" + name]
+        assert abs(vol - ref) <= 1e-3 * abs(ref), (name, vol, ref)   # the OBJ text is written with %f: 6 decimals
+        total += vol
+    assert abs(total - (meta["volume_union"] + meta["volume_diff"] + meta["volume_intersect"])) <= 1e-3 * abs(total)
