@@ -292,6 +292,35 @@ int sb_shard_info(const sb_shard *s, size_t *selected_a, size_t *selected_b, dou
                   uint64_t *fallbacks);
 void sb_shard_destroy(sb_shard *s);
 
+/* ---- several GPUs from ONE host process (`sb_comm_create` + the multi-GPU front end) ------
+ * What a C++ caller of SolidBoolean::combine() (src/solidboolean.cpp:288) needs to reach GPUs 1..N-1:
+ * no MPI, no torch.distributed.  A comm owns one context per rank (devices[r], or device r when
+ * devices is NULL; the same device may appear more than once), and per call one host thread per rank.
+ * sb_comm_set_meshes hands both meshes to every rank (host buffers, same layouts as sb_mesh_upload; a
+ * second call with the same counts only replaces the bytes).  sb_comm_front_end runs sb_shard_front_end
+ * on every rank -- selection, build of the selected triangles, broad phase, predicate, both
+ * classifications, each for the rank's own slab of faces -- and gathers: the per-face flags of all ranks
+ * are OR-ed on rank 0's GPU (peer copies; every face belongs to one rank) and copied into insideA / insideB
+ * (nT(A) / nT(B) bytes, either may be NULL); the hit pairs and segments of all ranks, merged in (a, b) order,
+ * are then available from sb_comm_hits.  n_cand / n_hit = the totals over the ranks = the single-GPU counts.
+ * replaces: src/solidboolean.cpp:94-122 (search + predicate loop) and :482-510 (decideGroupSide) across GPUs. */
+typedef struct sb_comm sb_comm;
+typedef struct sb_comm_rank_info {
+    int device;
+    size_t selected_a, selected_b; /* triangles of A / B the rank selected and built */
+    double z_lo, z_hi;             /* its slab of face centroids */
+    size_t candidates, hits;       /* its share of the pairs */
+    uint64_t fallbacks;            /* front ends that needed the whole meshes (third ray) */
+} sb_comm_rank_info;
+int sb_comm_create(int n_ranks, const int *devices, sb_comm **out);
+int sb_comm_size(const sb_comm *c);
+int sb_comm_set_meshes(sb_comm *c, const double *xyzA, size_t nVA, const uint32_t *triA, size_t nTA,
+                       const double *xyzB, size_t nVB, const uint32_t *triB, size_t nTB);
+int sb_comm_front_end(sb_comm *c, unsigned flags, size_t *n_cand, size_t *n_hit, uint8_t *insideA, uint8_t *insideB);
+int sb_comm_hits(const sb_comm *c, uint32_t *ab /* 2 n_hit */, double *seg /* 6 n_hit */);
+int sb_comm_rank(const sb_comm *c, int rank, sb_comm_rank_info *out);
+void sb_comm_destroy(sb_comm *c);
+
 /* ---- batches of small booleans (BASELINE configs[4]: 1,000 x 5K-triangle jobs; SURVEY 8e "C5") --------
  * The reference runs one SolidBoolean per call (test/main.cpp:92-103); a 5K-triangle mesh cannot fill a
  * B200.  A BATCH MESH holds the meshes of n_jobs independent jobs end to end and goes through the same

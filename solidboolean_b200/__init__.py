@@ -30,6 +30,11 @@ class _BvhInfo(C.Structure):
                 ("num_internal", C.c_uint32), ("root", C.c_int32)]
 
 
+class _CommRankInfo(C.Structure):
+    _fields_ = [("device", C.c_int), ("selected_a", C.c_size_t), ("selected_b", C.c_size_t), ("z_lo", C.c_double),
+                ("z_hi", C.c_double), ("candidates", C.c_size_t), ("hits", C.c_size_t), ("fallbacks", C.c_uint64)]
+
+
 class _GridInfo(C.Structure):
     _fields_ = [("nu", C.c_uint32 * 3), ("nv", C.c_uint32 * 3), ("total_cells", C.c_uint32),
                 ("total_refs", C.c_uint32), ("big", C.c_uint32 * 3), ("mean_extent", C.c_float * 3)]
@@ -59,6 +64,13 @@ ABI = {
     "sb_shard_info": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_uint64)]),
     "sb_shard_destroy": (None, [_vp]),
+    "sb_comm_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]),
+    "sb_comm_size": (C.c_int, [_vp]),
+    "sb_comm_set_meshes": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "sb_comm_front_end": (C.c_int, [_vp, C.c_uint, C.POINTER(_sz), C.POINTER(_sz), _vp, _vp]),
+    "sb_comm_hits": (C.c_int, [_vp, _vp, _vp]),
+    "sb_comm_rank": (C.c_int, [_vp, C.c_int, C.POINTER(_CommRankInfo)]),
+    "sb_comm_destroy": (None, [_vp]),
     "sb_mesh_upload_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_vp)]),
     "sb_mesh_update": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "sb_mesh_build": (C.c_int, [_vp]),
@@ -411,6 +423,59 @@ class Shard:
     def close(self):
         if getattr(self, "h", None) and getattr(self.a.ctx, "h", None):
             self.lib.sb_shard_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """Several GPUs from one process (sb_comm_*): devices = list of CUDA device numbers, one rank each
+    (the same device may appear twice)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        h = _vp()
+        _check(self.lib.sb_comm_create(len(devices), devs, C.byref(h)))
+        self.h = h
+        self.nTA = self.nTB = 0
+        self.num_candidates = self.num_hits = 0
+
+    @property
+    def size(self):
+        return int(self.lib.sb_comm_size(self.h))
+
+    def set_meshes(self, a, b):
+        xa, ta = np.ascontiguousarray(a[0], np.float64), np.ascontiguousarray(a[1], np.uint32)
+        xb, tb = np.ascontiguousarray(b[0], np.float64), np.ascontiguousarray(b[1], np.uint32)
+        _check(self.lib.sb_comm_set_meshes(self.h, _ptr(xa), len(xa), _ptr(ta), len(ta), _ptr(xb), len(xb), _ptr(tb), len(tb)))
+        self.nTA, self.nTB = len(ta), len(tb)
+
+    def front_end(self, flags=0):
+        """-> (insideA, insideB): per-face flags of both meshes; the counts land in num_candidates / num_hits."""
+        ia, ib = np.zeros(self.nTA, np.uint8), np.zeros(self.nTB, np.uint8)
+        nc, nh = _sz(0), _sz(0)
+        _check(self.lib.sb_comm_front_end(self.h, flags, C.byref(nc), C.byref(nh), _ptr(ia), _ptr(ib)))
+        self.num_candidates, self.num_hits = int(nc.value), int(nh.value)
+        return ia, ib
+
+    def hits(self):
+        ab, seg = np.zeros((self.num_hits, 2), np.uint32), np.zeros((self.num_hits, 6), np.float64)
+        _check(self.lib.sb_comm_hits(self.h, _ptr(ab), _ptr(seg)))
+        return ab, seg
+
+    def rank_info(self, r):
+        i = _CommRankInfo()
+        _check(self.lib.sb_comm_rank(self.h, r, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in _CommRankInfo._fields_}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_comm_destroy(self.h)
         self.h = None
 
     def __del__(self):

@@ -26,6 +26,13 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
+} // namespace
+
+// (for the translation units that sit on top of the ABI: sb_comm.cu)
+void sbi_set_error(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
+
+namespace {
+
 #define SB_CUDA(expr)                                                                                   \
     do {                                                                                                \
         cudaError_t e_ = (expr);                                                                        \

@@ -82,6 +82,9 @@ struct MeshDev {
     double latPitch = 0.0;
 };
 
+// sb_capi.cu: sets the calling thread's sb_last_error() text
+void sbi_set_error(const char *msg);
+
 struct LaunchCounter {
     uint64_t kernels = 0;
 };
