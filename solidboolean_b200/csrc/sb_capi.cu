@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -71,6 +72,7 @@ static_assert(sizeof(DeviceScalars) <= 128, "lane slot too small");
 } // namespace
 
 struct sb_context {
+    std::recursive_mutex mu; // held by every entry point that works on this context (DeviceGuard)
     int device = 0;
     int smCount = 148;
     cudaStream_t stream = nullptr;
@@ -201,18 +203,32 @@ struct sb_cuts {
 
 namespace {
 
+// Every entry point starts with one of these: the context's device becomes current and -- the reference
+// allows concurrent SolidBoolean objects over shared const SolidMesh from several threads (SURVEY 8b,
+// "Threading") -- the context is locked for the duration of the call.  A context owns ONE stream, one block
+// of pinned read-back scalars, one radix workspace: calls on the same context from several host threads are
+// serialised here (recursive: entry points call each other); different contexts run side by side.
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;
+    std::recursive_mutex *mu = nullptr;
     explicit DeviceGuard(int dev)
     {
         if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess)
+            ok = true;
+    }
+    explicit DeviceGuard(const sb_context *c) : mu(&const_cast<sb_context *>(c)->mu)
+    {
+        mu->lock();
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(c->device) == cudaSuccess)
             ok = true;
     }
     ~DeviceGuard()
     {
         if (prev >= 0)
             cudaSetDevice(prev);
+        if (mu)
+            mu->unlock();
     }
 };
 
@@ -524,7 +540,7 @@ void sb_context_destroy(sb_context *c)
 {
     if (!c)
         return;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c->device); // (not the locking form: the mutex goes away with the context)
     cudaStreamSynchronize(c->stream);
     for (auto &s : c->spans) {
         cudaEventDestroy(s.a);
@@ -559,7 +575,7 @@ int sb_context_synchronize(sb_context *c)
 {
     if (!c)
         return fail(SB_ERR_INVALID, "context is null");
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     SB_CUDA(cudaStreamSynchronize(c->stream));
     return SB_OK;
 }
@@ -615,7 +631,7 @@ int sb_context_reset_timing(sb_context *c)
 {
     if (!c)
         return fail(SB_ERR_INVALID, "context is null");
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     int r = drain_spans(c);
     if (r)
         return r;
@@ -630,7 +646,7 @@ int sb_context_get_timing(sb_context *c, float *ms, uint64_t *kernel_launches)
 {
     if (!c)
         return fail(SB_ERR_INVALID, "context is null");
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     int r = drain_spans(c);
     if (r)
         return r;
@@ -664,7 +680,7 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
         return fail(SB_ERR_INVALID, "null geometry pointer");
     if (nT && !nV)
         return fail(SB_ERR_INVALID, "triangles without vertices");
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     sb_mesh *m = nullptr;
     int r = mesh_alloc(ctx, nV, nT, &m);
     if (r)
@@ -697,7 +713,7 @@ int sb_mesh_upload_device(sb_context *ctx, const void *d_xyz, size_t nV, const v
         return fail(SB_ERR_INVALID, "null geometry pointer");
     if (nT && !nV)
         return fail(SB_ERR_INVALID, "triangles without vertices");
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     sb_mesh *m = nullptr;
     int r = mesh_alloc(ctx, nV, nT, &m); // (the mesh stream waits for the context stream here)
     if (r)
@@ -728,7 +744,7 @@ int sb_mesh_update(sb_mesh *m, const void *xyz, const void *tri, int on_device)
     if (m->d.triJob || m->d.sharedVtx)
         return fail(SB_ERR_INVALID, "only plain meshes can be updated");
     sb_context *c = m->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     order_after_context(c, m);
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (xyz && m->d.nV)
@@ -763,7 +779,7 @@ int sb_batch_upload(sb_context *ctx, size_t n_jobs, const double *xyz, const siz
         return fail(SB_ERR_INVALID, "triangles without vertices");
     if (!(lattice_pitch > 0.0) || !(lattice_pitch < 1.0e30))
         return fail(SB_ERR_INVALID, "lattice_pitch must be a positive number (>= 4 x the largest |coordinate| of both batches)");
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     sb_mesh *m = nullptr;
     int r = mesh_alloc(ctx, nV, nT, &m, n_jobs);
     if (r)
@@ -883,7 +899,7 @@ static int mesh_finish(const sb_mesh *mc)
     if (!m || !m->gridPending)
         return SB_OK;
     m->gridPending = false;
-    DeviceGuard g(m->ctx->device);
+    DeviceGuard g(m->ctx);
     int r = grid_size_and_fill(m, false);
     if (r) {
         m->built = false;
@@ -935,7 +951,7 @@ int sb_mesh_build(sb_mesh *m)
     if (!m)
         return fail(SB_ERR_INVALID, "mesh is null");
     sb_context *c = m->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     cudaStream_t st = m->stream;
     m->gridPending = false; // an unfinished first build is simply redone
     if (c->sortBeginBit >= 0) {
@@ -1129,7 +1145,7 @@ int sb_mesh_create(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
     int r = sb_mesh_upload(ctx, xyz, nV, tri, nT, out);
     if (r)
         return r;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     r = sb_mesh_build(*out);
     if (!r)
         r = mesh_check(*out);
@@ -1144,7 +1160,7 @@ void sb_mesh_destroy(sb_mesh *m)
 {
     if (!m)
         return;
-    DeviceGuard g(m->ctx->device);
+    DeviceGuard g(m->ctx);
     if (m->stream) {
         // free in mesh-stream order, after the context stream is done with the buffers
         order_after_context(m->ctx, m);
@@ -1184,7 +1200,7 @@ static int mesh_download(const sb_mesh *m, void *dst, const void *src, size_t by
         if (rf)
             return rf;
     }
-    DeviceGuard g(m->ctx->device);
+    DeviceGuard g(m->ctx);
     use_mesh(m->ctx, m);
     if (bytes)
         SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->ctx->stream));
@@ -1204,7 +1220,7 @@ int sb_mesh_normals(const sb_mesh *m, double *out)
         if (rf)
             return rf;
     }
-    DeviceGuard g(m->ctx->device);
+    DeviceGuard g(m->ctx);
     use_mesh(m->ctx, m);
     if (m->d.nT)
         SB_CUDA(cudaMemcpy2DAsync(out, 24, m->d.nrm4, 32, 24, m->d.nT, cudaMemcpyDeviceToHost, m->ctx->stream));
@@ -1226,7 +1242,7 @@ int sb_mesh_triangle_boxes(const sb_mesh *m, double *out)
             return rf;
     }
     sb_context *c = m->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     use_mesh(c, m);
     double2 *tmp = nullptr;
     int r = alloc_async(c, &tmp, 3 * (size_t)m->d.nT, nullptr);
@@ -1256,7 +1272,7 @@ int sb_mesh_bvh_info(const sb_mesh *m, sb_bvh_info *out)
     if (!m || !out || !m->built)
         return fail(SB_ERR_INVALID, "null or unbuilt mesh");
     {
-        DeviceGuard g(m->ctx->device);
+        DeviceGuard g(m->ctx);
         int rt = ensure_tree(m);
         if (rt)
             return rt;
@@ -1275,7 +1291,7 @@ int sb_mesh_bvh_info(const sb_mesh *m, sb_bvh_info *out)
 int sb_mesh_bvh_nodes(const sb_mesh *m, void *out)
 {
     if (m && m->built) {
-        DeviceGuard g(m->ctx->device);
+        DeviceGuard g(m->ctx);
         int rt = ensure_tree(m);
         if (rt)
             return rt;
@@ -1348,7 +1364,7 @@ void sb_isect_destroy(sb_isect *x)
 {
     if (!x)
         return;
-    DeviceGuard g(x->ctx->device);
+    DeviceGuard g(x->ctx);
     for (void *p : x->owned)
         cudaFreeAsync(p, x->ctx->stream);
     delete x;
@@ -1382,7 +1398,7 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
             return rb;
     }
     sb_context *c = A->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     {
         int rt = ensure_tree(B);
         if (rt)
@@ -1517,7 +1533,7 @@ int sb_fp64_peak(sb_context *c, double *nofma_gflops, double *fma_gflops)
 {
     if (!c)
         return fail(SB_ERR_INVALID, "context is null");
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     double *scratch = nullptr;
     SB_CUDA(cudaMalloc(&scratch, 64));
     cudaEvent_t e0, e1;
@@ -1591,7 +1607,7 @@ int sb_isect_candidates(const sb_isect *xc, uint32_t *ab, uint8_t *code)
     if (!x || !ab)
         return fail(SB_ERR_INVALID, "null isect or output");
     sb_context *c = x->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     if (!x->nCand)
         return SB_OK;
     {
@@ -1622,7 +1638,7 @@ int sb_isect_hits(const sb_isect *x, uint32_t *ab, double *seg)
     if (!x)
         return fail(SB_ERR_INVALID, "isect is null");
     sb_context *c = x->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     if (!x->nHit)
         return SB_OK;
     if (ab)
@@ -1645,7 +1661,7 @@ int sb_batch_job_ranges(const sb_isect *x, size_t *hit_start)
     const size_t J = A->d.nJobs, H = x->nHit;
     std::vector<uint32_t> ab(2 * std::max<size_t>(H, 1));
     if (H) {
-        DeviceGuard g(x->ctx->device);
+        DeviceGuard g(x->ctx);
         SB_CUDA(cudaMemcpyAsync(ab.data(), x->hitAB, 8 * H, cudaMemcpyDeviceToHost, x->ctx->stream));
         SB_CUDA(cudaStreamSynchronize(x->ctx->stream));
     }
@@ -1665,7 +1681,7 @@ int sb_isect_face_flags(const sb_isect *x, uint8_t *flagsA, uint8_t *flagsB)
     if (!x)
         return fail(SB_ERR_INVALID, "isect is null");
     sb_context *c = x->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     if (flagsA && x->A->d.nT)
         SB_CUDA(cudaMemcpyAsync(flagsA, x->flagsA, x->A->d.nT, cudaMemcpyDeviceToHost, c->stream));
     if (flagsB && x->B->d.nT)
@@ -1681,7 +1697,7 @@ int sb_isect_device_ptrs(const sb_isect *xc, void **cand_keys, unsigned *bits_b,
     if (!x)
         return fail(SB_ERR_INVALID, "isect is null");
     if (cand_keys) {
-        DeviceGuard g(x->ctx->device);
+        DeviceGuard g(x->ctx);
         int rs = ensure_candidates_sorted(x);
         if (rs)
             return rs;
@@ -1701,7 +1717,7 @@ void sb_uncut_destroy(sb_uncut *u)
 {
     if (!u)
         return;
-    DeviceGuard g(u->ctx->device);
+    DeviceGuard g(u->ctx);
     for (void *p : u->owned)
         cudaFreeAsync(p, u->ctx->stream);
     delete u;
@@ -1798,7 +1814,7 @@ int sb_isect_uncut(const sb_isect *x, int which, size_t vertex_offset, size_t tr
     if (!x || !out || (which != 0 && which != 1))
         return fail(SB_ERR_INVALID, "null isect / out, or which not 0 / 1");
     *out = nullptr;
-    DeviceGuard g(x->ctx->device);
+    DeviceGuard g(x->ctx);
     return uncut_run(which == 0 ? x->A : x->B, which == 0 ? x->flagsA : x->flagsB, vertex_offset, triangle_offset, out);
 }
 
@@ -1808,7 +1824,7 @@ int sb_mesh_uncut(const sb_mesh *mesh, const uint8_t *cut_flags, size_t vertex_o
         return fail(SB_ERR_INVALID, "null mesh or out");
     *out = nullptr;
     sb_context *c = mesh->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     use_mesh(c, mesh); // the geometry upload ran on the mesh stream
     uint8_t *dCut = nullptr;
     if (cut_flags && mesh->d.nT) {
@@ -1845,7 +1861,7 @@ int sb_uncut_triangles(const sb_uncut *u, uint32_t *face, uint32_t *tri3)
     if (!u)
         return fail(SB_ERR_INVALID, "uncut is null");
     sb_context *c = u->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     const size_t n = uncut_tri_count(u);
     if (!n)
         return SB_OK;
@@ -1884,7 +1900,7 @@ int sb_uncut_half_edges(const sb_uncut *u, uint64_t *keys, uint32_t *owner)
     if (!u)
         return fail(SB_ERR_INVALID, "uncut is null");
     sb_context *c = u->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     const size_t n = 3 * (size_t)u->nTri;
     if (!n)
         return SB_OK;
@@ -1913,7 +1929,7 @@ int sb_uncut_adjacency(const sb_uncut *u, int32_t *adj3)
     if (!u || !adj3)
         return fail(SB_ERR_INVALID, "null uncut or output");
     sb_context *c = u->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     if (!u->nTri)
         return SB_OK;
     if (u->repeatOrd != 0xffffffffu) {
@@ -1946,7 +1962,7 @@ int sb_uncut_components(const sb_uncut *uc, uint32_t *label, size_t *n_component
     if (!u)
         return fail(SB_ERR_INVALID, "uncut is null");
     sb_context *c = u->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     if (n_components)
         *n_components = 0;
     if (!u->nTri)
@@ -2044,7 +2060,7 @@ void sb_cuts_destroy(sb_cuts *k)
 {
     if (!k)
         return;
-    DeviceGuard g(k->ctx->device);
+    DeviceGuard g(k->ctx);
     for (void *p : k->owned)
         cudaFreeAsync(p, k->ctx->stream);
     delete k;
@@ -2058,7 +2074,7 @@ int sb_isect_contexts(const sb_isect *x, int which, sb_cuts **out)
     if (x->noSort)
         return fail(SB_ERR_INVALID, "contexts need the hits in ascending order (SB_ISECT_NO_SORT was set)");
     sb_context *c = x->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     sb_cuts *k = new (std::nothrow) sb_cuts;
     if (!k)
         return fail(SB_ERR_NOMEM, "out of host memory");
@@ -2115,7 +2131,7 @@ int sb_cuts_fetch(const sb_cuts *k, uint32_t *tri, uint32_t *point_start, double
     if (!k)
         return fail(SB_ERR_INVALID, "cuts is null");
     sb_context *c = k->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     if (!k->nCtx) {
         if (point_start) point_start[0] = 0;
         if (relation_start) relation_start[0] = 0;
@@ -2152,7 +2168,7 @@ int sb_isect_pack_device(const sb_isect *x, void *d_record, size_t cap)
     if (!x || !d_record)
         return fail(SB_ERR_INVALID, "null isect or record");
     sb_context *c = x->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     char *rec = static_cast<char *>(d_record);
     const unsigned long long header[2] = {x->nCand, x->nHit};
     // 16 bytes from the stack: copied into the driver's staging at enqueue time
@@ -2173,7 +2189,7 @@ int sb_tri_tri_batch(sb_context *c, const double *tris18, size_t n, int32_t *ret
         return fail(SB_ERR_INVALID, "batch too large");
     if (!n)
         return SB_OK;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     double *dT = nullptr, *dSeg = nullptr;
     int32_t *dRet = nullptr, *dCop = nullptr;
     std::vector<void *> owned;
@@ -2422,7 +2438,7 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
     if (!Q)
         return SB_OK;
     sb_context *c = target->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     use_mesh(c, target);
     int r = ensure_classify_out(c, 4 * Q, 0);
     if (r)
@@ -2511,7 +2527,7 @@ int sb_classify_faces(const sb_mesh *query, const sb_mesh *target, uint8_t *insi
         return fail(SB_ERR_INVALID, "inside is null");
     if (!query)
         return fail(SB_ERR_INVALID, "null mesh");
-    DeviceGuard g(query->ctx->device);
+    DeviceGuard g(query->ctx);
     uint8_t *dIn = nullptr, *dAx = nullptr;
     int r = classify_faces_impl(query, target, 0, query->d.nT, per_axis != nullptr, nullptr, &dIn, &dAx);
     if (r)
@@ -2531,7 +2547,7 @@ int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target, size_t
 {
     if (!query || !d_inside)
         return fail(SB_ERR_INVALID, "null mesh or output");
-    DeviceGuard g(query->ctx->device);
+    DeviceGuard g(query->ctx);
     uint8_t *dIn = nullptr, *dAx = nullptr;
     // the slow path for overflowing rays needs the counters on the host, so this
     // call synchronises once after the kernel (a 40-byte read-back)
@@ -2561,7 +2577,7 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
             return rf;
     }
     sb_context *c = A->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     aEnd = std::min<size_t>(aEnd, A->d.nT);
     bEnd = std::min<size_t>(bEnd, B->d.nT);
     aBegin = std::min(aBegin, aEnd);
@@ -2657,7 +2673,7 @@ int sb_shard_create(const sb_mesh *A, const sb_mesh *B, int rank, int n_ranks, s
     if (A->d.triJob || B->d.triJob || A->d.sharedVtx || B->d.sharedVtx)
         return fail(SB_ERR_INVALID, "shards are made of plain meshes");
     sb_context *c = A->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     sb_shard *s = new (std::nothrow) sb_shard;
     if (!s)
         return fail(SB_ERR_NOMEM, "out of host memory");
@@ -2720,7 +2736,7 @@ void sb_shard_destroy(sb_shard *s)
 {
     if (!s)
         return;
-    DeviceGuard g(s->ctx->device);
+    DeviceGuard g(s->ctx);
     for (int k = 0; k < 2; ++k) {
         if (s->sub[k])
             sb_mesh_destroy(s->sub[k]);
@@ -2854,7 +2870,7 @@ int sb_shard_front_end(sb_shard *s, unsigned flags, sb_isect **out, void *d_insi
         return fail(SB_ERR_INVALID, "null argument");
     *out = nullptr;
     sb_context *c = s->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     const int n = s->n, rank = s->rank;
     bool confirmed = true;
     const bool speculate = s->planValid && s->sub[0] && s->sub[1] && !getenv("SB_SHARD_NO_SPECULATION");

@@ -45,11 +45,10 @@ bool ReTriangulator::collectChains()
 {
     const size_t n = m_points.size();
     std::vector<char> used(n, 0);
-    for (size_t i = 3; i < n; ++i)
-        if (m_adjacency[i].size() > 2) {
-            std::cout << "ReTriangulator: branching intersection curve" << std::endl;
-            return false;
-        }
+    // A point of degree > 2 (PositionKey welding can merge the end points of neighbouring segments) does not
+    // stop the reference: lookupPolylinesFromNeighborMap (src/retriangulator.cpp:48-95) starts at the degree-1
+    // points, then at whatever is left, and every walk greedily follows the first unvisited neighbour.  Same here
+    // (neighbours in ascending order instead of hash order).
     auto walk = [&](size_t start) {
         std::vector<size_t> chain;
         size_t prev = n, cur = start;
@@ -76,7 +75,7 @@ bool ReTriangulator::collectChains()
                 m_polylines.push_back(chain);
         }
     for (size_t i = 3; i < n; ++i) // what is left are cycles
-        if (!used[i] && m_adjacency[i].size() == 2) {
+        if (!used[i] && m_adjacency[i].size() >= 2) {
             std::vector<size_t> chain = walk(i);
             bool closed = chain.size() >= 3 &&
                 std::find(m_adjacency[chain.back()].begin(), m_adjacency[chain.back()].end(), chain.front()) !=

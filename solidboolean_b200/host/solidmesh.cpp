@@ -3,17 +3,20 @@
 #include <iostream>
 #include "solidboolean_b200.h"
 
+// One context per process.  The reference allows concurrent SolidBoolean objects over shared const
+// SolidMesh from several threads (it has no mutable global state); here every call of the C ABI locks
+// its context for the duration of the call (sb_capi.cu, DeviceGuard), so such callers are serialised on
+// the GPU's single stream of work instead of racing on it.  Created once, thread-safely (C++11 static).
 sb_context *SolidMesh::sharedContext()
 {
-    thread_local sb_context *ctx = nullptr;
-    thread_local bool tried = false;
-    if (!ctx && !tried) {
-        tried = true;
-        if (sb_context_create(0, &ctx) != SB_OK) {
+    static sb_context *ctx = []() -> sb_context * {
+        sb_context *c = nullptr;
+        if (sb_context_create(0, &c) != SB_OK) {
             std::cout << "solidboolean_b200: " << sb_last_error() << std::endl;
-            ctx = nullptr;
+            c = nullptr;
         }
-    }
+        return c;
+    }();
     return ctx;
 }
 
