@@ -103,7 +103,10 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
     return (uint32_t)f;
 }
 
-__global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
+#ifndef SB_TRIPREP_MINB
+#define SB_TRIPREP_MINB 1
+#endif
+__global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double4 *__restrict__ nrm4,
     uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
     unsigned long long *__restrict__ extentSum, const uint16_t *__restrict__ triJob)
@@ -174,7 +177,10 @@ __global__ void __launch_bounds__(256) tri_prepare_kernel(const double4 *__restr
 }
 
 // ---- K1b --------------------------------------------------------------------
-__global__ void __launch_bounds__(256) leaf_gather_kernel(const uint32_t *__restrict__ sortedTri,
+#ifndef SB_LEAF_MINB
+#define SB_LEAF_MINB 1
+#endif
+__global__ void __launch_bounds__(256, SB_LEAF_MINB) leaf_gather_kernel(const uint32_t *__restrict__ sortedTri,
     const uint32_t *__restrict__ sortedKey, const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, uint32_t nTpad, Rec32 *__restrict__ leaf, double2 *__restrict__ sbox, double *__restrict__ scent,
     Rec32 *__restrict__ cbox, uint32_t *__restrict__ ckey, const GridParams *__restrict__ gp, uint4 *__restrict__ qbox,

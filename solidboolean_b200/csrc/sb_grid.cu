@@ -123,19 +123,26 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
 #if SB_FILL_AGG
         // Morton-neighbouring triangles mostly land in the same cells: one atomic per distinct cell
         // of the warp, the lanes that share it take consecutive slots below the returned end
+        // (the four atomics of a lane are issued before the first of them is waited for: grouping first,
+        // then the leaders' atomics, then the shuffles that hand the results round -- one round trip, not four)
         const unsigned act = __activemask();
         const uint32_t lane = threadIdx.x & 31, below = lanemask_lt();
-        auto claim = [&](bool want, uint32_t cell) {
-            const unsigned peers = __match_any_sync(act, want ? cell : 0xffffffffu - lane);
-            const int leader = __ffs(peers) - 1;
-            uint32_t end = 0;
-            if (want && (int)lane == leader)
-                end = atomicSub(&E[cell], (uint32_t)__popc(peers));
-            end = __shfl_sync(act, end, leader);
-            return end - 1u - (uint32_t)__popc(peers & below);
-        };
-        const uint32_t p00 = claim(true, c00 + 1), p10 = claim(du, c00 + 2), p01 = claim(dv, c00 + nu + 1),
-                       p11 = claim(du && dv, c00 + nu + 2);
+        const bool want[4] = {true, du, dv, du && dv};
+        const uint32_t cell[4] = {c00 + 1, c00 + 2, c00 + nu + 1, c00 + nu + 2};
+        unsigned peers[4];
+        uint32_t end[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            peers[k] = __match_any_sync(act, want[k] ? cell[k] : 0xffffffffu - lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (want[k] && (int)lane == __ffs(peers[k]) - 1)
+                end[k] = atomicSub(&E[cell[k]], (uint32_t)__popc(peers[k]));
+        uint32_t pos[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            pos[k] = __shfl_sync(act, end[k], __ffs(peers[k]) - 1) - 1u - (uint32_t)__popc(peers[k] & below);
+        const uint32_t p00 = pos[0], p10 = pos[1], p01 = pos[2], p11 = pos[3];
 #else
         uint32_t p00 = atomicSub(&E[c00 + 1], 1u) - 1u, p10 = 0, p01 = 0, p11 = 0;
         if (du) p10 = atomicSub(&E[c00 + 2], 1u) - 1u;
