@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const
     if (!(fabs(len) <= 2.2204460492503131e-16))
         n = {xdiv(cr.x, len), xdiv(cr.y, len), xdiv(cr.z, len)};
     stg256(nrm4 + i, n.x, n.y, n.z,
-        __longlong_as_double((long long)(nV <= (1u << SB_PACKED_IDX_BITS) ? pack_tri_idx(i0, i1, i2) : SB_PACKED_IDX_NONE)));
+        __longlong_as_double((long long)pack_tri_idx(i0, i1, i2)));
     // 30-bit Morton key of the box centre inside the mesh box (ordering only)
     double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
     double ex = dkey_inv(bounds[3]) - blx, ey = dkey_inv(bounds[4]) - bly, ez = dkey_inv(bounds[5]) - blz;

@@ -135,6 +135,11 @@ struct sb_mesh {
     cudaEvent_t ready = nullptr;     // everything built (incl. the ray grids)
     cudaStream_t treeStream = nullptr; // the (latency-bound) LBVH kernel runs here, beside the grid scan / fill
     cudaEvent_t leavesDone = nullptr;  // leaf kernel finished (orders treeStream behind the mesh stream)
+    // sb_mesh_update put new geometry into a mesh whose reference list was sized for the old one: the next build
+    // fills within the old capacity (bounds-guarded) and sends the new counts to the host; the first use of the
+    // mesh reads them (mesh_finish) -- new big-list lengths, and a proper first build if the capacity was exceeded
+    bool geomChanged = false, verifyPending = false;
+    cudaEvent_t verifyEv = nullptr;
     cudaEvent_t leafReady = nullptr; // sorted leaves / boxes / centroids: all a QUERY mesh needs,
                                      // recorded before the grids (and the LBVH) are built
     uint32_t *radixWs = nullptr;     // in the arena
@@ -446,6 +451,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
         cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithPriority(&m->treeStream, cudaStreamNonBlocking, prioHigh) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->leavesDone, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->verifyEv, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->leafReady, cudaEventDisableTiming) != cudaSuccess) {
         cudaFreeAsync(m->arena, ctx->stream);
         delete m;
@@ -753,6 +759,7 @@ int sb_mesh_update(sb_mesh *m, const void *xyz, const void *tri, int on_device)
         SB_CUDA(cudaMemcpyAsync(m->d.tri, tri, 12 * (size_t)m->d.nT, kind, m->stream));
     m->built = false;
     m->gridPending = false;
+    m->geomChanged = true; // the next build reports its reference counts (mesh_finish checks them against the capacity)
     SB_CUDA(cudaEventRecord(m->ready, m->stream));
     SB_CUDA(cudaEventRecord(m->leafReady, m->stream));
     return SB_OK;
@@ -880,6 +887,11 @@ static int grid_size_and_fill(sb_mesh *m, bool readback = true)
     size_t bytes = refBytes + 16 * 3 * (size_t)std::max<uint32_t>(bigMax, 1);
     if (m->gridArena)
         cudaFreeAsync(m->gridArena, st);
+    if (m->buildGraph) { // the captured rebuild has the old lists' addresses and capacities in its kernel arguments
+        cudaGraphExecDestroy(m->buildGraph);
+        cudaGraphExecDestroy(m->gridGraph);
+        m->buildGraph = m->gridGraph = nullptr;
+    }
     SB_CUDA(cudaMallocAsync(&m->gridArena, bytes, st));
     m->gridArenaBytes = bytes;
     m->d.gridRefs = static_cast<uint2 *>(m->gridArena);
@@ -896,6 +908,24 @@ static int grid_size_and_fill(sb_mesh *m, bool readback = true)
 static int mesh_finish(const sb_mesh *mc)
 {
     sb_mesh *m = const_cast<sb_mesh *>(mc);
+    if (m && m->verifyPending) {
+        // a rebuild after sb_mesh_update: did the new geometry fit the reference lists sized for the old one?
+        m->verifyPending = false;
+        DeviceGuard g(m->ctx);
+        SB_CUDA(cudaEventSynchronize(m->verifyEv));
+        if (*reinterpret_cast<int *>(m->hErr))
+            return mesh_error(m, *reinterpret_cast<int *>(m->hErr));
+        const uint32_t *h = m->hCounts;
+        if (h[0] > m->d.gridRefCap || std::max(h[1], std::max(h[2], h[3])) > m->d.gridBigCap) {
+            m->gridSized = false; // no: a first build sizes them again (counts on their way, finished below)
+            int rb = sb_mesh_build(m);
+            if (rb)
+                return rb;
+        } else {
+            for (int k = 0; k < 3; ++k)
+                m->d.gridBigN[k] = h[1 + k];
+        }
+    }
     if (!m || !m->gridPending)
         return SB_OK;
     m->gridPending = false;
@@ -1041,6 +1071,14 @@ int sb_mesh_build(sb_mesh *m)
             SB_CUDA(cudaGraphLaunch(m->buildGraph, st));
             SB_CUDA(cudaGraphLaunch(m->gridGraph, st));
         }
+        if (m->geomChanged) { // new geometry in a list sized for the old one: counts to the host, checked at first use
+            int rv = grid_counts_readback(m);
+            if (rv)
+                return rv;
+            SB_CUDA(cudaEventRecord(m->verifyEv, st));
+            m->verifyPending = true;
+            m->geomChanged = false;
+        }
         // Recorded at the END of a rebuild on purpose: letting the other mesh's face queries
         // start as soon as the sorted centroids exist (between the two graphs) was measured
         // slower -- the two long classification launches then no longer run side by side and
@@ -1080,8 +1118,16 @@ int sb_mesh_build(sb_mesh *m)
             // deterministic, so the reference count equals the one the list was
             // sized for -- no host round trip (the fill is bounds-guarded anyway).
             SB_CUDA(sbk_grid_fill(st, m->d, c->lc));
+            if (m->geomChanged) {
+                int rv = grid_counts_readback(m);
+                if (rv)
+                    return rv;
+                SB_CUDA(cudaEventRecord(m->verifyEv, st));
+                m->verifyPending = true;
+            }
         }
     }
+    m->geomChanged = false;
     if (m->d.nT && !m->gridSized) {
         // first build: the list has to be sized from the counts.  They are sent to the host
         // here; the rest (size, fill, `ready`) happens at the first use of the mesh
@@ -1179,6 +1225,8 @@ void sb_mesh_destroy(sb_mesh *m)
         cudaEventDestroy(m->leafReady);
     if (m->leavesDone)
         cudaEventDestroy(m->leavesDone);
+    if (m->verifyEv)
+        cudaEventDestroy(m->verifyEv);
     if (m->buildGraph)
         cudaGraphExecDestroy(m->buildGraph);
     if (m->gridGraph)

@@ -632,7 +632,6 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     T.vtx = target.vtx;
     T.tri = target.tri;
     T.nrm4 = target.nrm4;
-    T.packedIdx = target.nV <= (1u << SB_PACKED_IDX_BITS);
     Out o = {};
     o.inside = a.inside;
     o.perAxis = a.perAxis;

@@ -52,7 +52,6 @@ struct Target {
     int naxes;                 // ray grids the target has (2: the third is built on demand, see ensure_grid3)
     const double4 *vtx;
     const uint32_t *tri;
-    bool packedIdx;            // nrm4[].w holds the vertex indices (meshes of at most 2^21 vertices)
     const double4 *nrm4;       // per triangle: unit normal + packed vertex indices (sb_common.cuh)
 };
 
@@ -225,13 +224,10 @@ __device__ __forceinline__ bool eval_entry(const Target &T, const d3 &p, int axi
     // first round trip: the triangle's record = normal + packed vertex indices (one 256-bit gather) ...
     const double4 rec = ldg256(T.nrm4 + f);
     uint32_t i0, i1, i2;
-    if (T.packedIdx) {
-        const unsigned long long w = (unsigned long long)__double_as_longlong(rec.w);
-        constexpr uint32_t m = (1u << SB_PACKED_IDX_BITS) - 1u;
-        i0 = (uint32_t)w & m;
-        i1 = (uint32_t)(w >> SB_PACKED_IDX_BITS) & m;
-        i2 = (uint32_t)(w >> (2 * SB_PACKED_IDX_BITS)) & m;
-    } else {
+    const unsigned long long w = (unsigned long long)__double_as_longlong(rec.w);
+    if (w != SB_PACKED_IDX_NONE) {
+        unpack_tri_idx(w, i0, i1, i2);
+    } else { // (rare: corners too far apart in the vertex array, or more than 4 M vertices)
         i0 = __ldg(T.tri + 3 * (size_t)f);
         i1 = __ldg(T.tri + 3 * (size_t)f + 1);
         i2 = __ldg(T.tri + 3 * (size_t)f + 2);

@@ -144,15 +144,28 @@ __device__ __forceinline__ d3 load_vertex(const double4 *v, uint32_t i)
 }
 
 // Per-triangle record of the classifier (sb_build.cu writes it, sb_classify*.cu read it): the unit normal
-// (SolidMesh::prepare, src/solidmesh.cpp:47-55) and, in the fourth word, the triangle's three vertex indices,
-// 21 bits each -- ONE 256-bit gather instead of three index loads followed by three normal loads, and one
-// dependent round trip less.  Meshes with more than 2^21 vertices leave the word all ones and the kernels
-// read the index triple from `tri`.
-#define SB_PACKED_IDX_BITS 21
+// (SolidMesh::prepare, src/solidmesh.cpp:47-55) and, in the fourth word, the triangle's three vertex indices
+// -- ONE 256-bit gather instead of three index loads followed by three normal loads, and one dependent round
+// trip less.  Layout of the word: i0 in 22 bits, i1 - i0 and i2 - i0 as signed 21-bit differences (the corners
+// of a triangle are rarely more than a million vertices apart; a batch mesh keeps every job's vertices together).
+// A triangle that does not fit (i0 >= 2^22 - 1 or a difference outside +-2^20) gets the all-ones word and the
+// kernels read its index triple from `tri`.
 #define SB_PACKED_IDX_NONE 0xffffffffffffffffull
 __device__ __forceinline__ unsigned long long pack_tri_idx(uint32_t i0, uint32_t i1, uint32_t i2)
 {
-    return (unsigned long long)i0 | ((unsigned long long)i1 << SB_PACKED_IDX_BITS) | ((unsigned long long)i2 << (2 * SB_PACKED_IDX_BITS));
+    const long long d1 = (long long)i1 - (long long)i0, d2 = (long long)i2 - (long long)i0;
+    const long long lim = 1ll << 20;
+    if (i0 >= (1u << 22) - 1u || d1 < -lim || d1 >= lim || d2 < -lim || d2 >= lim)
+        return SB_PACKED_IDX_NONE;
+    return (unsigned long long)i0 | ((unsigned long long)(d1 & 0x1fffff) << 22) | ((unsigned long long)(d2 & 0x1fffff) << 43);
+}
+__device__ __forceinline__ void unpack_tri_idx(unsigned long long w, uint32_t &i0, uint32_t &i1, uint32_t &i2)
+{
+    i0 = (uint32_t)w & 0x3fffffu;
+    const int d1 = ((int)((uint32_t)(w >> 22) << 11)) >> 11; // sign-extend 21 bits
+    const int d2 = ((int)((uint32_t)(w >> 43) << 11)) >> 11;
+    i1 = (uint32_t)((int)i0 + d1);
+    i2 = (uint32_t)((int)i0 + d2);
 }
 
 __device__ __forceinline__ uint32_t lanemask_lt()

@@ -661,3 +661,65 @@ def test_config_c4_stated_size_vs_reference_pins(ctx):
     """BASELINE config 4 at its stated size: near-coincident icospheres k=8, 1,310,720 x2 triangles,
     8,238,598 candidate pairs."""
     _check_against_fullsize_pins(ctx, "c4k8", *meshgen.config_c4(k=8))
+
+
+def test_mesh_update_new_geometry_into_sized_lists(ctx, oracle):
+    """sb_mesh_update + sb_mesh_build: new coordinates of the same counts into meshes whose ray-grid reference
+    lists were sized for the old geometry.  The rebuild fills within the old capacity and reports its counts;
+    the first use checks them (more references than the capacity -> the lists are sized again).  Every frame
+    must equal the oracle on that frame's geometry -- including frames that need MORE references than the
+    first one (stretched so that the triangle boxes straddle many more cells) and big-list triangles that
+    appear only later."""
+    a0, b0 = meshgen.icosphere(4), meshgen.torus(64, 32, center=(0.013, 0.007, 0.011))
+    ma, mb = ctx.mesh(*a0), ctx.mesh(*b0)
+    rng = np.random.default_rng(5)
+
+    def frames():
+        yield a0[0] * np.array([1.0, 1.0, 0.05]), b0[0]                       # squashed: anisotropic boxes
+        yield a0[0] + rng.normal(0, 0.02, a0[0].shape), b0[0] * 1.1          # noisy: larger, overlapping boxes
+        va = a0[0].copy(); va[::97] *= 40.0                                   # a few far vertices: huge triangles (big lists)
+        yield va, b0[0]
+        yield a0[0], b0[0]                                                    # and back
+    for va, vb in frames():
+        xa = np.ascontiguousarray(va, np.float64); xb = np.ascontiguousarray(vb, np.float64)
+        ma.update(xa.ctypes.data, 0); mb.update(xb.ctypes.data, 0)
+        ma.build(); mb.build()
+        a, b = (xa, a0[1]), (xb, b0[1])
+        x = ma.intersect(mb)
+        ab, code = x.candidates()
+        ref = oracle.candidate_pairs(a, b)
+        assert np.array_equal(ab, ref)
+        ret, cop, hit, seg = oracle.predicate_pairs(a, b, ref)
+        hab, hseg = x.hits()
+        assert np.array_equal(hab, ref[hit.astype(bool)]) and hseg.tobytes() == seg[hit.astype(bool)].tobytes()
+        ia, pa = ma.classify_faces_against(mb)
+        ib, pb = mb.classify_faces_against(ma)
+        oa, opa, _ = oracle.classify(b, oracle.centroids(*a))
+        ob, opb, _ = oracle.classify(a, oracle.centroids(*b))
+        assert np.array_equal(pa, opa) and np.array_equal(ia, oa)
+        assert np.array_equal(pb, opb) and np.array_equal(ib, ob)
+        x.close()
+    ma.close(); mb.close()
+
+
+def test_vertex_indices_far_apart_use_the_index_fallback(ctx, oracle):
+    """The classifier's triangle record packs the three vertex indices as (i0, i1 - i0, i2 - i0) with 21-bit
+    differences; a triangle whose corners lie more than 2^20 vertices apart keeps the all-ones word and the kernel
+    reads `tri`.  Target with 2.2 M vertices, every triangle using one far copy of a corner."""
+    v, t = meshgen.icosphere(3)
+    far = 2_200_000
+    big = np.repeat(v[:1], far + len(v), axis=0)
+    big[:len(v)] = v
+    big[far:far + len(v)] = v
+    t2 = t.copy()
+    t2[:, 1] += far                                    # second corner from the far copy: |i1 - i0| > 2^20
+    tgt = (np.ascontiguousarray(big), np.ascontiguousarray(t2.astype(np.uint32)))
+    q = meshgen.torus(48, 24, center=(0.013, 0.007, 0.011))
+    mt, mq = ctx.mesh(*tgt), ctx.mesh(*q)
+    iq, pq = mq.classify_faces_against(mt)
+    oi, op, _ = oracle.classify(tgt, oracle.centroids(*q))
+    assert np.array_equal(pq, op) and np.array_equal(iq, oi)
+    x = mq.intersect(mt)
+    ab, _ = x.candidates()
+    assert np.array_equal(ab, oracle.candidate_pairs(q, tgt))
+    x.close(); mt.close(); mq.close()
