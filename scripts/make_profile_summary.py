@@ -70,13 +70,16 @@ with open(out_md, "w") as f:
             "compare SHARES, never absolutes; bench values are never taken from these runs.\n\n")
     f.write("## Launch list of `SB_GRAPHS=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (graphs off so that every kernel is listed)\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (raw list: profiles/" + RND + "_launches_bench.csv;\n"
-            "3 resident steps + 5 host-buffer steps; fp64_peak_kernel = the FP64 issue-rate microbenchmark of the bench line; torch kernels = L2 flush / result copies)\n\n")
+            "C3: 3 resident steps + 9 host-buffer steps; the `other_configs` leg: 13 steps each of C2 and of C4 at its stated size (8.2 M candidate pairs: most of the\n"
+            "broad_phase / predicate / classify2 time of this list); the `next_rows` leg: 4 repetitions of the widened rows (cuts_*, rank_*, uncut_*, halfedge_*, cc_*);\n"
+            "fp64_peak_kernel = the FP64 issue-rate microbenchmark of the bench line; torch kernels = L2 flush / result copies)\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write("| %s | %d | %.1f | %.1f%% |\n" % (k, len(v), sum(v), 100 * sum(v) / tot))
     f.write("| **all** | %d | %.1f | 100%% |\n\n" % (sum(len(v) for v in agg.values()), tot))
     f.write("## Per-kernel counters of one serial step (`SB_GRAPHS=0 scripts/stage_times.py c3 2 --serial`, the launches of the second step)\n")
-    f.write("`ncu --set full --clock-control none`; execution order (the window may start inside a step):\n"
+    f.write("`ncu --section SpeedOfLight,MemoryWorkloadAnalysis,ComputeWorkloadAnalysis,Occupancy,LaunchStats,WarpStateStats,SchedulerStats,InstructionStats`\n"
+            "`+ dram / L1-pipe / fp64 metrics, --clock-control none`; execution order (the window may start inside a step):\n"
             "build(A), build(B), broad phase, predicate, hit-key sort, classify A-in-B, classify B-in-A; torch kernels = the script's own result checks.\n"
             "`L1 pipe %` = l1tex__data_pipe_lsu_wavefronts (the busiest unit of the classifier).  The source-level capture of the classifier\n"
             "(`--set full --import-source on`) is summarised in profiles/" + RND + "_classify_lines.md; `GB/s` = (dram rd + dram wr) / time against the measured 6,558 GB/s copy rate.\n\n")
