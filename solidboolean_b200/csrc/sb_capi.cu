@@ -357,6 +357,17 @@ int alloc_async(sb_context *c, T **p, size_t count, std::vector<void *> *owned)
     return SB_OK;
 }
 
+// releases a stream-ordered scratch allocation on every way out of a function
+struct ScratchGuard {
+    void *p;
+    cudaStream_t s;
+    ~ScratchGuard()
+    {
+        if (p)
+            cudaFreeAsync(p, s);
+    }
+};
+
 int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJobs = 0, const sb_mesh *vertexParent = nullptr)
 {
     if (nV >= (1ull << 31) || nT >= (1ull << SB_MAX_TRIANGLE_BITS))
@@ -491,6 +502,8 @@ int sb_context_create(int device, sb_context **out)
     if (!c)
         return fail(SB_ERR_NOMEM, "out of host memory");
     c->device = device;
+    // (everything below that can fail runs inside `init`: a failure releases what was created so far)
+    auto init = [&]() -> int {
     cudaDeviceProp prop;
     SB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->smCount = prop.multiProcessorCount;
@@ -517,6 +530,16 @@ int sb_context_create(int device, sb_context **out)
     SB_CUDA(cudaEventCreate(&c->t0));
     SB_CUDA(cudaEventCreateWithFlags(&c->orderEvent, cudaEventDisableTiming));
     SB_CUDA(cudaEventRecord(c->t0, c->stream));
+    return SB_OK;
+    };
+    if (int r = init()) {
+        char msg[512];
+        snprintf(msg, sizeof(msg), "%s", g_err);
+        sb_context_destroy(c); // tolerates the members that were never created
+        cudaGetLastError();
+        snprintf(g_err, sizeof(g_err), "%s", msg);
+        return r;
+    }
     if (const char *e = getenv("SB_SORT_BEGIN_BIT"))
         c->sortBeginBit = std::max(0, std::min(atoi(e), 24));
     if (const char *e = getenv("SB_GRAPHS"))
@@ -1491,7 +1514,7 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
     unsigned long long *keys = nullptr;
     size_t nCand = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        SB_TRY(alloc_async(c, &keys, cap, nullptr));
+        SB_TRY(alloc_async(c, &keys, cap, &x->owned)); // owned from the start: an error below releases it with the isect
         {
             StageTimer t(c, SB_STAGE_BROAD);
             SB_CUDA_X(cudaMemsetAsync(c->dScalars, 0, sizeof(DeviceScalars), c->stream));
@@ -1503,13 +1526,13 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         nCand = (size_t)c->hScalars->pairCount;
         if (nCand <= cap)
             break;
+        x->owned.pop_back();
         cudaFreeAsync(keys, c->stream);
         keys = nullptr;
         if (attempt == 1)
             return bail(fail(SB_ERR_CAPACITY, "candidate buffer overflow after retry (%zu > %zu)", nCand, cap));
         cap = nCand;
     }
-    x->owned.push_back(keys);
     if (nCand >= (1ull << 32))
         return bail(fail(SB_ERR_CAPACITY, "too many candidate pairs (%zu)", nCand));
     x->nCand = nCand;
@@ -1879,7 +1902,11 @@ int sb_mesh_uncut(const sb_mesh *mesh, const uint8_t *cut_flags, size_t vertex_o
         int r = alloc_async(c, &dCut, mesh->d.nT, nullptr);
         if (r)
             return r;
-        SB_CUDA(cudaMemcpyAsync(dCut, cut_flags, mesh->d.nT, cudaMemcpyHostToDevice, c->stream));
+        cudaError_t ec = cudaMemcpyAsync(dCut, cut_flags, mesh->d.nT, cudaMemcpyHostToDevice, c->stream);
+        if (ec != cudaSuccess) {
+            cudaFreeAsync(dCut, c->stream);
+            return fail(SB_ERR_CUDA, "cudaMemcpyAsync(cut flags): %s", cudaGetErrorString(ec));
+        }
     }
     int r = uncut_run(mesh, dCut, vertex_offset, triangle_offset, out);
     if (dCut)
@@ -2495,6 +2522,7 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
     r = alloc_async(c, &dPts, 3 * Q, nullptr);
     if (r)
         return r;
+    ScratchGuard ptsGuard{dPts, c->stream};
     SB_CUDA(cudaMemcpyAsync(dPts, pts, 24 * Q, cudaMemcpyHostToDevice, c->stream));
     ClassifyArgs a;
     a.pts = dPts;
@@ -2514,7 +2542,6 @@ int sb_classify(const sb_mesh *target, const double *pts, size_t Q, uint8_t *ins
             SB_CUDA(cudaMemcpyAsync(per_axis, a.perAxis, 3 * Q, cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA(cudaStreamSynchronize(c->stream));
     }
-    cudaFreeAsync(dPts, c->stream);
     return r;
 }
 

@@ -243,6 +243,10 @@ void ReTriangulator::triangulateRegions()
         for (size_t h : holeLoops)
             push(m_loops[h]);
         std::vector<size_t> tri = earclip::triangulate(rings);
+        // a simple polygon with h holes has n + 2h - 2 triangles; fewer = no ear found, a hole without a visible
+        // bridge, or a degenerate rest (earcut.hpp hands back its partial output just as silently: counted here)
+        if (tri.size() / 3 != local.size() + 2 * holeLoops.size() - 2)
+            ++m_incompleteRegions;
         for (size_t i = 0; i + 2 < tri.size(); i += 3)
             m_triangles.push_back({local[tri[i]], local[tri[i + 1]], local[tri[i + 2]]});
     };

@@ -23,6 +23,8 @@ public:
     bool reTriangulate();
     const std::vector<std::vector<size_t>> &polygons() const { return m_polygons; }
     const std::vector<std::vector<size_t>> &triangles() const { return m_triangles; }
+    // regions whose triangulation came out short (see triangulateRegions); 0 on well-formed input
+    size_t incompleteRegions() const { return m_incompleteRegions; }
 
 private:
     typedef std::array<double, 2> P2;
@@ -39,6 +41,7 @@ private:
     std::vector<std::vector<size_t>> m_loops;     // closed chains
     std::vector<std::vector<size_t>> m_polygons;  // boundary ring split by the polylines
     std::vector<std::vector<size_t>> m_triangles;
+    size_t m_incompleteRegions = 0;
 };
 
 #endif

@@ -136,6 +136,8 @@ bool SolidBoolean::retriangulateCutTriangles(const std::map<size_t, CutTriangle>
             std::cout << "Retriangle failed" << std::endl;
             return false;
         }
+        if (splitter.incompleteRegions()) // reported the reference's way (a message, no exception); the result may have a hole there
+            std::cout << "Retriangle incomplete: triangle " << it.first << ", " << splitter.incompleteRegions() << " region(s)" << std::endl;
         std::vector<size_t> global = {t[0] + vertexOffset, t[1] + vertexOffset, t[2] + vertexOffset};
         for (const Vector3 &p : it.second.points)
             global.push_back(weldPoint(p));
