@@ -231,6 +231,18 @@ int sb_uncut_adjacency(const sb_uncut *u, int32_t *adj3);
  * triangle index of j's component, i.e. the triangle the reference's loop over ascending indices
  * opens that group with; *n_components = number of groups.  SURVEY 8f row 3.  label may be NULL. */
 int sb_uncut_components(const sb_uncut *u, uint32_t *label, size_t *n_components);
+/* The whole flood of buildFaceGroups (src/solidboolean.cpp:167-239) for one mesh's side of the result: the uncut
+ * triangles of `u` AND the retriangulated pieces the host produced (pieces: 3 x n_pieces vertex ids in the numbering of
+ * the result vertex array, i.e. with u's vertex offset applied to original vertices).  fences: 2 x n_fences vertex ids,
+ * the edges of the intersection loops (:176-203): a fill does not cross them in either direction.  Triangles joined through
+ * opposite half-edges that are not fences form a group (connected components on the device, sb_flood.cu).  NODES are
+ * numbered: uncut triangle j -> j (0 .. n_triangles-1, the order of sb_uncut_triangles), piece i -> n_triangles + i;
+ * label_uncut[j] / label_piece[i] = the lowest node of the triangle's group; *n_groups = number of groups.
+ * Where two loop seeds of the reference reach the same region its queue order splits the region between two groups on the
+ * same side of every loop; a group here is the union of those (same triangles selected by every operation).
+ * Not offered (SB_ERR_INVALID) when the half-edge map was truncated by a repeated half-edge.  SURVEY 8f row 3. */
+int sb_uncut_face_groups(const sb_uncut *u, const uint32_t *pieces, size_t n_pieces, const uint32_t *fences, size_t n_fences,
+                         uint32_t *label_uncut, uint32_t *label_piece, size_t *n_groups);
 /* Device pointers of the same arrays (valid until sb_uncut_destroy) for device-side consumers;
  * any out pointer may be NULL.  After a repeated half-edge (*ok == 0) they hold the untruncated
  * arrays of ALL uncut faces. */

@@ -111,6 +111,7 @@ ABI = {
     "sb_uncut_half_edges": (C.c_int, [_vp, _vp, _vp]),
     "sb_uncut_adjacency": (C.c_int, [_vp, _vp]),
     "sb_uncut_components": (C.c_int, [_vp, _vp, C.POINTER(_sz)]),
+    "sb_uncut_face_groups": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, C.POINTER(_sz)]),
     "sb_uncut_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                        C.POINTER(_vp)]),
     "sb_classify": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
@@ -659,6 +660,18 @@ class Uncut:
         n = _sz(0)
         _check(self.lib.sb_uncut_components(self.h, _ptr(label), C.byref(n)))
         return label, int(n.value)
+
+    def face_groups(self, pieces, fences):
+        """sb_uncut_face_groups: the flood over the uncut triangles and the retriangulated `pieces` [nP, 3] (result
+        vertex ids), not crossing the `fences` [nF, 2] -> label_uncut [n], label_piece [nP] (lowest node of the group;
+        nodes = uncut triangles 0..n-1, then pieces), group count"""
+        pc = np.ascontiguousarray(pieces, np.uint32).reshape(-1, 3)
+        fc = np.ascontiguousarray(fences, np.uint32).reshape(-1, 2)
+        lu, lp = np.zeros(self.num_triangles, np.uint32), np.zeros(len(pc), np.uint32)
+        n = _sz(0)
+        _check(self.lib.sb_uncut_face_groups(self.h, _ptr(pc) if len(pc) else None, len(pc), _ptr(fc) if len(fc) else None, len(fc),
+                                             _ptr(lu) if len(lu) else None, _ptr(lp) if len(lp) else None, C.byref(n)))
+        return lu, lp, int(n.value)
 
     def device_ptrs(self):
         p = [_vp() for _ in range(5)]

@@ -22,7 +22,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libsolidboolean_b200.so")
-SOURCES = ["sb_capi.cu", "sb_build.cu", "sb_broad.cu", "sb_narrow.cu", "sb_classify.cu", "sb_classify2.cu", "sb_grid.cu", "sb_halfedge.cu", "sb_cuts.cu", "sb_shard.cu", "sb_comm.cu"]
+SOURCES = ["sb_capi.cu", "sb_build.cu", "sb_broad.cu", "sb_narrow.cu", "sb_classify.cu", "sb_classify2.cu", "sb_grid.cu", "sb_halfedge.cu", "sb_cuts.cu", "sb_shard.cu", "sb_comm.cu", "sb_flood.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
          "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]

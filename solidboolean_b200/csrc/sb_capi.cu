@@ -2117,6 +2117,84 @@ int sb_uncut_components(const sb_uncut *uc, uint32_t *label, size_t *n_component
     return SB_OK;
 }
 
+// the flood of buildFaceGroups over the uncut triangles AND the retriangulated pieces (sb_flood.cu)
+int sb_uncut_face_groups(const sb_uncut *uc, const uint32_t *pieces, size_t n_pieces, const uint32_t *fences, size_t n_fences,
+    uint32_t *label_uncut, uint32_t *label_piece, size_t *n_groups)
+{
+    sb_uncut *u = const_cast<sb_uncut *>(uc);
+    if (!u || (n_pieces && (!pieces || !label_piece)) || (n_fences && !fences))
+        return fail(SB_ERR_INVALID, "null argument");
+    if (n_pieces >= (1u << 28) || n_fences >= (1u << 28))
+        return fail(SB_ERR_INVALID, "too many pieces / fences");
+    sb_context *c = u->ctx;
+    DeviceGuard g(c);
+    if (n_groups)
+        *n_groups = 0;
+    if (u->repeatOrd != 0xffffffffu)
+        return fail(SB_ERR_INVALID, "the half-edge map was truncated by a repeated half-edge: the groups then depend on the order of the "
+                                    "reference's flood (host)");
+    const uint32_t nU = u->nTri, nP = (uint32_t)n_pieces, nF = (uint32_t)n_fences;
+    if (nU && !label_uncut)
+        return fail(SB_ERR_INVALID, "label_uncut is null");
+    if (nU + (size_t)nP == 0)
+        return SB_OK;
+    if (nU) { // the uncut triangles' own components first (kept on the device)
+        int r = sb_uncut_components(u, nullptr, nullptr);
+        if (r)
+            return r;
+    }
+    StageTimer timer(c, SB_STAGE_HALFEDGE);
+    uint32_t maxV = 0;
+    for (size_t i = 0; i < 3 * n_pieces; ++i)
+        maxV = std::max(maxV, pieces[i]);
+    for (size_t i = 0; i < 2 * n_fences; ++i)
+        maxV = std::max(maxV, fences[i]);
+    unsigned keyBits = 1;
+    while (keyBits < 32 && (maxV >> keyBits))
+        ++keyBits;
+    uint32_t *dPieces = nullptr, *dFences = nullptr, *scratch = nullptr, *dLabU = nullptr, *dLabP = nullptr;
+    std::vector<void *> tmp;
+    auto bail = [&](int rc) {
+        for (void *q : tmp)
+            cudaFreeAsync(q, c->stream);
+        return rc;
+    };
+#define SB_TRY_F(expr)             \
+    do {                           \
+        int r_ = (expr);           \
+        if (r_)                    \
+            return bail(r_);       \
+    } while (0)
+#define SB_CUDA_F(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return bail(fail(SB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)));           \
+    } while (0)
+    SB_TRY_F(alloc_async(c, &dPieces, 3 * n_pieces, &tmp));
+    SB_TRY_F(alloc_async(c, &dFences, 2 * n_fences, &tmp));
+    SB_TRY_F(alloc_async(c, &scratch, sbk_flood_scratch_words(nU, nP, nF), &tmp));
+    SB_TRY_F(alloc_async(c, &dLabU, nU, &tmp));
+    SB_TRY_F(alloc_async(c, &dLabP, nP, &tmp));
+    if (nP)
+        SB_CUDA_F(cudaMemcpyAsync(dPieces, pieces, 12 * n_pieces, cudaMemcpyHostToDevice, c->stream));
+    if (nF)
+        SB_CUDA_F(cudaMemcpyAsync(dFences, fences, 8 * n_fences, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA_F(sbk_flood(c->stream, dPieces, nP, dFences, nF, u->keys, u->owner, 3 * nU, u->label, nU, u->triangleOffset, keyBits, scratch,
+        c->smCount, dLabU, dLabP, &c->dScalars->ccCount, c->lc));
+    SB_CUDA_F(cudaMemcpyAsync(&c->hScalars->ccCount, &c->dScalars->ccCount, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    if (nU)
+        SB_CUDA_F(cudaMemcpyAsync(label_uncut, dLabU, 4 * (size_t)nU, cudaMemcpyDeviceToHost, c->stream));
+    if (nP)
+        SB_CUDA_F(cudaMemcpyAsync(label_piece, dLabP, 4 * (size_t)nP, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA_F(cudaStreamSynchronize(c->stream));
+#undef SB_TRY_F
+#undef SB_CUDA_F
+    if (n_groups)
+        *n_groups = c->hScalars->ccCount;
+    return bail(SB_OK);
+}
+
 int sb_uncut_device_ptrs(const sb_uncut *u, void **face, void **tri3, void **keys, void **owner, void **adj3)
 {
     if (!u)

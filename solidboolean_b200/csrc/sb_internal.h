@@ -138,6 +138,12 @@ cudaError_t sbk_uncut_components(cudaStream_t s, const int32_t *adj, uint32_t nT
     const uint32_t *sortedTri /* Morton order of the mesh, or null */, const uint32_t *face, uint32_t nT, uint32_t *scratch,
     uint32_t *label, uint32_t *count, LaunchCounter &lc);
 
+// sb_flood.cu -- buildFaceGroups over uncut components + retriangulated pieces
+size_t sbk_flood_scratch_words(uint32_t nU, uint32_t nP, uint32_t nF);
+cudaError_t sbk_flood(cudaStream_t s, const uint32_t *pieces, uint32_t nP, const uint32_t *fences, uint32_t nF,
+    const unsigned long long *uKeys, const uint32_t *uOwner, uint32_t nUK, const uint32_t *uLabel, uint32_t nU, uint32_t triangleOffset,
+    unsigned keyBits, uint32_t *scratch, int smCount, uint32_t *labelUncut, uint32_t *labelPiece, unsigned int *nGroups, LaunchCounter &lc);
+
 // sb_cuts.cu -- per-triangle intersection contexts (the pair-loop body of SolidBoolean::combine)
 size_t sbk_cut_contexts_scratch(size_t nHits); // 4-byte words
 cudaError_t sbk_cut_contexts(cudaStream_t s, const uint32_t *hitAB, const double *seg, uint32_t n, int which, unsigned bitsTri,

@@ -95,8 +95,15 @@ bool SolidBoolean::copyUncutTriangles(const void *isect, int which, size_t verte
     topology.grouped = false;
     // SB_HOST_FLOOD=legacy: triangle-by-triangle flood through the half-edge map, as the reference
     // does it (comparison / debugging)
+    // SB_HOST_FLOOD=host: the flood over the retriangulated pieces on the host (round 1), the uncut components from the GPU
     static const bool legacyFlood = [] { const char *e = std::getenv("SB_HOST_FLOOD"); return e && std::string(e) == "legacy"; }();
-    if (rc == SB_OK && ok && triangleCount && !legacyFlood) {
+    static const bool hostFlood = [] { const char *e = std::getenv("SB_HOST_FLOOD"); return e && std::string(e) == "host"; }();
+    if (rc == SB_OK && ok && !legacyFlood && !hostFlood) {
+        // the whole flood runs on the GPU once the pieces exist (deviceFaceGroups): the object stays alive until then
+        topology.device = uncut;
+        topology.grouped = true;
+        uncut = nullptr;
+    } else if (rc == SB_OK && ok && triangleCount && !legacyFlood) {
         // face groups + neighbours of the uncut triangles, computed on the GPU
         topology.label.resize(triangleCount);
         topology.adjacency.resize(3 * triangleCount);
@@ -105,7 +112,8 @@ bool SolidBoolean::copyUncutTriangles(const void *isect, int which, size_t verte
             rc = sb_uncut_adjacency(uncut, topology.adjacency.data());
         topology.grouped = rc == SB_OK;
     }
-    sb_uncut_destroy(uncut);
+    if (uncut)
+        sb_uncut_destroy(uncut);
     if (rc != SB_OK) {
         std::cout << "addUnintersectedTriangles failed: " << sb_last_error() << std::endl;
         return false;
@@ -203,6 +211,52 @@ bool SolidBoolean::traceLoops(const EdgeGraph &edges, std::vector<std::vector<si
             return false;
         }
         loops.push_back(loop);
+    }
+    return true;
+}
+
+// buildFaceGroups on the GPU (sb_uncut_face_groups): the uncut triangles of this mesh's side (kept on
+// the device since addUnintersectedTriangles) and its retriangulated pieces m_newTriangles[pieceBegin, pieceEnd) are
+// flooded together, the edges of the intersection loops are the fences.  Groups come back as labels (lowest node of the
+// group) and are laid out in ascending label order; within a group the triangles ascend.
+bool SolidBoolean::deviceFaceGroups(const std::vector<std::vector<size_t>> &loops, const UncutTopology &uncut, size_t pieceBegin,
+    size_t pieceEnd, std::vector<std::vector<size_t>> &groups)
+{
+    const size_t pieceCount = pieceEnd - pieceBegin;
+    std::vector<uint32_t> pieces(3 * pieceCount), fences;
+    for (size_t i = 0; i < pieceCount; ++i)
+        for (int k = 0; k < 3; ++k)
+            pieces[3 * i + k] = (uint32_t)m_newTriangles[pieceBegin + i][k];
+    for (const auto &loop : loops)
+        for (size_t i = 0; i < loop.size(); ++i) {
+            fences.push_back((uint32_t)loop[i]);
+            fences.push_back((uint32_t)loop[(i + 1) % loop.size()]);
+        }
+    std::vector<uint32_t> labelUncut(uncut.count), labelPiece(pieceCount);
+    size_t groupCount = 0;
+    if (sb_uncut_face_groups(static_cast<const sb_uncut *>(uncut.device), pieces.data(), pieceCount, fences.data(), fences.size() / 2,
+            labelUncut.data(), labelPiece.data(), &groupCount) != SB_OK) {
+        std::cout << "buildFaceGroups on the device failed: " << sb_last_error() << std::endl;
+        return false;
+    }
+    // label (a node id) -> group index in ascending label order; counting sort of the members
+    const size_t nodeCount = uncut.count + pieceCount;
+    std::vector<uint32_t> groupOf(nodeCount, 0xffffffffu);
+    size_t next = 0;
+    for (size_t n = 0; n < nodeCount; ++n) {
+        const uint32_t l = n < uncut.count ? labelUncut[n] : labelPiece[n - uncut.count];
+        if (l == n)
+            groupOf[n] = (uint32_t)next++;
+    }
+    std::vector<size_t> sizes(next, 0);
+    for (size_t n = 0; n < nodeCount; ++n)
+        ++sizes[groupOf[n < uncut.count ? labelUncut[n] : labelPiece[n - uncut.count]]];
+    groups.assign(next, std::vector<size_t>());
+    for (size_t g = 0; g < next; ++g)
+        groups[g].reserve(sizes[g]);
+    for (size_t n = 0; n < nodeCount; ++n) {
+        const uint32_t l = n < uncut.count ? labelUncut[n] : labelPiece[n - uncut.count];
+        groups[groupOf[l]].push_back(n < uncut.count ? uncut.first + n : pieceBegin + (n - uncut.count));
     }
     return true;
 }
@@ -433,16 +487,30 @@ bool SolidBoolean::combine()
     sb_isect_destroy(isect);
     benchEnd_addUnintersectedTriangles = now();
 
+    // (the uncut objects stay on the device for the flood; released on every way out)
+    struct UncutRelease {
+        UncutTopology &a, &b;
+        ~UncutRelease()
+        {
+            if (a.device) sb_uncut_destroy(static_cast<sb_uncut *>(a.device));
+            if (b.device) sb_uncut_destroy(static_cast<sb_uncut *>(b.device));
+            a.device = b.device = nullptr;
+        }
+    } uncutRelease{firstUncut, secondUncut};
+
     benchBegin_reTriangulate = now();
     EdgeGraph firstLoopEdges, secondLoopEdges;
+    const size_t firstPieceBegin = m_newTriangles.size();
     if (!retriangulateCutTriangles(firstCuts, m_firstMesh, 0, firstHalfEdges, firstLoopEdges)) {
         std::cout << "Retriangulate first mesh failed" << std::endl;
         return false;
     }
+    const size_t secondPieceBegin = m_newTriangles.size();
     if (!retriangulateCutTriangles(secondCuts, m_secondMesh, firstVertexCount, secondHalfEdges, secondLoopEdges)) {
         std::cout << "Retriangulate second mesh failed" << std::endl;
         return false;
     }
+    const size_t secondPieceEnd = m_newTriangles.size();
     benchEnd_reTriangulate = now();
 
     benchBegin_buildPolygonsFromEdges = now();
@@ -454,8 +522,23 @@ bool SolidBoolean::combine()
     benchEnd_buildPolygonsFromEdges = now();
 
     benchBegin_buildFaceGroups = now();
-    growFaceGroups(loops, firstHalfEdges, firstUncut, firstStart, firstCount, m_firstGroups);
-    growFaceGroups(loops, secondHalfEdges, secondUncut, secondStart, secondCount, m_secondGroups);
+    // host flood (the device one was refused or is switched off): the uncut components and their neighbours from the GPU
+    // (round 1), the walk over the retriangulated pieces here
+    auto hostFlood = [&](UncutTopology &u, const HalfEdgeMap &map, size_t start, size_t count, std::vector<std::vector<size_t>> &groups) {
+        if (u.device && u.label.empty() && u.count) {
+            u.label.resize(u.count);
+            u.adjacency.resize(3 * u.count);
+            const sb_uncut *d = static_cast<const sb_uncut *>(u.device);
+            u.grouped = sb_uncut_components(d, u.label.data(), nullptr) == SB_OK && sb_uncut_adjacency(d, u.adjacency.data()) == SB_OK;
+        } else if (u.device && !u.count) {
+            u.grouped = false;
+        }
+        growFaceGroups(loops, map, u, start, count, groups);
+    };
+    if (!firstUncut.device || !deviceFaceGroups(loops, firstUncut, firstPieceBegin, secondPieceBegin, m_firstGroups))
+        hostFlood(firstUncut, firstHalfEdges, firstStart, firstCount, m_firstGroups);
+    if (!secondUncut.device || !deviceFaceGroups(loops, secondUncut, secondPieceBegin, secondPieceEnd, m_secondGroups))
+        hostFlood(secondUncut, secondHalfEdges, secondStart, secondCount, m_secondGroups);
     benchEnd_buildFaceGroups = now();
 
     // ---- GPU: inside/outside of every group ----

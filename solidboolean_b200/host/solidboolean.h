@@ -75,6 +75,7 @@ private:
         bool grouped = false; // labels / adjacency valid (false after a repeated half-edge)
         std::vector<uint32_t> label;
         std::vector<int32_t> adjacency;
+        void *device = nullptr; // sb_uncut kept for the device flood (sb_uncut_face_groups); released by combine()
     };
 
     static uint64_t halfEdgeKey(size_t from, size_t to) { return ((uint64_t)from << 32) | (uint64_t)to; }
@@ -84,6 +85,8 @@ private:
     bool retriangulateCutTriangles(const std::map<size_t, CutTriangle> &cuts, const SolidMesh *mesh, size_t vertexOffset,
         HalfEdgeMap &halfEdges, EdgeGraph &loopEdges);
     bool traceLoops(const EdgeGraph &edges, std::vector<std::vector<size_t>> &loops);
+    bool deviceFaceGroups(const std::vector<std::vector<size_t>> &loops, const UncutTopology &uncut, size_t pieceBegin, size_t pieceEnd,
+        std::vector<std::vector<size_t>> &groups);
     void growFaceGroups(const std::vector<std::vector<size_t>> &loops, const HalfEdgeMap &halfEdges, const UncutTopology &uncut,
         size_t firstTriangle, size_t triangleCount, std::vector<std::vector<size_t>> &groups);
     bool classifyGroups(const std::vector<std::vector<size_t>> &groups, const SolidMesh *against, std::vector<bool> &inside);

@@ -207,6 +207,11 @@ int sb_uncut_components(const sb_uncut *u, uint32_t *label, size_t *n)
     if (n) *n = c;
     return SB_OK;
 }
+// (the flood over the pieces is a device kernel: the stand-in refuses, the mirror then runs its host flood)
+int sb_uncut_face_groups(const sb_uncut *, const uint32_t *, size_t, const uint32_t *, size_t, uint32_t *, uint32_t *, size_t *)
+{
+    return SB_ERR_INVALID;
+}
 int sb_classify(const sb_mesh *t, const double *pts, size_t Q, uint8_t *inside, uint8_t *per_axis)
 {
     if (Q)

@@ -187,3 +187,95 @@ def test_uncut_config_c4_many_fragments(ctx, oracle):
     check_uncut(u, r, a[1], 7)
     u.close(); raw.close()
     x.close(); ma.close(); mb.close()
+
+
+def _host_groups(tris, fences):
+    """Checker for sb_uncut_face_groups: connected components of `tris` (node = row) through opposite half-edges that
+    are not fences (either direction), label = lowest node of the component.  Plain union-find on the host."""
+    n = len(tris)
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    fence = set()
+    for a, b in fences:
+        fence.add((int(a), int(b))); fence.add((int(b), int(a)))
+    owner = {}
+    for t, tri in enumerate(tris):
+        for k in range(3):
+            owner[(int(tri[k]), int(tri[(k + 1) % 3]))] = t
+    for t, tri in enumerate(tris):
+        for k in range(3):
+            a, b = int(tri[k]), int(tri[(k + 1) % 3])
+            if (a, b) in fence:
+                continue
+            o = owner.get((b, a))
+            if o is not None and o != t:
+                ra, rb = find(t), find(o)
+                if ra != rb:
+                    parent[max(ra, rb)] = min(ra, rb)
+    return np.array([find(t) for t in range(n)], np.uint32)
+
+
+@pytest.mark.parametrize("voff,toff", [(0, 0), (1000, 77)])
+def test_face_groups_over_uncut_triangles_and_pieces(ctx, voff, toff):
+    """SURVEY 8f row 3 on the device: a band of faces around the equator of an icosphere plays the cut triangles (their
+    own triangles handed back as `pieces`, as a trivial retriangulation would), two closed vertex rings inside the band
+    are the intersection loops.  The groups must be the connected components the host checker finds: the two caps
+    (uncut components + the band pieces on their side of a ring) and the strip between the rings."""
+    v, t = meshgen.icosphere(4)
+    m = ctx.mesh(v, t)
+    z = v[t].mean(axis=1)[:, 2]
+    cut = (np.abs(z) < 0.25).astype(np.uint8)
+    u = m.uncut(cut, voff, toff)
+    face, tri3 = u.triangles()
+    pieces = (t[cut.astype(bool)] + voff).astype(np.uint32)
+    # fences: the edges of the band faces that cross z = +-0.1 ... need CLOSED curves made of mesh edges: take every edge
+    # whose two adjacent faces lie on different sides of the plane z = c (the boundary of {faces with centroid z > c})
+    def ring(c):
+        side = z > c
+        own = {}
+        for f, tri in enumerate(t):
+            for k in range(3):
+                own[(int(tri[k]), int(tri[(k + 1) % 3]))] = f
+        out = []
+        for (a, b), f in own.items():
+            g = own.get((b, a))
+            if g is not None and side[f] and not side[g]:
+                out.append((a + voff, b + voff))
+        return out
+    fences = np.array(ring(0.1) + ring(-0.1), np.uint32)
+    assert len(fences) > 20
+    lu, lp, n = u.face_groups(pieces, fences)
+    nodes = np.concatenate([tri3, pieces])                      # uncut triangles first, then the pieces
+    ref = _host_groups(nodes, fences)
+    assert np.array_equal(lu, ref[:len(tri3)]) and np.array_equal(lp, ref[len(tri3):])
+    assert n == len(np.unique(ref)) == 3
+    # no fences: everything is one group; no pieces: the uncut components themselves
+    lu1, lp1, n1 = u.face_groups(pieces, np.zeros((0, 2), np.uint32))
+    assert n1 == 1 and np.all(lu1 == 0) and np.all(lp1 == 0)
+    lu2, _, n2 = u.face_groups(np.zeros((0, 3), np.uint32), np.zeros((0, 2), np.uint32))
+    lab, ncomp = u.components()
+    assert n2 == ncomp == 2 and np.array_equal(lu2, lab - toff)
+    u.close(); m.close()
+
+
+def test_face_groups_random_cuts_and_fences(ctx):
+    """Random third of the faces cut (thousands of uncut fragments), random fences on cut-face edges."""
+    rng = np.random.default_rng(3)
+    v, t = meshgen.torus(96, 48)
+    m = ctx.mesh(v, t)
+    cut = (rng.random(len(t)) < 0.33).astype(np.uint8)
+    u = m.uncut(cut, 0, 0)
+    _, tri3 = u.triangles()
+    pieces = t[cut.astype(bool)].astype(np.uint32)
+    pick = pieces[rng.random(len(pieces)) < 0.5]
+    fences = np.concatenate([pick[:, [0, 1]], pick[::3, [1, 2]]]).astype(np.uint32)
+    lu, lp, n = u.face_groups(pieces, fences)
+    ref = _host_groups(np.concatenate([tri3, pieces]), fences)
+    assert np.array_equal(lu, ref[:len(tri3)]) and np.array_equal(lp, ref[len(tri3):])
+    assert n == len(np.unique(ref))
+    u.close(); m.close()
