@@ -141,6 +141,14 @@ int sb_isect_candidates(const sb_isect *isect, uint32_t *ab, uint8_t *code);
 /* Intersecting, non-coplanar pairs (what intersectTwoFaces accepts) and their
  * segments: seg = source xyz, target xyz per hit. */
 int sb_isect_hits(const sb_isect *isect, uint32_t *ab, double *seg);
+/* WHICH EDGE each end point of a hit's segment lies on, carried out of the predicate -- the branch of
+ * CONSTRUCT_INTERSECTION taken (thirdparty/GuigueDevillers03/tri_tri_intersect.c:285-356) names the two edges, the
+ * permutations of :443-471 / :360-385 map them back to the caller's vertex order.  One byte per hit, in the order of
+ * sb_isect_hits: bits 0-1 = edge of the SOURCE point (edge k joins vertices k and (k + 1) mod 3 of its triangle), bit 2 =
+ * the edge belongs to B's triangle (else A's); bits 4-5 / bit 6 the same for the TARGET point; bit 7 is always set.
+ * With it the retriangulation of a cut face attaches polyline ends to the face's boundary without the absolute-epsilon
+ * collinearity test of src/vector2.h:212-215 (src/retriangulator.cpp:97-105). */
+int sb_isect_hit_edges(const sb_isect *isect, uint8_t *tags /* n_hit */);
 /* Per-face "intersected" flags (m_firstIntersectedFaces / m_secondIntersectedFaces,
  * src/solidboolean.cpp:318-319): nT(A) and nT(B) bytes. */
 int sb_isect_face_flags(const sb_isect *isect, uint8_t *flagsA, uint8_t *flagsB);

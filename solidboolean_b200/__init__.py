@@ -91,6 +91,7 @@ ABI = {
     "sb_isect_counts": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "sb_isect_candidates": (C.c_int, [_vp, _vp, _vp]),
     "sb_isect_hits": (C.c_int, [_vp, _vp, _vp]),
+    "sb_isect_hit_edges": (C.c_int, [_vp, _vp]),
     "sb_isect_face_flags": (C.c_int, [_vp, _vp, _vp]),
     "sb_isect_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint), C.POINTER(_vp),
                                        C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
@@ -590,6 +591,14 @@ class Isect:
         finally:
             self.lib.sb_cuts_destroy(h)
         return dict(tri=tri, point_start=ps, points=pts, edge_start=es, edges=edges)
+
+    def hit_edges(self):
+        """sb_isect_hit_edges -> tags [n_hit] uint8: bits 0-1 edge of the source point, bit 2 on B's triangle;
+        bits 4-5 / 6 the same for the target point; bit 7 set."""
+        tags = np.zeros(self.num_hits, np.uint8)
+        if self.num_hits:
+            _check(self.lib.sb_isect_hit_edges(self.h, _ptr(tags)))
+        return tags
 
     def uncut(self, which: int, vertex_offset=0, triangle_offset=0) -> "Uncut":
         """sb_isect_uncut: the faces of mesh `which` the intersection left alone + their half-edge map."""

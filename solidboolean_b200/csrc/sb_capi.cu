@@ -172,6 +172,7 @@ struct sb_isect {
     void *candAlloc[2] = {nullptr, nullptr};
     uint32_t *hitAB = nullptr;
     double2 *hitSeg = nullptr;
+    uint8_t *hitTag = nullptr;     // nHit: which edges the segment end points lie on (sb_tritri.cuh tt_segment_tag)
     uint8_t *flagsA = nullptr, *flagsB = nullptr;
     unsigned long long paths[5] = {0, 0, 0, 0, 0}; // predicate exit histogram
     std::vector<void *> owned; // stream-ordered allocations to release
@@ -1542,14 +1543,16 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
     unsigned long long *hitKeys = nullptr, *hitKeysTmp = nullptr, *keysTmp = nullptr;
     uint32_t *hitSlot = nullptr, *hitSlotTmp = nullptr;
     double2 *hitSegRaw = nullptr;
+    uint8_t *hitTagRaw = nullptr;
     if (nCand) {
+        SB_TRY(alloc_async(c, &hitTagRaw, nCand, &x->owned));
         SB_TRY(alloc_async(c, &hitKeys, nCand, &x->owned));
         SB_TRY(alloc_async(c, &hitSlot, nCand, &x->owned));
         SB_TRY(alloc_async(c, &hitSegRaw, 3 * nCand, &x->owned));
         {
             StageTimer t(c, SB_STAGE_PREDICATE);
             SB_CUDA_X(sbk_predicate(c->stream, A->d, B->d, keys, (uint32_t)nCand, x->bitsB, hitKeys, hitSlot, hitSegRaw,
-                &c->dScalars->hitCount, x->flagsA, x->flagsB, c->dScalars->paths, c->lc));
+                &c->dScalars->hitCount, x->flagsA, x->flagsB, c->dScalars->paths, hitTagRaw, c->lc));
         }
         SB_CUDA_X(cudaMemcpyAsync(c->hScalars, c->dScalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA_X(cudaStreamSynchronize(c->stream));
@@ -1576,8 +1579,9 @@ int sb_intersect_range(const sb_mesh *A, const sb_mesh *B, size_t begin, size_t 
         if (x->nHit) {
             SB_TRY(alloc_async(c, &x->hitAB, 2 * x->nHit, &x->owned));
             SB_TRY(alloc_async(c, &x->hitSeg, 3 * x->nHit, &x->owned));
+            SB_TRY(alloc_async(c, &x->hitTag, x->nHit, &x->owned));
             SB_CUDA_X(sbk_gather_hits(c->stream, sortedHitKeys, sortedSlot, hitSegRaw, (uint32_t)x->nHit, x->bitsB, x->hitAB,
-                x->hitSeg, c->lc));
+                x->hitSeg, hitTagRaw, x->hitTag, c->lc));
         }
     }
 #undef SB_TRY
@@ -1716,6 +1720,21 @@ int sb_isect_hits(const sb_isect *x, uint32_t *ab, double *seg)
         SB_CUDA(cudaMemcpyAsync(ab, x->hitAB, 8 * x->nHit, cudaMemcpyDeviceToHost, c->stream));
     if (seg)
         SB_CUDA(cudaMemcpyAsync(seg, x->hitSeg, 48 * x->nHit, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_isect_hit_edges(const sb_isect *x, uint8_t *tags)
+{
+    if (!x || !tags)
+        return fail(SB_ERR_INVALID, "null argument");
+    sb_context *c = x->ctx;
+    DeviceGuard g(c);
+    if (!x->nHit)
+        return SB_OK;
+    if (!x->hitTag)
+        return fail(SB_ERR_INVALID, "this intersection carries no edge tags");
+    SB_CUDA(cudaMemcpyAsync(tags, x->hitTag, x->nHit, cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
     return SB_OK;
 }

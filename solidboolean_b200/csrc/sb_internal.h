@@ -108,10 +108,11 @@ cudaError_t sbk_broad_phase(cudaStream_t s, const MeshDev &A, const MeshDev &B, 
 // sb_narrow.cu
 cudaError_t sbk_predicate(cudaStream_t s, const MeshDev &A, const MeshDev &B, unsigned long long *keys, uint32_t nPairs,
     unsigned bitsB, unsigned long long *hitKeys, uint32_t *hitSlot, double2 *hitSeg, unsigned int *hitCount,
-    uint8_t *flagsA, uint8_t *flagsB, unsigned long long *pathCounts, LaunchCounter &lc);
+    uint8_t *flagsA, uint8_t *flagsB, unsigned long long *pathCounts, uint8_t *hitTag /* per slot, or null */, LaunchCounter &lc);
 cudaError_t sbk_fp64_peak(cudaStream_t s, int smCount, double *scratch, int iters, bool fma, unsigned long long *flops);
 cudaError_t sbk_gather_hits(cudaStream_t s, const unsigned long long *sortedHitKeys, const uint32_t *sortedSlot,
-    const double2 *hitSeg, uint32_t nHits, unsigned bitsB, uint32_t *outAB, double2 *outSeg, LaunchCounter &lc);
+    const double2 *hitSeg, uint32_t nHits, unsigned bitsB, uint32_t *outAB, double2 *outSeg, const uint8_t *hitTag, uint8_t *outTag,
+    LaunchCounter &lc);
 cudaError_t sbk_decode_candidates(cudaStream_t s, const unsigned long long *keys, uint32_t n, unsigned bitsB,
     uint32_t *outAB, uint8_t *outCode, LaunchCounter &lc);
 cudaError_t sbk_tri_tri_batch(cudaStream_t s, const double *tris18, uint32_t n, int32_t *ret, int32_t *coplanar,

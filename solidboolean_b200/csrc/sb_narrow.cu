@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__re
     const double4 *__restrict__ vtxB, const uint32_t *__restrict__ triB,
     unsigned long long *__restrict__ hitKeys, uint32_t *__restrict__ hitSlot, double2 *__restrict__ hitSeg,
     unsigned int *__restrict__ hitCount, uint8_t *__restrict__ flagsA, uint8_t *__restrict__ flagsB,
-    unsigned long long *__restrict__ pathCounts)
+    unsigned long long *__restrict__ pathCounts, uint8_t *__restrict__ hitTag)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__re
     unsigned long long ab = 0;
     d3 src = {0, 0, 0}, tgt = {0, 0, 0};
     uint32_t a = 0, b = 0;
+    unsigned tag = 0;
     if (i < nPairs) {
         unsigned long long key = keys[i];
         ab = key >> 2;
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__re
         d3 p1 = load_vertex(vtxA, a0), q1 = load_vertex(vtxA, a1), r1 = load_vertex(vtxA, a2);
         d3 p2 = load_vertex(vtxB, b0), q2 = load_vertex(vtxB, b1), r2 = load_vertex(vtxB, b2);
         int coplanar = 0;
-        int ret = tri_tri_intersection(p1, q1, r1, p2, q2, r2, coplanar, src, tgt, path);
+        int ret = tri_tri_intersection(p1, q1, r1, p2, q2, r2, coplanar, src, tgt, path, &tag);
         keys[i] = key | (unsigned long long)((ret ? 1 : 0) | (coplanar ? 2 : 0));
         hit = ret && !coplanar; // intersectTwoFaces, src/solidboolean.cpp:117-121
     }
@@ -62,6 +63,8 @@ __global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__re
         o[0] = make_double2(src.x, src.y);
         o[1] = make_double2(src.z, tgt.x);
         o[2] = make_double2(tgt.y, tgt.z);
+        if (hitTag)
+            hitTag[slot] = (uint8_t)tag; // which edges the end points lie on (sb_tritri.cuh tt_segment_tag)
         flagsA[a] = 1;
         flagsB[b] = 1;
     }
@@ -69,11 +72,13 @@ __global__ void __launch_bounds__(128) predicate_kernel(unsigned long long *__re
 
 __global__ void __launch_bounds__(256) gather_hits_kernel(const unsigned long long *__restrict__ sortedKeys,
     const uint32_t *__restrict__ sortedSlot, const double2 *__restrict__ hitSeg, uint32_t nHits, unsigned bitsB,
-    uint32_t *__restrict__ outAB, double2 *__restrict__ outSeg)
+    uint32_t *__restrict__ outAB, double2 *__restrict__ outSeg, const uint8_t *__restrict__ hitTag, uint8_t *__restrict__ outTag)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nHits)
         return;
+    if (outTag)
+        outTag[i] = hitTag[sortedSlot[i]];
     unsigned long long ab = sortedKeys[i];
     outAB[2 * (size_t)i] = (uint32_t)(ab >> bitsB);
     outAB[2 * (size_t)i + 1] = (uint32_t)(ab & ((1ull << bitsB) - 1));
@@ -120,22 +125,23 @@ __global__ void __launch_bounds__(128) tri_tri_batch_kernel(const double *__rest
 
 cudaError_t sbk_predicate(cudaStream_t s, const MeshDev &A, const MeshDev &B, unsigned long long *keys, uint32_t nPairs,
     unsigned bitsB, unsigned long long *hitKeys, uint32_t *hitSlot, double2 *hitSeg, unsigned int *hitCount,
-    uint8_t *flagsA, uint8_t *flagsB, unsigned long long *pathCounts, LaunchCounter &lc)
+    uint8_t *flagsA, uint8_t *flagsB, unsigned long long *pathCounts, uint8_t *hitTag, LaunchCounter &lc)
 {
     if (nPairs == 0)
         return cudaSuccess;
     predicate_kernel<<<(nPairs + 127) / 128, 128, 0, s>>>(keys, nPairs, bitsB, A.vtx, A.tri, B.vtx, B.tri, hitKeys, hitSlot,
-        hitSeg, hitCount, flagsA, flagsB, pathCounts);
+        hitSeg, hitCount, flagsA, flagsB, pathCounts, hitTag);
     lc.kernels += 1;
     return cudaGetLastError();
 }
 
 cudaError_t sbk_gather_hits(cudaStream_t s, const unsigned long long *sortedHitKeys, const uint32_t *sortedSlot,
-    const double2 *hitSeg, uint32_t nHits, unsigned bitsB, uint32_t *outAB, double2 *outSeg, LaunchCounter &lc)
+    const double2 *hitSeg, uint32_t nHits, unsigned bitsB, uint32_t *outAB, double2 *outSeg, const uint8_t *hitTag, uint8_t *outTag,
+    LaunchCounter &lc)
 {
     if (nHits == 0)
         return cudaSuccess;
-    gather_hits_kernel<<<(nHits + 255) / 256, 256, 0, s>>>(sortedHitKeys, sortedSlot, hitSeg, nHits, bitsB, outAB, outSeg);
+    gather_hits_kernel<<<(nHits + 255) / 256, 256, 0, s>>>(sortedHitKeys, sortedSlot, hitSeg, nHits, bitsB, outAB, outSeg, hitTag, outTag);
     lc.kernels += 1;
     return cudaGetLastError();
 }

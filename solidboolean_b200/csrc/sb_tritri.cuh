@@ -168,8 +168,12 @@ __device__ __forceinline__ d3 edge_plane_point(const d3 &base, const d3 &num, co
 
 // CONSTRUCT_INTERSECTION, tri_tri_intersect.c:285-356.  N1, N2: normals of the
 // caller's UNPERMUTED triangles.
+// `which` (0..3) names the branch taken, i.e. which edges the two end points lie on:
+//   0: source on T1's edge p1-r1, target on T2's edge p2-r2      1: source on T2's p2-q2, target on T2's p2-r2
+//   2: source on T1's p1-r1,      target on T1's p1-q1           3: source on T2's p2-q2, target on T1's p1-q1
+// (carried out of the predicate so that retriangulation need not find the edge again with a tolerance)
 __device__ __forceinline__ int tt_construct(const d3 &p1, const d3 &q1, const d3 &r1,
-    const d3 &p2, const d3 &q2, const d3 &r2, const d3 &N1, const d3 &N2, d3 &source, d3 &target)
+    const d3 &p2, const d3 &q2, const d3 &r2, const d3 &N1, const d3 &N2, d3 &source, d3 &target, int &which)
 {
     d3 v1 = d3sub(q1, p1);
     d3 v2 = d3sub(r2, p1);
@@ -184,10 +188,12 @@ __device__ __forceinline__ int tt_construct(const d3 &p1, const d3 &q1, const d3
             if (d3dot(v, N) > 0.0) {
                 source = edge_plane_point(p1, d3sub(p1, p2), d3sub(p1, r1), N2);
                 target = edge_plane_point(p2, d3sub(p2, p1), d3sub(p2, r2), N1);
+                which = 0;
                 return 1;
             }
             source = edge_plane_point(p2, d3sub(p2, p1), d3sub(p2, q2), N1);
             target = edge_plane_point(p2, d3sub(p2, p1), d3sub(p2, r2), N1);
+            which = 1;
             return 1;
         }
         return 0;
@@ -201,11 +207,35 @@ __device__ __forceinline__ int tt_construct(const d3 &p1, const d3 &q1, const d3
     if (d3dot(v, N) >= 0.0) {
         source = edge_plane_point(p1, d3sub(p1, p2), d3sub(p1, r1), N2);
         target = edge_plane_point(p1, d3sub(p1, p2), d3sub(p1, q1), N2);
+        which = 2;
         return 1;
     }
     source = edge_plane_point(p2, d3sub(p2, p1), d3sub(p2, q2), N1);
     target = edge_plane_point(p1, d3sub(p1, p2), d3sub(p1, q1), N2);
+    which = 3;
     return 1;
+}
+
+// Edge k of a triangle joins its vertices k and (k + 1) mod 3; the edge between vertices i != j:
+__device__ __forceinline__ int tt_edge_of(int i, int j) { return i + j == 1 ? 0 : (i + j == 3 ? 1 : 2); }
+
+// Where the end points of a constructed segment lie, in terms of the caller's UNPERMUTED triangles:
+//   bits 0-1: edge of the source point (0..2), bit 2: on T2 (else T1); bits 4-5 / 6: the same for the target; bit 7: set.
+#define SB_SEG_TAG_VALID 0x80u
+__device__ __forceinline__ unsigned tt_segment_tag(int which, int rot1, bool swap1, int rot2, bool swap2)
+{
+    // the permutations of tri_tri_intersection below, applied to vertex NUMBERS instead of coordinates
+    int i1a = rot1 == 0 ? 0 : (rot1 == 1 ? 2 : 1), i1b = rot1 == 0 ? 1 : (rot1 == 1 ? 0 : 2), i1c = rot1 == 0 ? 2 : (rot1 == 1 ? 1 : 0);
+    if (swap2) {
+        int t = i1b; i1b = i1c; i1c = t;
+    }
+    const int jb = swap1 ? 2 : 1, jc = swap1 ? 1 : 2;
+    const int i2a = rot2 == 0 ? 0 : (rot2 == 1 ? jc : jb), i2b = rot2 == 0 ? jb : (rot2 == 1 ? 0 : jc), i2c = rot2 == 0 ? jc : (rot2 == 1 ? jb : 0);
+    const unsigned e1r = (unsigned)tt_edge_of(i1a, i1c), e1q = (unsigned)tt_edge_of(i1a, i1b);
+    const unsigned e2r = (unsigned)tt_edge_of(i2a, i2c) | 4u, e2q = (unsigned)tt_edge_of(i2a, i2b) | 4u;
+    const unsigned src = (which == 0 || which == 2) ? e1r : e2q;
+    const unsigned tgt = which == 0 ? e2r : (which == 1 ? e2r : e1q);
+    return src | (tgt << 4) | SB_SEG_TAG_VALID;
 }
 
 // Which exit a pair took (flop accounting of SURVEY 8d: 41 / 82 / 139 / 185 flops)
@@ -220,7 +250,7 @@ enum TriTriPath {
 // tri_tri_intersection_test_3d, tri_tri_intersect.c:395-472.
 // coplanar is only ever set to 1; source/target only written with a segment.
 __device__ __forceinline__ int tri_tri_intersection(const d3 &p1, const d3 &q1, const d3 &r1,
-    const d3 &p2, const d3 &q2, const d3 &r2, int &coplanar, d3 &source, d3 &target, int &path)
+    const d3 &p2, const d3 &q2, const d3 &r2, int &coplanar, d3 &source, d3 &target, int &path, unsigned *tag = nullptr)
 {
     // signs of T1's vertices against plane(T2)  (:407-421)
     d3 N2 = d3cross(d3sub(p2, r2), d3sub(q2, r2));
@@ -265,8 +295,11 @@ __device__ __forceinline__ int tri_tri_intersection(const d3 &p1, const d3 &q1, 
     d3 cc2 = sel3(c2.rot, c2v, b2, p2);
     d3 bb1 = c2.swap ? c1v : b1;
     d3 cc1 = c2.swap ? b1 : c1v;
-    int r = tt_construct(a1, bb1, cc1, a2, bb2, cc2, N1, N2, source, target);
+    int which = 0;
+    int r = tt_construct(a1, bb1, cc1, a2, bb2, cc2, N1, N2, source, target, which);
     path = r ? TT_SEGMENT : TT_REJECT_INTERVAL;
+    if (tag)
+        *tag = r ? tt_segment_tag(which, c1.rot, c1.swap, c2.rot, c2.swap) : 0u;
     return r;
 }
 

@@ -23,10 +23,14 @@ ReTriangulator::P2 ReTriangulator::project(const Vector3 &p) const
 }
 
 void ReTriangulator::setEdges(const std::vector<Vector3> &points,
-    const std::unordered_map<size_t, std::unordered_set<size_t>> *neighborMapFrom3)
+    const std::unordered_map<size_t, std::unordered_set<size_t>> *neighborMapFrom3, const std::vector<int> *pointEdges)
 {
     for (const Vector3 &p : points)
         m_points.push_back(project(p));
+    m_pointEdge.assign(m_points.size(), -1);
+    if (pointEdges)
+        for (size_t i = 0; i < pointEdges->size() && 3 + i < m_points.size(); ++i)
+            m_pointEdge[3 + i] = (*pointEdges)[i];
     m_adjacency.assign(m_points.size(), std::vector<size_t>());
     if (neighborMapFrom3)
         for (const auto &it : *neighborMapFrom3) {
@@ -114,6 +118,17 @@ bool ReTriangulator::splitBoundaryRing()
         int bestEdge = -1;
         double bestD = 0.0, bestT = 0.0;
         const P2 &p = m_points[point];
+        const int known = point < m_pointEdge.size() ? m_pointEdge[point] : -1;
+        if (known >= 0 && known < 3) {
+            // the predicate constructed this point ON edge `known` (base - alpha * edge vector): no tolerance involved
+            const P2 &a = m_points[known], &b = m_points[(known + 1) % 3];
+            double ex = b[0] - a[0], ey = b[1] - a[1], len2 = ex * ex + ey * ey;
+            if (len2 > 0.0) {
+                double t = ((p[0] - a[0]) * ex + (p[1] - a[1]) * ey) / len2;
+                onEdge[known].push_back(RingEntry{point, polyline, front, std::min(1.0, std::max(0.0, t))});
+                return true;
+            }
+        }
         for (int i = 0; i < 3; ++i) {
             const P2 &a = m_points[i], &b = m_points[(i + 1) % 3];
             double ex = b[0] - a[0], ey = b[1] - a[1], len2 = ex * ex + ey * ey;

@@ -18,8 +18,11 @@ class ReTriangulator
 {
 public:
     ReTriangulator(const std::vector<Vector3> &trianglePoints, const Vector3 &normal);
+    // pointEdges (optional, one per point): the edge of THIS triangle the point lies on (0..2: edge k joins corners k and
+    // k + 1), as the predicate reported it (sb_isect_hit_edges), or -1 = not on the boundary / unknown.  A polyline end with
+    // a known edge is attached to it directly; the others fall back to the geometric test.
     void setEdges(const std::vector<Vector3> &points,
-        const std::unordered_map<size_t, std::unordered_set<size_t>> *neighborMapFrom3);
+        const std::unordered_map<size_t, std::unordered_set<size_t>> *neighborMapFrom3, const std::vector<int> *pointEdges = nullptr);
     bool reTriangulate();
     const std::vector<std::vector<size_t>> &polygons() const { return m_polygons; }
     const std::vector<std::vector<size_t>> &triangles() const { return m_triangles; }
@@ -37,6 +40,7 @@ private:
     Vector3 m_origin, m_axisU, m_axisV;
     std::vector<P2> m_points;
     std::vector<std::vector<size_t>> m_adjacency; // per point, sorted neighbours
+    std::vector<int> m_pointEdge;                 // per point (corners included: -1), see setEdges
     std::vector<std::vector<size_t>> m_polylines; // open chains, endpoints on the boundary
     std::vector<std::vector<size_t>> m_loops;     // closed chains
     std::vector<std::vector<size_t>> m_polygons;  // boundary ring split by the polylines

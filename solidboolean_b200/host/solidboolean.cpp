@@ -1,4 +1,5 @@
 #include "solidboolean.h"
+#include "positionkey.h"
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -139,7 +140,7 @@ bool SolidBoolean::retriangulateCutTriangles(const std::map<size_t, CutTriangle>
     for (const auto &it : cuts) {
         const auto &t = triangles[it.first];
         ReTriangulator splitter({vertices[t[0]], vertices[t[1]], vertices[t[2]]}, normals[it.first]);
-        splitter.setEdges(it.second.points, &it.second.neighbors);
+        splitter.setEdges(it.second.points, &it.second.neighbors, it.second.pointEdges.empty() ? nullptr : &it.second.pointEdges);
         if (!splitter.reTriangulate()) {
             std::cout << "Retriangle failed" << std::endl;
             return false;
@@ -433,6 +434,27 @@ bool SolidBoolean::combine()
         std::cout << "combine failed: " << sb_last_error() << std::endl;
         return false;
     }
+    // which edge every segment end point lies on, straight from the predicate; per cut triangle and welded
+    // position: edge 0..2 of THAT triangle, or interior.  (A stand-in ABI without tags leaves the map empty: geometric attach.)
+    std::vector<uint8_t> hitTags(hitCount);
+    std::map<std::pair<size_t, PositionKey>, int> edgeOfPoint[2];
+    if (hitCount && sb_isect_hit_edges(isect, hitTags.data()) == SB_OK) {
+        for (size_t h = 0; h < hitCount; ++h)
+            for (int end = 0; end < 2; ++end) {
+                const unsigned t = hitTags[h] >> (4 * end);
+                const int edge = (int)(t & 3u), onSecond = (int)((t >> 2) & 1u);
+                const PositionKey key(m_hitSegments[6 * h + 3 * end], m_hitSegments[6 * h + 3 * end + 1], m_hitSegments[6 * h + 3 * end + 2]);
+                for (int which = 0; which < 2; ++which) {
+                    auto slot = std::make_pair((size_t)m_hitPairs[2 * h + which], key);
+                    const int mine = onSecond == which ? edge : -1;
+                    auto it = edgeOfPoint[which].find(slot);
+                    if (it == edgeOfPoint[which].end())
+                        edgeOfPoint[which].insert({slot, mine});
+                    else if (it->second < 0)
+                        it->second = mine; // a welded twin that does lie on the boundary decides
+                }
+            }
+    }
     // ---- GPU: the per-triangle contexts the reference builds in the body of its pair loop
     // (src/solidboolean.cpp:296-339): welded points in first-seen order + the relations between them
     std::map<size_t, CutTriangle> firstCuts, secondCuts; // ordered: deterministic output
@@ -458,8 +480,13 @@ bool SolidBoolean::combine()
         auto &cuts = which == 0 ? firstCuts : secondCuts;
         for (size_t c = 0; c < contextCount; ++c) {
             CutTriangle &cut = cuts[triangle[c]];
-            for (size_t p = pointStart[c]; p < pointStart[c + 1]; ++p)
+            for (size_t p = pointStart[c]; p < pointStart[c + 1]; ++p) {
                 cut.points.push_back(Vector3(points[3 * p], points[3 * p + 1], points[3 * p + 2]));
+                if (!edgeOfPoint[which].empty()) {
+                    auto it = edgeOfPoint[which].find(std::make_pair((size_t)triangle[c], PositionKey(points[3 * p], points[3 * p + 1], points[3 * p + 2])));
+                    cut.pointEdges.push_back(it == edgeOfPoint[which].end() ? -1 : it->second);
+                }
+            }
             for (size_t r = relationStart[c]; r < relationStart[c + 1]; ++r) {
                 cut.neighbors[relations[2 * r]].insert(relations[2 * r + 1]);
                 cut.neighbors[relations[2 * r + 1]].insert(relations[2 * r]);

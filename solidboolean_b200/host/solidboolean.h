@@ -50,6 +50,7 @@ private:
     // them (sb_isect_contexts = the reference's IntersectedContext, src/solidboolean.cpp:296-339)
     struct CutTriangle {
         std::vector<Vector3> points;
+        std::vector<int> pointEdges; // per point: edge of this triangle it lies on (sb_isect_hit_edges), -1 = interior / unknown
         std::unordered_map<size_t, std::unordered_set<size_t>> neighbors; // indices are 3 + local point
     };
     // half-edge (from << 32 | to) -> triangle.  The uncut triangles' entries arrive from the GPU

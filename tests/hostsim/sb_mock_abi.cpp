@@ -207,6 +207,8 @@ int sb_uncut_components(const sb_uncut *u, uint32_t *label, size_t *n)
     if (n) *n = c;
     return SB_OK;
 }
+// (no edge tags from the oracle: the mirror then attaches polyline ends geometrically)
+int sb_isect_hit_edges(const sb_isect *, uint8_t *) { return SB_ERR_INVALID; }
 // (the flood over the pieces is a device kernel: the stand-in refuses, the mirror then runs its host flood)
 int sb_uncut_face_groups(const sb_uncut *, const uint32_t *, size_t, const uint32_t *, size_t, uint32_t *, uint32_t *, size_t *)
 {

@@ -723,3 +723,55 @@ def test_vertex_indices_far_apart_use_the_index_fallback(ctx, oracle):
     ab, _ = x.candidates()
     assert np.array_equal(ab, oracle.candidate_pairs(q, tgt))
     x.close(); mt.close(); mq.close()
+
+
+def _check_hit_edges(a, b, hab, seg, tags):
+    """Every tagged end point lies on the edge the tag names (distance to the edge's segment below 1e-9 of the
+    triangle's size): independent, geometric check of sb_isect_hit_edges."""
+    assert len(tags) == len(hab) and np.all(tags & 0x80)
+    va, ta = a
+    vb, tb = b
+    for shift, pts in ((0, seg[:, 0:3]), (4, seg[:, 3:6])):
+        edge = (tags >> shift) & 3
+        on_b = ((tags >> (shift + 2)) & 1).astype(bool)
+        assert np.all(edge < 3)
+        tri = np.where(on_b[:, None], tb[hab[:, 1]], ta[hab[:, 0]])          # vertex ids of the owning triangle
+        verts = np.where(on_b[:, None, None], vb[tb[hab[:, 1]]], va[ta[hab[:, 0]]])
+        i0 = edge
+        i1 = (edge + 1) % 3
+        p0 = verts[np.arange(len(tags)), i0]
+        p1 = verts[np.arange(len(tags)), i1]
+        d = p1 - p0
+        t = np.einsum("ij,ij->i", pts - p0, d) / np.maximum(np.einsum("ij,ij->i", d, d), 1e-300)
+        tc = np.clip(t, 0.0, 1.0)
+        dist = np.linalg.norm(pts - (p0 + tc[:, None] * d), axis=1)
+        size = np.linalg.norm(verts.max(axis=1) - verts.min(axis=1), axis=1)
+        assert np.all(dist <= 1e-9 * size), (float((dist / size).max()), int(np.argmax(dist / size)))
+        assert tri.shape[1] == 3
+
+
+def test_hit_edge_tags_name_the_edges_the_end_points_lie_on(ctx):
+    """the edge ids carried out of the predicate, on inputs that exercise every permutation:
+    two soups of random triangles (thousands of hits in general position), C2's curve, a mesh pair with shared planes."""
+    rng = np.random.default_rng(21)
+
+    def soup(n, scale):
+        c = rng.uniform(-1, 1, (n, 1, 3))
+        v = (c + rng.normal(0, scale, (n, 3, 3))).reshape(-1, 3)
+        return np.ascontiguousarray(v), np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    cases = [(soup(3000, 0.15), soup(3000, 0.15)), meshgen.config_c2(),
+             (meshgen.icosphere(3), meshgen.torus(48, 24, center=(0.013, 0.007, 0.011)))]
+    seen = set()
+    for a, b in cases:
+        ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+        x = ma.intersect(mb)
+        hab, seg = x.hits()
+        tags = x.hit_edges()
+        assert len(hab) > 100
+        _check_hit_edges(a, b, hab.astype(np.int64), seg, tags)
+        seen |= set(int(t) & 0x77 for t in tags)
+        x.close(); ma.close(); mb.close()
+    # all four branches of CONSTRUCT_INTERSECTION occur: (T1,T2), (T2,T2), (T1,T1), (T2,T1) as (source, target) owners
+    owners = set(((t >> 2) & 1, (t >> 6) & 1) for t in seen)
+    assert owners == {(0, 1), (1, 1), (0, 0), (1, 0)}
+    assert len(seen) >= 20                                                   # and most (edge, edge) combinations
