@@ -9,6 +9,47 @@
 #define SB_DBL_EPSILON 2.2204460492503131e-16
 #define SB_DBL_MAX 1.7976931348623157e+308
 
+// n / d, correctly rounded (= __ddiv_rn, bit for bit), for the quotient the classifier forms once per candidate: the ray
+// parameter s = n / d of Vector3::intersectSegmentAndPlane (src/vector3.h:264-280), whose denominator is ~1e308 (the test
+// axis is DBL_MAX long) and whose result is therefore SUBNORMAL.  The library division leaves its fast path for such operands
+// (~100 instructions where the fast path has ~25).  Here: the denominator is scaled by 2^-600 (exact), the quotient q formed
+// in the normal range (fast path, correctly rounded), and scaled back by one multiplication, which rounds a second time when
+// the result is subnormal.  The two roundings differ from one only if q landed exactly on a midpoint of the subnormal grid
+// without the true quotient being there: detected exactly (q - back == half a grid step), decided by the sign of the exact
+// residual n - q d' (one FMA).  Everything else falls through to __ddiv_rn.  Checked against the host's division on 1.6e8
+// operand pairs incl. 6e7 constructed ties (the harness is described in DESIGN section 4) and by every parity test.
+#ifndef SB_RAY_DIV_FAST
+#define SB_RAY_DIV_FAST 1
+#endif
+__device__ __forceinline__ double xdiv_huge_den(double n, double d)
+{
+#if SB_RAY_DIV_FAST && !defined(SB_HOST_SIM)
+    const int en = (__double2hiint(n) >> 20) & 0x7ff, ed = (__double2hiint(d) >> 20) & 0x7ff;
+    if (ed >= 1023 + 1000 && ed < 0x7ff && en >= 1023 - 200 && en <= 1023 + 200) {
+        const double dS = __dmul_rn(d, 0x1p-600); // exact
+        const double q = __ddiv_rn(n, dS);        // normal range
+        if (fabs(q) >= 0x1p-470) {
+            double s = __dmul_rn(q, 0x1p-600);
+            if (fabs(s) < 0x1p-1022) {
+                const double back = __dmul_rn(s, 0x1p600); // exact
+                const double diff = __dsub_rn(q, back);    // exact
+                if (fabs(diff) == 0x1p-475) {              // q on a midpoint of the subnormal grid (step 2^-1074 -> 2^-474 here)
+                    const double r = __fma_rn(-q, dS, n);  // sign of n - q d': on which side of q the true quotient lies
+                    if (r != 0.0) {
+                        const bool above = (r > 0.0) == (dS > 0.0);
+                        const double other = __dadd_rn(back, __dmul_rn(2.0, diff));
+                        const double lo = back < other ? back : other, hi = back < other ? other : back;
+                        s = __dmul_rn(above ? hi : lo, 0x1p-600);
+                    }
+                }
+            }
+            return s;
+        }
+    }
+#endif
+    return xdiv(n, d);
+}
+
 // Vector3::normal; the zero vector when |cross| <= DBL_EPSILON (Double::isZero).
 __device__ __forceinline__ d3 tri_normal(const d3 &a, const d3 &b, const d3 &c)
 {
@@ -42,7 +83,7 @@ __device__ __forceinline__ bool ray_tri_hit(const d3 &p, const d3 &end,
     double n = d3dot(neg, w);
     if (fabs(d) <= SB_DBL_EPSILON)
         return false;
-    double s = xdiv(n, d);
+    double s = xdiv_huge_den(n, d);
     // s < 0 || s > 1 || isnan(s) || isinf(s)  (src/vector3.h:274)
     if (!(s >= 0.0 && s <= 1.0))
         return false;
@@ -73,7 +114,7 @@ __device__ __forceinline__ bool ray_tri_hit_filtered(const d3 &p, const d3 &end,
     double n = d3dot(neg, w);
     if (fabs(d) <= SB_DBL_EPSILON)
         return false;
-    double s = xdiv(n, d);
+    double s = xdiv_huge_den(n, d);
     if (!(s >= 0.0 && s <= 1.0))
         return false;
     hit = {xadd(p.x, xmul(s, u.x)), xadd(p.y, xmul(s, u.y)), xadd(p.z, xmul(s, u.z))};
