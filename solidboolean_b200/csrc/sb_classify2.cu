@@ -38,6 +38,9 @@ namespace {
 #ifndef SB_CLS2_MINB
 #define SB_CLS2_MINB 6
 #endif
+#ifndef SB_CLS2_OPEN
+#define SB_CLS2_OPEN 1         // evaluation steps may end inside a ray (32 of 32 lanes instead of 27)
+#endif
 #ifndef SB_CLS2_FULLCHUNKS
 #define SB_CLS2_FULLCHUNKS 1   // evaluation steps wait for 32 entries (except in a round's last window)
 #endif
@@ -224,6 +227,90 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
                 carry = pos - S;
                 break;
             }
+#if SB_CLS2_OPEN
+            // A step takes the next 32 entries whatever rays they belong to.  The ray of its last lanes may go on behind the
+            // step (in the pool, or -- `cont` -- in the next window): such an OPEN ray has no vote yet, its distinct keys are
+            // collected in W.list (longRay / longCount) and the step that holds its last entries adds its own to them.  An open
+            // ray that turns out to have no further entries is closed by the next step (or at the end of the round).
+            const uint32_t e = S + lane;
+            const uint32_t avail = min(32u, pos - S);
+            const bool have = (uint32_t)lane < avail;
+            const uint32_t o = have ? (uint32_t)W.owner[e] : 0x100u;
+            const uint32_t onext = S + 32 < pos ? (uint32_t)W.owner[S + 32] : (avail == 32u ? cont : 0xffu);
+            const uint32_t rid = have ? o : 0x200u + lane;
+            const uint32_t ridPrev = __shfl_up_sync(SB_FULL, rid, 1);
+            const uint32_t heads = __ballot_sync(SB_FULL, have && (lane == 0 || rid != ridPrev));
+            const uint32_t openMask = __ballot_sync(SB_FULL, have && o == onext); // a suffix of the step (or nothing)
+            const uint32_t rid0 = __shfl_sync(SB_FULL, rid, 0);
+            if (longRay != 0xffu && rid0 != longRay) {
+                if (lane == 0) // the open ray had no further entries: what was collected is its answer
+                    W.vote[longRay] = (uint8_t)(longCount & 1u);
+                longRay = 0xffu;
+            }
+            bool h = false, isCand = false;
+            long long k0 = 0, k1 = 0, k2 = 0;
+            if (have) {
+                const int ow = rid & 31;
+                const d3 pp = {W.px[ow], W.py[ow], W.pz[ow]};
+                h = eval_entry<true>(T, pp, axis0 + (int)(rid >> 5), W.tri[e], k0, k1, k2, isCand);
+                if (h) {
+                    W.key[lane][0] = k0;
+                    W.key[lane][1] = k1;
+                    W.key[lane][2] = k2;
+                }
+            }
+            __syncwarp();
+            const uint32_t hm = __ballot_sync(SB_FULL, h);
+            // std::set<PositionKey>: a hit whose key equals that of an earlier hit of the ray does not count
+            const int segStart = 31 - __clz(heads & lelane);
+            uint32_t prior = h ? (hm & ltmask & ~((1u << segStart) - 1u)) : 0u;
+            while (prior) {
+                const int qq = __ffs(prior) - 1;
+                prior &= prior - 1;
+                if (W.key[qq][0] == k0 && W.key[qq][1] == k1 && W.key[qq][2] == k2) {
+                    h = false;
+                    break;
+                }
+            }
+            if (h && rid == longRay) // ... nor does one that equals a key of the ray's earlier steps
+                for (uint32_t t = 0; t < min(longCount, (uint32_t)KL); ++t)
+                    if (W.list[t][0] == k0 && W.list[t][1] == k1 && W.list[t][2] == k2) {
+                        h = false;
+                        break;
+                    }
+            const uint32_t dm = __ballot_sync(SB_FULL, h), cm = __ballot_sync(SB_FULL, isCand);
+            // closed segments: the vote of their ray
+            if (have && ((heads >> lane) & 1u) && !((openMask >> lane) & 1u)) {
+                const uint32_t after = heads & ~lelane;
+                const uint32_t segEnd = after ? (uint32_t)__ffs(after) - 1u : avail;
+                const uint32_t segMask = (segEnd >= 32 ? 0xffffffffu : (1u << segEnd) - 1u) & ~ltmask;
+                const uint32_t before = rid == longRay ? longCount : 0u;
+                // parity of the distinct crossings | exact candidates of this step (<= 32) << 1
+                W.vote[rid] = (uint8_t)(((__popc(dm & segMask) + before) & 1) | (__popc(cm & segMask) << 1));
+            }
+            if (!(openMask & 1u) && rid0 == longRay)
+                longRay = 0xffu; // its last entries were the first segment of this step
+            if (openMask) {
+                if (longRay != onext) { // a ray opens here
+                    longRay = onext;
+                    longCount = 0;
+                }
+                const uint32_t mine = dm & openMask;
+                const uint32_t at = longCount + __popc(mine & ltmask);
+                if (h && ((openMask >> lane) & 1u) && at < (uint32_t)KL) {
+                    W.list[at][0] = k0;
+                    W.list[at][1] = k1;
+                    W.list[at][2] = k2;
+                }
+                longCount += __popc(mine);
+                if (longCount > (uint32_t)KL) // more distinct crossings than the list holds: the general kernel takes the point
+                    legacy |= 1u << (longRay & 31u);
+                if ((uint32_t)lane == (longRay & 31u))
+                    exact += __popc(cm & openMask);
+            }
+            __syncwarp();
+            S += avail;
+#else
             const uint32_t e = S + lane;
             const bool inPool = e < pos;
             const uint32_t o = inPool ? (uint32_t)W.owner[e] : 0x100u;
@@ -308,6 +395,7 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
             }
             __syncwarp();
             S += cnt;
+#endif
         }
         if (carry) { // at most 32 entries (cnt == 0 of a chunk that reaches the end of the pool)
             const bool mv = (uint32_t)lane < carry;
@@ -321,6 +409,10 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
         }
         __syncwarp();
     }
+#if SB_CLS2_OPEN
+    if (longRay != 0xffu && lane == 0) // still open at the end of the round: no further entries came
+        W.vote[longRay] = (uint8_t)(longCount & 1u);
+#endif
     __syncwarp();
     const uint32_t v0 = W.vote[lane], v1 = W.vote[32 + lane];
     exact += (v0 >> 1) + (v1 >> 1); // of this lane's own rays: dropped again if the point goes to the general kernel
