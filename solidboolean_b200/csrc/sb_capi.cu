@@ -79,6 +79,7 @@ struct sb_context {
     LaunchCounter lc;
     // stage timing
     bool timing = false;
+    bool earlyLeaf = false;
     struct Span {
         int stage;
         cudaEvent_t a, b;
@@ -545,6 +546,8 @@ int sb_context_create(int device, sb_context **out)
         c->sortBeginBit = std::max(0, std::min(atoi(e), 24));
     if (const char *e = getenv("SB_GRAPHS"))
         c->useGraphs = atoi(e) != 0;
+    if (const char *e = getenv("SB_EARLY_LEAF")) // dev: a mesh's face queries may start once its sorted centroids exist
+        c->earlyLeaf = atoi(e) != 0;
     if (const char *e = getenv("SB_GRID3_EAGER_BELOW"))
         c->grid3EagerBelow = (size_t)std::max(0ll, atoll(e));
     if (const char *e = getenv("SB_CLASSIFY_POOL_LIMIT"))
@@ -1093,6 +1096,8 @@ int sb_mesh_build(sb_mesh *m)
         {
             StageTimer t(c, SB_STAGE_BUILD, st);
             SB_CUDA(cudaGraphLaunch(m->buildGraph, st));
+            if (c->earlyLeaf)
+                SB_CUDA(cudaEventRecord(m->leafReady, st));
             SB_CUDA(cudaGraphLaunch(m->gridGraph, st));
         }
         if (m->geomChanged) { // new geometry in a list sized for the old one: counts to the host, checked at first use
@@ -1107,7 +1112,8 @@ int sb_mesh_build(sb_mesh *m)
         // start as soon as the sorted centroids exist (between the two graphs) was measured
         // slower -- the two long classification launches then no longer run side by side and
         // the later one ends with its tail alone (1.32 -> 1.37 ms/step at 1M+1M).
-        SB_CUDA(cudaEventRecord(m->leafReady, st));
+        if (!c->earlyLeaf)
+            SB_CUDA(cudaEventRecord(m->leafReady, st));
         c->lc.kernels += m->graphKernels;
         m->treeBuilt = m->treeWanted;
         SB_CUDA(cudaEventRecord(m->ready, st));
