@@ -10,6 +10,6 @@ timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pyte
 timeout 1500 compute-sanitizer --tool racecheck python -m pytest $W -m "gpu and not slow" -q -x -k "fixtures or edge or fragments" > gpurun_out/sanitizer_racecheck.log 2>&1; tail -3 gpurun_out/sanitizer_racecheck.log
 python scripts/racecheck_allow.py gpurun_out/sanitizer_racecheck.log; echo "racecheck (widened rows) allow-list rc=$?"
 timeout 1500 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_batch.py tests/test_gpu_shard.py -m "gpu and not slow" -q -x \
-    -k "bundled or small_and_ragged or cell_borders or ragged_jobs or degenerate" > gpurun_out/sanitizer_racecheck2.log 2>&1; tail -3 gpurun_out/sanitizer_racecheck2.log
+    -k "bundled or small_and_ragged or cell_borders or ragged_jobs or degenerate or many_layers" > gpurun_out/sanitizer_racecheck2.log 2>&1; tail -3 gpurun_out/sanitizer_racecheck2.log
 python scripts/racecheck_allow.py gpurun_out/sanitizer_racecheck2.log; echo "racecheck (round 2 kernels) allow-list rc=$?"
 timeout 900 compute-sanitizer --tool initcheck --error-exitcode 9 python -m pytest $W -m "gpu and not slow" -q -x -k "fixtures" > gpurun_out/sanitizer_initcheck.log 2>&1; echo "initcheck rc=$?"; tail -4 gpurun_out/sanitizer_initcheck.log

@@ -9,7 +9,7 @@ txt = open(sys.argv[1], errors="replace").read()
 reports = re.findall(r"(?:Error|Warning): Race reported.*?(?=\n=========\s*\n|\Z)", txt, flags=re.S)
 by = collections.Counter(); bad = collections.Counter()
 for b in reports:
-    names = sorted(set(re.findall(r"access at (?:<unnamed>::)?([A-Za-z_0-9:]+)[(<+]", b)))
+    names = sorted(set(re.findall(r"access at (?:[a-z ]+ )?(?:<unnamed>::)?([A-Za-z_0-9]+)[(<+]", b)))
     key = " / ".join(names) or "?"
     by[key] += 1
     if not names or not all(any(a in n for a in ALLOW) for n in names):

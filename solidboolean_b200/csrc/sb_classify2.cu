@@ -291,6 +291,7 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
             if (!(openMask & 1u) && rid0 == longRay)
                 longRay = 0xffu; // its last entries were the first segment of this step
             if (openMask) {
+                __syncwarp(); // (the list of a ray closed in this step was read above; a ray opening here writes it from slot 0)
                 if (longRay != onext) { // a ray opens here
                     longRay = onext;
                     longCount = 0;
