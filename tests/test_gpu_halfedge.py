@@ -279,3 +279,25 @@ def test_face_groups_random_cuts_and_fences(ctx):
     assert np.array_equal(lu, ref[:len(tri3)]) and np.array_equal(lp, ref[len(tri3):])
     assert n == len(np.unique(ref))
     u.close(); m.close()
+
+
+def test_face_groups_and_hit_edges_reject_bad_arguments(ctx):
+    import ctypes as C
+    lib = sb.load_library()
+    v, t = meshgen.icosphere(2)
+    m = ctx.mesh(v, t)
+    u = m.uncut(None, 0, 0)
+    n = C.c_size_t(0)
+    lu = np.zeros(u.num_triangles, np.uint32)
+    # pieces announced but no array / no output array
+    assert lib.sb_uncut_face_groups(u.h, None, 4, None, 0, lu.ctypes.data_as(C.c_void_p), None, C.byref(n)) == 1
+    pc = np.zeros((2, 3), np.uint32)
+    assert lib.sb_uncut_face_groups(u.h, pc.ctypes.data_as(C.c_void_p), 2, None, 0, lu.ctypes.data_as(C.c_void_p), None, C.byref(n)) == 1
+    assert lib.sb_uncut_face_groups(None, None, 0, None, 0, None, None, C.byref(n)) == 1
+    assert lib.sb_uncut_face_groups(u.h, None, 0, None, 3, lu.ctypes.data_as(C.c_void_p), None, C.byref(n)) == 1   # fences without an array
+    assert lib.sb_isect_hit_edges(None, None) == 1
+    # degenerate but valid: pieces that touch nothing are groups of their own
+    far = np.array([[10_000, 10_001, 10_002]], np.uint32)
+    lu2, lp2, n2 = u.face_groups(far, np.zeros((0, 2), np.uint32))
+    assert n2 == 2 and lp2[0] == u.num_triangles and np.all(lu2 == 0)
+    u.close(); m.close()
