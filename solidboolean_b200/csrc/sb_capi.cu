@@ -80,6 +80,14 @@ struct sb_context {
     // stage timing
     bool timing = false;
     bool earlyLeaf = false;
+    // Destroyed plain meshes are PARKED (device arena, streams, events, captured rebuild graphs and all) and handed out again
+    // by the next sb_mesh_upload of the same counts -- a caller that makes a new SolidMesh per operation then pays what
+    // sb_mesh_update pays: the copies and a full rebuild, no allocation, no stream creation, no first-build round trip (the
+    // reference lists keep their size and are verified against the new geometry, see sb_mesh_update).  At most
+    // SB_MESH_CACHE meshes (default 4, 0 = off) and 4 GiB of device memory are kept; sb_context_destroy releases them.
+    std::vector<sb_mesh *> parked;
+    size_t parkedBytes = 0;
+    int parkMax = 4;
     struct Span {
         int stage;
         cudaEvent_t a, b;
@@ -141,6 +149,7 @@ struct sb_mesh {
     // mesh reads them (mesh_finish) -- new big-list lengths, and a proper first build if the capacity was exceeded
     bool geomChanged = false, verifyPending = false;
     cudaEvent_t verifyEv = nullptr;
+    size_t arenaBytes = 0;           // size of `arena` (accounting of the parked meshes)
     cudaEvent_t leafReady = nullptr; // sorted leaves / boxes / centroids: all a QUERY mesh needs,
                                      // recorded before the grids (and the LBVH) are built
     uint32_t *radixWs = nullptr;     // in the arena
@@ -412,6 +421,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
     size_t oScan = take(4 * sbk_grid_scan_status_words(3u << d.gridCellBits));
     size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32 + 96 * 8);
     // stream-ordered allocation: the pool keeps the block cached between calls
+    m->arenaBytes = off;
     cudaError_t e = cudaMallocAsync(&m->arena, off, ctx->stream);
     if (e != cudaSuccess) {
         delete m;
@@ -546,6 +556,8 @@ int sb_context_create(int device, sb_context **out)
         c->sortBeginBit = std::max(0, std::min(atoi(e), 24));
     if (const char *e = getenv("SB_GRAPHS"))
         c->useGraphs = atoi(e) != 0;
+    if (const char *e = getenv("SB_MESH_CACHE"))
+        c->parkMax = std::max(0, std::min(atoi(e), 64));
     if (const char *e = getenv("SB_EARLY_LEAF")) // dev: a mesh's face queries may start once its sorted centroids exist
         c->earlyLeaf = atoi(e) != 0;
     if (const char *e = getenv("SB_GRID3_EAGER_BELOW"))
@@ -569,11 +581,16 @@ int sb_context_create(int device, sb_context **out)
     return SB_OK;
 }
 
+static void mesh_destroy_now(sb_mesh *m);
+
 void sb_context_destroy(sb_context *c)
 {
     if (!c)
         return;
     DeviceGuard g(c->device); // (not the locking form: the mutex goes away with the context)
+    for (sb_mesh *m : c->parked)
+        mesh_destroy_now(m);
+    c->parked.clear();
     cudaStreamSynchronize(c->stream);
     for (auto &s : c->spans) {
         cudaEventDestroy(s.a);
@@ -715,9 +732,24 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
         return fail(SB_ERR_INVALID, "triangles without vertices");
     DeviceGuard g(ctx);
     sb_mesh *m = nullptr;
-    int r = mesh_alloc(ctx, nV, nT, &m);
-    if (r)
-        return r;
+    for (size_t k = 0; k < ctx->parked.size(); ++k)
+        if (ctx->parked[k]->d.nV == nV && ctx->parked[k]->d.nT == nT) {
+            // a parked mesh of the same counts: new bytes into it, exactly what sb_mesh_update does
+            m = ctx->parked[k];
+            ctx->parked.erase(ctx->parked.begin() + (std::ptrdiff_t)k);
+            ctx->parkedBytes -= m->arenaBytes + m->gridArenaBytes;
+            m->built = false;
+            m->gridPending = false;
+            m->verifyPending = false;
+            m->geomChanged = true;
+            order_after_context(ctx, m);
+            break;
+        }
+    if (!m) {
+        int r = mesh_alloc(ctx, nV, nT, &m);
+        if (r)
+            return r;
+    }
     cudaError_t e = cudaSuccess;
     if (nV)
         e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, m->stream);
@@ -728,7 +760,7 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
     if (e == cudaSuccess)
         e = cudaEventRecord(m->leafReady, m->stream);
     if (e != cudaSuccess) {
-        sb_mesh_destroy(m);
+        mesh_destroy_now(m);
         return fail(SB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
     }
     *out = m;
@@ -1232,11 +1264,8 @@ int sb_mesh_create(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
     return r;
 }
 
-void sb_mesh_destroy(sb_mesh *m)
+static void mesh_destroy_now(sb_mesh *m)
 {
-    if (!m)
-        return;
-    DeviceGuard g(m->ctx);
     if (m->stream) {
         // free in mesh-stream order, after the context stream is done with the buffers
         order_after_context(m->ctx, m);
@@ -1262,6 +1291,22 @@ void sb_mesh_destroy(sb_mesh *m)
     if (m->gridGraph)
         cudaGraphExecDestroy(m->gridGraph);
     delete m;
+}
+
+void sb_mesh_destroy(sb_mesh *m)
+{
+    if (!m)
+        return;
+    sb_context *c = m->ctx;
+    DeviceGuard g(c);
+    const size_t bytes = m->arenaBytes + m->gridArenaBytes;
+    if (m->stream && !m->d.triJob && !m->d.sharedVtx && !m->d.origFace && (int)c->parked.size() < c->parkMax &&
+        c->parkedBytes + bytes <= ((size_t)4 << 30)) {
+        c->parked.push_back(m); // see sb_context::parked
+        c->parkedBytes += bytes;
+        return;
+    }
+    mesh_destroy_now(m);
 }
 
 size_t sb_mesh_num_triangles(const sb_mesh *m) { return m ? m->d.nT : 0; }

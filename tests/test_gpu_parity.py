@@ -775,3 +775,32 @@ def test_hit_edge_tags_name_the_edges_the_end_points_lie_on(ctx):
     owners = set(((t >> 2) & 1, (t >> 6) & 1) for t in seen)
     assert owners == {(0, 1), (1, 1), (0, 0), (1, 0)}
     assert len(seen) >= 20                                                   # and most (edge, edge) combinations
+
+
+def test_parked_mesh_is_revived_with_new_geometry_and_topology(oracle):
+    """sb_mesh_destroy parks plain meshes; sb_mesh_upload of the same counts hands the object out again (arena, streams,
+    captured rebuild, reference-list sizes verified against the new geometry).  A caller that makes new meshes of the same
+    sizes per operation -- different coordinates AND a different triangle order each time -- must get each operation's own
+    result."""
+    c = sb.Context(0)
+    rng = np.random.default_rng(11)
+    a0, b0 = meshgen.icosphere(4), meshgen.torus(64, 32, center=(0.013, 0.007, 0.011))
+    for it in range(4):
+        perm_a, perm_b = rng.permutation(len(a0[1])), rng.permutation(len(b0[1]))
+        rot = np.array([[np.cos(0.3 * it), -np.sin(0.3 * it), 0], [np.sin(0.3 * it), np.cos(0.3 * it), 0], [0, 0, 1.0]])
+        a = (np.ascontiguousarray(a0[0] @ rot.T * (1.0 + 0.1 * it)), np.ascontiguousarray(a0[1][perm_a]))
+        b = (np.ascontiguousarray(b0[0] + 0.02 * it), np.ascontiguousarray(b0[1][perm_b]))
+        ma, mb = c.mesh(*a), c.mesh(*b)
+        x = ma.intersect(mb)
+        ab, _ = x.candidates()
+        ref = oracle.candidate_pairs(a, b)
+        assert np.array_equal(ab, ref)
+        _, _, hit, seg = oracle.predicate_pairs(a, b, ref)
+        hab, hseg = x.hits()
+        assert np.array_equal(hab, ref[hit.astype(bool)]) and hseg.tobytes() == seg[hit.astype(bool)].tobytes()
+        ia, pa = ma.classify_faces_against(mb)
+        oa, opa, _ = oracle.classify(b, oracle.centroids(*a))
+        assert np.array_equal(pa, opa) and np.array_equal(ia, oa)
+        assert np.array_equal(ma.normals(), oracle.normals(*a))
+        x.close(); ma.close(); mb.close()       # parked; the next round's meshes of the same counts revive them
+    c.close()
