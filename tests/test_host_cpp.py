@@ -82,7 +82,8 @@ def run_boolean(lib, a, b):
 
 
 def check_solid(res, meta, a, b, vol_rtol=1e-6):
-    assert res["ok"], res["log"]
+    assert meta.get("combine_ok", True) is True          # the reference's own combine() returned true on this input ...
+    assert res["ok"], res["log"]                         # ... and so does the mirror's
     assert (res["P"], res["H"]) == (meta["P"], meta["H"])
     v = res["vertices"]
     # result vertex array = A's vertices, then B's, then welded new points
