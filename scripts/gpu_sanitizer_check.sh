@@ -7,6 +7,8 @@ W="tests/test_gpu_contexts.py tests/test_gpu_halfedge.py"
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest $W -m "gpu and not slow" -q -x > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_batch.py tests/test_gpu_shard.py tests/test_gpu_comm.py -m "gpu and not slow" -q -x \
     -k "bundled or small_and_ragged or single_triangle or cell_borders or ragged_jobs or degenerate or bad_arguments or update" > gpurun_out/sanitizer_memcheck2.log 2>&1; echo "memcheck (round 2 kernels) rc=$?"; tail -4 gpurun_out/sanitizer_memcheck2.log
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_halfedge.py tests/test_gpu_comm.py tests/test_gpu_parity.py -m "gpu and not slow" -q -x \
+    -k "face_groups or comm_equals or hit_edge or parked or far_apart or bad_arguments" > gpurun_out/sanitizer_memcheck3.log 2>&1; echo "memcheck (flood, comm, edge tags, parked meshes) rc=$?"; tail -4 gpurun_out/sanitizer_memcheck3.log
 timeout 1500 compute-sanitizer --tool racecheck python -m pytest $W -m "gpu and not slow" -q -x -k "fixtures or edge or fragments" > gpurun_out/sanitizer_racecheck.log 2>&1; tail -3 gpurun_out/sanitizer_racecheck.log
 python scripts/racecheck_allow.py gpurun_out/sanitizer_racecheck.log; echo "racecheck (widened rows) allow-list rc=$?"
 timeout 1500 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_batch.py tests/test_gpu_shard.py -m "gpu and not slow" -q -x \
