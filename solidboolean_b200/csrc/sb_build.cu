@@ -14,6 +14,7 @@
 // The reference's top-down mean-split tree (axisalignedboundingboxtree.cpp:27-141)
 // is not reproduced: the candidate-pair set only depends on the leaf boxes.
 #include "sb_internal.h"
+#include <algorithm>
 #include "sb_radix.cuh"
 #include "sb_gridq.cuh"
 
@@ -106,16 +107,30 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 #ifndef SB_TRIPREP_MINB
 #define SB_TRIPREP_MINB 1
 #endif
+#ifndef SB_TRIPREP_HIST
+#define SB_TRIPREP_HIST 1 // the kernel also counts the radix digits of the Morton keys it writes: no separate histogram pass over them
+#endif
+// Grid-stride over the triangles (with SB_TRIPREP_HIST the grid is one resident wave, so that a CTA's digit counts
+// are flushed once for many triangles).
 __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
     uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double4 *__restrict__ nrm4,
     uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
-    unsigned long long *__restrict__ extentSum, const uint16_t *__restrict__ triJob)
+    unsigned long long *__restrict__ extentSum, const uint16_t *__restrict__ triJob,
+    uint32_t *__restrict__ hist /* [passes][256] of the sort to come, or null */, uint32_t *__restrict__ histTicket, int beginBit, int passes)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // this triangle's box extents as 2^-24 fractions of the mesh extent (integers:
+    __shared__ uint32_t s_hist[4 * 256];
+    if (hist) {
+        for (int k = threadIdx.x; k < passes * 256; k += 256)
+            s_hist[k] = 0;
+        __syncthreads();
+    }
+    // the triangles' box extents as 2^-24 fractions of the mesh extent (integers:
     // the sums, and with them the ray-grid resolution, do not depend on atomic order)
-    unsigned int sx = 0, sy = 0, sz = 0;
-    if (i < nT) {
+    unsigned long long sx = 0, sy = 0, sz = 0;
+    const double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
+    const double ex = dkey_inv(bounds[3]) - blx, ey = dkey_inv(bounds[4]) - bly, ez = dkey_inv(bounds[5]) - blz;
+    const double ix = ex > 0 ? 1.0 / ex : 0.0, iy = ey > 0 ? 1.0 / ey : 0.0, iz = ez > 0 ? 1.0 / ez : 0.0;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < nT; i += gridDim.x * 256) {
     uint32_t i0 = tri[3 * (size_t)i], i1 = tri[3 * (size_t)i + 1], i2 = tri[3 * (size_t)i + 2];
     if (i0 >= nV || i1 >= nV || i2 >= nV) { // reported as SB_ERR_INVALID by the host
         *err = 1;
@@ -138,19 +153,20 @@ __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const
     stg256(nrm4 + i, n.x, n.y, n.z,
         __longlong_as_double((long long)pack_tri_idx(i0, i1, i2)));
     // 30-bit Morton key of the box centre inside the mesh box (ordering only)
-    double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
-    double ex = dkey_inv(bounds[3]) - blx, ey = dkey_inv(bounds[4]) - bly, ez = dkey_inv(bounds[5]) - blz;
-    double ix = ex > 0 ? 1.0 / ex : 0.0, iy = ey > 0 ? 1.0 / ey : 0.0, iz = ez > 0 ? 1.0 / ez : 0.0;
     uint32_t qx = quant10(0.5 * (bx.lox + bx.hix), blx, ix);
     uint32_t qy = quant10(0.5 * (bx.loy + bx.hiy), bly, iy);
     uint32_t qz = quant10(0.5 * (bx.loz + bx.hiz), blz, iz);
     const uint32_t morton = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
     // batch mesh: the job leads the key (12 bits), 20 Morton bits follow -- every job is one run of the order
-    mkey[i] = triJob ? ((uint32_t)triJob[i] << 20) | (morton >> 10) : morton;
+    const uint32_t key = triJob ? ((uint32_t)triJob[i] << 20) | (morton >> 10) : morton;
+    mkey[i] = key;
     order[i] = i;
-    sx = (unsigned int)fmin(fmax((bx.hix - bx.lox) * ix * 16777216.0, 0.0), 16777216.0); // NaN -> 0
-    sy = (unsigned int)fmin(fmax((bx.hiy - bx.loy) * iy * 16777216.0, 0.0), 16777216.0);
-    sz = (unsigned int)fmin(fmax((bx.hiz - bx.loz) * iz * 16777216.0, 0.0), 16777216.0);
+    if (hist)
+        for (int p = 0; p < passes; ++p)
+            atomicAdd(&s_hist[p * 256 + ((key >> (beginBit + 8 * p)) & 255u)], 1u);
+    sx += (unsigned int)fmin(fmax((bx.hix - bx.lox) * ix * 16777216.0, 0.0), 16777216.0); // NaN -> 0
+    sy += (unsigned int)fmin(fmax((bx.hiy - bx.loy) * iy * 16777216.0, 0.0), 16777216.0);
+    sz += (unsigned int)fmin(fmax((bx.hiz - bx.loz) * iz * 16777216.0, 0.0), 16777216.0);
     }
     // mean triangle-box extent per axis (sizes the ray grids): CTA reduction, then
     // three atomics per CTA spread over 32 slots (same-address atomics serialise)
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const
         sy += __shfl_xor_sync(SB_FULL, sy, off);
         sz += __shfl_xor_sync(SB_FULL, sz, off);
     }
-    __shared__ unsigned int s_ext[8][3];
+    __shared__ unsigned long long s_ext[8][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_ext[warp][0] = sx;
@@ -174,6 +190,8 @@ __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const
             t += s_ext[w][threadIdx.x];
         atomicAdd(extentSum + 3 * (blockIdx.x & 31) + threadIdx.x, t);
     }
+    if (hist)
+        sbradix::hist_flush_and_scan<8>(s_hist, passes, hist, histTicket);
 }
 
 // ---- K1b --------------------------------------------------------------------
@@ -425,13 +443,24 @@ cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int sm
             return eb;
         lc.kernels -= 1;
     }
-    tri_prepare_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.nrm4, m.mkey, m.order, m.err,
-        m.extentSum, m.triJob);
-    lc.kernels += 2;
     sbradix::Workspace ws;
     ws.mem = radixWs;
+    const int endBit = m.triJob ? 32 : 30;
+    const int passes = sbradix::sort_passes(m.nT, m.sortBeginBit, endBit, 8);
+    const bool fused = SB_TRIPREP_HIST && passes > 0 && passes <= 4;
+    uint32_t blocks = (m.nT + 255) / 256;
+    if (fused) {
+        sbradix::sort_clear(s, ws, m.nT, passes);
+        static int perSm = 0; // one resident wave
+        if (!perSm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, tri_prepare_kernel, 256, 0) != cudaSuccess || perSm < 1))
+            perSm = 2;
+        blocks = std::min<uint32_t>(blocks, (uint32_t)(smCount * perSm));
+    }
+    tri_prepare_kernel<<<blocks, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.nrm4, m.mkey, m.order, m.err,
+        m.extentSum, m.triJob, fused ? sbradix::sort_hist(ws) : nullptr, sbradix::sort_ticket(ws), m.sortBeginBit, passes);
+    lc.kernels += 2;
     uint32_t *sk = nullptr, *sv = nullptr;
-    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, m.triJob ? 32 : 30, ws, smCount, &sk, &sv);
+    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, endBit, ws, smCount, &sk, &sv, fused);
     m.sortedKey = sk;
     m.sortedTri = sv;
     return cudaGetLastError();

@@ -121,6 +121,7 @@ struct sb_context {
     uint32_t *scanScratch = nullptr; // grid-build scan status words
     size_t scanScratchWords = 0;
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
+    int gridSlabBits = 2;            // at most 2^this depth slabs per ray-grid cell (SB_GRID_SLABS = the bits; 0: one list per cell)
     int sortBeginBit = -1;           // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT); -1 = by mesh size
     uint32_t classifyPoolLimit = 0;  // SB_CLASSIFY_POOL_LIMIT: rays with more matches take the general path (tests)
     std::vector<void *> shardPinned;  // pinned read-back blocks of destroyed shards, reused (cudaMallocHost is slow)
@@ -299,21 +300,6 @@ int ensure_radix_ws(sb_context *c, size_t n)
     return SB_OK;
 }
 
-int ensure_scan_scratch(sb_context *c, uint32_t totalCells)
-{
-    size_t words = sbk_grid_scan_status_words(totalCells);
-    if (words <= c->scanScratchWords)
-        return SB_OK;
-    if (c->scanScratch) {
-        SB_CUDA(cudaStreamSynchronize(c->stream));
-        SB_CUDA(cudaFree(c->scanScratch));
-        c->scanScratch = nullptr;
-    }
-    SB_CUDA(cudaMalloc(&c->scanScratch, words * sizeof(uint32_t)));
-    c->scanScratchWords = words;
-    return SB_OK;
-}
-
 int ensure_classify_out(sb_context *c, size_t bytes, uint32_t overflowCap)
 {
     if (bytes > c->classifyOutBytes) {
@@ -418,8 +404,8 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
     }
     size_t oTriJob = take(nJobs ? 2 * nT : 0), oJobStart = take(nJobs ? 8 * (nJobs + 1) : 0);
     size_t oRadix = take(4 * sbk_radix_workspace_words(nT));
-    size_t oScan = take(4 * sbk_grid_scan_status_words(3u << d.gridCellBits));
-    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * ((size_t)(3u << d.gridCellBits) + 2)), oGridBig = take(32 + 96 * 8);
+    size_t oScan = take(4 * sbk_grid_scan_status_words(d.gridCellBits));
+    size_t oGridP = take(sizeof(GridParams)), oGridE = take(4 * (sbk_grid_entry_bound(d.gridCellBits) + 8)), oGridBig = take(32 + 96 * 8);
     // stream-ordered allocation: the pool keeps the block cached between calls
     m->arenaBytes = off;
     cudaError_t e = cudaMallocAsync(&m->arena, off, ctx->stream);
@@ -449,7 +435,7 @@ int mesh_alloc(sb_context *ctx, size_t nV, size_t nT, sb_mesh **out, size_t nJob
     d.root = (int *)(b + oRoot);
     d.err = d.root + 1;
     d.gridParams = (GridParams *)(b + oGridP);
-    d.gridE = (uint32_t *)(b + oGridE);
+    d.gridE = (uint32_t *)(b + oGridE) + 3; // &gridE[1] is 16-byte aligned: the scan and the clear work on E + 1 with 128-bit accesses
     d.gridBigCount = (uint32_t *)(b + oGridBig);
     d.extentSum = (unsigned long long *)(d.gridBigCount + 8);
     if (vertexParent) {
@@ -566,6 +552,8 @@ int sb_context_create(int device, sb_context **out)
         c->classifyPoolLimit = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("SB_CLASSIFY_V2"))
         c->classifyBalanced = atoi(e) != 0;
+    if (const char *e = getenv("SB_GRID_SLABS"))
+        c->gridSlabBits = std::max(0, std::min(atoi(e), 4));
     if (const char *e = getenv("SB_GRID_BETA")) {
         float b = (float)atof(e);
         if (b > 0.01f && b < 100.0f)
@@ -1096,7 +1084,7 @@ int sb_mesh_build(sb_mesh *m)
             int r = capture(&m->buildGraph, [&]() {
                 cudaError_t e = cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st); // (batch: the upload's index check stays)
                 if (e == cudaSuccess) e = sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc);
-                if (e == cudaSuccess) e = sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc);
+                if (e == cudaSuccess) e = sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->gridSlabBits, c->lc);
                 if (e == cudaSuccess) e = sbk_build_leaves(st, m->d, c->lc);
                 return e;
             });
@@ -1156,7 +1144,7 @@ int sb_mesh_build(sb_mesh *m)
         StageTimer t(c, SB_STAGE_BUILD, st);
         SB_CUDA(cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st));
         SB_CUDA(sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc));
-        SB_CUDA(sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->lc));
+        SB_CUDA(sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->gridSlabBits, c->lc));
         SB_CUDA(sbk_build_leaves(st, m->d, c->lc)); // also counts the grid cells
         m->treeBuilt = false;
         // classification queries of this mesh's faces can start here (sorted centroids)

@@ -106,7 +106,6 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
     const RaySetup rs = ray_setup(g, axis, p, job);
     if (!rs.any)
         return make_uint2(0, 0);
-    const uint32_t cbase = g.cellBase[axis], nu = g.nu[axis];
     const uint4 *bigList = T.bigRefs + (size_t)axis * T.bigCap;
     const uint32_t nBig = big_list_length(T, axis);
     const RayQ rqAbs = ray_pack(rs.aU, rs.bU, rs.aV, rs.bV, rs.aA);
@@ -116,8 +115,8 @@ __device__ __noinline__ uint2 big_ray(const GridParams &g, const Target &T, cons
     auto ranges = [&](auto &&visit) {
         for (uint32_t cv = rs.cv0; cv <= rs.cv1; ++cv)
             for (uint32_t cu = rs.cu0; cu <= rs.cu1; ++cu) {
-                const uint32_t cell = cbase + cv * nu + cu;
-                const uint32_t i0 = __ldg(T.E + cell + 1), i1 = __ldg(T.E + cell + 2) & ~1u;
+                uint32_t i0, i1;
+                grid_ray_range(g, T.E, axis, cu, cv, rs.aA, i0, i1);
                 const CellRay cq = ray_in_cell(g, axis, rs, cu, cv);
                 const bool firstU = cu == rs.cu0, firstV = cv == rs.cv0;
                 visit([&](uint32_t i, uint32_t &id) {
@@ -289,9 +288,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
         if (r.any && !legacy0) {
             const CellRay cq = ray_in_cell(g, axis0, r, r.cu0, r.cv0);
             qx0 = cq.x; qy0 = cq.y;
-            const uint32_t cell = g.cellBase[axis0] + r.cv0 * g.nu[axis0] + r.cu0;
-            a0 = __ldg(T.E + cell + 1);
-            b0 = __ldg(T.E + cell + 2) & ~1u; // the next cell's share may begin with an unused slot
+            grid_ray_range(g, T.E, axis0, r.cu0, r.cv0, r.aA, a0, b0);
             const uint32_t nBig = big_list_length(T, axis0);
             if (nBig)
                 n0 = big_count(T.bigRefs + (size_t)axis0 * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA));
@@ -303,9 +300,7 @@ __device__ __forceinline__ uint32_t trace_round(const GridParams &g, const Targe
         if (r.any && !legacy1) {
             const CellRay cq = ray_in_cell(g, axis0 + 1, r, r.cu0, r.cv0);
             qx1 = cq.x; qy1 = cq.y;
-            const uint32_t cell = g.cellBase[axis0 + 1] + r.cv0 * g.nu[axis0 + 1] + r.cu0;
-            a1 = __ldg(T.E + cell + 1);
-            b1 = __ldg(T.E + cell + 2) & ~1u;
+            grid_ray_range(g, T.E, axis0 + 1, r.cu0, r.cv0, r.aA, a1, b1);
             const uint32_t nBig = big_list_length(T, axis0 + 1);
             if (nBig)
                 n1 = big_count(T.bigRefs + (size_t)(axis0 + 1) * T.bigCap, nBig, ray_pack(r.aU, r.bU, r.aV, r.bV, r.aA));

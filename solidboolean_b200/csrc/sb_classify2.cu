@@ -94,9 +94,8 @@ __device__ __forceinline__ bool setup_slot(const GridParams &g, const Target &T,
     if (r.cu0 != r.cu1 || r.cv0 != r.cv1)
         return true;
     const CellRay cq = ray_in_cell(g, AXIS, r, r.cu0, r.cv0);
-    const uint32_t cell = g.cellBase[AXIS] + r.cv0 * g.nu[AXIS] + r.cu0;
-    const uint32_t a = __ldg(T.E + cell + 1);
-    const uint32_t b = __ldg(T.E + cell + 2) & ~1u; // the next cell's share may begin with an unused slot
+    uint32_t a, b; // the sub-lists of the depth slabs the ray can reach (sb_gridq.cuh)
+    grid_ray_range(g, T.E, AXIS, r.cu0, r.cv0, r.aA, a, b);
     rx = cq.x;
     ry = cq.y;
     ra = a;

@@ -19,6 +19,7 @@
 // hit neighbouring cells.
 #include "sb_internal.h"
 #include "sb_gridq.cuh"
+#include <algorithm>
 
 #ifndef SB_FILL_AGG
 #define SB_FILL_AGG 1 // warp-aggregated slot claims in the fill pass (build 0.562 -> 0.544 ms at C3)
@@ -33,8 +34,18 @@ namespace {
 // is a shift of the 15-bit coordinate.  maxBits bounds cells per axis (allocation).
 __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds,
     const unsigned long long *__restrict__ extentSum,
-    uint32_t nT, int maxBits, float beta, int batch, double latPitch, int *err, GridParams *out)
+    uint32_t nT, int maxBits, float beta, int batch, double latPitch, int naxes, int slabBitsMax, int *err, GridParams *out)
 {
+    // launched with one warp: the 32 partial extent sums per axis are read side by side
+    unsigned long long isumAxis[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        unsigned long long v = extentSum[3 * (threadIdx.x & 31) + d];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_xor_sync(SB_FULL, v, off);
+        isumAxis[d] = v;
+    }
     if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
     GridParams g;
@@ -54,9 +65,7 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
         // batch: jobs one lattice step apart must not meet, whatever their place inside [-M, M]
         if (batch && !(4.0 * fmax(fabs(lo), fabs(hi)) <= latPitch))
             atomicOr(err, 2);
-        unsigned long long isum = 0; // fixed point: 2^-24 fractions of the mesh extent
-        for (int k = 0; k < 32; ++k)
-            isum += extentSum[3 * k + d];
+        const unsigned long long isum = isumAxis[d]; // fixed point: 2^-24 fractions of the mesh extent
         double mean = nT ? (double)isum / 16777216.0 * ext / (double)nT : 0.0;
         double cells = (ext > 0.0 && mean > 0.0) ? ext / ((double)beta * mean) : 1.0;
         int b = (int)floor(log2(fmax(cells, 1.0)) + 0.5);
@@ -76,9 +85,21 @@ __global__ void grid_params_kernel(const unsigned long long *__restrict__ bounds
         g.shiftV[a] = SB_Q_BITS - kv;
         g.nu[a] = 1u << ku;
         g.cellBase[a] = base;
-        base += 1u << (ku + kv);
+        // depth slabs (sb_gridq.cuh): about 2 nT / cells of them per cell (a cell holds ~3.6 nT / cells references:
+        // a couple per sub-list; E stays within ~2 nT entries per grid), at most 2^slabBitsMax, and inside the
+        // allocation bound of 2^maxBits entries per grid; never more than the job-local bits of the coordinate
+        int sb = 0;
+        while (sb < slabBitsMax && sb < localBits && ku + kv + sb + 1 <= maxBits && ((size_t)3 << (ku + kv + sb)) <= (size_t)4 * nT)
+            ++sb;
+        g.slabBits[a] = (uint32_t)sb;
+        base += 1u << (ku + kv + sb);
+        base = (base + 15u) & ~15u; // a scan thread's 16 entries never straddle two grids (different slab counts)
+        if (a + 1 == naxes)
+            g.usedCells = base;
     }
     g.totalCells = base;
+    if (naxes >= 3)
+        g.usedCells = base;
     *out = g;
 }
 
@@ -109,8 +130,9 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
             bigRefs[(size_t)a * bigCap + slot] = grid_ref_pack(qlu, qhu, qlv, qhv, qla, qha, q.w);
         return;
     }
-    const uint32_t base = g.cellBase[a], nu = g.nu[a];
-    const int su = g.shiftU[a], sv = g.shiftV[a];
+    const uint32_t nu = g.nu[a];
+    const int su = g.shiftU[a], sv = g.shiftV[a], sb = (int)g.slabBits[a];
+    const uint32_t base = g.cellBase[a] + grid_slab(qha, g, a) + 1; // entry of (cell, slab of the far bound) = base + (cell << sb)
     // the reference of this triangle in cell (cu, cv): its box clipped to the cell, cell-relative
     auto ref_in = [&](uint32_t cu, uint32_t cv) {
         return cell_ref_pack(qlu, qhu, qlv, qhv, qha, cu, cv, su, sv, cu > cu0, cv > cv0, q.w);
@@ -119,7 +141,7 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
         // common case (footprint at most 2 x 2 cells): all atomics are issued before the
         // first dependent store, so their round trips overlap instead of adding up
         const bool du = cu1 != cu0, dv = cv1 != cv0;
-        const uint32_t c00 = base + cv0 * nu + cu0;
+        const uint32_t c00 = cv0 * nu + cu0;
 #if SB_FILL_AGG
         // Morton-neighbouring triangles mostly land in the same cells: one atomic per distinct cell
         // of the warp, the lanes that share it take consecutive slots below the returned end
@@ -128,7 +150,7 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
         const unsigned act = __activemask();
         const uint32_t lane = threadIdx.x & 31, below = lanemask_lt();
         const bool want[4] = {true, du, dv, du && dv};
-        const uint32_t cell[4] = {c00 + 1, c00 + 2, c00 + nu + 1, c00 + nu + 2};
+        const uint32_t cell[4] = {base + (c00 << sb), base + ((c00 + 1) << sb), base + ((c00 + nu) << sb), base + ((c00 + nu + 1) << sb)};
         unsigned peers[4];
         uint32_t end[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -144,10 +166,10 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
             pos[k] = __shfl_sync(act, end[k], __ffs(peers[k]) - 1) - 1u - (uint32_t)__popc(peers[k] & below);
         const uint32_t p00 = pos[0], p10 = pos[1], p01 = pos[2], p11 = pos[3];
 #else
-        uint32_t p00 = atomicSub(&E[c00 + 1], 1u) - 1u, p10 = 0, p01 = 0, p11 = 0;
-        if (du) p10 = atomicSub(&E[c00 + 2], 1u) - 1u;
-        if (dv) p01 = atomicSub(&E[c00 + nu + 1], 1u) - 1u;
-        if (du && dv) p11 = atomicSub(&E[c00 + nu + 2], 1u) - 1u;
+        uint32_t p00 = atomicSub(&E[base + (c00 << sb)], 1u) - 1u, p10 = 0, p01 = 0, p11 = 0;
+        if (du) p10 = atomicSub(&E[base + ((c00 + 1) << sb)], 1u) - 1u;
+        if (dv) p01 = atomicSub(&E[base + ((c00 + nu) << sb)], 1u) - 1u;
+        if (du && dv) p11 = atomicSub(&E[base + ((c00 + nu + 1) << sb)], 1u) - 1u;
 #endif
         if (p00 < refCap) refs[p00] = ref_in(cu0, cv0);
         if (du && p10 < refCap) refs[p10] = ref_in(cu1, cv0);
@@ -157,7 +179,7 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const uint4 *__restrict_
     }
     for (uint32_t cv = cv0; cv <= cv1; ++cv)
         for (uint32_t cu = cu0; cu <= cu1; ++cu) {
-            uint32_t pos = atomicSub(&E[base + cv * nu + cu + 1], 1u) - 1u; // fill each cell back to front
+            uint32_t pos = atomicSub(&E[base + ((cv * nu + cu) << sb)], 1u) - 1u; // fill each sub-list back to front
             if (pos < refCap)
                 refs[pos] = ref_in(cu, cv);
         }
@@ -192,11 +214,42 @@ constexpr int SCAN_ITEMS = SB_SCAN_ITEMS;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_PREFIX = 2ull << 62, SCAN_MASK = (1ull << 62) - 1;
 
+template <int K>
+__device__ __forceinline__ void pad_cells(uint32_t (&v)[SCAN_ITEMS])
+{
+    static_assert(SCAN_ITEMS % K == 0, "whole cells per thread");
+#pragma unroll
+    for (int c = 0; c < SCAN_ITEMS; c += K) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            t += v[c + k];
+        v[c] += t & 1u;
+    }
+}
+
+// zeroes E[0 .. usedCells + 1] (the counts of the grids that are binned, and the closing entry)
+__global__ void __launch_bounds__(256) grid_clear_kernel(uint32_t *__restrict__ E, const GridParams *__restrict__ gp)
+{
+    const uint32_t n4 = (gp->usedCells + 1 + 3) / 4; // uint4 groups from &E[1] (aligned), after E[0]
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        E[0] = 0u;
+    uint4 *p = reinterpret_cast<uint4 *>(E + 1);
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void grid_set_used_kernel(GridParams *gp, int naxes)
+{
+    gp->usedCells = naxes >= 3 ? gp->totalCells : gp->cellBase[naxes];
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *__restrict__ data,
     const GridParams *__restrict__ gp, volatile unsigned long long *status, uint32_t *__restrict__ tileCounter,
     uint32_t *__restrict__ totalOut)
 {
-    const uint32_t n = gp->totalCells + 1; // E[0 .. totalCells]
+    // data = E + 1 (16-byte aligned): data[e] = number of references of entry e; E[0] stays 0
+    const uint32_t n = gp->usedCells;
     if ((unsigned long long)blockIdx.x * SCAN_TILE >= n)
         return; // launched for the allocation bound; only the first ceil(n / TILE) CTAs take a ticket
     __shared__ uint32_t s_tile;
@@ -210,7 +263,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
     const uint32_t base = tile * SCAN_TILE + tid * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t sum = 0;
-    static_assert(SCAN_ITEMS % 4 == 0, "128-bit loads");
+    static_assert(SCAN_ITEMS == 16, "128-bit loads; whole cells per thread (pad_cells, grid bases are multiples of 16)");
     const bool whole = base + SCAN_ITEMS <= n; // (the array is only allocated up to the cell bound + 2)
     if (whole) {
 #pragma unroll
@@ -221,14 +274,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
     } else {
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i)
-            v[i] = base + i < n ? data[base + i] : 0xffffffffu; // (+1 & ~1 -> 0)
+            v[i] = base + i < n ? data[base + i] : 0u;
+    }
+    // Every CELL's share (its 1 << slabBits sub-lists together) is rounded up to an even number of
+    // references: the cell ends (and the 16-byte pairs the classifier loads) stay aligned.  The unused
+    // slot of an odd cell is put in FRONT of its first sub-list, so the sub-lists of a cell stay
+    // contiguous up to the cell's (even) end.  A thread's 16 entries lie inside one grid (grid bases are
+    // multiples of 16) and hold whole cells (1 << slabBits divides 16).
+    {
+        const uint32_t sbits = base >= gp->cellBase[2] ? gp->slabBits[2] : base >= gp->cellBase[1] ? gp->slabBits[1] : gp->slabBits[0];
+        switch (sbits) {
+        case 0: pad_cells<1>(v); break;
+        case 1: pad_cells<2>(v); break;
+        case 2: pad_cells<4>(v); break;
+        case 3: pad_cells<8>(v); break;
+        default: pad_cells<16>(v); break;
+        }
     }
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        // every cell's share is rounded up to an even number of references: the ends (and the
-        // 16-byte pairs the classifier loads) stay aligned; a list with an odd count starts
-        // one slot after its share does
-        sum += (v[i] + 1u) & ~1u;
+        sum += v[i];
         v[i] = sum; // inclusive within the thread
     }
     uint32_t incl = sum;
@@ -248,36 +313,39 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
             warpOff += s_warp[w];
         total += s_warp[w];
     }
-    if (tid == 0) {
+    if (warp == 0) {
+        // decoupled look-back by the whole first warp: 32 predecessors per round trip (lane k reads tile t - k),
+        // everything up to the nearest published inclusive prefix is summed in one go
         unsigned long long excl = 0;
         if (tile == 0) {
-            status[0] = (unsigned long long)total | SCAN_PREFIX;
+            if (lane == 0)
+                status[0] = (unsigned long long)total | SCAN_PREFIX;
         } else {
-            status[tile] = (unsigned long long)total | SCAN_AGG;
-            // LOOK predecessors per round trip (the tiles are resident together, the walk can be long)
-            constexpr int LOOK = 8;
+            if (lane == 0)
+                status[tile] = (unsigned long long)total | SCAN_AGG;
             int t = (int)tile - 1;
-            bool done = false;
-            while (!done) {
-                unsigned long long s[LOOK];
+            for (;;) {
+                const int idx = t - lane;
+                const unsigned long long sv = idx >= 0 ? status[idx] : SCAN_PREFIX + 0ull; // before the first tile: an empty prefix
+                const unsigned notReady = __ballot_sync(SB_FULL, sv == 0);
+                const unsigned isPrefix = __ballot_sync(SB_FULL, (sv & SCAN_PREFIX) != 0);
+                const unsigned usable = notReady ? (1u << (__ffs(notReady) - 1)) - 1u : 0xffffffffu; // nearer than the first unpublished tile
+                const unsigned pfx = isPrefix & usable;
+                const unsigned take = pfx ? (2u << (__ffs(pfx) - 1)) - 1u : usable; // up to and including the nearest prefix
+                unsigned long long v = ((take >> lane) & 1u) ? (sv & SCAN_MASK) : 0ull;
 #pragma unroll
-                for (int k = 0; k < LOOK; ++k) {
-                    s[k] = SCAN_PREFIX + 0ull; // before the first tile: an empty prefix
-                    if (t - k >= 0)
-                        s[k] = status[t - k];
-                }
-#pragma unroll
-                for (int k = 0; k < LOOK; ++k) {
-                    if (done || s[k] == 0)
-                        break; // not published yet: look again from here
-                    excl += s[k] & SCAN_MASK;
-                    done = (s[k] & SCAN_PREFIX) != 0;
-                    --t;
-                }
+                for (int d = 16; d > 0; d >>= 1)
+                    v += __shfl_xor_sync(SB_FULL, v, d);
+                excl += v;
+                if (pfx)
+                    break;
+                t -= __popc(take); // (nothing usable: look again from the same place)
             }
-            status[tile] = (excl + total) | SCAN_PREFIX;
+            if (lane == 0)
+                status[tile] = (excl + total) | SCAN_PREFIX;
         }
-        s_excl = excl;
+        if (lane == 0)
+            s_excl = excl;
     }
     __syncthreads();
     const uint32_t off = (uint32_t)s_excl + warpOff + incl - sum;
@@ -291,36 +359,50 @@ __global__ void __launch_bounds__(SCAN_THREADS) inclusive_scan_kernel(uint32_t *
             if (base + i < n)
                 data[base + i] = off + v[i];
     }
-    if (base < n && n - 1 - base < SCAN_ITEMS) { // this thread holds E[totalCells] = number of references
+    if (base < n && n - 1 - base < SCAN_ITEMS) { // this thread holds the last entry's end = number of references
         uint32_t last = 0;
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i)
             if (base + i == n - 1)
                 last = off + v[i];
-        data[n] = last; // E[totalCells + 1]: end of the last cell after the fill
+        data[n] = last; // E[usedCells + 1]: end of the last cell after the fill
         *totalOut = last;
     }
 }
 
 } // namespace
 
-size_t sbk_grid_scan_status_words(uint32_t maxCells)
+size_t sbk_grid_entry_bound(uint32_t gridCellBits)
 {
-    size_t tiles = ((size_t)maxCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    return ((size_t)3 << gridCellBits) + 64; // three grids of at most 2^bits entries, each rounded up to a multiple of 16
+}
+
+size_t sbk_grid_scan_status_words(uint32_t gridCellBits)
+{
+    size_t tiles = (sbk_grid_entry_bound(gridCellBits) + SCAN_TILE - 1) / SCAN_TILE;
     return 2 * tiles + 4; // u64 status per tile + the tile counter
 }
 
+static void grid_clear(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc)
+{
+    cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
+    cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * sbk_grid_scan_status_words(m.gridCellBits), s);
+    // only the entries in use (the allocation bound is ~8x what a typical mesh takes)
+    const size_t bound = sbk_grid_entry_bound(m.gridCellBits);
+    const uint32_t blocks = (uint32_t)std::min<size_t>((bound / 4 + 255) / 256, 148 * 8);
+    grid_clear_kernel<<<blocks, 256, 0, s>>>(m.gridE, m.gridParams);
+    lc.kernels += 1;
+}
+
 // Phase 0 (before the leaf kernel, which counts): cleared counters + grid parameters.
-cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc)
+cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, int slabBitsMax, LaunchCounter &lc)
 {
     if (m.nT == 0)
         return cudaSuccess;
-    const uint32_t maxCells = 3u << m.gridCellBits;
-    cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)maxCells + 2), s);
-    cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
-    cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * sbk_grid_scan_status_words(maxCells), s);
-    grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, m.extentSum, m.nT, (int)m.gridCellBits, beta, m.triJob ? 1 : 0, m.latPitch, m.err, m.gridParams);
+    grid_params_kernel<<<1, 32, 0, s>>>(m.bounds, m.extentSum, m.nT, (int)m.gridCellBits, beta, m.triJob ? 1 : 0, m.latPitch,
+        m.gridAxes, std::max(0, std::min(slabBitsMax, 4)), m.err, m.gridParams);
     lc.kernels += 1;
+    grid_clear(s, m, scanScratch, lc);
     return cudaGetLastError();
 }
 
@@ -328,10 +410,9 @@ cudaError_t sbk_grid_recount(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, 
 {
     if (m.nT == 0)
         return cudaSuccess;
-    const uint32_t maxCells = 3u << m.gridCellBits;
-    cudaMemsetAsync(m.gridE, 0, sizeof(uint32_t) * ((size_t)maxCells + 2), s);
-    cudaMemsetAsync(m.gridBigCount, 0, sizeof(uint32_t) * 8, s);
-    cudaMemsetAsync(scanScratch, 0, sizeof(uint32_t) * sbk_grid_scan_status_words(maxCells), s);
+    grid_set_used_kernel<<<1, 1, 0, s>>>(m.gridParams, m.gridAxes);
+    lc.kernels += 1;
+    grid_clear(s, m, scanScratch, lc);
     grid_count_kernel<<<(m.nT + 255) / 256, 256, 0, s>>>(m.qbox, m.nT, m.gridParams, m.gridE, m.gridBigCount, m.gridAxes);
     lc.kernels += 1;
     return cudaGetLastError();
@@ -343,12 +424,11 @@ cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, Lau
 {
     if (m.nT == 0)
         return cudaSuccess;
-    const uint32_t maxCells = 3u << m.gridCellBits;
-    size_t statusWords = sbk_grid_scan_status_words(maxCells);
-    uint32_t tiles = (maxCells + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    size_t statusWords = sbk_grid_scan_status_words(m.gridCellBits);
+    uint32_t tiles = (uint32_t)((sbk_grid_entry_bound(m.gridCellBits) + SCAN_TILE - 1) / SCAN_TILE);
     unsigned long long *status = reinterpret_cast<unsigned long long *>(scanScratch);
     uint32_t *counter = scanScratch + statusWords - 2;
-    inclusive_scan_kernel<<<tiles, SCAN_THREADS, 0, s>>>(m.gridE, m.gridParams, status, counter, m.gridBigCount + 6);
+    inclusive_scan_kernel<<<tiles, SCAN_THREADS, 0, s>>>(m.gridE + 1, m.gridParams, status, counter, m.gridBigCount + 6);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -175,8 +175,39 @@ __device__ __forceinline__ GridFootprint grid_footprint(const uint4 &q, const Gr
     return f;
 }
 
-// count pass for one triangle: +1 on every cell it covers on the first `naxes` grids
-// (E[c + 1] = number of references of cell c), or on the axis's big-list counter
+// ---- depth slabs -------------------------------------------------------------------------
+// A cell's list is ordered by the depth slab of each triangle's FAR bound along the ray axis
+// (slab = the top slabBits[a] bits of the job-local 15- / 10-bit coordinate: monotone, so
+// hi_a >= aA implies slab(hi_a) >= slab(aA)).  E holds one entry per (cell, slab), slabs
+// ascending inside a cell; a ray that starts at depth aA reads the sub-lists of the slabs
+// >= slab(aA) only: [E[e0 + slab + 1], E[e0 + (1 << slabBits) + 1] & ~1), a suffix of the
+// cell's list.  References are not duplicated (the far bound picks ONE slab), so the fill
+// costs what it did; the 12-bit depth test of the reference itself is unchanged.
+__device__ __forceinline__ uint32_t grid_slab(uint32_t qa, const GridParams &g, int a)
+{
+    const int sb = (int)g.slabBits[a];
+    const int sh = (g.latShift ? (int)g.latShift : SB_Q_BITS) - sb;
+    return (qa >> sh) & ((1u << sb) - 1u);
+}
+
+// first entry (slab 0) of cell (cu, cv) of grid a
+__device__ __forceinline__ uint32_t grid_entry0(const GridParams &g, int a, uint32_t cu, uint32_t cv)
+{
+    return g.cellBase[a] + ((cv * g.nu[a] + cu) << g.slabBits[a]);
+}
+
+// the references a ray in cell (cu, cv) of grid a has to look at when it starts at quantised depth aA:
+// [i0, i1), i1 even; i0 may be odd (the slot before it then belongs to a nearer slab or is padding)
+__device__ __forceinline__ void grid_ray_range(const GridParams &g, const uint32_t *__restrict__ E, int a, uint32_t cu, uint32_t cv,
+    uint32_t aA, uint32_t &i0, uint32_t &i1)
+{
+    const uint32_t e0 = grid_entry0(g, a, cu, cv);
+    i0 = __ldg(E + e0 + grid_slab(aA, g, a) + 1);
+    i1 = __ldg(E + e0 + (1u << g.slabBits[a]) + 1) & ~1u; // the next cell's share may begin with an unused slot
+}
+
+// count pass for one triangle: +1 on every (cell, slab of its far bound) it covers on the first `naxes`
+// grids (E[e + 1] = number of references of entry e), or on the axis's big-list counter
 __device__ __forceinline__ void grid_count_tri(const uint4 &q, const GridParams &g, uint32_t *__restrict__ E,
     uint32_t *__restrict__ bigCount, int naxes)
 {
@@ -189,28 +220,31 @@ __device__ __forceinline__ void grid_count_tri(const uint4 &q, const GridParams 
             atomicAdd(&bigCount[a], 1u);
             continue;
         }
-        const uint32_t base = g.cellBase[a], nu = g.nu[a];
+        const uint32_t nu = g.nu[a];
+        const int sb = (int)g.slabBits[a];
+        const uint32_t base = g.cellBase[a] + grid_slab(f.qa >> 16, g, a) + 1; // + (cell << sb)
 #if SB_COUNT_AGG
         if (f.cu1 - f.cu0 <= 1 && f.cv1 - f.cv0 <= 1) {
-            // common case: one atomic per distinct cell of the warp's lanes that took this path
+            // common case: one atomic per distinct entry of the warp's lanes that took this path
             const unsigned act = __activemask();
             const uint32_t lane = threadIdx.x & 31;
             const bool du = f.cu1 != f.cu0, dv = f.cv1 != f.cv0;
-            const uint32_t c00 = base + f.cv0 * nu + f.cu0;
+            const uint32_t c00 = f.cv0 * nu + f.cu0;
             auto bump = [&](bool want, uint32_t cell) {
-                const unsigned peers = __match_any_sync(act, want ? cell : 0xffffffffu - lane);
+                const uint32_t e = base + (cell << sb);
+                const unsigned peers = __match_any_sync(act, want ? e : 0xffffffffu - lane);
                 if (want && (int)lane == __ffs(peers) - 1)
-                    atomicAdd(&E[cell], (uint32_t)__popc(peers));
+                    atomicAdd(&E[e], (uint32_t)__popc(peers));
             };
-            bump(true, c00 + 1);
-            bump(du, c00 + 2);
-            bump(dv, c00 + nu + 1);
-            bump(du && dv, c00 + nu + 2);
+            bump(true, c00);
+            bump(du, c00 + 1);
+            bump(dv, c00 + nu);
+            bump(du && dv, c00 + nu + 1);
             continue;
         }
 #endif
         for (uint32_t cv = f.cv0; cv <= f.cv1; ++cv)
             for (uint32_t cu = f.cu0; cu <= f.cu1; ++cu)
-                atomicAdd(&E[base + cv * nu + cu + 1], 1u);
+                atomicAdd(&E[base + ((cv * nu + cu) << sb)], 1u);
     }
 }

@@ -18,8 +18,12 @@ struct GridParams {
     double lo[3], hi[3];   // mesh bounds
     int shiftU[3], shiftV[3]; // cell = q >> shift
     uint32_t nu[3];        // cells along u
-    uint32_t cellBase[3];  // first cell of axis a in the concatenated cell space
-    uint32_t totalCells;
+    uint32_t cellBase[3];  // first entry of axis a in E (a multiple of 16)
+    uint32_t totalCells;   // entries of all three grids (cells x depth slabs, each grid rounded up to a multiple of 16)
+    uint32_t usedCells;    // ... of the grids actually binned (axes 0 .. gridAxes-1): what the clear and the scan cover
+    uint32_t slabBits[3];  // log2 of the depth slabs per cell: the list of a cell is ordered by the slab of each
+                           // triangle's FAR bound along the ray axis, so a ray starting at depth aA walks only the
+                           // sub-lists of the slabs >= slab(aA) -- a suffix of the cell's list (sb_gridq.cuh)
     uint32_t latShift;     // 0: plain mesh.  Batch mesh (sb_batch_upload): quantised coordinates are job-local in the bits
                            // below latShift (10), the job's lattice position (sb_gridq.cuh lattice3) sits above them
     double qmax;           // clamp of the job-local part: 32767 (plain) or 1023 (batch)
@@ -57,7 +61,7 @@ struct MeshDev {
     uint32_t gridCellBits = 0;          // at most 2^bits cells per axis (allocation bound)
     int gridAxes = 2;                   // grids actually binned: axes 0..gridAxes-1 (the third one only once a vote needed it)
     GridParams *gridParams = nullptr;
-    uint32_t *gridE = nullptr;          // totalCells + 2: cell c = refs[E[c+1] .. E[c+2])
+    uint32_t *gridE = nullptr;          // totalCells + 2: entry e = refs[E[e+1] .. E[e+2]); &gridE[1] is 16-byte aligned
     uint2 *gridRefs = nullptr;          // cell_ref_pack (sb_gridq.cuh): cell-relative quantised box + triangle id
     uint32_t gridRefCap = 0;            // entries allocated behind gridRefs
     uint4 *gridBigRefs = nullptr;       // 3 * gridBigCap: triangles covering too many cells (grid_ref_pack, absolute)
@@ -204,8 +208,9 @@ cudaError_t sbk_classify2(cudaStream_t s, const MeshDev &target, const ClassifyA
 size_t sbk_radix_workspace_words(size_t n);
 
 // sb_grid.cu
-size_t sbk_grid_scan_status_words(uint32_t maxCells);
-cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, LaunchCounter &lc);
+size_t sbk_grid_entry_bound(uint32_t gridCellBits);   // entries of E the allocation has to hold (+ 2 closing words)
+size_t sbk_grid_scan_status_words(uint32_t gridCellBits);
+cudaError_t sbk_grid_prepare(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, float beta, int slabBitsMax, LaunchCounter &lc);
 cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc);
 // counts again from the stored quantised boxes, for m.gridAxes axes (a mesh built with two grids gets its third)
 cudaError_t sbk_grid_recount(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc);

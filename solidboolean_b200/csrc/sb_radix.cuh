@@ -28,26 +28,18 @@ constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PREFIX = 2u << 30;
 constexpr uint32_t VALUE_MASK = (1u << 30) - 1;
 
-// Histogram of every digit position in one pass; the last CTA to finish turns
-// each 256-bin histogram into an exclusive prefix (global digit offsets).
-template <typename KeyT, int BITS>
-__global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ keys, uint32_t n,
-    int beginBit, int passes, uint32_t *__restrict__ hist /* [passes][256] */, uint32_t *__restrict__ ticket)
+// Tail of a histogram pass (hist_kernel below, or a producer kernel that counted the digits of the keys
+// it wrote -- tri_prepare_kernel of sb_build.cu): the CTA's shared-memory counts are added to the global
+// histogram; the last CTA to finish turns each 256-bin histogram into an exclusive prefix (global digit
+// offsets).  Called by all threads of the CTA, blockDim.x >= 256.
+template <int BITS>
+__device__ __forceinline__ void hist_flush_and_scan(uint32_t *s_hist, int passes, uint32_t *__restrict__ hist /* [passes][256] */,
+    uint32_t *__restrict__ ticket)
 {
     constexpr int RADIX = 1 << BITS;
-    constexpr int MAXP = BITS == 8 ? MAX_PASSES : 4;
-    __shared__ uint32_t s_hist[MAXP * RADIX];
     __shared__ bool s_last;
-    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
-        s_hist[i] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n; i += gridDim.x * THREADS) {
-        KeyT k = keys[i];
-        for (int p = 0; p < passes; ++p)
-            atomicAdd(&s_hist[p * RADIX + (uint32_t)((k >> (beginBit + BITS * p)) & (RADIX - 1))], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x)
         if (s_hist[i])
             atomicAdd(&hist[i], s_hist[i]);
     __threadfence();
@@ -78,6 +70,25 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ 
             hist[p * RADIX + threadIdx.x] = s_scan[threadIdx.x] - v;
         __syncthreads();
     }
+}
+
+// Histogram of every digit position in one pass over the keys.
+template <typename KeyT, int BITS>
+__global__ void __launch_bounds__(THREADS) hist_kernel(const KeyT *__restrict__ keys, uint32_t n,
+    int beginBit, int passes, uint32_t *__restrict__ hist /* [passes][256] */, uint32_t *__restrict__ ticket)
+{
+    constexpr int RADIX = 1 << BITS;
+    constexpr int MAXP = BITS == 8 ? MAX_PASSES : 4;
+    __shared__ uint32_t s_hist[MAXP * RADIX];
+    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
+        s_hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n; i += gridDim.x * THREADS) {
+        KeyT k = keys[i];
+        for (int p = 0; p < passes; ++p)
+            atomicAdd(&s_hist[p * RADIX + (uint32_t)((k >> (beginBit + BITS * p)) & (RADIX - 1))], 1u);
+    }
+    hist_flush_and_scan<BITS>(s_hist, passes, hist, ticket);
 }
 
 template <typename KeyT, bool HAS_VALUES, int BITS>
@@ -245,9 +256,28 @@ inline size_t tiles_for(size_t n) { return (n + TILE - 1) / TILE; }
 // Sort n keys on bits [beginBit, endBit) with BITS-bit digits.  Results land in
 // *outKeys/*outVals (either the primary or the tmp buffers).  Returns the number of
 // kernels launched.
+//
+// histByProducer: the kernel that wrote the keys also counted their digits (hist_flush_and_scan); the caller
+// then cleared the workspace with sort_clear BEFORE that kernel ran and passes the hist / ticket pointers
+// of sort_hist / sort_ticket to it.
+inline int sort_passes(size_t n, int beginBit, int endBit, int bits)
+{
+    if (n < 2 || endBit <= beginBit)
+        return 0;
+    const int maxp = bits == 8 ? MAX_PASSES : 4;
+    const int passes = (endBit - beginBit + bits - 1) / bits;
+    return passes > maxp ? maxp : passes;
+}
+inline void sort_clear(cudaStream_t stream, const Workspace &ws, size_t n, int passes)
+{
+    cudaMemsetAsync(ws.mem, 0, sizeof(uint32_t) * (MAX_PASSES * 512 + 16 + (size_t)passes * tiles_for(n) * 256), stream);
+}
+inline uint32_t *sort_hist(const Workspace &ws) { return ws.mem; }
+inline uint32_t *sort_ticket(const Workspace &ws) { return ws.mem + MAX_PASSES * 512; }
+
 template <typename KeyT, int BITS>
 int sort(cudaStream_t stream, KeyT *keys, KeyT *keysTmp, uint32_t *vals, uint32_t *valsTmp, size_t n,
-    int beginBit, int endBit, const Workspace &ws, int smCount, KeyT **outKeys, uint32_t **outVals)
+    int beginBit, int endBit, const Workspace &ws, int smCount, KeyT **outKeys, uint32_t **outVals, bool histByProducer = false)
 {
     constexpr int RADIX = 1 << BITS;
     constexpr int MAXP = BITS == 8 ? MAX_PASSES : 4;
@@ -264,13 +294,15 @@ int sort(cudaStream_t stream, KeyT *keys, KeyT *keysTmp, uint32_t *vals, uint32_
     uint32_t *ticket = ws.mem + MAX_PASSES * 512;
     uint32_t *counters = ticket + 1;
     uint32_t *lookback = ws.mem + MAX_PASSES * 512 + 16;
-    cudaMemsetAsync(ws.mem, 0, sizeof(uint32_t) * (MAX_PASSES * 512 + 16 + (size_t)passes * tiles * RADIX), stream);
-    int histBlocks = (int)((n + THREADS * 8 - 1) / (THREADS * 8));
-    if (histBlocks > smCount * 4)
-        histBlocks = smCount * 4;
-    if (histBlocks < 1)
-        histBlocks = 1;
-    hist_kernel<KeyT, BITS><<<histBlocks, THREADS, 0, stream>>>(keys, (uint32_t)n, beginBit, passes, hist, ticket);
+    if (!histByProducer) {
+        cudaMemsetAsync(ws.mem, 0, sizeof(uint32_t) * (MAX_PASSES * 512 + 16 + (size_t)passes * tiles * RADIX), stream);
+        int histBlocks = (int)((n + THREADS * 8 - 1) / (THREADS * 8));
+        if (histBlocks > smCount * 4)
+            histBlocks = smCount * 4;
+        if (histBlocks < 1)
+            histBlocks = 1;
+        hist_kernel<KeyT, BITS><<<histBlocks, THREADS, 0, stream>>>(keys, (uint32_t)n, beginBit, passes, hist, ticket);
+    }
     KeyT *kin = keys, *kout = keysTmp;
     uint32_t *vin = vals, *vout = valsTmp;
     for (int p = 0; p < passes; ++p) {
@@ -286,7 +318,7 @@ int sort(cudaStream_t stream, KeyT *keys, KeyT *keysTmp, uint32_t *vals, uint32_
     *outKeys = kin;
     if (outVals)
         *outVals = vin;
-    return 1 + passes;
+    return (histByProducer ? 0 : 1) + passes;
 }
 
 } // namespace sbradix
