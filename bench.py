@@ -570,6 +570,15 @@ def run_ours(args):
             geo_host[off:off + flat.numel()].copy_(flat)
         geo_dev = torch.empty(geo_slice * world, dtype=torch.uint8, device=dev)
 
+    def host_front_end(m1, m2):
+        # the reference-facing call with HOST buffers: flags and hits land in pinned memory (sb_front_end_host)
+        if "cap" not in host_hits:
+            cap = max(1024, int(H) * 3 // 2 + 64)
+            host_hits.update(cap=cap, ab=torch.zeros(2 * cap, dtype=torch.int32).pin_memory(),
+                             seg=torch.zeros(6 * cap, dtype=torch.float64).pin_memory())
+        return sb.Isect.front_end_host(m1, m2, out_in_a_t.data_ptr(), out_in_b_t.data_ptr(), host_hits["ab"].data_ptr(),
+                                       host_hits["seg"].data_ptr(), host_hits["cap"])
+
     def e2e_step():
         with torch.cuda.stream(ext):
             if world > 1:
@@ -595,8 +604,7 @@ def run_ours(args):
                 ma.update(pin[0].data_ptr(), pin[1].data_ptr())
                 mb.update(pin[2].data_ptr(), pin[3].data_ptr())
                 ma.build(); mb.build()
-                fa, fb = flags_views()
-                x = sb.Isect.front_end(ma, mb, fa.data_ptr(), fb.data_ptr())
+                x = host_front_end(ma, mb)
                 Pg, Hg = x.num_candidates, x.num_hits
             else:
                 # the same with two NEW meshes per step (sb_mesh_upload + sb_mesh_build + sb_mesh_destroy): allocation,
@@ -605,10 +613,18 @@ def run_ours(args):
                 xb = sb.Mesh.from_pointers(ctx, pin[2].data_ptr(), nVB, pin[3].data_ptr(), nB, build=False, keep=pin)
                 xa.build(); xb.build()
                 sh = None
-                fa, fb = flags_views()
-                x = sb.Isect.front_end(xa, xb, fa.data_ptr(), fb.data_ptr())
+                x = host_front_end(xa, xb)
                 Pg, Hg = x.num_candidates, x.num_hits
-            if rank == 0:  # results back to the host: per-face flags, hit pairs + segments -- all into PINNED
+            if rank == 0 and world == 1:
+                # sb_front_end_host has already put everything into the pinned host buffers (flags of both meshes, hit
+                # pairs + segments), each copy enqueued behind the stream that produced it; a hit list longer than
+                # the landing buffer is fetched with sb_isect_hits into a larger one
+                if host_hits["cap"] < x.num_hits:
+                    cap = x.num_hits * 3 // 2 + 64
+                    host_hits.update(cap=cap, ab=torch.zeros(2 * cap, dtype=torch.int32).pin_memory(),
+                                     seg=torch.zeros(6 * cap, dtype=torch.float64).pin_memory())
+                    sb._check(x.lib.sb_isect_hits(x.h, host_hits["ab"].data_ptr(), host_hits["seg"].data_ptr()))
+            elif rank == 0:  # results back to the host: per-face flags, hit pairs + segments -- all into PINNED
                 # buffers (the C ABI takes any host pointer; pageable ones make the copies staged and slow),
                 # flag copies enqueued first so that the one synchronisation inside sb_isect_hits covers all
                 out_in_a_t.copy_(fa, non_blocking=True)
@@ -696,7 +712,7 @@ def run_ours(args):
                          "kernel_ms_per_step": round(cls_ms, 4)},
             "e2e": {"value": H2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms,
-                    **({"how": "sb_mesh_update (H2D of all four arrays from pinned host memory) + sb_mesh_build x2 + sb_front_end + "
+                    **({"how": "sb_mesh_update (H2D of all four arrays from pinned host memory) + sb_mesh_build x2 + sb_front_end_host + "
                                "D2H of hit pairs, segments and per-face flags, every step; the two meshes are kept between steps",
                         "ms_per_step_new_meshes_every_step": e2e_fresh_ms} if e2e_fresh_ms is not None else {})},
             "gpu_launches": int(round(launches_per_step * args.steps)),

@@ -377,6 +377,16 @@ int sb_front_end(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **
 int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t a_begin, size_t a_end,
                        size_t b_begin, size_t b_end, unsigned flags, sb_isect **out,
                        void *d_insideA, void *d_insideB);
+/* The same with HOST outputs -- what a caller of SolidBoolean::combine() (src/solidboolean.cpp:288-349, :468-510)
+ * consumes on the CPU: insideA / insideB receive nT(A) / nT(B) flag bytes, hit_ab / hit_seg (optional, both or
+ * neither) the hit list as sb_isect_hits returns it when it has at most hit_capacity entries (otherwise they are
+ * left untouched and sb_isect_hits fetches it; sb_isect_counts tells).  Every result is copied as soon as the
+ * stream that produces it is done (A's flags while B's classification still runs, the hits while both do), so
+ * the device-to-host traffic hides behind the kernels; pinned host memory keeps the copies asynchronous.
+ * All buffers are complete when the call returns. */
+int sb_front_end_host(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out,
+                      uint8_t *insideA, uint8_t *insideB, uint32_t *hit_ab /* 2 x hit_capacity */,
+                      double *hit_seg /* 6 x hit_capacity */, size_t hit_capacity);
 
 /* ---- instrumentation --------------------------------------------------------
  * Stage timing with CUDA events on the context stream.  Stages accumulate the

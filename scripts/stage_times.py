@@ -18,7 +18,10 @@ ma = ctx.mesh(*a, build=False)
 mb = ctx.mesh(*b, build=False)
 da = torch.zeros(len(a[1]), dtype=torch.uint8, device="cuda")
 db = torch.zeros(len(b[1]), dtype=torch.uint8, device="cuda")
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if "--flush" in sys.argv else None   # as bench.py: L2 evicted between steps
 for it in range(reps):
+    if flush is not None:
+        flush.zero_(); torch.cuda.synchronize()
     ctx.reset_timing()
     t0 = time.perf_counter()
     ma.build(); mb.build()

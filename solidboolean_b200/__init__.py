@@ -120,6 +120,7 @@ ABI = {
     "sb_classify_faces_device": (C.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "sb_front_end": (C.c_int, [_vp, _vp, C.c_uint, C.POINTER(_vp), _vp, _vp]),
     "sb_front_end_range": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, C.c_uint, C.POINTER(_vp), _vp, _vp]),
+    "sb_front_end_host": (C.c_int, [_vp, _vp, C.c_uint, C.POINTER(_vp), _vp, _vp, _vp, _vp, _sz]),
     "sb_context_enable_timing": (C.c_int, [_vp, C.c_int]),
     "sb_context_reset_timing": (C.c_int, [_vp]),
     "sb_context_get_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
@@ -500,6 +501,23 @@ def batch_pitch(*arrays) -> float:
 
 class Isect:
     """Candidate pairs + intersecting pairs of two meshes (sb_isect)."""
+
+    @classmethod
+    def front_end_host(cls, a: Mesh, b: Mesh, inside_a_ptr: int, inside_b_ptr: int, hit_ab_ptr: int = 0, hit_seg_ptr: int = 0,
+                       hit_capacity: int = 0, flags=0):
+        """sb_front_end_host: the whole front end with HOST outputs (raw pointers, e.g. pinned torch tensors): per-face
+        flags of both meshes and, when it fits hit_capacity, the hit list (pairs + segments)."""
+        self = cls.__new__(cls)
+        self.a, self.b, self.lib = a, b, a.lib
+        h = _vp()
+        _check(self.lib.sb_front_end_host(a.h, b.h, flags, C.byref(h), _vp(inside_a_ptr), _vp(inside_b_ptr),
+                                          _vp(hit_ab_ptr) if hit_ab_ptr else None, _vp(hit_seg_ptr) if hit_seg_ptr else None,
+                                          hit_capacity))
+        self.h = h
+        nc, nh = _sz(0), _sz(0)
+        _check(self.lib.sb_isect_counts(h, C.byref(nc), C.byref(nh)))
+        self.num_candidates, self.num_hits = int(nc.value), int(nh.value)
+        return self
 
     @classmethod
     def front_end(cls, a: Mesh, b: Mesh, d_inside_a: int, d_inside_b: int, flags=0, a_range=None, b_range=None):

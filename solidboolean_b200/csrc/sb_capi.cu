@@ -120,6 +120,14 @@ struct sb_context {
     } lanes[3];
     uint32_t *scanScratch = nullptr; // grid-build scan status words
     size_t scanScratchWords = 0;
+    void *feFlags = nullptr;         // sb_front_end_host: device copy of the two flag arrays (grow-only)
+    size_t feFlagsBytes = 0;
+    uint64_t uploadSeq = 0;          // counts the host uploads (which of two fresh meshes arrives last)
+    bool optimisticVerify = true;    // SB_OPTIMISTIC=0: a front end waits for the rebuilds' reference counts before it enqueues anything
+    bool deferVerify = false;        // ... set while such a front end enqueues its work (mesh_finish then leaves the check alone)
+    uint64_t optimisticRedone = 0;   // front ends that had to be repeated because a rebuild did not fit its lists
+    bool streamClassify = false;     // SB_STREAM_CLASSIFY=1: chunk-by-chunk classification of a just-uploaded mesh (measured at
+                                     // C3: 1.97 against 1.98 ms per host-buffer step -- the GPU is busy either way; off)
     float gridBeta = 1.0f;           // ray-grid cell size / mean triangle-box extent (SB_GRID_BETA)
     int gridSlabBits = 2;            // at most 2^this depth slabs per ray-grid cell (SB_GRID_SLABS = the bits; 0: one list per cell)
     int sortBeginBit = -1;           // lowest Morton bit that is sorted (SB_SORT_BEGIN_BIT); -1 = by mesh size
@@ -172,6 +180,16 @@ struct sb_mesh {
     uint32_t *dJobStart = nullptr;   // ... and their device copy: [triangle starts][vertex starts] (in the arena)
     bool treeBuilt = false;          // LBVH topology built (lazily, on first use as a traversal target)
     bool treeWanted = false;         // the mesh has been a traversal target: rebuilds include the LBVH
+    // Geometry that has only just been sent from host memory (sb_mesh_upload / sb_mesh_update): the index triples go up
+    // in chunks with an event behind each, and the first front end after it classifies this mesh's faces in their
+    // ORIGINAL order chunk by chunk as they arrive (needs the other mesh's grids, not this mesh's build) -- that
+    // direction then runs beside the rest of the transfer and this mesh's build instead of after them.
+    static constexpr int MAX_CHUNKS = 4;
+    cudaEvent_t chunkEv[MAX_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t chunkEnd[MAX_CHUNKS] = {0, 0, 0, 0};
+    int nChunks = 0;
+    bool fresh = false;              // uploaded from the host since the last front end
+    uint64_t uploadSeq = 0;          // order of the uploads within the context
 };
 
 struct sb_isect {
@@ -552,6 +570,10 @@ int sb_context_create(int device, sb_context **out)
         c->classifyPoolLimit = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("SB_CLASSIFY_V2"))
         c->classifyBalanced = atoi(e) != 0;
+    if (const char *e = getenv("SB_OPTIMISTIC"))
+        c->optimisticVerify = atoi(e) != 0;
+    if (const char *e = getenv("SB_STREAM_CLASSIFY"))
+        c->streamClassify = atoi(e) != 0;
     if (const char *e = getenv("SB_GRID_SLABS"))
         c->gridSlabBits = std::max(0, std::min(atoi(e), 4));
     if (const char *e = getenv("SB_GRID_BETA")) {
@@ -605,6 +627,7 @@ void sb_context_destroy(sb_context *c)
     cudaFree(c->classifyOut);
     cudaFree(c->overflowList);
     cudaFree(c->scanScratch);
+    cudaFree(c->feFlags);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -709,6 +732,40 @@ int sb_context_classify_stats(sb_context *c, uint64_t *rays, uint64_t *candidate
 
 // ---- mesh ---------------------------------------------------------------------
 
+// host -> device copies of a mesh's two arrays on its stream: coordinates first, then the index triples in up to
+// MAX_CHUNKS pieces with an event behind each (see sb_mesh::chunkEv)
+static cudaError_t upload_from_host(sb_mesh *m, const void *xyz, const void *tri)
+{
+    cudaError_t e = cudaSuccess;
+    const size_t nV = m->d.nV, nT = m->d.nT;
+    if (xyz && nV)
+        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, m->stream);
+    m->nChunks = 0;
+    m->fresh = false;
+    if (e != cudaSuccess || !tri || !nT)
+        return e;
+    int n = nT >= (1u << 18) ? sb_mesh::MAX_CHUNKS : nT >= (1u << 16) ? 2 : 1;
+    const size_t per = (((nT + n - 1) / n) + 1023) / 1024 * 1024;
+    size_t done = 0;
+    for (int k = 0; k < n && done < nT && e == cudaSuccess; ++k) {
+        const size_t end = std::min(nT, done + per);
+        e = cudaMemcpyAsync(m->d.tri + 3 * done, static_cast<const uint32_t *>(tri) + 3 * done, 12 * (end - done),
+            cudaMemcpyHostToDevice, m->stream);
+        if (e == cudaSuccess && !m->chunkEv[k])
+            e = cudaEventCreateWithFlags(&m->chunkEv[k], cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(m->chunkEv[k], m->stream);
+        m->chunkEnd[k] = (uint32_t)end;
+        m->nChunks = k + 1;
+        done = end;
+    }
+    if (e == cudaSuccess && xyz) { // (both arrays new: what the faces' centroids are made of is on its way)
+        m->fresh = true;
+        m->uploadSeq = ++m->ctx->uploadSeq;
+    }
+    return e;
+}
+
 int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t *tri, size_t nT, sb_mesh **out)
 {
     if (!ctx || !out)
@@ -738,11 +795,7 @@ int sb_mesh_upload(sb_context *ctx, const double *xyz, size_t nV, const uint32_t
         if (r)
             return r;
     }
-    cudaError_t e = cudaSuccess;
-    if (nV)
-        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, m->stream);
-    if (e == cudaSuccess && nT)
-        e = cudaMemcpyAsync(m->d.tri, tri, 12 * nT, cudaMemcpyHostToDevice, m->stream);
+    cudaError_t e = upload_from_host(m, xyz, tri);
     if (e == cudaSuccess)
         e = cudaEventRecord(m->ready, m->stream);
     if (e == cudaSuccess)
@@ -799,11 +852,15 @@ int sb_mesh_update(sb_mesh *m, const void *xyz, const void *tri, int on_device)
     sb_context *c = m->ctx;
     DeviceGuard g(c);
     order_after_context(c, m);
-    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (xyz && m->d.nV)
-        SB_CUDA(cudaMemcpyAsync(m->d.xyz, xyz, 24 * (size_t)m->d.nV, kind, m->stream));
-    if (tri && m->d.nT)
-        SB_CUDA(cudaMemcpyAsync(m->d.tri, tri, 12 * (size_t)m->d.nT, kind, m->stream));
+    if (on_device) {
+        if (xyz && m->d.nV)
+            SB_CUDA(cudaMemcpyAsync(m->d.xyz, xyz, 24 * (size_t)m->d.nV, cudaMemcpyDeviceToDevice, m->stream));
+        if (tri && m->d.nT)
+            SB_CUDA(cudaMemcpyAsync(m->d.tri, tri, 12 * (size_t)m->d.nT, cudaMemcpyDeviceToDevice, m->stream));
+        m->fresh = false;
+    } else {
+        SB_CUDA(upload_from_host(m, xyz, tri));
+    }
     m->built = false;
     m->gridPending = false;
     m->geomChanged = true; // the next build reports its reference counts (mesh_finish checks them against the capacity)
@@ -951,27 +1008,65 @@ static int grid_size_and_fill(sb_mesh *m, bool readback = true)
     return SB_OK;
 }
 
+// A rebuild after sb_mesh_update: did the new geometry fit the reference lists sized for the old one?  Waits for the
+// counts the build sent to the host.  *changed: the lists overflowed (the mesh is then built again with lists of the
+// right size) or the per-axis big lists have other lengths than the host believed -- whatever was enqueued against
+// the mesh's grids before this check must be repeated.
+static int mesh_finish(const sb_mesh *mc);
+static int mesh_verify(sb_mesh *m, bool *changed)
+{
+    if (changed)
+        *changed = false;
+    if (!m || !m->verifyPending)
+        return SB_OK;
+    m->verifyPending = false;
+    DeviceGuard g(m->ctx);
+    SB_CUDA(cudaEventSynchronize(m->verifyEv));
+    if (*reinterpret_cast<int *>(m->hErr))
+        return mesh_error(m, *reinterpret_cast<int *>(m->hErr));
+    const uint32_t *h = m->hCounts;
+    if (h[0] > m->d.gridRefCap || std::max(h[1], std::max(h[2], h[3])) > m->d.gridBigCap) {
+        m->gridSized = false; // no: a first build sizes them again (counts on their way, finished by mesh_finish)
+        if (changed)
+            *changed = true;
+        int rb = sb_mesh_build(m);
+        if (rb)
+            return rb;
+    } else {
+        for (int k = 0; k < 3; ++k) {
+            if (changed && m->d.gridBigN[k] != h[1 + k])
+                *changed = true;
+            m->d.gridBigN[k] = h[1 + k];
+        }
+    }
+    return SB_OK;
+}
+
+// the same question without side effects (the counts are waited for): would mesh_verify report a change?
+static bool mesh_verify_would_change(const sb_mesh *m)
+{
+    if (!m || !m->verifyPending)
+        return false;
+    DeviceGuard g(m->ctx);
+    if (cudaEventSynchronize(m->verifyEv) != cudaSuccess || *reinterpret_cast<const int *>(m->hErr))
+        return true;
+    const uint32_t *h = m->hCounts;
+    if (h[0] > m->d.gridRefCap || std::max(h[1], std::max(h[2], h[3])) > m->d.gridBigCap)
+        return true;
+    for (int k = 0; k < 3; ++k)
+        if (m->d.gridBigN[k] != h[1 + k])
+            return true;
+    return false;
+}
+
 // Completes a first build whose reference list is still to be sized and filled.
 static int mesh_finish(const sb_mesh *mc)
 {
     sb_mesh *m = const_cast<sb_mesh *>(mc);
-    if (m && m->verifyPending) {
-        // a rebuild after sb_mesh_update: did the new geometry fit the reference lists sized for the old one?
-        m->verifyPending = false;
-        DeviceGuard g(m->ctx);
-        SB_CUDA(cudaEventSynchronize(m->verifyEv));
-        if (*reinterpret_cast<int *>(m->hErr))
-            return mesh_error(m, *reinterpret_cast<int *>(m->hErr));
-        const uint32_t *h = m->hCounts;
-        if (h[0] > m->d.gridRefCap || std::max(h[1], std::max(h[2], h[3])) > m->d.gridBigCap) {
-            m->gridSized = false; // no: a first build sizes them again (counts on their way, finished below)
-            int rb = sb_mesh_build(m);
-            if (rb)
-                return rb;
-        } else {
-            for (int k = 0; k < 3; ++k)
-                m->d.gridBigN[k] = h[1 + k];
-        }
+    if (m && m->verifyPending && !m->ctx->deferVerify) {
+        int rv = mesh_verify(m, nullptr);
+        if (rv)
+            return rv;
     }
     if (!m || !m->gridPending)
         return SB_OK;
@@ -1274,6 +1369,9 @@ static void mesh_destroy_now(sb_mesh *m)
         cudaEventDestroy(m->leavesDone);
     if (m->verifyEv)
         cudaEventDestroy(m->verifyEv);
+    for (cudaEvent_t ev : m->chunkEv)
+        if (ev)
+            cudaEventDestroy(ev);
     if (m->buildGraph)
         cudaGraphExecDestroy(m->buildGraph);
     if (m->gridGraph)
@@ -2447,6 +2545,8 @@ struct ClassifyJob {
     bool legacyPass = false;      // ... and this is the general kernel's launch over the points it left (same scratch,
     uint32_t legacy = 0;          //     counters carried on)
     bool noBalanced = false;      // after a failed legacy pass: everything through the general kernel
+    const sb_mesh *rawQuery = nullptr; // raw faces mode: the query mesh whose upload chunks pace the first launch
+    int launches = 0;             // classify_launch calls of this job (follow-up passes and retries included)
 };
 
 // can the balanced kernel take this launch?  (no per-axis big lists on the grids it may trace)
@@ -2461,10 +2561,15 @@ static bool classify_balanced_ok(const sb_context *c, const sb_mesh *target, con
     return true;
 }
 
+// rawQuery: the query mesh's faces in original order, one launch per upload chunk behind that chunk's event
+// (a0.rawFaces; first launch of a job only -- the follow-up launches go over lists of the same numbering)
 static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh *target, const ClassifyArgs &a0,
-    ClassifyJob &job, unsigned long long forceCap = 0)
+    ClassifyJob &job, unsigned long long forceCap = 0, const sb_mesh *rawQuery = nullptr)
 {
     ClassifyArgs a = a0;
+    if (rawQuery)
+        job.rawQuery = rawQuery;
+    rawQuery = job.rawQuery;
     if (a.perAxis) {
         int r = ensure_grid3(target); // all three rays of every point
         if (r)
@@ -2504,7 +2609,14 @@ static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh 
     const uint32_t traceBlocks = sbk_classify_blocks(job.second ? job.undecided : job.legacyPass ? job.legacy : job.points);
     if (traceFile)
         SB_CUDA(cudaMalloc(&trace, 32 * (size_t)traceBlocks));
-    {
+    const int nLaunch = rawQuery && !a.list && rawQuery->nChunks > 0 ? rawQuery->nChunks : 1;
+    for (int k = 0; k < nLaunch; ++k) {
+        if (nLaunch > 1 || (rawQuery && !a.list && rawQuery->nChunks == 1)) {
+            // faces [chunkEnd[k-1], chunkEnd[k]) once their index triples are on the device
+            SB_CUDA(cudaStreamWaitEvent(lane.stream, rawQuery->chunkEv[k], 0));
+            a.first = k ? rawQuery->chunkEnd[k - 1] : 0u;
+            a.end = rawQuery->chunkEnd[k];
+        }
         StageTimer t(c, SB_STAGE_CLASSIFY, lane.stream);
         if (job.balanced)
             SB_CUDA(sbk_classify2(lane.stream, target->d, a, &lane.d->stats[0], &lane.d->overflowCount, &lane.d->legacyCount,
@@ -2527,6 +2639,7 @@ static int classify_launch(sb_context *c, sb_context::Lane &lane, const sb_mesh 
     }
     SB_CUDA(cudaMemcpyAsync(lane.h, lane.d, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, lane.stream));
     job.launched = true;
+    job.launches += 1;
     return SB_OK;
 }
 
@@ -2557,7 +2670,9 @@ static int classify_finish(sb_context *c, sb_context::Lane &lane, const sb_mesh 
             if (job.legacyPass) {
                 // the lists live in the same allocation: start over, everything through the general kernel
                 release();
+                const int launchesSoFar = job.launches;
                 job = ClassifyJob();
+                job.launches = launchesSoFar;
                 job.noBalanced = true;
                 attempt = 0;
                 int r = classify_launch(c, lane, target, a, job, needed);
@@ -2765,8 +2880,17 @@ int sb_classify_faces_device(const sb_mesh *query, const sb_mesh *target, size_t
     return classify_faces_impl(query, target, begin, end, false, static_cast<uint8_t *>(d_inside), &dIn, &dAx);
 }
 
-int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t aEnd, size_t bBegin, size_t bEnd,
-    unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
+// host outputs of a front end (sb_front_end_host): every result is sent on its way as soon as the stream that produces it
+// is done -- A's flags while B's classification still runs, the hit list while both do
+struct FrontEndHostOut {
+    uint8_t *insideA = nullptr, *insideB = nullptr;
+    uint32_t *hitAB = nullptr;
+    double *hitSeg = nullptr;
+    size_t hitCap = 0;
+};
+
+static int front_end_core(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t aEnd, size_t bBegin, size_t bEnd,
+    unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB, const FrontEndHostOut *host)
 {
     if (!A || !B || !out || !d_insideA || !d_insideB)
         return fail(SB_ERR_INVALID, "null argument");
@@ -2780,13 +2904,6 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
         if (rb)
             return rb;
     }
-    {
-        int rf = mesh_finish(A);
-        if (!rf)
-            rf = mesh_finish(B);
-        if (rf)
-            return rf;
-    }
     sb_context *c = A->ctx;
     DeviceGuard g(c);
     aEnd = std::min<size_t>(aEnd, A->d.nT);
@@ -2795,30 +2912,123 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
     bBegin = std::min(bBegin, bEnd);
     if (aBegin % 32 || bBegin % 32)
         return fail(SB_ERR_INVALID, "range begin must be a multiple of 32");
+    // A mesh whose bytes have only just been sent from the host, later than the other mesh's: its faces are
+    // classified in their original order, chunk by chunk as the index triples arrive -- the launch waits for the
+    // TARGET's grids and the upload events only, not for this mesh's own build (nor does the host: the target is
+    // finished first, the streamed direction enqueued, and only then the just-uploaded mesh's build waited for)
+    auto streamed = [&](const sb_mesh *q, const sb_mesh *t, size_t begin, size_t end) {
+        return c->streamClassify && q->fresh && q->nChunks > 0 && q->uploadSeq > t->uploadSeq && begin == 0 && end == q->d.nT &&
+               end > 0 && !q->d.triJob && !q->d.origFace && !q->d.ownFilter && !q->d.sharedVtx && !t->d.sharedVtx && t->d.nT;
+    };
+    const bool rawA = streamed(A, B, aBegin, aEnd), rawB = !rawA && streamed(B, A, bBegin, bEnd);
+    const_cast<sb_mesh *>(A)->fresh = false;
+    const_cast<sb_mesh *>(B)->fresh = false;
+    // Optimistic enqueue.  After sb_mesh_update + sb_mesh_build the host does not know yet whether the rebuild's
+    // references fitted the lists sized for the old geometry (the counts arrive when the build is done).  Waiting for
+    // them here would leave the GPU idle between the build and the first kernel of the front end (wake-up + a dozen
+    // launches: ~50 us of a 2 ms step); instead everything is enqueued behind the builds right away -- the balanced
+    // classifier keeps its reads inside the allocations whatever the lists hold (sb_classify.cuh Target) -- and the
+    // counts are checked once they are there, before anything is handed out: had they changed (lists overflowed, big
+    // lists appeared), the run is thrown away and repeated the careful way.
+    auto plain = [](const sb_mesh *m) {
+        return !m->d.triJob && !m->d.origFace && !m->d.sharedVtx && !m->gridPending && m->gridSized &&
+               !m->d.gridBigN[0] && !m->d.gridBigN[1] && !m->d.gridBigN[2];
+    };
+    const bool optimistic = SB_CLS_GUARDS && c->optimisticVerify && (A->verifyPending || B->verifyPending) && plain(A) && plain(B) && !rawA && !rawB &&
+                            c->classifyBalanced && !c->classifyPoolLimit && A->d.nT && B->d.nT;
+    struct DeferGuard {
+        sb_context *c;
+        ~DeferGuard() { c->deferVerify = false; }
+    } deferGuard{c};
+    c->deferVerify = optimistic;
     // the two classification directions run on their own lanes, behind whatever the
     // context stream has enqueued so far and behind the builds they read
     cudaEventRecord(c->orderEvent, c->stream);
     ClassifyArgs qa, qb;
     qa.queryMesh = &A->d; qa.begin = (uint32_t)aBegin; qa.end = (uint32_t)aEnd; qa.inside = static_cast<uint8_t *>(d_insideA);
     qb.queryMesh = &B->d; qb.begin = (uint32_t)bBegin; qb.end = (uint32_t)bEnd; qb.inside = static_cast<uint8_t *>(d_insideB);
+    qa.rawFaces = rawA;
+    qb.rawFaces = rawB;
     ClassifyJob ja, jb;
     int r = SB_OK;
-    for (int l = 1; l <= 2 && !r; ++l) {
+    bool finished[2] = {false, false}; // mesh_finish done for A / B
+    auto finish = [&](int which) {
+        if (finished[which])
+            return SB_OK;
+        finished[which] = true;
+        return mesh_finish(which ? B : A);
+    };
+    for (int step = 0; step < 2 && !r; ++step) {
+        const int l = rawB ? 2 - step : 1 + step; // (a streamed direction is enqueued first)
         sb_context::Lane &lane = c->lanes[l];
-        cudaStreamWaitEvent(lane.stream, c->orderEvent, 0);
-        // queries need the other mesh's sorted centroids only; the target needs its grids
-        cudaStreamWaitEvent(lane.stream, l == 1 ? A->leafReady : A->ready, 0);
-        cudaStreamWaitEvent(lane.stream, l == 1 ? B->ready : B->leafReady, 0);
         const sb_mesh *target = l == 1 ? B : A;
+        const sb_mesh *query = l == 1 ? A : B;
+        const bool raw = l == 1 ? rawA : rawB;
+        r = finish(l == 1 ? 1 : 0); // the target's grids (first build: sized and filled here; rebuild: capacity verified)
+        if (!r && !raw)
+            r = finish(l == 1 ? 0 : 1);
+        if (r)
+            break;
+        cudaStreamWaitEvent(lane.stream, c->orderEvent, 0);
+        // queries need the other mesh's sorted centroids only (raw: nothing of the query's build); the target needs its grids
+        cudaStreamWaitEvent(lane.stream, target->ready, 0);
+        if (!raw)
+            cudaStreamWaitEvent(lane.stream, query->leafReady, 0);
         const ClassifyArgs &q = l == 1 ? qa : qb;
         if (q.end > q.begin && target->d.nT)
-            r = classify_launch(c, lane, target, q, l == 1 ? ja : jb);
+            r = classify_launch(c, lane, target, q, l == 1 ? ja : jb, 0, raw ? query : nullptr);
         else if (q.end > q.begin && !q.queryMesh->origFace) // empty target: nothing is inside it
             cudaMemsetAsync(q.inside, 0, q.queryMesh->nT, lane.stream); // (a multi-GPU selection writes its own faces only;
                                                                         //  the caller's array starts out cleared)
+        // host outputs: the flags follow their kernel at once (no host round trip in between); a job that turns out to
+        // need further launches (points left to the general kernel, third rays) sends them again when it is done
+        if (!r && host && (l == 1 ? host->insideA : host->insideB) && query->d.nT)
+            cudaMemcpyAsync(l == 1 ? host->insideA : host->insideB, q.inside, query->d.nT, cudaMemcpyDeviceToHost, lane.stream);
     }
+    if (!r)
+        r = finish(0);
+    if (!r)
+        r = finish(1);
     // broad + narrow phase on the context stream meanwhile
     int ri = r ? r : sb_intersect_range(A, B, aBegin, aEnd, flags, out);
+    c->deferVerify = false;
+    if (optimistic) {
+        // (the intersection has synchronised the context stream behind both builds: the counts are on the host)
+        if (mesh_verify_would_change(A) || mesh_verify_would_change(B)) {
+            c->optimisticRedone += 1;
+            for (int l = 1; l <= 2; ++l) {
+                ClassifyJob &job = l == 1 ? ja : jb;
+                cudaStreamSynchronize(c->lanes[l].stream);
+                if (job.scratch)
+                    cudaFreeAsync(job.scratch, c->lanes[l].stream);
+                if (job.firstScratch)
+                    cudaFreeAsync(job.firstScratch, c->lanes[l].stream);
+                job.scratch = job.firstScratch = nullptr;
+            }
+            if (*out) {
+                sb_isect_destroy(*out);
+                *out = nullptr;
+            }
+            // the careful way: the checks first (rebuilding what did not fit), then the same call again
+            int rv = mesh_finish(A);
+            if (!rv)
+                rv = mesh_finish(B);
+            if (rv)
+                return rv;
+            return front_end_core(A, B, aBegin, aEnd, bBegin, bEnd, flags, out, d_insideA, d_insideB, host);
+        }
+        int rv = mesh_verify(const_cast<sb_mesh *>(A), nullptr);
+        if (!rv)
+            rv = mesh_verify(const_cast<sb_mesh *>(B), nullptr);
+        if (rv && !r)
+            r = rv;
+    }
+    bool hitsSent = false;
+    if (!ri && host && host->hitAB && host->hitSeg && *out && (*out)->nHit && (*out)->nHit <= host->hitCap) {
+        cudaMemcpyAsync(host->hitAB, (*out)->hitAB, 8 * (*out)->nHit, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(host->hitSeg, (*out)->hitSeg, 48 * (*out)->nHit, cudaMemcpyDeviceToHost, c->stream);
+        hitsSent = true;
+    }
     c->lastRays = c->lastCands = 0;
     bool firstStats = true;
     if (ja.launched) {
@@ -2826,13 +3036,19 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
         firstStats = false;
         if (!r) r = rf;
     }
+    if (host && host->insideA && A->d.nT && !r && ja.launches > 1)
+        cudaMemcpyAsync(host->insideA, d_insideA, A->d.nT, cudaMemcpyDeviceToHost, c->lanes[1].stream);
     if (jb.launched) {
         int rf = classify_finish(c, c->lanes[2], A, qb, jb, !firstStats);
         firstStats = false;
         if (!r) r = rf;
     }
+    if (host && host->insideB && B->d.nT && !r && jb.launches > 1)
+        cudaMemcpyAsync(host->insideB, d_insideB, B->d.nT, cudaMemcpyDeviceToHost, c->lanes[2].stream);
     cudaStreamSynchronize(c->lanes[1].stream);
     cudaStreamSynchronize(c->lanes[2].stream);
+    if (hitsSent && cudaStreamSynchronize(c->stream) != cudaSuccess && !r)
+        r = fail(SB_ERR_CUDA, "front end: copying the hit list to the host failed");
     if (!r)
         r = ri;
     if (r && *out) {
@@ -2842,9 +3058,46 @@ int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t
     return r;
 }
 
+int sb_front_end_range(const sb_mesh *A, const sb_mesh *B, size_t aBegin, size_t aEnd, size_t bBegin, size_t bEnd,
+    unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
+{
+    return front_end_core(A, B, aBegin, aEnd, bBegin, bEnd, flags, out, d_insideA, d_insideB, nullptr);
+}
+
 int sb_front_end(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out, void *d_insideA, void *d_insideB)
 {
     return sb_front_end_range(A, B, 0, A ? A->d.nT : 0, 0, B ? B->d.nT : 0, flags, out, d_insideA, d_insideB);
+}
+
+int sb_front_end_host(const sb_mesh *A, const sb_mesh *B, unsigned flags, sb_isect **out, uint8_t *insideA, uint8_t *insideB,
+    uint32_t *hit_ab, double *hit_seg, size_t hit_capacity)
+{
+    if (!A || !B || !out || !insideA || !insideB)
+        return fail(SB_ERR_INVALID, "null argument");
+    if (A->ctx != B->ctx)
+        return fail(SB_ERR_INVALID, "meshes belong to different contexts");
+    sb_context *c = A->ctx;
+    DeviceGuard g(c);
+    // the per-face flags live in a buffer the context keeps (grow-only)
+    const size_t nA = A->d.nT, nB = B->d.nT, offB = align256(std::max<size_t>(nA, 1)), need = offB + std::max<size_t>(nB, 1);
+    if (need > c->feFlagsBytes) {
+        if (c->feFlags) {
+            SB_CUDA(cudaDeviceSynchronize());
+            SB_CUDA(cudaFree(c->feFlags));
+            c->feFlags = nullptr;
+            c->feFlagsBytes = 0;
+        }
+        SB_CUDA(cudaMalloc(&c->feFlags, need + need / 4));
+        c->feFlagsBytes = need + need / 4;
+    }
+    FrontEndHostOut h;
+    h.insideA = insideA;
+    h.insideB = insideB;
+    h.hitAB = hit_ab;
+    h.hitSeg = hit_seg;
+    h.hitCap = hit_ab && hit_seg ? hit_capacity : 0;
+    uint8_t *dA = static_cast<uint8_t *>(c->feFlags), *dB = dA + offB;
+    return front_end_core(A, B, 0, nA, 0, nB, flags, out, dA, dB, &h);
 }
 
 // ---- multi-GPU shards (sb_shard.cu) --------------------------------------------------------

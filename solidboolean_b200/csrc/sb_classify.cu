@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WarpStage &W = s_stage[threadIdx.x >> 5];
-    const uint32_t j = blockIdx.x * CT + threadIdx.x;
+    const uint32_t j = q.first + blockIdx.x * CT + threadIdx.x;
 
     d3 p = {0, 0, 0};
     uint32_t outIndex = 0, local = 0, job = 0;
@@ -503,7 +503,10 @@ __global__ void __launch_bounds__(CT, SB_CLS_MINB) classify_kernel(const __grid_
     if (active) {
         local = q.list ? __ldg(q.list + j) : j;
         const uint32_t idx = q.begin + local;
-        if (q.pts) {
+        if (q.rawTri) {
+            p = raw_face_centroid(q, idx);
+            outIndex = idx;
+        } else if (q.pts) {
             p = {q.pts[3 * (size_t)idx], q.pts[3 * (size_t)idx + 1], q.pts[3 * (size_t)idx + 2]};
             outIndex = idx;
         } else if (idx < q.nT) {
@@ -612,12 +615,18 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     q.ownMode = qm && qm->ownFilter ? (qm->ownClosed ? 2 : 1) : 0;
     q.ownLo = qm ? qm->ownLo : 0.0;
     q.ownHi = qm ? qm->ownHi : 0.0;
-    if (q.count == 0)
+    q.rawTri = a.rawFaces && qm ? qm->tri : nullptr;
+    q.rawXyz = a.rawFaces && qm ? qm->xyz : nullptr;
+    q.rawNV = qm ? qm->nV : 0;
+    q.first = a.list ? 0u : a.first;
+    if (q.count <= q.first)
         return cudaSuccess;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;
     T.refs = target.gridRefs;
+    T.refPairs = (target.gridRefCap + 8) / 2;
+    T.nT = target.nT;
     T.bigRefs = target.gridBigRefs;
     T.bigCap = target.gridBigCap;
     T.bigN0 = target.gridBigN[0];
@@ -641,7 +650,7 @@ cudaError_t sbk_classify(cudaStream_t s, const MeshDev &target, const ClassifyAr
     o.poolLimit = poolLimit ? (poolLimit < (uint32_t)POOL ? poolLimit : (uint32_t)POOL) : (uint32_t)POOL;
     if (trace)
         cudaMemsetAsync(trace, 0, 32 * (size_t)((q.count + CT - 1) / CT), s);
-    classify_kernel<<<(q.count + CT - 1) / CT, CT, 0, s>>>(q, T, o);
+    classify_kernel<<<(q.count - q.first + CT - 1) / CT, CT, 0, s>>>(q, T, o);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -53,6 +53,11 @@ struct Target {
     const double4 *vtx;
     const uint32_t *tri;
     const double4 *nrm4;       // per triangle: unit normal + packed vertex indices (sb_common.cuh)
+    // A front end enqueued BEFORE the host has checked that a rebuild's references fitted the lists sized for the old
+    // geometry (sb_capi.cu, optimistic enqueue) may walk lists whose tail was never written: reads stay inside the
+    // allocation (refPairs) and triangle numbers inside the mesh (nT); such a run's results are thrown away
+    uint32_t refPairs;         // readable 16-byte pairs behind refs
+    uint32_t nT;
 };
 
 struct Query {
@@ -67,7 +72,28 @@ struct Query {
     const uint32_t *origFace;  // multi-GPU selection (faces mode): query face -> the parent's triangle id (output index), or null
     int ownMode;               // ... and only the faces with centroid z in [ownLo, ownHi) (2: <= ownHi) are classified
     double ownLo, ownHi;
+    // raw faces mode (rawTri != null): the query faces in their ORIGINAL order straight from the uploaded arrays --
+    // the query mesh need not be built (a mesh whose bytes have only just arrived, sb_capi.cu front end): point j is
+    // face begin + j, j runs from `first` (the launch covers one upload chunk: faces [first, count))
+    const uint32_t *rawTri;
+    const double *rawXyz;
+    uint32_t rawNV;
+    uint32_t first;
 };
+
+// centroid of face f of a raw query, ((v0 + v1) + v2) / 3.0 (src/solidboolean.cpp:497-499) -- the same operations on
+// the same doubles as the leaf kernel of sb_build.cu, which reads the padded copies
+__device__ __forceinline__ d3 raw_face_centroid(const Query &q, uint32_t f)
+{
+    uint32_t i0 = __ldg(q.rawTri + 3 * (size_t)f), i1 = __ldg(q.rawTri + 3 * (size_t)f + 1), i2 = __ldg(q.rawTri + 3 * (size_t)f + 2);
+    if (i0 >= q.rawNV || i1 >= q.rawNV || i2 >= q.rawNV) // (the build reports it)
+        i0 = i1 = i2 = 0;
+    const double *x = q.rawXyz;
+    const d3 a = {__ldg(x + 3 * (size_t)i0), __ldg(x + 3 * (size_t)i0 + 1), __ldg(x + 3 * (size_t)i0 + 2)};
+    const d3 b = {__ldg(x + 3 * (size_t)i1), __ldg(x + 3 * (size_t)i1 + 1), __ldg(x + 3 * (size_t)i1 + 2)};
+    const d3 c = {__ldg(x + 3 * (size_t)i2), __ldg(x + 3 * (size_t)i2 + 1), __ldg(x + 3 * (size_t)i2 + 2)};
+    return {xdiv(xadd(xadd(a.x, b.x), c.x), 3.0), xdiv(xadd(xadd(a.y, b.y), c.y), 3.0), xdiv(xadd(xadd(a.z, b.z), c.z), 3.0)};
+}
 
 struct Out {
     uint8_t *inside;           // indexed by point index / original triangle id
@@ -221,6 +247,12 @@ template <bool FINITE = false>
 __device__ __forceinline__ bool eval_entry(const Target &T, const d3 &p, int axis, uint32_t f, long long &k0, long long &k1,
     long long &k2, bool &isCand)
 {
+#if SB_CLS_GUARDS
+    if (f >= T.nT) { // (only in a run whose lists overflowed, see Target)
+        isCand = false;
+        return false;
+    }
+#endif
     // first round trip: the triangle's record = normal + packed vertex indices (one 256-bit gather) ...
     const double4 rec = ldg256(T.nrm4 + f);
     uint32_t i0, i1, i2;

@@ -29,6 +29,7 @@
 // host launches over that list afterwards; they are rare (C3: none).
 // Majority vote, lazy third ray and the "third grid missing" list work as in sb_classify.cu.
 #include "sb_classify.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -186,7 +187,11 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
                 rr[k] = gi < wn ? (uint32_t)W.own[gi] - 1u : 64u;
                 qq[k] = make_uint4(0u, 0u, 0u, 0u);
                 if (gi < wn)
+#if SB_CLS_GUARDS
+                    qq[k] = __ldg(pairs + min(W.rayBase[rr[k]] + w0 + gi, T.refPairs - 1u));
+#else
                     qq[k] = __ldg(pairs + (W.rayBase[rr[k]] + w0 + gi));
+#endif
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -429,14 +434,17 @@ __global__ void __launch_bounds__(CT2, SB_CLS2_MINB) classify2_kernel(const __gr
     __syncthreads();
     const int lane = threadIdx.x & 31;
     Stage2 &W = s_stage[threadIdx.x >> 5];
-    const uint32_t j = blockIdx.x * CT2 + threadIdx.x;
+    const uint32_t j = q.first + blockIdx.x * CT2 + threadIdx.x;
 
     d3 p = {0, 0, 0};
     uint32_t outIndex = 0, job = 0;
     bool active = j < q.count;
     if (active) {
         const uint32_t idx = q.begin + j;
-        if (q.pts) {
+        if (q.rawTri) {
+            p = raw_face_centroid(q, idx);
+            outIndex = idx;
+        } else if (q.pts) {
             p = {q.pts[3 * (size_t)idx], q.pts[3 * (size_t)idx + 1], q.pts[3 * (size_t)idx + 2]};
             outIndex = idx;
         } else if (idx < q.nT) {
@@ -544,10 +552,18 @@ cudaError_t sbk_classify2(cudaStream_t s, const MeshDev &target, const ClassifyA
     q.ownMode = qm && qm->ownFilter ? (qm->ownClosed ? 2 : 1) : 0;
     q.ownLo = qm ? qm->ownLo : 0.0;
     q.ownHi = qm ? qm->ownHi : 0.0;
+    q.rawTri = a.rawFaces && qm ? qm->tri : nullptr;
+    q.rawXyz = a.rawFaces && qm ? qm->xyz : nullptr;
+    q.rawNV = qm ? qm->nV : 0;
+    q.first = a.first;
+    if (q.count <= q.first)
+        return cudaSuccess;
     Target T;
     T.gp = target.gridParams;
     T.E = target.gridE;
     T.refs = target.gridRefs;
+    T.refPairs = (target.gridRefCap + 8) / 2;
+    T.nT = target.nT;
     T.bigRefs = target.gridBigRefs;
     T.bigCap = target.gridBigCap;
     T.bigN0 = T.bigN1 = T.bigN2 = 0;
@@ -563,7 +579,7 @@ cudaError_t sbk_classify2(cudaStream_t s, const MeshDev &target, const ClassifyA
     o.undecidedList = a.undecidedList;
     o.legacyCount = legacyCount;
     o.legacyList = legacyList;
-    classify2_kernel<<<(q.count + CT2 - 1) / CT2, CT2, 0, s>>>(q, T, o);
+    classify2_kernel<<<(q.count - q.first + CT2 - 1) / CT2, CT2, 0, s>>>(q, T, o);
     lc.kernels += 1;
     return cudaGetLastError();
 }

@@ -6,6 +6,12 @@
 #include <stddef.h>
 #include "sb_common.cuh"
 
+// The balanced classifier keeps its reads inside the allocations whatever the cell lists hold (what the optimistic
+// enqueue of sb_capi.cu's front end relies on); 0 = without those two checks (dev: their cost), no optimistic enqueue.
+#ifndef SB_CLS_GUARDS
+#define SB_CLS_GUARDS 1
+#endif
+
 // Cluster size K of the LBVH (leaves are K Morton-consecutive triangles).
 #ifndef SB_CLUSTER
 #define SB_CLUSTER 8
@@ -185,6 +191,10 @@ struct ClassifyArgs {
     const uint32_t *list = nullptr;
     uint32_t listCount = 0;
     bool thirdAxisOnly = false;
+    // raw faces: the query mesh's faces in ORIGINAL order from its uploaded arrays (it need not be built); the launch
+    // covers faces [first, end) with begin = 0 -- one launch per upload chunk, lists and counters shared
+    bool rawFaces = false;
+    uint32_t first = 0;
 };
 // One launch classifies all points (sb_classify.cu).  Lazy vote when only `inside` is
 // wanted: axes 0 and 1 for every point, axis 2 where the two disagree

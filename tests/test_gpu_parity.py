@@ -804,3 +804,144 @@ def test_parked_mesh_is_revived_with_new_geometry_and_topology(oracle):
         assert np.array_equal(ma.normals(), oracle.normals(*a))
         x.close(); ma.close(); mb.close()       # parked; the next round's meshes of the same counts revive them
     c.close()
+
+
+@pytest.mark.parametrize("last", ["b", "a"])
+@pytest.mark.parametrize("pool_limit", [None, "8"])
+def test_streamed_classification_of_a_just_uploaded_mesh(oracle, monkeypatch, last, pool_limit):
+    """sb_mesh_upload / sb_mesh_update send the index triples in chunks; the first sb_front_end after it classifies
+    the faces of the mesh that arrived LAST in their original order, chunk by chunk, straight from the uploaded
+    arrays (not from that mesh's build).  Flags must equal the oracle's and the ordinary (Morton-order) path's --
+    with either mesh last, through the general kernel too (SB_CLASSIFY_POOL_LIMIT), with an OPEN target whose
+    first two rays disagree (undecided list + third grid on demand) and after sb_mesh_update of new coordinates."""
+    import torch
+    monkeypatch.setenv("SB_GRID3_EAGER_BELOW", "0")
+    monkeypatch.setenv("SB_STREAM_CLASSIFY", "1")   # (off by default: no gain at C3, the GPU is busy either way)
+    if pool_limit:
+        monkeypatch.setenv("SB_CLASSIFY_POOL_LIMIT", pool_limit)
+    ctx = sb.Context(0)
+    a = meshgen.icosphere(7)                                            # 327,680 faces: four upload chunks
+    b = meshgen.torus(256, 128, center=(0.013, 0.007, 0.011))          # 65,536 faces: two
+    # an open target: a band of the sphere's faces removed -> x and y rays of some points disagree
+    cen = oracle.centroids(*a)
+    a_open = (a[0], np.ascontiguousarray(a[1][np.abs(cen[:, 2] - 0.31) > 0.05]))
+    for A, B in ((a, b), (a_open, b)):
+        keep = [np.ascontiguousarray(A[0], np.float64), np.ascontiguousarray(A[1], np.uint32),
+                np.ascontiguousarray(B[0], np.float64), np.ascontiguousarray(B[1], np.uint32)]
+        mk = lambda i: sb.Mesh.from_pointers(ctx, keep[2 * i].ctypes.data, len(keep[2 * i]), keep[2 * i + 1].ctypes.data,
+                                             len(keep[2 * i + 1]), build=False, keep=keep)
+        if last == "b":
+            ma = mk(0); mb = mk(1)
+        else:
+            mb = mk(1); ma = mk(0)
+        ma.build(); mb.build()
+        da = torch.full((len(A[1]),), 7, dtype=torch.uint8, device="cuda")
+        db = torch.full((len(B[1]),), 7, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+        oa, _, _ = oracle.classify(B, oracle.centroids(*A))
+        ob, _, _ = oracle.classify(A, oracle.centroids(*B))
+        assert np.array_equal(da.cpu().numpy(), oa) and np.array_equal(db.cpu().numpy(), ob)
+        rays1 = ctx.classify_stats()
+        ref_hits = x.hits()
+        x.close()
+        # the same meshes again, nothing uploaded in between: the ordinary path (Morton order of both builds)
+        da.fill_(7); db.fill_(7); torch.cuda.synchronize()   # (torch's stream is not ordered with the library's)
+        x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+        assert np.array_equal(da.cpu().numpy(), oa) and np.array_equal(db.cpu().numpy(), ob)
+        assert ctx.classify_stats() == rays1 and all(u.tobytes() == v.tobytes() for u, v in zip(x.hits(), ref_hits))
+        x.close()
+        # new coordinates into the same meshes (sb_mesh_update), both orders of arrival
+        va = np.ascontiguousarray(A[0] * np.array([1.0, 0.9, 1.1])); vb = np.ascontiguousarray(B[0] * 1.05)
+        for m, v, t in ((ma, va, keep[1]), (mb, vb, keep[3])) if last == "b" else ((mb, vb, keep[3]), (ma, va, keep[1])):
+            m.update(v.ctypes.data, t.ctypes.data)
+        ma.build(); mb.build()
+        da.fill_(7); db.fill_(7); torch.cuda.synchronize()
+        x = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+        oa, _, _ = oracle.classify((vb, B[1]), oracle.centroids(va, A[1]))
+        ob, _, _ = oracle.classify((va, A[1]), oracle.centroids(vb, B[1]))
+        assert np.array_equal(da.cpu().numpy(), oa) and np.array_equal(db.cpu().numpy(), ob)
+        x.close(); ma.close(); mb.close()
+    ctx.close()
+
+
+def test_front_end_with_host_outputs(ctx, oracle):
+    """sb_front_end_host = sb_front_end + the copies to the host, each enqueued behind the stream that produced it:
+    same flags, same hit list; a landing buffer that is too small for the hit list is left alone."""
+    import torch
+    a, b = meshgen.icosphere(5), meshgen.torus(96, 48, center=(0.013, 0.007, 0.011))
+    ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+    da = torch.zeros(len(a[1]), dtype=torch.uint8, device="cuda"); db = torch.zeros(len(b[1]), dtype=torch.uint8, device="cuda")
+    ref = sb.Isect.front_end(ma, mb, da.data_ptr(), db.data_ptr())
+    rab, rseg = ref.hits()
+    assert len(rab) > 0
+    for pinned in (True, False):
+        ha = torch.full((len(a[1]),), 9, dtype=torch.uint8); hb = torch.full((len(b[1]),), 9, dtype=torch.uint8)
+        cap = len(rab) + 5
+        hab = torch.full((2 * cap,), -1, dtype=torch.int32); hseg = torch.full((6 * cap,), -1.0, dtype=torch.float64)
+        if pinned:
+            ha, hb, hab, hseg = ha.pin_memory(), hb.pin_memory(), hab.pin_memory(), hseg.pin_memory()
+        x = sb.Isect.front_end_host(ma, mb, ha.data_ptr(), hb.data_ptr(), hab.data_ptr(), hseg.data_ptr(), cap)
+        assert (x.num_candidates, x.num_hits) == (ref.num_candidates, ref.num_hits)
+        assert np.array_equal(ha.numpy(), da.cpu().numpy()) and np.array_equal(hb.numpy(), db.cpu().numpy())
+        n = x.num_hits
+        assert np.array_equal(hab.numpy()[:2 * n].reshape(-1, 2).astype(np.uint32), rab)
+        assert hseg.numpy()[:6 * n].tobytes() == rseg.tobytes() and int(hab[2 * n]) == -1
+        x.close()
+        # too small a landing buffer: untouched, sb_isect_hits still delivers
+        hab.fill_(-1)
+        x = sb.Isect.front_end_host(ma, mb, ha.data_ptr(), hb.data_ptr(), hab.data_ptr(), hseg.data_ptr(), len(rab) - 1)
+        assert int(hab[0]) == -1 and np.array_equal(x.hits()[0], rab)
+        x.close()
+        # flags only
+        ha.fill_(9)
+        x = sb.Isect.front_end_host(ma, mb, ha.data_ptr(), hb.data_ptr())
+        assert np.array_equal(ha.numpy(), da.cpu().numpy())
+        x.close()
+    oa, _, _ = oracle.classify(b, oracle.centroids(*a))
+    assert np.array_equal(da.cpu().numpy(), oa)
+    ref.close(); ma.close(); mb.close()
+
+
+@pytest.mark.parametrize("optimistic", ["1", "0"])
+def test_front_end_right_after_update_is_enqueued_before_the_counts_are_known(oracle, monkeypatch, optimistic):
+    """sb_mesh_update + sb_mesh_build + sb_front_end_host back to back: the front end is enqueued behind the rebuilds
+    without waiting for their reference counts (SB_OPTIMISTIC, default on) and checks them afterwards.  Frames whose
+    references still fit, a frame that needs MORE references than the lists hold and one where big-list triangles
+    appear (both: the run is repeated after a proper rebuild) -- every frame must equal the oracle."""
+    import torch
+    monkeypatch.setenv("SB_OPTIMISTIC", optimistic)
+    ctx = sb.Context(0)
+    a0, b0 = meshgen.icosphere(5), meshgen.torus(96, 48, center=(0.013, 0.007, 0.011))
+    ma, mb = ctx.mesh(*a0), ctx.mesh(*b0)
+    rng = np.random.default_rng(11)
+    ha = torch.zeros(len(a0[1]), dtype=torch.uint8).pin_memory(); hb = torch.zeros(len(b0[1]), dtype=torch.uint8).pin_memory()
+    cap = 1 << 16
+    hab = torch.zeros(2 * cap, dtype=torch.int32).pin_memory(); hseg = torch.zeros(6 * cap, dtype=torch.float64).pin_memory()
+
+    def frames():
+        yield a0[0] * 1.01, b0[0]                                              # fits
+        yield a0[0] * np.array([1.0, 1.0, 0.05]), b0[0]                       # squashed: anisotropic boxes
+        yield a0[0] + rng.normal(0, 0.02, a0[0].shape), b0[0] * 1.1          # noisy: many more references than the lists hold
+        va = a0[0].copy(); va[::97] *= 40.0                                   # a few far vertices: huge triangles (big lists appear)
+        yield va, b0[0]
+        yield a0[0], b0[0]                                                    # and back (big lists vanish)
+        yield a0[0] * 0.99, b0[0] * 1.01                                      # fits again
+    for va, vb in frames():
+        xa = np.ascontiguousarray(va, np.float64); xb = np.ascontiguousarray(vb, np.float64)
+        ma.update(xa.ctypes.data, 0); mb.update(xb.ctypes.data, 0)
+        ma.build(); mb.build()
+        ha.fill_(9); hb.fill_(9)
+        x = sb.Isect.front_end_host(ma, mb, ha.data_ptr(), hb.data_ptr(), hab.data_ptr(), hseg.data_ptr(), cap)
+        a, b = (xa, a0[1]), (xb, b0[1])
+        ref = oracle.candidate_pairs(a, b)
+        ret, cop, hit, seg = oracle.predicate_pairs(a, b, ref)
+        n = x.num_hits
+        assert x.num_candidates == len(ref) and n == int(hit.sum()) and n <= cap
+        assert np.array_equal(hab.numpy()[:2 * n].reshape(-1, 2).astype(np.uint32), ref[hit.astype(bool)])
+        assert hseg.numpy()[:6 * n].tobytes() == seg[hit.astype(bool)].tobytes()
+        oa, _, _ = oracle.classify(b, oracle.centroids(*a))
+        ob, _, _ = oracle.classify(a, oracle.centroids(*b))
+        assert np.array_equal(ha.numpy(), oa) and np.array_equal(hb.numpy(), ob)
+        x.close()
+    ma.close(); mb.close(); ctx.close()
