@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import contextlib
 import os
 import subprocess
 import sys
@@ -580,7 +581,9 @@ def run_ours(args):
                                        host_hits["seg"].data_ptr(), host_hits["cap"])
 
     def e2e_step():
-        with torch.cuda.stream(ext):
+        # (one GPU: the step makes no torch call -- everything goes through the C ABI -- so torch's current stream is left
+        #  alone: entering / leaving torch.cuda.stream() costs ~40 us of host time per step)
+        with (torch.cuda.stream(ext) if world > 1 else contextlib.nullcontext()):
             if world > 1:
                 mine = geo_dev[rank * geo_slice:(rank + 1) * geo_slice]
                 mine.copy_(geo_host[rank * geo_slice:(rank + 1) * geo_slice], non_blocking=True)   # H2D of this rank's share
@@ -1002,14 +1005,18 @@ def run_c5(args):
             with torch.cuda.stream(ext):
                 xa, xb = make(0, False), make(1, False)
                 xa.build(); xb.build()
-                x = sb.Isect.front_end(xa, xb, flagsA.data_ptr(), flagsB.data_ptr())
-                out_a.copy_(flagsA, non_blocking=True)
-                out_b.copy_(flagsB, non_blocking=True)
-                if host_hits.get("cap", -1) < x.num_hits:
+                if "cap" not in host_hits:
+                    cap = max(1024, int(H) * 3 // 2 + 64)
+                    host_hits.update(cap=cap, ab=torch.zeros(2 * cap, dtype=torch.int32).pin_memory(),
+                                     seg=torch.zeros(6 * cap, dtype=torch.float64).pin_memory())
+                # flags of both batches and the hit list land in pinned host memory (sb_front_end_host)
+                x = sb.Isect.front_end_host(xa, xb, out_a.data_ptr(), out_b.data_ptr(), host_hits["ab"].data_ptr(),
+                                            host_hits["seg"].data_ptr(), host_hits["cap"])
+                if host_hits["cap"] < x.num_hits:
                     cap = x.num_hits * 3 // 2 + 64
                     host_hits.update(cap=cap, ab=torch.zeros(2 * cap, dtype=torch.int32).pin_memory(),
                                      seg=torch.zeros(6 * cap, dtype=torch.float64).pin_memory())
-                sb._check(x.lib.sb_isect_hits(x.h, host_hits["ab"].data_ptr(), host_hits["seg"].data_ptr()))
+                    sb._check(x.lib.sb_isect_hits(x.h, host_hits["ab"].data_ptr(), host_hits["seg"].data_ptr()))
                 last["ranges"] = x.job_ranges()
                 res = (x.num_candidates, x.num_hits)
                 x.close(); xa.close(); xb.close()

@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t quant10(double c, double lo, double inv)
 }
 
 #ifndef SB_TRIPREP_MINB
-#define SB_TRIPREP_MINB 1
+#define SB_TRIPREP_MINB 4 // 64 registers: four CTAs per SM (74 without the bound: three)
 #endif
 #ifndef SB_TRIPREP_HIST
 #define SB_TRIPREP_HIST 1 // the kernel also counts the radix digits of the Morton keys it writes: no separate histogram pass over them
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const
 
 // ---- K1b --------------------------------------------------------------------
 #ifndef SB_LEAF_MINB
-#define SB_LEAF_MINB 1
+#define SB_LEAF_MINB 4 // 64 registers: four CTAs per SM (the depth slabs took the kernel to 66 and one CTA less: 96 -> 109 us at C3)
 #endif
 __global__ void __launch_bounds__(256, SB_LEAF_MINB) leaf_gather_kernel(const uint32_t *__restrict__ sortedTri,
     const uint32_t *__restrict__ sortedKey, const double4 *__restrict__ vtx, const uint32_t *__restrict__ tri,
