@@ -443,7 +443,8 @@ def run_ours(args):
     shard = sb.Shard(ma, mb, rank, world) if world > 1 else None
 
     def resident_step():
-        with torch.cuda.stream(ext):
+        # (one GPU: no torch call inside the step, so torch's current stream is left alone -- see e2e_step)
+        with (torch.cuda.stream(ext) if world > 1 else contextlib.nullcontext()):
             while True:
                 if world > 1:
                     # sb_shard_front_end: this rank's slab of faces -- selection, build of the selected triangles
