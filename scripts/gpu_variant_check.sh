@@ -1,8 +1,8 @@
-# where do the resident bench step's extra microseconds come from?  stage times with the L2 flushed between steps, per variant
+# compile-time variants (scripts/variants.py) against the product build: stage times at C3
 V=solidboolean_b200/lib/variants
-for v in "default 2" "default 0" "nohist 2" "noguard 2"; do set -- $v
-  if [ $1 = default ]; then L=""; else L=$PWD/$V/libsb_$1.so; fi
-  echo "== $1 slabs $2"
-  SB_LIB_PATH=$L SB_GRID_SLABS=$2 python scripts/stage_times.py c3 8 --flush 2>&1 | tail -4 | head -2 | cut -c1-200
-  SB_LIB_PATH=$L SB_GRID_SLABS=$2 python scripts/stage_times.py c3 8 2>&1 | tail -3 | head -1 | cut -c1-200
+for v in default minb5 minb4 r256x16 default; do
+  if [ $v = default ]; then L=""; else L=$PWD/$V/libsb_$v.so; fi
+  echo "== $v"
+  SB_LIB_PATH=$L python scripts/stage_times.py c3 8 2>&1 | tail -4 | head -2 | cut -c1-200
 done
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "update or host_outputs or bundled or cell_borders or c3_every" 2>&1 | tail -3

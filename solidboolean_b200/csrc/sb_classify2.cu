@@ -97,6 +97,11 @@ __device__ __forceinline__ bool setup_slot(const GridParams &g, const Target &T,
     const CellRay cq = ray_in_cell(g, AXIS, r, r.cu0, r.cv0);
     uint32_t a, b; // the sub-lists of the depth slabs the ray can reach (sb_gridq.cuh)
     grid_ray_range(g, T.E, AXIS, r.cu0, r.cv0, r.aA, a, b);
+#if SB_CLS_GUARDS
+    // (a run enqueued before the host knew whether the rebuild fitted its lists, see Target: the walk stays inside the allocation)
+    b = min(b, 2u * T.refPairs);
+    a = min(a, b);
+#endif
     rx = cq.x;
     ry = cq.y;
     ra = a;
@@ -187,11 +192,7 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
                 rr[k] = gi < wn ? (uint32_t)W.own[gi] - 1u : 64u;
                 qq[k] = make_uint4(0u, 0u, 0u, 0u);
                 if (gi < wn)
-#if SB_CLS_GUARDS
-                    qq[k] = __ldg(pairs + min(W.rayBase[rr[k]] + w0 + gi, T.refPairs - 1u));
-#else
                     qq[k] = __ldg(pairs + (W.rayBase[rr[k]] + w0 + gi));
-#endif
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
