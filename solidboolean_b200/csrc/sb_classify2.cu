@@ -51,6 +51,20 @@ constexpr int WINP = 256;             // pairs per window (one owner byte each)
 constexpr int POOL2 = 2 * WINP + 32;  // every reference of a window may match, plus the held-back tail
 constexpr int KL = 32;                // distinct keys kept for a ray that spans several chunks
 
+#ifndef SB_CLS2_PREFETCH
+#define SB_CLS2_PREFETCH 0 // 1 / 2: a matched triangle's record is prefetched into L1 / L2 when the walk finds it
+#endif
+__device__ __forceinline__ void prefetch_record(const Target &T, uint32_t id)
+{
+#if SB_CLS2_PREFETCH == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(T.nrm4 + id));
+#elif SB_CLS2_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(T.nrm4 + id));
+#else
+    (void)T; (void)id;
+#endif
+}
+
 struct __align__(16) Stage2 {
     uint32_t tri[POOL2];    // triangle ids of the matches, ray by ray
     long long key[32][3];   // PositionKeys of the current chunk's hits
@@ -210,13 +224,17 @@ __device__ __forceinline__ uint32_t trace_round2(const GridParams &g, const Targ
                 const uint32_t b0 = __ballot_sync(SB_FULL, m0), b1 = __ballot_sync(SB_FULL, m1);
                 uint32_t at = pos + __popc(b0 & ltmask) + __popc(b1 & ltmask);
                 if (m0) {
-                    W.tri[at] = cell_ref_id(make_uint2(q.x, q.y));
+                    const uint32_t id = cell_ref_id(make_uint2(q.x, q.y));
+                    W.tri[at] = id;
                     W.owner[at] = (uint8_t)r;
+                    prefetch_record(T, id);
                     ++at;
                 }
                 if (m1) {
-                    W.tri[at] = cell_ref_id(make_uint2(q.z, q.w));
+                    const uint32_t id = cell_ref_id(make_uint2(q.z, q.w));
+                    W.tri[at] = id;
                     W.owner[at] = (uint8_t)r;
+                    prefetch_record(T, id);
                 }
                 pos += __popc(b0) + __popc(b1);
             }
