@@ -2951,6 +2951,15 @@ static int front_end_core(const sb_mesh *A, const sb_mesh *B, size_t aBegin, siz
     qb.rawFaces = rawB;
     ClassifyJob ja, jb;
     int r = SB_OK;
+    auto is_pinned = [](const void *p) {
+        cudaPointerAttributes at;
+        if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool earlyA = host && is_pinned(host->insideA), earlyB = host && is_pinned(host->insideB);
     bool finished[2] = {false, false}; // mesh_finish done for A / B
     auto finish = [&](int which) {
         if (finished[which])
@@ -2982,7 +2991,8 @@ static int front_end_core(const sb_mesh *A, const sb_mesh *B, size_t aBegin, siz
                                                                         //  the caller's array starts out cleared)
         // host outputs: the flags follow their kernel at once (no host round trip in between); a job that turns out to
         // need further launches (points left to the general kernel, third rays) sends them again when it is done
-        if (!r && host && (l == 1 ? host->insideA : host->insideB) && query->d.nT)
+        // (pinned host memory only: a copy to pageable memory would block this thread until the kernel is done)
+        if (!r && host && (l == 1 ? host->insideA : host->insideB) && query->d.nT && (l == 1 ? earlyA : earlyB))
             cudaMemcpyAsync(l == 1 ? host->insideA : host->insideB, q.inside, query->d.nT, cudaMemcpyDeviceToHost, lane.stream);
     }
     if (!r)
@@ -3036,14 +3046,14 @@ static int front_end_core(const sb_mesh *A, const sb_mesh *B, size_t aBegin, siz
         firstStats = false;
         if (!r) r = rf;
     }
-    if (host && host->insideA && A->d.nT && !r && ja.launches > 1)
+    if (host && host->insideA && A->d.nT && !r && (ja.launches > 1 || !earlyA))
         cudaMemcpyAsync(host->insideA, d_insideA, A->d.nT, cudaMemcpyDeviceToHost, c->lanes[1].stream);
     if (jb.launched) {
         int rf = classify_finish(c, c->lanes[2], A, qb, jb, !firstStats);
         firstStats = false;
         if (!r) r = rf;
     }
-    if (host && host->insideB && B->d.nT && !r && jb.launches > 1)
+    if (host && host->insideB && B->d.nT && !r && (jb.launches > 1 || !earlyB))
         cudaMemcpyAsync(host->insideB, d_insideB, B->d.nT, cudaMemcpyDeviceToHost, c->lanes[2].stream);
     cudaStreamSynchronize(c->lanes[1].stream);
     cudaStreamSynchronize(c->lanes[2].stream);
