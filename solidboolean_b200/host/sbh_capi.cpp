@@ -3,7 +3,10 @@
 #include <cstdint>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <sstream>
+#include <streambuf>
+#include <string>
 #include <vector>
 #include "solidboolean.h"
 
@@ -20,6 +23,70 @@ struct Job {
     double stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
     ~Job() { delete op; }
 };
+
+// The reference-style messages (std::cout) are kept for the caller.  Several jobs may run at once (the classes allow it:
+// tests/test_host_cpp.py::test_concurrent_booleans_from_several_threads_gpu), so std::cout is redirected ONCE while any job
+// is active -- into one sink whose writes are locked -- and handed back by the last job to leave.  (A per-job
+// rdbuf swap handed a finished job's dead buffer back to std::cout when two jobs overlapped: a crash at process exit.)
+class LockedSink : public std::streambuf
+{
+public:
+    size_t size()
+    {
+        std::lock_guard<std::mutex> l(m_mu);
+        return m_text.size();
+    }
+    std::string since(size_t from)
+    {
+        std::lock_guard<std::mutex> l(m_mu);
+        return from < m_text.size() ? m_text.substr(from) : std::string();
+    }
+protected:
+    int_type overflow(int_type ch) override
+    {
+        if (ch != traits_type::eof()) {
+            std::lock_guard<std::mutex> l(m_mu);
+            m_text.push_back((char)ch);
+        }
+        return ch;
+    }
+    std::streamsize xsputn(const char *s, std::streamsize n) override
+    {
+        std::lock_guard<std::mutex> l(m_mu);
+        m_text.append(s, (size_t)n);
+        return n;
+    }
+private:
+    std::mutex m_mu;
+    std::string m_text;
+};
+
+std::mutex g_redirectMu;
+int g_activeJobs = 0;
+LockedSink *g_sink = nullptr;
+std::streambuf *g_coutBuf = nullptr;
+
+size_t redirect_enter()
+{
+    std::lock_guard<std::mutex> l(g_redirectMu);
+    if (g_activeJobs++ == 0) {
+        g_sink = new LockedSink;
+        g_coutBuf = std::cout.rdbuf(g_sink);
+    }
+    return g_sink->size();
+}
+
+std::string redirect_leave(size_t from)
+{
+    std::lock_guard<std::mutex> l(g_redirectMu);
+    std::string text = g_sink->since(from);
+    if (--g_activeJobs == 0) {
+        std::cout.rdbuf(g_coutBuf);
+        delete g_sink;
+        g_sink = nullptr;
+    }
+    return text;
+}
 
 void fill(std::vector<Vector3> &v, std::vector<std::vector<size_t>> &t, const double *xyz, size_t nV, const uint32_t *tri, size_t nT)
 {
@@ -40,8 +107,7 @@ void *sbh_boolean(const double *xyzA, size_t nVA, const uint32_t *triA, size_t n
     Job *j = new Job;
     fill(j->va, j->ta, xyzA, nVA, triA, nTA);
     fill(j->vb, j->tb, xyzB, nVB, triB, nTB);
-    std::ostringstream sink;
-    std::streambuf *old = std::cout.rdbuf(sink.rdbuf()); // keep the reference-style messages for the caller
+    const size_t logFrom = redirect_enter(); // keep the reference-style messages for the caller
     j->a.setVertices(&j->va);
     j->a.setTriangles(&j->ta);
     j->a.prepare();
@@ -55,8 +121,7 @@ void *sbh_boolean(const double *xyzA, size_t nVA, const uint32_t *triA, size_t n
         j->op->fetchDiff(j->result[1]);
         j->op->fetchIntersect(j->result[2]);
     }
-    std::cout.rdbuf(old);
-    j->log = sink.str();
+    j->log = redirect_leave(logFrom);
     auto ms = [](SolidBoolean::TimePoint a, SolidBoolean::TimePoint b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     SolidBoolean *s = j->op;
     j->stageMs[0] = ms(s->benchBegin_searchPotentialIntersectedPairs, s->benchEnd_searchPotentialIntersectedPairs);

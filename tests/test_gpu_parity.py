@@ -806,6 +806,7 @@ def test_parked_mesh_is_revived_with_new_geometry_and_topology(oracle):
     c.close()
 
 
+@pytest.mark.slow
 @pytest.mark.parametrize("last", ["b", "a"])
 @pytest.mark.parametrize("pool_limit", [None, "8"])
 def test_streamed_classification_of_a_just_uploaded_mesh(oracle, monkeypatch, last, pool_limit):
