@@ -25,6 +25,8 @@ if os.environ.get("E2E_SAMPLER"):
 for it in range(steps + 3):
     flush.fill_(it & 0xff); torch.cuda.synchronize()
     spans = os.environ.get("E2E_SPANS") and it == steps + 2
+    if os.environ.get("E2E_SPANS") == "all" and not spans:   # timing on in every step (the last one prints)
+        ctx.enable_timing(True); ctx.reset_timing()
     if spans:   # last step: the stage spans (ms since the reset) on stderr, host time stamps of the calls below
         ctx.enable_timing(True); ctx.reset_timing(); os.environ["SB_DEBUG_SPANS"] = "1"
     t0 = time.perf_counter()

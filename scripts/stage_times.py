@@ -13,7 +13,7 @@ a, b = {"c2": meshgen.config_c2, "c3": meshgen.config_c3, "c4": meshgen.config_c
 print("gen %.2fs  A %d tris  B %d tris" % (time.time() - t0, len(a[1]), len(b[1])), flush=True)
 import torch
 ctx = sb.Context(0)
-ctx.enable_timing(True)
+ctx.enable_timing("--no-timing" not in sys.argv)   # --no-timing: no stage events on the streams (wall time only)
 ma = ctx.mesh(*a, build=False)
 mb = ctx.mesh(*b, build=False)
 da = torch.zeros(len(a[1]), dtype=torch.uint8, device="cuda")

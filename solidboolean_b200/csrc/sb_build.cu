@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const
     uint32_t nT, uint32_t nV, const unsigned long long *__restrict__ bounds, double4 *__restrict__ nrm4,
     uint32_t *__restrict__ mkey, uint32_t *__restrict__ order, int *__restrict__ err,
     unsigned long long *__restrict__ extentSum, const uint16_t *__restrict__ triJob,
-    uint32_t *__restrict__ hist /* [passes][256] of the sort to come, or null */, uint32_t *__restrict__ histTicket, int beginBit, int passes)
+    uint32_t *__restrict__ hist /* [passes][256] of the sort to come, or null */, uint32_t *__restrict__ histTicket /* null: one of several
+    launches over ranges of the triangles, the histogram is finished by sbradix::hist_scan_kernel */, int beginBit, int passes, uint32_t first)
 {
     __shared__ uint32_t s_hist[4 * 256];
     if (hist) {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256, SB_TRIPREP_MINB) tri_prepare_kernel(const
     const double blx = dkey_inv(bounds[0]), bly = dkey_inv(bounds[1]), blz = dkey_inv(bounds[2]);
     const double ex = dkey_inv(bounds[3]) - blx, ey = dkey_inv(bounds[4]) - bly, ez = dkey_inv(bounds[5]) - blz;
     const double ix = ex > 0 ? 1.0 / ex : 0.0, iy = ey > 0 ? 1.0 / ey : 0.0, iz = ez > 0 ? 1.0 / ez : 0.0;
-    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < nT; i += gridDim.x * 256) {
+    for (uint32_t i = first + blockIdx.x * 256 + threadIdx.x; i < nT; i += gridDim.x * 256) { // (nT: end of this launch's range)
     uint32_t i0 = tri[3 * (size_t)i], i1 = tri[3 * (size_t)i + 1], i2 = tri[3 * (size_t)i + 2];
     if (i0 >= nV || i1 >= nV || i2 >= nV) { // reported as SB_ERR_INVALID by the host
         *err = 1;
@@ -432,35 +433,97 @@ cudaError_t sbk_bounds_pad(cudaStream_t s, MeshDev &m, int smCount, LaunchCounte
     return cudaGetLastError();
 }
 
-cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc)
+static uint32_t tri_prepare_blocks(uint32_t count, int smCount, bool fused)
 {
-    if (m.nT == 0)
-        return cudaSuccess;
-    cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(unsigned long long), s);
-    if (!m.sharedVtx) { // (a multi-GPU selection reads its parent's padded vertices and bounds)
-        cudaError_t eb = sbk_bounds_pad(s, m, smCount, lc);
-        if (eb != cudaSuccess)
-            return eb;
-        lc.kernels -= 1;
-    }
-    sbradix::Workspace ws;
-    ws.mem = radixWs;
-    const int endBit = m.triJob ? 32 : 30;
-    const int passes = sbradix::sort_passes(m.nT, m.sortBeginBit, endBit, 8);
-    const bool fused = SB_TRIPREP_HIST && passes > 0 && passes <= 4;
-    uint32_t blocks = (m.nT + 255) / 256;
+    uint32_t blocks = (count + 255) / 256;
     if (fused) {
-        sbradix::sort_clear(s, ws, m.nT, passes);
         static int perSm = 0; // one resident wave
         if (!perSm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, tri_prepare_kernel, 256, 0) != cudaSuccess || perSm < 1))
             perSm = 2;
         blocks = std::min<uint32_t>(blocks, (uint32_t)(smCount * perSm));
     }
-    tri_prepare_kernel<<<blocks, 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.nrm4, m.mkey, m.order, m.err,
-        m.extentSum, m.triJob, fused ? sbradix::sort_hist(ws) : nullptr, sbradix::sort_ticket(ws), m.sortBeginBit, passes);
-    lc.kernels += 2;
+    return std::max<uint32_t>(blocks, 1);
+}
+
+static bool sort_is_fused(const MeshDev &m, int &passes, int &endBit)
+{
+    endBit = m.triJob ? 32 : 30;
+    passes = sbradix::sort_passes(m.nT, m.sortBeginBit, endBit, 8);
+    return SB_TRIPREP_HIST && passes > 0 && passes <= 4;
+}
+
+// The head of sbk_build_sort in three pieces, for a mesh whose arrays are still arriving from the host (sb_capi.cu
+// upload_from_host): clears + bounds + padded vertices once the coordinates are there, the per-triangle kernel over
+// each chunk of index triples as it lands, the digit offsets when all of them have been counted.
+bool sbk_prep_supported(const MeshDev &m)
+{
+    int passes, endBit;
+    return m.nT && !m.sharedVtx && !m.triJob && sort_is_fused(m, passes, endBit);
+}
+
+cudaError_t sbk_prep_begin(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc)
+{
+    int passes, endBit;
+    sort_is_fused(m, passes, endBit);
+    cudaMemsetAsync(m.root, 0, 8, s); // root + the index-check flag the per-triangle kernel raises
+    cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(unsigned long long), s);
+    sbradix::Workspace ws;
+    ws.mem = radixWs;
+    sbradix::sort_clear(s, ws, m.nT, passes);
+    return sbk_bounds_pad(s, m, smCount, lc);
+}
+
+cudaError_t sbk_prep_triangles(cudaStream_t s, MeshDev &m, uint32_t *radixWs, uint32_t first, uint32_t end, int smCount, LaunchCounter &lc)
+{
+    if (end <= first)
+        return cudaSuccess;
+    int passes, endBit;
+    sort_is_fused(m, passes, endBit);
+    sbradix::Workspace ws;
+    ws.mem = radixWs;
+    tri_prepare_kernel<<<tri_prepare_blocks(end - first, smCount, true), 256, 0, s>>>(m.vtx, m.tri, end, m.nV, m.bounds, m.nrm4, m.mkey,
+        m.order, m.err, m.extentSum, m.triJob, sbradix::sort_hist(ws), nullptr, m.sortBeginBit, passes, first);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sbk_prep_end(cudaStream_t s, MeshDev &m, uint32_t *radixWs, LaunchCounter &lc)
+{
+    int passes, endBit;
+    sort_is_fused(m, passes, endBit);
+    sbradix::Workspace ws;
+    ws.mem = radixWs;
+    sbradix::hist_scan_kernel<<<1, 256, 0, s>>>(sbradix::sort_hist(ws), passes);
+    lc.kernels += 1;
+    return cudaGetLastError();
+}
+
+// prepared: sbk_prep_begin / _triangles / _end have run for this geometry -- only the sort passes are left
+cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc, bool prepared)
+{
+    if (m.nT == 0)
+        return cudaSuccess;
+    sbradix::Workspace ws;
+    ws.mem = radixWs;
+    int passes, endBit;
+    const bool fused = sort_is_fused(m, passes, endBit);
+    if (!prepared) {
+        cudaMemsetAsync(m.extentSum, 0, 96 * sizeof(unsigned long long), s);
+        if (!m.sharedVtx) { // (a multi-GPU selection reads its parent's padded vertices and bounds)
+            cudaError_t eb = sbk_bounds_pad(s, m, smCount, lc);
+            if (eb != cudaSuccess)
+                return eb;
+            lc.kernels -= 1;
+        }
+        if (fused)
+            sbradix::sort_clear(s, ws, m.nT, passes);
+        tri_prepare_kernel<<<tri_prepare_blocks(m.nT, smCount, fused), 256, 0, s>>>(m.vtx, m.tri, m.nT, m.nV, m.bounds, m.nrm4, m.mkey, m.order, m.err,
+            m.extentSum, m.triJob, fused ? sbradix::sort_hist(ws) : nullptr, sbradix::sort_ticket(ws), m.sortBeginBit, passes, 0u);
+        lc.kernels += 2;
+    }
     uint32_t *sk = nullptr, *sv = nullptr;
-    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, endBit, ws, smCount, &sk, &sv, fused);
+    lc.kernels += sbradix::sort<uint32_t, 8>(s, m.mkey, m.mkeyTmp, m.order, m.orderTmp, m.nT, m.sortBeginBit, endBit, ws, smCount, &sk, &sv,
+        fused || prepared);
     m.sortedKey = sk;
     m.sortedTri = sv;
     return cudaGetLastError();

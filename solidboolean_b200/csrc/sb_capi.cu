@@ -123,6 +123,11 @@ struct sb_context {
     void *feFlags = nullptr;         // sb_front_end_host: device copy of the two flag arrays (grow-only)
     size_t feFlagsBytes = 0;
     uint64_t uploadSeq = 0;          // counts the host uploads (which of two fresh meshes arrives last)
+    bool earlyPrep = false;          // SB_EARLY_PREP=1: the head of a mesh's build (bounds, padded vertices, per-triangle kernel) runs beside its
+                                     // upload, chunk by chunk.  Measured at C3: 1.87 against 1.89 ms per host-buffer step (the 35 us it hides are
+                                     // partly paid back in stream waits); with the stage events of sb_context_enable_timing on the streams the first
+                                     // mesh's build is then held back until the second mesh's upload is over (2.13 ms) -- off
+    size_t earlyPrepMin = 1u << 16;  // ... meshes below this many triangles always do (SB_EARLY_PREP_MIN; tests lower it)
     bool optimisticVerify = true;    // SB_OPTIMISTIC=0: a front end waits for the rebuilds' reference counts before it enqueues anything
     bool deferVerify = false;        // ... set while such a front end enqueues its work (mesh_finish then leaves the check alone)
     uint64_t optimisticRedone = 0;   // front ends that had to be repeated because a rebuild did not fit its lists
@@ -188,6 +193,11 @@ struct sb_mesh {
     cudaEvent_t chunkEv[MAX_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t chunkEnd[MAX_CHUNKS] = {0, 0, 0, 0};
     int nChunks = 0;
+    // ... and the head of this mesh's build runs while they arrive, on treeStream: bounds + padded vertices behind the
+    // coordinates, the per-triangle kernel (normals, Morton keys, digit counts) behind each chunk of index triples
+    // (sb_build.cu sbk_prep_*); the next sb_mesh_build waits for prepEv and goes on from the sort passes
+    bool prepared = false;
+    cudaEvent_t xyzEv = nullptr, prepEv = nullptr;
     bool fresh = false;              // uploaded from the host since the last front end
     uint64_t uploadSeq = 0;          // order of the uploads within the context
 };
@@ -570,6 +580,10 @@ int sb_context_create(int device, sb_context **out)
         c->classifyPoolLimit = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("SB_CLASSIFY_V2"))
         c->classifyBalanced = atoi(e) != 0;
+    if (const char *e = getenv("SB_EARLY_PREP"))
+        c->earlyPrep = atoi(e) != 0;
+    if (const char *e = getenv("SB_EARLY_PREP_MIN"))
+        c->earlyPrepMin = (size_t)std::max(1ll, atoll(e));
     if (const char *e = getenv("SB_OPTIMISTIC"))
         c->optimisticVerify = atoi(e) != 0;
     if (const char *e = getenv("SB_STREAM_CLASSIFY"))
@@ -732,32 +746,85 @@ int sb_context_classify_stats(sb_context *c, uint64_t *rays, uint64_t *candidate
 
 // ---- mesh ---------------------------------------------------------------------
 
+// how many Morton bits the build sorts (a function of the mesh size and the context's settings)
+static void decide_sort_bits(const sb_context *c, sb_mesh *m)
+{
+    if (c->sortBeginBit >= 0) {
+        m->d.sortBeginBit = c->sortBeginBit;
+    } else if (m->d.triJob) {
+        m->d.sortBeginBit = 8; // batch: 12 job bits + the 12 leading Morton bits = three passes
+    } else {
+        // The order only has to be spatially coherent: 8 or more Morton cells per triangle are
+        // plenty (ties keep their input order), so a 1M-triangle mesh sorts 24 of the 30 bits
+        // -- three 8-bit passes instead of four -- and a 5K-triangle mesh two.
+        int want = 3;
+        while (want < 30 && ((size_t)1 << (want - 3)) < m->d.nT)
+            ++want;
+        const int passes = std::min(4, (want + 7) / 8);
+        m->d.sortBeginBit = std::max(0, 30 - 8 * passes);
+    }
+}
+
 // host -> device copies of a mesh's two arrays on its stream: coordinates first, then the index triples in up to
 // MAX_CHUNKS pieces with an event behind each (see sb_mesh::chunkEv)
 static cudaError_t upload_from_host(sb_mesh *m, const void *xyz, const void *tri)
 {
     cudaError_t e = cudaSuccess;
+    sb_context *c = m->ctx;
     const size_t nV = m->d.nV, nT = m->d.nT;
-    if (xyz && nV)
-        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, m->stream);
     m->nChunks = 0;
     m->fresh = false;
+    m->prepared = false;
+    decide_sort_bits(c, m);
+    // the head of the build beside the transfer (both arrays new, a plain mesh of some size)
+    bool prep = c->earlyPrep && xyz && tri && nV && nT >= c->earlyPrepMin && sbk_prep_supported(m->d);
+    auto ev = [&](cudaEvent_t *p) { return *p ? cudaSuccess : cudaEventCreateWithFlags(p, cudaEventDisableTiming); };
+    if (prep) {
+        e = ev(&m->xyzEv);
+        if (e == cudaSuccess) e = ev(&m->prepEv);
+        // treeStream behind whatever the mesh stream still does with the buffers the preparation writes
+        if (e == cudaSuccess) e = cudaEventRecord(m->prepEv, m->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(m->treeStream, m->prepEv, 0);
+    }
+    if (e == cudaSuccess && xyz && nV)
+        e = cudaMemcpyAsync(m->d.xyz, xyz, 24 * nV, cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess && prep) {
+        e = cudaEventRecord(m->xyzEv, m->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(m->treeStream, m->xyzEv, 0);
+        if (e == cudaSuccess) {
+            StageTimer t(c, SB_STAGE_BUILD, m->treeStream);
+            e = sbk_prep_begin(m->treeStream, m->d, m->radixWs, c->smCount, c->lc);
+        }
+    }
     if (e != cudaSuccess || !tri || !nT)
         return e;
     int n = nT >= (1u << 18) ? sb_mesh::MAX_CHUNKS : nT >= (1u << 16) ? 2 : 1;
+    if (prep && c->earlyPrepMin < (1u << 16) && nT >= 2048)
+        n = sb_mesh::MAX_CHUNKS; // (tests: ranged launches on small meshes too)
     const size_t per = (((nT + n - 1) / n) + 1023) / 1024 * 1024;
     size_t done = 0;
     for (int k = 0; k < n && done < nT && e == cudaSuccess; ++k) {
         const size_t end = std::min(nT, done + per);
         e = cudaMemcpyAsync(m->d.tri + 3 * done, static_cast<const uint32_t *>(tri) + 3 * done, 12 * (end - done),
             cudaMemcpyHostToDevice, m->stream);
-        if (e == cudaSuccess && !m->chunkEv[k])
-            e = cudaEventCreateWithFlags(&m->chunkEv[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = ev(&m->chunkEv[k]);
         if (e == cudaSuccess)
             e = cudaEventRecord(m->chunkEv[k], m->stream);
+        if (e == cudaSuccess && prep) {
+            e = cudaStreamWaitEvent(m->treeStream, m->chunkEv[k], 0);
+            if (e == cudaSuccess) {
+                StageTimer t(c, SB_STAGE_BUILD, m->treeStream);
+                e = sbk_prep_triangles(m->treeStream, m->d, m->radixWs, (uint32_t)done, (uint32_t)end, c->smCount, c->lc);
+            }
+        }
         m->chunkEnd[k] = (uint32_t)end;
         m->nChunks = k + 1;
         done = end;
+    }
+    if (e == cudaSuccess && prep) {
+        e = sbk_prep_end(m->treeStream, m->d, m->radixWs, c->lc);
+        if (e == cudaSuccess) e = cudaEventRecord(m->prepEv, m->treeStream);
+        m->prepared = e == cudaSuccess;
     }
     if (e == cudaSuccess && xyz) { // (both arrays new: what the faces' centroids are made of is on its way)
         m->fresh = true;
@@ -1126,20 +1193,9 @@ int sb_mesh_build(sb_mesh *m)
     DeviceGuard g(c);
     cudaStream_t st = m->stream;
     m->gridPending = false; // an unfinished first build is simply redone
-    if (c->sortBeginBit >= 0) {
-        m->d.sortBeginBit = c->sortBeginBit;
-    } else if (m->d.triJob) {
-        m->d.sortBeginBit = 8; // batch: 12 job bits + the 12 leading Morton bits = three passes
-    } else {
-        // The order only has to be spatially coherent: 8 or more Morton cells per triangle are
-        // plenty (ties keep their input order), so a 1M-triangle mesh sorts 24 of the 30 bits
-        // -- three 8-bit passes instead of four -- and a 5K-triangle mesh two.
-        int want = 3;
-        while (want < 30 && ((size_t)1 << (want - 3)) < m->d.nT)
-            ++want;
-        const int passes = std::min(4, (want + 7) / 8);
-        m->d.sortBeginBit = std::max(0, 30 - 8 * passes);
-    }
+    decide_sort_bits(c, m);
+    const bool prepared = m->prepared; // the head of the build has run beside the upload (upload_from_host)
+    m->prepared = false;
     if (m->d.sharedVtx)
         m->grid3Wanted = false;
     if ((m->d.gridAxes == 3) != m->grid3Wanted)
@@ -1148,7 +1204,7 @@ int sb_mesh_build(sb_mesh *m)
     // after whatever the context stream still does with this mesh's buffers
     order_after_context(c, m);
     if (c->useGraphs && m->d.nT && m->gridSized) {
-        const unsigned sig = (unsigned)m->d.gridAxes | (m->treeWanted ? 4u : 0u) | ((unsigned)m->d.sortBeginBit << 3);
+        const unsigned sig = (unsigned)m->d.gridAxes | (m->treeWanted ? 4u : 0u) | ((unsigned)m->d.sortBeginBit << 3) | (prepared ? 0x10000u : 0u);
         if (m->buildGraph && m->graphSig != sig) {
             cudaGraphExecDestroy(m->buildGraph);
             cudaGraphExecDestroy(m->gridGraph);
@@ -1177,8 +1233,10 @@ int sb_mesh_build(sb_mesh *m)
                 return SB_OK;
             };
             int r = capture(&m->buildGraph, [&]() {
-                cudaError_t e = cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st); // (batch: the upload's index check stays)
-                if (e == cudaSuccess) e = sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc);
+                cudaError_t e = cudaSuccess;
+                if (!prepared) // (prepared: cleared before the per-triangle kernel raised its index-check flag)
+                    e = cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st); // (batch: the upload's index check stays)
+                if (e == cudaSuccess) e = sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc, prepared);
                 if (e == cudaSuccess) e = sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->gridSlabBits, c->lc);
                 if (e == cudaSuccess) e = sbk_build_leaves(st, m->d, c->lc);
                 return e;
@@ -1208,6 +1266,8 @@ int sb_mesh_build(sb_mesh *m)
             }
             m->graphSig = sig;
         }
+        if (prepared)
+            SB_CUDA(cudaStreamWaitEvent(st, m->prepEv, 0));
         {
             StageTimer t(c, SB_STAGE_BUILD, st);
             SB_CUDA(cudaGraphLaunch(m->buildGraph, st));
@@ -1235,10 +1295,13 @@ int sb_mesh_build(sb_mesh *m)
         m->built = true;
         return SB_OK;
     }
+    if (prepared)
+        SB_CUDA(cudaStreamWaitEvent(st, m->prepEv, 0));
     {
         StageTimer t(c, SB_STAGE_BUILD, st);
-        SB_CUDA(cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st));
-        SB_CUDA(sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc));
+        if (!prepared)
+            SB_CUDA(cudaMemsetAsync(m->d.root, 0, m->d.triJob ? 4 : 8, st));
+        SB_CUDA(sbk_build_sort(st, m->d, m->radixWs, c->smCount, c->lc, prepared));
         SB_CUDA(sbk_grid_prepare(st, m->d, m->scanScratch, c->gridBeta, c->gridSlabBits, c->lc));
         SB_CUDA(sbk_build_leaves(st, m->d, c->lc)); // also counts the grid cells
         m->treeBuilt = false;
@@ -1372,6 +1435,10 @@ static void mesh_destroy_now(sb_mesh *m)
     for (cudaEvent_t ev : m->chunkEv)
         if (ev)
             cudaEventDestroy(ev);
+    if (m->xyzEv)
+        cudaEventDestroy(m->xyzEv);
+    if (m->prepEv)
+        cudaEventDestroy(m->prepEv);
     if (m->buildGraph)
         cudaGraphExecDestroy(m->buildGraph);
     if (m->gridGraph)

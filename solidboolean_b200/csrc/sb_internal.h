@@ -103,7 +103,13 @@ struct LaunchCounter {
 // sbk_build_sort: bounds, per-triangle data, Morton sort; sbk_build_leaves (after
 // sbk_grid_prepare): sorted leaves / boxes / centroids / clusters + quantised boxes and
 // the per-cell counts of the ray grids
-cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc);
+cudaError_t sbk_build_sort(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc, bool prepared = false);
+// the head of sbk_build_sort in pieces (bounds + padded vertices / per-triangle kernel over a range / digit offsets), for a
+// mesh whose arrays are still arriving from the host
+bool sbk_prep_supported(const MeshDev &m);
+cudaError_t sbk_prep_begin(cudaStream_t s, MeshDev &m, uint32_t *radixWs, int smCount, LaunchCounter &lc);
+cudaError_t sbk_prep_triangles(cudaStream_t s, MeshDev &m, uint32_t *radixWs, uint32_t first, uint32_t end, int smCount, LaunchCounter &lc);
+cudaError_t sbk_prep_end(cudaStream_t s, MeshDev &m, uint32_t *radixWs, LaunchCounter &lc);
 cudaError_t sbk_build_leaves(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
 cudaError_t sbk_build_tree(cudaStream_t s, MeshDev &m, LaunchCounter &lc);
 cudaError_t sbk_batch_fixup(cudaStream_t s, uint32_t *tri, uint32_t nT, const uint32_t *triStart, const uint32_t *vtxStart,

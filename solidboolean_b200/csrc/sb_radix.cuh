@@ -42,6 +42,8 @@ __device__ __forceinline__ void hist_flush_and_scan(uint32_t *s_hist, int passes
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x)
         if (s_hist[i])
             atomicAdd(&hist[i], s_hist[i]);
+    if (!ticket)
+        return; // one of several launches that count into the same histogram: hist_scan_kernel finishes it
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
@@ -68,6 +70,25 @@ __device__ __forceinline__ void hist_flush_and_scan(uint32_t *s_hist, int passes
         }
         if (own)
             hist[p * RADIX + threadIdx.x] = s_scan[threadIdx.x] - v;
+        __syncthreads();
+    }
+}
+
+// the exclusive scan on its own (one CTA of 256 threads), after several launches counted into the same histogram
+static __global__ void __launch_bounds__(256) hist_scan_kernel(uint32_t *__restrict__ hist, int passes)
+{
+    __shared__ uint32_t s_scan[256];
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t v = hist[p * 256 + threadIdx.x];
+        s_scan[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            const uint32_t t = (int)threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += t;
+            __syncthreads();
+        }
+        hist[p * 256 + threadIdx.x] = s_scan[threadIdx.x] - v;
         __syncthreads();
     }
 }

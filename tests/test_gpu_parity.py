@@ -946,3 +946,42 @@ def test_front_end_right_after_update_is_enqueued_before_the_counts_are_known(or
         assert np.array_equal(ha.numpy(), oa) and np.array_equal(hb.numpy(), ob)
         x.close()
     ma.close(); mb.close(); ctx.close()
+
+
+def test_build_head_runs_beside_the_upload(oracle, monkeypatch, golden_cases):
+    """sb_mesh_upload / sb_mesh_update from host memory start the head of the build while the arrays arrive (bounds and
+    padded vertices behind the coordinates, normals / Morton keys / digit counts behind each chunk of index triples);
+    sb_mesh_build goes on from the sort.  With the size threshold lowered every mesh here takes that path: results must
+    equal the oracle's, for new meshes, for updated ones (new coordinates AND new triangle order), and the index check
+    of the per-triangle kernel must still be reported."""
+    monkeypatch.setenv("SB_EARLY_PREP", "1")        # (off by default: 1 % at C3)
+    monkeypatch.setenv("SB_EARLY_PREP_MIN", "1")
+    ctx = sb.Context(0)
+    rng = np.random.default_rng(3)
+    for a, b in ((meshgen.icosphere(4), meshgen.torus(64, 32, center=(0.013, 0.007, 0.011))),
+                 (meshgen.icosphere(5), meshgen.icosphere(5, center=(0.21, 0.13, -0.05)))):
+        ma, mb = ctx.mesh(*a), ctx.mesh(*b)
+        for frame in range(3):
+            if frame:
+                pa, pb = rng.permutation(len(a[1])), rng.permutation(len(b[1]))
+                a = (np.ascontiguousarray(a[0] * (1.0 + 0.03 * frame)), np.ascontiguousarray(a[1][pa]))
+                b = (np.ascontiguousarray(b[0] + 0.01 * frame), np.ascontiguousarray(b[1][pb]))
+                ma.update(a[0].ctypes.data, a[1].ctypes.data); mb.update(b[0].ctypes.data, b[1].ctypes.data)
+                ma.build(); mb.build()
+            x = ma.intersect(mb)
+            ref = oracle.candidate_pairs(a, b)
+            ret, cop, hit, seg = oracle.predicate_pairs(a, b, ref)
+            assert np.array_equal(x.candidates()[0], ref)
+            hab, hseg = x.hits()
+            assert np.array_equal(hab, ref[hit.astype(bool)]) and hseg.tobytes() == seg[hit.astype(bool)].tobytes()
+            ia, pa_ = ma.classify_faces_against(mb)
+            oa, opa, _ = oracle.classify(b, oracle.centroids(*a))
+            assert np.array_equal(pa_, opa) and np.array_equal(ia, oa)
+            assert ma.normals().tobytes() == oracle.normals(*a).tobytes()
+            x.close()
+        ma.close(); mb.close()
+    bad = meshgen.icosphere(4)
+    tri = bad[1].copy(); tri[100, 1] = len(bad[0]) + 5
+    with pytest.raises(sb.SolidBooleanError):
+        ctx.mesh(bad[0], tri)
+    ctx.close()
