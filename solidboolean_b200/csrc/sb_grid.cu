@@ -5,8 +5,9 @@
 // box overlaps the ray box" is a 2-D point-location problem in the plane
 // perpendicular to the ray plus a half-line test along it.  For every mesh and
 // every axis we therefore bin the triangles' boxes into a 2-D grid over the two
-// perpendicular dimensions (CSR layout: per-cell ranges into one array of
-// 8-byte cell-relative references).  A ray then reads ONE cell list instead of walking a tree.
+// perpendicular dimensions (CSR layout: ranges per cell and depth slab -- sb_gridq.cuh -- into one array of
+// 8-byte cell-relative references).  A ray then reads the part of ONE cell list that lies at or beyond its own
+// depth instead of walking a tree.
 //
 // Exactness: cells and the 15-bit coordinates inside a reference are produced by
 // one monotone quantiser per world axis (sb_gridq.cuh), applied to triangle
@@ -418,8 +419,8 @@ cudaError_t sbk_grid_recount(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, 
     return cudaGetLastError();
 }
 
-// Phase 1 (after the leaf kernel): inclusive scan of the per-cell counts.  Afterwards
-// E[c + 1] = end of cell c and gridBigCount[6] = total number of references.
+// Phase 1 (after the leaf kernel): inclusive scan of the counts per entry e = (cell, depth slab).  Afterwards
+// E[e + 1] = end of entry e and gridBigCount[6] = total number of references.
 cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, LaunchCounter &lc)
 {
     if (m.nT == 0)
@@ -434,9 +435,10 @@ cudaError_t sbk_grid_scan(cudaStream_t s, MeshDev &m, uint32_t *scanScratch, Lau
 }
 
 // Phase 2 (after the caller sized refs / bigRefs from the counts): every
-// E[c + 1] turns from the (even) END of cell c into its START as the cell is filled
-// back to front; E[totalCells + 1] (written by the scan) closes the last cell.  The
-// list of cell c is then [E[c + 1], E[c + 2] & ~1): the share of the next cell may begin
+// E[e + 1] turns from the END of entry e into its START as the sub-list is filled
+// back to front; E[usedCells + 1] (written by the scan) closes the last cell.  The sub-lists of a cell are
+// contiguous and end on an even slot (the cell's share is rounded up, the unused slot sits in FRONT of its first
+// sub-list: pad_cells); what a ray reads is [E[e0 + slab + 1], E[e0 + slabs + 1] & ~1) (grid_ray_range): the share of the next cell may begin
 // with an unused slot.
 cudaError_t sbk_grid_fill(cudaStream_t s, MeshDev &m, LaunchCounter &lc)
 {
